@@ -1,0 +1,81 @@
+"""ctypes binding of ``libcabinet_b200.so`` (the C-ABI declared in ``include/cabinet_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C cabinet_b200/csrc``.  There is
+no fallback: if it is missing, importing the engine raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libcabinet_b200.so"
+CSRC = PKG / "csrc"
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_HSIGMOID, ACT_SIGMOID = 0, 1, 2, 3, 4
+
+_p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+# name -> argtypes; must list every symbol include/cabinet_b200.h declares (tests/test_abi.py checks this)
+SIGNATURES = {
+    "cabinet_last_error": ([], C.c_char_p),
+    "cabinet_abi_version": ([], _i),
+    "cabinet_device_info": ([C.POINTER(_i)] * 3, _i),
+    "cabinet_conv2d_simt": ([_p, _i, _ll, _ll, _ll, _ll, _ll, _p, _i, _ll, _ll, _ll, _p, _p, _ll, _p, _i, _ll, _ll,
+                             _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p], _i),
+    "cabinet_dwconv": ([_p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p], _i),
+    "cabinet_gate_mlp": ([_p, _f, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),
+    "cabinet_scale_act": ([_p, _ll, _i, _p, _i, _ll, _i, _i, _i, _p], _i),
+    "cabinet_psp_pool": ([_p, _ll, _i, _p, _i, _i, _i, _i, _p], _i),
+    "cabinet_psp_concat": ([_p, _ll, _p, _p, _ll, _i, _i, _i, _i, _i, _p], _i),
+    "cabinet_softmax_rows": ([_p, _p, _i, _ll, _i, _p], _i),
+    "cabinet_cab_combine": ([_p, _p, _p, _p, _ll, _p, _i, _ll, _i, _p], _i),
+    "cabinet_channel_sum": ([_p, _ll, _i, _i, _ll, _i, _p, _p], _i),
+    "cabinet_bilinear_nhwc": ([_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p], _i),
+    "cabinet_upsample_logits_nchw": ([_p, _i, _i, _i, _i, _p, _i, _i, _i, _p], _i),
+    "cabinet_upsample_argmax": ([_p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p], _i),
+    "cabinet_confusion_hist": ([_p, _i, _p, _i, _ll, _i, _i, _p, _p], _i),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> Path:
+    """Compile the library for sm_100a (nvcc cross-compiles; no GPU needed)."""
+    r = subprocess.run(["make", "-C", str(CSRC), "-j8"], capture_output=True, text=True)
+    if r.returncode != 0 or verbose:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode != 0:
+        raise RuntimeError("building libcabinet_b200.so failed")
+    return LIB_PATH
+
+
+def load():
+    """dlopen the library and set prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.is_file():
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(or `make -C cabinet_b200/csrc`). cabinet_b200 has no fallback path.")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (args, res) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = res
+        _lib = lib
+    return _lib
+
+
+class CabinetError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().cabinet_last_error().decode(errors="replace")
+        if rc == 1:
+            raise ValueError(f"{what}: {msg}")
+        raise CabinetError(f"{what}: {msg}")

@@ -1,0 +1,227 @@
+// Small fused elementwise / reduction kernels: SE & FFM gate MLP, scale(+act) apply, row softmax, CAB combine.
+#include "common.cuh"
+
+namespace {
+
+// One block per image.  mean -> fc1(+ReLU) -> fc2 -> gate.  fp32 throughout.
+__global__ void __launch_bounds__(256)
+gate_mlp_kernel(const float* __restrict__ gap_sum, float inv_hw, const float* __restrict__ w1,
+                const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                float* __restrict__ scale, int C, int Cmid, int gate) {
+    extern __shared__ float sm[];  // mean[C] | hidden[Cmid]
+    float* mean = sm;
+    float* hidden = sm + C;
+    const int n = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = gap_sum[static_cast<long long>(n) * C + c] * inv_hw;
+    __syncthreads();
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarps = blockDim.x / 32;
+    for (int j = warp; j < Cmid; j += nwarps) {
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) acc = fmaf(w1[static_cast<long long>(j) * C + c], mean[c], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) hidden[j] = fmaxf(acc + (b1 ? b1[j] : 0.f), 0.f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = b2 ? b2[c] : 0.f;
+        for (int j = 0; j < Cmid; ++j) acc = fmaf(w2[static_cast<long long>(c) * Cmid + j], hidden[j], acc);
+        scale[static_cast<long long>(n) * C + c] = cab_act(acc, gate);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+scale_act_kernel(T* __restrict__ x, long long ldx, const float* __restrict__ scale, long long HW, int C, int act,
+                 int plus_one) {
+    constexpr int V = Vec16<T>::N;
+    const int n = blockIdx.y;
+    const int CG = C / V;
+    const long long total = HW * CG;
+    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int cg = static_cast<int>(idx % CG);
+        const long long p = idx / CG;
+        T* ptr = x + (static_cast<long long>(n) * HW + p) * ldx + cg * V;
+        Vec16<T> v;
+        v.load(ptr);
+        float f[V];
+        v.unpack(f);
+        const float* sc = scale + static_cast<long long>(n) * C + cg * V;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            float s = __ldg(sc + i);
+            f[i] = plus_one ? fmaf(f[i], s, f[i]) : cab_act(f[i] * s, act);
+        }
+        v.pack(f);
+        v.store(ptr);
+    }
+}
+
+// One warp per row; cols arbitrary.  exp in fp32 with max subtraction (F.softmax semantics).
+template <typename T>
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ s, T* __restrict__ p, long long rows, int cols) {
+    const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= rows) return;
+    const float* in = s + row * cols;
+    float m = -INFINITY;
+    for (int c = lane; c < cols; c += 32) m = fmaxf(m, in[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int c = lane; c < cols; c += 32) sum += expf(in[c] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    T* out = p + row * cols;
+    for (int c = lane; c < cols; c += 32) out[c] = from_f32<T>(expf(in[c] - m) * inv);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+cab_combine_kernel(const T* __restrict__ g, const T* __restrict__ x, const T* __restrict__ r, T* __restrict__ out,
+                   long long ldo, int CG, const float* __restrict__ gamma, long long nvec) {
+    constexpr int V = Vec16<T>::N;
+    const float gm = __ldg(gamma);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        Vec16<T> gv, xv, rv, ov;
+        gv.load(g + i * V);
+        xv.load(x + i * V);
+        rv.load(r + i * V);
+        float gf[V], xf[V], rf[V], of[V];
+        gv.unpack(gf);
+        xv.unpack(xf);
+        rv.unpack(rf);
+#pragma unroll
+        for (int k = 0; k < V; ++k) of[k] = gm * gf[k] + (xf[k] + xf[k] * (1.f / (1.f + __expf(-rf[k]))));
+        ov.pack(of);
+        ov.store(out + (i / CG) * ldo + (i % CG) * V);
+    }
+}
+
+// Per-(image, channel) sum over pixels: grid (chunks, N); smem accumulation then one atomic per channel per block.
+template <typename T>
+__global__ void __launch_bounds__(256)
+channel_sum_kernel(const T* __restrict__ x, long long ldx, long long HW, int C, float* __restrict__ out,
+                   long long pix_per_block) {
+    constexpr int V = Vec16<T>::N;
+    extern __shared__ float s_sum[];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_sum[i] = 0.f;
+    __syncthreads();
+    const int n = blockIdx.y;
+    const int CG = C / V;
+    const long long p0 = blockIdx.x * pix_per_block;
+    const long long p1 = min(p0 + pix_per_block, HW);
+    const int rows = blockDim.x / CG;  // pixels processed per sweep (CG <= blockDim.x is checked by the host)
+    const int cg = threadIdx.x % CG, pr = threadIdx.x / CG;
+    if (pr < rows) {
+        float acc[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = 0.f;
+        for (long long p = p0 + pr; p < p1; p += rows) {
+            Vec16<T> v;
+            v.load(x + (static_cast<long long>(n) * HW + p) * ldx + cg * V);
+            float f[V];
+            v.unpack(f);
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[i] += f[i];
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) atomicAdd(&s_sum[cg * V + i], acc[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&out[static_cast<long long>(n) * C + i], s_sum[i]);
+}
+
+}  // namespace
+
+extern "C" int cabinet_channel_sum(const void* x, long long ldx, int dtype, int N, long long HW, int C, float* out,
+                                   cabinet_stream_t stream) {
+    CAB_REQUIRE(x && out, "channel_sum: null pointer");
+    const int V = dtype == CABINET_F32 ? 4 : 8;
+    CAB_REQUIRE(C > 0 && C % V == 0 && ldx % V == 0 && ldx >= C && C / V <= 256 && C * sizeof(float) <= 48 * 1024,
+                "channel_sum: unsupported C=%d ldx=%lld", C, ldx);
+    if (N == 0 || HW == 0) return CABINET_OK;
+    const long long pix_per_block = std::max<long long>(64, cab_ceil_div(HW, 148 * 4));
+    dim3 grid(static_cast<unsigned>(cab_ceil_div(HW, pix_per_block)), N);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == CABINET_BF16)
+        channel_sum_kernel<bf16><<<grid, 256, C * sizeof(float), s>>>(reinterpret_cast<const bf16*>(x), ldx, HW, C, out,
+                                                                      pix_per_block);
+    else
+        channel_sum_kernel<float><<<grid, 256, C * sizeof(float), s>>>(reinterpret_cast<const float*>(x), ldx, HW, C,
+                                                                       out, pix_per_block);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_gate_mlp(const float* gap_sum, float inv_hw, const float* w1, const float* b1,
+                                const float* w2, const float* b2, float* scale, int N, int C, int Cmid, int gate,
+                                cabinet_stream_t stream) {
+    CAB_REQUIRE(gap_sum && w1 && w2 && scale, "gate_mlp: null pointer");
+    CAB_REQUIRE(C > 0 && Cmid > 0 && (C + Cmid) * sizeof(float) <= 48 * 1024, "gate_mlp: C=%d Cmid=%d unsupported", C,
+                Cmid);
+    if (N == 0) return CABINET_OK;
+    gate_mlp_kernel<<<N, 256, (C + Cmid) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        gap_sum, inv_hw, w1, b1, w2, b2, scale, C, Cmid, gate);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_scale_act(void* x, long long ldx, int dtype, const float* scale, int N, long long HW, int C,
+                                 int act, int plus_one, cabinet_stream_t stream) {
+    CAB_REQUIRE(x && scale, "scale_act: null pointer");
+    const int V = dtype == CABINET_F32 ? 4 : 8;
+    CAB_REQUIRE(C > 0 && C % V == 0 && ldx % V == 0 && ldx >= C, "scale_act: C/ldx must be multiples of %d", V);
+    if (N == 0 || HW == 0) return CABINET_OK;
+    const long long total = HW * (C / V);
+    dim3 grid(static_cast<unsigned>(std::min<long long>(cab_ceil_div(total, 256), 148 * 16)), N);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == CABINET_BF16)
+        scale_act_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<bf16*>(x), ldx, scale, HW, C, act, plus_one);
+    else
+        scale_act_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<float*>(x), ldx, scale, HW, C, act, plus_one);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_softmax_rows(const float* s, void* p, int p_dtype, long long rows, int cols,
+                                    cabinet_stream_t stream) {
+    CAB_REQUIRE(s && p && cols > 0, "softmax_rows: bad arguments");
+    if (rows == 0) return CABINET_OK;
+    dim3 grid(static_cast<unsigned>(cab_ceil_div(rows, 8)));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p_dtype == CABINET_BF16)
+        softmax_rows_kernel<bf16><<<grid, 256, 0, st>>>(s, reinterpret_cast<bf16*>(p), rows, cols);
+    else
+        softmax_rows_kernel<float><<<grid, 256, 0, st>>>(s, reinterpret_cast<float*>(p), rows, cols);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_cab_combine(const void* g, const void* x, const void* r, void* out, long long ldo,
+                                   const float* gamma, int dtype, long long n_pixels, int C,
+                                   cabinet_stream_t stream) {
+    CAB_REQUIRE(g && x && r && out && gamma, "cab_combine: null pointer");
+    const int V = dtype == CABINET_F32 ? 4 : 8;
+    CAB_REQUIRE(C > 0 && C % V == 0 && ldo % V == 0 && ldo >= C, "cab_combine: C/ldo must be multiples of %d", V);
+    if (n_pixels == 0) return CABINET_OK;
+    const int CG = C / V;
+    const long long nvec = n_pixels * CG;
+    dim3 grid(static_cast<unsigned>(std::min<long long>(cab_ceil_div(nvec, 256), 148 * 16)));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == CABINET_BF16)
+        cab_combine_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(g), reinterpret_cast<const bf16*>(x),
+                                                     reinterpret_cast<const bf16*>(r), reinterpret_cast<bf16*>(out),
+                                                     ldo, CG, gamma, nvec);
+    else
+        cab_combine_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(g),
+                                                      reinterpret_cast<const float*>(x),
+                                                      reinterpret_cast<const float*>(r), reinterpret_cast<float*>(out),
+                                                      ldo, CG, gamma, nvec);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}

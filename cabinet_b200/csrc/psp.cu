@@ -1,0 +1,98 @@
+// Pyramid pooling pieces (src/models/cab.py:46-76): adaptive average pools (1,3,6,8) and the
+// [x, up(pool_s)...] 5C-channel concat that feeds the 1x1 `project` GEMM.  The maps here are 1/32 resolution
+// (<= 8160 pixels, 128 channels): negligible bytes next to the high-resolution layers.
+#include "common.cuh"
+
+namespace {
+
+__device__ __constant__ int kPspSize[4] = {1, 3, 6, 8};
+__device__ __constant__ int kPspOffset[4] = {0, 1, 10, 46};  // bin offsets inside the 110-entry table
+constexpr int kPspBins = 110;
+
+// grid (110, N), block = C threads (C <= 1024): one bin per block, channel per thread.
+template <typename T>
+__global__ void psp_pool_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ pooled, int H, int W,
+                                int C) {
+    const int bin = blockIdx.x, n = blockIdx.y;
+    int si = 3;
+    if (bin < 1) si = 0; else if (bin < 10) si = 1; else if (bin < 46) si = 2;
+    const int s = kPspSize[si];
+    const int local = bin - kPspOffset[si];
+    const int by = local / s, bx = local % s;
+    // ATen adaptive_avg_pool2d bins: [floor(i*H/s), ceil((i+1)*H/s))
+    const int h0 = (by * H) / s, h1 = ((by + 1) * H + s - 1) / s;
+    const int w0 = (bx * W) / s, w1 = ((bx + 1) * W + s - 1) / s;
+    const T* base = x + static_cast<long long>(n) * H * W * ldx;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int h = h0; h < h1; ++h)
+            for (int w = w0; w < w1; ++w) acc += to_f32<T>(base[(static_cast<long long>(h) * W + w) * ldx + c]);
+        pooled[(static_cast<long long>(n) * kPspBins + bin) * C + c] = acc / static_cast<float>((h1 - h0) * (w1 - w0));
+    }
+}
+
+// thread per (pixel, channel): out[pix][0:C] = x, out[pix][C*(1+si) + c] = bilinear(pooled_si)(pix, c)
+template <typename T>
+__global__ void __launch_bounds__(256)
+psp_concat_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ pooled, T* __restrict__ out,
+                  long long ldo, int H, int W, int C, long long total) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = static_cast<int>(idx % C);
+    const long long pix = idx / C;
+    const int w = static_cast<int>(pix % W);
+    const long long t = pix / W;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    T* o = out + pix * ldo;
+    o[c] = x[pix * ldx + c];
+    const float* pn = pooled + static_cast<long long>(n) * kPspBins * C;
+#pragma unroll
+    for (int si = 0; si < 4; ++si) {
+        const int s = kPspSize[si];
+        const float* ps = pn + static_cast<long long>(kPspOffset[si]) * C;
+        int y0, y1, x0, x1;
+        float wy, wx;
+        cab_bilinear_tap(h, static_cast<float>(s) / static_cast<float>(H), s, y0, y1, wy);
+        cab_bilinear_tap(w, static_cast<float>(s) / static_cast<float>(W), s, x0, x1, wx);
+        const float v00 = ps[(y0 * s + x0) * C + c], v01 = ps[(y0 * s + x1) * C + c];
+        const float v10 = ps[(y1 * s + x0) * C + c], v11 = ps[(y1 * s + x1) * C + c];
+        const float v = (1.f - wy) * ((1.f - wx) * v00 + wx * v01) + wy * ((1.f - wx) * v10 + wx * v11);
+        o[static_cast<long long>(C) * (1 + si) + c] = from_f32<T>(v);
+    }
+}
+
+}  // namespace
+
+extern "C" int cabinet_psp_pool(const void* x, long long ldx, int dtype, float* pooled, int N, int H, int W, int C,
+                                cabinet_stream_t stream) {
+    CAB_REQUIRE(x && pooled && H > 0 && W > 0 && C > 0 && ldx >= C, "psp_pool: bad arguments");
+    if (N == 0) return CABINET_OK;
+    dim3 grid(kPspBins, N);
+    const int threads = std::min(1024, ((C + 31) / 32) * 32);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == CABINET_BF16)
+        psp_pool_kernel<bf16><<<grid, threads, 0, s>>>(reinterpret_cast<const bf16*>(x), ldx, pooled, H, W, C);
+    else
+        psp_pool_kernel<float><<<grid, threads, 0, s>>>(reinterpret_cast<const float*>(x), ldx, pooled, H, W, C);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_psp_concat(const void* x, long long ldx, const float* pooled, void* out, long long ldo,
+                                  int dtype, int N, int H, int W, int C, cabinet_stream_t stream) {
+    CAB_REQUIRE(x && pooled && out && H > 0 && W > 0 && C > 0 && ldx >= C && ldo >= 5LL * C,
+                "psp_concat: bad arguments");
+    if (N == 0) return CABINET_OK;
+    const long long total = static_cast<long long>(N) * H * W * C;
+    dim3 grid(static_cast<unsigned>(cab_ceil_div(total, 256)));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == CABINET_BF16)
+        psp_concat_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), ldx, pooled,
+                                                    reinterpret_cast<bf16*>(out), ldo, H, W, C, total);
+    else
+        psp_concat_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), ldx, pooled,
+                                                     reinterpret_cast<float*>(out), ldo, H, W, C, total);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}

@@ -1,0 +1,401 @@
+"""Execution engine: BN-folded packed weights + the kernel schedule of ``CABiNet.forward``.
+
+Host side of the hot path.  It owns no arithmetic: every tensor op of the reference forward
+(``src/models/cabinet.py:207-247`` and everything it calls) is one of the C-ABI entry points of
+``libcabinet_b200.so``; PyTorch is used for device memory (caching allocator), the current stream
+and parameter storage only.
+
+Layout: activations are NHWC in HBM, bf16 (``precision='bf16'``) or fp32 (``'fp32'`` parity mode);
+class-logit maps at 1/32 and 1/8 resolution and all GAP/SE statistics stay fp32.  Concatenations
+(``torch.cat`` at cabinet.py:87,143) are never materialised by a copy: producers write channel
+slices of one wider buffer through their pixel stride.
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_HSIGMOID, ACT_HSWISH, ACT_NONE, ACT_RELU, ACT_SIGMOID, BF16, F32, check
+from .constants import BN_EPS
+
+
+@dataclass
+class Map:
+    """A (N,H,W,C) NHWC view: base tensor kept alive + pointer/stride bookkeeping."""
+
+    t: torch.Tensor
+    N: int
+    H: int
+    W: int
+    C: int
+    ld: int
+    off: int = 0  # channel offset inside the pixel
+
+    @property
+    def dt(self) -> int:
+        return BF16 if self.t.dtype == torch.bfloat16 else F32
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr() + self.off * self.t.element_size()
+
+    def slice(self, c0: int, c: int) -> "Map":
+        return Map(self.t, self.N, self.H, self.W, c, self.ld, self.off + c0)
+
+    def nhwc(self) -> torch.Tensor:
+        """Dense torch view (tests/debug)."""
+        return self.t.view(self.N, self.H, self.W, self.ld)[..., self.off:self.off + self.C]
+
+
+def _fold(conv_w, conv_b, bn, eps=BN_EPS):
+    """Conv + eval-BN -> (w', b') in fp32: y = conv(x, w') + b'  (fold before any rounding)."""
+    w = conv_w.detach().float()
+    cout = w.shape[0]
+    if bn is None:
+        b = conv_b.detach().float().clone() if conv_b is not None else torch.zeros(cout, device=w.device)
+        return w, b
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + eps)
+    b = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    if conv_b is not None:
+        b = b + conv_b.detach().float() * scale
+    return w * scale.view(-1, 1, 1, 1), b
+
+
+class ConvLayer:
+    """Dense conv (+folded BN) packed for the kernels: w [Cout][KH*KW*Cin] (c fastest), fp32 bias."""
+
+    def __init__(self, conv, bn, act, wdtype):
+        w, b = _fold(conv.weight, conv.bias, bn)
+        self.cout, self.cin, self.kh, self.kw = w.shape
+        self.stride, self.pad = conv.stride[0], conv.padding[0]
+        self.act = act
+        self.w = w.permute(0, 2, 3, 1).reshape(self.cout, -1).contiguous().to(wdtype)
+        self.b = b.contiguous()
+        self.tc = None  # tcgen05 packing, attached by the engine when the layer is eligible
+
+
+class DwLayer:
+    """Depthwise conv (+folded BN): w [k*k][C] fp32, bias fp32."""
+
+    def __init__(self, conv, bn, act):
+        w, b = _fold(conv.weight, conv.bias, bn)
+        self.c, self.k, self.stride, self.act = w.shape[0], w.shape[2], conv.stride[0], act
+        self.w = w.view(self.c, -1).t().contiguous()
+        self.b = b.contiguous()
+
+
+class GateLayer:
+    """SE (Linear/Linear + hard-sigmoid) or FFM (1x1/1x1 + sigmoid) channel gate, fp32."""
+
+    def __init__(self, w1, b1, w2, b2, gate):
+        f = lambda t: None if t is None else t.detach().float().reshape(t.shape[0], -1).contiguous()  # noqa: E731
+        self.w1, self.w2 = f(w1), f(w2)
+        self.b1 = None if b1 is None else b1.detach().float().contiguous()
+        self.b2 = None if b2 is None else b2.detach().float().contiguous()
+        self.cmid, self.c = self.w1.shape
+        self.gate = gate
+
+
+def _out_size(n, k, s, p):
+    return (n + 2 * p - k) // s + 1
+
+
+class Engine:
+    def __init__(self, model, precision: str = "bf16"):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        p0 = next(model.parameters())
+        if not p0.is_cuda:
+            raise RuntimeError("cabinet_b200 engine needs the model on a CUDA device (no CPU path)")
+        self.lib = _lib.load()
+        self.dev = p0.device
+        self.precision = precision
+        self.tdt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.dt = BF16 if precision == "bf16" else F32
+        self.n_classes = model.n_classes
+        self.stamp = None
+        self.launches = 0  # kernels enqueued by the last forward
+        self.use_tc = precision == "bf16"
+        self.debug = False
+        self.stages = {}
+        with torch.no_grad():
+            self._pack(model)
+
+    # ------------------------------------------------------------------ packing
+    def _pack(self, m):
+        wd = self.tdt
+        f32 = torch.float32
+        mob = m.mobile
+        # stems read the fp32 NCHW input directly; their (tiny) weights stay fp32
+        self.stem = ConvLayer(mob.features[0][0], mob.features[0][1], ACT_HSWISH, f32)
+        self.blocks = []
+        for blk in list(mob.features)[1:]:
+            s, c = blk.spec, blk.conv
+            act = ACT_HSWISH if s["hs"] else ACT_RELU
+            e = dict(spec=s, act=act)
+            if s["expand"]:
+                e["pw1"] = ConvLayer(c[0], c[1], act, wd)
+                e["dw"] = DwLayer(c[3], c[4], ACT_NONE if s["se"] else act)
+                se, pw2, bn2 = c[5], c[7], c[8]
+            else:
+                e["dw"] = DwLayer(c[0], c[1], act)
+                se, pw2, bn2 = c[3], c[4], c[5]
+            if s["se"]:
+                e["se"] = GateLayer(se.fc[0].weight, se.fc[0].bias, se.fc[2].weight, se.fc[2].bias, ACT_HSIGMOID)
+            e["pw2"] = ConvLayer(pw2, bn2, ACT_NONE, wd)
+            self.blocks.append(e)
+        self.last = ConvLayer(mob.conv[0], mob.conv[1], ACT_HSWISH, wd)
+
+        sb = m.sb
+        self.sb1 = ConvLayer(sb.conv1.conv, sb.conv1.bn, ACT_RELU, f32)
+        self.sb2 = ConvLayer(sb.conv2.conv, sb.conv2.bn, ACT_RELU, wd)
+        self.sb3 = ConvLayer(sb.conv3.conv, sb.conv3.bn, ACT_RELU, wd)
+        self.sb4 = ConvLayer(sb.conv_out.conv, sb.conv_out.bn, ACT_RELU, wd)
+
+        ab, ga = m.ab, m.ab.a2block.global_attn
+        self.conva = ConvLayer(ab.conva[0], ab.conva[1], ACT_RELU, wd)
+        self.to_q = ConvLayer(ga.to_query[0], ga.to_query[1], ACT_RELU, wd)
+        self.to_k = ConvLayer(ga.to_key[0], ga.to_key[1], ACT_RELU, wd)
+        self.to_v = ConvLayer(ga.to_value, None, ACT_NONE, wd)
+        self.psp_k = ConvLayer(ga.psp_key.project, None, ACT_NONE, wd)
+        self.psp_v = ConvLayer(ga.psp_value.project, None, ACT_NONE, wd)
+        self.proj_out = ConvLayer(ga.project_out, None, ACT_NONE, wd)
+        self.local = [DwLayer(d.block[0], d.block[1], ACT_RELU) for d in ab.a2block.local_attn.refine]
+        self.gamma = ab.a2block.gamma.detach().float().contiguous()
+        self.convb = ConvLayer(ab.convb, None, ACT_NONE, wd)
+        self.b1 = ConvLayer(ab.b1, ab.b2, ACT_RELU, wd)
+        self.b4 = ConvLayer(ab.b4, None, ACT_NONE, wd)
+        self.key_ch = self.to_k.cout
+
+        ffm = m.ffm
+        self.ffm_blk = ConvLayer(ffm.convblk.conv, ffm.convblk.bn, ACT_RELU, wd)
+        self.ffm_gate = GateLayer(ffm.conv1.weight, None, ffm.conv2.weight, None, ACT_SIGMOID)
+        self.head_conv = ConvLayer(m.conv_out.conv.conv, m.conv_out.conv.bn, ACT_RELU, wd)
+        self.head_out = ConvLayer(m.conv_out.conv_out, None, ACT_NONE, wd)
+
+    # ------------------------------------------------------------------ kernel wrappers
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def new(self, N, H, W, C, dtype=None) -> Map:
+        t = torch.empty((N, H, W, C), dtype=dtype or self.tdt, device=self.dev)
+        return Map(t, N, H, W, C, C)
+
+    def conv(self, x: Map, L: ConvLayer, out: Optional[Map] = None, res: Optional[Map] = None, out_dtype=None,
+             nchw_input: Optional[torch.Tensor] = None) -> Map:
+        """Dense conv + bias + act (+ residual).  ``nchw_input``: read the fp32 NCHW network input in place."""
+        if nchw_input is not None:
+            N, _, H, W = nchw_input.shape
+            xptr, xdt = nchw_input.data_ptr(), F32
+            sxn, sxh, sxw, sxc = 3 * H * W, W, 1, H * W
+            cin = 3
+        else:
+            N, H, W, cin = x.N, x.H, x.W, x.C
+            xptr, xdt = x.ptr, x.dt
+            sxn, sxh, sxw, sxc = H * W * x.ld, W * x.ld, x.ld, 1
+        assert cin == L.cin, (cin, L.cin)
+        OH, OW = _out_size(H, L.kh, L.stride, L.pad), _out_size(W, L.kw, L.stride, L.pad)
+        if out is None:
+            out = self.new(N, OH, OW, L.cout, out_dtype)
+        assert (out.N, out.H, out.W, out.C) == (N, OH, OW, L.cout)
+        wdt = BF16 if L.w.dtype == torch.bfloat16 else F32
+        check(self.lib.cabinet_conv2d_simt(
+            xptr, xdt, sxn, sxh, sxw, sxc, 0, L.w.data_ptr(), wdt, L.w.shape[1], 1, 0, L.b.data_ptr(),
+            res.ptr if res is not None else None, res.ld if res is not None else 0,
+            out.ptr, out.dt, out.ld, 0, 1, N, H, W, cin, L.cout, L.kh, L.kw, L.stride, L.pad, OH, OW, L.act, 1.0,
+            self.stream), "conv2d_simt")
+        self.launches += 1
+        return out
+
+    def dwconv(self, x: Map, L: DwLayer, gap: Optional[torch.Tensor] = None) -> Map:
+        p = (L.k - 1) // 2
+        OH, OW = _out_size(x.H, L.k, L.stride, p), _out_size(x.W, L.k, L.stride, p)
+        out = self.new(x.N, OH, OW, x.C)
+        check(self.lib.cabinet_dwconv(x.ptr, x.ld, L.w.data_ptr(), L.b.data_ptr(), out.ptr, out.ld, x.dt, x.N, x.H,
+                                      x.W, x.C, L.k, L.stride, OH, OW, L.act,
+                                      gap.data_ptr() if gap is not None else None, self.stream), "dwconv")
+        self.launches += 1
+        return out
+
+    def gate(self, gap: torch.Tensor, hw: int, G: GateLayer) -> torch.Tensor:
+        scale = torch.empty_like(gap)
+        check(self.lib.cabinet_gate_mlp(gap.data_ptr(), 1.0 / hw, G.w1.data_ptr(),
+                                        G.b1.data_ptr() if G.b1 is not None else None, G.w2.data_ptr(),
+                                        G.b2.data_ptr() if G.b2 is not None else None, scale.data_ptr(),
+                                        gap.shape[0], G.c, G.cmid, G.gate, self.stream), "gate_mlp")
+        self.launches += 1
+        return scale
+
+    def scale_act(self, x: Map, scale: torch.Tensor, act: int, plus_one: bool = False):
+        check(self.lib.cabinet_scale_act(x.ptr, x.ld, x.dt, scale.data_ptr(), x.N, x.H * x.W, x.C, act,
+                                         int(plus_one), self.stream), "scale_act")
+        self.launches += 1
+
+    def psp(self, x: Map, L: ConvLayer) -> Map:
+        """PSP encoder: pools -> 5C concat -> 1x1 project (reference: cab.py:65-76)."""
+        pooled = torch.empty((x.N, 110, x.C), dtype=torch.float32, device=self.dev)
+        check(self.lib.cabinet_psp_pool(x.ptr, x.ld, x.dt, pooled.data_ptr(), x.N, x.H, x.W, x.C, self.stream),
+              "psp_pool")
+        cat = self.new(x.N, x.H, x.W, 5 * x.C)
+        check(self.lib.cabinet_psp_concat(x.ptr, x.ld, pooled.data_ptr(), cat.ptr, cat.ld, x.dt, x.N, x.H, x.W, x.C,
+                                          self.stream), "psp_concat")
+        self.launches += 2
+        return self.conv(cat, L)
+
+    def attention(self, q: Map, k: Map, v: Map) -> Map:
+        """softmax(q k^T / sqrt(d)) v per image (reference: cab.py:149-153).  q,k,v: [N, L, d] dense."""
+        N, Lq, d = q.N, q.H * q.W, q.C
+        s = torch.empty((N, Lq, Lq), dtype=torch.float32, device=self.dev)
+        # S[b][i][j] = alpha * sum_c q[b][i][c] k[b][j][c]   (k acts as the [Cout=L][K=d] "weights")
+        check(self.lib.cabinet_conv2d_simt(
+            q.ptr, q.dt, 0, 0, q.ld, 1, Lq * q.ld, k.ptr, k.dt, k.ld, 1, Lq * k.ld, None, None, 0,
+            s.data_ptr(), F32, Lq, Lq * Lq, N, 1, 1, Lq, d, Lq, 1, 1, 1, 0, 1, Lq, ACT_NONE, float(d) ** -0.5,
+            self.stream), "attention scores")
+        p = torch.empty((N, Lq, Lq), dtype=self.tdt, device=self.dev)
+        check(self.lib.cabinet_softmax_rows(s.data_ptr(), p.data_ptr(), self.dt, N * Lq, Lq, self.stream), "softmax")
+        ctx = self.new(q.N, q.H, q.W, d)
+        # ctx[b][i][c] = sum_j P[b][i][j] v[b][j][c]   (v read as [Cout=d][K=L] with strides (1, ld))
+        check(self.lib.cabinet_conv2d_simt(
+            p.data_ptr(), self.dt, 0, 0, Lq, 1, Lq * Lq, v.ptr, v.dt, 1, v.ld, Lq * v.ld, None, None, 0,
+            ctx.ptr, ctx.dt, ctx.ld, Lq * ctx.ld, N, 1, 1, Lq, Lq, d, 1, 1, 1, 0, 1, Lq, ACT_NONE, 1.0,
+            self.stream), "attention context")
+        self.launches += 3
+        return ctx
+
+    def bilinear(self, x: Map, out: Map):
+        check(self.lib.cabinet_bilinear_nhwc(x.ptr, x.ld, x.dt, out.ptr, out.ld, out.dt, x.N, x.H, x.W, x.C, out.H,
+                                             out.W, self.stream), "bilinear_nhwc")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ the forward schedule
+    def _trunk(self, x: torch.Tensor):
+        """Everything up to the two fp32 class-logit maps: (final8 [N,H/8,W/8,C], aux8 [N,H/8,W/8,C])."""
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        if x.device != self.dev:
+            raise RuntimeError(f"input on {x.device}, model on {self.dev}")
+        N, _, H, W = x.shape
+        self.launches = 0
+        dev, C = self.dev, self.n_classes
+        n_se = sum(1 for b in self.blocks if "se" in b)
+        gap_all = torch.zeros((n_se + 1, N, 1024), dtype=torch.float32, device=dev)  # one memset per forward
+        self.launches += 1
+
+        # ---- spatial branch (reference: cabinet.py:108-129) -> channels [0:128] of the FFM concat buffer
+        s1 = self.conv(None, self.sb1, nchw_input=x)
+        s2 = self.conv(s1, self.sb2)
+        s3 = self.conv(s2, self.sb3)
+        H8, W8 = s3.H, s3.W
+        cat_ffm = self.new(N, H8, W8, 128 + 256)
+        self.conv(s3, self.sb4, out=cat_ffm.slice(0, 128))
+
+        # ---- backbone (reference: mobilenetv3.py:202-205)
+        f = self.conv(None, self.stem, nchw_input=x)
+        gi = 0
+        for e in self.blocks:
+            s = e["spec"]
+            h = self.conv(f, e["pw1"]) if s["expand"] else f
+            if "se" in e:
+                gap = gap_all[gi].view(-1)[: N * s["exp"]].view(N, s["exp"])
+                gi += 1
+                d = self.dwconv(h, e["dw"], gap)
+                scale = self.gate(gap, d.H * d.W, e["se"])
+                # expand form: SE then activation; no-expand form: activation (already applied) then SE (F10)
+                self.scale_act(d, scale, e["act"] if s["expand"] else ACT_NONE)
+            else:
+                d = self.dwconv(h, e["dw"])
+            f = self.conv(d, e["pw2"], res=f if s["identity"] else None)
+        h32, w32 = f.H, f.W
+        cat_b1 = self.new(N, h32, w32, self.last.cout + 256)  # [mobile_feat | CAB feat] (reference: cabinet.py:87)
+        mf = self.conv(f, self.last, out=cat_b1.slice(0, self.last.cout))
+
+        # ---- attention branch (reference: cabinet.py:75-94, cab.py:131-162,175-184,213-216)
+        feat = self.conv(mf, self.conva)
+        q = self.conv(feat, self.to_q)
+        k = self.psp(self.conv(feat, self.to_k), self.psp_k)
+        v = self.psp(self.conv(feat, self.to_v), self.psp_v)
+        ctx = self.attention(q, k, v)
+        g = self.conv(ctx, self.proj_out)
+        r = feat
+        for L in self.local:
+            r = self.dwconv(r, L)
+        feat2 = cat_b1.slice(self.last.cout, 256)
+        check(self.lib.cabinet_cab_combine(g.ptr, feat.ptr, r.ptr, feat2.ptr, feat2.ld, self.gamma.data_ptr(),
+                                           self.dt, N * h32 * w32, 256, self.stream), "cab_combine")
+        self.launches += 1
+        low = self.conv(feat2, self.convb)
+        fused = self.conv(cat_b1, self.b1)
+        high = self.conv(fused, self.b4, out_dtype=torch.float32)  # class logits stay fp32
+
+        # ---- 1/32 -> 1/8 (reference: cabinet.py:228-233)
+        self.bilinear(low, cat_ffm.slice(128, 256))
+        aux8 = self.new(N, H8, W8, C, torch.float32)
+        self.bilinear(high, aux8)
+
+        # ---- feature fusion (reference: cabinet.py:142-153)
+        ff = self.conv(cat_ffm, self.ffm_blk)
+        gap = gap_all[n_se].view(-1)[: N * 256].view(N, 256)
+        check(self.lib.cabinet_channel_sum(ff.ptr, ff.ld, ff.dt, N, H8 * W8, 256, gap.data_ptr(), self.stream),
+              "channel_sum")
+        self.launches += 1
+        att = self.gate(gap, H8 * W8, self.ffm_gate)
+        self.scale_act(ff, att, ACT_NONE, plus_one=True)
+
+        # ---- head (reference: cabinet.py:162-172)
+        hc = self.conv(ff, self.head_conv)
+        final8 = self.conv(hc, self.head_out, out_dtype=torch.float32)
+        if self.debug:  # stage activations for the parity tests (keeps the buffers alive)
+            self.stages = dict(feat_sb=cat_ffm.slice(0, 128), mobile_feat=mf, low=low, high=high, feat_fuse=ff,
+                               final8=final8, aux8=aux8)
+        return final8, aux8
+
+    @torch.no_grad()
+    def forward(self, x, out_dtype=torch.float32):
+        """-> (final_logit, high_res_logit_up) NCHW (reference: cabinet.py:240-247)."""
+        N, _, H, W = x.shape
+        final8, aux8 = self._trunk(x)
+        odt = BF16 if out_dtype == torch.bfloat16 else F32
+        outs = []
+        for src in (final8, aux8):
+            y = torch.empty((N, self.n_classes, H, W), dtype=torch.bfloat16 if odt == BF16 else torch.float32,
+                            device=self.dev)
+            check(self.lib.cabinet_upsample_logits_nchw(src.ptr, N, src.H, src.W, src.C, y.data_ptr(), odt, H, W,
+                                                        self.stream), "upsample_logits_nchw")
+            self.launches += 1
+            outs.append(y)
+        return outs[0], outs[1]
+
+    @torch.no_grad()
+    def forward_mask(self, x):
+        N, _, H, W = x.shape
+        final8, _ = self._trunk(x)
+        mask = torch.empty((N, H, W), dtype=torch.uint8, device=self.dev)
+        check(self.lib.cabinet_upsample_argmax(final8.ptr, N, final8.H, final8.W, final8.C, mask.data_ptr(), H, W,
+                                               None, 0, 255, None, self.stream), "upsample_argmax")
+        self.launches += 1
+        return mask
+
+    @torch.no_grad()
+    def forward_hist(self, x, labels, hist, ignore_label=255):
+        N, _, H, W = x.shape
+        if labels.dim() == 4:
+            labels = labels.squeeze(1)
+        if labels.dtype not in (torch.int64, torch.uint8) or labels.device != self.dev or not labels.is_contiguous():
+            raise ValueError("labels must be a contiguous int64/uint8 (N,H,W) tensor on the model's device")
+        if hist.dtype != torch.int64 or tuple(hist.shape) != (self.n_classes, self.n_classes) or hist.device != self.dev:
+            raise ValueError("hist must be an int64 (C,C) tensor on the model's device")
+        if tuple(labels.shape) != (N, H, W):
+            raise ValueError(f"labels shape {tuple(labels.shape)} != {(N, H, W)}")
+        final8, _ = self._trunk(x)
+        mask = torch.empty((N, H, W), dtype=torch.uint8, device=self.dev)
+        check(self.lib.cabinet_upsample_argmax(final8.ptr, N, final8.H, final8.W, final8.C, mask.data_ptr(), H, W,
+                                               labels.data_ptr(), 0 if labels.dtype == torch.int64 else 1,
+                                               ignore_label, hist.data_ptr(), self.stream), "upsample_argmax+hist")
+        self.launches += 1
+        return mask

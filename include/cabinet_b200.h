@@ -1,0 +1,137 @@
+/* libcabinet_b200.so — C-ABI of the B200-native CABiNet forward hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every pointer is a DEVICE pointer unless the
+ * parameter is documented as host; every entry point enqueues work on `stream` (a cudaStream_t
+ * passed as void*) and returns without synchronising.  Return value: 0 = ok, CABINET_ERR_INVALID
+ * = rejected arguments, CABINET_ERR_CUDA = CUDA runtime/driver failure; cabinet_last_error()
+ * gives the message (thread-local).  The library allocates no persistent device memory: the
+ * caller (PyTorch's caching allocator in the shipped host code) owns all buffers.
+ *
+ * Activations are NHWC; `ld*` arguments are the PIXEL stride in elements (>= channels), which is
+ * how channel-concatenation (reference torch.cat) is expressed without a copy.  Element types are
+ * CABINET_F32 or CABINET_BF16.  The reference is pure PyTorch: each entry point cites
+ * the reference Python it replaces (paths relative to the reference repo root); there is no
+ * pre-existing FFI in the reference, INTEGRATION.md shows the binding a maintainer would add.
+ */
+#ifndef CABINET_B200_H
+#define CABINET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CABINET_ABI_VERSION 1
+
+enum { CABINET_OK = 0, CABINET_ERR_INVALID = 1, CABINET_ERR_CUDA = 2 };
+enum { CABINET_F32 = 0, CABINET_BF16 = 1 };
+enum {
+    CABINET_ACT_NONE = 0,
+    CABINET_ACT_RELU = 1,     /* nn.ReLU */
+    CABINET_ACT_HSWISH = 2,   /* src/models/mobilenetv3.py:53-65 */
+    CABINET_ACT_HSIGMOID = 3, /* src/models/mobilenetv3.py:38-50 */
+    CABINET_ACT_SIGMOID = 4   /* nn.Sigmoid */
+};
+
+typedef void* cabinet_stream_t; /* cudaStream_t */
+
+const char* cabinet_last_error(void);
+int cabinet_abi_version(void);
+/* Fills SM count and compute capability of the current device. */
+int cabinet_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense convolution + folded-BN bias + activation + residual, CUDA-core implicit GEMM
+ * (fp32 accumulate).  The fp32 parity mode of the whole path and the Cin=3 stems run here.
+ * Replaces nn.Conv2d -> nn.BatchNorm2d(eval) -> {ReLU,HardSwish,-} [-> x + .] at
+ *   src/models/cabinet.py:19-44 (ConvBNReLU), :59-63,68-72 (conva, convb, b1-b4),
+ *   src/models/mobilenetv3.py:86-99 (stems), :126-151 (pw convs), src/models/cab.py:58-63,107-128.
+ * Also used as a batched GEMM (grid over `batches`) for the fp32-mode attention products
+ *   src/models/cab.py:149-153 (torch.bmm).
+ *   out[b][m][co] = act( sum_k x_patch[b][m][k] * w[b][co*w_sco + k*w_sk] + bias[co] ) + res[b][m][co]
+ * x is addressed with explicit element strides (sxn, sxh, sxw, sxc) so both NHWC activations and the
+ * fp32 NCHW network input are read in place; k runs over (ky, kx, c) with c fastest.
+ */
+int cabinet_conv2d_simt(const void* x, int x_dtype, long long sxn, long long sxh, long long sxw, long long sxc,
+                        long long x_batch_stride,
+                        const void* w, int w_dtype, long long w_sco, long long w_sk, long long w_batch_stride,
+                        const float* bias,
+                        const void* res, long long ldres,
+                        void* y, int y_dtype, long long ldy, long long y_batch_stride,
+                        int batches, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                        int OH, int OW, int act, float alpha, cabinet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Depthwise k x k (k in {3,5}, stride in {1,2}, pad (k-1)/2) + folded-BN bias + activation,
+ * optional per-(image, channel) sum of the written values for the SE / GAP consumers.
+ * Replaces the groups=C nn.Conv2d + BatchNorm2d (+act) at src/models/mobilenetv3.py:112-123,130-141
+ * and src/models/cab.py:18-38 (DWConv).  w is [k*k][C] fp32 (BN scale folded), bias [C] fp32.
+ * gap_sum ([N][C] fp32, may be NULL) must be zeroed by the caller; it is accumulated atomically.
+ */
+int cabinet_dwconv(const void* x, long long ldx, const float* w, const float* bias, void* y, long long ldy,
+                   int dtype, int N, int H, int W, int C, int k, int stride, int OH, int OW, int act,
+                   float* gap_sum, cabinet_stream_t stream);
+
+/* Squeeze-excite / FFM channel gate: scale[n][c] = gate(b2 + W2 * relu(b1 + W1 * (sum[n]/HW))).
+ * Replaces src/models/mobilenetv3.py:68-83 (gate = CABINET_ACT_HSIGMOID, biases present) and
+ * src/models/cabinet.py:146-150 (gate = CABINET_ACT_SIGMOID, b1 = b2 = NULL).  All fp32. */
+int cabinet_gate_mlp(const float* gap_sum, float inv_hw, const float* w1, const float* b1, const float* w2,
+                     const float* b2, float* scale, int N, int C, int Cmid, int gate, cabinet_stream_t stream);
+
+/* In place: x[n][p][c] = act(x * scale[n][c])            (plus_one = 0; SE apply, mobilenetv3.py:83 + act)
+ *           x[n][p][c] = x * scale[n][c] + x             (plus_one = 1; FFM, src/models/cabinet.py:152-153) */
+int cabinet_scale_act(void* x, long long ldx, int dtype, const float* scale, int N, long long HW, int C, int act,
+                      int plus_one, cabinet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PSP (src/models/cab.py:46-76).  psp_pool: adaptive average pools of sizes (1,3,6,8) -> pooled
+ * [N][110][C] fp32 (bins floor(i*H/s) .. ceil((i+1)*H/s)).  psp_concat: writes the 5C-channel
+ * tensor [x, up(pool1), up(pool3), up(pool6), up(pool8)] (bilinear, align_corners=False) that the
+ * 1x1 `project` conv consumes. */
+int cabinet_psp_pool(const void* x, long long ldx, int dtype, float* pooled, int N, int H, int W, int C,
+                     cabinet_stream_t stream);
+int cabinet_psp_concat(const void* x, long long ldx, const float* pooled, void* out, long long ldo, int dtype,
+                       int N, int H, int W, int C, cabinet_stream_t stream);
+
+/* Row softmax, in place semantics split: s [rows][cols] fp32 (already scaled) -> p [rows][cols] (dtype).
+ * Replaces F.softmax(attn, dim=-1) at src/models/cab.py:151 in the fp32 parity mode. */
+int cabinet_softmax_rows(const float* s, void* p, int p_dtype, long long rows, int cols, cabinet_stream_t stream);
+
+/* out[p][0:C] = gamma * g + x + x * sigmoid(r)   (src/models/cab.py:182-184,213-216).  g, x, r are dense
+ * [n_pixels][C]; out has pixel stride ldo (it is written straight into the b1 concat buffer,
+ * src/models/cabinet.py:87).  gamma is a DEVICE scalar (the nn.Parameter itself). */
+int cabinet_cab_combine(const void* g, const void* x, const void* r, void* out, long long ldo, const float* gamma,
+                        int dtype, long long n_pixels, int C, cabinet_stream_t stream);
+
+/* out[n][c] += sum over pixels of x[n][p][c]  (out fp32, zeroed by the caller): the global average pool of
+ * src/models/cabinet.py:146 when the producing GEMM did not already emit the partial sums. */
+int cabinet_channel_sum(const void* x, long long ldx, int dtype, int N, long long HW, int C, float* out,
+                        cabinet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Bilinear resize, align_corners=False, NHWC -> NHWC (src/models/cabinet.py:228-233). */
+int cabinet_bilinear_nhwc(const void* x, long long ldx, int x_dtype, void* y, long long ldy, int y_dtype, int N,
+                          int IH, int IW, int C, int OH, int OW, cabinet_stream_t stream);
+
+/* Final x8 bilinear of fp32 NHWC class logits [N][IH][IW][C] (src/models/cabinet.py:240-245):
+ *   _nchw   -> NCHW logits (fp32 or bf16), the tensors CABiNet.forward returns;
+ *   _argmax -> uint8 mask [N][OH][OW] = argmax_c (first maximum wins, like torch.argmax), logits never stored
+ *              (src/scripts/evaluate.py:222); if hist != NULL also accumulates the confusion matrix
+ *              hist[pred*C + label] (int64, src/scripts/evaluate.py:162-191) for labels != ignore_label;
+ *              labels are int64 (label_dtype 0) or uint8 (label_dtype 1), values clipped to [0, C-1]. */
+int cabinet_upsample_logits_nchw(const float* x, int N, int IH, int IW, int C, void* y, int y_dtype, int OH, int OW,
+                                 cabinet_stream_t stream);
+int cabinet_upsample_argmax(const float* x, int N, int IH, int IW, int C, uint8_t* mask, int OH, int OW,
+                            const void* labels, int label_dtype, int ignore_label, long long* hist,
+                            cabinet_stream_t stream);
+
+/* Confusion matrix of an existing prediction map (pred int64 or uint8 like labels):
+ * hist[clip(pred)*C + clip(label)] += 1 where label != ignore_label (src/scripts/evaluate.py:162-191). */
+int cabinet_confusion_hist(const void* pred, int pred_dtype, const void* labels, int label_dtype, long long n_pixels,
+                           int C, int ignore_label, long long* hist, cabinet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CABINET_B200_H */

@@ -1,0 +1,247 @@
+"""GPU: each C-ABI kernel against the same op in plain fp32 torch on the CPU (seeded inputs)."""
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from cabinet_b200 import _lib  # noqa: E402
+from cabinet_b200._lib import ACT_HSIGMOID, ACT_HSWISH, ACT_NONE, ACT_RELU, ACT_SIGMOID, BF16, F32, check  # noqa: E402
+from tests.gpu_util import from_map, rel_l2, to_map, tol  # noqa: E402
+
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def gen(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dt(t):
+    return BF16 if t == torch.bfloat16 else F32
+
+
+def act_ref(x, act):
+    return {ACT_NONE: lambda v: v, ACT_RELU: F.relu, ACT_HSWISH: lambda v: v * F.relu6(v + 3) / 6,
+            ACT_HSIGMOID: lambda v: F.relu6(v + 3) / 6, ACT_SIGMOID: torch.sigmoid}[act](x)
+
+
+def q(x, dtype):
+    """Round through the storage dtype so the reference sees the same inputs as the kernel."""
+    return x.to(dtype).float()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("cin,cout,k,s,p,H,W,act,res", [
+    (16, 64, 1, 1, 0, 17, 23, ACT_RELU, False),
+    (24, 24, 1, 1, 0, 9, 31, ACT_NONE, True),
+    (64, 64, 3, 2, 1, 33, 18, ACT_RELU, False),
+    (72, 40, 3, 1, 1, 8, 8, ACT_HSWISH, False),
+    (200, 80, 1, 1, 0, 5, 7, ACT_NONE, True),
+])
+def test_conv2d_simt(dtype, cin, cout, k, s, p, H, W, act, res):
+    lib = _lib.load()
+    N = 2
+    x = q(gen(N, cin, H, W, seed=1), dtype)
+    w = q(gen(cout, cin, k, k, seed=2, scale=(cin * k * k) ** -0.5), dtype)
+    b = gen(cout, seed=3, scale=0.1)
+    OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    r = q(gen(N, cout, OH, OW, seed=4), dtype) if res else None
+    ref = act_ref(F.conv2d(x, w, b, s, p), act)
+    if res:
+        ref = ref + r
+    xm = to_map(x, dtype, ld=cin + 8, off=8)  # strided input (channel slice of a wider buffer)
+    ym = to_map(torch.zeros(N, cout, OH, OW), dtype, ld=cout + 16, off=16)
+    rm = to_map(r, dtype) if res else None
+    wp = w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().to("cuda", dtype)
+    bd = b.cuda()
+    check(lib.cabinet_conv2d_simt(xm.ptr, xm.dt, H * W * xm.ld, W * xm.ld, xm.ld, 1, 0, wp.data_ptr(), dt(dtype),
+                                  wp.shape[1], 1, 0, bd.data_ptr(), rm.ptr if res else None, rm.ld if res else 0,
+                                  ym.ptr, ym.dt, ym.ld, 0, 1, N, H, W, cin, cout, k, k, s, p, OH, OW, act, 1.0,
+                                  stream()), "conv")
+    torch.cuda.synchronize()
+    assert rel_l2(from_map(ym), ref) < tol(dtype)
+    assert float(ym.t[..., :16].abs().max()) == 0  # the neighbouring slice is untouched
+
+
+def test_conv2d_simt_reads_nchw_fp32_input():
+    lib = _lib.load()
+    x = gen(2, 3, 37, 41, seed=5)
+    for (cout, k, s, p) in [(16, 3, 2, 1), (64, 7, 2, 3)]:
+        w = gen(cout, 3, k, k, seed=6, scale=0.2)
+        b = gen(cout, seed=7, scale=0.1)
+        ref = F.relu(F.conv2d(x, w, b, s, p))
+        OH, OW = ref.shape[2:]
+        ym = to_map(torch.zeros_like(ref), torch.bfloat16)
+        xd, wp, bd = x.cuda(), w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous().cuda(), b.cuda()
+        check(lib.cabinet_conv2d_simt(xd.data_ptr(), F32, 3 * 37 * 41, 41, 1, 37 * 41, 0, wp.data_ptr(), F32,
+                                      wp.shape[1], 1, 0, bd.data_ptr(), None, 0, ym.ptr, BF16, ym.ld, 0, 1, 2, 37, 41,
+                                      3, cout, k, k, s, p, OH, OW, ACT_RELU, 1.0, stream()), "stem")
+        torch.cuda.synchronize()
+        assert rel_l2(from_map(ym), ref) < 4e-3
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,k,s,H,W,act,gap", [
+    (16, 3, 1, 13, 21, ACT_RELU, False), (64, 3, 2, 32, 32, ACT_RELU, False), (72, 5, 2, 19, 27, ACT_NONE, True),
+    (120, 5, 1, 16, 9, ACT_NONE, True), (240, 3, 2, 7, 5, ACT_HSWISH, False), (960, 5, 1, 4, 4, ACT_NONE, True),
+    (8, 3, 1, 1, 1, ACT_RELU, True),
+])
+def test_dwconv(dtype, C, k, s, H, W, act, gap):
+    lib = _lib.load()
+    N = 2
+    x = q(gen(N, C, H, W, seed=1), dtype)
+    w = gen(C, 1, k, k, seed=2, scale=0.3)
+    b = gen(C, seed=3, scale=0.1)
+    p = (k - 1) // 2
+    ref = act_ref(F.conv2d(x, w, b, s, p, 1, C), act)
+    OH, OW = ref.shape[2:]
+    xm, ym = to_map(x, dtype), to_map(torch.zeros_like(ref), dtype)
+    wp, bd = w.view(C, -1).t().contiguous().cuda(), b.cuda()
+    g = torch.zeros(N, C, device="cuda") if gap else None
+    check(lib.cabinet_dwconv(xm.ptr, xm.ld, wp.data_ptr(), bd.data_ptr(), ym.ptr, ym.ld, dt(dtype), N, H, W, C, k, s,
+                             OH, OW, act, g.data_ptr() if gap else None, stream()), "dwconv")
+    torch.cuda.synchronize()
+    assert rel_l2(from_map(ym), ref) < tol(dtype)
+    if gap:
+        assert rel_l2(g.cpu(), ref.sum(dim=(2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("C,Cmid,gate,bias", [(72, 24, ACT_HSIGMOID, True), (960, 240, ACT_HSIGMOID, True),
+                                               (256, 64, ACT_SIGMOID, False)])
+def test_gate_mlp_and_scale_act(C, Cmid, gate, bias):
+    lib = _lib.load()
+    N, HW = 3, 35
+    sums = gen(N, C, seed=1) * HW
+    w1, w2 = gen(Cmid, C, seed=2, scale=C ** -0.5), gen(C, Cmid, seed=3, scale=Cmid ** -0.5)
+    b1, b2 = (gen(Cmid, seed=4, scale=0.1), gen(C, seed=5, scale=0.5)) if bias else (None, None)
+    h = F.relu(F.linear(sums / HW, w1, b1))
+    ref = act_ref(F.linear(h, w2, b2), gate)
+    d = lambda t: None if t is None else t.cuda()  # noqa: E731
+    sd, w1d, w2d, b1d, b2d = d(sums), d(w1), d(w2), d(b1), d(b2)
+    out = torch.empty(N, C, device="cuda")
+    check(lib.cabinet_gate_mlp(sd.data_ptr(), 1.0 / HW, w1d.data_ptr(), b1d.data_ptr() if bias else None,
+                               w2d.data_ptr(), b2d.data_ptr() if bias else None, out.data_ptr(), N, C, Cmid, gate,
+                               stream()), "gate")
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu(), ref) < 1e-5
+    for dtype in DTYPES:
+        x = q(gen(N, C, 5, 7, seed=6), dtype)
+        for act, plus in [(ACT_HSWISH, False), (ACT_RELU, False), (ACT_NONE, True)]:
+            xm = to_map(x, dtype)
+            check(lib.cabinet_scale_act(xm.ptr, xm.ld, xm.dt, out.data_ptr(), N, 35, C, act, int(plus), stream()), "sa")
+            torch.cuda.synchronize()
+            sc = ref.view(N, C, 1, 1)
+            want = x * sc + x if plus else act_ref(x * sc, act)
+            assert rel_l2(from_map(xm), want) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("H,W", [(32, 32), (3, 4), (9, 13), (68, 120)])
+def test_psp_pool_and_concat(dtype, H, W):
+    lib = _lib.load()
+    N, C = 2, 128
+    x = q(gen(N, C, H, W, seed=1), dtype)
+    pools = [F.adaptive_avg_pool2d(x, (s, s)) for s in (1, 3, 6, 8)]
+    ref_pooled = torch.cat([p.permute(0, 2, 3, 1).reshape(N, -1, C) for p in pools], dim=1)
+    ref_cat = torch.cat([x] + [F.interpolate(p, size=(H, W), mode="bilinear", align_corners=False) for p in pools], 1)
+    xm = to_map(x, dtype)
+    pooled = torch.empty(N, 110, C, device="cuda")
+    cat = to_map(torch.zeros(N, 5 * C, H, W), dtype)
+    check(lib.cabinet_psp_pool(xm.ptr, xm.ld, xm.dt, pooled.data_ptr(), N, H, W, C, stream()), "pool")
+    check(lib.cabinet_psp_concat(xm.ptr, xm.ld, pooled.data_ptr(), cat.ptr, cat.ld, xm.dt, N, H, W, C, stream()), "cat")
+    torch.cuda.synchronize()
+    assert rel_l2(pooled.cpu(), ref_pooled) < 1e-5
+    assert rel_l2(from_map(cat), ref_cat) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_softmax_and_cab_combine(dtype):
+    lib = _lib.load()
+    s = gen(37, 300, seed=1, scale=3.0).cuda()
+    p = torch.empty(37, 300, dtype=dtype, device="cuda")
+    check(lib.cabinet_softmax_rows(s.data_ptr(), p.data_ptr(), dt(dtype), 37, 300, stream()), "softmax")
+    g, x, r = (q(gen(2, 256, 6, 5, seed=i), dtype) for i in (2, 3, 4))
+    gm, xm, rm = to_map(g, dtype), to_map(x, dtype), to_map(r, dtype)
+    out = to_map(torch.zeros(2, 256, 6, 5), dtype, ld=256 + 64, off=64)
+    gamma = torch.tensor([0.37], device="cuda")
+    check(lib.cabinet_cab_combine(gm.ptr, xm.ptr, rm.ptr, out.ptr, out.ld, gamma.data_ptr(), dt(dtype), 2 * 30, 256,
+                                  stream()), "combine")
+    torch.cuda.synchronize()
+    assert rel_l2(p.float().cpu(), F.softmax(s.cpu(), dim=-1)) < tol(dtype)
+    assert rel_l2(from_map(out), 0.37 * g + x + x * torch.sigmoid(r)) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_channel_sum(dtype):
+    lib = _lib.load()
+    x = q(gen(3, 256, 20, 13, seed=1), dtype)
+    xm = to_map(x, dtype)
+    out = torch.zeros(3, 256, device="cuda")
+    check(lib.cabinet_channel_sum(xm.ptr, xm.ld, xm.dt, 3, 260, 256, out.data_ptr(), stream()), "sum")
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu(), x.sum(dim=(2, 3))) < 1e-5
+
+
+@pytest.mark.parametrize("C,IH,IW,OH,OW", [(256, 4, 4, 16, 16), (19, 3, 4, 9, 13), (8, 2, 3, 17, 33), (8, 1, 1, 8, 8)])
+def test_bilinear_nhwc(C, IH, IW, OH, OW):
+    lib = _lib.load()
+    for din, dout in [(torch.bfloat16, torch.bfloat16), (torch.float32, torch.float32)]:
+        x = q(gen(2, C, IH, IW, seed=1), din)
+        ref = F.interpolate(x, size=(OH, OW), mode="bilinear", align_corners=False)
+        xm = to_map(x, din)
+        ym = to_map(torch.zeros_like(ref), dout, ld=C + 8, off=4 if dout == torch.float32 else 8)
+        check(lib.cabinet_bilinear_nhwc(xm.ptr, xm.ld, xm.dt, ym.ptr, ym.ld, ym.dt, 2, IH, IW, C, OH, OW, stream()), "bl")
+        torch.cuda.synchronize()
+        assert rel_l2(from_map(ym), ref) < tol(dout)
+
+
+@pytest.mark.parametrize("C,IH,IW,OH,OW", [(8, 16, 16, 128, 128), (19, 9, 13, 70, 100), (8, 5, 7, 37, 51)])
+def test_logits_tail_nchw_argmax_hist(C, IH, IW, OH, OW):
+    lib = _lib.load()
+    N = 2
+    x = gen(N, C, IH, IW, seed=1)
+    ref = F.interpolate(x, size=(OH, OW), mode="bilinear", align_corners=False)
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    for odt in (torch.float32, torch.bfloat16):
+        y = torch.empty(N, C, OH, OW, dtype=odt, device="cuda")
+        check(lib.cabinet_upsample_logits_nchw(xd.data_ptr(), N, IH, IW, C, y.data_ptr(), dt(odt), OH, OW, stream()), "up")
+        torch.cuda.synchronize()
+        assert rel_l2(y.float().cpu(), ref) < (1e-5 if odt == torch.float32 else 4e-3)
+        if odt == torch.float32:
+            y32 = y.cpu()
+    labels = torch.randint(0, C, (N, OH, OW), generator=torch.Generator().manual_seed(3))
+    labels[:, OH // 3, :] = 255
+    mask = torch.empty(N, OH, OW, dtype=torch.uint8, device="cuda")
+    hist = torch.zeros(C, C, dtype=torch.int64, device="cuda")
+    for ldt, lab in ((0, labels.cuda()), (1, labels.to(torch.uint8).cuda())):
+        check(lib.cabinet_upsample_argmax(xd.data_ptr(), N, IH, IW, C, mask.data_ptr(), OH, OW, lab.data_ptr(), ldt, 255,
+                                          hist.data_ptr(), stream()), "argmax")
+    torch.cuda.synchronize()
+    # bit-exact vs argmax of OUR fp32 upsample (same arithmetic); and vs torch up to fp32 round-off ties
+    want = torch.argmax(y32, dim=1)
+    assert torch.equal(mask.cpu().long(), want)
+    assert (mask.cpu().long() == torch.argmax(ref, dim=1)).float().mean() > 0.9995
+    from oracle.evaluator_oracle import compute_hist
+    h = sum(compute_hist(want[i].numpy(), labels[i].numpy(), C, 255) for i in range(N))
+    np.testing.assert_array_equal(hist.cpu().numpy(), 2 * h)  # accumulated twice (int64 + uint8 labels)
+    # standalone confusion matrix incl. out-of-range predictions/labels (clipped like the reference)
+    pred = torch.randint(-2, C + 3, (5000,), generator=torch.Generator().manual_seed(4))
+    lab = torch.randint(0, C + 2, (5000,), generator=torch.Generator().manual_seed(5))
+    lab[::7] = 255
+    hist2 = torch.zeros(C, C, dtype=torch.int64, device="cuda")
+    pd, ld_ = pred.cuda(), lab.cuda()
+    check(lib.cabinet_confusion_hist(pd.data_ptr(), 0, ld_.data_ptr(), 0, 5000, C, 255, hist2.data_ptr(), stream()), "hist")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(hist2.cpu().numpy(), compute_hist(pred.numpy(), lab.numpy(), C, 255))
+
+
+def test_empty_batch_is_a_noop():
+    lib = _lib.load()
+    check(lib.cabinet_softmax_rows(1, 1, F32, 0, 5, stream()), "softmax")
+    check(lib.cabinet_confusion_hist(1, 0, 1, 0, 0, 4, 255, 1, stream()), "hist")
