@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the CABiNet forward hot path (BASELINE.json: images/sec at 1024x1024, MNv3-Large).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One process per GPU (N > 1: launched by torchrun).  A step = one forward of the hot path over one batch of
+synthetic images per GPU.  Prints ONE JSON line on rank 0.
+
+* ``value``     images/sec of ``CABiNet.forward`` (both bf16 NCHW logit tensors returned), inputs resident in HBM,
+                timed with CUDA events, max over ranks.  Inputs (201 MB per batch) exceed the 126 MB L2.
+* ``e2e``       the same metric through the public evaluation call with HOST buffers: pinned fp32 images ->
+                H2D -> ``model.accumulate_hist`` (forward + fused upsample/argmax/confusion matrix) -> D2H of the
+                uint8 mask, every step inside the timed region; the per-rank int64 confusion matrices are
+                all-reduced over NCCL once at the end (the path's only collective, evaluate.py:230-235).
+* ``roofline``  dominant kernel family by device time: algorithmic bytes (or flops) / CUDA-event duration of its
+                launches, against MEASURED_PEAKS.json.
+* ``cpu_baseline`` the oracle port of the reference forward on the host cores (rank 0, N = 1 only).
+* ``--impl reference`` times that same CPU implementation as the reference arm.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "images/sec at 1024x1024 (MNv3-L)"
+UNIT = "images/s"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.is_file():
+        try:
+            d = json.loads(p.read_text())
+            return {k: float(d[k]) for k in FALLBACK_PEAKS if k in d} | {"source": "measured"}
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_id: str):
+        self.gpu_id, self.proc, self.lines = gpu_id, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpu_id, f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v == "Active":
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_forward_rate(mode, n_classes, size, batch, iters, warmup):
+    """Oracle port of the reference forward on the host cores -> (images/s, threads)."""
+    import torch
+
+    from cabinet_b200.constants import BACKBONE_CFGS
+    from cabinet_b200.synthetic import build_model, make_input
+    from oracle import cabinet_oracle
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = build_model(n_classes, mode)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = make_input(batch, size, size)
+    times = []
+    for i in range(warmup + iters):
+        t0 = time.perf_counter()
+        cabinet_oracle.cabinet_forward(sd, x, BACKBONE_CFGS[mode])
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return batch / statistics.median(times), torch.get_num_threads(), times
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (oracle port; the Python reference tree does
+    not travel to the GPU box), all host threads, one image per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    rate, threads, times = cpu_forward_rate(args.mode, args.classes, args.size, 1, args.steps, max(1, min(args.warmup, 2)))
+    ms = 1e3 * statistics.median(times)
+    sample = f"{args.steps} steps x 1 image {args.size}x{args.size}, fp32, oracle port of src/models/cabinet.py forward"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, batch=1),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0}))
+
+
+def workload_config(args, batch=None):
+    return {"workload": f"CABiNet MobileNetV3-{args.mode.capitalize()} forward, {args.size}x{args.size}, "
+                        f"batch {batch or args.batch} per GPU, {args.classes} classes (BASELINE configs[1])",
+            "mode": args.mode, "size": args.size, "batch_per_gpu": batch or args.batch, "n_classes": args.classes,
+            "outputs": "final + aux logits, bf16 NCHW", "cache": "inputs (201 MB/batch) larger than the 126 MB L2",
+            "weights": "random-init seed 0 + perturbed BN/bias/gamma (synthetic.py)", "parallelism": f"dp{args.gpus}"}
+
+
+def summarise_trace(rows, steps, peaks):
+    """Per-kernel-family totals -> table + the dominant family's roofline entry."""
+    fam = {}
+    for r in rows:
+        f = fam.setdefault(r["kernel"], {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
+        f["ms"] += r["ms"]
+        f["bytes"] += r["bytes"]
+        f["flops"] += r["flops"]
+        f["launches"] += 1
+    total = sum(f["ms"] for f in fam.values()) or 1.0
+    table = []
+    for k, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+        gbs = f["bytes"] / (f["ms"] * 1e-3) / 1e9 if f["ms"] else 0.0
+        tfl = f["flops"] / (f["ms"] * 1e-3) / 1e12 if f["ms"] else 0.0
+        table.append({"kernel": k, "share": f["ms"] / total, "ms_per_step": f["ms"] / steps,
+                      "launches_per_step": f["launches"] / steps, "GB/s": gbs, "TFLOP/s": tfl})
+    return table
+
+
+def roofline_entry(row, fam_rows, peaks, timed_in_step=True):
+    nbytes = sum(r["bytes"] for r in fam_rows)
+    flops = sum(r["flops"] for r in fam_rows)
+    ms = sum(r["ms"] for r in fam_rows)
+    n = len(fam_rows)
+    tf_peak = peaks["bf16_tflops_sustained" if timed_in_step else "bf16_tflops"]
+    t_hbm = nbytes / (peaks["hbm_gbs"] * 1e9)
+    t_tc = flops / (tf_peak * 1e12)
+    if t_tc > t_hbm:
+        ach = flops / (ms * 1e-3) / 1e12
+        return {"kernel": row["kernel"], "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": ach / tf_peak, "traffic": None, "launches": n, "avg_launch_us": 1e3 * ms / n,
+                "algorithmic_flops_per_launch": flops / n, "peak_source": peaks["source"]}
+    ach = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": row["kernel"], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": ach / peaks["hbm_gbs"], "traffic": None, "launches": n, "avg_launch_us": 1e3 * ms / n,
+            "algorithmic_bytes_per_launch": nbytes / n, "peak_source": peaks["source"]}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from cabinet_b200.synthetic import build_model, make_input, make_labels
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    K, Wm, B, S, C = args.steps, args.warmup, args.batch, args.size, args.classes
+
+    model = build_model(C, args.mode).to(dev)
+    model.precision = args.precision
+    model.logits_dtype = torch.bfloat16
+    eng = model.engine()
+    x_host = make_input(B, S, S, seed=7 + rank).pin_memory()          # each rank owns different images
+    lb_host = make_labels(B, S, S, C, seed=11 + rank).to(torch.uint8).pin_memory()
+    x = x_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    uuid = str(torch.cuda.get_device_properties(local).uuid)
+    gpu_id = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+
+    # ---------------- device-resident throughput (value)
+    with torch.no_grad():
+        for _ in range(Wm):
+            model(x)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(gpu_id) as clk:
+            e0.record()
+            for _ in range(K):
+                out = model(x)
+            e1.record()
+            barrier()
+        launches = eng.launches * K
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        value = world * B * K / (ms_total * 1e-3)
+        clocks = clk.summary()
+        del out
+
+        # ---------------- per-kernel roofline: same K steps, every launch bracketed by CUDA events on its stream
+        eng.start_trace()
+        for _ in range(K):
+            model(x)
+        rows = eng.stop_trace()
+        table = summarise_trace(rows, K, peaks)
+        dom = table[0]
+        roof = roofline_entry(dom, [r for r in rows if r["kernel"] == dom["kernel"]], peaks)
+        traced_ms = sum(r["ms"] for r in rows) / K
+
+        # ---------------- end to end through the public evaluation call, host buffers
+        hist = torch.zeros(C, C, dtype=torch.int64, device=dev)
+        mask_host = torch.empty((B, S, S), dtype=torch.uint8).pin_memory()
+        xd = torch.empty_like(x)
+        lbd = torch.empty((B, S, S), dtype=torch.uint8, device=dev)
+
+        def e2e_step():
+            xd.copy_(x_host, non_blocking=True)
+            lbd.copy_(lb_host, non_blocking=True)
+            m = model.accumulate_hist(xd, lbd, hist)
+            mask_host.copy_(m, non_blocking=True)
+
+        for _ in range(max(1, Wm // 2)):
+            e2e_step()
+        hist.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(K):
+            e2e_step()
+        if world > 1:
+            dist.all_reduce(hist)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
+        e2e_val = world * B * K / (e2e_ms * 1e-3)
+        valid = int((lb_host != 255).sum()) * K
+        hist_sum = int(hist.sum().item())
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + lb_host.numel(),
+                "d2h_bytes_per_step": mask_host.numel(), "ms_per_step": e2e_ms / K, "wall_s": wall,
+                "api": "CABiNet.accumulate_hist (forward + fused upsample/argmax/confusion matrix) + mask D2H",
+                "hist_checksum_ok": (world > 1) or hist_sum == valid},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        "kernels": table, "traced_ms_per_step": traced_ms, "peaks": peaks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        rate, threads, times = cpu_forward_rate(args.mode, C, S, 1, 5, 2)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"5 timed forwards of 1 image {S}x{S} fp32 (median), oracle port of the "
+                                          f"reference forward, {sum(times):.1f} s of CPU work"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--mode", default="large", choices=["large", "small"])
+    ap.add_argument("--classes", type=int, default=8)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

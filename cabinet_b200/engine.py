@@ -69,8 +69,9 @@ def _fold(conv_w, conv_b, bn, eps=BN_EPS):
 class ConvLayer:
     """Dense conv (+folded BN) packed for the kernels: w [Cout][KH*KW*Cin] (c fastest), fp32 bias."""
 
-    def __init__(self, conv, bn, act, wdtype):
+    def __init__(self, conv, bn, act, wdtype, name=""):
         w, b = _fold(conv.weight, conv.bias, bn)
+        self.name = name
         self.cout, self.cin, self.kh, self.kw = w.shape
         self.stride, self.pad = conv.stride[0], conv.padding[0]
         self.act = act
@@ -82,8 +83,9 @@ class ConvLayer:
 class DwLayer:
     """Depthwise conv (+folded BN): w [k*k][C] fp32, bias fp32."""
 
-    def __init__(self, conv, bn, act):
+    def __init__(self, conv, bn, act, name=""):
         w, b = _fold(conv.weight, conv.bias, bn)
+        self.name = name
         self.c, self.k, self.stride, self.act = w.shape[0], w.shape[2], conv.stride[0], act
         self.w = w.view(self.c, -1).t().contiguous()
         self.b = b.contiguous()
@@ -123,6 +125,7 @@ class Engine:
         self.use_tc = precision == "bf16"
         self.debug = False
         self.stages = {}
+        self.trace, self.trace_filter = None, None
         with torch.no_grad():
             self._pack(model)
 
@@ -132,56 +135,72 @@ class Engine:
         f32 = torch.float32
         mob = m.mobile
         # stems read the fp32 NCHW input directly; their (tiny) weights stay fp32
-        self.stem = ConvLayer(mob.features[0][0], mob.features[0][1], ACT_HSWISH, f32)
+        self.stem = ConvLayer(mob.features[0][0], mob.features[0][1], ACT_HSWISH, f32, "mobile.stem")
         self.blocks = []
-        for blk in list(mob.features)[1:]:
+        for bi, blk in enumerate(list(mob.features)[1:], 1):
             s, c = blk.spec, blk.conv
             act = ACT_HSWISH if s["hs"] else ACT_RELU
             e = dict(spec=s, act=act)
             if s["expand"]:
-                e["pw1"] = ConvLayer(c[0], c[1], act, wd)
-                e["dw"] = DwLayer(c[3], c[4], ACT_NONE if s["se"] else act)
+                e["pw1"] = ConvLayer(c[0], c[1], act, wd, f"mobile.f{bi}.expand")
+                e["dw"] = DwLayer(c[3], c[4], ACT_NONE if s["se"] else act, f"mobile.f{bi}.dw")
                 se, pw2, bn2 = c[5], c[7], c[8]
             else:
-                e["dw"] = DwLayer(c[0], c[1], act)
+                e["dw"] = DwLayer(c[0], c[1], act, f"mobile.f{bi}.dw")
                 se, pw2, bn2 = c[3], c[4], c[5]
             if s["se"]:
                 e["se"] = GateLayer(se.fc[0].weight, se.fc[0].bias, se.fc[2].weight, se.fc[2].bias, ACT_HSIGMOID)
-            e["pw2"] = ConvLayer(pw2, bn2, ACT_NONE, wd)
+            e["pw2"] = ConvLayer(pw2, bn2, ACT_NONE, wd, f"mobile.f{bi}.project")
             self.blocks.append(e)
-        self.last = ConvLayer(mob.conv[0], mob.conv[1], ACT_HSWISH, wd)
+        self.last = ConvLayer(mob.conv[0], mob.conv[1], ACT_HSWISH, wd, "mobile.conv")
 
         sb = m.sb
-        self.sb1 = ConvLayer(sb.conv1.conv, sb.conv1.bn, ACT_RELU, f32)
-        self.sb2 = ConvLayer(sb.conv2.conv, sb.conv2.bn, ACT_RELU, wd)
-        self.sb3 = ConvLayer(sb.conv3.conv, sb.conv3.bn, ACT_RELU, wd)
-        self.sb4 = ConvLayer(sb.conv_out.conv, sb.conv_out.bn, ACT_RELU, wd)
+        self.sb1 = ConvLayer(sb.conv1.conv, sb.conv1.bn, ACT_RELU, f32, "sb.conv1")
+        self.sb2 = ConvLayer(sb.conv2.conv, sb.conv2.bn, ACT_RELU, wd, "sb.conv2")
+        self.sb3 = ConvLayer(sb.conv3.conv, sb.conv3.bn, ACT_RELU, wd, "sb.conv3")
+        self.sb4 = ConvLayer(sb.conv_out.conv, sb.conv_out.bn, ACT_RELU, wd, "sb.conv_out")
 
         ab, ga = m.ab, m.ab.a2block.global_attn
-        self.conva = ConvLayer(ab.conva[0], ab.conva[1], ACT_RELU, wd)
-        self.to_q = ConvLayer(ga.to_query[0], ga.to_query[1], ACT_RELU, wd)
-        self.to_k = ConvLayer(ga.to_key[0], ga.to_key[1], ACT_RELU, wd)
-        self.to_v = ConvLayer(ga.to_value, None, ACT_NONE, wd)
-        self.psp_k = ConvLayer(ga.psp_key.project, None, ACT_NONE, wd)
-        self.psp_v = ConvLayer(ga.psp_value.project, None, ACT_NONE, wd)
-        self.proj_out = ConvLayer(ga.project_out, None, ACT_NONE, wd)
-        self.local = [DwLayer(d.block[0], d.block[1], ACT_RELU) for d in ab.a2block.local_attn.refine]
+        self.conva = ConvLayer(ab.conva[0], ab.conva[1], ACT_RELU, wd, "ab.conva")
+        self.to_q = ConvLayer(ga.to_query[0], ga.to_query[1], ACT_RELU, wd, "cab.to_query")
+        self.to_k = ConvLayer(ga.to_key[0], ga.to_key[1], ACT_RELU, wd, "cab.to_key")
+        self.to_v = ConvLayer(ga.to_value, None, ACT_NONE, wd, "cab.to_value")
+        self.psp_k = ConvLayer(ga.psp_key.project, None, ACT_NONE, wd, "cab.psp_key")
+        self.psp_v = ConvLayer(ga.psp_value.project, None, ACT_NONE, wd, "cab.psp_value")
+        self.proj_out = ConvLayer(ga.project_out, None, ACT_NONE, wd, "cab.project_out")
+        self.local = [DwLayer(d.block[0], d.block[1], ACT_RELU, f"cab.local{i}")
+                      for i, d in enumerate(ab.a2block.local_attn.refine)]
         self.gamma = ab.a2block.gamma.detach().float().contiguous()
-        self.convb = ConvLayer(ab.convb, None, ACT_NONE, wd)
-        self.b1 = ConvLayer(ab.b1, ab.b2, ACT_RELU, wd)
-        self.b4 = ConvLayer(ab.b4, None, ACT_NONE, wd)
+        self.convb = ConvLayer(ab.convb, None, ACT_NONE, wd, "ab.convb")
+        self.b1 = ConvLayer(ab.b1, ab.b2, ACT_RELU, wd, "ab.b1")
+        self.b4 = ConvLayer(ab.b4, None, ACT_NONE, wd, "ab.b4")
         self.key_ch = self.to_k.cout
 
         ffm = m.ffm
-        self.ffm_blk = ConvLayer(ffm.convblk.conv, ffm.convblk.bn, ACT_RELU, wd)
+        self.ffm_blk = ConvLayer(ffm.convblk.conv, ffm.convblk.bn, ACT_RELU, wd, "ffm.convblk")
         self.ffm_gate = GateLayer(ffm.conv1.weight, None, ffm.conv2.weight, None, ACT_SIGMOID)
-        self.head_conv = ConvLayer(m.conv_out.conv.conv, m.conv_out.conv.bn, ACT_RELU, wd)
-        self.head_out = ConvLayer(m.conv_out.conv_out, None, ACT_NONE, wd)
+        self.head_conv = ConvLayer(m.conv_out.conv.conv, m.conv_out.conv.bn, ACT_RELU, wd, "conv_out.conv")
+        self.head_out = ConvLayer(m.conv_out.conv_out, None, ACT_NONE, wd, "conv_out.conv_out")
 
     # ------------------------------------------------------------------ kernel wrappers
     @property
     def stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _run(self, kernel: str, layer: str, nbytes: int, flops: int, fn, *args):
+        """Enqueue one kernel.  With tracing on, bracket it with CUDA events on the launching stream and keep
+        its ALGORITHMIC bytes/flops (each operand once) for the roofline report."""
+        tr = self.trace
+        if tr is not None and (self.trace_filter is None or kernel in self.trace_filter):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            tr.append((kernel, layer, nbytes, flops, e0, e1))
+        else:
+            rc = fn(*args)
+        check(rc, f"{kernel}[{layer}]")
+        self.launches += 1
 
     def new(self, N, H, W, C, dtype=None) -> Map:
         t = torch.empty((N, H, W, C), dtype=dtype or self.tdt, device=self.dev)
@@ -192,86 +211,94 @@ class Engine:
         """Dense conv + bias + act (+ residual).  ``nchw_input``: read the fp32 NCHW network input in place."""
         if nchw_input is not None:
             N, _, H, W = nchw_input.shape
-            xptr, xdt = nchw_input.data_ptr(), F32
+            xptr, xdt, xes = nchw_input.data_ptr(), F32, 4
             sxn, sxh, sxw, sxc = 3 * H * W, W, 1, H * W
             cin = 3
         else:
             N, H, W, cin = x.N, x.H, x.W, x.C
-            xptr, xdt = x.ptr, x.dt
+            xptr, xdt, xes = x.ptr, x.dt, x.t.element_size()
             sxn, sxh, sxw, sxc = H * W * x.ld, W * x.ld, x.ld, 1
-        assert cin == L.cin, (cin, L.cin)
+        assert cin == L.cin, (L.name, cin, L.cin)
         OH, OW = _out_size(H, L.kh, L.stride, L.pad), _out_size(W, L.kw, L.stride, L.pad)
         if out is None:
             out = self.new(N, OH, OW, L.cout, out_dtype)
-        assert (out.N, out.H, out.W, out.C) == (N, OH, OW, L.cout)
+        assert (out.N, out.H, out.W, out.C) == (N, OH, OW, L.cout), L.name
+        M = N * OH * OW
+        nbytes = (N * H * W * cin * xes + M * L.cout * out.t.element_size() + L.w.numel() * L.w.element_size()
+                  + (M * L.cout * res.t.element_size() if res is not None else 0))
+        flops = 2 * M * L.cout * L.cin * L.kh * L.kw
+        if self.use_tc and L.tc is not None and nchw_input is None and x.dt == BF16:
+            self._conv_tc(x, L, out, res, OH, OW, nbytes, flops)
+            return out
         wdt = BF16 if L.w.dtype == torch.bfloat16 else F32
-        check(self.lib.cabinet_conv2d_simt(
-            xptr, xdt, sxn, sxh, sxw, sxc, 0, L.w.data_ptr(), wdt, L.w.shape[1], 1, 0, L.b.data_ptr(),
-            res.ptr if res is not None else None, res.ld if res is not None else 0,
-            out.ptr, out.dt, out.ld, 0, 1, N, H, W, cin, L.cout, L.kh, L.kw, L.stride, L.pad, OH, OW, L.act, 1.0,
-            self.stream), "conv2d_simt")
-        self.launches += 1
+        self._run("conv2d_simt", L.name, nbytes, flops, self.lib.cabinet_conv2d_simt,
+                  xptr, xdt, sxn, sxh, sxw, sxc, 0, L.w.data_ptr(), wdt, L.w.shape[1], 1, 0, L.b.data_ptr(),
+                  res.ptr if res is not None else None, res.ld if res is not None else 0,
+                  out.ptr, out.dt, out.ld, 0, 1, N, H, W, cin, L.cout, L.kh, L.kw, L.stride, L.pad, OH, OW, L.act,
+                  1.0, self.stream)
         return out
 
     def dwconv(self, x: Map, L: DwLayer, gap: Optional[torch.Tensor] = None) -> Map:
         p = (L.k - 1) // 2
         OH, OW = _out_size(x.H, L.k, L.stride, p), _out_size(x.W, L.k, L.stride, p)
         out = self.new(x.N, OH, OW, x.C)
-        check(self.lib.cabinet_dwconv(x.ptr, x.ld, L.w.data_ptr(), L.b.data_ptr(), out.ptr, out.ld, x.dt, x.N, x.H,
-                                      x.W, x.C, L.k, L.stride, OH, OW, L.act,
-                                      gap.data_ptr() if gap is not None else None, self.stream), "dwconv")
-        self.launches += 1
+        es = x.t.element_size()
+        nbytes = x.N * x.C * (x.H * x.W + OH * OW) * es + L.w.numel() * 4
+        self._run("dwconv", L.name, nbytes, 2 * x.N * OH * OW * x.C * L.k * L.k, self.lib.cabinet_dwconv,
+                  x.ptr, x.ld, L.w.data_ptr(), L.b.data_ptr(), out.ptr, out.ld, x.dt, x.N, x.H, x.W, x.C, L.k, L.stride,
+                  OH, OW, L.act, gap.data_ptr() if gap is not None else None, self.stream)
         return out
 
-    def gate(self, gap: torch.Tensor, hw: int, G: GateLayer) -> torch.Tensor:
+    def gate(self, gap: torch.Tensor, hw: int, G: GateLayer, name: str) -> torch.Tensor:
         scale = torch.empty_like(gap)
-        check(self.lib.cabinet_gate_mlp(gap.data_ptr(), 1.0 / hw, G.w1.data_ptr(),
-                                        G.b1.data_ptr() if G.b1 is not None else None, G.w2.data_ptr(),
-                                        G.b2.data_ptr() if G.b2 is not None else None, scale.data_ptr(),
-                                        gap.shape[0], G.c, G.cmid, G.gate, self.stream), "gate_mlp")
-        self.launches += 1
+        self._run("gate_mlp", name, (G.w1.numel() + G.w2.numel()) * 4, 4 * gap.shape[0] * G.c * G.cmid,
+                  self.lib.cabinet_gate_mlp, gap.data_ptr(), 1.0 / hw, G.w1.data_ptr(),
+                  G.b1.data_ptr() if G.b1 is not None else None, G.w2.data_ptr(),
+                  G.b2.data_ptr() if G.b2 is not None else None, scale.data_ptr(), gap.shape[0], G.c, G.cmid, G.gate,
+                  self.stream)
         return scale
 
-    def scale_act(self, x: Map, scale: torch.Tensor, act: int, plus_one: bool = False):
-        check(self.lib.cabinet_scale_act(x.ptr, x.ld, x.dt, scale.data_ptr(), x.N, x.H * x.W, x.C, act,
-                                         int(plus_one), self.stream), "scale_act")
-        self.launches += 1
+    def scale_act(self, x: Map, scale: torch.Tensor, act: int, name: str, plus_one: bool = False):
+        # not in the per-layer-fusion byte model (SE scale / FFM gate are "free riders" there): counted as 0 algorithmic
+        self._run("scale_act", name, 0, 0, self.lib.cabinet_scale_act, x.ptr, x.ld, x.dt, scale.data_ptr(), x.N,
+                  x.H * x.W, x.C, act, int(plus_one), self.stream)
 
     def psp(self, x: Map, L: ConvLayer) -> Map:
         """PSP encoder: pools -> 5C concat -> 1x1 project (reference: cab.py:65-76)."""
         pooled = torch.empty((x.N, 110, x.C), dtype=torch.float32, device=self.dev)
-        check(self.lib.cabinet_psp_pool(x.ptr, x.ld, x.dt, pooled.data_ptr(), x.N, x.H, x.W, x.C, self.stream),
-              "psp_pool")
+        es = x.t.element_size()
+        self._run("psp_pool", L.name, x.N * x.H * x.W * x.C * es, 0, self.lib.cabinet_psp_pool, x.ptr, x.ld, x.dt,
+                  pooled.data_ptr(), x.N, x.H, x.W, x.C, self.stream)
         cat = self.new(x.N, x.H, x.W, 5 * x.C)
-        check(self.lib.cabinet_psp_concat(x.ptr, x.ld, pooled.data_ptr(), cat.ptr, cat.ld, x.dt, x.N, x.H, x.W, x.C,
-                                          self.stream), "psp_concat")
-        self.launches += 2
+        self._run("psp_concat", L.name, 0, 0, self.lib.cabinet_psp_concat, x.ptr, x.ld, pooled.data_ptr(), cat.ptr,
+                  cat.ld, x.dt, x.N, x.H, x.W, x.C, self.stream)
         return self.conv(cat, L)
 
     def attention(self, q: Map, k: Map, v: Map) -> Map:
         """softmax(q k^T / sqrt(d)) v per image (reference: cab.py:149-153).  q,k,v: [N, L, d] dense."""
         N, Lq, d = q.N, q.H * q.W, q.C
+        es = q.t.element_size()
+        ctx = self.new(q.N, q.H, q.W, d)
         s = torch.empty((N, Lq, Lq), dtype=torch.float32, device=self.dev)
         # S[b][i][j] = alpha * sum_c q[b][i][c] k[b][j][c]   (k acts as the [Cout=L][K=d] "weights")
-        check(self.lib.cabinet_conv2d_simt(
-            q.ptr, q.dt, 0, 0, q.ld, 1, Lq * q.ld, k.ptr, k.dt, k.ld, 1, Lq * k.ld, None, None, 0,
-            s.data_ptr(), F32, Lq, Lq * Lq, N, 1, 1, Lq, d, Lq, 1, 1, 1, 0, 1, Lq, ACT_NONE, float(d) ** -0.5,
-            self.stream), "attention scores")
+        self._run("conv2d_simt", "cab.qk", 2 * N * Lq * d * es, 2 * N * Lq * Lq * d, self.lib.cabinet_conv2d_simt,
+                  q.ptr, q.dt, 0, 0, q.ld, 1, Lq * q.ld, k.ptr, k.dt, k.ld, 1, Lq * k.ld, None, None, 0,
+                  s.data_ptr(), F32, Lq, Lq * Lq, N, 1, 1, Lq, d, Lq, 1, 1, 1, 0, 1, Lq, ACT_NONE, float(d) ** -0.5,
+                  self.stream)
         p = torch.empty((N, Lq, Lq), dtype=self.tdt, device=self.dev)
-        check(self.lib.cabinet_softmax_rows(s.data_ptr(), p.data_ptr(), self.dt, N * Lq, Lq, self.stream), "softmax")
-        ctx = self.new(q.N, q.H, q.W, d)
+        self._run("softmax_rows", "cab.softmax", 0, 0, self.lib.cabinet_softmax_rows, s.data_ptr(), p.data_ptr(),
+                  self.dt, N * Lq, Lq, self.stream)
         # ctx[b][i][c] = sum_j P[b][i][j] v[b][j][c]   (v read as [Cout=d][K=L] with strides (1, ld))
-        check(self.lib.cabinet_conv2d_simt(
-            p.data_ptr(), self.dt, 0, 0, Lq, 1, Lq * Lq, v.ptr, v.dt, 1, v.ld, Lq * v.ld, None, None, 0,
-            ctx.ptr, ctx.dt, ctx.ld, Lq * ctx.ld, N, 1, 1, Lq, Lq, d, 1, 1, 1, 0, 1, Lq, ACT_NONE, 1.0,
-            self.stream), "attention context")
-        self.launches += 3
+        self._run("conv2d_simt", "cab.pv", 2 * N * Lq * d * es, 2 * N * Lq * Lq * d, self.lib.cabinet_conv2d_simt,
+                  p.data_ptr(), self.dt, 0, 0, Lq, 1, Lq * Lq, v.ptr, v.dt, 1, v.ld, Lq * v.ld, None, None, 0,
+                  ctx.ptr, ctx.dt, ctx.ld, Lq * ctx.ld, N, 1, 1, Lq, Lq, d, 1, 1, 1, 0, 1, Lq, ACT_NONE, 1.0,
+                  self.stream)
         return ctx
 
-    def bilinear(self, x: Map, out: Map):
-        check(self.lib.cabinet_bilinear_nhwc(x.ptr, x.ld, x.dt, out.ptr, out.ld, out.dt, x.N, x.H, x.W, x.C, out.H,
-                                             out.W, self.stream), "bilinear_nhwc")
-        self.launches += 1
+    def bilinear(self, x: Map, out: Map, name: str):
+        nbytes = x.N * x.C * (x.H * x.W * x.t.element_size() + out.H * out.W * out.t.element_size())
+        self._run("bilinear_nhwc", name, nbytes, 0, self.lib.cabinet_bilinear_nhwc, x.ptr, x.ld, x.dt, out.ptr, out.ld,
+                  out.dt, x.N, x.H, x.W, x.C, out.H, out.W, self.stream)
 
     # ------------------------------------------------------------------ the forward schedule
     def _trunk(self, x: torch.Tensor):
@@ -305,9 +332,9 @@ class Engine:
                 gap = gap_all[gi].view(-1)[: N * s["exp"]].view(N, s["exp"])
                 gi += 1
                 d = self.dwconv(h, e["dw"], gap)
-                scale = self.gate(gap, d.H * d.W, e["se"])
+                scale = self.gate(gap, d.H * d.W, e["se"], e["dw"].name)
                 # expand form: SE then activation; no-expand form: activation (already applied) then SE (F10)
-                self.scale_act(d, scale, e["act"] if s["expand"] else ACT_NONE)
+                self.scale_act(d, scale, e["act"] if s["expand"] else ACT_NONE, e["dw"].name)
             else:
                 d = self.dwconv(h, e["dw"])
             f = self.conv(d, e["pw2"], res=f if s["identity"] else None)
@@ -326,26 +353,25 @@ class Engine:
         for L in self.local:
             r = self.dwconv(r, L)
         feat2 = cat_b1.slice(self.last.cout, 256)
-        check(self.lib.cabinet_cab_combine(g.ptr, feat.ptr, r.ptr, feat2.ptr, feat2.ld, self.gamma.data_ptr(),
-                                           self.dt, N * h32 * w32, 256, self.stream), "cab_combine")
-        self.launches += 1
+        es = feat.t.element_size()
+        self._run("cab_combine", "cab", 2 * N * h32 * w32 * 256 * es, 0, self.lib.cabinet_cab_combine, g.ptr, feat.ptr,
+                  r.ptr, feat2.ptr, feat2.ld, self.gamma.data_ptr(), self.dt, N * h32 * w32, 256, self.stream)
         low = self.conv(feat2, self.convb)
         fused = self.conv(cat_b1, self.b1)
         high = self.conv(fused, self.b4, out_dtype=torch.float32)  # class logits stay fp32
 
         # ---- 1/32 -> 1/8 (reference: cabinet.py:228-233)
-        self.bilinear(low, cat_ffm.slice(128, 256))
+        self.bilinear(low, cat_ffm.slice(128, 256), "low_up")
         aux8 = self.new(N, H8, W8, C, torch.float32)
-        self.bilinear(high, aux8)
+        self.bilinear(high, aux8, "high_up")
 
         # ---- feature fusion (reference: cabinet.py:142-153)
         ff = self.conv(cat_ffm, self.ffm_blk)
         gap = gap_all[n_se].view(-1)[: N * 256].view(N, 256)
-        check(self.lib.cabinet_channel_sum(ff.ptr, ff.ld, ff.dt, N, H8 * W8, 256, gap.data_ptr(), self.stream),
-              "channel_sum")
-        self.launches += 1
-        att = self.gate(gap, H8 * W8, self.ffm_gate)
-        self.scale_act(ff, att, ACT_NONE, plus_one=True)
+        self._run("channel_sum", "ffm.gap", 0, 0, self.lib.cabinet_channel_sum, ff.ptr, ff.ld, ff.dt, N, H8 * W8, 256,
+                  gap.data_ptr(), self.stream)
+        att = self.gate(gap, H8 * W8, self.ffm_gate, "ffm.gate")
+        self.scale_act(ff, att, ACT_NONE, "ffm.gate", plus_one=True)
 
         # ---- head (reference: cabinet.py:162-172)
         hc = self.conv(ff, self.head_conv)
@@ -361,25 +387,31 @@ class Engine:
         N, _, H, W = x.shape
         final8, aux8 = self._trunk(x)
         odt = BF16 if out_dtype == torch.bfloat16 else F32
+        tdt = torch.bfloat16 if odt == BF16 else torch.float32
         outs = []
-        for src in (final8, aux8):
-            y = torch.empty((N, self.n_classes, H, W), dtype=torch.bfloat16 if odt == BF16 else torch.float32,
-                            device=self.dev)
-            check(self.lib.cabinet_upsample_logits_nchw(src.ptr, N, src.H, src.W, src.C, y.data_ptr(), odt, H, W,
-                                                        self.stream), "upsample_logits_nchw")
-            self.launches += 1
+        for name, src in (("final_up", final8), ("aux_up", aux8)):
+            y = torch.empty((N, self.n_classes, H, W), dtype=tdt, device=self.dev)
+            nbytes = src.t.numel() * 4 + y.numel() * y.element_size()
+            self._run("upsample_logits_nchw", name, nbytes, 0, self.lib.cabinet_upsample_logits_nchw, src.ptr, N,
+                      src.H, src.W, src.C, y.data_ptr(), odt, H, W, self.stream)
             outs.append(y)
         return outs[0], outs[1]
+
+    def _argmax(self, final8: Map, N, H, W, labels=None, hist=None, ignore_label=255):
+        mask = torch.empty((N, H, W), dtype=torch.uint8, device=self.dev)
+        nbytes = final8.t.numel() * 4 + mask.numel() + (labels.numel() * labels.element_size() if labels is not None else 0)
+        self._run("upsample_argmax", "mask" if hist is None else "mask+hist", nbytes, 0,
+                  self.lib.cabinet_upsample_argmax, final8.ptr, N, final8.H, final8.W, final8.C, mask.data_ptr(), H, W,
+                  labels.data_ptr() if labels is not None else None,
+                  0 if labels is None or labels.dtype == torch.int64 else 1, ignore_label,
+                  hist.data_ptr() if hist is not None else None, self.stream)
+        return mask
 
     @torch.no_grad()
     def forward_mask(self, x):
         N, _, H, W = x.shape
         final8, _ = self._trunk(x)
-        mask = torch.empty((N, H, W), dtype=torch.uint8, device=self.dev)
-        check(self.lib.cabinet_upsample_argmax(final8.ptr, N, final8.H, final8.W, final8.C, mask.data_ptr(), H, W,
-                                               None, 0, 255, None, self.stream), "upsample_argmax")
-        self.launches += 1
-        return mask
+        return self._argmax(final8, N, H, W)
 
     @torch.no_grad()
     def forward_hist(self, x, labels, hist, ignore_label=255):
@@ -393,9 +425,16 @@ class Engine:
         if tuple(labels.shape) != (N, H, W):
             raise ValueError(f"labels shape {tuple(labels.shape)} != {(N, H, W)}")
         final8, _ = self._trunk(x)
-        mask = torch.empty((N, H, W), dtype=torch.uint8, device=self.dev)
-        check(self.lib.cabinet_upsample_argmax(final8.ptr, N, final8.H, final8.W, final8.C, mask.data_ptr(), H, W,
-                                               labels.data_ptr(), 0 if labels.dtype == torch.int64 else 1,
-                                               ignore_label, hist.data_ptr(), self.stream), "upsample_argmax+hist")
-        self.launches += 1
-        return mask
+        return self._argmax(final8, N, H, W, labels, hist, ignore_label)
+
+    # ------------------------------------------------------------------ tracing (bench / profiles)
+    def start_trace(self, kernels=None):
+        """Bracket every launch (or only the named kernels) with CUDA events until ``stop_trace``."""
+        self.trace, self.trace_filter = [], (set(kernels) if kernels else None)
+
+    def stop_trace(self):
+        """-> list of dict(kernel, layer, bytes, flops, ms); synchronises."""
+        torch.cuda.synchronize(self.dev)
+        rows = [dict(kernel=k, layer=l, bytes=b, flops=f, ms=e0.elapsed_time(e1)) for k, l, b, f, e0, e1 in self.trace]
+        self.trace = None
+        return rows
