@@ -1,0 +1,332 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in TMEM), bf16 NHWC.
+//
+//   D[128 pixels x block_n couts] = sum over (tap, 64-channel block)  A_tap[128 x 64] * W_tap[block_n x 64]^T
+//
+// * A tiles are fetched by TMA straight from the NHWC activation: the 128 output pixels of a CTA are a TH x TW
+//   patch of one image, each filter tap is ONE 4-D box load {64 ch, TW, TH, 1} at a shifted coordinate, and the
+//   zero padding of the convolution is TMA's out-of-bounds zero fill (negative / past-the-end coordinates).
+//   Stride-2 convolutions use one tensor map per input parity (py, px): map(py,px)[h][w] = x[2h+py][2w+px], so a
+//   tap is again a plain shifted box.  1x1 convolutions view the tensor as [N*H*W][C] (no tile waste).
+// * W tiles ([Cout_pad][taps*Cin_pad] bf16, K-major, BN folded) come through a 2-D tensor map.
+// * Both land in 128-byte-swizzled shared memory, which is exactly the canonical K-major SWIZZLE_128B UMMA
+//   layout, so descriptors are built from the stage base + 32 B per K=16 step.
+// * Warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+//   warps 2-5 = epilogue (tcgen05.ld -> +bias -> act -> +residual -> bf16/fp32 NHWC stores).
+//   smem ring full/empty mbarriers; tcgen05.commit releases ring slots and publishes the accumulator.
+// * Several CTAs are resident per SM (smem <= ~100 KB, TMEM <= 256 columns each) so one CTA's epilogue overlaps
+//   another's loads/MMAs.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // bf16 elements: 128 bytes = one swizzle row
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int MAX_STAGES = 6;
+constexpr int NUM_THREADS = 192;
+
+struct TcConvParams {
+    int N, OH, OW, Cin, Cout;
+    int KW, stride, pad;
+    int TW, TH, tiles_w, tiles_h;
+    int cin_blocks, num_k_blocks;
+    int block_n, tmem_cols, stages;
+    int act, y_dtype;
+    const float* bias;
+    const bf16* res;
+    long long ldres;
+    void* y;
+    long long ldy;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 3)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+               const __grid_constant__ CUtensorMap tmB, const TcConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_stage_bytes = p.block_n * BLOCK_K * 2;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + p.stages * A_STAGE_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tc::prefetch_tmap(&tmA0);
+        tc::prefetch_tmap(&tmB);
+        for (int s = 0; s < p.stages; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        tc::mbar_init(&tmem_full_bar, 1);
+        tc::mbar_fence_init();
+        tc::fence_proxy_async();
+    }
+    if (warp == 1) tc::tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_base_smem;
+
+    // tile decode: blockIdx.x -> (image, patch row, patch col); blockIdx.y -> cout tile
+    const int tw_i = blockIdx.x % p.tiles_w;
+    const int t = blockIdx.x / p.tiles_w;
+    const int th_i = t % p.tiles_h;
+    const int img = t / p.tiles_h;
+    const int ow0 = tw_i * p.TW, oh0 = th_i * p.TH;
+    const int n0 = blockIdx.y * p.block_n;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            const uint32_t tx_bytes = A_STAGE_BYTES + b_stage_bytes;
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (kb / p.stages) & 1;
+                tc::mbar_wait(&empty_bar[s], ph ^ 1);
+                tc::mbar_expect_tx(&full_bar[s], tx_bytes);
+                const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
+                const int ky = tap / p.KW, kx = tap - ky * p.KW;
+                const int ty = ky - p.pad, tx = kx - p.pad;
+                const CUtensorMap* map = &tmA0;
+                int dy = ty, dx = tx;
+                if (p.stride == 2) {
+                    const int py = ty & 1, px = tx & 1;
+                    dy = (ty - py) >> 1;
+                    dx = (tx - px) >> 1;
+                    const int id = py * 2 + px;
+                    map = id == 0 ? &tmA0 : id == 1 ? &tmA1 : id == 2 ? &tmA2 : &tmA3;
+                }
+                tc::tma_load_4d(sA + s * A_STAGE_BYTES, map, &full_bar[s], cb * BLOCK_K, ow0 + dx, oh0 + dy, img);
+                tc::tma_load_2d(sB + s * b_stage_bytes, &tmB, &full_bar[s], kb * BLOCK_K, n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer =================
+            const uint32_t idesc = tc::make_idesc_bf16(BLOCK_M, p.block_n);
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (kb / p.stages) & 1;
+                tc::mbar_wait(&full_bar[s], ph);
+                tc::tc_fence_after();
+                const int cb = kb % p.cin_blocks;
+                const int ksteps = min(BLOCK_K / 16, (p.Cin - cb * BLOCK_K + 15) / 16);  // skip all-zero K tails
+                const uint32_t a_addr = tc::smem_u32(sA + s * A_STAGE_BYTES);
+                const uint32_t b_addr = tc::smem_u32(sB + s * b_stage_bytes);
+                for (int k = 0; k < ksteps; ++k)
+                    tc::umma_bf16(tmem, tc::make_desc_sw128(a_addr + k * 32), tc::make_desc_sw128(b_addr + k * 32),
+                                  idesc, (kb | k) != 0 ? 1u : 0u);
+                tc::umma_commit(&empty_bar[s]);  // ring slot is free once these MMAs have read it
+            }
+            tc::umma_commit(&tmem_full_bar);     // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue: TMEM -> registers -> global =================
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const int oh = oh0 + row / p.TW, ow = ow0 + row % p.TW;
+        const bool valid = oh < p.OH && ow < p.OW;
+        const long long pix = (static_cast<long long>(img) * p.OH + oh) * p.OW + ow;
+        tc::mbar_wait(&tmem_full_bar, 0);
+        tc::tc_fence_after();
+        const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16);
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+            uint32_t r[16];
+            tc::tmem_ld16(taddr + c0, r);
+            tc::tmem_ld_wait();
+            const int co0 = n0 + c0;
+            if (!valid || co0 >= p.Cout) continue;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float b = (co0 + j < p.Cout) ? __ldg(p.bias + co0 + j) : 0.f;
+                v[j] = cab_act(__uint_as_float(r[j]) + b, p.act);
+            }
+            if (p.res) {
+                const bf16* rp = p.res + pix * p.ldres + co0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (co0 + 8 * h + 8 <= p.Cout) {
+                        Vec16<bf16> rv;
+                        rv.load(rp + 8 * h);
+                        float rf[8];
+                        rv.unpack(rf);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[8 * h + j] += rf[j];
+                    } else {
+                        for (int j = 0; j < 8; ++j)
+                            if (co0 + 8 * h + j < p.Cout) v[8 * h + j] += __bfloat162float(rp[8 * h + j]);
+                    }
+                }
+            }
+            if (p.y_dtype == CABINET_BF16) {
+                bf16* yp = reinterpret_cast<bf16*>(p.y) + pix * p.ldy + co0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (co0 + 8 * h + 8 <= p.Cout) {
+                        Vec16<bf16> ov;
+                        ov.pack(v + 8 * h);
+                        ov.store(yp + 8 * h);
+                    } else {
+                        for (int j = 0; j < 8; ++j)
+                            if (co0 + 8 * h + j < p.Cout) yp[8 * h + j] = __float2bfloat16_rn(v[8 * h + j]);
+                    }
+                }
+            } else {
+                float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + co0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (co0 + j < p.Cout) yp[j] = v[j];
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem, p.tmem_cols);
+    }
+}
+
+int g_smem_attr_set = 0;
+
+}  // namespace
+
+cab_encode_tiled_fn cab_get_encode_tiled() {
+    static cab_encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<cab_encode_tiled_fn>(sym);
+    }
+    return fn;
+}
+
+int cab_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, CUtensorMapL2promotion promo) {
+    cab_encode_tiled_fn enc = cab_get_encode_tiled();
+    if (!enc) {
+        cabinet_set_error("cuTensorMapEncodeTiled is unavailable (driver too old or no driver)");
+        return CABINET_ERR_CUDA;
+    }
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+    }
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        cabinet_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)",
+                          static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                          (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                          rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+        return CABINET_ERR_CUDA;
+    }
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_packed,
+                               int Cout, int KH, int KW, int stride, int pad, const float* bias, const void* res,
+                               long long ldres, void* y, int y_dtype, long long ldy, int OH, int OW, int act,
+                               cabinet_stream_t stream) {
+    CAB_REQUIRE(x && w_packed && bias && y, "conv_tc: null pointer");
+    CAB_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && OH > 0 && OW > 0,
+                "conv_tc: bad sizes");
+    CAB_REQUIRE(stride == 1 || stride == 2, "conv_tc: stride must be 1 or 2");
+    CAB_REQUIRE(stride == 1 || (H >= 2 && W >= 2), "conv_tc: stride-2 needs H, W >= 2");
+    CAB_REQUIRE(ldx % 8 == 0 && ldx >= Cin && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                "conv_tc: input needs 16-byte aligned pixels (ldx %% 8 == 0)");
+    CAB_REQUIRE(ldy >= Cout && (y_dtype == CABINET_F32 || (ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0)),
+                "conv_tc: bf16 output needs 16-byte aligned pixels");
+    CAB_REQUIRE(!res || (ldres % 8 == 0 && (reinterpret_cast<uintptr_t>(res) & 15) == 0), "conv_tc: residual alignment");
+    CAB_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0, "conv_tc: weight alignment");
+    if (N == 0) return CABINET_OK;
+
+    TcConvParams p;
+    const bool flat = KH == 1 && KW == 1 && stride == 1 && pad == 0;
+    const int taps = KH * KW;
+    p.Cin = Cin; p.Cout = Cout; p.KW = KW; p.stride = stride; p.pad = pad;
+    p.cin_blocks = (Cin + BLOCK_K - 1) / BLOCK_K;
+    p.num_k_blocks = taps * p.cin_blocks;
+    const int n16 = ((Cout + 15) / 16) * 16;
+    const int n_tiles = (n16 + 255) / 256;
+    p.block_n = (((n16 + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < p.block_n) p.tmem_cols *= 2;
+    const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
+    p.stages = std::max(2, std::min({p.num_k_blocks, MAX_STAGES, (100 * 1024) / stage_bytes}));
+    p.act = act; p.y_dtype = y_dtype; p.bias = bias; p.res = reinterpret_cast<const bf16*>(res); p.ldres = ldres;
+    p.y = y; p.ldy = ldy;
+
+    CUtensorMap tmA[4], tmB;
+    const uint64_t es = 2;
+    if (flat) {
+        const long long P = static_cast<long long>(N) * H * W;
+        p.N = 1; p.OH = 1; p.OW = static_cast<int>(P);
+        CAB_REQUIRE(P < (1LL << 31), "conv_tc: too many pixels");
+        p.TW = BLOCK_M; p.TH = 1; p.tiles_w = static_cast<int>(cab_ceil_div(P, BLOCK_M)); p.tiles_h = 1;
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)P, 1, 1};
+        const uint64_t strides[3] = {(uint64_t)ldx * es, (uint64_t)ldx * es * P, (uint64_t)ldx * es * P};
+        const uint32_t box[4] = {BLOCK_K, BLOCK_M, 1, 1};
+        int rc = cab_make_tmap_bf16(&tmA[0], x, 4, dims, strides, box);
+        if (rc) return rc;
+        tmA[1] = tmA[2] = tmA[3] = tmA[0];
+    } else {
+        p.N = N; p.OH = OH; p.OW = OW;
+        // pick the TH x TW = 128 patch shape that wastes the fewest pixels (ties: wider)
+        long long best = -1;
+        for (int tw = 128; tw >= 4; tw >>= 1) {
+            const int th = BLOCK_M / tw;
+            const long long cover = cab_ceil_div(OW, tw) * tw * cab_ceil_div(OH, th) * th;
+            if (best < 0 || cover < best) { best = cover; p.TW = tw; p.TH = th; }
+        }
+        p.tiles_w = static_cast<int>(cab_ceil_div(OW, p.TW));
+        p.tiles_h = static_cast<int>(cab_ceil_div(OH, p.TH));
+        const uint32_t box[4] = {BLOCK_K, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+        const bf16* xb = reinterpret_cast<const bf16*>(x);
+        for (int py = 0; py < stride; ++py)
+            for (int px = 0; px < stride; ++px) {
+                const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)((W - px + stride - 1) / stride),
+                                          (uint64_t)((H - py + stride - 1) / stride), (uint64_t)N};
+                const uint64_t strides[3] = {(uint64_t)ldx * es * stride, (uint64_t)ldx * es * W * stride,
+                                             (uint64_t)ldx * es * W * H};
+                int rc = cab_make_tmap_bf16(&tmA[py * stride + px], xb + (static_cast<long long>(py) * W + px) * ldx, 4,
+                                            dims, strides, box);
+                if (rc) return rc;
+            }
+        if (stride == 1) tmA[1] = tmA[2] = tmA[3] = tmA[0];
+    }
+    {
+        const uint64_t ktot = static_cast<uint64_t>(taps) * p.cin_blocks * BLOCK_K;
+        const uint64_t dims[2] = {ktot, (uint64_t)n16};
+        const uint64_t strides[1] = {ktot * es};
+        const uint32_t box[2] = {BLOCK_K, (uint32_t)p.block_n};
+        int rc = cab_make_tmap_bf16(&tmB, w_packed, 2, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (rc) return rc;
+    }
+    const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024;
+    if (!g_smem_attr_set) {
+        CAB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        g_smem_attr_set = 1;
+    }
+    const long long m_tiles = static_cast<long long>(p.N) * p.tiles_h * p.tiles_w;
+    CAB_REQUIRE(m_tiles < (1LL << 31), "conv_tc: too many tiles");
+    dim3 grid(static_cast<unsigned>(m_tiles), n_tiles);
+    conv_tc_kernel<<<grid, NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, p);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}

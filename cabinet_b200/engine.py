@@ -77,7 +77,12 @@ class ConvLayer:
         self.act = act
         self.w = w.permute(0, 2, 3, 1).reshape(self.cout, -1).contiguous().to(wdtype)
         self.b = b.contiguous()
-        self.tc = None  # tcgen05 packing, attached by the engine when the layer is eligible
+        self.tc = None  # tcgen05 packing: bf16 [ceil16(Cout)][taps][ceil64(Cin)], zero padded
+        if wdtype == torch.bfloat16 and self.stride in (1, 2):
+            n16, c64, taps = -(-self.cout // 16) * 16, -(-self.cin // 64) * 64, self.kh * self.kw
+            pk = torch.zeros((n16, taps, c64), dtype=torch.float32, device=w.device)
+            pk[: self.cout, :, : self.cin] = w.permute(0, 2, 3, 1).reshape(self.cout, taps, self.cin)
+            self.tc = pk.to(torch.bfloat16).contiguous()
 
 
 class DwLayer:
@@ -227,7 +232,9 @@ class Engine:
         nbytes = (N * H * W * cin * xes + M * L.cout * out.t.element_size() + L.w.numel() * L.w.element_size()
                   + (M * L.cout * res.t.element_size() if res is not None else 0))
         flops = 2 * M * L.cout * L.cin * L.kh * L.kw
-        if self.use_tc and L.tc is not None and nchw_input is None and x.dt == BF16:
+        if (self.use_tc and L.tc is not None and nchw_input is None and x.dt == BF16 and x.ld % 8 == 0
+                and x.off % 8 == 0 and (L.stride == 1 or (H >= 2 and W >= 2))
+                and (out.dt == F32 or (out.ld % 8 == 0 and out.off % 8 == 0))):
             self._conv_tc(x, L, out, res, OH, OW, nbytes, flops)
             return out
         wdt = BF16 if L.w.dtype == torch.bfloat16 else F32
@@ -237,6 +244,12 @@ class Engine:
                   out.ptr, out.dt, out.ld, 0, 1, N, H, W, cin, L.cout, L.kh, L.kw, L.stride, L.pad, OH, OW, L.act,
                   1.0, self.stream)
         return out
+
+    def _conv_tc(self, x: Map, L: ConvLayer, out: Map, res: Optional[Map], OH, OW, nbytes, flops):
+        self._run("conv_tc", L.name, nbytes, flops, self.lib.cabinet_conv_tc, x.ptr, x.ld, x.N, x.H, x.W, x.C,
+                  L.tc.data_ptr(), L.cout, L.kh, L.kw, L.stride, L.pad, L.b.data_ptr(),
+                  res.ptr if res is not None else None, res.ld if res is not None else 0, out.ptr, out.dt, out.ld,
+                  OH, OW, L.act, self.stream)
 
     def dwconv(self, x: Map, L: DwLayer, gap: Optional[torch.Tensor] = None) -> Map:
         p = (L.k - 1) // 2

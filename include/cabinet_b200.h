@@ -63,6 +63,18 @@ int cabinet_conv2d_simt(const void* x, int x_dtype, long long sxn, long long sxh
                         int OH, int OW, int act, float alpha, cabinet_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * The same convolution on the tensor cores: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), operands staged by TMA
+ * (im2col-free implicit GEMM: one shifted 4-D box per filter tap, zero padding = TMA out-of-bounds fill).
+ * bf16 NHWC input (16-byte aligned pixels), stride 1 or 2, any kernel size / padding.
+ * w_packed: bf16 [ceil16(Cout)][KH*KW][ceil64(Cin)] (zero padded, BN folded).  y: bf16 or fp32 NHWC.
+ * Replaces the same reference call sites as cabinet_conv2d_simt in the bf16 mode; the dense k x k layers
+ * (src/models/cabinet.py:59-63,68,111-114,159) are the tensor-bound ones.
+ *   out[m][co] = act( sum_k x_patch[m][k] * w[co][k] + bias[co] ) + res[m][co] */
+int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_packed, int Cout,
+                    int KH, int KW, int stride, int pad, const float* bias, const void* res, long long ldres,
+                    void* y, int y_dtype, long long ldy, int OH, int OW, int act, cabinet_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Depthwise k x k (k in {3,5}, stride in {1,2}, pad (k-1)/2) + folded-BN bias + activation,
  * optional per-(image, channel) sum of the written values for the SE / GAP consumers.
  * Replaces the groups=C nn.Conv2d + BatchNorm2d (+act) at src/models/mobilenetv3.py:112-123,130-141

@@ -245,3 +245,58 @@ def test_empty_batch_is_a_noop():
     lib = _lib.load()
     check(lib.cabinet_softmax_rows(1, 1, F32, 0, 5, stream()), "softmax")
     check(lib.cabinet_confusion_hist(1, 0, 1, 0, 0, 4, 255, 1, stream()), "hist")
+
+
+TC_CASES = [
+    # cin, cout, k, s, p, H, W, act, res, out_fp32
+    (16, 64, 1, 1, 0, 17, 23, ACT_RELU, False, False),      # K = 16: single 16-wide MMA step, OOB-filled K tail
+    (24, 72, 1, 1, 0, 9, 31, ACT_HSWISH, False, False),     # K, N not multiples of 16/64
+    (72, 24, 1, 1, 0, 16, 16, ACT_NONE, True, False),       # linear bottleneck + residual
+    (200, 80, 1, 1, 0, 5, 7, ACT_NONE, True, False),        # 4 K blocks with a ragged tail
+    (160, 960, 1, 1, 0, 8, 8, ACT_HSWISH, False, False),    # N = 960 -> 4 cout tiles of 240
+    (256, 19, 1, 1, 0, 6, 10, ACT_NONE, False, True),       # class head: N = 19, fp32 output
+    (256, 8, 1, 1, 0, 16, 16, ACT_NONE, False, True),
+    (64, 64, 3, 1, 1, 20, 36, ACT_RELU, False, False),      # 3x3 stride 1: 9 shifted box loads, OOB = zero padding
+    (64, 64, 3, 2, 1, 33, 18, ACT_RELU, False, False),      # 3x3 stride 2, odd height: parity tensor maps
+    (64, 64, 3, 2, 1, 64, 64, ACT_RELU, False, False),
+    (128, 256, 3, 1, 1, 3, 4, ACT_RELU, False, False),      # map smaller than one tile
+    (320, 256, 3, 1, 1, 32, 32, ACT_RELU, False, False),    # long K loop (45 k-blocks): ring wrap-around
+    (640, 128, 1, 1, 0, 32, 32, ACT_NONE, False, False),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,s,p,H,W,act,res,out_fp32", TC_CASES)
+def test_conv_tc(cin, cout, k, s, p, H, W, act, res, out_fp32):
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    N = 3
+    x = q(gen(N, cin, H, W, seed=1), dtype)
+    w = q(gen(cout, cin, k, k, seed=2, scale=(cin * k * k) ** -0.5), dtype)
+    b = gen(cout, seed=3, scale=0.1)
+    OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    r = q(gen(N, cout, OH, OW, seed=4), dtype) if res else None
+    ref = act_ref(F.conv2d(x, w, b, s, p), act)
+    if res:
+        ref = ref + r
+    xm = to_map(x, dtype, ld=cin + 16, off=8)   # channel slice of a wider (concat) buffer
+    odt = torch.float32 if out_fp32 else dtype
+    ym = to_map(torch.zeros(N, cout, OH, OW), odt, ld=cout + 16, off=16 if not out_fp32 else 3)
+    ym.t.fill_(7.0)
+    rm = to_map(r, dtype) if res else None
+    n16, c64 = -(-cout // 16) * 16, -(-cin // 64) * 64
+    pk = torch.zeros(n16, k * k, c64)
+    pk[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin)
+    pk = pk.to("cuda", dtype).contiguous()
+    bd = b.cuda()
+    check(lib.cabinet_conv_tc(xm.ptr, xm.ld, N, H, W, cin, pk.data_ptr(), cout, k, k, s, p, bd.data_ptr(),
+                              rm.ptr if res else None, rm.ld if res else 0, ym.ptr, ym.dt, ym.ld, OH, OW, act,
+                              stream()), "conv_tc")
+    torch.cuda.synchronize()
+    got = from_map(ym)
+    err = rel_l2(got, ref)
+    print(f"conv_tc cin={cin} cout={cout} k={k} s={s} {H}x{W}: rel_l2 {err:.3e}")
+    assert err < (2e-5 if out_fp32 else 6e-3) * (3 if out_fp32 else 1) or err < 6e-3 and not out_fp32
+    # neighbouring channels of the wider output buffer are untouched
+    full = ym.t.float()
+    assert float((full[..., : ym.off] - 7.0).abs().max()) == 0
+    assert float((full[..., ym.off + cout:] - 7.0).abs().max()) == 0
