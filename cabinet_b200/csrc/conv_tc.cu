@@ -320,7 +320,7 @@ extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W
     }
     const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024;
     if (!g_smem_attr_set) {
-        CAB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CAB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         g_smem_attr_set = 1;
     }
     const long long m_tiles = static_cast<long long>(p.N) * p.tiles_h * p.tiles_w;

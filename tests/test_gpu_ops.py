@@ -280,7 +280,7 @@ def test_conv_tc(cin, cout, k, s, p, H, W, act, res, out_fp32):
         ref = ref + r
     xm = to_map(x, dtype, ld=cin + 16, off=8)   # channel slice of a wider (concat) buffer
     odt = torch.float32 if out_fp32 else dtype
-    ym = to_map(torch.zeros(N, cout, OH, OW), odt, ld=cout + 16, off=16 if not out_fp32 else 3)
+    ym = to_map(torch.zeros(N, cout, OH, OW), odt, ld=cout + 24, off=16 if not out_fp32 else 3)
     ym.t.fill_(7.0)
     rm = to_map(r, dtype) if res else None
     n16, c64 = -(-cout // 16) * 16, -(-cin // 64) * 64
@@ -295,7 +295,7 @@ def test_conv_tc(cin, cout, k, s, p, H, W, act, res, out_fp32):
     got = from_map(ym)
     err = rel_l2(got, ref)
     print(f"conv_tc cin={cin} cout={cout} k={k} s={s} {H}x{W}: rel_l2 {err:.3e}")
-    assert err < (2e-5 if out_fp32 else 6e-3) * (3 if out_fp32 else 1) or err < 6e-3 and not out_fp32
+    assert err < (2e-5 if out_fp32 else 6e-3)  # fp32 out: accumulation order only; bf16 out: one rounding
     # neighbouring channels of the wider output buffer are untouched
     full = ym.t.float()
     assert float((full[..., : ym.off] - 7.0).abs().max()) == 0
