@@ -3,7 +3,8 @@
 
 namespace {
 
-// One block per image.  mean -> fc1(+ReLU) -> fc2 -> gate.  fp32 throughout.
+// grid (N, splits): every block recomputes the (cheap) hidden layer of its image, then produces a 1/splits slice
+// of the C gates.  Warp-per-output dot products so the weight rows are read coalesced.  fp32 throughout.
 __global__ void __launch_bounds__(256)
 gate_mlp_kernel(const float* __restrict__ gap_sum, float inv_hw, const float* __restrict__ w1,
                 const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
@@ -17,16 +18,20 @@ gate_mlp_kernel(const float* __restrict__ gap_sum, float inv_hw, const float* __
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarps = blockDim.x / 32;
     for (int j = warp; j < Cmid; j += nwarps) {
         float acc = 0.f;
-        for (int c = lane; c < C; c += 32) acc = fmaf(w1[static_cast<long long>(j) * C + c], mean[c], acc);
+        for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(w1 + static_cast<long long>(j) * C + c), mean[c], acc);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) hidden[j] = fmaxf(acc + (b1 ? b1[j] : 0.f), 0.f);
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float acc = b2 ? b2[c] : 0.f;
-        for (int j = 0; j < Cmid; ++j) acc = fmaf(w2[static_cast<long long>(c) * Cmid + j], hidden[j], acc);
-        scale[static_cast<long long>(n) * C + c] = cab_act(acc, gate);
+    const int per = (C + gridDim.y - 1) / gridDim.y;
+    const int c_begin = blockIdx.y * per, c_end = min(C, c_begin + per);
+    for (int c = c_begin + warp; c < c_end; c += nwarps) {
+        float acc = 0.f;
+        for (int j = lane; j < Cmid; j += 32) acc = fmaf(__ldg(w2 + static_cast<long long>(c) * Cmid + j), hidden[j], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) scale[static_cast<long long>(n) * C + c] = cab_act(acc + (b2 ? b2[c] : 0.f), gate);
     }
 }
 
@@ -165,7 +170,8 @@ extern "C" int cabinet_gate_mlp(const float* gap_sum, float inv_hw, const float*
     CAB_REQUIRE(C > 0 && Cmid > 0 && (C + Cmid) * sizeof(float) <= 48 * 1024, "gate_mlp: C=%d Cmid=%d unsupported", C,
                 Cmid);
     if (N == 0) return CABINET_OK;
-    gate_mlp_kernel<<<N, 256, (C + Cmid) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+    const int splits = std::max(1, std::min(16, C / 32));
+    gate_mlp_kernel<<<dim3(N, splits), 256, (C + Cmid) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
         gap_sum, inv_hw, w1, b1, w2, b2, scale, C, Cmid, gate);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;

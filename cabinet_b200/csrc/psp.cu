@@ -9,10 +9,11 @@ __device__ __constant__ int kPspSize[4] = {1, 3, 6, 8};
 __device__ __constant__ int kPspOffset[4] = {0, 1, 10, 46};  // bin offsets inside the 110-entry table
 constexpr int kPspBins = 110;
 
-// grid (110, N), block = C threads (C <= 1024): one bin per block, channel per thread.
+// grid (110, N): one bin per block; threads = (C/4 channel quads) x (pixel lanes), smem tree over the pixel lanes.
 template <typename T>
-__global__ void psp_pool_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ pooled, int H, int W,
-                                int C) {
+__global__ void __launch_bounds__(256)
+psp_pool_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ pooled, int H, int W, int C) {
+    __shared__ float4 red[256];
     const int bin = blockIdx.x, n = blockIdx.y;
     int si = 3;
     if (bin < 1) si = 0; else if (bin < 10) si = 1; else if (bin < 46) si = 2;
@@ -22,12 +23,29 @@ __global__ void psp_pool_kernel(const T* __restrict__ x, long long ldx, float* _
     // ATen adaptive_avg_pool2d bins: [floor(i*H/s), ceil((i+1)*H/s))
     const int h0 = (by * H) / s, h1 = ((by + 1) * H + s - 1) / s;
     const int w0 = (bx * W) / s, w1 = ((bx + 1) * W + s - 1) / s;
-    const T* base = x + static_cast<long long>(n) * H * W * ldx;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float acc = 0.f;
-        for (int h = h0; h < h1; ++h)
-            for (int w = w0; w < w1; ++w) acc += to_f32<T>(base[(static_cast<long long>(h) * W + w) * ldx + c]);
-        pooled[(static_cast<long long>(n) * kPspBins + bin) * C + c] = acc / static_cast<float>((h1 - h0) * (w1 - w0));
+    const int bw = w1 - w0, npix = (h1 - h0) * bw;
+    const int CQ = C / 4;                    // channel quads (C % 4 == 0, CQ <= 256 checked by the host)
+    const int lanes = blockDim.x / CQ;       // pixel lanes
+    const int cq = threadIdx.x % CQ, pl = threadIdx.x / CQ;
+    const T* base = x + static_cast<long long>(n) * H * W * ldx + cq * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pl < lanes) {
+        for (int i = pl; i < npix; i += lanes) {
+            const int h = h0 + i / bw, w = w0 + i % bw;
+            const T* p = base + (static_cast<long long>(h) * W + w) * ldx;
+            acc.x += to_f32<T>(p[0]); acc.y += to_f32<T>(p[1]); acc.z += to_f32<T>(p[2]); acc.w += to_f32<T>(p[3]);
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (pl == 0) {
+        for (int l = 1; l < lanes; ++l) {
+            const float4 o = red[l * CQ + cq];
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        const float inv = 1.f / static_cast<float>(npix);
+        float* out = pooled + (static_cast<long long>(n) * kPspBins + bin) * C + cq * 4;
+        *reinterpret_cast<float4*>(out) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
     }
 }
 
@@ -66,10 +84,11 @@ psp_concat_kernel(const T* __restrict__ x, long long ldx, const float* __restric
 
 extern "C" int cabinet_psp_pool(const void* x, long long ldx, int dtype, float* pooled, int N, int H, int W, int C,
                                 cabinet_stream_t stream) {
-    CAB_REQUIRE(x && pooled && H > 0 && W > 0 && C > 0 && ldx >= C, "psp_pool: bad arguments");
+    CAB_REQUIRE(x && pooled && H > 0 && W > 0 && C > 0 && ldx >= C && C % 4 == 0 && C <= 1024,
+                "psp_pool: bad arguments (C must be a multiple of 4, <= 1024)");
     if (N == 0) return CABINET_OK;
     dim3 grid(kPspBins, N);
-    const int threads = std::min(1024, ((C + 31) / 32) * 32);
+    const int threads = 256;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == CABINET_BF16)
         psp_pool_kernel<bf16><<<grid, threads, 0, s>>>(reinterpret_cast<const bf16*>(x), ldx, pooled, H, W, C);

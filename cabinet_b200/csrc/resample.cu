@@ -43,59 +43,91 @@ bilinear_nhwc_kernel(const TI* __restrict__ x, long long ldx, TO* __restrict__ y
 }
 
 // ---------------------------------------------------------------------------------- logits tail
-// Each thread produces PX consecutive output pixels of one row for ALL classes.
-// Source rows are addressed through the two y taps; x taps are recomputed per pixel (cheap).
+// Each thread produces 8 consecutive output pixels [8g, 8g+8) of one output row for ALL classes and hands them,
+// class by class, to a consumer (NCHW store / running argmax).
+//  * exact x8 path (OH = 8*IH, OW = 8*IW, the CABiNet case whenever H, W are multiples of 64): the 8 pixels
+//    touch only source columns g-1, g, g+1 with compile-time weights, the row touches source rows (k-1,k) or
+//    (k,k+1): 6 fp32 vectors per class chunk -> 8 outputs, ~2.5 ALU ops per output.
+//  * generic path (any sizes): per-pixel taps, 4 loads per output.
+// Both evaluate the same expression tree per output, so the NCHW kernel and the argmax kernel agree bit for bit:
+//   v = top + wy * (bot - top),  top/bot = a + wx * (b - a).
+constexpr int PXG = 8;
 
-
-template <typename TO, int PX>
-__global__ void __launch_bounds__(256)
-upsample_logits_nchw_kernel(const float* __restrict__ x, int IH, int IW, int C, TO* __restrict__ y, int OH, int OW,
-                            float sh, float sw) {
-    const int groups_w = (OW + PX - 1) / PX;
-    const int gw = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gw >= groups_w) return;
-    const int oh = blockIdx.y, n = blockIdx.z;
+template <bool EXACT8, typename Consumer>
+__device__ __forceinline__ void upsample_group8(const float* __restrict__ x, int n, int oh, int g, int IH, int IW,
+                                                int C, int OW, float sh, float sw, Consumer&& consume) {
     int y0, y1;
     float wy;
     cab_bilinear_tap(oh, sh, IH, y0, y1, wy);
     const float* r0 = x + (static_cast<long long>(n) * IH + y0) * IW * C;
     const float* r1 = x + (static_cast<long long>(n) * IH + y1) * IW * C;
-    const int ow0 = gw * PX;
-    int x0[PX], x1[PX];
-    float wx[PX];
+    if constexpr (EXACT8) {
+        const int xa = max(g - 1, 0), xb = g, xc = min(g + 1, IW - 1);
+        for (int c = 0; c < C; ++c) {
+            const float ta = __ldg(r0 + xa * C + c), tb = __ldg(r0 + xb * C + c), tcc = __ldg(r0 + xc * C + c);
+            const float ba = __ldg(r1 + xa * C + c), bb = __ldg(r1 + xb * C + c), bc = __ldg(r1 + xc * C + c);
+            const float va = ta + wy * (ba - ta), vb = tb + wy * (bb - tb), vc = tcc + wy * (bc - tcc);
+            const float d0 = vb - va, d1 = vc - vb;
+            float v[PXG];
 #pragma unroll
-    for (int p = 0; p < PX; ++p) cab_bilinear_tap(min(ow0 + p, OW - 1), sw, IW, x0[p], x1[p], wx[p]);
-    const bool full = (ow0 + PX <= OW) && (OW % PX == 0);
-    for (int c = 0; c < C; ++c) {
-        float v[PX];
-#pragma unroll
-        for (int p = 0; p < PX; ++p) {
-            const float a = (1.f - wx[p]) * __ldg(r0 + x0[p] * C + c) + wx[p] * __ldg(r0 + x1[p] * C + c);
-            const float b = (1.f - wx[p]) * __ldg(r1 + x0[p] * C + c) + wx[p] * __ldg(r1 + x1[p] * C + c);
-            v[p] = (1.f - wy) * a + wy * b;
+            for (int j = 0; j < 4; ++j) {
+                // at the left edge (g == 0) ATen clamps src to 0 -> weight 0 on column 0; va == vb there, so the
+                // unclamped static weight gives the same value
+                v[j] = va + ((j + 4.5f) * 0.125f) * d0;
+                v[j + 4] = vb + ((j + 0.5f) * 0.125f) * d1;
+            }
+            consume(c, v);
         }
+    } else {
+        int x0[PXG], x1[PXG];
+        float wx[PXG];
+#pragma unroll
+        for (int p = 0; p < PXG; ++p) cab_bilinear_tap(min(g * PXG + p, OW - 1), sw, IW, x0[p], x1[p], wx[p]);
+        for (int c = 0; c < C; ++c) {
+            float v[PXG];
+#pragma unroll
+            for (int p = 0; p < PXG; ++p) {
+                const float t0 = __ldg(r0 + x0[p] * C + c), t1 = __ldg(r0 + x1[p] * C + c);
+                const float b0 = __ldg(r1 + x0[p] * C + c), b1 = __ldg(r1 + x1[p] * C + c);
+                const float top = t0 + wx[p] * (t1 - t0), bot = b0 + wx[p] * (b1 - b0);
+                v[p] = top + wy * (bot - top);
+            }
+            consume(c, v);
+        }
+    }
+}
+
+template <typename TO, bool EXACT8>
+__global__ void __launch_bounds__(128)
+upsample_logits_nchw_kernel(const float* __restrict__ x, int IH, int IW, int C, TO* __restrict__ y, int OH, int OW,
+                            float sh, float sw) {
+    const int groups_w = (OW + PXG - 1) / PXG;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups_w) return;
+    const int oh = blockIdx.y, n = blockIdx.z;
+    const int ow0 = g * PXG;
+    const bool full = (OW % PXG) == 0;  // rows are 16-byte aligned and the group is complete
+    upsample_group8<EXACT8>(x, n, oh, g, IH, IW, C, OW, sh, sw, [&](int c, const float* v) {
         TO* o = y + ((static_cast<long long>(n) * C + c) * OH + oh) * OW + ow0;
         if (full) {
             if constexpr (sizeof(TO) == 4) {
-#pragma unroll
-                for (int p = 0; p < PX; p += 4)
-                    __stcs(reinterpret_cast<float4*>(o + p), make_float4(v[p], v[p + 1], v[p + 2], v[p + 3]));
+                __stcs(reinterpret_cast<float4*>(o), make_float4(v[0], v[1], v[2], v[3]));
+                __stcs(reinterpret_cast<float4*>(o) + 1, make_float4(v[4], v[5], v[6], v[7]));
             } else {
-                static_assert(PX == 8, "bf16 path stores 8 pixels = 16 bytes");
                 Vec16<bf16> ov;
                 ov.pack(v);
                 __stcs(reinterpret_cast<uint4*>(o), ov.raw);
             }
         } else {
 #pragma unroll
-            for (int p = 0; p < PX; ++p)
+            for (int p = 0; p < PXG; ++p)
                 if (ow0 + p < OW) o[p] = from_f32<TO>(v[p]);
         }
-    }
+    });
 }
 
-template <int PX>
-__global__ void __launch_bounds__(256)
+template <bool EXACT8>
+__global__ void __launch_bounds__(128)
 upsample_argmax_kernel(const float* __restrict__ x, int IH, int IW, int C, uint8_t* __restrict__ mask, int OH, int OW,
                        float sh, float sw, const void* __restrict__ labels, int label_dtype, int ignore_label,
                        unsigned long long* __restrict__ hist) {
@@ -104,53 +136,41 @@ upsample_argmax_kernel(const float* __restrict__ x, int IH, int IW, int C, uint8
         for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_hist[i] = 0u;
         __syncthreads();
     }
-    const int groups_w = (OW + PX - 1) / PX;
-    const int gw = blockIdx.x * blockDim.x + threadIdx.x;
+    const int groups_w = (OW + PXG - 1) / PXG;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int oh = blockIdx.y, n = blockIdx.z;
-    if (gw < groups_w) {
-        int y0, y1;
-        float wy;
-        cab_bilinear_tap(oh, sh, IH, y0, y1, wy);
-        const float* r0 = x + (static_cast<long long>(n) * IH + y0) * IW * C;
-        const float* r1 = x + (static_cast<long long>(n) * IH + y1) * IW * C;
-        const int ow0 = gw * PX;
-        float best[PX];
-        int arg[PX];
-        int x0[PX], x1[PX];
-        float wx[PX];
+    if (g < groups_w) {
+        const int ow0 = g * PXG;
+        float best[PXG];
+        int arg[PXG];
 #pragma unroll
-        for (int p = 0; p < PX; ++p) {
-            cab_bilinear_tap(min(ow0 + p, OW - 1), sw, IW, x0[p], x1[p], wx[p]);
+        for (int p = 0; p < PXG; ++p) {
             best[p] = -INFINITY;
             arg[p] = 0;
         }
-        for (int c = 0; c < C; ++c) {
+        upsample_group8<EXACT8>(x, n, oh, g, IH, IW, C, OW, sh, sw, [&](int c, const float* v) {
 #pragma unroll
-            for (int p = 0; p < PX; ++p) {
-                const float a = (1.f - wx[p]) * __ldg(r0 + x0[p] * C + c) + wx[p] * __ldg(r0 + x1[p] * C + c);
-                const float b = (1.f - wx[p]) * __ldg(r1 + x0[p] * C + c) + wx[p] * __ldg(r1 + x1[p] * C + c);
-                const float v = (1.f - wy) * a + wy * b;
-                if (v > best[p]) {  // strict: first maximum wins (torch.argmax)
-                    best[p] = v;
+            for (int p = 0; p < PXG; ++p)
+                if (v[p] > best[p]) {  // strict: first maximum wins (torch.argmax)
+                    best[p] = v[p];
                     arg[p] = c;
                 }
-            }
-        }
+        });
         const long long obase = (static_cast<long long>(n) * OH + oh) * OW + ow0;
         if (mask) {
-            if (ow0 + PX <= OW && (OW % PX) == 0 && PX == 8) {
+            if ((OW % PXG) == 0) {
                 uint32_t lo = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
                 uint32_t hi = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
                 *reinterpret_cast<uint2*>(mask + obase) = make_uint2(lo, hi);
             } else {
 #pragma unroll
-                for (int p = 0; p < PX; ++p)
+                for (int p = 0; p < PXG; ++p)
                     if (ow0 + p < OW) mask[obase + p] = static_cast<uint8_t>(arg[p]);
             }
         }
         if (hist) {
 #pragma unroll
-            for (int p = 0; p < PX; ++p) {
+            for (int p = 0; p < PXG; ++p) {
                 if (ow0 + p >= OW) continue;
                 long long lb = label_dtype == 0 ? reinterpret_cast<const long long*>(labels)[obase + p]
                                                 : static_cast<long long>(reinterpret_cast<const uint8_t*>(labels)[obase + p]);
@@ -218,19 +238,17 @@ extern "C" int cabinet_upsample_logits_nchw(const float* x, int N, int IH, int I
     if (N == 0) return CABINET_OK;
     const float sh = static_cast<float>(IH) / static_cast<float>(OH), sw = static_cast<float>(IW) / static_cast<float>(OW);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool exact8 = OH == 8 * IH && OW == 8 * IW;
+    const int groups = (OW + PXG - 1) / PXG;
+    dim3 grid((groups + 127) / 128, OH, N);
+#define CAB_UP(TO, E8) \
+    upsample_logits_nchw_kernel<TO, E8><<<grid, 128, 0, s>>>(x, IH, IW, C, reinterpret_cast<TO*>(y), OH, OW, sh, sw)
     if (y_dtype == CABINET_F32) {
-        constexpr int PX = 4;
-        const int groups = (OW + PX - 1) / PX;
-        dim3 grid((groups + 127) / 128, OH, N);
-        upsample_logits_nchw_kernel<float, PX><<<grid, 128, 0, s>>>(x, IH, IW, C, reinterpret_cast<float*>(y), OH, OW,
-                                                                    sh, sw);
+        if (exact8) CAB_UP(float, true); else CAB_UP(float, false);
     } else {
-        constexpr int PX = 8;
-        const int groups = (OW + PX - 1) / PX;
-        dim3 grid((groups + 127) / 128, OH, N);
-        upsample_logits_nchw_kernel<bf16, PX><<<grid, 128, 0, s>>>(x, IH, IW, C, reinterpret_cast<bf16*>(y), OH, OW, sh,
-                                                                   sw);
+        if (exact8) CAB_UP(bf16, true); else CAB_UP(bf16, false);
     }
+#undef CAB_UP
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }
@@ -245,13 +263,18 @@ extern "C" int cabinet_upsample_argmax(const float* x, int N, int IH, int IW, in
     CAB_REQUIRE(OH <= 65535 && N <= 65535, "upsample_argmax: OH/N exceed grid limits");
     if (N == 0) return CABINET_OK;
     const float sh = static_cast<float>(IH) / static_cast<float>(OH), sw = static_cast<float>(IW) / static_cast<float>(OW);
-    constexpr int PX = 8;
-    const int groups = (OW + PX - 1) / PX;
+    const bool exact8 = OH == 8 * IH && OW == 8 * IW;
+    const int groups = (OW + PXG - 1) / PXG;
     dim3 grid((groups + 127) / 128, OH, N);
     const size_t smem = hist ? sizeof(unsigned) * C * C : 0;
-    upsample_argmax_kernel<PX><<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
-        x, IH, IW, C, mask, OH, OW, sh, sw, labels, label_dtype, ignore_label,
-        reinterpret_cast<unsigned long long*>(hist));
+    auto* h = reinterpret_cast<unsigned long long*>(hist);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (exact8)
+        upsample_argmax_kernel<true><<<grid, 128, smem, s>>>(x, IH, IW, C, mask, OH, OW, sh, sw, labels, label_dtype,
+                                                            ignore_label, h);
+    else
+        upsample_argmax_kernel<false><<<grid, 128, smem, s>>>(x, IH, IW, C, mask, OH, OW, sh, sw, labels, label_dtype,
+                                                             ignore_label, h);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

@@ -1,0 +1,278 @@
+// Fused network stems on the tensor cores: both convolutions that read the fp32 NCHW input image
+//   sb.conv1      7x7 s2 p3, 3 -> 64, BN, ReLU       (src/models/cabinet.py:111, 19-44)
+//   mobile stem   3x3 s2 p1, 3 -> 16, BN, HardSwish  (src/models/mobilenetv3.py:86-91,173)
+// are ONE implicit GEMM  D[128 px x 80] = A[128 x 192] * W[80 x 192]^T : the 3x3 filter is embedded in the centre of
+// a 7x7 one (same stride, same centre), so the image is read from HBM exactly once (it is 12.6 MB/img fp32, the
+// largest single read of the network) and both NHWC bf16 outputs are written once.
+//
+// K layout: k = (c*7 + ky)*8 + kx with kx in 0..7 (kx = 7 has zero weight), 168 padded to 192 = 3 K-blocks of 64.
+// With that order one 16-byte A chunk (8 bf16) is 8 CONSECUTIVE input floats of one image row, so the im2col
+// build is 4 LDS.64 + 4 packs + 1 STS.128 per chunk, written directly in the SWIZZLE_128B K-major UMMA layout.
+//
+// Persistent, warp specialised (320 threads):
+//   warp 0      TMA producer: weights once; per tile one 3-D fp32 box {40 cols, 21 rows, 3 ch} (OOB = zero padding)
+//   warp 1      TMEM allocator + MMA issuer: 12 x tcgen05.mma (M128 N80 K16) per tile, 2 accumulator stages
+//   warps 2-5   converters: fp32 window -> bf16 im2col A tile in shared memory (2 stages), fence.proxy.async
+//   warps 6-9   epilogue: tcgen05.ld, +bias, ReLU (cols 0-63) / HardSwish (cols 64-79), bf16 NHWC stores
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TH = 8, TW = 16;             // output patch = 128 pixels
+constexpr int WIN_H = 21, WIN_W = 40;      // input window rows / cols (fp32)
+constexpr int WIN_BYTES = 3 * WIN_H * WIN_W * 4;      // 10080
+constexpr int WIN_STRIDE = 10240;                     // stage pitch (128-byte aligned)
+constexpr int WIN_STAGES = 3;
+constexpr int KBLOCKS = 3;
+constexpr int A_KB_BYTES = 128 * 128;                 // one [128 x 64] bf16 K-block
+constexpr int A_STAGE_BYTES = KBLOCKS * A_KB_BYTES;   // 49152
+constexpr int A_STAGES = 2;
+constexpr int NOUT = 80;                              // 64 + 16
+constexpr int W_KB_BYTES = NOUT * 128;                // 10240
+constexpr int ACC_STAGES = 2;
+constexpr int ACC_COLS = 128;                         // TMEM columns per accumulator stage (80 used)
+constexpr int NUM_THREADS = 320;
+constexpr int SMEM_BYTES = KBLOCKS * W_KB_BYTES + A_STAGES * A_STAGE_BYTES + WIN_STAGES * WIN_STRIDE + 1024;
+
+struct StemParams {
+    int N, OH, OW, tiles_w, tiles_h, num_tiles;
+    const float* bias;
+    bf16* y_sb;
+    long long ld_sb;
+    bf16* y_stem;
+    long long ld_stem;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const StemParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t w_bar, win_full[WIN_STAGES], win_empty[WIN_STAGES], a_full[A_STAGES],
+        a_empty[A_STAGES], acc_full[ACC_STAGES], acc_empty[ACC_STAGES];
+    __shared__ uint32_t tmem_base_smem;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sW = smem;                                    // 3 x [80 x 64] bf16, swizzled
+    uint8_t* sA = sW + KBLOCKS * W_KB_BYTES;               // 2 x 3 x [128 x 64] bf16, swizzled (30720 = 30 x 1024)
+    uint8_t* sWin = sA + A_STAGES * A_STAGE_BYTES;         // 3 x [3][21][40] fp32
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tc::prefetch_tmap(&tmX);
+        tc::prefetch_tmap(&tmW);
+        tc::mbar_init(&w_bar, 1);
+        for (int s = 0; s < WIN_STAGES; ++s) {
+            tc::mbar_init(&win_full[s], 1);
+            tc::mbar_init(&win_empty[s], 4);
+        }
+        for (int s = 0; s < A_STAGES; ++s) {
+            tc::mbar_init(&a_full[s], 4);
+            tc::mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < ACC_STAGES; ++s) {
+            tc::mbar_init(&acc_full[s], 1);
+            tc::mbar_init(&acc_empty[s], 4);
+        }
+        tc::mbar_fence_init();
+        tc::fence_proxy_async();
+    }
+    if (warp == 1) tc::tmem_alloc(&tmem_base_smem, ACC_STAGES * ACC_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_base_smem;
+
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            tc::mbar_expect_tx(&w_bar, KBLOCKS * W_KB_BYTES);
+            for (int kb = 0; kb < KBLOCKS; ++kb) tc::tma_load_2d(sW + kb * W_KB_BYTES, &tmW, &w_bar, kb * 64, 0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int s = it % WIN_STAGES;
+                const uint32_t ph = (it / WIN_STAGES) & 1;
+                const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+                const int oh0 = (r / p.tiles_w) * TH, ow0 = (r % p.tiles_w) * TW;
+                tc::mbar_wait(&win_empty[s], ph ^ 1);
+                tc::mbar_expect_tx(&win_full[s], WIN_BYTES);
+                tc::tma_load_3d(sWin + s * WIN_STRIDE, &tmX, &win_full[s], 2 * ow0 - 3, 2 * oh0 - 3, 3 * img);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer =================
+            const uint32_t idesc = tc::make_idesc_bf16(128, NOUT);
+            tc::mbar_wait(&w_bar, 0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int as = it % A_STAGES, cs = it % ACC_STAGES;
+                const uint32_t aph = (it / A_STAGES) & 1, cph = (it / ACC_STAGES) & 1;
+                tc::mbar_wait(&acc_empty[cs], cph ^ 1);
+                tc::mbar_wait(&a_full[as], aph);
+                tc::tc_fence_after();
+                const uint32_t a_addr = tc::smem_u32(sA + as * A_STAGE_BYTES);
+                const uint32_t w_addr = tc::smem_u32(sW);
+                const uint32_t d = tmem + cs * ACC_COLS;
+#pragma unroll
+                for (int kb = 0; kb < KBLOCKS; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::umma_bf16(d, tc::make_desc_sw128(a_addr + kb * A_KB_BYTES + k * 32),
+                                      tc::make_desc_sw128(w_addr + kb * W_KB_BYTES + k * 32), idesc, (kb | k) ? 1u : 0u);
+                tc::umma_commit(&a_empty[as]);
+                tc::umma_commit(&acc_full[cs]);
+            }
+        }
+        __syncwarp();
+    } else if (warp < 6) {
+        // ================= converters: fp32 window -> swizzled bf16 im2col =================
+        const int r = (warp - 2) * 32 + lane;  // A row = output pixel of the patch
+        const int oy = r / TW, ox = r % TW;
+        // chunks 21..23 of K-block 2 are K padding: zero them once in both stages (weights there are zero too)
+        for (int as = 0; as < A_STAGES; ++as)
+            for (int cc = 5; cc < 8; ++cc)
+                *reinterpret_cast<uint4*>(sA + as * A_STAGE_BYTES + 2 * A_KB_BYTES + r * 128 + ((cc ^ (r & 7)) << 4)) =
+                    make_uint4(0, 0, 0, 0);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int ws = it % WIN_STAGES, as = it % A_STAGES;
+            const uint32_t wph = (it / WIN_STAGES) & 1, aph = (it / A_STAGES) & 1;
+            tc::mbar_wait(&win_full[ws], wph);
+            tc::mbar_wait(&a_empty[as], aph ^ 1);
+            const float* win = reinterpret_cast<const float*>(sWin + ws * WIN_STRIDE);
+            uint8_t* arow = sA + as * A_STAGE_BYTES + r * 128;
+#pragma unroll
+            for (int j = 0; j < 21; ++j) {  // j = c*7 + ky
+                const int c = j / 7, ky = j % 7;
+                const float2* src = reinterpret_cast<const float2*>(win + (c * WIN_H + 2 * oy + ky) * WIN_W + 2 * ox);
+                const float2 f0 = src[0], f1 = src[1], f2 = src[2], f3 = src[3];
+                const uint4 v = make_uint4(pack_bf16x2(f0.x, f0.y), pack_bf16x2(f1.x, f1.y), pack_bf16x2(f2.x, f2.y),
+                                           pack_bf16x2(f3.x, f3.y));
+                const int kb = j >> 3, cc = j & 7;
+                *reinterpret_cast<uint4*>(arow + kb * A_KB_BYTES + ((cc ^ (r & 7)) << 4)) = v;
+            }
+            tc::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+                tc::mbar_arrive(&a_full[as]);
+                tc::mbar_arrive(&win_empty[ws]);
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int oy = r / TW, ox = r % TW;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int cs = it % ACC_STAGES;
+            const uint32_t cph = (it / ACC_STAGES) & 1;
+            const int img = tile / tiles_per_img, rr = tile - img * tiles_per_img;
+            const int oh = (rr / p.tiles_w) * TH + oy, ow = (rr % p.tiles_w) * TW + ox;
+            const bool valid = oh < p.OH && ow < p.OW;
+            const long long pix = (static_cast<long long>(img) * p.OH + oh) * p.OW + ow;
+            tc::mbar_wait(&acc_full[cs], cph);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem + cs * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+            for (int c0 = 0; c0 < NOUT; c0 += 16) {
+                uint32_t acc[16];
+                tc::tmem_ld16(taddr + c0, acc);
+                tc::tmem_ld_wait();
+                if (valid) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float t = __uint_as_float(acc[j]) + __ldg(p.bias + c0 + j);
+                        v[j] = c0 < 64 ? fmaxf(t, 0.f) : t * (fminf(fmaxf(t + 3.f, 0.f), 6.f) / 6.f);
+                    }
+                    bf16* dst = c0 < 64 ? p.y_sb + pix * p.ld_sb + c0 : p.y_stem + pix * p.ld_stem + (c0 - 64);
+                    Vec16<bf16> o0, o1;
+                    o0.pack(v);
+                    o1.pack(v + 8);
+                    o0.store(dst);
+                    o1.store(dst + 8);
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_empty[cs]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem, ACC_STAGES * ACC_COLS);
+    }
+}
+
+int g_attr_set = 0;
+
+}  // namespace
+
+extern "C" int cabinet_stem_tc(const float* x, int N, int H, int W, const void* w_packed, const float* bias,
+                               void* y_sb, long long ld_sb, void* y_stem, long long ld_stem, int OH, int OW,
+                               cabinet_stream_t stream) {
+    CAB_REQUIRE(x && w_packed && bias && y_sb && y_stem, "stem_tc: null pointer");
+    CAB_REQUIRE(N >= 0 && H > 0 && W > 0 && W % 4 == 0, "stem_tc: W must be a multiple of 4 (TMA row pitch)");
+    CAB_REQUIRE(OH == (H - 1) / 2 + 1 && OW == (W - 1) / 2 + 1, "stem_tc: inconsistent output size");
+    CAB_REQUIRE(ld_sb >= 64 && ld_sb % 8 == 0 && ld_stem >= 16 && ld_stem % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(y_sb) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_stem) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
+                "stem_tc: alignment");
+    if (N == 0) return CABINET_OK;
+    cab_encode_tiled_fn enc = cab_get_encode_tiled();
+    CAB_REQUIRE(enc != nullptr, "stem_tc: cuTensorMapEncodeTiled unavailable");
+
+    CUtensorMap tmX, tmW;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)3 * N};
+        cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+        cuuint32_t box[3] = {WIN_W, WIN_H, 3};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            cabinet_set_error("stem_tc: input tensor map encode failed (CUresult %d)", (int)r);
+            return CABINET_ERR_CUDA;
+        }
+    }
+    {
+        const uint64_t dims[2] = {KBLOCKS * 64, NOUT};
+        const uint64_t strides[1] = {KBLOCKS * 64 * 2};
+        const uint32_t box[2] = {64, NOUT};
+        int rc = cab_make_tmap_bf16(&tmW, w_packed, 2, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (rc) return rc;
+    }
+    StemParams p;
+    p.N = N; p.OH = OH; p.OW = OW;
+    p.tiles_w = (OW + TW - 1) / TW;
+    p.tiles_h = (OH + TH - 1) / TH;
+    const long long nt = static_cast<long long>(N) * p.tiles_w * p.tiles_h;
+    CAB_REQUIRE(nt < (1LL << 31), "stem_tc: too many tiles");
+    p.num_tiles = static_cast<int>(nt);
+    p.bias = bias;
+    p.y_sb = reinterpret_cast<bf16*>(y_sb); p.ld_sb = ld_sb;
+    p.y_stem = reinterpret_cast<bf16*>(y_stem); p.ld_stem = ld_stem;
+    if (!g_attr_set) {
+        CAB_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        g_attr_set = 1;
+    }
+    int dev = 0, sms = 148;
+    CAB_CUDA(cudaGetDevice(&dev));
+    CAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = static_cast<int>(std::min<long long>(nt, sms));
+    stem_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmX, tmW, p);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}

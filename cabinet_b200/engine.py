@@ -160,6 +160,18 @@ class Engine:
         self.last = ConvLayer(mob.conv[0], mob.conv[1], ACT_HSWISH, wd, "mobile.conv")
 
         sb = m.sb
+        self.stem_tc = None
+        if self.precision == "bf16":
+            # fused stems: [80][192] bf16, k = (c*7 + ky)*8 + kx; the 3x3 stem sits in the centre of a 7x7 footprint
+            w7, b7 = _fold(sb.conv1.conv.weight, None, sb.conv1.bn)
+            w3, b3 = _fold(mob.features[0][0].weight, None, mob.features[0][1])
+            pk = torch.zeros((80, 3, 7, 8), dtype=torch.float32, device=w7.device)
+            pk[:64, :, :, :7] = w7
+            pk[64:, :, 2:5, 2:5] = w3
+            self.stem_tc = (pk.reshape(80, 168).contiguous(), torch.cat([b7, b3]).contiguous())
+            wk = torch.zeros((80, 192), dtype=torch.float32, device=w7.device)
+            wk[:, :168] = self.stem_tc[0]
+            self.stem_tc = (wk.to(torch.bfloat16).contiguous(), self.stem_tc[1])
         self.sb1 = ConvLayer(sb.conv1.conv, sb.conv1.bn, ACT_RELU, f32, "sb.conv1")
         self.sb2 = ConvLayer(sb.conv2.conv, sb.conv2.bn, ACT_RELU, wd, "sb.conv2")
         self.sb3 = ConvLayer(sb.conv3.conv, sb.conv3.bn, ACT_RELU, wd, "sb.conv3")
@@ -328,7 +340,16 @@ class Engine:
         self.launches += 1
 
         # ---- spatial branch (reference: cabinet.py:108-129) -> channels [0:128] of the FFM concat buffer
-        s1 = self.conv(None, self.sb1, nchw_input=x)
+        fused_stems = self.use_tc and self.stem_tc is not None and W % 4 == 0
+        if fused_stems:
+            OH2, OW2 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            s1, f0 = self.new(N, OH2, OW2, 64), self.new(N, OH2, OW2, 16)
+            nbytes = x.numel() * 4 + (s1.t.numel() + f0.t.numel()) * 2 + 80 * 192 * 2
+            self._run("stem_tc", "sb.conv1+mobile.stem", nbytes, 2 * N * OH2 * OW2 * (64 * 147 + 16 * 27),
+                      self.lib.cabinet_stem_tc, x.data_ptr(), N, H, W, self.stem_tc[0].data_ptr(),
+                      self.stem_tc[1].data_ptr(), s1.ptr, s1.ld, f0.ptr, f0.ld, OH2, OW2, self.stream)
+        else:
+            s1 = self.conv(None, self.sb1, nchw_input=x)
         s2 = self.conv(s1, self.sb2)
         s3 = self.conv(s2, self.sb3)
         H8, W8 = s3.H, s3.W
@@ -336,7 +357,7 @@ class Engine:
         self.conv(s3, self.sb4, out=cat_ffm.slice(0, 128))
 
         # ---- backbone (reference: mobilenetv3.py:202-205)
-        f = self.conv(None, self.stem, nchw_input=x)
+        f = f0 if fused_stems else self.conv(None, self.stem, nchw_input=x)
         gi = 0
         for e in self.blocks:
             s = e["spec"]
