@@ -5,7 +5,8 @@
 // a 7x7 one (same stride, same centre), so the image is read from HBM exactly once (it is 12.6 MB/img fp32, the
 // largest single read of the network) and both NHWC bf16 outputs are written once.
 //
-// K layout: k = (c*7 + ky)*8 + kx with kx in 0..7 (kx = 7 has zero weight), 168 padded to 192 = 3 K-blocks of 64.
+// K layout: k = (c*7 + ky)*8 + kx with kx in 0..7 (kx = 0 has zero weight: the window starts one column left of
+// the filter footprint so that the TMA start coordinate is 16-byte aligned), 168 padded to 192 = 3 K-blocks of 64.
 // With that order one 16-byte A chunk (8 bf16) is 8 CONSECUTIVE input floats of one image row, so the im2col
 // build is 4 LDS.64 + 4 packs + 1 STS.128 per chunk, written directly in the SWIZZLE_128B K-major UMMA layout.
 //
@@ -102,7 +103,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 const int oh0 = (r / p.tiles_w) * TH, ow0 = (r % p.tiles_w) * TW;
                 tc::mbar_wait(&win_empty[s], ph ^ 1);
                 tc::mbar_expect_tx(&win_full[s], WIN_BYTES);
-                tc::tma_load_3d(sWin + s * WIN_STRIDE, &tmX, &win_full[s], 2 * ow0 - 3, 2 * oh0 - 3, 3 * img);
+                // the innermost TMA coordinate must be 16-byte aligned: start one column left of the 7x7 footprint
+                tc::tma_load_3d(sWin + s * WIN_STRIDE, &tmX, &win_full[s], 2 * ow0 - 4, 2 * oh0 - 3, 3 * img);
             }
         }
         __syncwarp();

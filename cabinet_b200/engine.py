@@ -166,8 +166,8 @@ class Engine:
             w7, b7 = _fold(sb.conv1.conv.weight, None, sb.conv1.bn)
             w3, b3 = _fold(mob.features[0][0].weight, None, mob.features[0][1])
             pk = torch.zeros((80, 3, 7, 8), dtype=torch.float32, device=w7.device)
-            pk[:64, :, :, :7] = w7
-            pk[64:, :, 2:5, 2:5] = w3
+            pk[:64, :, :, 1:8] = w7  # kx = 0 is the zero-weight alignment slot
+            pk[64:, :, 2:5, 3:6] = w3
             self.stem_tc = (pk.reshape(80, 168).contiguous(), torch.cat([b7, b3]).contiguous())
             wk = torch.zeros((80, 192), dtype=torch.float32, device=w7.device)
             wk[:, :168] = self.stem_tc[0]

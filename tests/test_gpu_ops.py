@@ -315,8 +315,8 @@ def test_stem_tc(N, H, W):
     ref_st = t * F.relu6(t + 3) / 6
     OH, OW = ref_sb.shape[2:]
     pk = torch.zeros(80, 3, 7, 8)
-    pk[:64, :, :, :7] = w7
-    pk[64:, :, 2:5, 2:5] = w3
+    pk[:64, :, :, 1:8] = w7
+    pk[64:, :, 2:5, 3:6] = w3
     wk = torch.zeros(80, 192)
     wk[:, :168] = pk.reshape(80, 168)
     wk, bias = wk.to("cuda", torch.bfloat16).contiguous(), torch.cat([b7, b3]).cuda()
