@@ -2,19 +2,22 @@
 //
 //   D[128 pixels x block_n couts] = sum over (tap, 64-channel block)  A_tap[128 x 64] * W_tap[block_n x 64]^T
 //
-// * A tiles are fetched by TMA straight from the NHWC activation: the 128 output pixels of a CTA are a TH x TW
+// * A tiles are fetched by TMA straight from the NHWC activation: the 128 output pixels of a tile are a TH x TW
 //   patch of one image, each filter tap is ONE 4-D box load {64 ch, TW, TH, 1} at a shifted coordinate, and the
 //   zero padding of the convolution is TMA's out-of-bounds zero fill (negative / past-the-end coordinates).
 //   Stride-2 convolutions use one tensor map per input parity (py, px): map(py,px)[h][w] = x[2h+py][2w+px], so a
 //   tap is again a plain shifted box.  1x1 convolutions view the tensor as [N*H*W][C] (no tile waste).
-// * W tiles ([Cout_pad][taps*Cin_pad] bf16, K-major, BN folded) come through a 2-D tensor map.
-// * Both land in 128-byte-swizzled shared memory, which is exactly the canonical K-major SWIZZLE_128B UMMA
-//   layout, so descriptors are built from the stage base + 32 B per K=16 step.
-// * Warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-//   warps 2-5 = epilogue (tcgen05.ld -> +bias -> act -> +residual -> bf16/fp32 NHWC stores).
-//   smem ring full/empty mbarriers; tcgen05.commit releases ring slots and publishes the accumulator.
-// * Several CTAs are resident per SM (smem <= ~100 KB, TMEM <= 256 columns each) so one CTA's epilogue overlaps
-//   another's loads/MMAs.
+// * W tiles ([Cout_pad][taps*Cin_pad] bf16, K-major, BN folded) come through a 2-D tensor map; when the whole
+//   weight matrix is <= 64 KB (every memory-bound 1x1 layer) it is loaded ONCE per CTA and stays resident.
+// * Both land in 128-byte-swizzled shared memory = the canonical K-major SWIZZLE_128B UMMA layout, so MMA
+//   descriptors are the stage base + 32 B per K=16 step.
+// * PERSISTENT and pipelined across tiles: one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...; the smem ring
+//   never drains between tiles and two TMEM accumulator stages let the MMAs of tile i+1 run under the epilogue of
+//   tile i.  Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+//   warps 2-5 / 6-9 = two epilogue warpgroups (even / odd tiles).
+// * Epilogue: tcgen05.ld -> +bias -> act -> (+residual) -> bf16 -> 128B-swizzled smem staging -> TMA store
+//   (full-line writes, image-border and channel clipping by the tensor map); fp32 outputs (class logits) are
+//   stored directly.
 #include "tc_common.cuh"
 
 namespace {
@@ -22,15 +25,18 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // bf16 elements: 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int MAX_STAGES = 6;
-constexpr int NUM_THREADS = 192;
+constexpr int C_STAGE_BYTES = BLOCK_M * 128;  // one [128 rows x 64 ch] bf16 store box
+constexpr int MAX_STAGES = 8;
+constexpr int NUM_THREADS = 320;
+constexpr int B_RESIDENT_MAX = 64 * 1024;
+constexpr int SMEM_LIMIT = 225 * 1024;
 
 struct TcConvParams {
-    int N, OH, OW, Cin, Cout;
+    int OH, OW, Cin, Cout;
     int KW, stride, pad;
     int TW, TH, tiles_w, tiles_h;
     int cin_blocks, num_k_blocks;
-    int block_n, tmem_cols, stages;
+    int block_n, n_tiles, num_tiles, tmem_cols, stages, b_resident;
     int act, y_dtype;
     const float* bias;
     const bf16* res;
@@ -39,31 +45,54 @@ struct TcConvParams {
     long long ldy;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 3)
+struct TileCoord {
+    int img, oh0, ow0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int tile) {
+    TileCoord c;
+    const int m = tile / p.n_tiles;
+    c.n0 = (tile - m * p.n_tiles) * p.block_n;
+    const int tw_i = m % p.tiles_w;
+    const int t = m / p.tiles_w;
+    c.ow0 = tw_i * p.TW;
+    c.oh0 = (t % p.tiles_h) * p.TH;
+    c.img = t / p.tiles_h;
+    return c;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
-               const __grid_constant__ CUtensorMap tmB, const TcConvParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
+               const TcConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], bres_bar;
     __shared__ uint32_t tmem_base_smem;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_stage_bytes = p.block_n * BLOCK_K * 2;
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + p.stages * A_STAGE_BYTES;
+    uint8_t* sC = smem;                                   // 4 x 16 KB store staging (2 per epilogue warpgroup)
+    uint8_t* sA = sC + 4 * C_STAGE_BYTES;                 // ring: stages x 16 KB
+    uint8_t* sB = sA + p.stages * A_STAGE_BYTES;          // ring (stages x b_stage) or resident (num_k_blocks x b_stage)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         tc::prefetch_tmap(&tmA0);
         tc::prefetch_tmap(&tmB);
+        tc::prefetch_tmap(&tmY);
         for (int s = 0; s < p.stages; ++s) {
             tc::mbar_init(&full_bar[s], 1);
             tc::mbar_init(&empty_bar[s], 1);
         }
-        tc::mbar_init(&tmem_full_bar, 1);
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&acc_full[s], 1);
+            tc::mbar_init(&acc_empty[s], 4);
+        }
+        tc::mbar_init(&bres_bar, 1);
         tc::mbar_fence_init();
         tc::fence_proxy_async();
     }
@@ -72,38 +101,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = tmem_base_smem;
-
-    // tile decode: blockIdx.x -> (image, patch row, patch col); blockIdx.y -> cout tile
-    const int tw_i = blockIdx.x % p.tiles_w;
-    const int t = blockIdx.x / p.tiles_w;
-    const int th_i = t % p.tiles_h;
-    const int img = t / p.tiles_h;
-    const int ow0 = tw_i * p.TW, oh0 = th_i * p.TH;
-    const int n0 = blockIdx.y * p.block_n;
+    const int acc_stride = p.tmem_cols >> 1;  // columns per accumulator stage (>= block_n)
 
     if (warp == 0) {
         if (lane == 0) {
             // ================= TMA producer =================
-            const uint32_t tx_bytes = A_STAGE_BYTES + b_stage_bytes;
-            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (kb / p.stages) & 1;
-                tc::mbar_wait(&empty_bar[s], ph ^ 1);
-                tc::mbar_expect_tx(&full_bar[s], tx_bytes);
-                const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
-                const int ky = tap / p.KW, kx = tap - ky * p.KW;
-                const int ty = ky - p.pad, tx = kx - p.pad;
-                const CUtensorMap* map = &tmA0;
-                int dy = ty, dx = tx;
-                if (p.stride == 2) {
-                    const int py = ty & 1, px = tx & 1;
-                    dy = (ty - py) >> 1;
-                    dx = (tx - px) >> 1;
-                    const int id = py * 2 + px;
-                    map = id == 0 ? &tmA0 : id == 1 ? &tmA1 : id == 2 ? &tmA2 : &tmA3;
+            if (p.b_resident) {
+                tc::mbar_expect_tx(&bres_bar, p.num_k_blocks * b_stage_bytes);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb)
+                    tc::tma_load_2d(sB + kb * b_stage_bytes, &tmB, &bres_bar, kb * BLOCK_K, 0);
+            }
+            const uint32_t tx_bytes = A_STAGE_BYTES + (p.b_resident ? 0 : b_stage_bytes);
+            int g = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord tcd = decode_tile(p, tile);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb, ++g) {
+                    const int s = g % p.stages;
+                    const uint32_t ph = (g / p.stages) & 1;
+                    tc::mbar_wait(&empty_bar[s], ph ^ 1);
+                    tc::mbar_expect_tx(&full_bar[s], tx_bytes);
+                    const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
+                    const int ky = tap / p.KW, kx = tap - ky * p.KW;
+                    const int ty = ky - p.pad, tx = kx - p.pad;
+                    const CUtensorMap* map = &tmA0;
+                    int dy = ty, dx = tx;
+                    if (p.stride == 2) {
+                        const int py = ty & 1, px = tx & 1;
+                        dy = (ty - py) >> 1;
+                        dx = (tx - px) >> 1;
+                        const int id = py * 2 + px;
+                        map = id == 0 ? &tmA0 : id == 1 ? &tmA1 : id == 2 ? &tmA2 : &tmA3;
+                    }
+                    tc::tma_load_4d(sA + s * A_STAGE_BYTES, map, &full_bar[s], cb * BLOCK_K, tcd.ow0 + dx, tcd.oh0 + dy,
+                                    tcd.img);
+                    if (!p.b_resident) tc::tma_load_2d(sB + s * b_stage_bytes, &tmB, &full_bar[s], kb * BLOCK_K, tcd.n0);
                 }
-                tc::tma_load_4d(sA + s * A_STAGE_BYTES, map, &full_bar[s], cb * BLOCK_K, ow0 + dx, oh0 + dy, img);
-                tc::tma_load_2d(sB + s * b_stage_bytes, &tmB, &full_bar[s], kb * BLOCK_K, n0);
             }
         }
         __syncwarp();
@@ -111,82 +143,117 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) {
             // ================= MMA issuer =================
             const uint32_t idesc = tc::make_idesc_bf16(BLOCK_M, p.block_n);
-            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (kb / p.stages) & 1;
-                tc::mbar_wait(&full_bar[s], ph);
+            if (p.b_resident) tc::mbar_wait(&bres_bar, 0);
+            int g = 0, it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                tc::mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
                 tc::tc_fence_after();
-                const int cb = kb % p.cin_blocks;
-                const int ksteps = min(BLOCK_K / 16, (p.Cin - cb * BLOCK_K + 15) / 16);  // skip all-zero K tails
-                const uint32_t a_addr = tc::smem_u32(sA + s * A_STAGE_BYTES);
-                const uint32_t b_addr = tc::smem_u32(sB + s * b_stage_bytes);
-                for (int k = 0; k < ksteps; ++k)
-                    tc::umma_bf16(tmem, tc::make_desc_sw128(a_addr + k * 32), tc::make_desc_sw128(b_addr + k * 32),
-                                  idesc, (kb | k) != 0 ? 1u : 0u);
-                tc::umma_commit(&empty_bar[s]);  // ring slot is free once these MMAs have read it
+                const uint32_t d = tmem + acc * acc_stride;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb, ++g) {
+                    const int s = g % p.stages;
+                    const uint32_t ph = (g / p.stages) & 1;
+                    tc::mbar_wait(&full_bar[s], ph);
+                    tc::tc_fence_after();
+                    const int cb = kb % p.cin_blocks;
+                    const int ksteps = min(BLOCK_K / 16, (p.Cin - cb * BLOCK_K + 15) / 16);  // skip all-zero K tails
+                    const uint32_t a_addr = tc::smem_u32(sA + s * A_STAGE_BYTES);
+                    const uint32_t b_addr = tc::smem_u32(sB + (p.b_resident ? kb : s) * b_stage_bytes);
+                    for (int k = 0; k < ksteps; ++k)
+                        tc::umma_bf16(d, tc::make_desc_sw128(a_addr + k * 32), tc::make_desc_sw128(b_addr + k * 32),
+                                      idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc::umma_commit(&empty_bar[s]);  // ring slot is free once these MMAs have read it
+                }
+                tc::umma_commit(&acc_full[acc]);     // accumulator of this tile complete
             }
-            tc::umma_commit(&tmem_full_bar);     // accumulator complete
         }
         __syncwarp();
     } else {
-        // ================= epilogue: TMEM -> registers -> global =================
+        // ================= epilogue warpgroup e (tiles it = e, e+2, ...) =================
+        const int e = (warp - 2) >> 2;
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
-        const int oh = oh0 + row / p.TW, ow = ow0 + row % p.TW;
-        const bool valid = oh < p.OH && ow < p.OW;
-        const long long pix = (static_cast<long long>(img) * p.OH + oh) * p.OW + ow;
-        tc::mbar_wait(&tmem_full_bar, 0);
-        tc::tc_fence_after();
-        const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16);
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-            uint32_t r[16];
-            tc::tmem_ld16(taddr + c0, r);
-            tc::tmem_ld_wait();
-            const int co0 = n0 + c0;
-            if (!valid || co0 >= p.Cout) continue;
-            float v[16];
+        const bool leader = (warp - 2) % 4 == 0 && lane == 0;
+        uint8_t* myC = sC + e * 2 * C_STAGE_BYTES;
+        uint32_t store_seq = 0;
+        int it = e;
+        for (int tile = blockIdx.x + e * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
+            const TileCoord tcd = decode_tile(p, tile);
+            const int oh = tcd.oh0 + row / p.TW, ow = tcd.ow0 + row % p.TW;
+            const bool valid = oh < p.OH && ow < p.OW;
+            const long long pix = (static_cast<long long>(tcd.img) * p.OH + oh) * p.OW + ow;
+            tc::mbar_wait(&acc_full[e], (it >> 1) & 1);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem + e * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+            const int ngroups = (p.block_n + 63) >> 6;
+            for (int grp = 0; grp < ngroups; ++grp) {
+                uint8_t* buf = myC + (store_seq & 1) * C_STAGE_BYTES;
+                if (p.y_dtype == CABINET_BF16) {
+                    // the TMA store that used this buffer two groups ago must have finished reading it
+                    if (leader) tc::bulk_wait_read<1>();
+                    tc::named_bar_sync(1 + e, 128);
+                }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float b = (co0 + j < p.Cout) ? __ldg(p.bias + co0 + j) : 0.f;
-                v[j] = cab_act(__uint_as_float(r[j]) + b, p.act);
-            }
-            if (p.res) {
-                const bf16* rp = p.res + pix * p.ldres + co0;
+                for (int c = 0; c < 4; ++c) {
+                    const int c0 = grp * 64 + c * 16;
+                    if (c0 >= p.block_n) break;
+                    uint32_t r[16];
+                    tc::tmem_ld16(taddr + c0, r);
+                    tc::tmem_ld_wait();
+                    const int co0 = tcd.n0 + c0;
+                    float v[16];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (co0 + 8 * h + 8 <= p.Cout) {
-                        Vec16<bf16> rv;
-                        rv.load(rp + 8 * h);
-                        float rf[8];
-                        rv.unpack(rf);
+                    for (int j = 0; j < 16; ++j) {
+                        const float b = (co0 + j < p.Cout) ? __ldg(p.bias + co0 + j) : 0.f;
+                        v[j] = cab_act(__uint_as_float(r[j]) + b, p.act);
+                    }
+                    if (p.res && valid && co0 < p.Cout) {
+                        const bf16* rp = p.res + pix * p.ldres + co0;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[8 * h + j] += rf[j];
-                    } else {
-                        for (int j = 0; j < 8; ++j)
-                            if (co0 + 8 * h + j < p.Cout) v[8 * h + j] += __bfloat162float(rp[8 * h + j]);
+                        for (int h = 0; h < 2; ++h) {
+                            if (co0 + 8 * h + 8 <= p.Cout) {
+                                Vec16<bf16> rv;
+                                rv.load(rp + 8 * h);
+                                float rf[8];
+                                rv.unpack(rf);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[8 * h + j] += rf[j];
+                            } else {
+                                for (int j = 0; j < 8; ++j)
+                                    if (co0 + 8 * h + j < p.Cout) v[8 * h + j] += __bfloat162float(rp[8 * h + j]);
+                            }
+                        }
+                    }
+                    if (p.y_dtype == CABINET_BF16) {
+                        Vec16<bf16> o0, o1;
+                        o0.pack(v);
+                        o1.pack(v + 8);
+                        uint8_t* rowp = buf + row * 128;
+                        *reinterpret_cast<uint4*>(rowp + (((2 * c) ^ (row & 7)) << 4)) = o0.raw;
+                        *reinterpret_cast<uint4*>(rowp + (((2 * c + 1) ^ (row & 7)) << 4)) = o1.raw;
+                    } else if (valid) {
+                        float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + co0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (co0 + j < p.Cout) yp[j] = v[j];
                     }
                 }
-            }
-            if (p.y_dtype == CABINET_BF16) {
-                bf16* yp = reinterpret_cast<bf16*>(p.y) + pix * p.ldy + co0;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (co0 + 8 * h + 8 <= p.Cout) {
-                        Vec16<bf16> ov;
-                        ov.pack(v + 8 * h);
-                        ov.store(yp + 8 * h);
-                    } else {
-                        for (int j = 0; j < 8; ++j)
-                            if (co0 + 8 * h + j < p.Cout) yp[8 * h + j] = __float2bfloat16_rn(v[8 * h + j]);
+                if (p.y_dtype == CABINET_BF16) {
+                    tc::fence_proxy_async();
+                    tc::named_bar_sync(1 + e, 128);
+                    if (leader) {
+                        tc::tma_store_4d(&tmY, buf, tcd.n0 + grp * 64, tcd.ow0, tcd.oh0, tcd.img);
+                        tc::bulk_commit();
                     }
+                    ++store_seq;
                 }
-            } else {
-                float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + co0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (co0 + j < p.Cout) yp[j] = v[j];
             }
+            // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&acc_empty[e]);
         }
+        if (leader) tc::bulk_wait<0>();
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -263,21 +330,27 @@ extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W
     p.cin_blocks = (Cin + BLOCK_K - 1) / BLOCK_K;
     p.num_k_blocks = taps * p.cin_blocks;
     const int n16 = ((Cout + 15) / 16) * 16;
-    const int n_tiles = (n16 + 255) / 256;
-    p.block_n = (((n16 + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+    // one cout tile when it fits an accumulator stage (<= 256 columns), else 256-wide tiles (a multiple of the
+    // 64-channel store box, so the boxes of neighbouring tiles never overlap; the tail is clipped by the map)
+    p.n_tiles = (n16 + 255) / 256;
+    p.block_n = p.n_tiles == 1 ? n16 : 256;
     p.tmem_cols = 32;
-    while (p.tmem_cols < p.block_n) p.tmem_cols *= 2;
-    const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
-    p.stages = std::max(2, std::min({p.num_k_blocks, MAX_STAGES, (100 * 1024) / stage_bytes}));
+    while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
+    const int b_stage_bytes = p.block_n * BLOCK_K * 2;
+    p.b_resident = (p.n_tiles == 1 && p.num_k_blocks * b_stage_bytes <= B_RESIDENT_MAX) ? 1 : 0;
+    const int fixed = 4 * C_STAGE_BYTES + (p.b_resident ? p.num_k_blocks * b_stage_bytes : 0) + 1024;
+    const int stage_bytes = A_STAGE_BYTES + (p.b_resident ? 0 : b_stage_bytes);
+    p.stages = std::max(2, std::min(MAX_STAGES, (SMEM_LIMIT - fixed) / stage_bytes));
     p.act = act; p.y_dtype = y_dtype; p.bias = bias; p.res = reinterpret_cast<const bf16*>(res); p.ldres = ldres;
     p.y = y; p.ldy = ldy;
 
-    CUtensorMap tmA[4], tmB;
+    CUtensorMap tmA[4], tmB, tmY;
     const uint64_t es = 2;
+    int Ng = N;
     if (flat) {
         const long long P = static_cast<long long>(N) * H * W;
-        p.N = 1; p.OH = 1; p.OW = static_cast<int>(P);
         CAB_REQUIRE(P < (1LL << 31), "conv_tc: too many pixels");
+        Ng = 1; p.OH = 1; p.OW = static_cast<int>(P);
         p.TW = BLOCK_M; p.TH = 1; p.tiles_w = static_cast<int>(cab_ceil_div(P, BLOCK_M)); p.tiles_h = 1;
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)P, 1, 1};
         const uint64_t strides[3] = {(uint64_t)ldx * es, (uint64_t)ldx * es * P, (uint64_t)ldx * es * P};
@@ -286,7 +359,7 @@ extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W
         if (rc) return rc;
         tmA[1] = tmA[2] = tmA[3] = tmA[0];
     } else {
-        p.N = N; p.OH = OH; p.OW = OW;
+        p.OH = OH; p.OW = OW;
         // pick the TH x TW = 128 patch shape that wastes the fewest pixels (ties: wider)
         long long best = -1;
         for (int tw = 128; tw >= 4; tw >>= 1) {
@@ -318,15 +391,31 @@ extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W
         int rc = cab_make_tmap_bf16(&tmB, w_packed, 2, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
     }
-    const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024;
+    if (y_dtype == CABINET_BF16) {
+        // store map: {Cout (true extent: clips padded / foreign channels), OW, OH, N}, 64-channel boxes
+        const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)p.OW, (uint64_t)p.OH, (uint64_t)Ng};
+        const uint64_t strides[3] = {(uint64_t)ldy * es, (uint64_t)ldy * es * p.OW, (uint64_t)ldy * es * p.OW * p.OH};
+        const uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+        int rc = cab_make_tmap_bf16(&tmY, y, 4, dims, strides, box);
+        if (rc) return rc;
+    } else {
+        tmY = tmB;  // unused
+    }
+    const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(p.stages) * stage_bytes;
     if (!g_smem_attr_set) {
-        CAB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        CAB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT + 1024));
         g_smem_attr_set = 1;
     }
-    const long long m_tiles = static_cast<long long>(p.N) * p.tiles_h * p.tiles_w;
-    CAB_REQUIRE(m_tiles < (1LL << 31), "conv_tc: too many tiles");
-    dim3 grid(static_cast<unsigned>(m_tiles), n_tiles);
-    conv_tc_kernel<<<grid, NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, p);
+    const long long m_tiles = static_cast<long long>(Ng) * p.tiles_h * p.tiles_w;
+    const long long tiles = m_tiles * p.n_tiles;
+    CAB_REQUIRE(tiles < (1LL << 31), "conv_tc: too many tiles");
+    p.num_tiles = static_cast<int>(tiles);
+    int dev = 0, sms = 148;
+    CAB_CUDA(cudaGetDevice(&dev));
+    CAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = static_cast<int>(std::min<long long>(tiles, sms));
+    conv_tc_kernel<<<grid, NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB,
+                                                                                   tmY, p);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }
