@@ -49,6 +49,24 @@ __device__ __forceinline__ float cab_act(float v, int act) {
     }
 }
 
+// Activation over a small register array: ONE uniform branch per call, straight-line code per case
+// (a per-element switch compiles to an indirect branch per element and serialises the whole epilogue).
+template <int N> __device__ __forceinline__ void cab_act_vec(float* v, int act) {
+    if (act == CABINET_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = fmaxf(v[i], 0.f);
+    } else if (act == CABINET_ACT_HSWISH) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = v[i] * (fminf(fmaxf(v[i] + 3.f, 0.f), 6.f) * (1.f / 6.f));
+    } else if (act == CABINET_ACT_HSIGMOID) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = fminf(fmaxf(v[i] + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    } else if (act == CABINET_ACT_SIGMOID) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = 1.f / (1.f + __expf(-v[i]));
+    }
+}
+
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }

@@ -103,14 +103,19 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(ConvArgs a) {
     for (int i = 0; i < 4; ++i) {
         long long m = m0 + ty * 4 + i;
         if (m >= a.M) continue;
+        float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int co = n0 + tx * 4 + j;
+            const int co = n0 + tx * 4 + j;
+            v[j] = acc[i][j] * a.alpha + ((a.bias && co < a.Cout) ? a.bias[co] : 0.f);
+        }
+        cab_act_vec<4>(v, a.act);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = n0 + tx * 4 + j;
             if (co >= a.Cout) continue;
-            float v = acc[i][j] * a.alpha + (a.bias ? a.bias[co] : 0.f);
-            v = cab_act(v, a.act);
-            if (res) v += to_f32<TY>(res[m * a.ldres + co]);
-            y[m * a.ldy + co] = from_f32<TY>(v);
+            if (res) v[j] += to_f32<TY>(res[m * a.ldres + co]);
+            y[m * a.ldy + co] = from_f32<TY>(v[j]);
         }
     }
 }

@@ -37,7 +37,7 @@ struct TcConvParams {
     int TW, TH, tiles_w, tiles_h;
     int cin_blocks, num_k_blocks;
     int block_n, n_tiles, num_tiles, tmem_cols, stages, b_resident;
-    int act, y_dtype;
+    int act, y_dtype, debug;
     const float* bias;
     const bf16* res;
     long long ldres;
@@ -119,6 +119,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     const int s = g % p.stages;
                     const uint32_t ph = (g / p.stages) & 1;
                     tc::mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (p.debug & 4) {
+                        tc::mbar_arrive(&full_bar[s]);
+                        continue;
+                    }
                     tc::mbar_expect_tx(&full_bar[s], tx_bytes);
                     const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
                     const int ky = tap / p.KW, kx = tap - ky * p.KW;
@@ -196,17 +200,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int c0 = grp * 64 + c * 16;
-                    if (c0 >= p.block_n) break;
+                    if (c0 >= p.block_n || (p.debug & 2)) break;
                     uint32_t r[16];
                     tc::tmem_ld16(taddr + c0, r);
                     tc::tmem_ld_wait();
                     const int co0 = tcd.n0 + c0;
                     float v[16];
+                    if (co0 + 16 <= p.Cout) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float b = (co0 + j < p.Cout) ? __ldg(p.bias + co0 + j) : 0.f;
-                        v[j] = cab_act(__uint_as_float(r[j]) + b, p.act);
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0) + j4);
+                            v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
+                            v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
+                            v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
+                            v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            v[j] = __uint_as_float(r[j]) + ((co0 + j < p.Cout) ? __ldg(p.bias + co0 + j) : 0.f);
                     }
+                    cab_act_vec<16>(v, p.act);
                     if (p.res && valid && co0 < p.Cout) {
                         const bf16* rp = p.res + pix * p.ldres + co0;
 #pragma unroll
@@ -241,7 +255,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if (p.y_dtype == CABINET_BF16) {
                     tc::fence_proxy_async();
                     tc::named_bar_sync(1 + e, 128);
-                    if (leader) {
+                    if (leader && !(p.debug & 1)) {
                         tc::tma_store_4d(&tmY, buf, tcd.n0 + grp * 64, tcd.ow0, tcd.oh0, tcd.img);
                         tc::bulk_commit();
                     }
@@ -264,6 +278,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 }
 
 int g_smem_attr_set = 0;
+int g_debug = 0;
 
 }  // namespace
 
@@ -306,6 +321,12 @@ int cab_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint6
     return CABINET_OK;
 }
 
+extern "C" int cabinet_debug_flags(int flags) {
+    const int old = g_debug;
+    g_debug = flags;
+    return old;
+}
+
 extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_packed,
                                int Cout, int KH, int KW, int stride, int pad, const float* bias, const void* res,
                                long long ldres, void* y, int y_dtype, long long ldy, int OH, int OW, int act,
@@ -342,7 +363,7 @@ extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W
     const int stage_bytes = A_STAGE_BYTES + (p.b_resident ? 0 : b_stage_bytes);
     p.stages = std::max(2, std::min(MAX_STAGES, (SMEM_LIMIT - fixed) / stage_bytes));
     p.act = act; p.y_dtype = y_dtype; p.bias = bias; p.res = reinterpret_cast<const bf16*>(res); p.ldres = ldres;
-    p.y = y; p.ldy = ldy;
+    p.y = y; p.ldy = ldy; p.debug = g_debug;
 
     CUtensorMap tmA[4], tmB, tmY;
     const uint64_t es = 2;

@@ -90,11 +90,9 @@ dwconv_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ 
         for (int r = 0; r < RUN; ++r) {
             const int ow = ow0 + r;
             if (ow >= OW) continue;
+            cab_act_vec<V>(acc[r], act);
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                acc[r][v] = cab_act(acc[r][v], act);
-                gsum[v] += acc[r][v];
-            }
+            for (int v = 0; v < V; ++v) gsum[v] += acc[r][v];
             Vec16<T> ov;
             ov.pack(acc[r]);
             ov.store(yout + static_cast<long long>(ow) * ldy);

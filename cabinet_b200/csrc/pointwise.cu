@@ -53,10 +53,13 @@ scale_act_kernel(T* __restrict__ x, long long ldx, const float* __restrict__ sca
         float f[V];
         v.unpack(f);
         const float* sc = scale + static_cast<long long>(n) * C + cg * V;
+        if (plus_one) {
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            float s = __ldg(sc + i);
-            f[i] = plus_one ? fmaf(f[i], s, f[i]) : cab_act(f[i] * s, act);
+            for (int i = 0; i < V; ++i) f[i] = fmaf(f[i], __ldg(sc + i), f[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) f[i] *= __ldg(sc + i);
+            cab_act_vec<V>(f, act);
         }
         v.pack(f);
         v.store(ptr);

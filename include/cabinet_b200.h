@@ -40,6 +40,8 @@ const char* cabinet_last_error(void);
 int cabinet_abi_version(void);
 /* Fills SM count and compute capability of the current device. */
 int cabinet_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Kernel-development switches (bench/debug only; 0 = normal operation). Returns the previous value. */
+int cabinet_debug_flags(int flags);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense convolution + folded-BN bias + activation + residual, CUDA-core implicit GEMM
