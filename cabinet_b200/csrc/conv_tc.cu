@@ -295,7 +295,7 @@ cab_encode_tiled_fn cab_get_encode_tiled() {
 }
 
 int cab_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                       const uint32_t* box, CUtensorMapL2promotion promo) {
+                       const uint32_t* box, CUtensorMapL2promotion promo, CUtensorMapSwizzle swizzle) {
     cab_encode_tiled_fn enc = cab_get_encode_tiled();
     if (!enc) {
         cabinet_set_error("cuTensorMapEncodeTiled is unavailable (driver too old or no driver)");
@@ -310,7 +310,7 @@ int cab_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint6
         if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
     }
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         cabinet_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)",
                           static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),

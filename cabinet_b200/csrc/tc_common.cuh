@@ -140,7 +140,8 @@ cab_encode_tiled_fn cab_get_encode_tiled();
 // bf16 tensor map, rank <= 5, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides in BYTES for
 // dims 1..rank-1 (dim 0 is contiguous).
 int cab_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                       const uint32_t* box, CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+                       const uint32_t* box, CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B);
 
 namespace tc {
 // ----------------------------------------------------------------------------- TMA stores (smem -> global, bulk group)

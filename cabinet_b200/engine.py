@@ -269,9 +269,15 @@ class Engine:
         out = self.new(x.N, OH, OW, x.C)
         es = x.t.element_size()
         nbytes = x.N * x.C * (x.H * x.W + OH * OW) * es + L.w.numel() * 4
-        self._run("dwconv", L.name, nbytes, 2 * x.N * OH * OW * x.C * L.k * L.k, self.lib.cabinet_dwconv,
-                  x.ptr, x.ld, L.w.data_ptr(), L.b.data_ptr(), out.ptr, out.ld, x.dt, x.N, x.H, x.W, x.C, L.k, L.stride,
-                  OH, OW, L.act, gap.data_ptr() if gap is not None else None, self.stream)
+        flops = 2 * x.N * OH * OW * x.C * L.k * L.k
+        gp = gap.data_ptr() if gap is not None else None
+        if self.use_tc and x.dt == BF16 and x.ld % 8 == 0 and x.off % 8 == 0:
+            self._run("dwconv_tma", L.name, nbytes, flops, self.lib.cabinet_dwconv_tma, x.ptr, x.ld, L.w.data_ptr(),
+                      L.b.data_ptr(), out.ptr, out.ld, x.N, x.H, x.W, x.C, L.k, L.stride, OH, OW, L.act, gp, self.stream)
+        else:
+            self._run("dwconv", L.name, nbytes, flops, self.lib.cabinet_dwconv, x.ptr, x.ld, L.w.data_ptr(),
+                      L.b.data_ptr(), out.ptr, out.ld, x.dt, x.N, x.H, x.W, x.C, L.k, L.stride, OH, OW, L.act, gp,
+                      self.stream)
         return out
 
     def gate(self, gap: torch.Tensor, hw: int, G: GateLayer, name: str) -> torch.Tensor:

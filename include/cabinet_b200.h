@@ -95,6 +95,12 @@ int cabinet_dwconv(const void* x, long long ldx, const float* w, const float* bi
                    int dtype, int N, int H, int W, int C, int k, int stride, int OH, int OW, int act,
                    float* gap_sum, cabinet_stream_t stream);
 
+/* The same depthwise convolution for bf16 with the input patch (+halo) staged in shared memory by one TMA box per
+ * CTA (zero padding = TMA out-of-bounds fill).  Same arguments / semantics as cabinet_dwconv (bf16 only). */
+int cabinet_dwconv_tma(const void* x, long long ldx, const float* w, const float* bias, void* y, long long ldy, int N,
+                       int H, int W, int C, int k, int stride, int OH, int OW, int act, float* gap_sum,
+                       cabinet_stream_t stream);
+
 /* Squeeze-excite / FFM channel gate: scale[n][c] = gate(b2 + W2 * relu(b1 + W1 * (sum[n]/HW))).
  * Replaces src/models/mobilenetv3.py:68-83 (gate = CABINET_ACT_HSIGMOID, biases present) and
  * src/models/cabinet.py:146-150 (gate = CABINET_ACT_SIGMOID, b1 = b2 = NULL).  All fp32. */

@@ -67,7 +67,7 @@ def test_schedule_shapes_and_abi(cpu_engine, mode, C, shape, precision):
     assert final.shape == (shape[0], C, shape[2], shape[3]) and aux.shape == final.shape
     names = [c[0] for c in rec.calls]
     n_blocks = 15 if mode == "large" else 11
-    assert names.count("cabinet_dwconv") == n_blocks + 3
+    assert names.count("cabinet_dwconv") + names.count("cabinet_dwconv_tma") == n_blocks + 3
     assert names.count("cabinet_upsample_logits_nchw") == 2
     assert names.count("cabinet_psp_pool") == 2 and names.count("cabinet_softmax_rows") == 1
     assert eng.launches == len(rec.calls) + 1  # + the gap-sum memset

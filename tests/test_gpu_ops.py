@@ -329,3 +329,29 @@ def test_stem_tc(N, H, W):
     e1, e2 = rel_l2(from_map(y_sb), ref_sb), rel_l2(from_map(y_st), ref_st)
     print(f"stem_tc {N}x{H}x{W}: sb {e1:.3e} stem {e2:.3e}")
     assert e1 < 6e-3 and e2 < 6e-3
+
+
+@pytest.mark.parametrize("C,k,s,H,W,act,gap", [
+    (16, 3, 1, 13, 21, ACT_RELU, False), (64, 3, 2, 32, 32, ACT_RELU, False), (72, 5, 2, 19, 27, ACT_NONE, True),
+    (120, 5, 1, 16, 9, ACT_NONE, True), (240, 3, 2, 7, 5, ACT_HSWISH, False), (960, 5, 1, 4, 4, ACT_NONE, True),
+    (8, 3, 1, 1, 1, ACT_RELU, True), (200, 3, 1, 40, 33, ACT_HSWISH, True), (672, 5, 2, 33, 64, ACT_NONE, True),
+])
+def test_dwconv_tma(C, k, s, H, W, act, gap):
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    N = 2
+    x = q(gen(N, C, H, W, seed=1), dtype)
+    w = gen(C, 1, k, k, seed=2, scale=0.3)
+    b = gen(C, seed=3, scale=0.1)
+    p = (k - 1) // 2
+    ref = act_ref(F.conv2d(x, w, b, s, p, 1, C), act)
+    OH, OW = ref.shape[2:]
+    xm, ym = to_map(x, dtype, ld=C + 8, off=8), to_map(torch.zeros_like(ref), dtype, ld=C + 16, off=8)
+    wp, bd = w.view(C, -1).t().contiguous().cuda(), b.cuda()
+    g = torch.zeros(N, C, device="cuda") if gap else None
+    check(lib.cabinet_dwconv_tma(xm.ptr, xm.ld, wp.data_ptr(), bd.data_ptr(), ym.ptr, ym.ld, N, H, W, C, k, s, OH, OW,
+                                 act, g.data_ptr() if gap else None, stream()), "dwconv_tma")
+    torch.cuda.synchronize()
+    assert rel_l2(from_map(ym), ref) < tol(dtype)
+    if gap:
+        assert rel_l2(g.cpu(), ref.sum(dim=(2, 3))) < 1e-4
