@@ -29,7 +29,7 @@ constexpr int C_STAGE_BYTES = BLOCK_M * 128;  // one [128 rows x 64 ch] bf16 sto
 constexpr int MAX_STAGES = 8;
 constexpr int NUM_THREADS = 320;
 constexpr int B_RESIDENT_MAX = 64 * 1024;
-constexpr int SMEM_LIMIT = 225 * 1024;
+constexpr int SMEM_LIMIT = 220 * 1024;
 
 struct TcConvParams {
     int OH, OW, Cin, Cout;
@@ -61,6 +61,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int tile
     return c;
 }
 
+template <int ACT, bool HAS_RES, bool OUT_F32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
@@ -71,6 +72,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], bres_bar;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float s_bias[2][256];  // per epilogue warpgroup: bias slice of its current cout tile
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_stage_bytes = p.block_n * BLOCK_K * 2;
@@ -177,68 +179,88 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int e = (warp - 2) >> 2;
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
-        const bool leader = (warp - 2) % 4 == 0 && lane == 0;
+        const int gtid = threadIdx.x - 64 - e * 128;  // 0..127 inside the warpgroup
+        const bool leader = gtid == 0;
         uint8_t* myC = sC + e * 2 * C_STAGE_BYTES;
+        float* myBias = s_bias[e];
         uint32_t store_seq = 0;
-        int it = e;
+        int it = e, bias_n0 = -1;
         for (int tile = blockIdx.x + e * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
             const TileCoord tcd = decode_tile(p, tile);
             const int oh = tcd.oh0 + row / p.TW, ow = tcd.ow0 + row % p.TW;
             const bool valid = oh < p.OH && ow < p.OW;
             const long long pix = (static_cast<long long>(tcd.img) * p.OH + oh) * p.OW + ow;
+            if (tcd.n0 != bias_n0) {  // (re)load this cout tile's bias slice, zero padded
+                tc::named_bar_sync(1 + e, 128);  // everyone is done reading the previous slice
+                for (int i = gtid; i < p.block_n; i += 128) myBias[i] = (tcd.n0 + i < p.Cout) ? __ldg(p.bias + tcd.n0 + i) : 0.f;
+                bias_n0 = tcd.n0;
+                tc::named_bar_sync(1 + e, 128);
+            }
             tc::mbar_wait(&acc_full[e], (it >> 1) & 1);
             tc::tc_fence_after();
             const uint32_t taddr = tmem + e * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
             const int ngroups = (p.block_n + 63) >> 6;
             for (int grp = 0; grp < ngroups; ++grp) {
                 uint8_t* buf = myC + (store_seq & 1) * C_STAGE_BYTES;
-                if (p.y_dtype == CABINET_BF16) {
-                    // the TMA store that used this buffer two groups ago must have finished reading it
+                const int nch = min(4, (p.block_n - grp * 64) >> 4);  // 16-column chunks in this 64-column group
+                // issue all TMEM loads of the group, then one wait: 64 independent values per thread
+                uint32_t r[64];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < nch) tc::tmem_ld16(taddr + grp * 64 + c * 16, r + 16 * c);
+                tc::tmem_ld_wait();
+                if (grp == ngroups - 1) {
+                    // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&acc_empty[e]);
+                }
+                if constexpr (!OUT_F32) {
+                    // the TMA store that used this staging buffer two groups ago must have finished reading it
                     if (leader) tc::bulk_wait_read<1>();
                     tc::named_bar_sync(1 + e, 128);
                 }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
+                    if (c >= nch) break;
                     const int c0 = grp * 64 + c * 16;
-                    if (c0 >= p.block_n || (p.debug & 2)) break;
-                    uint32_t r[16];
-                    tc::tmem_ld16(taddr + c0, r);
-                    tc::tmem_ld_wait();
                     const int co0 = tcd.n0 + c0;
                     float v[16];
-                    if (co0 + 16 <= p.Cout) {
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co0) + j4);
-                            v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
-                            v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
-                            v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
-                            v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            v[j] = __uint_as_float(r[j]) + ((co0 + j < p.Cout) ? __ldg(p.bias + co0 + j) : 0.f);
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 b = *reinterpret_cast<const float4*>(myBias + c0 + 4 * j4);
+                        v[4 * j4 + 0] = __uint_as_float(r[16 * c + 4 * j4 + 0]) + b.x;
+                        v[4 * j4 + 1] = __uint_as_float(r[16 * c + 4 * j4 + 1]) + b.y;
+                        v[4 * j4 + 2] = __uint_as_float(r[16 * c + 4 * j4 + 2]) + b.z;
+                        v[4 * j4 + 3] = __uint_as_float(r[16 * c + 4 * j4 + 3]) + b.w;
                     }
-                    cab_act_vec<16>(v, p.act);
-                    if (p.res && valid && co0 < p.Cout) {
-                        const bf16* rp = p.res + pix * p.ldres + co0;
+                    if constexpr (ACT == CABINET_ACT_RELU) {
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            if (co0 + 8 * h + 8 <= p.Cout) {
-                                Vec16<bf16> rv;
-                                rv.load(rp + 8 * h);
-                                float rf[8];
-                                rv.unpack(rf);
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if constexpr (ACT == CABINET_ACT_HSWISH) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) v[8 * h + j] += rf[j];
-                            } else {
-                                for (int j = 0; j < 8; ++j)
-                                    if (co0 + 8 * h + j < p.Cout) v[8 * h + j] += __bfloat162float(rp[8 * h + j]);
+                        for (int j = 0; j < 16; ++j) v[j] *= __saturatef(fmaf(v[j], 1.f / 6.f, 0.5f));  // relu6(v+3)/6
+                    }
+                    if constexpr (HAS_RES) {
+                        if (valid && co0 < p.Cout) {
+                            const bf16* rp = p.res + pix * p.ldres + co0;
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                if (co0 + 8 * h + 8 <= p.Cout) {
+                                    Vec16<bf16> rv;
+                                    rv.load(rp + 8 * h);
+                                    float rf[8];
+                                    rv.unpack(rf);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[8 * h + j] += rf[j];
+                                } else {
+                                    for (int j = 0; j < 8; ++j)
+                                        if (co0 + 8 * h + j < p.Cout) v[8 * h + j] += __bfloat162float(rp[8 * h + j]);
+                                }
                             }
                         }
                     }
-                    if (p.y_dtype == CABINET_BF16) {
+                    if constexpr (!OUT_F32) {
                         Vec16<bf16> o0, o1;
                         o0.pack(v);
                         o1.pack(v + 8);
@@ -252,7 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             if (co0 + j < p.Cout) yp[j] = v[j];
                     }
                 }
-                if (p.y_dtype == CABINET_BF16) {
+                if constexpr (!OUT_F32) {
                     tc::fence_proxy_async();
                     tc::named_bar_sync(1 + e, 128);
                     if (leader && !(p.debug & 1)) {
@@ -262,10 +284,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     ++store_seq;
                 }
             }
-            // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&acc_empty[e]);
         }
         if (leader) tc::bulk_wait<0>();
     }
@@ -277,7 +295,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
 }
 
-int g_smem_attr_set = 0;
 int g_debug = 0;
 
 }  // namespace
@@ -423,10 +440,7 @@ extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W
         tmY = tmB;  // unused
     }
     const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(p.stages) * stage_bytes;
-    if (!g_smem_attr_set) {
-        CAB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT + 1024));
-        g_smem_attr_set = 1;
-    }
+
     const long long m_tiles = static_cast<long long>(Ng) * p.tiles_h * p.tiles_w;
     const long long tiles = m_tiles * p.n_tiles;
     CAB_REQUIRE(tiles < (1LL << 31), "conv_tc: too many tiles");
@@ -435,8 +449,29 @@ extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W
     CAB_CUDA(cudaGetDevice(&dev));
     CAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = static_cast<int>(std::min<long long>(tiles, sms));
-    conv_tc_kernel<<<grid, NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB,
-                                                                                   tmY, p);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CAB_TC_LAUNCH(ACT_, RES_, F32_)                                                                              \
+    do {                                                                                                             \
+        static bool attr_done = false;                                                                               \
+        if (!attr_done) {                                                                                            \
+            CAB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_, RES_, F32_>,                                          \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT + 1024));          \
+            attr_done = true;                                                                                        \
+        }                                                                                                            \
+        conv_tc_kernel<ACT_, RES_, F32_><<<grid, NUM_THREADS, smem, st>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmY, p); \
+    } while (0)
+    const bool f32 = y_dtype == CABINET_F32;
+    if (f32 && !res && act == CABINET_ACT_NONE) CAB_TC_LAUNCH(CABINET_ACT_NONE, false, true);
+    else if (!f32 && !res && act == CABINET_ACT_NONE) CAB_TC_LAUNCH(CABINET_ACT_NONE, false, false);
+    else if (!f32 && !res && act == CABINET_ACT_RELU) CAB_TC_LAUNCH(CABINET_ACT_RELU, false, false);
+    else if (!f32 && !res && act == CABINET_ACT_HSWISH) CAB_TC_LAUNCH(CABINET_ACT_HSWISH, false, false);
+    else if (!f32 && res && act == CABINET_ACT_NONE) CAB_TC_LAUNCH(CABINET_ACT_NONE, true, false);
+    else {
+        cabinet_set_error("conv_tc: unsupported epilogue combination (act %d, residual %d, fp32 out %d)", act,
+                          res != nullptr, (int)f32);
+        return CABINET_ERR_INVALID;
+    }
+#undef CAB_TC_LAUNCH
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }
