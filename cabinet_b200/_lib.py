@@ -32,10 +32,12 @@ SIGNATURES = {
     "cabinet_dwconv": ([_p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p], _i),
     "cabinet_dwconv_tma": ([_p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p], _i),
     "cabinet_gate_mlp": ([_p, _f, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),
+    "cabinet_gate_fc": ([_p, _f, _p, _p, _p, _i, _i, _i, _i, _p], _i),
     "cabinet_scale_act": ([_p, _ll, _i, _p, _i, _ll, _i, _i, _i, _p], _i),
     "cabinet_psp_pool": ([_p, _ll, _i, _p, _i, _i, _i, _i, _p], _i),
     "cabinet_psp_concat": ([_p, _ll, _p, _p, _ll, _i, _i, _i, _i, _i, _p], _i),
     "cabinet_softmax_rows": ([_p, _p, _i, _ll, _i, _p], _i),
+    "cabinet_attention_tc": ([_p, _ll, _p, _ll, _p, _ll, _p, _p, _ll, _i, _i, _i, _f, _p], _i),
     "cabinet_cab_combine": ([_p, _p, _p, _p, _ll, _p, _i, _ll, _i, _p], _i),
     "cabinet_channel_sum": ([_p, _ll, _i, _i, _ll, _i, _p, _p], _i),
     "cabinet_bilinear_nhwc": ([_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p], _i),

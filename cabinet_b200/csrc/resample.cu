@@ -42,6 +42,38 @@ bilinear_nhwc_kernel(const TI* __restrict__ x, long long ldx, TO* __restrict__ y
     }
 }
 
+// bf16 -> bf16, C % 8 == 0: one thread = one output pixel x 8 channels (four 16-byte loads, one 16-byte store)
+__global__ void __launch_bounds__(256)
+bilinear_nhwc_bf16x8_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy, int IH,
+                            int IW, int C, int OH, int OW, long long total, float sh, float sw) {
+    const int CG = C / 8;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cg = static_cast<int>(idx % CG);
+    long long t = idx / CG;
+    const int ow = static_cast<int>(t % OW);
+    t /= OW;
+    const int oh = static_cast<int>(t % OH);
+    const int n = static_cast<int>(t / OH);
+    int y0, y1, x0, x1;
+    float wy, wx;
+    cab_bilinear_tap(oh, sh, IH, y0, y1, wy);
+    cab_bilinear_tap(ow, sw, IW, x0, x1, wx);
+    const bf16* b = x + static_cast<long long>(n) * IH * IW * ldx + cg * 8;
+    Vec16<bf16> v00, v01, v10, v11, o;
+    v00.load(b + (static_cast<long long>(y0) * IW + x0) * ldx);
+    v01.load(b + (static_cast<long long>(y0) * IW + x1) * ldx);
+    v10.load(b + (static_cast<long long>(y1) * IW + x0) * ldx);
+    v11.load(b + (static_cast<long long>(y1) * IW + x1) * ldx);
+    float f00[8], f01[8], f10[8], f11[8], r[8];
+    v00.unpack(f00); v01.unpack(f01); v10.unpack(f10); v11.unpack(f11);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        r[c] = (1.f - wy) * ((1.f - wx) * f00[c] + wx * f01[c]) + wy * ((1.f - wx) * f10[c] + wx * f11[c]);
+    o.pack(r);
+    o.store(y + ((static_cast<long long>(n) * OH + oh) * OW + ow) * ldy + cg * 8);
+}
+
 // ---------------------------------------------------------------------------------- logits tail
 // Each thread produces 8 consecutive output pixels [8g, 8g+8) of one output row for ALL classes and hands them,
 // class by class, to a consumer (NCHW store / running argmax).
@@ -215,10 +247,18 @@ extern "C" int cabinet_bilinear_nhwc(const void* x, long long ldx, int x_dtype, 
     CAB_REQUIRE(x && y && IH > 0 && IW > 0 && OH > 0 && OW > 0 && C > 0 && ldx >= C && ldy >= C,
                 "bilinear_nhwc: bad arguments");
     if (N == 0) return CABINET_OK;
-    const long long total = static_cast<long long>(N) * OH * OW * ((C + 3) / 4);
-    dim3 grid(static_cast<unsigned>(cab_ceil_div(total, 256)));
     const float sh = static_cast<float>(IH) / static_cast<float>(OH), sw = static_cast<float>(IW) / static_cast<float>(OW);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (x_dtype == CABINET_BF16 && y_dtype == CABINET_BF16 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 &&
+        (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+        const long long tot8 = static_cast<long long>(N) * OH * OW * (C / 8);
+        bilinear_nhwc_bf16x8_kernel<<<static_cast<unsigned>(cab_ceil_div(tot8, 256)), 256, 0, s>>>(
+            reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(y), ldy, IH, IW, C, OH, OW, tot8, sh, sw);
+        CAB_LAUNCH_CHECK();
+        return CABINET_OK;
+    }
+    const long long total = static_cast<long long>(N) * OH * OW * ((C + 3) / 4);
+    dim3 grid(static_cast<unsigned>(cab_ceil_div(total, 256)));
 #define CAB_BL(TI, TO)                                                                                       \
     bilinear_nhwc_kernel<TI, TO><<<grid, 256, 0, s>>>(reinterpret_cast<const TI*>(x), ldx,                   \
                                                       reinterpret_cast<TO*>(y), ldy, IH, IW, C, OH, OW, total, sh, sw)

@@ -281,12 +281,16 @@ class Engine:
         return out
 
     def gate(self, gap: torch.Tensor, hw: int, G: GateLayer, name: str) -> torch.Tensor:
+        """Channel gate of SE / FFM: two batched tiny FC layers (mean -> ReLU hidden -> gate), fp32."""
+        n = gap.shape[0]
+        hidden = torch.empty((n, G.cmid), dtype=torch.float32, device=self.dev)
         scale = torch.empty_like(gap)
-        self._run("gate_mlp", name, (G.w1.numel() + G.w2.numel()) * 4, 4 * gap.shape[0] * G.c * G.cmid,
-                  self.lib.cabinet_gate_mlp, gap.data_ptr(), 1.0 / hw, G.w1.data_ptr(),
-                  G.b1.data_ptr() if G.b1 is not None else None, G.w2.data_ptr(),
-                  G.b2.data_ptr() if G.b2 is not None else None, scale.data_ptr(), gap.shape[0], G.c, G.cmid, G.gate,
-                  self.stream)
+        self._run("gate_fc", name, G.w1.numel() * 4, 2 * n * G.c * G.cmid, self.lib.cabinet_gate_fc, gap.data_ptr(),
+                  1.0 / hw, G.w1.data_ptr(), G.b1.data_ptr() if G.b1 is not None else None, hidden.data_ptr(), n, G.c,
+                  G.cmid, ACT_RELU, self.stream)
+        self._run("gate_fc", name, G.w2.numel() * 4, 2 * n * G.c * G.cmid, self.lib.cabinet_gate_fc, hidden.data_ptr(),
+                  1.0, G.w2.data_ptr(), G.b2.data_ptr() if G.b2 is not None else None, scale.data_ptr(), n, G.cmid,
+                  G.c, G.gate, self.stream)
         return scale
 
     def scale_act(self, x: Map, scale: torch.Tensor, act: int, name: str, plus_one: bool = False):
@@ -310,6 +314,13 @@ class Engine:
         N, Lq, d = q.N, q.H * q.W, q.C
         es = q.t.element_size()
         ctx = self.new(q.N, q.H, q.W, d)
+        if self.use_tc and d == 128 and q.dt == BF16 and all(m.ld % 8 == 0 and m.off % 8 == 0 for m in (q, k, v)):
+            vt = torch.empty((N, d, -(-Lq // 8) * 8), dtype=torch.bfloat16, device=self.dev)
+            self._run("attention_tc", "cab.attention", 4 * N * Lq * d * es, 4 * N * Lq * Lq * d,
+                      self.lib.cabinet_attention_tc, q.ptr, q.ld, k.ptr, k.ld, v.ptr, v.ld, vt.data_ptr(), ctx.ptr,
+                      ctx.ld, N, Lq, d, float(d) ** -0.5, self.stream)
+            self.launches += 1  # the V transpose pre-kernel
+            return ctx
         s = torch.empty((N, Lq, Lq), dtype=torch.float32, device=self.dev)
         # S[b][i][j] = alpha * sum_c q[b][i][c] k[b][j][c]   (k acts as the [Cout=L][K=d] "weights")
         self._run("conv2d_simt", "cab.qk", 2 * N * Lq * d * es, 2 * N * Lq * Lq * d, self.lib.cabinet_conv2d_simt,

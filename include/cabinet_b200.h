@@ -107,6 +107,12 @@ int cabinet_dwconv_tma(const void* x, long long ldx, const float* w, const float
 int cabinet_gate_mlp(const float* gap_sum, float inv_hw, const float* w1, const float* b1, const float* w2,
                      const float* b2, float* scale, int N, int C, int Cmid, int gate, cabinet_stream_t stream);
 
+/* One layer of that gate for the whole batch at once (each weight is read once for all images):
+ *   out[n][j] = act(b[j] + sum_c W[j][c] * in[n][c] * in_scale),  in [N][C], W [J][C], out [N][J], all fp32.
+ * The engine runs the SE / FFM gate as gate_fc(ReLU, in_scale = 1/HW) -> gate_fc(hard-sigmoid | sigmoid). */
+int cabinet_gate_fc(const float* in, float in_scale, const float* W, const float* b, float* out, int N, int C, int J,
+                    int act, cabinet_stream_t stream);
+
 /* In place: x[n][p][c] = act(x * scale[n][c])            (plus_one = 0; SE apply, mobilenetv3.py:83 + act)
  *           x[n][p][c] = x * scale[n][c] + x             (plus_one = 1; FFM, src/models/cabinet.py:152-153) */
 int cabinet_scale_act(void* x, long long ldx, int dtype, const float* scale, int N, long long HW, int C, int act,
@@ -125,6 +131,13 @@ int cabinet_psp_concat(const void* x, long long ldx, const float* pooled, void* 
 /* Row softmax, in place semantics split: s [rows][cols] fp32 (already scaled) -> p [rows][cols] (dtype).
  * Replaces F.softmax(attn, dim=-1) at src/models/cab.py:151 in the fp32 parity mode. */
 int cabinet_softmax_rows(const float* s, void* p, int p_dtype, long long rows, int cols, cabinet_stream_t stream);
+
+/* Fused attention on the tensor cores: ctx[n] = softmax(q[n] k[n]^T * scale) v[n]  (src/models/cab.py:149-153) for
+ * bf16 q, k, v [N][L][128] (row strides ld*), never materialising the L x L scores.  vt_workspace: bf16
+ * [N][128][ceil8(L)] scratch for the transposed values.  ctx: bf16 [N][L][128] (row stride ldc). */
+int cabinet_attention_tc(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                         void* vt_workspace, void* ctx, long long ldc, int N, int L, int d, float scale,
+                         cabinet_stream_t stream);
 
 /* out[p][0:C] = gamma * g + x + x * sigmoid(r)   (src/models/cab.py:182-184,213-216).  g, x, r are dense
  * [n_pixels][C]; out has pixel stride ldo (it is written straight into the b1 concat buffer,

@@ -69,8 +69,9 @@ def test_schedule_shapes_and_abi(cpu_engine, mode, C, shape, precision):
     n_blocks = 15 if mode == "large" else 11
     assert names.count("cabinet_dwconv") + names.count("cabinet_dwconv_tma") == n_blocks + 3
     assert names.count("cabinet_upsample_logits_nchw") == 2
-    assert names.count("cabinet_psp_pool") == 2 and names.count("cabinet_softmax_rows") == 1
-    assert eng.launches == len(rec.calls) + 1  # + the gap-sum memset
+    assert names.count("cabinet_psp_pool") == 2 and names.count("cabinet_softmax_rows") + names.count("cabinet_attention_tc") == 1
+    extra = 1 + names.count("cabinet_attention_tc")  # the gap-sum memset (+ the V transpose inside attention_tc)
+    assert eng.launches == len(rec.calls) + extra
     rec.calls.clear()
     mask = eng.forward_mask(x)
     assert mask.shape == (shape[0], shape[2], shape[3]) and mask.dtype == torch.uint8

@@ -355,3 +355,37 @@ def test_dwconv_tma(C, k, s, H, W, act, gap):
     assert rel_l2(from_map(ym), ref) < tol(dtype)
     if gap:
         assert rel_l2(g.cpu(), ref.sum(dim=(2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("N,C,J,act,bias", [(16, 960, 240, ACT_RELU, True), (3, 72, 24, ACT_HSIGMOID, True),
+                                             (19, 64, 256, ACT_SIGMOID, False), (1, 8, 8, ACT_NONE, True)])
+def test_gate_fc(N, C, J, act, bias):
+    lib = _lib.load()
+    x, W = gen(N, C, seed=1), gen(J, C, seed=2, scale=C ** -0.5)
+    b = gen(J, seed=3, scale=0.2) if bias else None
+    ref = act_ref(F.linear(x * 0.25, W, b), act)
+    xd, Wd, bd = x.cuda(), W.cuda(), (b.cuda() if bias else None)
+    out = torch.empty(N, J, device="cuda")
+    check(lib.cabinet_gate_fc(xd.data_ptr(), 0.25, Wd.data_ptr(), bd.data_ptr() if bias else None, out.data_ptr(), N, C,
+                              J, act, stream()), "gate_fc")
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("N,L", [(2, 1024), (3, 12), (1, 300), (2, 128), (1, 2040)])
+def test_attention_tc(N, L):
+    """Fused tcgen05 attention vs softmax(q k^T / sqrt(d)) v in fp32 (bf16-rounded inputs)."""
+    lib = _lib.load()
+    d = 128
+    bf = torch.bfloat16
+    qf, kf, vf = (q(gen(N, L, d, seed=i, scale=s), bf) for i, s in ((1, 1.0), (2, 1.5), (3, 1.0)))
+    ref = torch.softmax(qf @ kf.transpose(1, 2) * d ** -0.5, dim=-1) @ vf
+    qd, kd, vd = (t.to("cuda", bf).contiguous() for t in (qf, kf, vf))
+    vt = torch.empty(N, d, (L + 7) // 8 * 8, dtype=bf, device="cuda")
+    ctx = torch.zeros(N, L, d, dtype=bf, device="cuda")
+    check(lib.cabinet_attention_tc(qd.data_ptr(), d, kd.data_ptr(), d, vd.data_ptr(), d, vt.data_ptr(), ctx.data_ptr(),
+                                   d, N, L, d, d ** -0.5, stream()), "attention_tc")
+    torch.cuda.synchronize()
+    err = rel_l2(ctx.float().cpu(), ref)
+    print(f"attention_tc N={N} L={L}: rel_l2 {err:.3e}")
+    assert err < 8e-3  # P is rounded to bf16 before the P V product (like the reference under bf16 autocast)
