@@ -131,6 +131,9 @@ class Engine:
         self.debug = False
         self.stages = {}
         self.trace, self.trace_filter = None, None
+        self.use_cuda_graph = False
+        self.sub_batch = 0          # > 0: run the schedule over chunks of this many images
+        self._graphs = {}
         with torch.no_grad():
             self._pack(model)
 
@@ -432,21 +435,59 @@ class Engine:
                                final8=final8, aux8=aux8)
         return final8, aux8
 
-    @torch.no_grad()
-    def forward(self, x, out_dtype=torch.float32):
-        """-> (final_logit, high_res_logit_up) NCHW (reference: cabinet.py:240-247)."""
+    def _logits(self, x, outs, odt):
+        """Trunk + the two x8 upsamples, written into rows of the preallocated NCHW outputs."""
         N, _, H, W = x.shape
         final8, aux8 = self._trunk(x)
-        odt = BF16 if out_dtype == torch.bfloat16 else F32
-        tdt = torch.bfloat16 if odt == BF16 else torch.float32
-        outs = []
-        for name, src in (("final_up", final8), ("aux_up", aux8)):
-            y = torch.empty((N, self.n_classes, H, W), dtype=tdt, device=self.dev)
+        for name, src, y in (("final_up", final8, outs[0]), ("aux_up", aux8, outs[1])):
             nbytes = src.t.numel() * 4 + y.numel() * y.element_size()
             self._run("upsample_logits_nchw", name, nbytes, 0, self.lib.cabinet_upsample_logits_nchw, src.ptr, N,
                       src.H, src.W, src.C, y.data_ptr(), odt, H, W, self.stream)
-            outs.append(y)
+
+    def _forward_eager(self, x, out_dtype):
+        N, _, H, W = x.shape
+        odt = BF16 if out_dtype == torch.bfloat16 else F32
+        tdt = torch.bfloat16 if odt == BF16 else torch.float32
+        outs = [torch.empty((N, self.n_classes, H, W), dtype=tdt, device=self.dev) for _ in range(2)]
+        chunk = self.sub_batch if self.sub_batch and self.sub_batch < N else N
+        launches = 0
+        for i in range(0, N, chunk):  # images are independent units: optional L2-sized sub-batches
+            self._logits(x[i:i + chunk], [o[i:i + chunk] for o in outs], odt)
+            launches += self.launches
+        self.launches = launches
         return outs[0], outs[1]
+
+    @torch.no_grad()
+    def forward(self, x, out_dtype=torch.float32):
+        """-> (final_logit, high_res_logit_up) NCHW (reference: cabinet.py:240-247).
+
+        With ``use_cuda_graph`` the whole kernel schedule of a given input shape is captured once and replayed; the
+        returned tensors are then the graph's static output buffers (overwritten by the next call of that shape)."""
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        if not self.use_cuda_graph or self.trace is not None or self.debug:
+            return self._forward_eager(x, out_dtype)
+        key = (tuple(x.shape), out_dtype, self.sub_batch)
+        g = self._graphs.get(key)
+        if g is None:
+            static_x = x.clone()
+            cur = torch.cuda.current_stream(self.dev)
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # warm-up outside capture (lazy function attributes, allocator)
+                self._forward_eager(static_x, out_dtype)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = self._forward_eager(static_x, out_dtype)
+            g = (graph, static_x, outs, self.launches)
+            self._graphs[key] = g
+        graph, static_x, outs, launches = g
+        if x.data_ptr() != static_x.data_ptr():
+            static_x.copy_(x, non_blocking=True)
+        graph.replay()
+        self.launches = launches
+        return outs
 
     def _argmax(self, final8: Map, N, H, W, labels=None, hist=None, ignore_label=255):
         mask = torch.empty((N, H, W), dtype=torch.uint8, device=self.dev)

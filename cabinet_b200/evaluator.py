@@ -1,0 +1,135 @@
+"""Device-resident mirror of the reference evaluator ``MscEvalV0`` (``src/scripts/evaluate.py:32-256``).
+
+Same constructor and result dict.  Differences, all on the hot-path side of the boundary:
+  * the confusion matrix is an int64 (C, C) tensor that lives on the device (the reference keeps float64 on the
+    CPU and ships an int64 mask over PCIe per image); counts are integers < 2^53 so the values are identical;
+  * the fast mode (``scales=(1.0,)``, ``flip=False``, image not larger than the crop) is ONE fused call per batch:
+    forward -> bilinear x8 -> argmax -> ``hist[pred, label]`` (``CABiNet.accumulate_hist``), logits never reach HBM;
+  * the general mode (multi-scale / flip / sliding window) follows the reference step by step on the device and
+    finishes with the ``cabinet_confusion_hist`` kernel;
+  * under ``torch.distributed`` every rank evaluates its own shard of the loader and the histograms are
+    all-reduced once (the reference: ``dist.reduce(dst=0)``, ``evaluate.py:230-235``); every rank gets the result.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .constants import EVAL_STRIDE_RATE
+
+try:
+    import torch.distributed as dist
+except ImportError:  # pragma: no cover
+    dist = None
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous, balanced split of ``n_items`` units over ``world`` ranks (first ranks take the remainder)."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def reduce_hist(hist: torch.Tensor) -> torch.Tensor:
+    """Sum the per-rank int64 confusion matrices (no-op without an initialised process group)."""
+    if dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    return hist
+
+
+def metrics_from_hist(hist) -> Dict[str, Any]:
+    """IoU / accuracy tail (reference: evaluate.py:239-251), float64 on the host."""
+    h = hist.detach().cpu().numpy().astype(np.float64) if isinstance(hist, torch.Tensor) else np.asarray(hist, np.float64)
+    ious = np.diag(h) / (h.sum(axis=0) + h.sum(axis=1) - np.diag(h) + 1e-8)
+    return {"mIoU": np.nanmean(ious), "accuracy": np.diag(h).sum() / h.sum(),
+            "iou_per_class": {f"class_{i}": ious[i] for i in range(len(ious))}, "confusion_matrix": h}
+
+
+class MscEvalV0:
+    def __init__(self, model, dataloader, n_classes: int, ignore_label: int = 255, scales: Sequence[float] = (1.0,),
+                 flip: bool = False, cropsize: int = 1024, device: torch.device = None):
+        self.model, self.dl, self.n_classes, self.ignore_label = model, dataloader, n_classes, ignore_label
+        self.scales, self.flip, self.cropsize = tuple(scales), flip, cropsize
+        self.device = device or next(model.parameters()).device
+
+    # ---- general mode: the reference algorithm, tensors stay on the device
+    def eval_chip(self, crop):
+        prob = F.softmax(self.model(crop)[0].float(), dim=1)
+        if self.flip:
+            fl = self.model(torch.flip(crop, dims=(3,)).contiguous())[0].float()
+            prob = (prob + F.softmax(torch.flip(fl, dims=(3,)), dim=1)) * 0.5
+        return prob
+
+    def crop_eval(self, image):
+        cs = self.cropsize
+        N, _, H, W = image.shape
+        indices = None
+        if H < cs or W < cs:  # centre zero-pad (reference: evaluate.py:60-72,102-111)
+            tgt = (cs, cs) if max(H, W) < cs else (cs if H < W else H, cs if W < H else W)
+            ph, pw = max(tgt[0] - H, 0), max(tgt[1] - W, 0)
+            padded = torch.zeros(N, 3, tgt[0], tgt[1], device=image.device)
+            padded[:, :, ph // 2: ph // 2 + H, pw // 2: pw // 2 + W] = image
+            indices, image = (ph // 2, ph // 2 + H, pw // 2, pw // 2 + W), padded
+        fh, fw = image.shape[2:]
+        prob = torch.zeros((N, self.n_classes, fh, fw), device=image.device)
+        count = torch.zeros((1, 1, fh, fw), device=image.device)
+        if fh < cs or fw < cs:
+            prob += self.eval_chip(image)
+            count += 1
+        else:
+            stride = int(cs * EVAL_STRIDE_RATE)
+            for iy in range(math.ceil((fh - cs) / stride) + 1):
+                for ix in range(math.ceil((fw - cs) / stride) + 1):
+                    y1, x1 = min(fh, stride * iy + cs), min(fw, stride * ix + cs)
+                    prob[:, :, y1 - cs:y1, x1 - cs:x1] += self.eval_chip(image[:, :, y1 - cs:y1, x1 - cs:x1].contiguous())
+                    count[:, :, y1 - cs:y1, x1 - cs:x1] += 1
+        prob = prob / count.clamp(min=1)
+        if indices is not None:
+            prob = prob[:, :, indices[0]:indices[1], indices[2]:indices[3]]
+        return prob
+
+    def scale_crop_eval(self, image, scale):
+        H, W = image.shape[2:]
+        scaled = F.interpolate(image, [int(H * scale), int(W * scale)], mode="bilinear", align_corners=False)
+        return F.interpolate(self.crop_eval(scaled), (H, W), mode="bilinear", align_corners=False)
+
+    def _hist_from_preds(self, preds, labels, hist):
+        from . import _lib
+
+        lib = _lib.load()
+        preds, labels = preds.contiguous(), labels.contiguous()
+        _lib.check(lib.cabinet_confusion_hist(preds.data_ptr(), 0 if preds.dtype == torch.int64 else 1, labels.data_ptr(),
+                                              0 if labels.dtype == torch.int64 else 1, preds.numel(), self.n_classes,
+                                              self.ignore_label, hist.data_ptr(),
+                                              torch.cuda.current_stream(hist.device).cuda_stream), "confusion_hist")
+
+    @torch.no_grad()
+    def evaluate(self) -> Dict[str, Any]:
+        self.model.eval()
+        dev = next(self.model.parameters()).device
+        hist = torch.zeros((self.n_classes, self.n_classes), dtype=torch.int64, device=dev)
+        fast = self.scales == (1.0,) and not self.flip and hasattr(self.model, "accumulate_hist")
+        for images, labels in self.dl:
+            images = images.to(dev, non_blocking=True)
+            labels = labels.to(dev, non_blocking=True)
+            if labels.dim() == 4:
+                labels = labels.squeeze(1)
+            if labels.dtype not in (torch.int64, torch.uint8):
+                labels = labels.long()
+            H, W = images.shape[2:]
+            if fast and H == self.cropsize and W == self.cropsize:  # one chip == the image: argmax(softmax) == argmax
+                self.model.accumulate_hist(images.float().contiguous(), labels.contiguous(), hist, self.ignore_label)
+                continue
+            probs = torch.zeros((images.size(0), self.n_classes, H, W), device=dev)
+            for s in self.scales:
+                probs += self.scale_crop_eval(images.float(), s)
+            self._hist_from_preds(torch.argmax(probs, dim=1), labels, hist)
+        reduce_hist(hist)
+        return metrics_from_hist(hist)
+
+    __call__ = evaluate

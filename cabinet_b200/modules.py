@@ -254,6 +254,7 @@ class CABiNet(nn.Module):
     Extra (non-reference) knobs, all attributes so the constructor stays identical:
       ``precision``     "bf16" (tcgen05 path, default) or "fp32" (CUDA-core parity mode)
       ``logits_dtype``  dtype of the two returned NCHW logit tensors (default fp32 like the reference)
+      ``use_cuda_graph`` / ``sub_batch``  replay a captured schedule / process the batch in L2-sized chunks
     """
 
     def __init__(self, n_classes: int, backbone_weights: Optional[Path] = None, cfgs=None, mode="large"):
@@ -274,6 +275,8 @@ class CABiNet(nn.Module):
         self.conv_out = CABiNetOutput(256, 256, n_classes)
         self.precision = "bf16"
         self.logits_dtype = torch.float32
+        self.use_cuda_graph = False  # replay a captured kernel schedule per input shape (static output buffers)
+        self.sub_batch = 0           # > 0: run the schedule over chunks of this many images (L2-resident activations)
         self.__dict__["_engine"] = None
 
     # ------------------------------------------------------------------ engine plumbing
@@ -290,6 +293,7 @@ class CABiNet(nn.Module):
             eng = Engine(self, precision=self.precision)
             eng.stamp = stamp
             self.__dict__["_engine"] = eng
+        eng.use_cuda_graph, eng.sub_batch = bool(self.use_cuda_graph), int(self.sub_batch)
         return eng
 
     def repack(self):
