@@ -108,12 +108,67 @@ class MscEvalV0:
                                               self.ignore_label, hist.data_ptr(),
                                               torch.cuda.current_stream(hist.device).cuda_stream), "confusion_hist")
 
+    def _fast_pipelined(self, dev, hist, masks_out=None):
+        """Fast mode over the whole loader with host->device copies one batch ahead of the fused forward.
+
+        Two device buffer sets; a copy stream uploads batch i+1 while the compute stream runs batch i
+        (forward + x8 upsample + argmax + confusion matrix in one fused tail).  ``masks_out``: optional list that
+        receives a pinned uint8 host tensor per batch (asynchronous D2H, valid after the final synchronise)."""
+        cur = torch.cuda.current_stream(dev)
+        copy_stream = torch.cuda.Stream(dev)
+        bufs, ready, consumed = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None, None]
+        n_batches = 0
+        for i, (images, labels) in enumerate(self.dl):
+            b = i & 1
+            if labels.dim() == 4:
+                labels = labels.squeeze(1)
+            if labels.dtype not in (torch.int64, torch.uint8):
+                labels = labels.long()
+            H, W = images.shape[2:]
+            if H != self.cropsize or W != self.cropsize:
+                raise ValueError("fast pipelined mode needs images of exactly cropsize x cropsize")
+            if bufs[b] is None or bufs[b][0].shape != images.shape or bufs[b][1].dtype != labels.dtype:
+                bufs[b] = (torch.empty(images.shape, dtype=torch.float32, device=dev),
+                           torch.empty(labels.shape, dtype=labels.dtype, device=dev))
+                # the caching allocator may hand out memory that kernels already queued on the compute stream
+                # still touch: order the copy stream after them, and tell the allocator about the second stream
+                copy_stream.wait_stream(cur)
+                for t in bufs[b]:
+                    t.record_stream(copy_stream)
+            with torch.cuda.stream(copy_stream):
+                if consumed[b] is not None:
+                    copy_stream.wait_event(consumed[b])  # the forward that last read this buffer set is done
+                bufs[b][0].copy_(images, non_blocking=True)
+                bufs[b][1].copy_(labels, non_blocking=True)
+                ready[b].record(copy_stream)
+            cur.wait_event(ready[b])
+            mask = self.model.accumulate_hist(bufs[b][0], bufs[b][1], hist, self.ignore_label)
+            if masks_out is not None:
+                host = torch.empty(mask.shape, dtype=torch.uint8, pin_memory=True) if len(masks_out) <= i else masks_out[i]
+                host.copy_(mask, non_blocking=True)
+                if len(masks_out) <= i:
+                    masks_out.append(host)
+            consumed[b] = torch.cuda.Event()
+            consumed[b].record(cur)
+            n_batches += 1
+        return n_batches
+
     @torch.no_grad()
-    def evaluate(self) -> Dict[str, Any]:
+    def evaluate(self, masks_out=None) -> Dict[str, Any]:
         self.model.eval()
         dev = next(self.model.parameters()).device
         hist = torch.zeros((self.n_classes, self.n_classes), dtype=torch.int64, device=dev)
         fast = self.scales == (1.0,) and not self.flip and hasattr(self.model, "accumulate_hist")
+        if fast and getattr(self, "pipelined", True):
+            try:
+                first = next(iter(self.dl))
+                uniform = first[0].shape[2] == self.cropsize and first[0].shape[3] == self.cropsize
+            except StopIteration:
+                uniform = False
+            if uniform:
+                self._fast_pipelined(dev, hist, masks_out)
+                reduce_hist(hist)
+                return metrics_from_hist(hist)
         for images, labels in self.dl:
             images = images.to(dev, non_blocking=True)
             labels = labels.to(dev, non_blocking=True)
