@@ -10,11 +10,15 @@
 // With that order one 16-byte A chunk (8 bf16) is 8 CONSECUTIVE input floats of one image row, so the im2col
 // build is 4 LDS.64 + 4 packs + 1 STS.128 per chunk, written directly in the SWIZZLE_128B K-major UMMA layout.
 //
-// Persistent, warp specialised (320 threads):
+// The folded-BN bias rides in the GEMM: K slots 168/169 of A hold 1.0 and the matching weight columns hold the bias
+// split into bf16 hi + lo parts (fp32-accurate to 2^-17), so the epilogue is activation + pack only.
+//
+// Persistent, warp specialised (448 threads):
 //   warp 0      TMA producer: weights once; per tile one 3-D fp32 box {40 cols, 21 rows, 3 ch} (OOB = zero padding)
 //   warp 1      TMEM allocator + MMA issuer: 12 x tcgen05.mma (M128 N80 K16) per tile, 2 accumulator stages
-//   warps 2-5   converters: fp32 window -> bf16 im2col A tile in shared memory (2 stages), fence.proxy.async
-//   warps 6-9   epilogue: tcgen05.ld, +bias, ReLU (cols 0-63) / HardSwish (cols 64-79), bf16 NHWC stores
+//   warps 2-9   converters (2 threads per A row): fp32 window -> bf16 im2col A tile in shared memory (2 stages)
+//   warps 10-13 epilogue: tcgen05.ld (80 columns at once), ReLU (cols 0-63) / HardSwish (cols 64-79), bf16 pack,
+//               swizzled smem staging, two TMA stores per tile (sb 64 ch, stem 16 ch)
 #include "tc_common.cuh"
 
 namespace {
@@ -32,16 +36,14 @@ constexpr int NOUT = 80;                              // 64 + 16
 constexpr int W_KB_BYTES = NOUT * 128;                // 10240
 constexpr int ACC_STAGES = 2;
 constexpr int ACC_COLS = 128;                         // TMEM columns per accumulator stage (80 used)
-constexpr int NUM_THREADS = 320;
-constexpr int SMEM_BYTES = KBLOCKS * W_KB_BYTES + A_STAGES * A_STAGE_BYTES + WIN_STAGES * WIN_STRIDE + 1024;
+constexpr int NUM_THREADS = 448;
+constexpr int CSB_BYTES = 128 * 128;                  // staged [128 px x 64 ch] bf16 (swizzled)
+constexpr int CST_BYTES = 128 * 32;                   // staged [128 px x 16 ch] bf16 (dense)
+constexpr int SMEM_BYTES =
+    KBLOCKS * W_KB_BYTES + A_STAGES * A_STAGE_BYTES + WIN_STAGES * WIN_STRIDE + 2 * (CSB_BYTES + CST_BYTES) + 1024;
 
 struct StemParams {
     int N, OH, OW, tiles_w, tiles_h, num_tiles;
-    const float* bias;
-    bf16* y_sb;
-    long long ld_sb;
-    bf16* y_stem;
-    long long ld_stem;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -50,7 +52,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const StemParams p) {
+stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmYsb, const __grid_constant__ CUtensorMap tmYst, const StemParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t w_bar, win_full[WIN_STAGES], win_empty[WIN_STAGES], a_full[A_STAGES],
         a_empty[A_STAGES], acc_full[ACC_STAGES], acc_empty[ACC_STAGES];
@@ -60,19 +63,23 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     uint8_t* sW = smem;                                    // 3 x [80 x 64] bf16, swizzled
     uint8_t* sA = sW + KBLOCKS * W_KB_BYTES;               // 2 x 3 x [128 x 64] bf16, swizzled (30720 = 30 x 1024)
     uint8_t* sWin = sA + A_STAGES * A_STAGE_BYTES;         // 3 x [3][21][40] fp32
+    uint8_t* sCsb = sWin + WIN_STAGES * WIN_STRIDE;        // 2 x staged sb output (1024-aligned: 30720 = 30 x 1024)
+    uint8_t* sCst = sCsb + 2 * CSB_BYTES;                  // 2 x staged stem output
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         tc::prefetch_tmap(&tmX);
         tc::prefetch_tmap(&tmW);
+        tc::prefetch_tmap(&tmYsb);
+        tc::prefetch_tmap(&tmYst);
         tc::mbar_init(&w_bar, 1);
         for (int s = 0; s < WIN_STAGES; ++s) {
             tc::mbar_init(&win_full[s], 1);
-            tc::mbar_init(&win_empty[s], 4);
+            tc::mbar_init(&win_empty[s], 8);
         }
         for (int s = 0; s < A_STAGES; ++s) {
-            tc::mbar_init(&a_full[s], 4);
+            tc::mbar_init(&a_full[s], 8);
             tc::mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < ACC_STAGES; ++s) {
@@ -134,15 +141,20 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
         }
         __syncwarp();
-    } else if (warp < 6) {
-        // ================= converters: fp32 window -> swizzled bf16 im2col =================
-        const int r = (warp - 2) * 32 + lane;  // A row = output pixel of the patch
+    } else if (warp < 10) {
+        // ================= converters: fp32 window -> swizzled bf16 im2col (2 threads per A row) =================
+        const int ct = threadIdx.x - 64;       // 0..255
+        const int r = ct & 127, half = ct >> 7;  // A row = output pixel of the patch; half = which chunks
         const int oy = r / TW, ox = r % TW;
-        // chunks 21..23 of K-block 2 are K padding: zero them once in both stages (weights there are zero too)
-        for (int as = 0; as < A_STAGES; ++as)
-            for (int cc = 5; cc < 8; ++cc)
-                *reinterpret_cast<uint4*>(sA + as * A_STAGE_BYTES + 2 * A_KB_BYTES + r * 128 + ((cc ^ (r & 7)) << 4)) =
-                    make_uint4(0, 0, 0, 0);
+        if (half == 0) {
+            // K padding chunks 21..23 of K-block 2 never change: chunk 21 = {1, 1, 0...} (the two bias slots), rest 0
+            for (int as = 0; as < A_STAGES; ++as) {
+                uint8_t* kb2 = sA + as * A_STAGE_BYTES + 2 * A_KB_BYTES + r * 128;
+                *reinterpret_cast<uint4*>(kb2 + ((5 ^ (r & 7)) << 4)) = make_uint4(0x3F803F80u, 0, 0, 0);
+                *reinterpret_cast<uint4*>(kb2 + ((6 ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(kb2 + ((7 ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+            }
+        }
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int ws = it % WIN_STAGES, as = it % A_STAGES;
@@ -152,7 +164,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             const float* win = reinterpret_cast<const float*>(sWin + ws * WIN_STRIDE);
             uint8_t* arow = sA + as * A_STAGE_BYTES + r * 128;
 #pragma unroll
-            for (int j = 0; j < 21; ++j) {  // j = c*7 + ky
+            for (int jj = 0; jj < 11; ++jj) {  // j = c*7 + ky; this thread takes j = half, half+2, ...
+                const int j = 2 * jj + half;
+                if (j >= 21) break;
                 const int c = j / 7, ky = j % 7;
                 const float2* src = reinterpret_cast<const float2*>(win + (c * WIN_H + 2 * oy + ky) * WIN_W + 2 * ox);
                 const float2 f0 = src[0], f1 = src[1], f2 = src[2], f3 = src[3];
@@ -172,42 +186,61 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         // ================= epilogue =================
         const int q = warp & 3;
         const int r = q * 32 + lane;
-        const int oy = r / TW, ox = r % TW;
+        const bool leader = warp == 10 && lane == 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int cs = it % ACC_STAGES;
             const uint32_t cph = (it / ACC_STAGES) & 1;
             const int img = tile / tiles_per_img, rr = tile - img * tiles_per_img;
-            const int oh = (rr / p.tiles_w) * TH + oy, ow = (rr % p.tiles_w) * TW + ox;
-            const bool valid = oh < p.OH && ow < p.OW;
-            const long long pix = (static_cast<long long>(img) * p.OH + oh) * p.OW + ow;
+            const int oh0 = (rr / p.tiles_w) * TH, ow0 = (rr % p.tiles_w) * TW;
+            uint8_t* bsb = sCsb + (it & 1) * CSB_BYTES;
+            uint8_t* bst = sCst + (it & 1) * CST_BYTES;
             tc::mbar_wait(&acc_full[cs], cph);
             tc::tc_fence_after();
             const uint32_t taddr = tmem + cs * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll
-            for (int c0 = 0; c0 < NOUT; c0 += 16) {
-                uint32_t acc[16];
-                tc::tmem_ld16(taddr + c0, acc);
-                tc::tmem_ld_wait();
-                if (valid) {
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float t = __uint_as_float(acc[j]) + __ldg(p.bias + c0 + j);
-                        v[j] = c0 < 64 ? fmaxf(t, 0.f) : t * (fminf(fmaxf(t + 3.f, 0.f), 6.f) / 6.f);
-                    }
-                    bf16* dst = c0 < 64 ? p.y_sb + pix * p.ld_sb + c0 : p.y_stem + pix * p.ld_stem + (c0 - 64);
-                    Vec16<bf16> o0, o1;
-                    o0.pack(v);
-                    o1.pack(v + 8);
-                    o0.store(dst);
-                    o1.store(dst + 8);
-                }
-            }
+            uint32_t a0[32], a1[32], a2[16];
+            tc::tmem_ld32(taddr, a0);
+            tc::tmem_ld32(taddr + 32, a1);
+            tc::tmem_ld16(taddr + 64, a2);
+            tc::tmem_ld_wait();
             tc::tc_fence_before();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&acc_empty[cs]);
+            if (lane == 0) tc::mbar_arrive(&acc_empty[cs]);   // accumulator stage is free again
+            // the stores that used this staging pair two tiles ago must have finished reading it
+            if (leader) tc::bulk_wait_read<1>();
+            tc::named_bar_sync(1, 128);
+            uint8_t* rowp = bsb + r * 128;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {  // 8 channels (16 bytes) per chunk, ReLU
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    v[j] = fmaxf(__uint_as_float(g < 4 ? a0[8 * g + j] : a1[8 * (g - 4) + j]), 0.f);
+                Vec16<bf16> o;
+                o.pack(v);
+                *reinterpret_cast<uint4*>(rowp + ((g ^ (r & 7)) << 4)) = o.raw;
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {  // backbone stem: HardSwish
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float t = __uint_as_float(a2[8 * g + j]);
+                    v[j] = t * __saturatef(fmaf(t, 1.f / 6.f, 0.5f));
+                }
+                Vec16<bf16> o;
+                o.pack(v);
+                *reinterpret_cast<uint4*>(bst + r * 32 + g * 16) = o.raw;
+            }
+            tc::fence_proxy_async();
+            tc::named_bar_sync(1, 128);
+            if (leader) {
+                tc::tma_store_4d(&tmYsb, bsb, 0, ow0, oh0, img);
+                tc::tma_store_4d(&tmYst, bst, 0, ow0, oh0, img);
+                tc::bulk_commit();
+            }
         }
+        if (leader) tc::bulk_wait<0>();
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -221,10 +254,10 @@ int g_attr_set = 0;
 
 }  // namespace
 
-extern "C" int cabinet_stem_tc(const float* x, int N, int H, int W, const void* w_packed, const float* bias,
+extern "C" int cabinet_stem_tc(const float* x, int N, int H, int W, const void* w_packed, const float* /*bias: folded*/,
                                void* y_sb, long long ld_sb, void* y_stem, long long ld_stem, int OH, int OW,
                                cabinet_stream_t stream) {
-    CAB_REQUIRE(x && w_packed && bias && y_sb && y_stem, "stem_tc: null pointer");
+    CAB_REQUIRE(x && w_packed && y_sb && y_stem, "stem_tc: null pointer");
     CAB_REQUIRE(N >= 0 && H > 0 && W > 0 && W % 4 == 0, "stem_tc: W must be a multiple of 4 (TMA row pitch)");
     CAB_REQUIRE(OH == (H - 1) / 2 + 1 && OW == (W - 1) / 2 + 1, "stem_tc: inconsistent output size");
     CAB_REQUIRE(ld_sb >= 64 && ld_sb % 8 == 0 && ld_stem >= 16 && ld_stem % 8 == 0 &&
@@ -263,9 +296,20 @@ extern "C" int cabinet_stem_tc(const float* x, int N, int H, int W, const void* 
     const long long nt = static_cast<long long>(N) * p.tiles_w * p.tiles_h;
     CAB_REQUIRE(nt < (1LL << 31), "stem_tc: too many tiles");
     p.num_tiles = static_cast<int>(nt);
-    p.bias = bias;
-    p.y_sb = reinterpret_cast<bf16*>(y_sb); p.ld_sb = ld_sb;
-    p.y_stem = reinterpret_cast<bf16*>(y_stem); p.ld_stem = ld_stem;
+    CUtensorMap tmYsb, tmYst;
+    {
+        const uint64_t dsb[4] = {64, (uint64_t)OW, (uint64_t)OH, (uint64_t)N};
+        const uint64_t ssb[3] = {(uint64_t)ld_sb * 2, (uint64_t)ld_sb * 2 * OW, (uint64_t)ld_sb * 2 * OW * OH};
+        const uint32_t bsb[4] = {64, TW, TH, 1};
+        int rc = cab_make_tmap_bf16(&tmYsb, y_sb, 4, dsb, ssb, bsb);
+        if (rc) return rc;
+        const uint64_t dst[4] = {16, (uint64_t)OW, (uint64_t)OH, (uint64_t)N};
+        const uint64_t sst[3] = {(uint64_t)ld_stem * 2, (uint64_t)ld_stem * 2 * OW, (uint64_t)ld_stem * 2 * OW * OH};
+        const uint32_t bst[4] = {16, TW, TH, 1};
+        rc = cab_make_tmap_bf16(&tmYst, y_stem, 4, dst, sst, bst, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+    }
     if (!g_attr_set) {
         CAB_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         g_attr_set = 1;
@@ -274,7 +318,7 @@ extern "C" int cabinet_stem_tc(const float* x, int N, int H, int W, const void* 
     CAB_CUDA(cudaGetDevice(&dev));
     CAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = static_cast<int>(std::min<long long>(nt, sms));
-    stem_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmX, tmW, p);
+    stem_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmX, tmW, tmYsb, tmYst, p);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

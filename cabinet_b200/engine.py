@@ -174,7 +174,10 @@ class Engine:
             self.stem_tc = (pk.reshape(80, 168).contiguous(), torch.cat([b7, b3]).contiguous())
             wk = torch.zeros((80, 192), dtype=torch.float32, device=w7.device)
             wk[:, :168] = self.stem_tc[0]
-            self.stem_tc = (wk.to(torch.bfloat16).contiguous(), self.stem_tc[1])
+            bias = self.stem_tc[1]
+            b_hi = bias.to(torch.bfloat16).float()
+            wk[:, 168], wk[:, 169] = b_hi, bias - b_hi  # bias rides in two spare K slots (A feeds 1.0 there)
+            self.stem_tc = (wk.to(torch.bfloat16).contiguous(), bias)
         self.sb1 = ConvLayer(sb.conv1.conv, sb.conv1.bn, ACT_RELU, f32, "sb.conv1")
         self.sb2 = ConvLayer(sb.conv2.conv, sb.conv2.bn, ACT_RELU, wd, "sb.conv2")
         self.sb3 = ConvLayer(sb.conv3.conv, sb.conv3.bn, ACT_RELU, wd, "sb.conv3")

@@ -80,7 +80,8 @@ int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W, int Cin, 
  * and the backbone stem (3x3 s2 p1, 3->16, BN, HardSwish; src/models/mobilenetv3.py:86-91,173) read the fp32 NCHW
  * image x [N][3][H][W] once (W % 4 == 0) and write their bf16 NHWC outputs.  w_packed: bf16 [80][192] with
  * k = (c*7 + ky)*8 + kx (rows 0-63 = 7x7 filters at kx 1..7, rows 64-79 = the 3x3 filters embedded at ky 2..4,
- * kx 3..5; zero elsewhere), bias fp32 [80], both BN-folded. */
+ * kx 3..5; zero elsewhere), BN-folded; the folded bias rides in K slots 168 / 169 as bf16 hi / lo parts (the kernel
+ * feeds 1.0 there), so the `bias` argument is unused and may be NULL. */
 int cabinet_stem_tc(const float* x, int N, int H, int W, const void* w_packed, const float* bias, void* y_sb,
                     long long ld_sb, void* y_stem, long long ld_stem, int OH, int OW, cabinet_stream_t stream);
 

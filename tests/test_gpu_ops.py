@@ -319,7 +319,10 @@ def test_stem_tc(N, H, W):
     pk[64:, :, 2:5, 3:6] = w3
     wk = torch.zeros(80, 192)
     wk[:, :168] = pk.reshape(80, 168)
-    wk, bias = wk.to("cuda", torch.bfloat16).contiguous(), torch.cat([b7, b3]).cuda()
+    bias = torch.cat([b7, b3])
+    wk[:, 168] = bias.to(torch.bfloat16).float()
+    wk[:, 169] = bias - wk[:, 168]
+    wk, bias = wk.to("cuda", torch.bfloat16).contiguous(), bias.cuda()
     xd = x.cuda()
     y_sb = to_map(torch.zeros(N, 64, OH, OW), torch.bfloat16)
     y_st = to_map(torch.zeros(N, 16, OH, OW), torch.bfloat16)
