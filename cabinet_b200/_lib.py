@@ -25,6 +25,7 @@ SIGNATURES = {
     "cabinet_abi_version": ([], _i),
     "cabinet_device_info": ([C.POINTER(_i)] * 3, _i),
     "cabinet_debug_flags": ([_i], _i),
+    "cabinet_debug_read": ([_p, _i], _i),
     "cabinet_conv2d_simt": ([_p, _i, _ll, _ll, _ll, _ll, _ll, _p, _i, _ll, _ll, _ll, _p, _p, _ll, _p, _i, _ll, _ll,
                              _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p], _i),
     "cabinet_conv_tc": ([_p, _ll, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _ll, _p, _i, _ll, _i, _i, _i, _p], _i),

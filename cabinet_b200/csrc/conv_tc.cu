@@ -45,6 +45,8 @@ struct TcConvParams {
     long long ldy;
 };
 
+__device__ long long g_dbg[8192];  // clock64 stamps of CTA 0's MMA warp when debug bit 8 is set
+
 struct TileCoord {
     int img, oh0, ow0, n0;
 };
@@ -114,20 +116,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     tc::tma_load_2d(sB + kb * b_stage_bytes, &tmB, &bres_bar, kb * BLOCK_K, 0);
             }
             const uint32_t tx_bytes = A_STAGE_BYTES + (p.b_resident ? 0 : b_stage_bytes);
-            int g = 0;
+            int s = 0;
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord tcd = decode_tile(p, tile);
-                for (int kb = 0; kb < p.num_k_blocks; ++kb, ++g) {
-                    const int s = g % p.stages;
-                    const uint32_t ph = (g / p.stages) & 1;
+                int tap = 0, cb = 0, ky = 0, kx = 0;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     tc::mbar_wait(&empty_bar[s], ph ^ 1);
                     if (p.debug & 4) {
                         tc::mbar_arrive(&full_bar[s]);
-                        continue;
-                    }
+                    } else {
                     tc::mbar_expect_tx(&full_bar[s], tx_bytes);
-                    const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
-                    const int ky = tap / p.KW, kx = tap - ky * p.KW;
                     const int ty = ky - p.pad, tx = kx - p.pad;
                     const CUtensorMap* map = &tmA0;
                     int dy = ty, dx = tx;
@@ -141,37 +140,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     tc::tma_load_4d(sA + s * A_STAGE_BYTES, map, &full_bar[s], cb * BLOCK_K, tcd.ow0 + dx, tcd.oh0 + dy,
                                     tcd.img);
                     if (!p.b_resident) tc::tma_load_2d(sB + s * b_stage_bytes, &tmB, &full_bar[s], kb * BLOCK_K, tcd.n0);
+                    }
+                    if (++cb == p.cin_blocks) {
+                        cb = 0;
+                        ++tap;
+                        if (++kx == p.KW) { kx = 0; ++ky; }
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ================= MMA issuer =================
-            const uint32_t idesc = tc::make_idesc_bf16(BLOCK_M, p.block_n);
-            if (p.b_resident) tc::mbar_wait(&bres_bar, 0);
-            int g = 0, it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                tc::mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
+        // ================= MMA issuer: warp-uniform control flow, one elected lane issues =================
+        const uint32_t leader = tc::elect_one();
+        const uint32_t idesc = tc::make_idesc_bf16(BLOCK_M, p.block_n);
+        const uint64_t a_desc0 = tc::make_desc_sw128(tc::smem_u32(sA));
+        const uint64_t b_desc0 = tc::make_desc_sw128(tc::smem_u32(sB));
+        const uint32_t a_step = A_STAGE_BYTES >> 4, b_step = static_cast<uint32_t>(b_stage_bytes) >> 4;
+        if (p.b_resident) tc::mbar_wait(&bres_bar, 0);
+        int g = 0, it = 0, s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            tc::mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
+            tc::tc_fence_after();
+            const uint32_t d = tmem + acc * acc_stride;
+            int cb = 0;
+            for (int kb = 0; kb < p.num_k_blocks; ++kb, ++g) {
+                const bool rec = (p.debug & 8) && blockIdx.x == 0 && g < 2000 && lane == 0;
+                if (rec) g_dbg[4 * g + 0] = clock64();
+                tc::mbar_wait(&full_bar[s], ph);
                 tc::tc_fence_after();
-                const uint32_t d = tmem + acc * acc_stride;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb, ++g) {
-                    const int s = g % p.stages;
-                    const uint32_t ph = (g / p.stages) & 1;
-                    tc::mbar_wait(&full_bar[s], ph);
-                    tc::tc_fence_after();
-                    const int cb = kb % p.cin_blocks;
-                    const int ksteps = min(BLOCK_K / 16, (p.Cin - cb * BLOCK_K + 15) / 16);  // skip all-zero K tails
-                    const uint32_t a_addr = tc::smem_u32(sA + s * A_STAGE_BYTES);
-                    const uint32_t b_addr = tc::smem_u32(sB + (p.b_resident ? kb : s) * b_stage_bytes);
-                    for (int k = 0; k < ksteps; ++k)
-                        tc::umma_bf16(d, tc::make_desc_sw128(a_addr + k * 32), tc::make_desc_sw128(b_addr + k * 32),
-                                      idesc, (kb | k) != 0 ? 1u : 0u);
-                    tc::umma_commit(&empty_bar[s]);  // ring slot is free once these MMAs have read it
-                }
-                tc::umma_commit(&acc_full[acc]);     // accumulator of this tile complete
+                if (rec) g_dbg[4 * g + 1] = clock64();
+                const int ksteps = min(BLOCK_K / 16, (p.Cin - cb * BLOCK_K + 15) / 16);  // skip all-zero K tails
+                const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(s * a_step);
+                const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((p.b_resident ? kb : s) * b_step);
+                tc::umma_bf16_if(leader, d, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u);
+                if (ksteps > 1) tc::umma_bf16_if(leader, d, a_desc + 2, b_desc + 2, idesc, 1u);
+                if (ksteps > 2) tc::umma_bf16_if(leader, d, a_desc + 4, b_desc + 4, idesc, 1u);
+                if (ksteps > 3) tc::umma_bf16_if(leader, d, a_desc + 6, b_desc + 6, idesc, 1u);
+                if (rec) g_dbg[4 * g + 2] = clock64();
+                tc::umma_commit_if(leader, &empty_bar[s]);  // ring slot is free once these MMAs have read it
+                if (rec) g_dbg[4 * g + 3] = clock64();
+                if (++cb == p.cin_blocks) cb = 0;
+                if (++s == p.stages) { s = 0; ph ^= 1; }
             }
+            tc::umma_commit_if(leader, &acc_full[acc]);     // accumulator of this tile complete
         }
         __syncwarp();
     } else {
@@ -335,6 +350,11 @@ int cab_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint6
                           rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
         return CABINET_ERR_CUDA;
     }
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_debug_read(long long* host_out, int n) {
+    CAB_CUDA(cudaMemcpyFromSymbol(host_out, g_dbg, sizeof(long long) * n));
     return CABINET_OK;
 }
 

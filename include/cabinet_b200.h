@@ -42,6 +42,7 @@ int cabinet_abi_version(void);
 int cabinet_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Kernel-development switches (bench/debug only; 0 = normal operation). Returns the previous value. */
 int cabinet_debug_flags(int flags);
+int cabinet_debug_read(long long* host_out, int n);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense convolution + folded-BN bias + activation + residual, CUDA-core implicit GEMM
