@@ -90,46 +90,46 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ================= MMA issuer =================
-            const uint32_t idesc = tc::make_idesc_bf16(128, 128);
-            const uint32_t q_addr = tc::smem_u32(sQ), p_addr = tc::smem_u32(sP);
-            tc::mbar_wait(&q_full, 0);
-            auto issue_pv = [&](int t) {  // O += P_t * V_t   (t is a pass-B index)
-                const int kidx = t - nkb;
-                const uint32_t v_addr = tc::smem_u32(sKV + (t & 1) * 4 * TILE_BYTES + 2 * TILE_BYTES);
-                tc::mbar_wait(&p_full, kidx & 1);
-                tc::tc_fence_after();
+        // ================= MMA issuer: warp-uniform control flow, one elected lane issues =================
+        const uint32_t leader = tc::elect_one();
+        const uint32_t idesc = tc::make_idesc_bf16(128, 128);
+        const uint64_t q_desc = tc::make_desc_sw128(tc::smem_u32(sQ)), p_desc = tc::make_desc_sw128(tc::smem_u32(sP));
+        const uint64_t kv_desc0 = tc::make_desc_sw128(tc::smem_u32(sKV));
+        constexpr uint32_t TILE16 = TILE_BYTES >> 4;
+        tc::mbar_wait(&q_full, 0);
+        auto issue_pv = [&](int t) {  // O += P_t * V_t   (t is a pass-B index)
+            const int kidx = t - nkb;
+            const uint64_t v_desc = kv_desc0 + static_cast<uint64_t>(((t & 1) * 4 + 2) * TILE16);
+            tc::mbar_wait(&p_full, kidx & 1);
+            tc::tc_fence_after();
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb)
+            for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc::umma_bf16(tmem_o, tc::make_desc_sw128(p_addr + kb * TILE_BYTES + k * 32),
-                                      tc::make_desc_sw128(v_addr + kb * TILE_BYTES + k * 32), idesc,
-                                      (kidx | kb | k) != 0 ? 1u : 0u);
-                tc::umma_commit(&p_empty);
-                tc::umma_commit(&kv_empty[t & 1]);
-            };
-            for (int t = 0; t < T; ++t) {
-                const int s = t & 1;
-                const uint32_t ph = (t >> 1) & 1;
-                tc::mbar_wait(&kv_full[s], ph);
-                tc::mbar_wait(&s_empty[s], ph ^ 1);
-                tc::tc_fence_after();
-                const uint32_t k_addr = tc::smem_u32(sKV + s * 4 * TILE_BYTES);
+                for (int k = 0; k < 4; ++k)
+                    tc::umma_bf16_if(leader, tmem_o, p_desc + (kb * TILE16 + 2 * k), v_desc + (kb * TILE16 + 2 * k), idesc,
+                                     (kidx | kb | k) != 0 ? 1u : 0u);
+            tc::umma_commit_if(leader, &p_empty);
+            tc::umma_commit_if(leader, &kv_empty[t & 1]);
+        };
+        for (int t = 0; t < T; ++t) {
+            const int s = t & 1;
+            const uint32_t ph = (t >> 1) & 1;
+            tc::mbar_wait(&kv_full[s], ph);
+            tc::mbar_wait(&s_empty[s], ph ^ 1);
+            tc::tc_fence_after();
+            const uint64_t k_desc = kv_desc0 + static_cast<uint64_t>(s * 4 * TILE16);
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb)
+            for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc::umma_bf16(tmem + s * 128, tc::make_desc_sw128(q_addr + kb * TILE_BYTES + k * 32),
-                                      tc::make_desc_sw128(k_addr + kb * TILE_BYTES + k * 32), idesc, (kb | k) ? 1u : 0u);
-                tc::umma_commit(&s_full[s]);
-                if (t < nkb) tc::umma_commit(&kv_empty[s]);  // pass A: K block is free once S is computed
-                else if (t > nkb) issue_pv(t - 1);            // pass B: P V of the previous block, lagging one S
-            }
-            issue_pv(T - 1);
-            tc::umma_commit(&o_full);
+                for (int k = 0; k < 4; ++k)
+                    tc::umma_bf16_if(leader, tmem + s * 128, q_desc + (kb * TILE16 + 2 * k), k_desc + (kb * TILE16 + 2 * k),
+                                     idesc, (kb | k) ? 1u : 0u);
+            tc::umma_commit_if(leader, &s_full[s]);
+            if (t < nkb) tc::umma_commit_if(leader, &kv_empty[s]);  // pass A: K block is free once S is computed
+            else if (t > nkb) issue_pv(t - 1);                       // pass B: P V of the previous block, lagging one S
         }
+        issue_pv(T - 1);
+        tc::umma_commit_if(leader, &o_full);
         __syncwarp();
     } else {
         // ================= softmax / epilogue: thread = query row =================

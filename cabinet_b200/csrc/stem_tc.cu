@@ -116,29 +116,29 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ================= MMA issuer =================
-            const uint32_t idesc = tc::make_idesc_bf16(128, NOUT);
-            tc::mbar_wait(&w_bar, 0);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const int as = it % A_STAGES, cs = it % ACC_STAGES;
-                const uint32_t aph = (it / A_STAGES) & 1, cph = (it / ACC_STAGES) & 1;
-                tc::mbar_wait(&acc_empty[cs], cph ^ 1);
-                tc::mbar_wait(&a_full[as], aph);
-                tc::tc_fence_after();
-                const uint32_t a_addr = tc::smem_u32(sA + as * A_STAGE_BYTES);
-                const uint32_t w_addr = tc::smem_u32(sW);
-                const uint32_t d = tmem + cs * ACC_COLS;
+        // ================= MMA issuer: warp-uniform control flow, one elected lane issues =================
+        const uint32_t leader = tc::elect_one();
+        const uint32_t idesc = tc::make_idesc_bf16(128, NOUT);
+        const uint64_t a_desc0 = tc::make_desc_sw128(tc::smem_u32(sA));
+        const uint64_t w_desc0 = tc::make_desc_sw128(tc::smem_u32(sW));
+        tc::mbar_wait(&w_bar, 0);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int as = it % A_STAGES, cs = it % ACC_STAGES;
+            const uint32_t aph = (it / A_STAGES) & 1, cph = (it / ACC_STAGES) & 1;
+            tc::mbar_wait(&acc_empty[cs], cph ^ 1);
+            tc::mbar_wait(&a_full[as], aph);
+            tc::tc_fence_after();
+            const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(as * (A_STAGE_BYTES >> 4));
+            const uint32_t d = tmem + cs * ACC_COLS;
 #pragma unroll
-                for (int kb = 0; kb < KBLOCKS; ++kb)
+            for (int kb = 0; kb < KBLOCKS; ++kb)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc::umma_bf16(d, tc::make_desc_sw128(a_addr + kb * A_KB_BYTES + k * 32),
-                                      tc::make_desc_sw128(w_addr + kb * W_KB_BYTES + k * 32), idesc, (kb | k) ? 1u : 0u);
-                tc::umma_commit(&a_empty[as]);
-                tc::umma_commit(&acc_full[cs]);
-            }
+                for (int k = 0; k < 4; ++k)
+                    tc::umma_bf16_if(leader, d, a_desc + (kb * (A_KB_BYTES >> 4) + 2 * k),
+                                     w_desc0 + (kb * (W_KB_BYTES >> 4) + 2 * k), idesc, (kb | k) ? 1u : 0u);
+            tc::umma_commit_if(leader, &a_empty[as]);
+            tc::umma_commit_if(leader, &acc_full[cs]);
         }
         __syncwarp();
     } else if (warp < 10) {
