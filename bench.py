@@ -165,6 +165,22 @@ def summarise_trace(rows, steps, peaks):
     return table
 
 
+def ncu_traffic_per_launch(kernel, args):
+    """dram read+write bytes per launch of a kernel family from the committed ncu capture of this workload
+    (profiles/r01_ncu_dram_traffic_per_family.json: one forward, batch 16, Large, 1024x1024), else None."""
+    p = ROOT / "profiles" / "r01_ncu_dram_traffic_per_family.json"
+    if not p.is_file() or (args.batch, args.size, args.mode, args.classes) != (16, 1024, "large", 8):
+        return None
+    try:
+        fam = json.loads(p.read_text())["families"]
+        for name, f in fam.items():
+            if name.startswith(kernel):
+                return (f["dram_read_bytes"] + f["dram_write_bytes"]) / f["launches"]
+    except Exception:
+        pass
+    return None
+
+
 def roofline_entry(row, fam_rows, peaks, timed_in_step=True):
     nbytes = sum(r["bytes"] for r in fam_rows)
     flops = sum(r["flops"] for r in fam_rows)
@@ -253,6 +269,8 @@ def run_ours(args):
         table = summarise_trace(rows, K, peaks)
         dom = table[0]
         roof = roofline_entry(dom, [r for r in rows if r["kernel"] == dom["kernel"]], peaks)
+        roof["traffic"] = ncu_traffic_per_launch(dom["kernel"], args)
+        roof["traffic_source"] = "profiles/r01_ncu_dram_traffic_per_family.json (ncu dram__bytes_read+write per launch)"
         traced_ms = sum(r["ms"] for r in rows) / K
 
         # ---------------- end to end through the public evaluation call, host buffers
