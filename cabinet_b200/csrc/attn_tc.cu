@@ -196,8 +196,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     Vec16<bf16> o;
                     o.pack(pv + 8 * g);
                     const int cidx = ch * 4 + g;  // 16-byte chunk index along the 128 keys
-                    uint8_t* dst = sP + (cidx >> 3) * TILE_BYTES + row * 128 + (((cidx & 7) ^ (row & 7)) << 4);
-                    *reinterpret_cast<uint4*>(dst) = o.raw;
+                    tc::sts128(tc::smem_u32(sP) + (cidx >> 3) * TILE_BYTES + row * 128 + (((cidx & 7) ^ (row & 7)) << 4), o.raw);
                 }
             }
             tc::fence_proxy_async();

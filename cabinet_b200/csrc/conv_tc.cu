@@ -279,9 +279,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         Vec16<bf16> o0, o1;
                         o0.pack(v);
                         o1.pack(v + 8);
-                        uint8_t* rowp = buf + row * 128;
-                        *reinterpret_cast<uint4*>(rowp + (((2 * c) ^ (row & 7)) << 4)) = o0.raw;
-                        *reinterpret_cast<uint4*>(rowp + (((2 * c + 1) ^ (row & 7)) << 4)) = o1.raw;
+                        const uint32_t rowa = tc::smem_u32(buf) + row * 128;
+                        tc::sts128(rowa + (((2 * c) ^ (row & 7)) << 4), o0.raw);
+                        tc::sts128(rowa + (((2 * c + 1) ^ (row & 7)) << 4), o1.raw);
                     } else if (valid) {
                         float* yp = reinterpret_cast<float*>(p.y) + pix * p.ldy + co0;
 #pragma unroll

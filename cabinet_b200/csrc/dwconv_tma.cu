@@ -3,8 +3,7 @@
 // One CTA = one 8 x 16 output patch of one image for one chunk of <= 64 channels.  A single 4-D TMA box
 // {CB channels, (16-1)*S+K cols, (8-1)*S+K rows, 1} brings the input patch INCLUDING its halo into shared memory;
 // the zero padding of the convolution is the TMA out-of-bounds fill, so the compute loop has no bounds checks and no
-// global loads except the (L1-resident) weights.  Each thread owns 8 channels x 4 consecutive output columns and slides
-// a register window along the row (K+3*S 16-byte LDS per filter row).  Several CTAs are resident per SM, so the TMA
+// global loads.  Several CTAs are resident per SM, so the TMA
 // fetch of one overlaps the FMAs / stores of the others.  Outputs are written with 16-byte stores that cover whole
 // 128-byte lines (8 lanes = the 64 channels of one pixel).
 // Epilogue: + folded-BN bias, activation, optional per-(image, channel) partial sums for the SE / GAP consumers.
@@ -24,12 +23,85 @@ struct DwParams {
     float* gap_sum;
 };
 
+// Warp = one output row of the 8 x 16 patch; lane = (column group, channel PAIR): one 32-bit word of the staged NHWC
+// pixel per lane, so a warp-wide LDS.32 of a full 64-channel chunk is one conflict-free 128-byte wavefront.  A chunk
+// narrower than 64 channels packs 16/COLS column groups into the warp (COLS = columns per lane) to keep lanes busy.
+// The thread keeps all K*K taps of its two channels in registers for its whole lifetime (loaded while the TMA is in
+// flight) and slides over its COLS output columns: ((COLS-1)*S + K) loads per filter row feed COLS*K*2 FMAs, no weight
+// traffic and no bounds checks in the loop.
+template <int K, int S, int COLS>
+__device__ __forceinline__ void dw_row(const DwParams& p, const uint8_t* tile, uint64_t* bar, float* s_gap, int cw,
+                                       int chunk, int n, int oh0, int ow0) {
+    constexpr int IWT = (TW - 1) * S + K;
+    constexpr int SPAN = (COLS - 1) * S + K;
+    const int row = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lanes_px = cw >> 1;               // lanes per pixel (channel pairs of this chunk)
+    const int grp = lane / lanes_px, cl = lane - grp * lanes_px;
+    const int c0 = chunk * 64 + cl * 2;
+    const bool active = grp < TW / COLS;
+    const int col0 = grp * COLS;
+
+    float2 w[K * K];
+    float acc[COLS][2];
+    if (active) {
+#pragma unroll
+        for (int t = 0; t < K * K; ++t) w[t] = __ldg(reinterpret_cast<const float2*>(p.w + t * p.C + c0));
+        const float2 b = __ldg(reinterpret_cast<const float2*>(p.bias + c0));
+#pragma unroll
+        for (int r = 0; r < COLS; ++r) {
+            acc[r][0] = b.x;
+            acc[r][1] = b.y;
+        }
+    }
+    tc::mbar_wait(bar, 0);
+    if (active) {
+        constexpr int pitch = 128;  // bytes per staged pixel (64-channel TMA box; narrower chunks are zero filled)
+        const uint32_t base = tc::smem_u32(tile) + ((row * S) * IWT + col0 * S) * pitch + cl * 4;
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const uint32_t rowp = base + ky * IWT * pitch;
+#pragma unroll
+            for (int sx = 0; sx < SPAN; ++sx) {
+                uint32_t raw;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(rowp + sx * pitch));
+                const float x0 = __uint_as_float(raw << 16), x1 = __uint_as_float(raw & 0xffff0000u);
+#pragma unroll
+                for (int r = 0; r < COLS; ++r) {
+                    const int kx = sx - r * S;  // compile-time after unrolling
+                    if (kx >= 0 && kx < K) {
+                        acc[r][0] = fmaf(x0, w[ky * K + kx].x, acc[r][0]);
+                        acc[r][1] = fmaf(x1, w[ky * K + kx].y, acc[r][1]);
+                    }
+                }
+            }
+        }
+        cab_act_vec<2 * COLS>(&acc[0][0], p.act);
+        const int oh = oh0 + row;
+        float g0 = 0.f, g1 = 0.f;
+        if (oh < p.OH) {
+            bf16* yout = p.y + ((static_cast<long long>(n) * p.OH + oh) * p.OW + ow0 + col0) * p.ldy + c0;
+#pragma unroll
+            for (int r = 0; r < COLS; ++r) {
+                if (ow0 + col0 + r < p.OW) {
+                    g0 += acc[r][0];
+                    g1 += acc[r][1];
+                    *reinterpret_cast<__nv_bfloat162*>(yout + static_cast<long long>(r) * p.ldy) =
+                        __floats2bfloat162_rn(acc[r][0], acc[r][1]);
+                }
+            }
+        }
+        if (p.gap_sum) {
+            atomicAdd(&s_gap[cl * 2], g0);
+            atomicAdd(&s_gap[cl * 2 + 1], g1);
+        }
+    }
+}
+
 template <int K, int S>
 __global__ void __launch_bounds__(256)
 dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmX, const DwParams p) {
     constexpr int PAD = (K - 1) / 2;
     constexpr int IWT = (TW - 1) * S + K, IHT = (TH - 1) * S + K;
-    constexpr int SPAN = (RUN - 1) * S + K;
     extern __shared__ __align__(128) uint8_t smem_dw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_gap[64];
@@ -37,100 +109,36 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmX, const DwParams p) {
     const int tiles_w = (p.OW + TW - 1) / TW;
     const int ow0 = (blockIdx.x % tiles_w) * TW, oh0 = (blockIdx.x / tiles_w) * TH;
     const int chunk = blockIdx.y, n = blockIdx.z;
-    const int CB = p.CB, CGB = CB >> 3;
     uint8_t* tile = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dw) + 127) & ~uintptr_t(127));
 
     if (threadIdx.x == 0) {
         tc::mbar_init(&bar, 1);
         tc::mbar_fence_init();
         tc::fence_proxy_async();
-        tc::mbar_expect_tx(&bar, static_cast<uint32_t>(IWT * IHT * CB * 2));
-        tc::tma_load_4d(tile, &tmX, &bar, chunk * CB, ow0 * S - PAD, oh0 * S - PAD, n);
+        tc::mbar_expect_tx(&bar, static_cast<uint32_t>(IWT * IHT * 128));
+        tc::tma_load_4d(tile, &tmX, &bar, chunk * 64, ow0 * S - PAD, oh0 * S - PAD, n);
     }
     if (p.gap_sum && threadIdx.x < 64) s_gap[threadIdx.x] = 0.f;
     __syncthreads();
 
-    const int cg = threadIdx.x % CGB;
-    const int rem = threadIdx.x / CGB;
-    const int run = rem % (TW / RUN), row = rem / (TW / RUN);
-    const int c0 = chunk * CB + cg * 8;
-    const bool active = row < TH && c0 < p.C;  // C % 8 == 0, so a group is either fully inside or outside
+    const int cw = min(64, p.C - chunk * 64);  // channels of this chunk (multiple of 8)
+    // columns per lane: as many column groups as fit into the 32 lanes (power of two)
+    if (cw > 32) dw_row<K, S, 16>(p, tile, &bar, s_gap, cw, chunk, n, oh0, ow0);
+    else if (cw > 16) dw_row<K, S, 8>(p, tile, &bar, s_gap, cw, chunk, n, oh0, ow0);
+    else if (cw > 8) dw_row<K, S, 4>(p, tile, &bar, s_gap, cw, chunk, n, oh0, ow0);
+    else dw_row<K, S, 2>(p, tile, &bar, s_gap, cw, chunk, n, oh0, ow0);
 
-    float acc[RUN][8];
-    if (active) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + 1);
-#pragma unroll
-        for (int r = 0; r < RUN; ++r) {
-            acc[r][0] = b0.x; acc[r][1] = b0.y; acc[r][2] = b0.z; acc[r][3] = b0.w;
-            acc[r][4] = b1.x; acc[r][5] = b1.y; acc[r][6] = b1.z; acc[r][7] = b1.w;
-        }
-    }
-    tc::mbar_wait(&bar, 0);
-    if (active) {
-        const int pitch = CB * 2;  // bytes per staged pixel
-        const uint8_t* base = tile + ((row * S) * IWT + run * RUN * S) * pitch + cg * 16;
-#pragma unroll
-        for (int ky = 0; ky < K; ++ky) {
-            float wk[K][8];
-#pragma unroll
-            for (int kx = 0; kx < K; ++kx) {
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w + (ky * K + kx) * p.C + c0));
-                const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w + (ky * K + kx) * p.C + c0) + 1);
-                wk[kx][0] = w0.x; wk[kx][1] = w0.y; wk[kx][2] = w0.z; wk[kx][3] = w0.w;
-                wk[kx][4] = w1.x; wk[kx][5] = w1.y; wk[kx][6] = w1.z; wk[kx][7] = w1.w;
-            }
-            const uint8_t* rowp = base + ky * IWT * pitch;
-#pragma unroll
-            for (int sx = 0; sx < SPAN; ++sx) {
-                Vec16<bf16> xv;
-                xv.raw = *reinterpret_cast<const uint4*>(rowp + sx * pitch);
-                float xf[8];
-                xv.unpack(xf);
-#pragma unroll
-                for (int r = 0; r < RUN; ++r) {
-                    const int kx = sx - r * S;  // compile-time after unrolling
-                    if (kx >= 0 && kx < K) {
-#pragma unroll
-                        for (int v = 0; v < 8; ++v) acc[r][v] = fmaf(xf[v], wk[kx][v], acc[r][v]);
-                    }
-                }
-            }
-        }
-        const int oh = oh0 + row;
-        float gsum[8];
-#pragma unroll
-        for (int v = 0; v < 8; ++v) gsum[v] = 0.f;
-        if (oh < p.OH) {
-            bf16* yout = p.y + ((static_cast<long long>(n) * p.OH + oh) * p.OW) * p.ldy + c0;
-#pragma unroll
-            for (int r = 0; r < RUN; ++r) {
-                const int ow = ow0 + run * RUN + r;
-                if (ow >= p.OW) continue;
-                cab_act_vec<8>(acc[r], p.act);
-#pragma unroll
-                for (int v = 0; v < 8; ++v) gsum[v] += acc[r][v];
-                Vec16<bf16> ov;
-                ov.pack(acc[r]);
-                ov.store(yout + static_cast<long long>(ow) * p.ldy);
-            }
-        }
-        if (p.gap_sum) {
-#pragma unroll
-            for (int v = 0; v < 8; ++v) atomicAdd(&s_gap[cg * 8 + v], gsum[v]);
-        }
-    }
     if (p.gap_sum) {
         __syncthreads();
-        const int c = chunk * CB + threadIdx.x;
-        if (threadIdx.x < CB && c < p.C) atomicAdd(&p.gap_sum[static_cast<long long>(n) * p.C + c], s_gap[threadIdx.x]);
+        const int c = chunk * 64 + threadIdx.x;
+        if (threadIdx.x < cw) atomicAdd(&p.gap_sum[static_cast<long long>(n) * p.C + c], s_gap[threadIdx.x]);
     }
 }
 
 template <int K, int S>
 int launch(const CUtensorMap& tm, const DwParams& p, int N, int n_chunks, cudaStream_t s) {
     constexpr int IWT = (TW - 1) * S + K, IHT = (TH - 1) * S + K;
-    const size_t smem = static_cast<size_t>(IWT) * IHT * p.CB * 2 + 128;
+    const size_t smem = static_cast<size_t>(IWT) * IHT * 128 + 128;
     static bool attr_set = false;
     if (!attr_set) {
         CAB_CUDA(cudaFuncSetAttribute(dwconv_tma_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -138,8 +146,7 @@ int launch(const CUtensorMap& tm, const DwParams& p, int N, int n_chunks, cudaSt
     }
     const int tiles = ((p.OW + TW - 1) / TW) * ((p.OH + TH - 1) / TH);
     dim3 grid(tiles, n_chunks, N);
-    const int threads = (p.CB / 8) * (TW / RUN) * TH;  // 32 * CB/8 <= 256
-    dwconv_tma_kernel<K, S><<<grid, threads, smem, s>>>(tm, p);
+    dwconv_tma_kernel<K, S><<<grid, 32 * TH, smem, s>>>(tm, p);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }
@@ -162,7 +169,7 @@ extern "C" int cabinet_dwconv_tma(const void* x, long long ldx, const float* w, 
     DwParams p;
     const int n_chunks = (C + 63) / 64;
     p.C = C; p.OH = OH; p.OW = OW; p.act = act; p.w = w; p.bias = bias;
-    p.CB = ((C + n_chunks - 1) / n_chunks + 7) / 8 * 8;
+    p.CB = 64;  // TMA box = 64 channels; the last chunk may be narrower (zero filled)
     p.y = reinterpret_cast<bf16*>(y); p.ldy = ldy; p.gap_sum = gap_sum;
     const int IWT = (TW - 1) * stride + k, IHT = (TH - 1) * stride + k;
     CUtensorMap tm;

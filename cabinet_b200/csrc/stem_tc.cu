@@ -149,10 +149,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (half == 0) {
             // K padding chunks 21..23 of K-block 2 never change: chunk 21 = {1, 1, 0...} (the two bias slots), rest 0
             for (int as = 0; as < A_STAGES; ++as) {
-                uint8_t* kb2 = sA + as * A_STAGE_BYTES + 2 * A_KB_BYTES + r * 128;
-                *reinterpret_cast<uint4*>(kb2 + ((5 ^ (r & 7)) << 4)) = make_uint4(0x3F803F80u, 0, 0, 0);
-                *reinterpret_cast<uint4*>(kb2 + ((6 ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(kb2 + ((7 ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+                const uint32_t kb2 = tc::smem_u32(sA) + as * A_STAGE_BYTES + 2 * A_KB_BYTES + r * 128;
+                tc::sts128(kb2 + ((5 ^ (r & 7)) << 4), make_uint4(0x3F803F80u, 0, 0, 0));
+                tc::sts128(kb2 + ((6 ^ (r & 7)) << 4), make_uint4(0, 0, 0, 0));
+                tc::sts128(kb2 + ((7 ^ (r & 7)) << 4), make_uint4(0, 0, 0, 0));
             }
         }
         int it = 0;
@@ -161,19 +161,20 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             const uint32_t wph = (it / WIN_STAGES) & 1, aph = (it / A_STAGES) & 1;
             tc::mbar_wait(&win_full[ws], wph);
             tc::mbar_wait(&a_empty[as], aph ^ 1);
-            const float* win = reinterpret_cast<const float*>(sWin + ws * WIN_STRIDE);
-            uint8_t* arow = sA + as * A_STAGE_BYTES + r * 128;
+            const uint32_t win = tc::smem_u32(sWin) + ws * WIN_STRIDE;
+            const uint32_t arow = tc::smem_u32(sA) + as * A_STAGE_BYTES + r * 128;
 #pragma unroll
             for (int jj = 0; jj < 11; ++jj) {  // j = c*7 + ky; this thread takes j = half, half+2, ...
                 const int j = 2 * jj + half;
                 if (j >= 21) break;
                 const int c = j / 7, ky = j % 7;
-                const float2* src = reinterpret_cast<const float2*>(win + (c * WIN_H + 2 * oy + ky) * WIN_W + 2 * ox);
-                const float2 f0 = src[0], f1 = src[1], f2 = src[2], f3 = src[3];
+                const uint32_t src = win + ((c * WIN_H + 2 * oy + ky) * WIN_W + 2 * ox) * 4;
+                const float2 f0 = tc::lds64f(src), f1 = tc::lds64f(src + 8), f2 = tc::lds64f(src + 16),
+                             f3 = tc::lds64f(src + 24);
                 const uint4 v = make_uint4(pack_bf16x2(f0.x, f0.y), pack_bf16x2(f1.x, f1.y), pack_bf16x2(f2.x, f2.y),
                                            pack_bf16x2(f3.x, f3.y));
                 const int kb = j >> 3, cc = j & 7;
-                *reinterpret_cast<uint4*>(arow + kb * A_KB_BYTES + ((cc ^ (r & 7)) << 4)) = v;
+                tc::sts128(arow + kb * A_KB_BYTES + ((cc ^ (r & 7)) << 4), v);
             }
             tc::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             __syncwarp();
@@ -209,7 +210,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             // the stores that used this staging pair two tiles ago must have finished reading it
             if (leader) tc::bulk_wait_read<1>();
             tc::named_bar_sync(1, 128);
-            uint8_t* rowp = bsb + r * 128;
+            const uint32_t rowp = tc::smem_u32(bsb) + r * 128;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {  // 8 channels (16 bytes) per chunk, ReLU
                 float v[8];
@@ -218,7 +219,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                     v[j] = fmaxf(__uint_as_float(g < 4 ? a0[8 * g + j] : a1[8 * (g - 4) + j]), 0.f);
                 Vec16<bf16> o;
                 o.pack(v);
-                *reinterpret_cast<uint4*>(rowp + ((g ^ (r & 7)) << 4)) = o.raw;
+                tc::sts128(rowp + ((g ^ (r & 7)) << 4), o.raw);
             }
 #pragma unroll
             for (int g = 0; g < 2; ++g) {  // backbone stem: HardSwish
@@ -230,7 +231,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 }
                 Vec16<bf16> o;
                 o.pack(v);
-                *reinterpret_cast<uint4*>(bst + r * 32 + g * 16) = o.raw;
+                tc::sts128(tc::smem_u32(bst) + r * 32 + g * 16, o.raw);
             }
             tc::fence_proxy_async();
             tc::named_bar_sync(1, 128);
