@@ -38,6 +38,8 @@ struct TcConvParams {
     int cin_blocks, num_k_blocks;
     int block_n, n_tiles, num_tiles, tmem_cols, stages, b_resident;
     int act, y_dtype, debug;
+    int a_act, hw;            // A-operand prologue: x <- act(x * a_scale[image][channel]); hw = pixels per image
+    const float* a_scale;     // [N][Cin] fp32 or nullptr
     const float* bias;
     const bf16* res;
     long long ldres;
@@ -63,8 +65,8 @@ __device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int tile
     return c;
 }
 
-template <int ACT, bool HAS_RES, bool OUT_F32>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int ACT, bool HAS_RES, bool OUT_F32, bool PRO>
+__global__ void __launch_bounds__(PRO ? NUM_THREADS + 128 : NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
@@ -72,6 +74,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t ready_bar[MAX_STAGES];  // PRO: A tile transformed in place, MMA may read it
     __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], bres_bar;
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float s_bias[2][256];  // per epilogue warpgroup: bias slice of its current cout tile
@@ -91,6 +94,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int s = 0; s < p.stages; ++s) {
             tc::mbar_init(&full_bar[s], 1);
             tc::mbar_init(&empty_bar[s], 1);
+            tc::mbar_init(&ready_bar[s], 4);
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&acc_full[s], 1);
@@ -170,7 +174,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int kb = 0; kb < p.num_k_blocks; ++kb, ++g) {
                 const bool rec = (p.debug & 8) && blockIdx.x == 0 && g < 2000 && lane == 0;
                 if (rec) g_dbg[4 * g + 0] = clock64();
-                tc::mbar_wait(&full_bar[s], ph);
+                tc::mbar_wait(PRO ? &ready_bar[s] : &full_bar[s], ph);
                 tc::tc_fence_after();
                 if (rec) g_dbg[4 * g + 1] = clock64();
                 const int ksteps = min(BLOCK_K / 16, (p.Cin - cb * BLOCK_K + 15) / 16);  // skip all-zero K tails
@@ -189,6 +193,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tc::umma_commit_if(leader, &acc_full[acc]);     // accumulator of this tile complete
         }
         __syncwarp();
+    } else if (PRO && warp >= 10) {
+        // ================= A-operand prologue (SE): x <- act(x * scale[image][channel]) in place =================
+        // reference: src/models/mobilenetv3.py:83 (x * y) followed by the activation at :143, fused in front of the
+        // project 1x1 so the depthwise output is read from HBM once and never rewritten.
+        const int r = (warp - 10) * 32 + lane;  // A row = pixel of the tile
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const TileCoord tcd = decode_tile(p, tile);
+            // image of this row: flat tiles index pixels of all images, spatial tiles belong to one image
+            const long long pixrow = static_cast<long long>(tcd.ow0) + r;
+            const int img = p.tiles_h == 1 && p.OH == 1 ? static_cast<int>(min(pixrow, static_cast<long long>(p.OW) - 1) / p.hw)
+                                                        : tcd.img;
+            const float* sc = p.a_scale + static_cast<long long>(img) * p.Cin;
+            int cb = 0;
+            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                tc::mbar_wait(&full_bar[s], ph);
+                const uint32_t rowa = tc::smem_u32(sA) + s * A_STAGE_BYTES + r * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = cb * BLOCK_K + ((j ^ (r & 7)) << 3);  // logical channels of physical 16-byte chunk j
+                    if (c < p.Cin) {
+                        Vec16<bf16> v;
+                        v.raw = tc::lds128(rowa + (j << 4));
+                        float f[8];
+                        v.unpack(f);
+                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + c));
+                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + c) + 1);
+                        f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+                        f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+                        cab_act_vec<8>(f, p.a_act);
+                        v.pack(f);
+                        tc::sts128(rowa + (j << 4), v.raw);
+                    }
+                }
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&ready_bar[s]);
+                if (++cb == p.cin_blocks) cb = 0;
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+        }
     } else {
         // ================= epilogue warpgroup e (tiles it = e, e+2, ...) =================
         const int e = (warp - 2) >> 2;
@@ -364,11 +410,26 @@ extern "C" int cabinet_debug_flags(int flags) {
     return old;
 }
 
+extern "C" int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, int W, int Cin, const float* a_scale,
+                                  int a_act, const void* w_packed, int Cout, int KH, int KW, int stride, int pad,
+                                  const float* bias, const void* res, long long ldres, void* y, int y_dtype,
+                                  long long ldy, int OH, int OW, int act, cabinet_stream_t stream);
+
 extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_packed,
                                int Cout, int KH, int KW, int stride, int pad, const float* bias, const void* res,
                                long long ldres, void* y, int y_dtype, long long ldy, int OH, int OW, int act,
                                cabinet_stream_t stream) {
+    return cabinet_conv_tc_se(x, ldx, N, H, W, Cin, nullptr, CABINET_ACT_NONE, w_packed, Cout, KH, KW, stride, pad, bias,
+                              res, ldres, y, y_dtype, ldy, OH, OW, act, stream);
+}
+
+extern "C" int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, int W, int Cin, const float* a_scale,
+                                  int a_act, const void* w_packed, int Cout, int KH, int KW, int stride, int pad,
+                                  const float* bias, const void* res, long long ldres, void* y, int y_dtype,
+                                  long long ldy, int OH, int OW, int act, cabinet_stream_t stream) {
     CAB_REQUIRE(x && w_packed && bias && y, "conv_tc: null pointer");
+    CAB_REQUIRE(!a_scale || (Cin % 8 == 0 && (reinterpret_cast<uintptr_t>(a_scale) & 15) == 0),
+                "conv_tc: the A-operand scale needs Cin %% 8 == 0 and a 16-byte aligned pointer");
     CAB_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && OH > 0 && OW > 0,
                 "conv_tc: bad sizes");
     CAB_REQUIRE(stride == 1 || stride == 2, "conv_tc: stride must be 1 or 2");
@@ -401,6 +462,7 @@ extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W
     p.stages = std::max(2, std::min(MAX_STAGES, (SMEM_LIMIT - fixed) / stage_bytes));
     p.act = act; p.y_dtype = y_dtype; p.bias = bias; p.res = reinterpret_cast<const bf16*>(res); p.ldres = ldres;
     p.y = y; p.ldy = ldy; p.debug = g_debug;
+    p.a_scale = a_scale; p.a_act = a_act; p.hw = H * W;
 
     CUtensorMap tmA[4], tmB, tmY;
     const uint64_t es = 2;
@@ -470,22 +532,27 @@ extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W
     CAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = static_cast<int>(std::min<long long>(tiles, sms));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define CAB_TC_LAUNCH(ACT_, RES_, F32_)                                                                              \
+#define CAB_TC_LAUNCH(ACT_, RES_, F32_, PRO_)                                                                        \
     do {                                                                                                             \
         static bool attr_done = false;                                                                               \
         if (!attr_done) {                                                                                            \
-            CAB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_, RES_, F32_>,                                          \
+            CAB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_, RES_, F32_, PRO_>,                                    \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT + 1024));          \
             attr_done = true;                                                                                        \
         }                                                                                                            \
-        conv_tc_kernel<ACT_, RES_, F32_><<<grid, NUM_THREADS, smem, st>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmY, p); \
+        conv_tc_kernel<ACT_, RES_, F32_, PRO_><<<grid, (PRO_) ? NUM_THREADS + 128 : NUM_THREADS, smem, st>>>(        \
+            tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmY, p);                                                            \
     } while (0)
     const bool f32 = y_dtype == CABINET_F32;
-    if (f32 && !res && act == CABINET_ACT_NONE) CAB_TC_LAUNCH(CABINET_ACT_NONE, false, true);
-    else if (!f32 && !res && act == CABINET_ACT_NONE) CAB_TC_LAUNCH(CABINET_ACT_NONE, false, false);
-    else if (!f32 && !res && act == CABINET_ACT_RELU) CAB_TC_LAUNCH(CABINET_ACT_RELU, false, false);
-    else if (!f32 && !res && act == CABINET_ACT_HSWISH) CAB_TC_LAUNCH(CABINET_ACT_HSWISH, false, false);
-    else if (!f32 && res && act == CABINET_ACT_NONE) CAB_TC_LAUNCH(CABINET_ACT_NONE, true, false);
+    if (a_scale) {
+        CAB_REQUIRE(!f32 && act == CABINET_ACT_NONE, "conv_tc: the A-operand prologue is built for the linear project conv");
+        if (res) CAB_TC_LAUNCH(CABINET_ACT_NONE, true, false, true);
+        else CAB_TC_LAUNCH(CABINET_ACT_NONE, false, false, true);
+    } else if (f32 && !res && act == CABINET_ACT_NONE) CAB_TC_LAUNCH(CABINET_ACT_NONE, false, true, false);
+    else if (!f32 && !res && act == CABINET_ACT_NONE) CAB_TC_LAUNCH(CABINET_ACT_NONE, false, false, false);
+    else if (!f32 && !res && act == CABINET_ACT_RELU) CAB_TC_LAUNCH(CABINET_ACT_RELU, false, false, false);
+    else if (!f32 && !res && act == CABINET_ACT_HSWISH) CAB_TC_LAUNCH(CABINET_ACT_HSWISH, false, false, false);
+    else if (!f32 && res && act == CABINET_ACT_NONE) CAB_TC_LAUNCH(CABINET_ACT_NONE, true, false, false);
     else {
         cabinet_set_error("conv_tc: unsupported epilogue combination (act %d, residual %d, fp32 out %d)", act,
                           res != nullptr, (int)f32);

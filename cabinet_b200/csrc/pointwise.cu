@@ -72,30 +72,36 @@ gate_fc_kernel(const float* __restrict__ in, float in_scale, const float* __rest
     }
 }
 
+// grid (pixel chunks, N); blockDim = (CG channel-vector lanes) x (pixel lanes): a thread keeps its 16-byte channel
+// vector's scales in registers and walks pixels with pure 32-bit strided addressing (no div/mod in the loop).
 template <typename T>
 __global__ void __launch_bounds__(256)
-scale_act_kernel(T* __restrict__ x, long long ldx, const float* __restrict__ scale, long long HW, int C, int act,
-                 int plus_one) {
+scale_act_kernel(T* __restrict__ x, long long ldx, const float* __restrict__ scale, int HW, int C, int act,
+                 int plus_one, int pix_per_block) {
     constexpr int V = Vec16<T>::N;
     const int n = blockIdx.y;
     const int CG = C / V;
-    const long long total = HW * CG;
-    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int cg = static_cast<int>(idx % CG);
-        const long long p = idx / CG;
-        T* ptr = x + (static_cast<long long>(n) * HW + p) * ldx + cg * V;
+    const int lanes = blockDim.x / CG;  // pixel lanes (CG <= 256 / 2 checked by the host)
+    const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+    if (pl >= lanes) return;
+    float sc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) sc[i] = __ldg(scale + static_cast<long long>(n) * C + cg * V + i);
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(p0 + pix_per_block, HW);
+    T* base = x + (static_cast<long long>(n) * HW) * ldx + cg * V;
+    for (int p = p0 + pl; p < p1; p += lanes) {
+        T* ptr = base + static_cast<long long>(p) * ldx;
         Vec16<T> v;
         v.load(ptr);
         float f[V];
         v.unpack(f);
-        const float* sc = scale + static_cast<long long>(n) * C + cg * V;
         if (plus_one) {
 #pragma unroll
-            for (int i = 0; i < V; ++i) f[i] = fmaf(f[i], __ldg(sc + i), f[i]);
+            for (int i = 0; i < V; ++i) f[i] = fmaf(f[i], sc[i], f[i]);
         } else {
 #pragma unroll
-            for (int i = 0; i < V; ++i) f[i] *= __ldg(sc + i);
+            for (int i = 0; i < V; ++i) f[i] *= sc[i];
             cab_act_vec<V>(f, act);
         }
         v.pack(f);
@@ -232,15 +238,24 @@ extern "C" int cabinet_scale_act(void* x, long long ldx, int dtype, const float*
                                  int act, int plus_one, cabinet_stream_t stream) {
     CAB_REQUIRE(x && scale, "scale_act: null pointer");
     const int V = dtype == CABINET_F32 ? 4 : 8;
-    CAB_REQUIRE(C > 0 && C % V == 0 && ldx % V == 0 && ldx >= C, "scale_act: C/ldx must be multiples of %d", V);
+    CAB_REQUIRE(C > 0 && C % V == 0 && ldx % V == 0 && ldx >= C && C / V <= 256 && HW < (1LL << 31) && N <= 65535,
+                "scale_act: C/ldx must be multiples of %d, C/%d <= 256", V, V);
     if (N == 0 || HW == 0) return CABINET_OK;
-    const long long total = HW * (C / V);
-    dim3 grid(static_cast<unsigned>(std::min<long long>(cab_ceil_div(total, 256), 148 * 16)), N);
+    const int CG = C / V;
+    const int threads = std::max(CG, 256 / CG * CG);   // a multiple of CG close to 256
+    const int lanes = threads / CG;
+    // ~8 pixels per thread, but at least ~4 blocks per SM across the batch
+    int pix_per_block = lanes * 8;
+    const long long want_blocks = 148LL * 8;
+    while (pix_per_block > lanes && cab_ceil_div(HW, pix_per_block) * N < want_blocks) pix_per_block -= lanes;
+    dim3 grid(static_cast<unsigned>(cab_ceil_div(HW, pix_per_block)), N);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == CABINET_BF16)
-        scale_act_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<bf16*>(x), ldx, scale, HW, C, act, plus_one);
+        scale_act_kernel<bf16><<<grid, threads, 0, s>>>(reinterpret_cast<bf16*>(x), ldx, scale, static_cast<int>(HW), C, act,
+                                                        plus_one, pix_per_block);
     else
-        scale_act_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<float*>(x), ldx, scale, HW, C, act, plus_one);
+        scale_act_kernel<float><<<grid, threads, 0, s>>>(reinterpret_cast<float*>(x), ldx, scale, static_cast<int>(HW), C, act,
+                                                         plus_one, pix_per_block);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

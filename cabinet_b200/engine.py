@@ -131,6 +131,7 @@ class Engine:
         self.debug = False
         self.stages = {}
         self.trace, self.trace_filter = None, None
+        self.fuse_se = False        # SE apply as A-operand prologue of the project GEMM (slower than scale_act today)
         self.use_cuda_graph = False
         self.sub_batch = 0          # > 0: run the schedule over chunks of this many images
         self._graphs = {}
@@ -230,7 +231,7 @@ class Engine:
         return Map(t, N, H, W, C, C)
 
     def conv(self, x: Map, L: ConvLayer, out: Optional[Map] = None, res: Optional[Map] = None, out_dtype=None,
-             nchw_input: Optional[torch.Tensor] = None) -> Map:
+             nchw_input: Optional[torch.Tensor] = None, a_scale: Optional[torch.Tensor] = None, a_act: int = 0) -> Map:
         """Dense conv + bias + act (+ residual).  ``nchw_input``: read the fp32 NCHW network input in place."""
         if nchw_input is not None:
             N, _, H, W = nchw_input.shape
@@ -253,8 +254,9 @@ class Engine:
         if (self.use_tc and L.tc is not None and nchw_input is None and x.dt == BF16 and x.ld % 8 == 0
                 and x.off % 8 == 0 and (L.stride == 1 or (H >= 2 and W >= 2))
                 and (out.dt == F32 or (out.ld % 8 == 0 and out.off % 8 == 0))):
-            self._conv_tc(x, L, out, res, OH, OW, nbytes, flops)
+            self._conv_tc(x, L, out, res, OH, OW, nbytes, flops, a_scale, a_act)
             return out
+        assert a_scale is None, "the SE prologue exists on the tcgen05 path only"
         wdt = BF16 if L.w.dtype == torch.bfloat16 else F32
         self._run("conv2d_simt", L.name, nbytes, flops, self.lib.cabinet_conv2d_simt,
                   xptr, xdt, sxn, sxh, sxw, sxc, 0, L.w.data_ptr(), wdt, L.w.shape[1], 1, 0, L.b.data_ptr(),
@@ -263,8 +265,9 @@ class Engine:
                   1.0, self.stream)
         return out
 
-    def _conv_tc(self, x: Map, L: ConvLayer, out: Map, res: Optional[Map], OH, OW, nbytes, flops):
-        self._run("conv_tc", L.name, nbytes, flops, self.lib.cabinet_conv_tc, x.ptr, x.ld, x.N, x.H, x.W, x.C,
+    def _conv_tc(self, x: Map, L: ConvLayer, out: Map, res: Optional[Map], OH, OW, nbytes, flops, a_scale=None, a_act=0):
+        self._run("conv_tc", L.name, nbytes, flops, self.lib.cabinet_conv_tc_se, x.ptr, x.ld, x.N, x.H, x.W, x.C,
+                  a_scale.data_ptr() if a_scale is not None else None, a_act,
                   L.tc.data_ptr(), L.cout, L.kh, L.kw, L.stride, L.pad, L.b.data_ptr(),
                   res.ptr if res is not None else None, res.ld if res is not None else 0, out.ptr, out.dt, out.ld,
                   OH, OW, L.act, self.stream)
@@ -391,7 +394,13 @@ class Engine:
                 d = self.dwconv(h, e["dw"], gap)
                 scale = self.gate(gap, d.H * d.W, e["se"], e["dw"].name)
                 # expand form: SE then activation; no-expand form: activation (already applied) then SE (F10)
-                self.scale_act(d, scale, e["act"] if s["expand"] else ACT_NONE, e["dw"].name)
+                se_act = e["act"] if s["expand"] else ACT_NONE
+                pw2 = e["pw2"]
+                if self.fuse_se and self.use_tc and pw2.tc is not None and d.dt == BF16 and d.C % 8 == 0:
+                    # fused: the project GEMM applies act(x * scale) to its A tiles in shared memory
+                    f = self.conv(d, pw2, res=f if s["identity"] else None, a_scale=scale, a_act=se_act)
+                    continue
+                self.scale_act(d, scale, se_act, e["dw"].name)
             else:
                 d = self.dwconv(h, e["dw"])
             f = self.conv(d, e["pw2"], res=f if s["identity"] else None)

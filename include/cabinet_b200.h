@@ -77,6 +77,15 @@ int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W, int Cin, 
                     int KH, int KW, int stride, int pad, const float* bias, const void* res, long long ldres,
                     void* y, int y_dtype, long long ldy, int OH, int OW, int act, cabinet_stream_t stream);
 
+/* cabinet_conv_tc with the squeeze-excite apply fused in front (A-operand prologue): the GEMM consumes
+ * act(x[n][p][c] * a_scale[n][c]) (a_scale fp32 [N][Cin]) without that tensor ever being written:
+ * SELayer's x * y (src/models/mobilenetv3.py:83) and the activation that follows it (:143) run in shared memory
+ * between the TMA load and the MMA.  Linear project convs only (act must be CABINET_ACT_NONE, bf16 output). */
+int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, int W, int Cin, const float* a_scale, int a_act,
+                       const void* w_packed, int Cout, int KH, int KW, int stride, int pad, const float* bias,
+                       const void* res, long long ldres, void* y, int y_dtype, long long ldy, int OH, int OW, int act,
+                       cabinet_stream_t stream);
+
 /* Both network stems in one tensor-core kernel: sb.conv1 (7x7 s2 p3, 3->64, BN, ReLU; src/models/cabinet.py:111)
  * and the backbone stem (3x3 s2 p1, 3->16, BN, HardSwish; src/models/mobilenetv3.py:86-91,173) read the fp32 NCHW
  * image x [N][3][H][W] once (W % 4 == 0) and write their bf16 NHWC outputs.  w_packed: bf16 [80][192] with

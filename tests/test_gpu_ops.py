@@ -392,3 +392,34 @@ def test_attention_tc(N, L):
     err = rel_l2(ctx.float().cpu(), ref)
     print(f"attention_tc N={N} L={L}: rel_l2 {err:.3e}")
     assert err < 8e-3  # P is rounded to bf16 before the P V product (like the reference under bf16 autocast)
+
+
+@pytest.mark.parametrize("cin,cout,H,W,a_act,res", [(72, 40, 16, 16, ACT_RELU, False), (120, 40, 9, 13, ACT_RELU, True),
+                                                      (672, 112, 8, 8, ACT_HSWISH, True), (960, 160, 5, 7, ACT_HSWISH, False),
+                                                      (16, 16, 33, 18, ACT_NONE, False)])
+def test_conv_tc_se_prologue(cin, cout, H, W, a_act, res):
+    """Project 1x1 with the SE apply fused in front: y = W * act(x * s[n, c]) + b (+ res)."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    N = 3
+    x = q(gen(N, cin, H, W, seed=1), dtype)
+    sc = torch.rand(N, cin, generator=torch.Generator().manual_seed(5))
+    w = q(gen(cout, cin, 1, 1, seed=2, scale=cin ** -0.5), dtype)
+    b = gen(cout, seed=3, scale=0.1)
+    r = q(gen(N, cout, H, W, seed=4), dtype) if res else None
+    a = q(act_ref(x * sc.view(N, cin, 1, 1), a_act), dtype)  # the kernel re-rounds the transformed tile to bf16
+    ref = F.conv2d(a, w, b) + (r if res else 0)
+    xm = to_map(x, dtype)
+    ym = to_map(torch.zeros(N, cout, H, W), dtype)
+    rm = to_map(r, dtype) if res else None
+    n16, c64 = -(-cout // 16) * 16, -(-cin // 64) * 64
+    pk = torch.zeros(n16, 1, c64)
+    pk[:cout, :, :cin] = w.reshape(cout, 1, cin)
+    pk, bd, scd = pk.to("cuda", dtype).contiguous(), b.cuda(), sc.cuda().contiguous()
+    check(lib.cabinet_conv_tc_se(xm.ptr, xm.ld, N, H, W, cin, scd.data_ptr(), a_act, pk.data_ptr(), cout, 1, 1, 1, 0,
+                                 bd.data_ptr(), rm.ptr if res else None, rm.ld if res else 0, ym.ptr, ym.dt, ym.ld, H, W,
+                                 ACT_NONE, stream()), "conv_tc_se")
+    torch.cuda.synchronize()
+    err = rel_l2(from_map(ym), ref)
+    print(f"conv_tc_se cin={cin} cout={cout}: rel_l2 {err:.3e}")
+    assert err < 6e-3
