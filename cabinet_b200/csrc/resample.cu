@@ -95,7 +95,35 @@ __device__ __forceinline__ void upsample_group8(const float* __restrict__ x, int
     const float* r1 = x + (static_cast<long long>(n) * IH + y1) * IW * C;
     if constexpr (EXACT8) {
         const int xa = max(g - 1, 0), xb = g, xc = min(g + 1, IW - 1);
-        for (int c = 0; c < C; ++c) {
+        int cstart = 0;
+        if ((C & 3) == 0) {  // 4 classes per 16-byte load: 6 loads feed 32 outputs
+            cstart = C;
+            for (int c4 = 0; c4 < C; c4 += 4) {
+                const float4 ta = __ldg(reinterpret_cast<const float4*>(r0 + xa * C + c4));
+                const float4 tb = __ldg(reinterpret_cast<const float4*>(r0 + xb * C + c4));
+                const float4 tcc = __ldg(reinterpret_cast<const float4*>(r0 + xc * C + c4));
+                const float4 ba = __ldg(reinterpret_cast<const float4*>(r1 + xa * C + c4));
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(r1 + xb * C + c4));
+                const float4 bc = __ldg(reinterpret_cast<const float4*>(r1 + xc * C + c4));
+                const float tav[4] = {ta.x, ta.y, ta.z, ta.w}, tbv[4] = {tb.x, tb.y, tb.z, tb.w};
+                const float tcv[4] = {tcc.x, tcc.y, tcc.z, tcc.w}, bav[4] = {ba.x, ba.y, ba.z, ba.w};
+                const float bbv[4] = {bb.x, bb.y, bb.z, bb.w}, bcv[4] = {bc.x, bc.y, bc.z, bc.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float va = tav[k] + wy * (bav[k] - tav[k]), vb = tbv[k] + wy * (bbv[k] - tbv[k]);
+                    const float vc = tcv[k] + wy * (bcv[k] - tcv[k]);
+                    const float d0 = vb - va, d1 = vc - vb;
+                    float v[PXG];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        v[j] = va + ((j + 4.5f) * 0.125f) * d0;
+                        v[j + 4] = vb + ((j + 0.5f) * 0.125f) * d1;
+                    }
+                    consume(c4 + k, v);
+                }
+            }
+        }
+        for (int c = cstart; c < C; ++c) {
             const float ta = __ldg(r0 + xa * C + c), tb = __ldg(r0 + xb * C + c), tcc = __ldg(r0 + xc * C + c);
             const float ba = __ldg(r1 + xa * C + c), bb = __ldg(r1 + xb * C + c), bc = __ldg(r1 + xc * C + c);
             const float va = ta + wy * (ba - ta), vb = tb + wy * (bb - tb), vc = tcc + wy * (bc - tcc);
