@@ -46,6 +46,7 @@ SIGNATURES = {
     "cabinet_bilinear_nhwc": ([_p, _ll, _i, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p], _i),
     "cabinet_upsample_logits_nchw": ([_p, _i, _i, _i, _i, _p, _i, _i, _i, _p], _i),
     "cabinet_upsample_argmax": ([_p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p], _i),
+    "cabinet_normalize_u8": ([_p, _p, _i, _i, _i, _f, _f, _f, _f, _f, _f, _p], _i),
     "cabinet_confusion_hist": ([_p, _i, _p, _i, _ll, _i, _i, _p, _p], _i),
 }
 

@@ -268,7 +268,50 @@ confusion_hist_kernel(const TP* __restrict__ pred, const TL* __restrict__ labels
         if (s_hist[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(s_hist[i]));
 }
 
+// uint8 HWC image -> normalised fp32 NCHW: y[n][c][h][w] = (x[n][h][w][c] / 255 - mean[c]) / std[c]
+// (torchvision ToTensor + Normalize of the reference datasets, src/datasets/uavid.py:175-183, cityscapes.py:102-109).
+// One thread = 4 pixels: three 32-bit loads (12 bytes), three float4 stores (one per plane).
+__global__ void __launch_bounds__(256)
+normalize_u8_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, long long HW4, long long HW, float m0, float m1,
+                    float m2, float i0, float i1, float i2) {
+    const int n = blockIdx.y;
+    const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= HW4) return;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(x + (static_cast<long long>(n) * HW + q * 4) * 3);
+    const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+    uint8_t b[12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        b[i] = (w0 >> (8 * i)) & 0xff;
+        b[4 + i] = (w1 >> (8 * i)) & 0xff;
+        b[8 + i] = (w2 >> (8 * i)) & 0xff;
+    }
+    const float k = 1.f / 255.f;
+    float* o = y + static_cast<long long>(n) * 3 * HW + q * 4;
+    __stcs(reinterpret_cast<float4*>(o), make_float4((b[0] * k - m0) * i0, (b[3] * k - m0) * i0, (b[6] * k - m0) * i0,
+                                                      (b[9] * k - m0) * i0));
+    __stcs(reinterpret_cast<float4*>(o + HW), make_float4((b[1] * k - m1) * i1, (b[4] * k - m1) * i1,
+                                                           (b[7] * k - m1) * i1, (b[10] * k - m1) * i1));
+    __stcs(reinterpret_cast<float4*>(o + 2 * HW), make_float4((b[2] * k - m2) * i2, (b[5] * k - m2) * i2,
+                                                               (b[8] * k - m2) * i2, (b[11] * k - m2) * i2));
+}
+
 }  // namespace
+
+extern "C" int cabinet_normalize_u8(const uint8_t* x, float* y, int N, int H, int W, float mean0, float mean1,
+                                    float mean2, float std0, float std1, float std2, cabinet_stream_t stream) {
+    CAB_REQUIRE(x && y && H > 0 && W > 0 && N >= 0 && N <= 65535, "normalize_u8: bad arguments");
+    const long long HW = static_cast<long long>(H) * W;
+    CAB_REQUIRE(HW % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                "normalize_u8: H*W must be a multiple of 4 and the buffers aligned");
+    CAB_REQUIRE(std0 > 0 && std1 > 0 && std2 > 0, "normalize_u8: std must be positive");
+    if (N == 0) return CABINET_OK;
+    dim3 grid(static_cast<unsigned>(cab_ceil_div(HW / 4, 256)), N);
+    normalize_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, HW / 4, HW, mean0, mean1, mean2,
+                                                                             1.f / std0, 1.f / std1, 1.f / std2);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
 
 extern "C" int cabinet_bilinear_nhwc(const void* x, long long ldx, int x_dtype, void* y, long long ldy, int y_dtype,
                                      int N, int IH, int IW, int C, int OH, int OW, cabinet_stream_t stream) {

@@ -178,6 +178,12 @@ int cabinet_upsample_argmax(const float* x, int N, int IH, int IW, int C, uint8_
                             const void* labels, int label_dtype, int ignore_label, long long* hist,
                             cabinet_stream_t stream);
 
+/* uint8 HWC image batch [N][H][W][3] -> normalised fp32 NCHW [N][3][H][W]: (x/255 - mean[c]) / std[c], i.e.
+ * torchvision ToTensor + Normalize of the reference datasets (src/datasets/uavid.py:175-183,
+ * src/datasets/cityscapes.py:102-109) on the device, so only 3 bytes per pixel cross PCIe.  H*W % 4 == 0. */
+int cabinet_normalize_u8(const uint8_t* x, float* y, int N, int H, int W, float mean0, float mean1, float mean2,
+                         float std0, float std1, float std2, cabinet_stream_t stream);
+
 /* Confusion matrix of an existing prediction map (pred int64 or uint8 like labels):
  * hist[clip(pred)*C + clip(label)] += 1 where label != ignore_label (src/scripts/evaluate.py:162-191). */
 int cabinet_confusion_hist(const void* pred, int pred_dtype, const void* labels, int label_dtype, long long n_pixels,

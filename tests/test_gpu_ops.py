@@ -423,3 +423,16 @@ def test_conv_tc_se_prologue(cin, cout, H, W, a_act, res):
     err = rel_l2(from_map(ym), ref)
     print(f"conv_tc_se cin={cin} cout={cout}: rel_l2 {err:.3e}")
     assert err < 6e-3
+
+
+def test_normalize_u8_matches_totensor_normalize():
+    lib = _lib.load()
+    N, H, W = 2, 18, 22
+    x = torch.randint(0, 256, (N, H, W, 3), generator=torch.Generator().manual_seed(1), dtype=torch.uint8)
+    mean, std = (0.480, 0.499, 0.457), (0.225, 0.208, 0.228)
+    ref = (x.permute(0, 3, 1, 2).float() / 255 - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    xd = x.cuda()
+    y = torch.empty(N, 3, H, W, device="cuda")
+    check(lib.cabinet_normalize_u8(xd.data_ptr(), y.data_ptr(), N, H, W, *mean, *std, stream()), "normalize_u8")
+    torch.cuda.synchronize()
+    assert float((y.cpu() - ref).abs().max()) < 2e-6
