@@ -49,19 +49,17 @@ psp_pool_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ pool
     }
 }
 
-// thread per (pixel, channel): out[pix][0:C] = x, out[pix][C*(1+si) + c] = bilinear(pooled_si)(pix, c)
+// grid (ceil(W*C/256), H, N); thread per (column, channel): out[pix][0:C] = x, out[pix][C*(1+si) + c] =
+// bilinear(pooled_si)(pix, c).  32-bit index arithmetic; row taps are per-block constants.
 template <typename T>
 __global__ void __launch_bounds__(256)
 psp_concat_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ pooled, T* __restrict__ out,
-                  long long ldo, int H, int W, int C, long long total) {
-    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c = static_cast<int>(idx % C);
-    const long long pix = idx / C;
-    const int w = static_cast<int>(pix % W);
-    const long long t = pix / W;
-    const int h = static_cast<int>(t % H);
-    const int n = static_cast<int>(t / H);
+                  long long ldo, int H, int W, int C) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<unsigned>(W) * C) return;
+    const int w = idx / C, c = idx - w * C;
+    const int h = blockIdx.y, n = blockIdx.z;
+    const long long pix = (static_cast<long long>(n) * H + h) * W + w;
     T* o = out + pix * ldo;
     o[c] = x[pix * ldx + c];
     const float* pn = pooled + static_cast<long long>(n) * kPspBins * C;
@@ -103,15 +101,15 @@ extern "C" int cabinet_psp_concat(const void* x, long long ldx, const float* poo
     CAB_REQUIRE(x && pooled && out && H > 0 && W > 0 && C > 0 && ldx >= C && ldo >= 5LL * C,
                 "psp_concat: bad arguments");
     if (N == 0) return CABINET_OK;
-    const long long total = static_cast<long long>(N) * H * W * C;
-    dim3 grid(static_cast<unsigned>(cab_ceil_div(total, 256)));
+    CAB_REQUIRE(H <= 65535 && N <= 65535, "psp_concat: H/N exceed grid limits");
+    dim3 grid(static_cast<unsigned>(cab_ceil_div(static_cast<long long>(W) * C, 256)), H, N);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == CABINET_BF16)
         psp_concat_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), ldx, pooled,
-                                                    reinterpret_cast<bf16*>(out), ldo, H, W, C, total);
+                                                    reinterpret_cast<bf16*>(out), ldo, H, W, C);
     else
         psp_concat_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), ldx, pooled,
-                                                     reinterpret_cast<float*>(out), ldo, H, W, C, total);
+                                                     reinterpret_cast<float*>(out), ldo, H, W, C);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

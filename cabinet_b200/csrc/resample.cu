@@ -42,19 +42,16 @@ bilinear_nhwc_kernel(const TI* __restrict__ x, long long ldx, TO* __restrict__ y
     }
 }
 
-// bf16 -> bf16, C % 8 == 0: one thread = one output pixel x 8 channels (four 16-byte loads, one 16-byte store)
+// bf16 -> bf16, C % 8 == 0: grid (x-chunks, OH, N); one thread = one output pixel x 8 channels (four 16-byte loads, one
+// 16-byte store); row taps are per-block constants, 32-bit index arithmetic only.
 __global__ void __launch_bounds__(256)
 bilinear_nhwc_bf16x8_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy, int IH,
-                            int IW, int C, int OH, int OW, long long total, float sh, float sw) {
-    const int CG = C / 8;
-    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int cg = static_cast<int>(idx % CG);
-    long long t = idx / CG;
-    const int ow = static_cast<int>(t % OW);
-    t /= OW;
-    const int oh = static_cast<int>(t % OH);
-    const int n = static_cast<int>(t / OH);
+                            int IW, int C, int OH, int OW, float sh, float sw) {
+    const int CG = C >> 3;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<unsigned>(OW) * CG) return;
+    const int ow = idx / CG, cg = idx - ow * CG;
+    const int oh = blockIdx.y, n = blockIdx.z;
     int y0, y1, x0, x1;
     float wy, wx;
     cab_bilinear_tap(oh, sh, IH, y0, y1, wy);
@@ -322,9 +319,10 @@ extern "C" int cabinet_bilinear_nhwc(const void* x, long long ldx, int x_dtype, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (x_dtype == CABINET_BF16 && y_dtype == CABINET_BF16 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 &&
         (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
-        const long long tot8 = static_cast<long long>(N) * OH * OW * (C / 8);
-        bilinear_nhwc_bf16x8_kernel<<<static_cast<unsigned>(cab_ceil_div(tot8, 256)), 256, 0, s>>>(
-            reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(y), ldy, IH, IW, C, OH, OW, tot8, sh, sw);
+        CAB_REQUIRE(OH <= 65535 && N <= 65535, "bilinear_nhwc: OH/N exceed grid limits");
+        dim3 g8(static_cast<unsigned>(cab_ceil_div(static_cast<long long>(OW) * (C / 8), 256)), OH, N);
+        bilinear_nhwc_bf16x8_kernel<<<g8, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(y),
+                                                       ldy, IH, IW, C, OH, OW, sh, sw);
         CAB_LAUNCH_CHECK();
         return CABINET_OK;
     }
