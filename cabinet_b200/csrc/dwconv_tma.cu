@@ -135,6 +135,130 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmX, const DwParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused no-expand inverted-residual block (reference: src/models/mobilenetv3.py:110-125,154-159 with inp == hidden,
+// no SE, stride 1, identity): y = x + W2 * act(dw3x3(x) + b1) + b2 for C <= 32 channels (Large f1: C = 16 at 1/2
+// resolution, the two largest-area tensors of the backbone).  The input patch (+halo) is staged once by TMA; the
+// depthwise result stays in shared memory (fp32), the tiny C x C pointwise runs on the CUDA cores and the residual
+// comes from the centre of the staged patch: one HBM read + one HBM write instead of five tensor passes.
+struct Mb1Params {
+    int C, OH, OW, act;
+    const float* w_dw;   // [9][C]
+    const float* b_dw;   // [C]
+    const float* w_pw;   // [C][C] (cout, cin)
+    const float* b_pw;   // [C]
+    bf16* y;
+    long long ldy;
+};
+
+constexpr int MB_TH = 16, MB_TW = 32;  // output patch of the fused block kernel (512 pixels)
+
+template <int C>
+__global__ void __launch_bounds__(256)
+mbconv1_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mb1Params p) {
+    constexpr int K = 3, PAD = 1, COLS = 8;
+    constexpr int IWT = MB_TW + 2, IHT = MB_TH + 2;
+    constexpr int PITCH = C * 2;            // staged pixel pitch in bytes (TMA box = exactly C channels)
+    constexpr int LANES_PX = C / 2;         // lanes per pixel (channel pairs)
+    constexpr int GROUPS = MB_TW / COLS;    // column groups per row
+    extern __shared__ __align__(128) uint8_t smem_dw[];
+    __shared__ __align__(8) uint64_t bar;
+    const int tiles_w = (p.OW + MB_TW - 1) / MB_TW;
+    const int ow0 = (blockIdx.x % tiles_w) * MB_TW, oh0 = (blockIdx.x / tiles_w) * MB_TH;
+    const int n = blockIdx.z;
+    uint8_t* tile = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dw) + 127) & ~uintptr_t(127));
+    float* hs = reinterpret_cast<float*>(tile + ((IWT * IHT * PITCH + 127) & ~127));  // [512 px][C] fp32 dw output
+
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_fence_init();
+        tc::fence_proxy_async();
+        tc::mbar_expect_tx(&bar, static_cast<uint32_t>(IWT * IHT * PITCH));
+        tc::tma_load_4d(tile, &tmX, &bar, 0, ow0 - PAD, oh0 - PAD, n);
+    }
+    __syncthreads();
+    // ---- phase 1: depthwise 3x3 + bias + act; work item = (row, column group of 8, channel pair)
+    {
+        constexpr int ITEMS = MB_TH * GROUPS * LANES_PX;
+        float2 w[K * K];
+        const int cl = threadIdx.x % LANES_PX;
+        const int c0 = cl * 2;
+#pragma unroll
+        for (int t = 0; t < K * K; ++t) w[t] = __ldg(reinterpret_cast<const float2*>(p.w_dw + t * C + c0));
+        const float2 b = __ldg(reinterpret_cast<const float2*>(p.b_dw + c0));
+        tc::mbar_wait(&bar, 0);
+        for (int item = threadIdx.x; item < ITEMS; item += 256) {  // 256 % LANES_PX == 0: cl is loop invariant
+            const int rest = item / LANES_PX;
+            const int grp = rest % GROUPS, row = rest / GROUPS;
+            const int col0 = grp * COLS;
+            float acc[COLS][2];
+#pragma unroll
+            for (int r = 0; r < COLS; ++r) {
+                acc[r][0] = b.x;
+                acc[r][1] = b.y;
+            }
+            const uint32_t base = tc::smem_u32(tile) + (row * IWT + col0) * PITCH + cl * 4;
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+                for (int sx = 0; sx < COLS + K - 1; ++sx) {
+                    uint32_t raw;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(base + (ky * IWT + sx) * PITCH));
+                    const float x0 = __uint_as_float(raw << 16), x1 = __uint_as_float(raw & 0xffff0000u);
+#pragma unroll
+                    for (int r = 0; r < COLS; ++r) {
+                        const int kx = sx - r;
+                        if (kx >= 0 && kx < K) {
+                            acc[r][0] = fmaf(x0, w[ky * K + kx].x, acc[r][0]);
+                            acc[r][1] = fmaf(x1, w[ky * K + kx].y, acc[r][1]);
+                        }
+                    }
+                }
+            cab_act_vec<2 * COLS>(&acc[0][0], p.act);
+#pragma unroll
+            for (int r = 0; r < COLS; ++r)
+                *reinterpret_cast<float2*>(hs + (row * MB_TW + col0 + r) * C + c0) = make_float2(acc[r][0], acc[r][1]);
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: pointwise C -> C (+ bias + residual); work item = (pixel, cout pair)
+    {
+        constexpr int PAIRS = C / 2;
+        const int cp = threadIdx.x % PAIRS;
+        const int co = cp * 2;
+        float w0[C], w1[C];
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+            w0[ci] = __ldg(p.w_pw + co * C + ci);
+            w1[ci] = __ldg(p.w_pw + (co + 1) * C + ci);
+        }
+        const float2 b = __ldg(reinterpret_cast<const float2*>(p.b_pw + co));
+        for (int px = threadIdx.x / PAIRS; px < MB_TH * MB_TW; px += 256 / PAIRS) {
+            const int row = px / MB_TW, col = px % MB_TW;
+            const int oh = oh0 + row, ow = ow0 + col;
+            if (oh >= p.OH || ow >= p.OW) continue;
+            const float* h = hs + px * C;
+            float o0 = b.x, o1 = b.y;
+#pragma unroll
+            for (int ci = 0; ci < C; ci += 4) {
+                const float4 hv = *reinterpret_cast<const float4*>(h + ci);
+                o0 = fmaf(hv.x, w0[ci], o0); o0 = fmaf(hv.y, w0[ci + 1], o0);
+                o0 = fmaf(hv.z, w0[ci + 2], o0); o0 = fmaf(hv.w, w0[ci + 3], o0);
+                o1 = fmaf(hv.x, w1[ci], o1); o1 = fmaf(hv.y, w1[ci + 1], o1);
+                o1 = fmaf(hv.z, w1[ci + 2], o1); o1 = fmaf(hv.w, w1[ci + 3], o1);
+            }
+            uint32_t raw;  // residual: the block input at the same pixel (centre of the staged patch)
+            asm volatile("ld.shared.u32 %0, [%1];"
+                         : "=r"(raw)
+                         : "r"(tc::smem_u32(tile) + ((row + PAD) * IWT + col + PAD) * PITCH + co * 2));
+            o0 += __uint_as_float(raw << 16);
+            o1 += __uint_as_float(raw & 0xffff0000u);
+            *reinterpret_cast<__nv_bfloat162*>(p.y + ((static_cast<long long>(n) * p.OH + oh) * p.OW + ow) * p.ldy + co) =
+                __floats2bfloat162_rn(o0, o1);
+        }
+    }
+}
+
 template <int K, int S>
 int launch(const CUtensorMap& tm, const DwParams& p, int N, int n_chunks, cudaStream_t s) {
     constexpr int IWT = (TW - 1) * S + K, IHT = (TH - 1) * S + K;
@@ -152,6 +276,44 @@ int launch(const CUtensorMap& tm, const DwParams& p, int N, int n_chunks, cudaSt
 }
 
 }  // namespace
+
+extern "C" int cabinet_mbconv_noexpand_fused(const void* x, long long ldx, const float* w_dw, const float* b_dw,
+                                             const float* w_pw, const float* b_pw, void* y, long long ldy, int N,
+                                             int H, int W, int C, int act, cabinet_stream_t stream) {
+    CAB_REQUIRE(x && w_dw && b_dw && w_pw && b_pw && y, "mbconv_noexpand_fused: null pointer");
+    CAB_REQUIRE(C >= 8 && C <= 32 && (C & (C - 1)) == 0, "mbconv_noexpand_fused: C must be 8, 16 or 32 (got %d)", C);
+    CAB_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(y) & 3) == 0 && N <= 65535,
+                "mbconv_noexpand_fused: alignment");
+    if (N == 0) return CABINET_OK;
+    CUtensorMap tm;
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t strides[3] = {(uint64_t)ldx * 2, (uint64_t)ldx * 2 * W, (uint64_t)ldx * 2 * W * H};
+    const uint32_t box[4] = {(uint32_t)C, (uint32_t)(MB_TW + 2), (uint32_t)(MB_TH + 2), 1};
+    int rc = cab_make_tmap_bf16(&tm, x, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    Mb1Params p;
+    p.C = C; p.OH = H; p.OW = W; p.act = act; p.w_dw = w_dw; p.b_dw = b_dw; p.w_pw = w_pw; p.b_pw = b_pw;
+    p.y = reinterpret_cast<bf16*>(y); p.ldy = ldy;
+    const size_t smem = static_cast<size_t>(MB_TW + 2) * (MB_TH + 2) * C * 2 + 128 +
+                        static_cast<size_t>(MB_TH) * MB_TW * C * 4 + 128;
+    const int tiles = ((W + MB_TW - 1) / MB_TW) * ((H + MB_TH - 1) / MB_TH);
+    dim3 grid(tiles, 1, N);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CAB_CUDA(cudaFuncSetAttribute(mbconv1_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CAB_CUDA(cudaFuncSetAttribute(mbconv1_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CAB_CUDA(cudaFuncSetAttribute(mbconv1_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        attr_done = true;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (C == 8) mbconv1_fused_kernel<8><<<grid, 256, smem, st>>>(tm, p);
+    else if (C == 16) mbconv1_fused_kernel<16><<<grid, 256, smem, st>>>(tm, p);
+    else mbconv1_fused_kernel<32><<<grid, 256, smem, st>>>(tm, p);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
 
 extern "C" int cabinet_dwconv_tma(const void* x, long long ldx, const float* w, const float* bias, void* y,
                                   long long ldy, int N, int H, int W, int C, int k, int stride, int OH, int OW, int act,

@@ -160,6 +160,10 @@ class Engine:
             if s["se"]:
                 e["se"] = GateLayer(se.fc[0].weight, se.fc[0].bias, se.fc[2].weight, se.fc[2].bias, ACT_HSIGMOID)
             e["pw2"] = ConvLayer(pw2, bn2, ACT_NONE, wd, f"mobile.f{bi}.project")
+            if (not s["expand"] and not s["se"] and s["identity"] and s["k"] == 3 and s["exp"] in (8, 16, 32)
+                    and self.precision == "bf16"):
+                w2, b2 = _fold(pw2.weight, pw2.bias, bn2)  # fused whole-block kernel keeps the pointwise in fp32
+                e["fused_pw"] = (w2.reshape(w2.shape[0], -1).contiguous(), b2.contiguous())
             self.blocks.append(e)
         self.last = ConvLayer(mob.conv[0], mob.conv[1], ACT_HSWISH, wd, "mobile.conv")
 
@@ -387,6 +391,16 @@ class Engine:
         gi = 0
         for e in self.blocks:
             s = e["spec"]
+            if "fused_pw" in e and self.use_tc and f.ld % 8 == 0 and f.off % 8 == 0:
+                o = self.new(f.N, f.H, f.W, s["out"])
+                dw = e["dw"]
+                es = f.t.element_size()
+                self._run("mbconv_noexpand_fused", dw.name.replace(".dw", ""), 2 * f.N * f.H * f.W * f.C * es,
+                          2 * f.N * f.H * f.W * f.C * (9 + f.C), self.lib.cabinet_mbconv_noexpand_fused, f.ptr, f.ld,
+                          dw.w.data_ptr(), dw.b.data_ptr(), e["fused_pw"][0].data_ptr(), e["fused_pw"][1].data_ptr(),
+                          o.ptr, o.ld, f.N, f.H, f.W, f.C, dw.act, self.stream)
+                f = o
+                continue
             h = self.conv(f, e["pw1"]) if s["expand"] else f
             if "se" in e:
                 gap = gap_all[gi].view(-1)[: N * s["exp"]].view(N, s["exp"])

@@ -112,6 +112,13 @@ int cabinet_dwconv_tma(const void* x, long long ldx, const float* w, const float
                        int H, int W, int C, int k, int stride, int OH, int OW, int act, float* gap_sum,
                        cabinet_stream_t stream);
 
+/* Whole no-expand inverted-residual block in one kernel (inp == hidden, no SE, stride 1, identity):
+ *   y = x + W_pw * act(dw3x3(x) + b_dw) + b_pw     (src/models/mobilenetv3.py:110-125,154-159; Large f1)
+ * bf16 NHWC in/out, C in {8,16,32}; w_dw fp32 [9][C], w_pw fp32 [C][C] (cout, cin), biases fp32, all BN-folded. */
+int cabinet_mbconv_noexpand_fused(const void* x, long long ldx, const float* w_dw, const float* b_dw,
+                                  const float* w_pw, const float* b_pw, void* y, long long ldy, int N, int H, int W,
+                                  int C, int act, cabinet_stream_t stream);
+
 /* Squeeze-excite / FFM channel gate: scale[n][c] = gate(b2 + W2 * relu(b1 + W1 * (sum[n]/HW))).
  * Replaces src/models/mobilenetv3.py:68-83 (gate = CABINET_ACT_HSIGMOID, biases present) and
  * src/models/cabinet.py:146-150 (gate = CABINET_ACT_SIGMOID, b1 = b2 = NULL).  All fp32. */

@@ -436,3 +436,22 @@ def test_normalize_u8_matches_totensor_normalize():
     check(lib.cabinet_normalize_u8(xd.data_ptr(), y.data_ptr(), N, H, W, *mean, *std, stream()), "normalize_u8")
     torch.cuda.synchronize()
     assert float((y.cpu() - ref).abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("C,H,W,act", [(16, 32, 48, ACT_RELU), (16, 13, 21, ACT_RELU), (32, 9, 7, ACT_HSWISH), (8, 40, 16, ACT_RELU)])
+def test_mbconv_noexpand_fused(C, H, W, act):
+    """y = x + W2 * act(dw3x3(x) + b1) + b2 in one kernel vs the three torch ops."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    N = 2
+    x = q(gen(N, C, H, W, seed=1), dtype)
+    wd, bd = gen(C, 1, 3, 3, seed=2, scale=0.3), gen(C, seed=3, scale=0.1)
+    wp, bp = gen(C, C, 1, 1, seed=4, scale=C ** -0.5), gen(C, seed=5, scale=0.1)
+    ref = x + F.conv2d(act_ref(F.conv2d(x, wd, bd, 1, 1, 1, C), act), wp, bp)
+    xm, ym = to_map(x, dtype, ld=C + 8, off=8), to_map(torch.zeros_like(ref), dtype)
+    wdd, bdd = wd.view(C, -1).t().contiguous().cuda(), bd.cuda()
+    wpd, bpd = wp.view(C, C).contiguous().cuda(), bp.cuda()
+    check(lib.cabinet_mbconv_noexpand_fused(xm.ptr, xm.ld, wdd.data_ptr(), bdd.data_ptr(), wpd.data_ptr(), bpd.data_ptr(),
+                                            ym.ptr, ym.ld, N, H, W, C, act, stream()), "mbconv1")
+    torch.cuda.synchronize()
+    assert rel_l2(from_map(ym), ref) < tol(dtype)
