@@ -475,6 +475,9 @@ class Engine:
         odt = BF16 if out_dtype == torch.bfloat16 else F32
         tdt = torch.bfloat16 if odt == BF16 else torch.float32
         outs = [torch.empty((N, self.n_classes, H, W), dtype=tdt, device=self.dev) for _ in range(2)]
+        if N == 0:  # empty batch: nothing to launch
+            self.launches = 0
+            return outs[0], outs[1]
         chunk = self.sub_batch if self.sub_batch and self.sub_batch < N else N
         launches = 0
         for i in range(0, N, chunk):  # images are independent units: optional L2-sized sub-batches
@@ -491,7 +494,7 @@ class Engine:
         returned tensors are then the graph's static output buffers (overwritten by the next call of that shape)."""
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
-        if not self.use_cuda_graph or self.trace is not None or self.debug:
+        if not self.use_cuda_graph or self.trace is not None or self.debug or x.shape[0] == 0:
             return self._forward_eager(x, out_dtype)
         key = (tuple(x.shape), out_dtype, self.sub_batch)
         g = self._graphs.get(key)
@@ -528,6 +531,8 @@ class Engine:
     @torch.no_grad()
     def forward_mask(self, x):
         N, _, H, W = x.shape
+        if N == 0:
+            return torch.empty((0, H, W), dtype=torch.uint8, device=self.dev)
         final8, _ = self._trunk(x)
         return self._argmax(final8, N, H, W)
 
@@ -542,6 +547,8 @@ class Engine:
             raise ValueError("hist must be an int64 (C,C) tensor on the model's device")
         if tuple(labels.shape) != (N, H, W):
             raise ValueError(f"labels shape {tuple(labels.shape)} != {(N, H, W)}")
+        if N == 0:
+            return torch.empty((0, H, W), dtype=torch.uint8, device=self.dev)
         final8, _ = self._trunk(x)
         return self._argmax(final8, N, H, W, labels, hist, ignore_label)
 
