@@ -281,8 +281,9 @@ def run_ours(args):
         from cabinet_b200.evaluator import MscEvalV0
 
         masks = [torch.empty((B, S, S), dtype=torch.uint8).pin_memory() for _ in range(K)]  # D2H targets, allocated up front
-        MscEvalV0(model, [(x_host, lb_host)] * 2, C, 255, (1.0,), False, cropsize=S).evaluate(masks_out=masks)
-        ev = MscEvalV0(model, [(x_host, lb_host)] * K, C, 255, (1.0,), False, cropsize=S)
+        ev = MscEvalV0(model, [(x_host, lb_host)] * 4, C, 255, (1.0,), False, cropsize=S)
+        ev.evaluate(masks_out=masks)  # warm-up: device buffers + captured graphs of the fused forward/hist call
+        ev.dl = [(x_host, lb_host)] * K
         barrier()
         t0 = time.perf_counter()
         e0.record()
@@ -301,8 +302,9 @@ def run_ours(args):
         u8_host = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8,
                                 generator=torch.Generator().manual_seed(21 + rank)).pin_memory()
         masks8 = masks
-        MscEvalV0(model, [(u8_host, lb_host)] * 2, C, 255, (1.0,), False, cropsize=S).evaluate(masks_out=masks8)
-        ev8 = MscEvalV0(model, [(u8_host, lb_host)] * K, C, 255, (1.0,), False, cropsize=S)
+        ev8 = MscEvalV0(model, [(u8_host, lb_host)] * 4, C, 255, (1.0,), False, cropsize=S)
+        ev8.evaluate(masks_out=masks8)
+        ev8.dl = [(u8_host, lb_host)] * K
         barrier()
         e0.record()
         res8 = ev8.evaluate(masks_out=masks8)
@@ -335,10 +337,10 @@ def run_ours(args):
         "kernels": table, "traced_ms_per_step": traced_ms, "peaks": peaks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        rate, threads, times = cpu_forward_rate(args.mode, C, S, 1, 5, 2)
+        rate, threads, times = cpu_forward_rate(args.mode, C, S, 1, 60, 3)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"5 timed forwards of 1 image {S}x{S} fp32 (median), oracle port of the "
-                                          f"reference forward, {sum(times):.1f} s of CPU work"}
+                                "sample": f"{len(times)} timed forwards of 1 image {S}x{S} fp32 (median), oracle port of "
+                                          f"the reference forward, {sum(times):.1f} s of CPU work on {threads} threads"}
     print(json.dumps(line))
 
 

@@ -346,7 +346,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
             }
         }
-        if (leader) tc::bulk_wait<0>();
+        if (leader) tc::bulk_wait_read<0>();  // smem must outlive the reads; global visibility comes with grid completion
     }
     tc::tc_fence_before();
     __syncthreads();

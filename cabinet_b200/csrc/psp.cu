@@ -11,9 +11,9 @@ constexpr int kPspBins = 110;
 
 // grid (110, N): one bin per block; threads = (C/4 channel quads) x (pixel lanes), smem tree over the pixel lanes.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 psp_pool_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ pooled, int H, int W, int C) {
-    __shared__ float4 red[256];
+    __shared__ float4 red[1024];
     const int bin = blockIdx.x, n = blockIdx.y;
     int si = 3;
     if (bin < 1) si = 0; else if (bin < 10) si = 1; else if (bin < 46) si = 2;
@@ -86,7 +86,7 @@ extern "C" int cabinet_psp_pool(const void* x, long long ldx, int dtype, float* 
                 "psp_pool: bad arguments (C must be a multiple of 4, <= 1024)");
     if (N == 0) return CABINET_OK;
     dim3 grid(kPspBins, N);
-    const int threads = 256;
+    const int threads = 1024;  // (C/4 channel quads) x (pixel lanes): the s = 1 bin spans the whole map
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == CABINET_BF16)
         psp_pool_kernel<bf16><<<grid, threads, 0, s>>>(reinterpret_cast<const bf16*>(x), ldx, pooled, H, W, C);

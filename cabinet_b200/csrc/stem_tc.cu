@@ -241,7 +241,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 tc::bulk_commit();
             }
         }
-        if (leader) tc::bulk_wait<0>();
+        if (leader) tc::bulk_wait_read<0>();  // smem must outlive the reads; global visibility comes with grid completion
     }
     tc::tc_fence_before();
     __syncthreads();

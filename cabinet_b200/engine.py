@@ -135,6 +135,7 @@ class Engine:
         self.use_cuda_graph = False
         self.sub_batch = 0          # > 0: run the schedule over chunks of this many images
         self._graphs = {}
+        self._graph_seen = {}
         with torch.no_grad():
             self._pack(model)
 
@@ -528,6 +529,27 @@ class Engine:
                   hist.data_ptr() if hist is not None else None, self.stream)
         return mask
 
+    def _graphed(self, key, fn):
+        """Run ``fn`` eagerly the first time a key (shapes + buffer addresses) is seen, capture it into a CUDA graph
+        the second time, replay afterwards.  ``fn`` must only touch the buffers named in the key."""
+        if not self.use_cuda_graph or self.trace is not None or self.debug:
+            return fn()
+        g = self._graphs.get(key)
+        if g is None:
+            seen = self._graph_seen.get(key, 0) + 1
+            self._graph_seen[key] = seen
+            if seen < 2 or len(self._graphs) >= 16:
+                return fn()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = fn()
+            g = (graph, out, self.launches)
+            self._graphs[key] = g
+        graph, out, launches = g
+        graph.replay()
+        self.launches = launches
+        return out
+
     @torch.no_grad()
     def forward_mask(self, x):
         N, _, H, W = x.shape
@@ -549,8 +571,16 @@ class Engine:
             raise ValueError(f"labels shape {tuple(labels.shape)} != {(N, H, W)}")
         if N == 0:
             return torch.empty((0, H, W), dtype=torch.uint8, device=self.dev)
-        final8, _ = self._trunk(x)
-        return self._argmax(final8, N, H, W, labels, hist, ignore_label)
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+
+        def run():
+            final8, _ = self._trunk(x)
+            return self._argmax(final8, N, H, W, labels, hist, ignore_label)
+
+        # static buffers (an evaluator's double-buffered device tensors) -> captured once, replayed afterwards
+        return self._graphed(("hist", tuple(x.shape), x.data_ptr(), labels.data_ptr(), labels.dtype, hist.data_ptr(),
+                              ignore_label), run)
 
     # ------------------------------------------------------------------ tracing (bench / profiles)
     def start_trace(self, kernels=None):

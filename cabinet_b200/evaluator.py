@@ -133,9 +133,11 @@ class MscEvalV0:
         (forward + x8 upsample + argmax + confusion matrix in one fused tail).  ``masks_out``: optional list that
         receives a pinned uint8 host tensor per batch (asynchronous D2H, valid after the final synchronise)."""
         cur = torch.cuda.current_stream(dev)
-        copy_stream = torch.cuda.Stream(dev)
-        bufs, ready, consumed = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None, None]
-        n_batches, x32 = 0, None
+        st = self.__dict__.setdefault("_pipe", {"stream": torch.cuda.Stream(dev), "bufs": [None, None], "x32": None})
+        copy_stream, bufs, x32 = st["stream"], st["bufs"], st["x32"]  # device buffers persist across evaluate() calls
+        ready, consumed = [torch.cuda.Event(), torch.cuda.Event()], [None, None]
+        copy_stream.wait_stream(cur)
+        n_batches = 0
         for i, (images, labels) in enumerate(self.dl):
             b = i & 1
             if labels.dim() == 4:
@@ -149,8 +151,8 @@ class MscEvalV0:
             if bufs[b] is None or bufs[b][0].shape != images.shape or bufs[b][1].dtype != labels.dtype:
                 bufs[b] = (torch.empty(images.shape, dtype=images.dtype if u8 else torch.float32, device=dev),
                            torch.empty(labels.shape, dtype=labels.dtype, device=dev))
-                if u8 and (x32 is None or x32.shape[0] != images.shape[0]):
-                    x32 = torch.empty((images.shape[0], 3, H, W), dtype=torch.float32, device=dev)
+                if u8 and (x32 is None or tuple(x32.shape) != (images.shape[0], 3, H, W)):
+                    x32 = st["x32"] = torch.empty((images.shape[0], 3, H, W), dtype=torch.float32, device=dev)
                 # the caching allocator may hand out memory that kernels already queued on the compute stream
                 # still touch: order the copy stream after them, and tell the allocator about the second stream
                 copy_stream.wait_stream(cur)
