@@ -18,6 +18,8 @@
 // * Epilogue: tcgen05.ld -> +bias -> act -> (+residual) -> bf16 -> 128B-swizzled smem staging -> TMA store
 //   (full-line writes, image-border and channel clipping by the tensor map); fp32 outputs (class logits) are
 //   stored directly.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -459,7 +461,11 @@ extern "C" int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, in
     p.b_resident = (p.n_tiles == 1 && p.num_k_blocks * b_stage_bytes <= B_RESIDENT_MAX) ? 1 : 0;
     const int fixed = 4 * C_STAGE_BYTES + (p.b_resident ? p.num_k_blocks * b_stage_bytes : 0) + 1024;
     const int stage_bytes = A_STAGE_BYTES + (p.b_resident ? 0 : b_stage_bytes);
-    p.stages = std::max(2, std::min(MAX_STAGES, (SMEM_LIMIT - fixed) / stage_bytes));
+    // experiment hook: CAB_SMEM_CAP_KB caps the dynamic smem of kernels whose accumulators need <= 256 TMEM columns, so
+    // that two CTAs (e.g. from two streams) can share an SM
+    static const int cap_kb = getenv("CAB_SMEM_CAP_KB") ? atoi(getenv("CAB_SMEM_CAP_KB")) : 0;
+    const int limit = (cap_kb > 0 && p.tmem_cols <= 256) ? std::max(cap_kb * 1024, fixed + 2 * stage_bytes) : SMEM_LIMIT;
+    p.stages = std::max(2, std::min(MAX_STAGES, (std::min(limit, SMEM_LIMIT) - fixed) / stage_bytes));
     p.act = act; p.y_dtype = y_dtype; p.bias = bias; p.res = reinterpret_cast<const bf16*>(res); p.ldres = ldres;
     p.y = y; p.ldy = ldy; p.debug = g_debug;
     p.a_scale = a_scale; p.a_act = a_act; p.hw = H * W;

@@ -136,6 +136,8 @@ class Engine:
         self.sub_batch = 0          # > 0: run the schedule over chunks of this many images
         self._graphs = {}
         self._graph_seen = {}
+        self.dual_stream = False    # experimental: two half-batches on two streams
+        self._side = None
         with torch.no_grad():
             self._pack(model)
 
@@ -479,6 +481,21 @@ class Engine:
         if N == 0:  # empty batch: nothing to launch
             self.launches = 0
             return outs[0], outs[1]
+        if self.dual_stream and N >= 2:
+            # two half-batches on two streams (fork / join): the latency-bound low-resolution chain of one half
+            # overlaps the bandwidth-bound high-resolution layers of the other
+            cur = torch.cuda.current_stream(self.dev)
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.dev)
+            half = N // 2
+            self._side.wait_stream(cur)
+            self._logits(x[:half], [o[:half] for o in outs], odt)
+            launches = self.launches
+            with torch.cuda.stream(self._side):
+                self._logits(x[half:], [o[half:] for o in outs], odt)
+            cur.wait_stream(self._side)
+            self.launches += launches
+            return outs[0], outs[1]
         chunk = self.sub_batch if self.sub_batch and self.sub_batch < N else N
         launches = 0
         for i in range(0, N, chunk):  # images are independent units: optional L2-sized sub-batches
@@ -497,7 +514,7 @@ class Engine:
             x = x.float().contiguous()
         if not self.use_cuda_graph or self.trace is not None or self.debug or x.shape[0] == 0:
             return self._forward_eager(x, out_dtype)
-        key = (tuple(x.shape), out_dtype, self.sub_batch)
+        key = (tuple(x.shape), out_dtype, self.sub_batch, self.dual_stream)
         g = self._graphs.get(key)
         if g is None:
             static_x = x.clone()
