@@ -1,0 +1,628 @@
+// Fused MobileNetV3 inverted-residual block (reference: src/models/mobilenetv3.py:102-159), bf16 NHWC:
+//
+//     expand 1x1 (+BN +act)  ->  depthwise k x k (+BN [+act])  ->  [ project 1x1 (+BN) (+identity) ]
+//
+// The expanded activation is the largest tensor of every block (3x-6x the block input); unfused it is written to
+// HBM by the expand GEMM and read back by the depthwise kernel.  Here it only ever exists in shared memory:
+//
+//   per output tile (TH x TW pixels of one image), per chunk of <= 64 expanded channels
+//     1. MMA1 (tcgen05, TMEM):  D1[input pixels incl. halo][64] = A1[pixels][Cin] * W1_chunk^T
+//        A1 is ONE 4-D TMA box {64 ch, IWT, IHT, 1} of the block input (OOB zero fill = conv padding of the input).
+//     2. epilogue 1 (CUDA cores):  TMEM -> +bias -> act -> 0 outside the image (the depthwise conv pads the EXPANDED
+//        map with zeros) -> bf16 -> E tile in shared memory (144-byte pixel pitch: conflict-free 16-byte stores).
+//     3. depthwise (CUDA cores):  warp = output row (segment), lane = channel pair, taps in registers, LDS.32 per
+//        lane; result -> A2 tile [out pixels][64] in the 128B-swizzled K-major UMMA layout.
+//     4a. PROJECT:  MMA2  D2[out pixels][Cout] += A2 * W2_chunk^T  (accumulates over the chunks in TMEM); after the
+//         last chunk: TMEM -> +bias (+ residual) -> bf16 -> staging -> TMA store.
+//     4b. !PROJECT (blocks with squeeze-excite): A2 is TMA-stored as the depthwise output of this chunk and the
+//         per-(image, channel) sums for the SE pooling are accumulated; scale/act and the project GEMM follow as
+//         separate kernels (the SE gate needs the global mean first).
+//
+// Persistent CTAs, two per SM (<= 113 KB shared memory, 256 TMEM columns each): the phases of one CTA are serial,
+// the second CTA fills the gaps.  Warps 0-7 compute, warp 8 issues TMA and MMAs (MMA1 runs one chunk ahead).
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int NCW = 8;                      // compute warps
+constexpr int NTHREADS = (NCW + 1) * 32;    // + control warp
+constexpr int E_PITCH = 144;                // bytes per staged expanded pixel (64 ch bf16 + 16 B skew)
+constexpr int A2_BYTES = 128 * 128;
+constexpr int W1_CHUNK = 64 * 128;
+constexpr int TMEM_COLS = 256;
+
+struct MbParams {
+    int H, W, OH, OW, Cin, Cexp, Cout, cout_pad;
+    int n_chunks, resident, tiles_w, tiles_h, num_tiles;
+    int act_e, act_dw, has_res, ksteps1;
+    int off_e, off_a2, off_w, w_buf_bytes, off_f32;
+    int off_aux, aux_bytes, a2_bytes;
+    const float* aux;  // [n_chunks][K*K + 2][64] fp32: depthwise taps, expand bias, depthwise bias (zero padded)
+    const float* b2;
+    const bf16* res;
+    long long ldres;
+    float* gap;
+    long long* dbg;  // optional clock64 stamps of CTA 0 / compute thread 0 (16 per chunk; cabinet_mbconv_debug)
+};
+
+long long* g_mb_dbg = nullptr;
+
+__device__ __forceinline__ float lds32f(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void reds_f32(uint32_t a, float v) { asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float4 lds128f(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+
+// Depthwise over one row segment: lane = (column group, channel pair).  COLS output columns per lane.
+template <int K, int S, int COLS, int IWT, int TW>
+__device__ __forceinline__ void dw_seg(const MbParams& p, uint32_t sE, uint32_t sA2, uint32_t s_gap, uint32_t s_aux,
+                                       int chunk, int lanes_px, int groups, int row, int seg_col0, bool row_valid,
+                                       int ow_base, bool want_gap) {
+    constexpr int SPAN = (COLS - 1) * S + K;
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / lanes_px, cl = lane - grp * lanes_px;
+    if (grp >= groups) return;
+    const int c0 = chunk * 64 + cl * 2;
+    const int col0 = seg_col0 + grp * COLS;
+    float2 w[K * K];
+#pragma unroll
+    for (int t = 0; t < K * K; ++t) w[t] = tc::lds64f(s_aux + t * 256 + cl * 8);
+    const float2 b = tc::lds64f(s_aux + (K * K + 1) * 256 + cl * 8);
+    float acc[COLS][2];
+#pragma unroll
+    for (int r = 0; r < COLS; ++r) {
+        acc[r][0] = b.x;
+        acc[r][1] = b.y;
+    }
+    const uint32_t base = sE + ((row * S) * IWT + col0 * S) * E_PITCH + cl * 4;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+#pragma unroll
+        for (int sx = 0; sx < SPAN; ++sx) {
+            uint32_t raw;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(base + (ky * IWT + sx) * E_PITCH));
+            const float x0 = __uint_as_float(raw << 16), x1 = __uint_as_float(raw & 0xffff0000u);
+#pragma unroll
+            for (int r = 0; r < COLS; ++r) {
+                const int kx = sx - r * S;  // compile-time after unrolling
+                if (kx >= 0 && kx < K) {
+                    acc[r][0] = fmaf(x0, w[ky * K + kx].x, acc[r][0]);
+                    acc[r][1] = fmaf(x1, w[ky * K + kx].y, acc[r][1]);
+                }
+            }
+        }
+    }
+    cab_act_vec<2 * COLS>(&acc[0][0], p.act_dw);
+    float g0 = 0.f, g1 = 0.f;
+    const int prow = row * TW + col0;
+#pragma unroll
+    for (int r = 0; r < COLS; ++r) {
+        const int pr = prow + r;
+        const __nv_bfloat162 hv = __floats2bfloat162_rn(acc[r][0], acc[r][1]);
+        sts32(sA2 + pr * 128 + ((((cl >> 2) ^ (pr & 7)) << 4) | ((cl & 3) << 2)), *reinterpret_cast<const uint32_t*>(&hv));
+        if (row_valid && ow_base + col0 + r < p.OW) {
+            g0 += acc[r][0];
+            g1 += acc[r][1];
+        }
+    }
+    if (want_gap) {
+        reds_f32(s_gap + (c0 << 2), g0);
+        reds_f32(s_gap + (c0 << 2) + 4, g1);
+    }
+}
+
+// bf16x2 pack of (lo, hi) with the expand activation folded in (ReLU rides on the convert instruction).
+template <int ACT> __device__ __forceinline__ uint32_t pack_act(float lo, float hi) {
+    uint32_t d;
+    if constexpr (ACT == CABINET_ACT_RELU) {
+        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    } else {
+        if constexpr (ACT == CABINET_ACT_HSWISH) {
+            lo *= __saturatef(fmaf(lo, 1.f / 6.f, 0.5f));  // x * relu6(x + 3) / 6
+            hi *= __saturatef(fmaf(hi, 1.f / 6.f, 0.5f));
+        }
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    }
+    return d;
+}
+
+// Epilogue 1 for one TMEM piece (this thread's pixel row, 32 columns): + bias, act, bf16, -> E.
+template <int ACT>
+__device__ __forceinline__ void epi1_piece(const uint32_t* v, uint32_t bias_addr, uint32_t dst, int ncol, bool keep) {
+#pragma unroll
+    for (int h16 = 0; h16 < 2; ++h16) {
+        if (h16 * 16 < ncol) {
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 bb = lds128f(bias_addr + h16 * 64 + 16 * j);
+                o[2 * j] = pack_act<ACT>(__uint_as_float(v[h16 * 16 + 4 * j + 0]) + bb.x,
+                                         __uint_as_float(v[h16 * 16 + 4 * j + 1]) + bb.y);
+                o[2 * j + 1] = pack_act<ACT>(__uint_as_float(v[h16 * 16 + 4 * j + 2]) + bb.z,
+                                             __uint_as_float(v[h16 * 16 + 4 * j + 3]) + bb.w);
+            }
+            if (!keep) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = 0u;
+            }
+            tc::sts128(dst + h16 * 32, make_uint4(o[0], o[1], o[2], o[3]));
+            tc::sts128(dst + h16 * 32 + 16, make_uint4(o[4], o[5], o[6], o[7]));
+        }
+    }
+}
+
+__device__ __forceinline__ void bulk_load_1d(uint8_t* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     tc::smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+
+template <int K, int S, int TH, int TW, bool PROJECT>
+__global__ void __launch_bounds__(NTHREADS, 2)
+mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                    const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY, const MbParams p) {
+    constexpr int PAD = (K - 1) / 2;
+    constexpr int IWT = (TW - 1) * S + K, IHT = (TH - 1) * S + K, NPIX = IWT * IHT, NMT = (NPIX + 127) / 128;
+    constexpr int NSEG = NCW / TH, WSEG = TW / NSEG, NOUT = TH * TW;
+    constexpr int D2COL = NMT * 64;
+    constexpr int AUX_BIAS = K * K * 256;  // byte offset of the expand bias inside a chunk's aux block
+    static_assert(NCW % TH == 0 && TW % NSEG == 0 && WSEG % 4 == 0 && NOUT <= 128 && D2COL + 64 <= TMEM_COLS, "tile shape");
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t a1_full, a1_free, w_full[2], d1_full, d1_free, dw_done, a2_free, d2_full, d2_free;
+    __shared__ uint32_t tmem_base_smem;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sA1 = tc::smem_u32(smem);
+    const uint32_t sE = sA1 + p.off_e, sA2 = sA1 + p.off_a2, sW = sA1 + p.off_w;
+    const uint32_t s_b2 = sA1 + p.off_f32;                      // [cout_pad] fp32
+    const uint32_t s_gap = s_b2 + p.cout_pad * 4;               // [n_chunks * 64]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nc = p.n_chunks;
+
+    if (threadIdx.x == 0) {
+        tc::prefetch_tmap(&tmX);
+        tc::prefetch_tmap(&tmW1);
+        tc::prefetch_tmap(&tmY);
+        if (PROJECT) tc::prefetch_tmap(&tmW2);
+        tc::mbar_init(&a1_full, 1);
+        tc::mbar_init(&a1_free, 1);
+        tc::mbar_init(&w_full[0], 1);
+        tc::mbar_init(&w_full[1], 1);
+        tc::mbar_init(&d1_full, 1);
+        tc::mbar_init(&d1_free, NCW);
+        tc::mbar_init(&dw_done, 1);
+        tc::mbar_init(&a2_free, 1);
+        tc::mbar_init(&d2_full, 1);
+        tc::mbar_init(&d2_free, NCW);
+        tc::mbar_fence_init();
+        tc::fence_proxy_async();
+    }
+    if (warp == NCW) tc::tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    for (int i = threadIdx.x; i < nc * 64; i += NTHREADS) sts32f(s_gap + 4 * i, 0.f);
+    if (PROJECT)
+        for (int i = threadIdx.x; i < p.cout_pad; i += NTHREADS) sts32f(s_b2 + 4 * i, i < p.Cout ? __ldg(p.b2 + i) : 0.f);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_base_smem;
+    const int n_my = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int exp16 = (p.Cexp + 15) & ~15;
+
+    if (warp == NCW) {
+        // ============================ control warp: TMA + MMA issue ============================
+        const uint32_t leader = tc::elect_one();
+        const uint32_t idesc1 = tc::make_idesc_bf16(128, 64);
+        const uint32_t idesc2 = tc::make_idesc_bf16(128, p.cout_pad);
+        const uint64_t a1_desc = tc::make_desc_sw128(sA1), a2_desc = tc::make_desc_sw128(sA2);
+        const int G = n_my * nc;
+        auto load_a1 = [&](int it) {
+            if (lane == 0) {
+                const int tile = blockIdx.x + it * gridDim.x;
+                const int tw_i = tile % p.tiles_w, t = tile / p.tiles_w;
+                const int ow0 = tw_i * TW, oh0 = (t % p.tiles_h) * TH, n = t / p.tiles_h;
+                tc::mbar_expect_tx(&a1_full, NPIX * 128);
+                tc::tma_load_4d(smem, &tmX, &a1_full, 0, ow0 * S - PAD, oh0 * S - PAD, n);
+            }
+            __syncwarp();
+        };
+        auto load_w = [&](int c, int buf) {
+            if (lane == 0) {
+                uint8_t* dst = smem + p.off_w + buf * p.w_buf_bytes;
+                tc::mbar_expect_tx(&w_full[buf], W1_CHUNK + (PROJECT ? p.cout_pad * 128 : 0) + p.aux_bytes);
+                tc::tma_load_2d(dst, &tmW1, &w_full[buf], 0, c * 64);
+                if (PROJECT) tc::tma_load_2d(dst + W1_CHUNK, &tmW2, &w_full[buf], c * 64, 0);
+                bulk_load_1d(dst + p.off_aux, reinterpret_cast<const uint8_t*>(p.aux) + static_cast<size_t>(c) * p.aux_bytes,
+                             p.aux_bytes, &w_full[buf]);
+            }
+            __syncwarp();
+        };
+        auto mma1 = [&](int it, int c) {
+            const int g = it * nc + c;
+            const int buf = p.resident ? c : (g & 1);
+            if (c == 0) tc::mbar_wait(&a1_full, it & 1);
+            tc::mbar_wait(&w_full[buf], p.resident ? 0 : ((g >> 1) & 1));
+            tc::mbar_wait(&d1_free, (g & 1) ^ 1);
+            tc::tc_fence_after();
+            const uint64_t b_desc = tc::make_desc_sw128(sW + buf * p.w_buf_bytes);
+#pragma unroll
+            for (int m = 0; m < NMT; ++m) {
+                const uint64_t ad = a1_desc + static_cast<uint64_t>(m * (16384 >> 4));
+                tc::umma_bf16_if(leader, tmem + m * 64, ad, b_desc, idesc1, 0u);
+                if (p.ksteps1 > 1) tc::umma_bf16_if(leader, tmem + m * 64, ad + 2, b_desc + 2, idesc1, 1u);
+                if (p.ksteps1 > 2) tc::umma_bf16_if(leader, tmem + m * 64, ad + 4, b_desc + 4, idesc1, 1u);
+                if (p.ksteps1 > 3) tc::umma_bf16_if(leader, tmem + m * 64, ad + 6, b_desc + 6, idesc1, 1u);
+            }
+            tc::umma_commit_if(leader, &d1_full);
+            if (c == nc - 1) tc::umma_commit_if(leader, &a1_free);
+        };
+
+        load_a1(0);
+        if (p.resident) {
+            for (int c = 0; c < nc; ++c) load_w(c, c);
+        } else {
+            load_w(0, 0);
+            load_w(1, 1);
+        }
+        mma1(0, 0);
+        for (int it = 0; it < n_my; ++it) {
+            for (int c = 0; c < nc; ++c) {
+                const int g = it * nc + c;
+                if (c + 1 < nc) mma1(it, c + 1);
+                if (c == (nc > 1 ? nc - 2 : 0) && it + 1 < n_my) {
+                    // the last MMA1 of this tile has been issued: once it has read A1, fetch the next tile's input
+                    tc::mbar_wait(&a1_free, it & 1);
+                    load_a1(it + 1);
+                }
+                tc::mbar_wait(&dw_done, g & 1);
+                if (PROJECT) {
+                    if (c == 0) tc::mbar_wait(&d2_free, (it & 1) ^ 1);
+                    tc::tc_fence_after();
+                    const int buf = p.resident ? c : (g & 1);
+                    const uint64_t b_desc = tc::make_desc_sw128(sW + buf * p.w_buf_bytes + W1_CHUNK);
+                    const int ks2 = min(64, exp16 - c * 64) >> 4;
+                    tc::umma_bf16_if(leader, tmem + D2COL, a2_desc, b_desc, idesc2, c > 0 ? 1u : 0u);
+                    if (ks2 > 1) tc::umma_bf16_if(leader, tmem + D2COL, a2_desc + 2, b_desc + 2, idesc2, 1u);
+                    if (ks2 > 2) tc::umma_bf16_if(leader, tmem + D2COL, a2_desc + 4, b_desc + 4, idesc2, 1u);
+                    if (ks2 > 3) tc::umma_bf16_if(leader, tmem + D2COL, a2_desc + 6, b_desc + 6, idesc2, 1u);
+                    tc::umma_commit_if(leader, &a2_free);
+                    if (c == nc - 1) tc::umma_commit_if(leader, &d2_full);
+                }
+                if (!p.resident && g + 2 < G) {
+                    // the weights / taps of chunk g+2 replace those of chunk g once nothing reads them any more:
+                    // MMA2(g) complete (project mode) or the depthwise pass of chunk g finished (dw_done above)
+                    if (PROJECT) tc::mbar_wait(&a2_free, g & 1);
+                    load_w((c + 2) % nc, g & 1);
+                }
+            }
+            if (it + 1 < n_my) mma1(it + 1, 0);
+        }
+        __syncwarp();
+    } else {
+        // ============================ compute warps ============================
+        const int q = warp & 3, hcol = warp >> 2;     // epilogue 1/2: TMEM lane quarter, column half
+        const int row_w = warp / NSEG, seg = warp % NSEG;
+        const bool want_gap = !PROJECT && p.gap != nullptr;
+        // this thread's pixel (row, column) inside the staged input patch for every M tile: tile independent
+        int pty[NMT], ptx[NMT];
+#pragma unroll
+        for (int m = 0; m < NMT; ++m) {
+            const int r = m * 128 + q * 32 + lane;
+            pty[m] = r / IWT;
+            ptx[m] = r - pty[m] * IWT;
+        }
+        int g = 0;
+        for (int it = 0; it < n_my; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int tw_i = tile % p.tiles_w, tq = tile / p.tiles_w;
+            const int ow0 = tw_i * TW, oh0 = (tq % p.tiles_h) * TH, n = tq / p.tiles_h;
+            const int ih0 = oh0 * S - PAD, iw0 = ow0 * S - PAD;
+            const bool border = ih0 < 0 || iw0 < 0 || ih0 + IHT > p.H || iw0 + IWT > p.W;
+            for (int c = 0; c < nc; ++c, ++g) {
+                const int buf = p.resident ? c : (g & 1);
+                const uint32_t s_aux = sW + buf * p.w_buf_bytes + p.off_aux;
+                const int v16 = min(64, exp16 - c * 64);
+                // ---- epilogue 1: D1 -> E (TMEM loads run one piece ahead of the conversion)
+                const bool rec = p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && g < 64;
+                if (rec) p.dbg[16 * g + 0] = clock64();
+                tc::mbar_wait(&w_full[buf], p.resident ? 0 : ((g >> 1) & 1));  // aux block (bias, taps) visible
+                tc::mbar_wait(&d1_full, g & 1);
+                if (rec) p.dbg[16 * g + 1] = clock64();
+                tc::tc_fence_after();
+                const int ncol = min(32, v16 - hcol * 32);
+                if (ncol > 0) {
+                    uint32_t va[32], vb[32];
+                    const uint32_t t0 = tmem + hcol * 32 + (static_cast<uint32_t>(q * 32) << 16);
+                    const uint32_t bias_addr = s_aux + AUX_BIAS + hcol * 128;
+                    tc::tmem_ld32(t0, va);
+#pragma unroll
+                    for (int m = 0; m < NMT; ++m) {
+                        if (m * 128 + q * 32 >= NPIX) break;
+                        uint32_t* cur = (m & 1) ? vb : va;
+                        uint32_t* nxt = (m & 1) ? va : vb;
+                        tc::tmem_ld_wait();
+                        if (rec && m < 3) p.dbg[16 * g + 9 + 2 * m] = clock64();
+                        if (m + 1 < NMT && (m + 1) * 128 + q * 32 < NPIX) tc::tmem_ld32(t0 + (m + 1) * 64, nxt);
+                        const int r = m * 128 + q * 32 + lane;
+                        if (r < NPIX) {
+                            bool keep = true;
+                            if (border) {
+                                const int ih = ih0 + pty[m], iw = iw0 + ptx[m];
+                                keep = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+                            }
+                            const uint32_t dst = sE + r * E_PITCH + hcol * 64;
+                            if (p.act_e == CABINET_ACT_RELU) epi1_piece<CABINET_ACT_RELU>(cur, bias_addr, dst, ncol, keep);
+                            else if (p.act_e == CABINET_ACT_HSWISH) epi1_piece<CABINET_ACT_HSWISH>(cur, bias_addr, dst, ncol, keep);
+                            else epi1_piece<CABINET_ACT_NONE>(cur, bias_addr, dst, ncol, keep);
+                        }
+                        if (rec && m < 2) p.dbg[16 * g + 10 + 2 * m] = clock64();
+                    }
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&d1_free);
+                if (rec) p.dbg[16 * g + 2] = clock64();
+                if (threadIdx.x == 0) tc::bulk_wait_read<0>();  // the TMA store that last read A2 is done with it
+                tc::named_bar_sync(1, NCW * 32);                // E complete
+                if (PROJECT && g > 0) tc::mbar_wait(&a2_free, (g - 1) & 1);
+                if (rec) p.dbg[16 * g + 3] = clock64();
+                // ---- depthwise: E -> A2
+                {
+                    const bool row_valid = oh0 + row_w < p.OH;
+                    if (v16 > 32)
+                        dw_seg<K, S, WSEG, IWT, TW>(p, sE, sA2, s_gap, s_aux, c, v16 >> 1, 1, row_w, seg * WSEG, row_valid, ow0, want_gap);
+                    else if (v16 > 16)
+                        dw_seg<K, S, WSEG / 2, IWT, TW>(p, sE, sA2, s_gap, s_aux, c, 16, 2, row_w, seg * WSEG, row_valid, ow0, want_gap);
+                    else
+                        dw_seg<K, S, WSEG / 4, IWT, TW>(p, sE, sA2, s_gap, s_aux, c, 8, 4, row_w, seg * WSEG, row_valid, ow0, want_gap);
+                }
+                if (rec) p.dbg[16 * g + 4] = clock64();
+                tc::fence_proxy_async();
+                tc::named_bar_sync(1, NCW * 32);                // A2 complete, E free
+                if (rec) p.dbg[16 * g + 5] = clock64();
+                if (threadIdx.x == 0) {
+                    tc::mbar_arrive(&dw_done);
+                    if (!PROJECT) {
+                        tc::tma_store_4d(&tmY, smem + p.off_a2, c * 64, ow0, oh0, n);
+                        tc::bulk_commit();
+                    }
+                }
+            }
+            if (PROJECT) {
+                // ---- epilogue 2: D2 -> +bias (+identity) -> bf16 -> staging -> TMA store
+                const bool rec2 = p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && g <= 64;
+                const int pr = q * 32 + lane;
+                const int prow = pr / TW, pcol = pr - prow * TW;
+                const int oh = oh0 + prow, ow = ow0 + pcol;
+                const bool valid = q * 32 < NOUT && oh < p.OH && ow < p.OW;
+                const long long pix = (static_cast<long long>(n) * p.OH + oh) * p.OW + ow;
+                // the identity operand of this thread's first 16 output channels travels while MMA2 finishes
+                uint4 res0 = make_uint4(0, 0, 0, 0), res1 = make_uint4(0, 0, 0, 0);
+                if (p.has_res && valid && hcol * 16 < p.Cout) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.ldres + hcol * 16);
+                    res0 = __ldg(rp);
+                    if (hcol * 16 + 16 <= p.Cout) res1 = __ldg(rp + 1);
+                }
+                tc::mbar_wait(&d2_full, it & 1);
+                if (rec2) p.dbg[16 * (g - 1) + 6] = clock64();
+                tc::tc_fence_after();
+                if (q * 32 < NOUT) {
+                    for (int j16 = hcol; j16 * 16 < p.cout_pad; j16 += 2) {
+                        uint32_t v[16];
+                        tc::tmem_ld16(tmem + D2COL + j16 * 16 + (static_cast<uint32_t>(q * 32) << 16), v);
+                        tc::tmem_ld_wait();
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 bb = lds128f(s_b2 + (j16 * 16 + 4 * j) * 4);
+                            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
+                            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+                            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
+                            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+                        }
+                        const int co0 = j16 * 16;
+                        if (p.has_res && valid && co0 < p.Cout) {
+                            Vec16<bf16> r0, r1;
+                            r0.raw = res0;
+                            r1.raw = res1;
+                            if (j16 != hcol) {
+                                const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.ldres + co0);
+                                r0.raw = __ldg(rp);
+                                r1.raw = co0 + 16 <= p.Cout ? __ldg(rp + 1) : make_uint4(0, 0, 0, 0);
+                            }
+                            float rf[16];
+                            r0.unpack(rf);
+                            r1.unpack(rf + 8);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] += rf[j];
+                        }
+                        Vec16<bf16> o0, o1;
+                        o0.pack(f);
+                        o1.pack(f + 8);
+                        const int grp = j16 >> 2, cc = (j16 & 3) * 2;
+                        const uint32_t rowa = (grp == 0 ? sA2 : sE + (grp - 1) * A2_BYTES) + pr * 128;
+                        tc::sts128(rowa + ((cc ^ (pr & 7)) << 4), o0.raw);
+                        tc::sts128(rowa + (((cc + 1) ^ (pr & 7)) << 4), o1.raw);
+                    }
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&d2_free);
+                if (rec2) p.dbg[16 * (g - 1) + 7] = clock64();
+                tc::fence_proxy_async();
+                tc::named_bar_sync(1, NCW * 32);
+                if (rec2) p.dbg[16 * (g - 1) + 8] = clock64();
+                if (threadIdx.x == 0) {
+                    for (int grp = 0; grp * 64 < p.cout_pad; ++grp)
+                        tc::tma_store_4d(&tmY, smem + (grp == 0 ? p.off_a2 : p.off_e + (grp - 1) * A2_BYTES), grp * 64, ow0, oh0, n);
+                    tc::bulk_commit();
+                    if (rec2) p.dbg[16 * (g - 1) + 14] = clock64();
+                }
+                if (p.cout_pad > 64) {  // part of the staging lives in E, which the next epilogue 1 overwrites
+                    if (threadIdx.x == 0) tc::bulk_wait_read<0>();
+                    tc::named_bar_sync(1, NCW * 32);
+                }
+            } else if (want_gap) {
+                // ---- per-tile flush of the SE pooling sums (all red.shared of this tile are ordered by the barrier)
+                for (int i = threadIdx.x; i < p.Cexp; i += NCW * 32) {
+                    const float s = lds32f(s_gap + 4 * i);
+                    if (s != 0.f) {
+                        atomicAdd(p.gap + static_cast<long long>(n) * p.Cexp + i, s);
+                        sts32f(s_gap + 4 * i, 0.f);
+                    }
+                }
+            }
+        }
+        if (threadIdx.x == 0) tc::bulk_wait_read<0>();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == NCW) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem, TMEM_COLS);
+    }
+}
+
+template <int K, int S, int TH, int TW, bool PROJECT>
+int launch_mb(const void* x, long long ldx, int N, const void* w1, const void* w2, void* y, long long ldy, int cy,
+              MbParams p, cudaStream_t st, bool probe) {
+    constexpr int IWT = (TW - 1) * S + K, IHT = (TH - 1) * S + K, NPIX = IWT * IHT, NMT = (NPIX + 127) / 128;
+    constexpr int NOUT = TH * TW;
+    if (NMT * 64 + (PROJECT ? p.cout_pad : 0) > TMEM_COLS) {
+        cabinet_set_error("mbconv_fused: TMEM budget (cout %d)", p.Cout);
+        return CABINET_ERR_INVALID;
+    }
+    p.tiles_w = (p.OW + TW - 1) / TW;
+    p.tiles_h = (p.OH + TH - 1) / TH;
+    const long long tiles = static_cast<long long>(N) * p.tiles_w * p.tiles_h;
+    CAB_REQUIRE(tiles < (1LL << 31), "mbconv_fused: too many tiles");
+    p.num_tiles = static_cast<int>(tiles);
+    const int a1_bytes = ((NPIX * 128 + 1023) / 1024) * 1024;
+    int e_bytes = ((NPIX * E_PITCH + 1023) / 1024) * 1024;
+    if (PROJECT && p.cout_pad > 64) e_bytes = std::max(e_bytes, ((p.cout_pad + 63) / 64 - 1) * A2_BYTES);
+    p.a2_bytes = ((NOUT * 128 + 1023) / 1024) * 1024;  // MMA2 reads 128 rows: the tail runs into the weight buffers
+    p.off_e = a1_bytes;
+    p.off_a2 = p.off_e + e_bytes;
+    p.off_w = p.off_a2 + p.a2_bytes;
+    p.aux_bytes = (K * K + 2) * 256;
+    p.off_aux = W1_CHUNK + (PROJECT ? p.cout_pad * 128 : 0);
+    p.w_buf_bytes = ((p.off_aux + p.aux_bytes + 1023) / 1024) * 1024;
+    p.resident = p.n_chunks <= 2 ? 1 : 0;
+    p.off_f32 = p.off_w + std::min(p.n_chunks, 2) * p.w_buf_bytes;
+    const size_t smem = static_cast<size_t>(std::max(p.off_f32, p.off_a2 + A2_BYTES)) + (p.n_chunks * 64 + p.cout_pad) * 4 + 1024;
+    if (smem > 113 * 1024) {
+        cabinet_set_error("mbconv_fused: shared-memory budget (%zu bytes)", smem);
+        return CABINET_ERR_INVALID;
+    }
+    if (probe) return CABINET_OK;
+
+    CUtensorMap tmX, tmW1, tmW2, tmY;
+    {
+        const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)N};
+        const uint64_t strides[3] = {(uint64_t)ldx * 2, (uint64_t)ldx * 2 * p.W, (uint64_t)ldx * 2 * p.W * p.H};
+        const uint32_t box[4] = {64, (uint32_t)IWT, (uint32_t)IHT, 1};
+        int rc = cab_make_tmap_bf16(&tmX, x, 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[2] = {64, (uint64_t)((p.Cexp + 15) / 16 * 16)};
+        const uint64_t strides[1] = {128};
+        const uint32_t box[2] = {64, 64};
+        int rc = cab_make_tmap_bf16(&tmW1, w1, 2, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (rc) return rc;
+    }
+    if (PROJECT) {
+        const uint64_t kk = static_cast<uint64_t>((p.Cexp + 63) / 64) * 64;
+        const uint64_t dims[2] = {kk, (uint64_t)p.cout_pad};
+        const uint64_t strides[1] = {kk * 2};
+        const uint32_t box[2] = {64, (uint32_t)p.cout_pad};
+        int rc = cab_make_tmap_bf16(&tmW2, w2, 2, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        if (rc) return rc;
+    } else {
+        tmW2 = tmW1;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t)cy, (uint64_t)p.OW, (uint64_t)p.OH, (uint64_t)N};
+        const uint64_t strides[3] = {(uint64_t)ldy * 2, (uint64_t)ldy * 2 * p.OW, (uint64_t)ldy * 2 * p.OW * p.OH};
+        const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, 1};
+        int rc = cab_make_tmap_bf16(&tmY, y, 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    int dev = 0, sms = 148;
+    CAB_CUDA(cudaGetDevice(&dev));
+    CAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = static_cast<int>(std::min<long long>(tiles, 2LL * sms));
+    static bool attr_done = false;
+    if (!attr_done) {
+        CAB_CUDA(cudaFuncSetAttribute(mbconv_fused_kernel<K, S, TH, TW, PROJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      113 * 1024));
+        attr_done = true;
+    }
+    mbconv_fused_kernel<K, S, TH, TW, PROJECT><<<grid, NTHREADS, smem, st>>>(tmX, tmW1, tmW2, tmY, p);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+}  // namespace
+
+extern "C" int cabinet_mbconv_debug(long long* device_stamps) {
+    g_mb_dbg = device_stamps;
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_expand,
+                                    const float* aux_packed, int Cexp, int act_expand, int k, int stride, int act_dw,
+                                    const void* w_project, const float* b_project, int Cout, int residual, void* y,
+                                    long long ldy, int OH, int OW, float* gap_sum, cabinet_stream_t stream) {
+    CAB_REQUIRE(x && w_expand && aux_packed && y, "mbconv_fused: null pointer");
+    CAB_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2), "mbconv_fused: k must be 3|5 and stride 1|2");
+    CAB_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cin <= 64 && Cexp > 0 && Cexp % 8 == 0 && Cexp <= 1024,
+                "mbconv_fused: needs Cin <= 64 and Cexp %% 8 == 0 (got Cin %d, Cexp %d)", Cin, Cexp);
+    const int pad = (k - 1) / 2;
+    CAB_REQUIRE(OH == (H + 2 * pad - k) / stride + 1 && OW == (W + 2 * pad - k) / stride + 1,
+                "mbconv_fused: inconsistent output size");
+    CAB_REQUIRE(ldx % 8 == 0 && ldx >= Cin && ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_expand) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(aux_packed) & 15) == 0,
+                "mbconv_fused: alignment");
+    const bool project = w_project != nullptr;
+    if (project) {
+        CAB_REQUIRE(b_project && Cout > 0 && Cout <= 128 && ldy >= Cout && (reinterpret_cast<uintptr_t>(w_project) & 15) == 0,
+                    "mbconv_fused: project needs a bias and Cout <= 128");
+        CAB_REQUIRE(!residual || (stride == 1 && Cin == Cout && Cin % 8 == 0), "mbconv_fused: identity needs stride 1, Cin == Cout");
+        CAB_REQUIRE(!gap_sum, "mbconv_fused: pooling sums exist in the depthwise-output mode only");
+    } else {
+        CAB_REQUIRE(ldy >= Cexp && !residual, "mbconv_fused: depthwise-output mode writes Cexp channels, no identity");
+    }
+    if (N == 0) return CABINET_OK;
+    MbParams p;
+    p.H = H; p.W = W; p.OH = OH; p.OW = OW; p.Cin = Cin; p.Cexp = Cexp; p.Cout = project ? Cout : 0;
+    p.cout_pad = project ? (Cout + 15) / 16 * 16 : 0;
+    p.n_chunks = (Cexp + 63) / 64;
+    p.act_e = act_expand; p.act_dw = act_dw; p.has_res = residual ? 1 : 0;
+    p.ksteps1 = (Cin + 15) / 16;
+    p.aux = aux_packed; p.b2 = b_project;
+    p.res = reinterpret_cast<const bf16*>(x); p.ldres = ldx; p.gap = gap_sum; p.dbg = g_mb_dbg;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int cy = project ? Cout : Cexp;
+#define CAB_MB(K_, S_, TH_, TW_, PROBE_)                                                                           \
+    (project ? launch_mb<K_, S_, TH_, TW_, true>(x, ldx, N, w_expand, w_project, y, ldy, cy, p, st, PROBE_)       \
+             : launch_mb<K_, S_, TH_, TW_, false>(x, ldx, N, w_expand, w_project, y, ldy, cy, p, st, PROBE_))
+    if (k == 3 && stride == 1) return CAB_MB(3, 1, 8, 16, false);
+    if (k == 5 && stride == 1) return CAB_MB(5, 1, 8, 16, false);
+    if (k == 3 && stride == 2) {
+        if (CAB_MB(3, 2, 4, 16, true) == CABINET_OK) return CAB_MB(3, 2, 4, 16, false);  // wider tile when it fits
+        return CAB_MB(3, 2, 4, 8, false);
+    }
+    return CAB_MB(5, 2, 4, 8, false);
+#undef CAB_MB
+}

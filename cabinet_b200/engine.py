@@ -131,6 +131,7 @@ class Engine:
         self.debug = False
         self.stages = {}
         self.trace, self.trace_filter = None, None
+        self.fuse_mbconv = True     # expand + depthwise (+ project) in one kernel for blocks with <= 64 input channels
         self.fuse_se = False        # SE apply as A-operand prologue of the project GEMM (slower than scale_act today)
         self.use_cuda_graph = False
         self.sub_batch = 0          # > 0: run the schedule over chunks of this many images
@@ -157,6 +158,13 @@ class Engine:
                 e["pw1"] = ConvLayer(c[0], c[1], act, wd, f"mobile.f{bi}.expand")
                 e["dw"] = DwLayer(c[3], c[4], ACT_NONE if s["se"] else act, f"mobile.f{bi}.dw")
                 se, pw2, bn2 = c[5], c[7], c[8]
+                if self.precision == "bf16":
+                    # fused-block side table: fp32 [chunks][k*k + 2][64] = depthwise taps, expand bias, depthwise bias
+                    dwl, kk, nc = e["dw"], e["dw"].k ** 2, -(-e["dw"].c // 64)
+                    aux = torch.zeros((nc * 64, kk + 2), dtype=f32, device=dwl.w.device)
+                    aux[: dwl.c, :kk] = dwl.w.t()
+                    aux[: dwl.c, kk], aux[: dwl.c, kk + 1] = e["pw1"].b, dwl.b
+                    e["aux"] = aux.view(nc, 64, kk + 2).permute(0, 2, 1).contiguous()
             else:
                 e["dw"] = DwLayer(c[0], c[1], act, f"mobile.f{bi}.dw")
                 se, pw2, bn2 = c[3], c[4], c[5]
@@ -296,6 +304,29 @@ class Engine:
                       self.stream)
         return out
 
+    def mbconv_fused(self, x: Map, e: dict, gap: Optional[torch.Tensor]) -> Map:
+        """Inverted-residual block with the expanded activation kept on chip (reference: mobilenetv3.py:126-159).
+        ``gap`` given (SE blocks): returns the pre-SE depthwise output and accumulates its pooling sums; else the
+        block output (project + identity included)."""
+        s, pw1, dw, pw2 = e["spec"], e["pw1"], e["dw"], e["pw2"]
+        pad = (dw.k - 1) // 2
+        OH, OW = _out_size(x.H, dw.k, dw.stride, pad), _out_size(x.W, dw.k, dw.stride, pad)
+        project = gap is None
+        cy = pw2.cout if project else dw.c
+        out = self.new(x.N, OH, OW, cy)
+        nbytes = (x.N * x.H * x.W * x.C + x.N * OH * OW * cy) * 2 + pw1.w.numel() * 2 + dw.w.numel() * 4
+        flops = 2 * x.N * x.H * x.W * x.C * dw.c + 2 * x.N * OH * OW * dw.c * dw.k * dw.k
+        if project:
+            nbytes += pw2.w.numel() * 2 + (x.N * OH * OW * cy * 2 if s["identity"] else 0)
+            flops += 2 * x.N * OH * OW * dw.c * pw2.cout
+        self._run("mbconv_fused", dw.name.replace(".dw", "") + ("" if project else ".expand+dw"), nbytes, flops,
+                  self.lib.cabinet_mbconv_fused, x.ptr, x.ld, x.N, x.H, x.W, x.C, pw1.tc.data_ptr(), e["aux"].data_ptr(),
+                  dw.c, pw1.act, dw.k, dw.stride, dw.act,
+                  pw2.tc.data_ptr() if project else None, pw2.b.data_ptr() if project else None,
+                  pw2.cout if project else 0, 1 if project and s["identity"] else 0, out.ptr, out.ld, OH, OW,
+                  gap.data_ptr() if gap is not None else None, self.stream)
+        return out
+
     def gate(self, gap: torch.Tensor, hw: int, G: GateLayer, name: str) -> torch.Tensor:
         """Channel gate of SE / FFM: two batched tiny FC layers (mean -> ReLU hidden -> gate), fp32."""
         n = gap.shape[0]
@@ -404,11 +435,30 @@ class Engine:
                           o.ptr, o.ld, f.N, f.H, f.W, f.C, dw.act, self.stream)
                 f = o
                 continue
-            h = self.conv(f, e["pw1"]) if s["expand"] else f
+            fuse = (s["expand"] and self.fuse_mbconv and self.use_tc and f.C <= 64 and f.dt == BF16 and f.ld % 8 == 0
+                    and f.off % 8 == 0 and s["exp"] % 8 == 0 and ("se" in e or s["out"] <= 128) and "aux" in e
+                    and not e.get("nofuse"))
+            d = None
+            if fuse:
+                # expand -> depthwise (-> project + identity): the expanded activation never leaves the SM
+                gap = None
+                if "se" in e:
+                    gap = gap_all[gi].view(-1)[: N * s["exp"]].view(N, s["exp"])
+                try:
+                    d = self.mbconv_fused(f, e, gap)
+                except ValueError as err:  # block shape outside the kernel's shared-memory / TMEM budget
+                    if "budget" not in str(err):
+                        raise
+                    e["nofuse"], fuse = True, False
+            if fuse and "se" not in e:
+                f = d
+                continue
+            h = self.conv(f, e["pw1"]) if s["expand"] and not fuse else f
             if "se" in e:
                 gap = gap_all[gi].view(-1)[: N * s["exp"]].view(N, s["exp"])
                 gi += 1
-                d = self.dwconv(h, e["dw"], gap)
+                if not fuse:
+                    d = self.dwconv(h, e["dw"], gap)
                 scale = self.gate(gap, d.H * d.W, e["se"], e["dw"].name)
                 # expand form: SE then activation; no-expand form: activation (already applied) then SE (F10)
                 se_act = e["act"] if s["expand"] else ACT_NONE

@@ -119,6 +119,26 @@ int cabinet_mbconv_noexpand_fused(const void* x, long long ldx, const float* w_d
                                   const float* w_pw, const float* b_pw, void* y, long long ldy, int N, int H, int W,
                                   int C, int act, cabinet_stream_t stream);
 
+/* Fused inverted-residual block with expansion (src/models/mobilenetv3.py:126-159), bf16 NHWC, Cin <= 64:
+ *   h = act_expand(W_e * x + b_e)            1x1 expand + BN + act          (mobilenetv3.py:128-131)
+ *   d = act_dw(dw_kxk(h) + b_dw)             depthwise + BN                 (mobilenetv3.py:132-141)
+ *   w_project != NULL:  y = W_p * d + b_p (+ x when residual)                (mobilenetv3.py:145-159), y has Cout channels
+ *   w_project == NULL:  y = d (Cexp channels) and gap_sum[n][c] += sum over pixels of d (blocks with squeeze-excite:
+ *                       the SE gate needs the global mean before the project conv; act_dw is NONE there).
+ * The expanded activation h never reaches HBM (TMEM -> shared memory -> depthwise).  w_expand / w_project use the
+ * cabinet_conv_tc packing (bf16 [ceil16(Cout)][1][ceil64(Cin)]).  aux_packed is fp32 [ceil(Cexp/64)][k*k + 2][64],
+ * zero padded, BN folded: rows 0..k*k-1 = depthwise taps of the chunk's 64 channels, row k*k = expand bias,
+ * row k*k+1 = depthwise bias (one bulk copy per chunk).  b_project fp32 [Cout].
+ * k in {3,5}, stride in {1,2}, pad (k-1)/2; Cexp % 8 == 0; Cout <= 128; gap_sum ([N][Cexp], zeroed by the caller) may be NULL. */
+int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_expand,
+                         const float* aux_packed, int Cexp, int act_expand, int k, int stride, int act_dw,
+                         const void* w_project, const float* b_project, int Cout, int residual, void* y, long long ldy,
+                         int OH, int OW, float* gap_sum, cabinet_stream_t stream);
+
+/* Profiling hook: when device_stamps (>= 1024 int64 on the device) is non-NULL, CTA 0 of every following
+ * cabinet_mbconv_fused launch records clock64() at its phase boundaries (16 slots per channel chunk); NULL turns it off. */
+int cabinet_mbconv_debug(long long* device_stamps);
+
 /* Squeeze-excite / FFM channel gate: scale[n][c] = gate(b2 + W2 * relu(b1 + W1 * (sum[n]/HW))).
  * Replaces src/models/mobilenetv3.py:68-83 (gate = CABINET_ACT_HSIGMOID, biases present) and
  * src/models/cabinet.py:146-150 (gate = CABINET_ACT_SIGMOID, b1 = b2 = NULL).  All fp32. */

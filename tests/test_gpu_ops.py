@@ -455,3 +455,100 @@ def test_mbconv_noexpand_fused(C, H, W, act):
                                             ym.ptr, ym.ld, N, H, W, C, act, stream()), "mbconv1")
     torch.cuda.synchronize()
     assert rel_l2(from_map(ym), ref) < tol(dtype)
+
+
+def _pack_aux(wd, be, bd):
+    """[chunks][k*k + 2][64] fp32: depthwise taps, expand bias, depthwise bias (include/cabinet_b200.h)."""
+    cexp, kk = wd.shape[0], wd.shape[2] * wd.shape[3]
+    nc = -(-cexp // 64)
+    aux = torch.zeros(nc * 64, kk + 2)
+    aux[:cexp, :kk] = wd.reshape(cexp, kk)
+    aux[:cexp, kk], aux[:cexp, kk + 1] = be, bd
+    return aux.view(nc, 64, kk + 2).permute(0, 2, 1).contiguous().cuda()
+
+
+def _pack_tc(w, dtype=torch.bfloat16):
+    cout, cin = w.shape[:2]
+    n16, c64 = -(-cout // 16) * 16, -(-cin // 64) * 64
+    pk = torch.zeros(n16, 1, c64)
+    pk[:cout, 0, :cin] = w.reshape(cout, cin)
+    return pk.to("cuda", dtype).contiguous()
+
+
+@pytest.mark.parametrize("cin,cexp,cout,k,s,H,W,act,res", [
+    (16, 64, 24, 3, 2, 40, 56, ACT_RELU, False),      # Large f2
+    (24, 72, 24, 3, 1, 24, 40, ACT_RELU, True),       # Large f3 (ragged second chunk of 8 channels)
+    (40, 240, 80, 3, 2, 20, 36, ACT_HSWISH, False),   # Large f7 (4 chunks, streamed weights, 2 store groups)
+    (40, 120, 40, 5, 1, 19, 23, ACT_RELU, True),      # k5 with project
+    (16, 16, 16, 3, 1, 9, 7, ACT_RELU, True),         # single narrow chunk, tile larger than the image
+    (24, 88, 24, 5, 2, 33, 17, ACT_HSWISH, False),    # Small f3-like k5 stride 2, odd sizes
+    (64, 128, 64, 3, 1, 16, 16, ACT_HSWISH, True),
+    (16, 72, 24, 3, 2, 30, 34, ACT_RELU, False),      # Small f2: two chunks at stride 2 (narrow-tile fallback)
+    (40, 240, 40, 5, 1, 14, 18, ACT_HSWISH, True),    # Small f5-like: four k5 chunks, streamed taps
+])
+def test_mbconv_fused_project(cin, cexp, cout, k, s, H, W, act, res):
+    """expand -> depthwise -> project (+identity) in one kernel vs the torch ops with the same bf16 roundings."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    N = 3
+    x = q(gen(N, cin, H, W, seed=1), dtype)
+    we, be = q(gen(cexp, cin, 1, 1, seed=2, scale=cin ** -0.5), dtype), gen(cexp, seed=3, scale=0.2)
+    wd, bd = gen(cexp, 1, k, k, seed=4, scale=1.0 / k), gen(cexp, seed=5, scale=0.1)
+    wp, bp = q(gen(cout, cexp, 1, 1, seed=6, scale=cexp ** -0.5), dtype), gen(cout, seed=7, scale=0.1)
+    pad = (k - 1) // 2
+    h = q(act_ref(F.conv2d(x, we, be), act), dtype)
+    d = q(act_ref(F.conv2d(h, wd, bd, s, pad, 1, cexp), act), dtype)
+    ref = F.conv2d(d, wp, bp)
+    if res:
+        ref = ref + x
+    OH, OW = ref.shape[2:]
+    xm = to_map(x, dtype, ld=cin + 8, off=8)
+    ym = to_map(torch.zeros_like(ref), dtype, ld=cout + 24, off=16)
+    ym.t.fill_(7.0)
+    aux, bpd = _pack_aux(wd, be, bd), bp.cuda()
+    pe, pp = _pack_tc(we), _pack_tc(wp)
+    check(lib.cabinet_mbconv_fused(xm.ptr, xm.ld, N, H, W, cin, pe.data_ptr(), aux.data_ptr(), cexp, act, k, s, act,
+                                   pp.data_ptr(), bpd.data_ptr(), cout, 1 if res else 0, ym.ptr, ym.ld, OH, OW, None,
+                                   stream()), "mbconv_fused")
+    torch.cuda.synchronize()
+    err = rel_l2(from_map(ym), ref)
+    print(f"mbconv_fused {cin}->{cexp}->{cout} k{k} s{s} {H}x{W}: rel_l2 {err:.3e}")
+    assert err < 8e-3  # three bf16 roundings (h, d, y); a flipped rounding of h or d moves y by ~1 bf16 ulp
+    full = ym.t.float()
+    assert float((full[..., : ym.off] - 7.0).abs().max()) == 0
+    assert float((full[..., ym.off + cout:] - 7.0).abs().max()) == 0
+
+
+@pytest.mark.parametrize("cin,cexp,k,s,H,W,act", [
+    (24, 72, 5, 2, 40, 56, ACT_RELU),       # Large f4
+    (40, 120, 5, 1, 24, 40, ACT_RELU),      # Large f5 / f6
+    (40, 240, 3, 1, 11, 13, ACT_HSWISH),
+    (16, 72, 3, 2, 17, 9, ACT_RELU),
+])
+def test_mbconv_fused_dw_out(cin, cexp, k, s, H, W, act):
+    """expand -> depthwise with the pre-SE output and its pooling sums (blocks with squeeze-excite)."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    N = 2
+    x = q(gen(N, cin, H, W, seed=1), dtype)
+    we, be = q(gen(cexp, cin, 1, 1, seed=2, scale=cin ** -0.5), dtype), gen(cexp, seed=3, scale=0.2)
+    wd, bd = gen(cexp, 1, k, k, seed=4, scale=1.0 / k), gen(cexp, seed=5, scale=0.1)
+    pad = (k - 1) // 2
+    h = q(act_ref(F.conv2d(x, we, be), act), dtype)
+    ref = F.conv2d(h, wd, bd, s, pad, 1, cexp)
+    OH, OW = ref.shape[2:]
+    xm = to_map(x, dtype)
+    ym = to_map(torch.zeros_like(ref), dtype, ld=cexp + 8, off=0)
+    ym.t.fill_(7.0)
+    gap = torch.zeros(N, cexp, device="cuda")
+    aux = _pack_aux(wd, be, bd)
+    pe = _pack_tc(we)
+    check(lib.cabinet_mbconv_fused(xm.ptr, xm.ld, N, H, W, cin, pe.data_ptr(), aux.data_ptr(), cexp, act, k, s,
+                                   ACT_NONE, None, None, 0, 0, ym.ptr, ym.ld, OH, OW, gap.data_ptr(), stream()),
+          "mbconv_fused")
+    torch.cuda.synchronize()
+    err = rel_l2(from_map(ym), ref)
+    gerr = rel_l2(gap.cpu(), ref.sum(dim=(2, 3)))
+    print(f"mbconv_fused(dw out) {cin}->{cexp} k{k} s{s} {H}x{W}: rel_l2 {err:.3e} gap {gerr:.3e}")
+    assert err < 6e-3 and gerr < 1e-3
+    assert float((ym.t.float()[..., cexp:] - 7.0).abs().max()) == 0
