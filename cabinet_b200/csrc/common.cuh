@@ -67,6 +67,17 @@ template <int N> __device__ __forceinline__ void cab_act_vec(float* v, int act) 
     }
 }
 
+// Packed fp32 FMA (Blackwell FFMA2): acc.{x,y} += x.{x,y} * w.{x,y} in ONE instruction -- two IEEE fp32 FMAs, bit-identical
+// to two fmaf() calls.  The depthwise kernels keep (channel c, channel c+1) pairs in adjacent registers for this.
+__device__ __forceinline__ void cab_ffma2(float2& acc, const float2 x, const float2 w) {
+    uint64_t a, b, c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(acc.x), "f"(acc.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(x.x), "f"(x.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(w.x), "f"(w.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(b), "l"(c));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(a));
+}
+
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }

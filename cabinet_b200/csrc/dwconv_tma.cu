@@ -42,16 +42,13 @@ __device__ __forceinline__ void dw_row(const DwParams& p, const uint8_t* tile, u
     const int col0 = grp * COLS;
 
     float2 w[K * K];
-    float acc[COLS][2];
+    float2 acc[COLS];
     if (active) {
 #pragma unroll
         for (int t = 0; t < K * K; ++t) w[t] = __ldg(reinterpret_cast<const float2*>(p.w + t * p.C + c0));
         const float2 b = __ldg(reinterpret_cast<const float2*>(p.bias + c0));
 #pragma unroll
-        for (int r = 0; r < COLS; ++r) {
-            acc[r][0] = b.x;
-            acc[r][1] = b.y;
-        }
+        for (int r = 0; r < COLS; ++r) acc[r] = b;
     }
     tc::mbar_wait(bar, 0);
     if (active) {
@@ -64,18 +61,15 @@ __device__ __forceinline__ void dw_row(const DwParams& p, const uint8_t* tile, u
             for (int sx = 0; sx < SPAN; ++sx) {
                 uint32_t raw;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(rowp + sx * pitch));
-                const float x0 = __uint_as_float(raw << 16), x1 = __uint_as_float(raw & 0xffff0000u);
+                const float2 xv = make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
 #pragma unroll
                 for (int r = 0; r < COLS; ++r) {
                     const int kx = sx - r * S;  // compile-time after unrolling
-                    if (kx >= 0 && kx < K) {
-                        acc[r][0] = fmaf(x0, w[ky * K + kx].x, acc[r][0]);
-                        acc[r][1] = fmaf(x1, w[ky * K + kx].y, acc[r][1]);
-                    }
+                    if (kx >= 0 && kx < K) cab_ffma2(acc[r], xv, w[ky * K + kx]);
                 }
             }
         }
-        cab_act_vec<2 * COLS>(&acc[0][0], p.act);
+        cab_act_vec<2 * COLS>(&acc[0].x, p.act);
         const int oh = oh0 + row;
         float g0 = 0.f, g1 = 0.f;
         if (oh < p.OH) {
@@ -83,10 +77,10 @@ __device__ __forceinline__ void dw_row(const DwParams& p, const uint8_t* tile, u
 #pragma unroll
             for (int r = 0; r < COLS; ++r) {
                 if (ow0 + col0 + r < p.OW) {
-                    g0 += acc[r][0];
-                    g1 += acc[r][1];
+                    g0 += acc[r].x;
+                    g1 += acc[r].y;
                     *reinterpret_cast<__nv_bfloat162*>(yout + static_cast<long long>(r) * p.ldy) =
-                        __floats2bfloat162_rn(acc[r][0], acc[r][1]);
+                        __floats2bfloat162_rn(acc[r].x, acc[r].y);
                 }
             }
         }
@@ -191,12 +185,9 @@ mbconv1_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mb1Params p)
             const int rest = item / LANES_PX;
             const int grp = rest % GROUPS, row = rest / GROUPS;
             const int col0 = grp * COLS;
-            float acc[COLS][2];
+            float2 acc[COLS];
 #pragma unroll
-            for (int r = 0; r < COLS; ++r) {
-                acc[r][0] = b.x;
-                acc[r][1] = b.y;
-            }
+            for (int r = 0; r < COLS; ++r) acc[r] = b;
             const uint32_t base = tc::smem_u32(tile) + (row * IWT + col0) * PITCH + cl * 4;
 #pragma unroll
             for (int ky = 0; ky < K; ++ky)
@@ -204,20 +195,17 @@ mbconv1_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mb1Params p)
                 for (int sx = 0; sx < COLS + K - 1; ++sx) {
                     uint32_t raw;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(base + (ky * IWT + sx) * PITCH));
-                    const float x0 = __uint_as_float(raw << 16), x1 = __uint_as_float(raw & 0xffff0000u);
+                    const float2 xv = make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
 #pragma unroll
                     for (int r = 0; r < COLS; ++r) {
                         const int kx = sx - r;
-                        if (kx >= 0 && kx < K) {
-                            acc[r][0] = fmaf(x0, w[ky * K + kx].x, acc[r][0]);
-                            acc[r][1] = fmaf(x1, w[ky * K + kx].y, acc[r][1]);
-                        }
+                        if (kx >= 0 && kx < K) cab_ffma2(acc[r], xv, w[ky * K + kx]);
                     }
                 }
-            cab_act_vec<2 * COLS>(&acc[0][0], p.act);
+            cab_act_vec<2 * COLS>(&acc[0].x, p.act);
 #pragma unroll
             for (int r = 0; r < COLS; ++r)
-                *reinterpret_cast<float2*>(hs + (row * MB_TW + col0 + r) * C + c0) = make_float2(acc[r][0], acc[r][1]);
+                *reinterpret_cast<float2*>(hs + (row * MB_TW + col0 + r) * C + c0) = acc[r];
         }
     }
     __syncthreads();

@@ -37,15 +37,23 @@ struct MbParams {
     int act_e, act_dw, has_res, ksteps1;
     int off_e, off_a2, off_w, w_buf_bytes, off_f32;
     int off_aux, aux_bytes, a2_bytes;
+    int step[3];       // gridDim.x split into (tile column, tile row, image) steps
     const float* aux;  // [n_chunks][K*K + 2][64] fp32: depthwise taps, expand bias, depthwise bias (zero padded)
     const float* b2;
     const bf16* res;
     long long ldres;
     float* gap;
-    long long* dbg;  // optional clock64 stamps of CTA 0 / compute thread 0 (16 per chunk; cabinet_mbconv_debug)
+    long long* dbg;  // clock64 stamps of CTA 0 / compute thread 0 (16 per chunk) in -DCAB_MB_DEBUG builds
 };
 
 long long* g_mb_dbg = nullptr;
+
+// Phase-boundary clock stamps (tools/dbg_mbconv.py): compiled in only with -DCAB_MB_DEBUG
+#ifdef CAB_MB_DEBUG
+#define MB_STAMP(cond, slot) do { if (cond) p.dbg[slot] = clock64(); } while (0)
+#else
+#define MB_STAMP(cond, slot) do { (void)(cond); } while (0)
+#endif
 
 __device__ __forceinline__ float lds32f(uint32_t a) {
     float v;
@@ -60,6 +68,41 @@ __device__ __forceinline__ float4 lds128f(uint32_t a) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
+
+// mbarrier wait for long waits: the suspend-time hint lets the hardware park the warp instead of re-issuing the
+// try_wait / branch pair every few cycles (those spins compete with the other CTA's compute warps for issue slots).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "nanosleep.u32 128;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(tc::smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Tile walk of a persistent CTA (tile += gridDim.x) without divisions: the step is pre-split on the host.
+struct TileIter {
+    int tw, th, n;
+    __device__ __forceinline__ void init(int tile, int tiles_w, int tiles_h) {
+        tw = tile % tiles_w;
+        const int t = tile / tiles_w;
+        th = t % tiles_h;
+        n = t / tiles_h;
+    }
+    __device__ __forceinline__ void next(const int* step, int tiles_w, int tiles_h) {
+        tw += step[0];
+        if (tw >= tiles_w) { tw -= tiles_w; ++th; }
+        th += step[1];
+        if (th >= tiles_h) { th -= tiles_h; ++n; }
+        n += step[2];
+    }
+};
 
 // Depthwise over one row segment: lane = (column group, channel pair).  COLS output columns per lane.
 template <int K, int S, int COLS, int IWT, int TW>
@@ -76,12 +119,9 @@ __device__ __forceinline__ void dw_seg(const MbParams& p, uint32_t sE, uint32_t 
 #pragma unroll
     for (int t = 0; t < K * K; ++t) w[t] = tc::lds64f(s_aux + t * 256 + cl * 8);
     const float2 b = tc::lds64f(s_aux + (K * K + 1) * 256 + cl * 8);
-    float acc[COLS][2];
+    float2 acc[COLS];
 #pragma unroll
-    for (int r = 0; r < COLS; ++r) {
-        acc[r][0] = b.x;
-        acc[r][1] = b.y;
-    }
+    for (int r = 0; r < COLS; ++r) acc[r] = b;
     const uint32_t base = sE + ((row * S) * IWT + col0 * S) * E_PITCH + cl * 4;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) {
@@ -89,28 +129,27 @@ __device__ __forceinline__ void dw_seg(const MbParams& p, uint32_t sE, uint32_t 
         for (int sx = 0; sx < SPAN; ++sx) {
             uint32_t raw;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(base + (ky * IWT + sx) * E_PITCH));
-            const float x0 = __uint_as_float(raw << 16), x1 = __uint_as_float(raw & 0xffff0000u);
+            const float2 xv = make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
 #pragma unroll
             for (int r = 0; r < COLS; ++r) {
                 const int kx = sx - r * S;  // compile-time after unrolling
-                if (kx >= 0 && kx < K) {
-                    acc[r][0] = fmaf(x0, w[ky * K + kx].x, acc[r][0]);
-                    acc[r][1] = fmaf(x1, w[ky * K + kx].y, acc[r][1]);
-                }
+                if (kx >= 0 && kx < K) cab_ffma2(acc[r], xv, w[ky * K + kx]);
             }
         }
     }
-    cab_act_vec<2 * COLS>(&acc[0][0], p.act_dw);
+    cab_act_vec<2 * COLS>(&acc[0].x, p.act_dw);
     float g0 = 0.f, g1 = 0.f;
     const int prow = row * TW + col0;
+    const uint32_t a2row = sA2 + prow * 128 + ((cl & 3) << 2);
 #pragma unroll
     for (int r = 0; r < COLS; ++r) {
-        const int pr = prow + r;
-        const __nv_bfloat162 hv = __floats2bfloat162_rn(acc[r][0], acc[r][1]);
-        sts32(sA2 + pr * 128 + ((((cl >> 2) ^ (pr & 7)) << 4) | ((cl & 3) << 2)), *reinterpret_cast<const uint32_t*>(&hv));
-        if (row_valid && ow_base + col0 + r < p.OW) {
-            g0 += acc[r][0];
-            g1 += acc[r][1];
+        // A2 row prow + r, 16-byte chunk (cl >> 2) ^ (row & 7); with 8-aligned segments (prow + r) & 7 == r & 7
+        const int sw = (COLS % 8 == 0 && TW % 8 == 0) ? (r & 7) : ((prow + r) & 7);
+        const __nv_bfloat162 hv = __floats2bfloat162_rn(acc[r].x, acc[r].y);
+        sts32(a2row + r * 128 + (((cl >> 2) ^ sw) << 4), *reinterpret_cast<const uint32_t*>(&hv));
+        if (want_gap && row_valid && ow_base + col0 + r < p.OW) {
+            g0 += acc[r].x;
+            g1 += acc[r].y;
         }
     }
     if (want_gap) {
@@ -225,14 +264,14 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         const uint32_t idesc2 = tc::make_idesc_bf16(128, p.cout_pad);
         const uint64_t a1_desc = tc::make_desc_sw128(sA1), a2_desc = tc::make_desc_sw128(sA2);
         const int G = n_my * nc;
-        auto load_a1 = [&](int it) {
+        TileIter lt;  // tile whose input patch is loaded next
+        lt.init(blockIdx.x, p.tiles_w, p.tiles_h);
+        auto load_a1 = [&](int) {
             if (lane == 0) {
-                const int tile = blockIdx.x + it * gridDim.x;
-                const int tw_i = tile % p.tiles_w, t = tile / p.tiles_w;
-                const int ow0 = tw_i * TW, oh0 = (t % p.tiles_h) * TH, n = t / p.tiles_h;
                 tc::mbar_expect_tx(&a1_full, NPIX * 128);
-                tc::tma_load_4d(smem, &tmX, &a1_full, 0, ow0 * S - PAD, oh0 * S - PAD, n);
+                tc::tma_load_4d(smem, &tmX, &a1_full, 0, lt.tw * TW * S - PAD, lt.th * TH * S - PAD, lt.n);
             }
+            lt.next(p.step, p.tiles_w, p.tiles_h);
             __syncwarp();
         };
         auto load_w = [&](int c, int buf) {
@@ -251,7 +290,7 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const int buf = p.resident ? c : (g & 1);
             if (c == 0) tc::mbar_wait(&a1_full, it & 1);
             tc::mbar_wait(&w_full[buf], p.resident ? 0 : ((g >> 1) & 1));
-            tc::mbar_wait(&d1_free, (g & 1) ^ 1);
+            mbar_wait_parked(&d1_free, (g & 1) ^ 1);
             tc::tc_fence_after();
             const uint64_t b_desc = tc::make_desc_sw128(sW + buf * p.w_buf_bytes);
 #pragma unroll
@@ -283,7 +322,7 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     tc::mbar_wait(&a1_free, it & 1);
                     load_a1(it + 1);
                 }
-                tc::mbar_wait(&dw_done, g & 1);
+                mbar_wait_parked(&dw_done, g & 1);
                 if (PROJECT) {
                     if (c == 0) tc::mbar_wait(&d2_free, (it & 1) ^ 1);
                     tc::tc_fence_after();
@@ -320,11 +359,14 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             pty[m] = r / IWT;
             ptx[m] = r - pty[m] * IWT;
         }
+        // epilogue 2: this thread's output pixel inside the tile
+        const int pr = q * 32 + lane;
+        const int prow = pr / TW, pcol = pr - prow * TW;
+        TileIter ti;
+        ti.init(blockIdx.x, p.tiles_w, p.tiles_h);
         int g = 0;
-        for (int it = 0; it < n_my; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int tw_i = tile % p.tiles_w, tq = tile / p.tiles_w;
-            const int ow0 = tw_i * TW, oh0 = (tq % p.tiles_h) * TH, n = tq / p.tiles_h;
+        for (int it = 0; it < n_my; ++it, ti.next(p.step, p.tiles_w, p.tiles_h)) {
+            const int ow0 = ti.tw * TW, oh0 = ti.th * TH, n = ti.n;
             const int ih0 = oh0 * S - PAD, iw0 = ow0 * S - PAD;
             const bool border = ih0 < 0 || iw0 < 0 || ih0 + IHT > p.H || iw0 + IWT > p.W;
             for (int c = 0; c < nc; ++c, ++g) {
@@ -333,10 +375,10 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 const int v16 = min(64, exp16 - c * 64);
                 // ---- epilogue 1: D1 -> E (TMEM loads run one piece ahead of the conversion)
                 const bool rec = p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && g < 64;
-                if (rec) p.dbg[16 * g + 0] = clock64();
+                MB_STAMP(rec, 16 * g + 0);
                 tc::mbar_wait(&w_full[buf], p.resident ? 0 : ((g >> 1) & 1));  // aux block (bias, taps) visible
                 tc::mbar_wait(&d1_full, g & 1);
-                if (rec) p.dbg[16 * g + 1] = clock64();
+                MB_STAMP(rec, 16 * g + 1);
                 tc::tc_fence_after();
                 const int ncol = min(32, v16 - hcol * 32);
                 if (ncol > 0) {
@@ -350,7 +392,7 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                         uint32_t* cur = (m & 1) ? vb : va;
                         uint32_t* nxt = (m & 1) ? va : vb;
                         tc::tmem_ld_wait();
-                        if (rec && m < 3) p.dbg[16 * g + 9 + 2 * m] = clock64();
+                        MB_STAMP(rec && m < 3, 16 * g + 9 + 2 * m);
                         if (m + 1 < NMT && (m + 1) * 128 + q * 32 < NPIX) tc::tmem_ld32(t0 + (m + 1) * 64, nxt);
                         const int r = m * 128 + q * 32 + lane;
                         if (r < NPIX) {
@@ -364,17 +406,17 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                             else if (p.act_e == CABINET_ACT_HSWISH) epi1_piece<CABINET_ACT_HSWISH>(cur, bias_addr, dst, ncol, keep);
                             else epi1_piece<CABINET_ACT_NONE>(cur, bias_addr, dst, ncol, keep);
                         }
-                        if (rec && m < 2) p.dbg[16 * g + 10 + 2 * m] = clock64();
+                        MB_STAMP(rec && m < 2, 16 * g + 10 + 2 * m);
                     }
                 }
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&d1_free);
-                if (rec) p.dbg[16 * g + 2] = clock64();
+                MB_STAMP(rec, 16 * g + 2);
                 if (threadIdx.x == 0) tc::bulk_wait_read<0>();  // the TMA store that last read A2 is done with it
                 tc::named_bar_sync(1, NCW * 32);                // E complete
                 if (PROJECT && g > 0) tc::mbar_wait(&a2_free, (g - 1) & 1);
-                if (rec) p.dbg[16 * g + 3] = clock64();
+                MB_STAMP(rec, 16 * g + 3);
                 // ---- depthwise: E -> A2
                 {
                     const bool row_valid = oh0 + row_w < p.OH;
@@ -385,10 +427,10 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     else
                         dw_seg<K, S, WSEG / 4, IWT, TW>(p, sE, sA2, s_gap, s_aux, c, 8, 4, row_w, seg * WSEG, row_valid, ow0, want_gap);
                 }
-                if (rec) p.dbg[16 * g + 4] = clock64();
+                MB_STAMP(rec, 16 * g + 4);
                 tc::fence_proxy_async();
                 tc::named_bar_sync(1, NCW * 32);                // A2 complete, E free
-                if (rec) p.dbg[16 * g + 5] = clock64();
+                MB_STAMP(rec, 16 * g + 5);
                 if (threadIdx.x == 0) {
                     tc::mbar_arrive(&dw_done);
                     if (!PROJECT) {
@@ -400,22 +442,20 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             if (PROJECT) {
                 // ---- epilogue 2: D2 -> +bias (+identity) -> bf16 -> staging -> TMA store
                 const bool rec2 = p.dbg && blockIdx.x == 0 && threadIdx.x == 0 && g <= 64;
-                const int pr = q * 32 + lane;
-                const int prow = pr / TW, pcol = pr - prow * TW;
-                const int oh = oh0 + prow, ow = ow0 + pcol;
-                const bool valid = q * 32 < NOUT && oh < p.OH && ow < p.OW;
-                const long long pix = (static_cast<long long>(n) * p.OH + oh) * p.OW + ow;
-                // the identity operand of this thread's first 16 output channels travels while MMA2 finishes
-                uint4 res0 = make_uint4(0, 0, 0, 0), res1 = make_uint4(0, 0, 0, 0);
-                if (p.has_res && valid && hcol * 16 < p.Cout) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.ldres + hcol * 16);
-                    res0 = __ldg(rp);
-                    if (hcol * 16 + 16 <= p.Cout) res1 = __ldg(rp + 1);
-                }
-                tc::mbar_wait(&d2_full, it & 1);
-                if (rec2) p.dbg[16 * (g - 1) + 6] = clock64();
-                tc::tc_fence_after();
-                if (q * 32 < NOUT) {
+                if (q * 32 < NOUT && hcol * 16 < p.cout_pad) {  // this warp owns rows / columns of D2
+                    const int oh = oh0 + prow, ow = ow0 + pcol;
+                    const bool valid = oh < p.OH && ow < p.OW;
+                    const long long pix = (static_cast<long long>(n) * p.OH + oh) * p.OW + ow;
+                    // the identity operand of this thread's first 16 output channels travels while MMA2 finishes
+                    uint4 res0 = make_uint4(0, 0, 0, 0), res1 = make_uint4(0, 0, 0, 0);
+                    if (p.has_res && valid && hcol * 16 < p.Cout) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.ldres + hcol * 16);
+                        res0 = __ldg(rp);
+                        if (hcol * 16 + 16 <= p.Cout) res1 = __ldg(rp + 1);
+                    }
+                    tc::mbar_wait(&d2_full, it & 1);
+                    MB_STAMP(rec2, 16 * (g - 1) + 6);
+                    tc::tc_fence_after();
                     for (int j16 = hcol; j16 * 16 < p.cout_pad; j16 += 2) {
                         uint32_t v[16];
                         tc::tmem_ld16(tmem + D2COL + j16 * 16 + (static_cast<uint32_t>(q * 32) << 16), v);
@@ -453,19 +493,20 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                         tc::sts128(rowa + ((cc ^ (pr & 7)) << 4), o0.raw);
                         tc::sts128(rowa + (((cc + 1) ^ (pr & 7)) << 4), o1.raw);
                     }
+                    tc::tc_fence_before();
                 }
-                tc::tc_fence_before();
+                // warps without a share of D2 arrive at once: they touch neither TMEM nor the staging tile
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&d2_free);
-                if (rec2) p.dbg[16 * (g - 1) + 7] = clock64();
+                MB_STAMP(rec2, 16 * (g - 1) + 7);
                 tc::fence_proxy_async();
                 tc::named_bar_sync(1, NCW * 32);
-                if (rec2) p.dbg[16 * (g - 1) + 8] = clock64();
+                MB_STAMP(rec2, 16 * (g - 1) + 8);
                 if (threadIdx.x == 0) {
                     for (int grp = 0; grp * 64 < p.cout_pad; ++grp)
                         tc::tma_store_4d(&tmY, smem + (grp == 0 ? p.off_a2 : p.off_e + (grp - 1) * A2_BYTES), grp * 64, ow0, oh0, n);
                     tc::bulk_commit();
-                    if (rec2) p.dbg[16 * (g - 1) + 14] = clock64();
+                    MB_STAMP(rec2, 16 * (g - 1) + 14);
                 }
                 if (p.cout_pad > 64) {  // part of the staging lives in E, which the next epilogue 1 overwrites
                     if (threadIdx.x == 0) tc::bulk_wait_read<0>();
@@ -561,6 +602,9 @@ int launch_mb(const void* x, long long ldx, int N, const void* w1, const void* w
     CAB_CUDA(cudaGetDevice(&dev));
     CAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = static_cast<int>(std::min<long long>(tiles, 2LL * sms));
+    p.step[0] = grid % p.tiles_w;
+    p.step[1] = (grid / p.tiles_w) % p.tiles_h;
+    p.step[2] = grid / (p.tiles_w * p.tiles_h);
     static bool attr_done = false;
     if (!attr_done) {
         CAB_CUDA(cudaFuncSetAttribute(mbconv_fused_kernel<K, S, TH, TW, PROJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -574,6 +618,7 @@ int launch_mb(const void* x, long long ldx, int N, const void* w1, const void* w
 
 }  // namespace
 
+// not part of the C-ABI header: profiling hook for tools/dbg_mbconv.py (effective in -DCAB_MB_DEBUG builds only)
 extern "C" int cabinet_mbconv_debug(long long* device_stamps) {
     g_mb_dbg = device_stamps;
     return CABINET_OK;
@@ -618,7 +663,10 @@ extern "C" int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, 
     (project ? launch_mb<K_, S_, TH_, TW_, true>(x, ldx, N, w_expand, w_project, y, ldy, cy, p, st, PROBE_)       \
              : launch_mb<K_, S_, TH_, TW_, false>(x, ldx, N, w_expand, w_project, y, ldy, cy, p, st, PROBE_))
     if (k == 3 && stride == 1) return CAB_MB(3, 1, 8, 16, false);
-    if (k == 5 && stride == 1) return CAB_MB(5, 1, 8, 16, false);
+    if (k == 5 && stride == 1) {
+        if (CAB_MB(5, 1, 8, 16, true) == CABINET_OK) return CAB_MB(5, 1, 8, 16, false);
+        return CAB_MB(5, 1, 8, 8, false);  // narrow tile: 12 x 12 input patch, fits next to streamed project weights
+    }
     if (k == 3 && stride == 2) {
         if (CAB_MB(3, 2, 4, 16, true) == CABINET_OK) return CAB_MB(3, 2, 4, 16, false);  // wider tile when it fits
         return CAB_MB(3, 2, 4, 8, false);

@@ -135,10 +135,6 @@ int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, int W, int 
                          const void* w_project, const float* b_project, int Cout, int residual, void* y, long long ldy,
                          int OH, int OW, float* gap_sum, cabinet_stream_t stream);
 
-/* Profiling hook: when device_stamps (>= 1024 int64 on the device) is non-NULL, CTA 0 of every following
- * cabinet_mbconv_fused launch records clock64() at its phase boundaries (16 slots per channel chunk); NULL turns it off. */
-int cabinet_mbconv_debug(long long* device_stamps);
-
 /* Squeeze-excite / FFM channel gate: scale[n][c] = gate(b2 + W2 * relu(b1 + W1 * (sum[n]/HW))).
  * Replaces src/models/mobilenetv3.py:68-83 (gate = CABINET_ACT_HSIGMOID, biases present) and
  * src/models/cabinet.py:146-150 (gate = CABINET_ACT_SIGMOID, b1 = b2 = NULL).  All fp32. */

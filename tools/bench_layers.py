@@ -33,6 +33,10 @@ jobs_all = {
     "f2.dw 3x3s2 64@512": (lambda x: eng.dwconv(x, blk[2]["dw"]), (B, 512, 512, 64), 64 / 4),
     "f5.dw 5x5 120@128": (lambda x: eng.dwconv(x, blk[5]["dw"]), (B, 128, 128, 120), 120),
     "f12.dw 3x3 672@64": (lambda x: eng.dwconv(x, blk[12]["dw"]), (B, 64, 64, 672), 672),
+    "mb.f2 16->64->24 s2@512": (lambda x: eng.mbconv_fused(x, blk[2], None), (B, 512, 512, 16), 24 / 4),
+    "mb.f3 24->72->24@256": (lambda x: eng.mbconv_fused(x, blk[3], None), (B, 256, 256, 24), 24),
+    "mb.f5 40->120 k5@128": (lambda x: eng.mbconv_fused(x, blk[5], torch.zeros(B, 120, device="cuda")), (B, 128, 128, 40), 120),
+    "mb.f7 40->240->80 s2@128": (lambda x: eng.mbconv_fused(x, blk[7], None), (B, 128, 128, 40), 80 / 4),
     "f14.dw 5x5 960@32": (lambda x: eng.dwconv(x, blk[14]["dw"]), (B, 32, 32, 960), 960),
 }
 import os

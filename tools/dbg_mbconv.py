@@ -1,4 +1,5 @@
-"""Phase timeline of the fused MBConv kernel (CTA 0, compute thread 0): python tools/dbg_mbconv.py [block]"""
+"""Phase timeline of the fused MBConv kernel (CTA 0, compute thread 0): python tools/dbg_mbconv.py [block]
+Needs a library built with the stamps compiled in: make -C cabinet_b200/csrc clean all NVCCFLAGS+=-DCAB_MB_DEBUG"""
 import sys
 
 import torch
@@ -11,6 +12,8 @@ model = build_model(8, "large").cuda()
 x = make_input(16, 1024, 1024).cuda()
 eng = model.engine()
 lib = _lib.load()
+import ctypes
+lib.cabinet_mbconv_debug.argtypes = [ctypes.c_void_p]
 model(x)
 torch.cuda.synchronize()
 buf = torch.zeros(2048, dtype=torch.int64, device="cuda")
