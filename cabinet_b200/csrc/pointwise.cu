@@ -172,13 +172,21 @@ channel_sum_kernel(const T* __restrict__ x, long long ldx, long long HW, int C, 
         float acc[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) acc[i] = 0.f;
-        for (long long p = p0 + pr; p < p1; p += rows) {
-            Vec16<T> v;
-            v.load(x + (static_cast<long long>(n) * HW + p) * ldx + cg * V);
-            float f[V];
-            v.unpack(f);
+        const T* base = x + static_cast<long long>(n) * HW * ldx + cg * V;
+        for (long long pb = p0 + pr; pb < p1; pb += 4LL * rows) {  // four independent 16-byte loads in flight
+            Vec16<T> v[4];
 #pragma unroll
-            for (int i = 0; i < V; ++i) acc[i] += f[i];
+            for (int u = 0; u < 4; ++u)
+                if (pb + u * rows < p1) v[u].load(base + (pb + u * rows) * ldx);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (pb + u * rows < p1) {
+                    float f[V];
+                    v[u].unpack(f);
+#pragma unroll
+                    for (int i = 0; i < V; ++i) acc[i] += f[i];
+                }
+            }
         }
 #pragma unroll
         for (int i = 0; i < V; ++i) atomicAdd(&s_sum[cg * V + i], acc[i]);
@@ -196,7 +204,8 @@ extern "C" int cabinet_channel_sum(const void* x, long long ldx, int dtype, int 
     CAB_REQUIRE(C > 0 && C % V == 0 && ldx % V == 0 && ldx >= C && C / V <= 256 && C * sizeof(float) <= 48 * 1024,
                 "channel_sum: unsupported C=%d ldx=%lld", C, ldx);
     if (N == 0 || HW == 0) return CABINET_OK;
-    const long long pix_per_block = std::max<long long>(64, cab_ceil_div(HW, 148 * 4));
+    // >= 256 pixels per block: the per-block tail is C global atomics, keep them rare next to the streaming part
+    const long long pix_per_block = std::max<long long>(256, cab_ceil_div(HW, 148 * 8));
     dim3 grid(static_cast<unsigned>(cab_ceil_div(HW, pix_per_block)), N);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == CABINET_BF16)

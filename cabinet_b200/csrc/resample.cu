@@ -71,6 +71,56 @@ bilinear_nhwc_bf16x8_kernel(const bf16* __restrict__ x, long long ldx, bf16* __r
     o.store(y + ((static_cast<long long>(n) * OH + oh) * OW + ow) * ldy + cg * 8);
 }
 
+// bf16 -> bf16, exact x4 (OH = 4*IH, OW = 4*IW: the 1/32 -> 1/8 feature upsample whenever H, W are multiples of 32):
+// one thread = one SOURCE pixel x 8 channels -> its 4 x 4 output pixels.  Output column 4g+j reads source columns
+// (g-1, g) with weight {0.625, 0.875} for j = 0, 1 and (g, g+1) with {0.125, 0.375} for j = 2, 3 (same for rows), so
+// nine 16-byte loads feed sixteen 16-byte stores (the per-pixel kernel needs 64 loads for them).  At the borders the
+// clamped neighbour equals the centre, which makes ATen's clamped source index and the static weight agree.
+__global__ void __launch_bounds__(256)
+bilinear_x4_bf16_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy, int IH, int IW,
+                        int C) {
+    const int CG = C >> 3;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<unsigned>(IW) * CG) return;
+    const int gx = idx / CG, cg = idx - gx * CG;
+    const int gy = blockIdx.y, n = blockIdx.z;
+    const int xs[3] = {max(gx - 1, 0), gx, min(gx + 1, IW - 1)};
+    const int ys[3] = {max(gy - 1, 0), gy, min(gy + 1, IH - 1)};
+    const bf16* b = x + static_cast<long long>(n) * IH * IW * ldx + cg * 8;
+    float f[3][3][8];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Vec16<bf16> v;
+            v.load(b + (static_cast<long long>(ys[r]) * IW + xs[c]) * ldx);
+            v.unpack(f[r][c]);
+        }
+    const int OW = 4 * IW;
+    bf16* o = y + ((static_cast<long long>(n) * 4 * IH + 4 * gy) * OW + 4 * gx) * ldy + cg * 8;
+#pragma unroll
+    for (int jy = 0; jy < 4; ++jy) {
+        const int ra = jy < 2 ? 0 : 1;                       // rows (ra, ra + 1)
+        const float wy = jy < 2 ? 0.625f + 0.25f * jy : 0.125f + 0.25f * (jy - 2);
+        float v[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[c][k] = f[ra][c][k] + wy * (f[ra + 1][c][k] - f[ra][c][k]);
+#pragma unroll
+        for (int jx = 0; jx < 4; ++jx) {
+            const int ca = jx < 2 ? 0 : 1;
+            const float wx = jx < 2 ? 0.625f + 0.25f * jx : 0.125f + 0.25f * (jx - 2);
+            float r[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = v[ca][k] + wx * (v[ca + 1][k] - v[ca][k]);
+            Vec16<bf16> ov;
+            ov.pack(r);
+            ov.store(o + (static_cast<long long>(jy) * OW + jx) * ldy);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------- logits tail
 // Each thread produces 8 consecutive output pixels [8g, 8g+8) of one output row for ALL classes and hands them,
 // class by class, to a consumer (NCHW store / running argmax).
@@ -320,6 +370,13 @@ extern "C" int cabinet_bilinear_nhwc(const void* x, long long ldx, int x_dtype, 
     if (x_dtype == CABINET_BF16 && y_dtype == CABINET_BF16 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 &&
         (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
         CAB_REQUIRE(OH <= 65535 && N <= 65535, "bilinear_nhwc: OH/N exceed grid limits");
+        if (OH == 4 * IH && OW == 4 * IW) {
+            dim3 g4(static_cast<unsigned>(cab_ceil_div(static_cast<long long>(IW) * (C / 8), 256)), IH, N);
+            bilinear_x4_bf16_kernel<<<g4, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(y),
+                                                       ldy, IH, IW, C);
+            CAB_LAUNCH_CHECK();
+            return CABINET_OK;
+        }
         dim3 g8(static_cast<unsigned>(cab_ceil_div(static_cast<long long>(OW) * (C / 8), 256)), OH, N);
         bilinear_nhwc_bf16x8_kernel<<<g8, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<bf16*>(y),
                                                        ldy, IH, IW, C, OH, OW, sh, sw);

@@ -188,7 +188,8 @@ def test_channel_sum(dtype):
     assert rel_l2(out.cpu(), x.sum(dim=(2, 3))) < 1e-5
 
 
-@pytest.mark.parametrize("C,IH,IW,OH,OW", [(256, 4, 4, 16, 16), (19, 3, 4, 9, 13), (8, 2, 3, 17, 33), (8, 1, 1, 8, 8)])
+@pytest.mark.parametrize("C,IH,IW,OH,OW", [(256, 4, 4, 16, 16), (19, 3, 4, 9, 13), (8, 2, 3, 17, 33), (8, 1, 1, 8, 8),
+                                               (16, 5, 7, 20, 28), (8, 1, 1, 4, 4), (24, 32, 32, 128, 128)])
 def test_bilinear_nhwc(C, IH, IW, OH, OW):
     lib = _lib.load()
     for din, dout in [(torch.bfloat16, torch.bfloat16), (torch.float32, torch.float32)]:
