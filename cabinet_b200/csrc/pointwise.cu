@@ -35,40 +35,55 @@ gate_mlp_kernel(const float* __restrict__ gap_sum, float inv_hw, const float* __
     }
 }
 
-// Batched tiny fully-connected layer: out[n][j] = act(b[j] + sum_c W[j][c] * in[n][c] * in_scale) for ALL images.
-// One warp per output j; every weight row is read once per chunk of 8 images (the per-image variant re-read
-// the whole matrix from L2 in every block).  grid = ceil(J / 8), block = 256.
-constexpr int FC_NB = 8;
+// Batched tiny fully-connected layer for ALL images: grid = (ceil(J / 8), ceil(N / FC_NB)), block = 256.
+constexpr int FC_NB = 8;      // images per block (blockIdx.y walks the batch)
+constexpr int FC_WMAX = 32;   // weights per lane kept in registers: rows of up to 32 * 32 = 1024 inputs
+
+// out[n][j] = act(b[j] + sum_c W[j][c] * in[n][c] * in_scale): warp = one output j for FC_NB images.  The whole
+// weight row of the warp is fetched into registers up front (all loads in flight at once, issued before the input
+// staging barrier), so a launch pays ONE global round trip instead of one per 32 inputs.
 __global__ void __launch_bounds__(256)
 gate_fc_kernel(const float* __restrict__ in, float in_scale, const float* __restrict__ W, const float* __restrict__ b,
                float* __restrict__ out, int N, int C, int J, int act) {
     extern __shared__ float s_in[];  // [FC_NB][C]
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int j = blockIdx.x * 8 + warp;
-    for (int n0 = 0; n0 < N; n0 += FC_NB) {
-        const int nb = min(FC_NB, N - n0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < nb * C; i += blockDim.x) s_in[i] = in[static_cast<long long>(n0) * C + i] * in_scale;
-        __syncthreads();
-        if (j < J) {
-            float acc[FC_NB];
+    const int n0 = blockIdx.y * FC_NB;
+    const int nb = min(FC_NB, N - n0);
+    float w[FC_WMAX];
+    if (j < J) {
+        const float* wr = W + static_cast<long long>(j) * C + lane;
 #pragma unroll
-            for (int k = 0; k < FC_NB; ++k) acc[k] = 0.f;
-            for (int c = lane; c < C; c += 32) {
-                const float w = __ldg(W + static_cast<long long>(j) * C + c);
+        for (int i = 0; i < FC_WMAX; ++i) w[i] = (lane + 32 * i < C) ? __ldg(wr + 32 * i) : 0.f;
+    }
+    for (int i = threadIdx.x; i < nb * C; i += blockDim.x) s_in[i] = in[static_cast<long long>(n0) * C + i] * in_scale;
+    __syncthreads();
+    if (j >= J) return;
+    float acc[FC_NB];
 #pragma unroll
-                for (int k = 0; k < FC_NB; ++k)
-                    if (k < nb) acc[k] = fmaf(w, s_in[k * C + c], acc[k]);
-            }
+    for (int k = 0; k < FC_NB; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < FC_WMAX; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) {
 #pragma unroll
             for (int k = 0; k < FC_NB; ++k)
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-            if (lane == 0) {
-                const float bj = b ? b[j] : 0.f;
-                for (int k = 0; k < nb; ++k) out[static_cast<long long>(n0 + k) * J + j] = cab_act(acc[k] + bj, act);
-            }
+                if (k < nb) acc[k] = fmaf(w[i], s_in[k * C + c], acc[k]);
         }
+    }
+#pragma unroll
+    for (int k = 0; k < FC_NB; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (lane == 0) {
+        const float bj = b ? b[j] : 0.f;
+        float v[FC_NB];
+#pragma unroll
+        for (int k = 0; k < FC_NB; ++k) v[k] = acc[k] + bj;
+        cab_act_vec<FC_NB>(v, act);
+#pragma unroll
+        for (int k = 0; k < FC_NB; ++k)
+            if (k < nb) out[static_cast<long long>(n0 + k) * J + j] = v[k];
     }
 }
 
@@ -234,10 +249,11 @@ extern "C" int cabinet_gate_mlp(const float* gap_sum, float inv_hw, const float*
 
 extern "C" int cabinet_gate_fc(const float* in, float in_scale, const float* W, const float* b, float* out, int N,
                                int C, int J, int act, cabinet_stream_t stream) {
-    CAB_REQUIRE(in && W && out && C > 0 && J > 0 && FC_NB * C * sizeof(float) <= 48 * 1024,
-                "gate_fc: bad arguments (C=%d J=%d)", C, J);
+    CAB_REQUIRE(in && W && out && C > 0 && J > 0 && C <= 32 * FC_WMAX, "gate_fc: bad arguments (C=%d J=%d, C <= 1024)", C, J);
     if (N == 0) return CABINET_OK;
-    gate_fc_kernel<<<(J + 7) / 8, 256, FC_NB * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+    CAB_REQUIRE((N + FC_NB - 1) / FC_NB <= 65535, "gate_fc: N exceeds grid limits");
+    gate_fc_kernel<<<dim3((J + 7) / 8, (N + FC_NB - 1) / FC_NB), 256, FC_NB * C * sizeof(float),
+                     static_cast<cudaStream_t>(stream)>>>(
         in, in_scale, W, b, out, N, C, J, act);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
