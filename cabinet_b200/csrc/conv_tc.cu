@@ -68,7 +68,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int tile
 }
 
 template <int ACT, bool HAS_RES, bool OUT_F32, bool PRO>
-__global__ void __launch_bounds__(PRO ? NUM_THREADS + 128 : NUM_THREADS, 1)
+__global__ void __launch_bounds__(PRO ? NUM_THREADS + 256 : NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
@@ -96,7 +96,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int s = 0; s < p.stages; ++s) {
             tc::mbar_init(&full_bar[s], 1);
             tc::mbar_init(&empty_bar[s], 1);
-            tc::mbar_init(&ready_bar[s], 4);
+            tc::mbar_init(&ready_bar[s], 8);
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&acc_full[s], 1);
@@ -199,7 +199,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // ================= A-operand prologue (SE): x <- act(x * scale[image][channel]) in place =================
         // reference: src/models/mobilenetv3.py:83 (x * y) followed by the activation at :143, fused in front of the
         // project 1x1 so the depthwise output is read from HBM once and never rewritten.
-        const int r = (warp - 10) * 32 + lane;  // A row = pixel of the tile
+        // 8 warps: thread = (A row = pixel of the tile, half of its eight 16-byte chunks).  All shared / global loads of
+        // a stage are issued before the first dependent instruction.
+        const int r = (threadIdx.x - NUM_THREADS) & 127, half = (threadIdx.x - NUM_THREADS) >> 7;
         int s = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -213,22 +215,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                 tc::mbar_wait(&full_bar[s], ph);
                 const uint32_t rowa = tc::smem_u32(sA) + s * A_STAGE_BYTES + r * 128;
+                {
+                uint4 raw[4];
+                float4 s0[4], s1[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int c = cb * BLOCK_K + ((j ^ (r & 7)) << 3);  // logical channels of physical 16-byte chunk j
+                for (int jj = 0; jj < 4; ++jj) {
+                    // walk LOGICAL chunks: the 8 rows of a quarter-warp then touch 8 different physical chunks
+                    // (conflict-free; walking physical chunks is an 8-way bank conflict) and share the scale address
+                    const int l = half * 4 + jj;
+                    const int j = l ^ (r & 7);
+                    const int c = cb * BLOCK_K + (l << 3);
+                    if (c < p.Cin) {
+                        raw[jj] = tc::lds128(rowa + (j << 4));
+                        s0[jj] = __ldg(reinterpret_cast<const float4*>(sc + c));
+                        s1[jj] = __ldg(reinterpret_cast<const float4*>(sc + c) + 1);
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int l = half * 4 + jj;
+                    const int j = l ^ (r & 7);
+                    const int c = cb * BLOCK_K + (l << 3);
                     if (c < p.Cin) {
                         Vec16<bf16> v;
-                        v.raw = tc::lds128(rowa + (j << 4));
+                        v.raw = raw[jj];
                         float f[8];
                         v.unpack(f);
-                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + c));
-                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(sc + c) + 1);
-                        f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
-                        f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+                        f[0] *= s0[jj].x; f[1] *= s0[jj].y; f[2] *= s0[jj].z; f[3] *= s0[jj].w;
+                        f[4] *= s1[jj].x; f[5] *= s1[jj].y; f[6] *= s1[jj].z; f[7] *= s1[jj].w;
                         cab_act_vec<8>(f, p.a_act);
                         v.pack(f);
                         tc::sts128(rowa + (j << 4), v.raw);
                     }
+                }
                 }
                 tc::fence_proxy_async();
                 __syncwarp();
@@ -546,7 +565,7 @@ extern "C" int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, in
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT + 1024));          \
             attr_done = true;                                                                                        \
         }                                                                                                            \
-        conv_tc_kernel<ACT_, RES_, F32_, PRO_><<<grid, (PRO_) ? NUM_THREADS + 128 : NUM_THREADS, smem, st>>>(        \
+        conv_tc_kernel<ACT_, RES_, F32_, PRO_><<<grid, (PRO_) ? NUM_THREADS + 256 : NUM_THREADS, smem, st>>>(        \
             tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmY, p);                                                            \
     } while (0)
     const bool f32 = y_dtype == CABINET_F32;

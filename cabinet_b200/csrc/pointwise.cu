@@ -56,7 +56,27 @@ gate_fc_kernel(const float* __restrict__ in, float in_scale, const float* __rest
 #pragma unroll
         for (int i = 0; i < FC_WMAX; ++i) w[i] = (lane + 32 * i < C) ? __ldg(wr + 32 * i) : 0.f;
     }
-    for (int i = threadIdx.x; i < nb * C; i += blockDim.x) s_in[i] = in[static_cast<long long>(n0) * C + i] * in_scale;
+    // stage the inputs of this block's images: rows are contiguous, so it is one flat copy; all loads of a thread are
+    // issued before the first store (C <= 1024, FC_NB = 8: at most 8 float4 per thread)
+    const float* src = in + static_cast<long long>(n0) * C;
+    const int total = nb * C;
+    if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = (threadIdx.x + u * 256) * 4;
+            if (i < total) v[u] = __ldg(reinterpret_cast<const float4*>(src + i));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = (threadIdx.x + u * 256) * 4;
+            if (i < total)
+                *reinterpret_cast<float4*>(s_in + i) =
+                    make_float4(v[u].x * in_scale, v[u].y * in_scale, v[u].z * in_scale, v[u].w * in_scale);
+        }
+    } else {
+        for (int i = threadIdx.x; i < total; i += blockDim.x) s_in[i] = src[i] * in_scale;
+    }
     __syncthreads();
     if (j >= J) return;
     float acc[FC_NB];

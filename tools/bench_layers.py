@@ -37,6 +37,10 @@ jobs_all = {
     "mb.f3 24->72->24@256": (lambda x: eng.mbconv_fused(x, blk[3], None), (B, 256, 256, 24), 24),
     "mb.f5 40->120 k5@128": (lambda x: eng.mbconv_fused(x, blk[5], torch.zeros(B, 120, device="cuda")), (B, 128, 128, 40), 120),
     "mb.f7 40->240->80 s2@128": (lambda x: eng.mbconv_fused(x, blk[7], None), (B, 128, 128, 40), 80 / 4),
+    "f12.project 672->112@64": (lambda x: eng.conv(x, blk[12]["pw2"]), (B, 64, 64, 672), 112),
+    "f12.project+SE 672->112@64": (lambda x: eng.conv(x, blk[12]["pw2"], a_scale=torch.ones(B, 672, device="cuda"), a_act=3), (B, 64, 64, 672), 112),
+    "f5.project 120->40@128": (lambda x: eng.conv(x, blk[5]["pw2"]), (B, 128, 128, 120), 40),
+    "f5.project+SE 120->40@128": (lambda x: eng.conv(x, blk[5]["pw2"], a_scale=torch.ones(B, 120, device="cuda"), a_act=1), (B, 128, 128, 120), 40),
     "f14.dw 5x5 960@32": (lambda x: eng.dwconv(x, blk[14]["dw"]), (B, 32, 32, 960), 960),
 }
 import os
