@@ -41,11 +41,21 @@ __device__ __forceinline__ void dw_row(const DwParams& p, const uint8_t* tile, u
     const bool active = grp < TW / COLS;
     const int col0 = grp * COLS;
 
-    float2 w[K * K];
+    // 3x3: all nine taps live in registers for the whole thread.  5x5: one filter row (5 taps) at a time, fetched one
+    // row ahead -- 25 resident taps cost 50 registers and halve the number of resident CTAs (the kernel is bound by
+    // the TMA round trip per CTA, so residency matters more than the 20 extra L1 loads).
+    constexpr bool ROWTAPS = K > 3;
+    float2 w[ROWTAPS ? K : K * K];
+    float2 wn[K];
     float2 acc[COLS];
     if (active) {
+        if constexpr (!ROWTAPS) {
 #pragma unroll
-        for (int t = 0; t < K * K; ++t) w[t] = __ldg(reinterpret_cast<const float2*>(p.w + t * p.C + c0));
+            for (int t = 0; t < K * K; ++t) w[t] = __ldg(reinterpret_cast<const float2*>(p.w + t * p.C + c0));
+        } else {
+#pragma unroll
+            for (int t = 0; t < K; ++t) wn[t] = __ldg(reinterpret_cast<const float2*>(p.w + t * p.C + c0));
+        }
         const float2 b = __ldg(reinterpret_cast<const float2*>(p.bias + c0));
 #pragma unroll
         for (int r = 0; r < COLS; ++r) acc[r] = b;
@@ -56,6 +66,15 @@ __device__ __forceinline__ void dw_row(const DwParams& p, const uint8_t* tile, u
         const uint32_t base = tc::smem_u32(tile) + ((row * S) * IWT + col0 * S) * pitch + cl * 4;
 #pragma unroll
         for (int ky = 0; ky < K; ++ky) {
+            if constexpr (ROWTAPS) {
+#pragma unroll
+                for (int t = 0; t < K; ++t) w[t] = wn[t];
+                if (ky + 1 < K) {
+#pragma unroll
+                    for (int t = 0; t < K; ++t)
+                        wn[t] = __ldg(reinterpret_cast<const float2*>(p.w + ((ky + 1) * K + t) * p.C + c0));
+                }
+            }
             const uint32_t rowp = base + ky * IWT * pitch;
 #pragma unroll
             for (int sx = 0; sx < SPAN; ++sx) {
@@ -65,7 +84,7 @@ __device__ __forceinline__ void dw_row(const DwParams& p, const uint8_t* tile, u
 #pragma unroll
                 for (int r = 0; r < COLS; ++r) {
                     const int kx = sx - r * S;  // compile-time after unrolling
-                    if (kx >= 0 && kx < K) cab_ffma2(acc[r], xv, w[ky * K + kx]);
+                    if (kx >= 0 && kx < K) cab_ffma2(acc[r], xv, w[ROWTAPS ? kx : ky * K + kx]);
                 }
             }
         }
@@ -92,7 +111,7 @@ __device__ __forceinline__ void dw_row(const DwParams& p, const uint8_t* tile, u
 }
 
 template <int K, int S>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, K > 3 ? 3 : 4)
 dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmX, const DwParams p) {
     constexpr int PAD = (K - 1) / 2;
     constexpr int IWT = (TW - 1) * S + K, IHT = (TH - 1) * S + K;

@@ -437,7 +437,9 @@ class Engine:
                 continue
             fuse = (s["expand"] and self.fuse_mbconv and self.use_tc and f.C <= 64 and f.dt == BF16 and f.ld % 8 == 0
                     and f.off % 8 == 0 and s["exp"] % 8 == 0 and ("se" in e or s["out"] <= 128) and "aux" in e
-                    and not e.get("nofuse"))
+                    and not e.get("nofuse")
+                    # 5x5 stride-2 tiles are 4 x 8 outputs behind an 11 x 19 halo: measured slower than expand + dwconv_tma
+                    and not (s["k"] == 5 and s["s"] == 2))
             d = None
             if fuse:
                 # expand -> depthwise (-> project + identity): the expanded activation never leaves the SM
