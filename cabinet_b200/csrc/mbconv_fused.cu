@@ -6,9 +6,11 @@
 // HBM by the expand GEMM and read back by the depthwise kernel.  Here it only ever exists in shared memory:
 //
 //   per output tile (TH x TW pixels of one image), per chunk of <= 64 expanded channels
-//     1. MMA1 (tcgen05, TMEM):  D1[input pixels incl. halo][64] = A1[pixels][Cin] * W1_chunk^T
+//     1. MMA1 (tcgen05, TMEM):  D1[input pixels incl. halo][64] = A1[pixels][Cin + 2] * W1_chunk^T
 //        A1 is ONE 4-D TMA box {64 ch, IWT, IHT, 1} of the block input (OOB zero fill = conv padding of the input).
-//     2. epilogue 1 (CUDA cores):  TMEM -> +bias -> act -> 0 outside the image (the depthwise conv pads the EXPANDED
+//        The expand bias rides in the GEMM: the control warp writes 1.0 into K slots Cin, Cin+1 of every A1 row and
+//        W1 carries (bias_hi, bias_lo) there, so epilogue 1 needs no per-element add.
+//     2. epilogue 1 (CUDA cores):  TMEM -> act -> 0 outside the image (the depthwise conv pads the EXPANDED
 //        map with zeros) -> bf16 -> E tile in shared memory (144-byte pixel pitch: conflict-free 16-byte stores).
 //     3. depthwise (CUDA cores):  warp = output row (segment), lane = channel pair, taps in registers, LDS.32 per
 //        lane; result -> A2 tile [out pixels][64] in the 128B-swizzled K-major UMMA layout.
@@ -104,60 +106,6 @@ struct TileIter {
     }
 };
 
-// Depthwise over one row segment: lane = (column group, channel pair).  COLS output columns per lane.
-template <int K, int S, int COLS, int IWT, int TW>
-__device__ __forceinline__ void dw_seg(const MbParams& p, uint32_t sE, uint32_t sA2, uint32_t s_gap, uint32_t s_aux,
-                                       int chunk, int lanes_px, int groups, int row, int seg_col0, bool row_valid,
-                                       int ow_base, bool want_gap) {
-    constexpr int SPAN = (COLS - 1) * S + K;
-    const int lane = threadIdx.x & 31;
-    const int grp = lane / lanes_px, cl = lane - grp * lanes_px;
-    if (grp >= groups) return;
-    const int c0 = chunk * 64 + cl * 2;
-    const int col0 = seg_col0 + grp * COLS;
-    float2 w[K * K];
-#pragma unroll
-    for (int t = 0; t < K * K; ++t) w[t] = tc::lds64f(s_aux + t * 256 + cl * 8);
-    const float2 b = tc::lds64f(s_aux + (K * K + 1) * 256 + cl * 8);
-    float2 acc[COLS];
-#pragma unroll
-    for (int r = 0; r < COLS; ++r) acc[r] = b;
-    const uint32_t base = sE + ((row * S) * IWT + col0 * S) * E_PITCH + cl * 4;
-#pragma unroll
-    for (int ky = 0; ky < K; ++ky) {
-#pragma unroll
-        for (int sx = 0; sx < SPAN; ++sx) {
-            uint32_t raw;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(base + (ky * IWT + sx) * E_PITCH));
-            const float2 xv = make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
-#pragma unroll
-            for (int r = 0; r < COLS; ++r) {
-                const int kx = sx - r * S;  // compile-time after unrolling
-                if (kx >= 0 && kx < K) cab_ffma2(acc[r], xv, w[ky * K + kx]);
-            }
-        }
-    }
-    cab_act_vec<2 * COLS>(&acc[0].x, p.act_dw);
-    float g0 = 0.f, g1 = 0.f;
-    const int prow = row * TW + col0;
-    const uint32_t a2row = sA2 + prow * 128 + ((cl & 3) << 2);
-#pragma unroll
-    for (int r = 0; r < COLS; ++r) {
-        // A2 row prow + r, 16-byte chunk (cl >> 2) ^ (row & 7); with 8-aligned segments (prow + r) & 7 == r & 7
-        const int sw = (COLS % 8 == 0 && TW % 8 == 0) ? (r & 7) : ((prow + r) & 7);
-        const __nv_bfloat162 hv = __floats2bfloat162_rn(acc[r].x, acc[r].y);
-        sts32(a2row + r * 128 + (((cl >> 2) ^ sw) << 4), *reinterpret_cast<const uint32_t*>(&hv));
-        if (want_gap && row_valid && ow_base + col0 + r < p.OW) {
-            g0 += acc[r].x;
-            g1 += acc[r].y;
-        }
-    }
-    if (want_gap) {
-        reds_f32(s_gap + (c0 << 2), g0);
-        reds_f32(s_gap + (c0 << 2) + 4, g1);
-    }
-}
-
 // bf16x2 pack of (lo, hi) with the expand activation folded in (ReLU rides on the convert instruction).
 template <int ACT> __device__ __forceinline__ uint32_t pack_act(float lo, float hi) {
     uint32_t d;
@@ -173,21 +121,84 @@ template <int ACT> __device__ __forceinline__ uint32_t pack_act(float lo, float 
     return d;
 }
 
-// Epilogue 1 for one TMEM piece (this thread's pixel row, 32 columns): + bias, act, bf16, -> E.
+// Depthwise over one row segment: lane = (column group, channel pair).  COLS output columns per lane.
+template <int K, int S, int COLS, int IWT, int TW>
+__device__ __forceinline__ void dw_seg(const MbParams& p, uint32_t sE, uint32_t sA2, uint32_t s_gap, uint32_t s_aux,
+                                       int chunk, int lanes_px, int groups, int row, int seg_col0, bool row_valid,
+                                       int ow_base, bool want_gap) {
+    constexpr int SPAN = (COLS - 1) * S + K;
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / lanes_px, cl = lane - grp * lanes_px;
+    if (grp >= groups) return;
+    const int c0 = chunk * 64 + cl * 2;
+    const int col0 = seg_col0 + grp * COLS;
+    // 3x3: nine taps in registers; 5x5: one filter row at a time from the shared-memory aux block (25 resident taps
+    // would need 50 of the 96 registers this kernel may use at two CTAs per SM)
+    constexpr bool ROWTAPS = K > 3;
+    float2 w[ROWTAPS ? K : K * K];
+    if constexpr (!ROWTAPS) {
+#pragma unroll
+        for (int t = 0; t < K * K; ++t) w[t] = tc::lds64f(s_aux + t * 256 + cl * 8);
+    }
+    const float2 b = tc::lds64f(s_aux + (K * K + 1) * 256 + cl * 8);
+    float2 acc[COLS];
+#pragma unroll
+    for (int r = 0; r < COLS; ++r) acc[r] = b;
+    const uint32_t base = sE + ((row * S) * IWT + col0 * S) * E_PITCH + cl * 4;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+        if constexpr (ROWTAPS) {
+#pragma unroll
+            for (int t = 0; t < K; ++t) w[t] = tc::lds64f(s_aux + (ky * K + t) * 256 + cl * 8);
+        }
+#pragma unroll
+        for (int sx = 0; sx < SPAN; ++sx) {
+            uint32_t raw;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(base + (ky * IWT + sx) * E_PITCH));
+            const float2 xv = make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
+#pragma unroll
+            for (int r = 0; r < COLS; ++r) {
+                const int kx = sx - r * S;  // compile-time after unrolling
+                if (kx >= 0 && kx < K) cab_ffma2(acc[r], xv, w[ROWTAPS ? kx : ky * K + kx]);
+            }
+        }
+    }
+    // ReLU rides on the bf16 convert; other activations take the generic path (the SE pooling sums exist only in the
+    // activation-free depthwise-output mode)
+    const bool relu_pack = p.act_dw == CABINET_ACT_RELU;
+    if (!relu_pack) cab_act_vec<2 * COLS>(&acc[0].x, p.act_dw);
+    float g0 = 0.f, g1 = 0.f;
+    const int prow = row * TW + col0;
+    const uint32_t a2row = sA2 + prow * 128 + ((cl & 3) << 2);
+    const uint32_t cq = static_cast<uint32_t>(cl >> 2) << 4;
+#pragma unroll
+    for (int r = 0; r < COLS; ++r) {
+        // A2 row prow + r, 16-byte chunk (cl >> 2) ^ (row & 7); with 8-aligned segments (prow + r) & 7 == r & 7
+        const int sw = (COLS % 8 == 0 && TW % 8 == 0) ? (r & 7) : ((prow + r) & 7);
+        const uint32_t hv = relu_pack ? pack_act<CABINET_ACT_RELU>(acc[r].x, acc[r].y)
+                                      : pack_act<CABINET_ACT_NONE>(acc[r].x, acc[r].y);
+        sts32(a2row + r * 128 + (cq ^ (static_cast<uint32_t>(sw) << 4)), hv);
+        if (want_gap && row_valid && ow_base + col0 + r < p.OW) {
+            g0 += acc[r].x;
+            g1 += acc[r].y;
+        }
+    }
+    if (want_gap) {
+        reds_f32(s_gap + (c0 << 2), g0);
+        reds_f32(s_gap + (c0 << 2) + 4, g1);
+    }
+}
+
+// Epilogue 1 for one TMEM piece (this thread's pixel row, 32 columns): act, bf16, -> E (the bias is already in D1).
 template <int ACT>
-__device__ __forceinline__ void epi1_piece(const uint32_t* v, uint32_t bias_addr, uint32_t dst, int ncol, bool keep) {
+__device__ __forceinline__ void epi1_piece(const uint32_t* v, uint32_t dst, int ncol, bool keep) {
 #pragma unroll
     for (int h16 = 0; h16 < 2; ++h16) {
         if (h16 * 16 < ncol) {
             uint32_t o[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 bb = lds128f(bias_addr + h16 * 64 + 16 * j);
-                o[2 * j] = pack_act<ACT>(__uint_as_float(v[h16 * 16 + 4 * j + 0]) + bb.x,
-                                         __uint_as_float(v[h16 * 16 + 4 * j + 1]) + bb.y);
-                o[2 * j + 1] = pack_act<ACT>(__uint_as_float(v[h16 * 16 + 4 * j + 2]) + bb.z,
-                                             __uint_as_float(v[h16 * 16 + 4 * j + 3]) + bb.w);
-            }
+            for (int j = 0; j < 8; ++j)
+                o[j] = pack_act<ACT>(__uint_as_float(v[h16 * 16 + 2 * j]), __uint_as_float(v[h16 * 16 + 2 * j + 1]));
             if (!keep) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = 0u;
@@ -213,7 +224,6 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     constexpr int IWT = (TW - 1) * S + K, IHT = (TH - 1) * S + K, NPIX = IWT * IHT, NMT = (NPIX + 127) / 128;
     constexpr int NSEG = NCW / TH, WSEG = TW / NSEG, NOUT = TH * TW;
     constexpr int D2COL = NMT * 64;
-    constexpr int AUX_BIAS = K * K * 256;  // byte offset of the expand bias inside a chunk's aux block
     static_assert(NCW % TH == 0 && TW % NSEG == 0 && WSEG % 4 == 0 && NOUT <= 128 && D2COL + 64 <= TMEM_COLS, "tile shape");
 
     extern __shared__ uint8_t smem_raw[];
@@ -288,7 +298,15 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         auto mma1 = [&](int it, int c) {
             const int g = it * nc + c;
             const int buf = p.resident ? c : (g & 1);
-            if (c == 0) tc::mbar_wait(&a1_full, it & 1);
+            if (c == 0) {
+                tc::mbar_wait(&a1_full, it & 1);
+                // bias slots: K columns Cin, Cin+1 of every staged pixel <- 1.0 (one 4-byte store per row, in the row's
+                // swizzled 16-byte chunk); this warp also issues the MMAs, so a proxy fence is all the ordering needed
+                const uint32_t ones = 0x3F803F80u;
+                for (int r = lane; r < NPIX; r += 32) sts32(sA1 + r * 128 + ((((p.Cin >> 3) ^ (r & 7))) << 4), ones);
+                tc::fence_proxy_async();
+                __syncwarp();
+            }
             tc::mbar_wait(&w_full[buf], p.resident ? 0 : ((g >> 1) & 1));
             mbar_wait_parked(&d1_free, (g & 1) ^ 1);
             tc::tc_fence_after();
@@ -384,7 +402,6 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 if (ncol > 0) {
                     uint32_t va[32], vb[32];
                     const uint32_t t0 = tmem + hcol * 32 + (static_cast<uint32_t>(q * 32) << 16);
-                    const uint32_t bias_addr = s_aux + AUX_BIAS + hcol * 128;
                     tc::tmem_ld32(t0, va);
 #pragma unroll
                     for (int m = 0; m < NMT; ++m) {
@@ -402,9 +419,9 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                                 keep = ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
                             }
                             const uint32_t dst = sE + r * E_PITCH + hcol * 64;
-                            if (p.act_e == CABINET_ACT_RELU) epi1_piece<CABINET_ACT_RELU>(cur, bias_addr, dst, ncol, keep);
-                            else if (p.act_e == CABINET_ACT_HSWISH) epi1_piece<CABINET_ACT_HSWISH>(cur, bias_addr, dst, ncol, keep);
-                            else epi1_piece<CABINET_ACT_NONE>(cur, bias_addr, dst, ncol, keep);
+                            if (p.act_e == CABINET_ACT_RELU) epi1_piece<CABINET_ACT_RELU>(cur, dst, ncol, keep);
+                            else if (p.act_e == CABINET_ACT_HSWISH) epi1_piece<CABINET_ACT_HSWISH>(cur, dst, ncol, keep);
+                            else epi1_piece<CABINET_ACT_NONE>(cur, dst, ncol, keep);
                         }
                         MB_STAMP(rec && m < 2, 16 * g + 10 + 2 * m);
                     }
@@ -630,8 +647,8 @@ extern "C" int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, 
                                     long long ldy, int OH, int OW, float* gap_sum, cabinet_stream_t stream) {
     CAB_REQUIRE(x && w_expand && aux_packed && y, "mbconv_fused: null pointer");
     CAB_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2), "mbconv_fused: k must be 3|5 and stride 1|2");
-    CAB_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cin <= 64 && Cexp > 0 && Cexp % 8 == 0 && Cexp <= 1024,
-                "mbconv_fused: needs Cin <= 64 and Cexp %% 8 == 0 (got Cin %d, Cexp %d)", Cin, Cexp);
+    CAB_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cin <= 56 && Cin % 8 == 0 && Cexp > 0 && Cexp % 8 == 0 && Cexp <= 1024,
+                "mbconv_fused: needs Cin %% 8 == 0, Cin <= 56 and Cexp %% 8 == 0 (got Cin %d, Cexp %d)", Cin, Cexp);
     const int pad = (k - 1) / 2;
     CAB_REQUIRE(OH == (H + 2 * pad - k) / stride + 1 && OW == (W + 2 * pad - k) / stride + 1,
                 "mbconv_fused: inconsistent output size");
@@ -654,7 +671,7 @@ extern "C" int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, 
     p.cout_pad = project ? (Cout + 15) / 16 * 16 : 0;
     p.n_chunks = (Cexp + 63) / 64;
     p.act_e = act_expand; p.act_dw = act_dw; p.has_res = residual ? 1 : 0;
-    p.ksteps1 = (Cin + 15) / 16;
+    p.ksteps1 = (Cin + 2 + 15) / 16;  // + the two bias slots
     p.aux = aux_packed; p.b2 = b_project;
     p.res = reinterpret_cast<const bf16*>(x); p.ldres = ldx; p.gap = gap_sum; p.dbg = g_mb_dbg;
     cudaStream_t st = static_cast<cudaStream_t>(stream);

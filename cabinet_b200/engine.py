@@ -163,8 +163,16 @@ class Engine:
                     dwl, kk, nc = e["dw"], e["dw"].k ** 2, -(-e["dw"].c // 64)
                     aux = torch.zeros((nc * 64, kk + 2), dtype=f32, device=dwl.w.device)
                     aux[: dwl.c, :kk] = dwl.w.t()
-                    aux[: dwl.c, kk], aux[: dwl.c, kk + 1] = e["pw1"].b, dwl.b
+                    aux[: dwl.c, kk + 1] = dwl.b
                     e["aux"] = aux.view(nc, 64, kk + 2).permute(0, 2, 1).contiguous()
+                    p1 = e["pw1"]
+                    if p1.cin % 8 == 0 and p1.cin <= 56:
+                        # expand weights with the bias as two extra K columns (bf16 hi + lo; the kernel feeds 1.0 there)
+                        wb = torch.zeros((-(-p1.cout // 16) * 16, 64), dtype=f32, device=dwl.w.device)
+                        wb[: p1.cout, : p1.cin] = p1.tc[: p1.cout, 0, : p1.cin].float()
+                        hi = p1.b.to(torch.bfloat16).float()
+                        wb[: p1.cout, p1.cin], wb[: p1.cout, p1.cin + 1] = hi, p1.b - hi
+                        e["w1b"] = wb.to(torch.bfloat16).contiguous()
             else:
                 e["dw"] = DwLayer(c[0], c[1], act, f"mobile.f{bi}.dw")
                 se, pw2, bn2 = c[3], c[4], c[5]
@@ -320,7 +328,7 @@ class Engine:
             nbytes += pw2.w.numel() * 2 + (x.N * OH * OW * cy * 2 if s["identity"] else 0)
             flops += 2 * x.N * OH * OW * dw.c * pw2.cout
         self._run("mbconv_fused", dw.name.replace(".dw", "") + ("" if project else ".expand+dw"), nbytes, flops,
-                  self.lib.cabinet_mbconv_fused, x.ptr, x.ld, x.N, x.H, x.W, x.C, pw1.tc.data_ptr(), e["aux"].data_ptr(),
+                  self.lib.cabinet_mbconv_fused, x.ptr, x.ld, x.N, x.H, x.W, x.C, e["w1b"].data_ptr(), e["aux"].data_ptr(),
                   dw.c, pw1.act, dw.k, dw.stride, dw.act,
                   pw2.tc.data_ptr() if project else None, pw2.b.data_ptr() if project else None,
                   pw2.cout if project else 0, 1 if project and s["identity"] else 0, out.ptr, out.ld, OH, OW,
@@ -435,8 +443,8 @@ class Engine:
                           o.ptr, o.ld, f.N, f.H, f.W, f.C, dw.act, self.stream)
                 f = o
                 continue
-            fuse = (s["expand"] and self.fuse_mbconv and self.use_tc and f.C <= 64 and f.dt == BF16 and f.ld % 8 == 0
-                    and f.off % 8 == 0 and s["exp"] % 8 == 0 and ("se" in e or s["out"] <= 128) and "aux" in e
+            fuse = (s["expand"] and self.fuse_mbconv and self.use_tc and f.dt == BF16 and f.ld % 8 == 0
+                    and f.off % 8 == 0 and s["exp"] % 8 == 0 and ("se" in e or s["out"] <= 128) and "w1b" in e
                     and not e.get("nofuse")
                     # 5x5 stride-2 tiles are 4 x 8 outputs behind an 11 x 19 halo: measured slower than expand + dwconv_tma
                     and not (s["k"] == 5 and s["s"] == 2))

@@ -125,10 +125,13 @@ int cabinet_mbconv_noexpand_fused(const void* x, long long ldx, const float* w_d
  *   w_project != NULL:  y = W_p * d + b_p (+ x when residual)                (mobilenetv3.py:145-159), y has Cout channels
  *   w_project == NULL:  y = d (Cexp channels) and gap_sum[n][c] += sum over pixels of d (blocks with squeeze-excite:
  *                       the SE gate needs the global mean before the project conv; act_dw is NONE there).
- * The expanded activation h never reaches HBM (TMEM -> shared memory -> depthwise).  w_expand / w_project use the
- * cabinet_conv_tc packing (bf16 [ceil16(Cout)][1][ceil64(Cin)]).  aux_packed is fp32 [ceil(Cexp/64)][k*k + 2][64],
- * zero padded, BN folded: rows 0..k*k-1 = depthwise taps of the chunk's 64 channels, row k*k = expand bias,
- * row k*k+1 = depthwise bias (one bulk copy per chunk).  b_project fp32 [Cout].
+ * The expanded activation h never reaches HBM (TMEM -> shared memory -> depthwise).
+ * w_expand: bf16 [ceil16(Cexp)][64], row = expanded channel: columns 0..Cin-1 = W_e (BN folded), columns Cin, Cin+1 =
+ *           b_e split into bf16 (hi, lo) -- the kernel feeds 1.0 into those two K slots, the bias is part of the GEMM --
+ *           remaining columns 0.  Needs Cin % 8 == 0 and Cin <= 56.
+ * w_project: the cabinet_conv_tc packing (bf16 [ceil16(Cout)][1][ceil64(Cexp)]); b_project fp32 [Cout].
+ * aux_packed: fp32 [ceil(Cexp/64)][k*k + 2][64], zero padded, BN folded: rows 0..k*k-1 = depthwise taps of the chunk's
+ *           64 channels, row k*k = reserved (0), row k*k+1 = depthwise bias (one bulk copy per chunk).
  * k in {3,5}, stride in {1,2}, pad (k-1)/2; Cexp % 8 == 0; Cout <= 128; gap_sum ([N][Cexp], zeroed by the caller) may be NULL. */
 int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_expand,
                          const float* aux_packed, int Cexp, int act_expand, int k, int stride, int act_dw,

@@ -468,6 +468,16 @@ def _pack_aux(wd, be, bd):
     return aux.view(nc, 64, kk + 2).permute(0, 2, 1).contiguous().cuda()
 
 
+def _pack_expand(we, be):
+    """[ceil16(Cexp)][64] bf16: expand weights + the bias as two extra K columns (hi, lo) -- include/cabinet_b200.h."""
+    cexp, cin = we.shape[:2]
+    pk = torch.zeros(-(-cexp // 16) * 16, 64)
+    pk[:cexp, :cin] = we.reshape(cexp, cin)
+    hi = be.to(torch.bfloat16).float()
+    pk[:cexp, cin], pk[:cexp, cin + 1] = hi, be - hi
+    return pk.to("cuda", torch.bfloat16).contiguous()
+
+
 def _pack_tc(w, dtype=torch.bfloat16):
     cout, cin = w.shape[:2]
     n16, c64 = -(-cout // 16) * 16, -(-cin // 64) * 64
@@ -483,7 +493,7 @@ def _pack_tc(w, dtype=torch.bfloat16):
     (40, 120, 40, 5, 1, 19, 23, ACT_RELU, True),      # k5 with project
     (16, 16, 16, 3, 1, 9, 7, ACT_RELU, True),         # single narrow chunk, tile larger than the image
     (24, 88, 24, 5, 2, 33, 17, ACT_HSWISH, False),    # Small f3-like k5 stride 2, odd sizes
-    (64, 128, 64, 3, 1, 16, 16, ACT_HSWISH, True),
+    (56, 128, 56, 3, 1, 16, 16, ACT_HSWISH, True),
     (16, 72, 24, 3, 2, 30, 34, ACT_RELU, False),      # Small f2: two chunks at stride 2 (narrow-tile fallback)
     (40, 240, 40, 5, 1, 14, 18, ACT_HSWISH, True),    # Small f5-like: four k5 chunks, streamed taps
 ])
@@ -507,7 +517,7 @@ def test_mbconv_fused_project(cin, cexp, cout, k, s, H, W, act, res):
     ym = to_map(torch.zeros_like(ref), dtype, ld=cout + 24, off=16)
     ym.t.fill_(7.0)
     aux, bpd = _pack_aux(wd, be, bd), bp.cuda()
-    pe, pp = _pack_tc(we), _pack_tc(wp)
+    pe, pp = _pack_expand(we, be), _pack_tc(wp)
     check(lib.cabinet_mbconv_fused(xm.ptr, xm.ld, N, H, W, cin, pe.data_ptr(), aux.data_ptr(), cexp, act, k, s, act,
                                    pp.data_ptr(), bpd.data_ptr(), cout, 1 if res else 0, ym.ptr, ym.ld, OH, OW, None,
                                    stream()), "mbconv_fused")
@@ -543,7 +553,7 @@ def test_mbconv_fused_dw_out(cin, cexp, k, s, H, W, act):
     ym.t.fill_(7.0)
     gap = torch.zeros(N, cexp, device="cuda")
     aux = _pack_aux(wd, be, bd)
-    pe = _pack_tc(we)
+    pe = _pack_expand(we, be)
     check(lib.cabinet_mbconv_fused(xm.ptr, xm.ld, N, H, W, cin, pe.data_ptr(), aux.data_ptr(), cexp, act, k, s,
                                    ACT_NONE, None, None, 0, 0, ym.ptr, ym.ld, OH, OW, gap.data_ptr(), stream()),
           "mbconv_fused")
