@@ -316,7 +316,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         v[4 * j4 + 2] = __uint_as_float(r[16 * c + 4 * j4 + 2]) + b.z;
                         v[4 * j4 + 3] = __uint_as_float(r[16 * c + 4 * j4 + 3]) + b.w;
                     }
-                    if constexpr (ACT == CABINET_ACT_RELU) {
+                    constexpr bool RELU_ON_CVT = ACT == CABINET_ACT_RELU && !HAS_RES && !OUT_F32;  // cvt.rn.relu.bf16x2
+                    if constexpr (ACT == CABINET_ACT_RELU && !RELU_ON_CVT) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                     } else if constexpr (ACT == CABINET_ACT_HSWISH) {
@@ -344,8 +345,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                     if constexpr (!OUT_F32) {
                         Vec16<bf16> o0, o1;
-                        o0.pack(v);
-                        o1.pack(v + 8);
+                        if constexpr (RELU_ON_CVT) {
+                            uint32_t w[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+                            o0.raw = make_uint4(w[0], w[1], w[2], w[3]);
+                            o1.raw = make_uint4(w[4], w[5], w[6], w[7]);
+                        } else {
+                            o0.pack(v);
+                            o1.pack(v + 8);
+                        }
                         const uint32_t rowa = tc::smem_u32(buf) + row * 128;
                         tc::sts128(rowa + (((2 * c) ^ (row & 7)) << 4), o0.raw);
                         tc::sts128(rowa + (((2 * c + 1) ^ (row & 7)) << 4), o1.raw);

@@ -213,13 +213,14 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             const uint32_t rowp = tc::smem_u32(bsb) + r * 128;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {  // 8 channels (16 bytes) per chunk, ReLU
-                float v[8];
+                uint32_t w[4];  // ReLU rides on the convert (cvt.rn.relu.bf16x2)
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    v[j] = fmaxf(__uint_as_float(g < 4 ? a0[8 * g + j] : a1[8 * (g - 4) + j]), 0.f);
-                Vec16<bf16> o;
-                o.pack(v);
-                tc::sts128(rowp + ((g ^ (r & 7)) << 4), o.raw);
+                for (int j = 0; j < 4; ++j) {
+                    const float lo = __uint_as_float(g < 4 ? a0[8 * g + 2 * j] : a1[8 * (g - 4) + 2 * j]);
+                    const float hi = __uint_as_float(g < 4 ? a0[8 * g + 2 * j + 1] : a1[8 * (g - 4) + 2 * j + 1]);
+                    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(hi), "f"(lo));
+                }
+                tc::sts128(rowp + ((g ^ (r & 7)) << 4), make_uint4(w[0], w[1], w[2], w[3]));
             }
 #pragma unroll
             for (int g = 0; g < 2; ++g) {  // backbone stem: HardSwish
