@@ -180,7 +180,9 @@ mbconv1_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mb1Params p)
     const int ow0 = (blockIdx.x % tiles_w) * MB_TW, oh0 = (blockIdx.x / tiles_w) * MB_TH;
     const int n = blockIdx.z;
     uint8_t* tile = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dw) + 127) & ~uintptr_t(127));
-    float* hs = reinterpret_cast<float*>(tile + ((IWT * IHT * PITCH + 127) & ~127));  // [512 px][C] fp32 dw output
+    constexpr bool MMA = C >= 16;  // pointwise on mma.sync (bf16 hidden tile) / on the CUDA cores (fp32 hidden tile)
+    uint8_t* hs_raw = tile + ((IWT * IHT * PITCH + 127) & ~127);
+    float* hs = reinterpret_cast<float*>(hs_raw);  // [512 px][C] depthwise output
 
     if (threadIdx.x == 0) {
         tc::mbar_init(&bar, 1);
@@ -222,14 +224,86 @@ mbconv1_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mb1Params p)
                     }
                 }
             cab_act_vec<2 * COLS>(&acc[0].x, p.act);
+            if constexpr (MMA) {
+                const uint32_t hb = tc::smem_u32(hs_raw) + ((row * MB_TW + col0) * C + c0) * 2;
 #pragma unroll
-            for (int r = 0; r < COLS; ++r)
-                *reinterpret_cast<float2*>(hs + (row * MB_TW + col0 + r) * C + c0) = acc[r];
+                for (int r = 0; r < COLS; ++r) {
+                    const __nv_bfloat162 hv = __floats2bfloat162_rn(acc[r].x, acc[r].y);
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(hb + r * C * 2), "r"(*reinterpret_cast<const uint32_t*>(&hv)) : "memory");
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < COLS; ++r)
+                    *reinterpret_cast<float2*>(hs + (row * MB_TW + col0 + r) * C + c0) = acc[r];
+            }
         }
     }
     __syncthreads();
-    // ---- phase 2: pointwise C -> C (+ bias + residual); work item = (pixel, cout pair)
-    {
+    // ---- phase 2: pointwise C -> C (+ bias + residual)
+    if constexpr (MMA) {
+        // warp-level tensor-core GEMM (mma.sync.m16n8k16, bf16 -> fp32): per 16 pixels one ldmatrix.x4 per 16 input
+        // channels and C/8 MMAs; the weight fragments live in registers for the whole CTA.  A TMEM round trip
+        // (tcgen05) does not pay for K = C = 16.
+        constexpr int KS = C / 16, NT = C / 8;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int gq = lane >> 2, tq = lane & 3;  // fragment row group / column pair
+        uint32_t bfrag[KS][NT][2];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const float* wp = p.w_pw + (nt * 8 + gq) * C + ks * 16 + hh * 8 + tq * 2;  // B[k][n] = W[n][k]
+                    const __nv_bfloat162 wv = __floats2bfloat162_rn(__ldg(wp), __ldg(wp + 1));
+                    bfrag[ks][nt][hh] = *reinterpret_cast<const uint32_t*>(&wv);
+                }
+        float2 bias[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) bias[nt] = __ldg(reinterpret_cast<const float2*>(p.b_pw + nt * 8 + tq * 2));
+        const uint32_t hbase = tc::smem_u32(hs_raw);
+        // ldmatrix.x4: lane -> (matrix = lane / 8, row = lane % 8); matrices: rows 0-7 / 8-15 x k 0-7 / 8-15
+        const uint32_t lm_off = ((lane & 7) + ((lane >> 3) & 1) * 8) * (C * 2) + (lane >> 4) * 16;
+        for (int mt = warp; mt < MB_TH * MB_TW / 16; mt += 8) {
+            const int px0 = mt * 16;  // 16 consecutive pixels of one tile row (MB_TW is a multiple of 16)
+            float acc[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                acc[nt][0] = bias[nt].x; acc[nt][1] = bias[nt].y; acc[nt][2] = bias[nt].x; acc[nt][3] = bias[nt].y;
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                uint32_t a0, a1, a2, a3;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                             : "r"(hbase + px0 * (C * 2) + lm_off + ks * 32));
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                                 : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bfrag[ks][nt][0]), "r"(bfrag[ks][nt][1]));
+            }
+            const int row = px0 / MB_TW, colb = px0 % MB_TW;
+            const int oh = oh0 + row;
+            if (oh >= p.OH) continue;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {  // fragment rows gq and gq + 8
+                const int col = colb + gq + hh * 8;
+                if (ow0 + col >= p.OW) continue;
+                const uint32_t res = tc::smem_u32(tile) + ((row + PAD) * IWT + col + PAD) * PITCH + tq * 4;
+                bf16* yp = p.y + ((static_cast<long long>(n) * p.OH + oh) * p.OW + ow0 + col) * p.ldy + tq * 2;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    uint32_t raw;  // residual: the block input at the same pixel (centre of the staged patch)
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(res + nt * 16));
+                    const float o0 = acc[nt][2 * hh] + __uint_as_float(raw << 16);
+                    const float o1 = acc[nt][2 * hh + 1] + __uint_as_float(raw & 0xffff0000u);
+                    *reinterpret_cast<__nv_bfloat162*>(yp + nt * 8) = __floats2bfloat162_rn(o0, o1);
+                }
+            }
+        }
+    } else {
+        // CUDA-core pointwise; work item = (pixel, cout pair)
         constexpr int PAIRS = C / 2;
         const int cp = threadIdx.x % PAIRS;
         const int co = cp * 2;
@@ -304,7 +378,7 @@ extern "C" int cabinet_mbconv_noexpand_fused(const void* x, long long ldx, const
     p.C = C; p.OH = H; p.OW = W; p.act = act; p.w_dw = w_dw; p.b_dw = b_dw; p.w_pw = w_pw; p.b_pw = b_pw;
     p.y = reinterpret_cast<bf16*>(y); p.ldy = ldy;
     const size_t smem = static_cast<size_t>(MB_TW + 2) * (MB_TH + 2) * C * 2 + 128 +
-                        static_cast<size_t>(MB_TH) * MB_TW * C * 4 + 128;
+                        static_cast<size_t>(MB_TH) * MB_TW * C * (C >= 16 ? 2 : 4) + 128;  // bf16 / fp32 hidden tile
     const int tiles = ((W + MB_TW - 1) / MB_TW) * ((H + MB_TH - 1) / MB_TH);
     dim3 grid(tiles, 1, N);
     static bool attr_done = false;
