@@ -169,11 +169,10 @@ constexpr int MB_TH = 16, MB_TW = 32;  // output patch of the fused block kernel
 template <int C>
 __global__ void __launch_bounds__(256)
 mbconv1_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mb1Params p) {
-    constexpr int K = 3, PAD = 1, COLS = 8;
+    constexpr int K = 3, PAD = 1;
     constexpr int IWT = MB_TW + 2, IHT = MB_TH + 2;
     constexpr int PITCH = C * 2;            // staged pixel pitch in bytes (TMA box = exactly C channels)
     constexpr int LANES_PX = C / 2;         // lanes per pixel (channel pairs)
-    constexpr int GROUPS = MB_TW / COLS;    // column groups per row
     extern __shared__ __align__(128) uint8_t smem_dw[];
     __shared__ __align__(8) uint64_t bar;
     const int tiles_w = (p.OW + MB_TW - 1) / MB_TW;
@@ -192,49 +191,55 @@ mbconv1_fused_kernel(const __grid_constant__ CUtensorMap tmX, const Mb1Params p)
         tc::tma_load_4d(tile, &tmX, &bar, 0, ow0 - PAD, oh0 - PAD, n);
     }
     __syncthreads();
-    // ---- phase 1: depthwise 3x3 + bias + act; work item = (row, column group of 8, channel pair)
+    // ---- phase 1: depthwise 3x3 + bias + act.  A warp covers CW = 32 / LANES_PX adjacent columns x all channel pairs
+    // (one contiguous 128-byte line of the staged patch per LDS: conflict-free; column GROUPS side by side in a warp
+    // would sit 256 B apart = the same banks, a 4-way conflict) and slides DOWN 8 output rows: 10 x 3 loads feed
+    // 8 x 9 packed FMAs per thread.
     {
-        constexpr int ITEMS = MB_TH * GROUPS * LANES_PX;
+        constexpr int CW = 32 / LANES_PX;            // columns per warp
+        constexpr int CGROUPS = MB_TW / CW;          // column groups per tile row
+        constexpr int ROWS = 8;                      // output rows per thread
+        constexpr int WITEMS = CGROUPS * (MB_TH / ROWS);
+        static_assert(MB_TW % CW == 0 && MB_TH % ROWS == 0, "tile shape");
         float2 w[K * K];
-        const int cl = threadIdx.x % LANES_PX;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int cl = lane % LANES_PX, j = lane / LANES_PX;
         const int c0 = cl * 2;
 #pragma unroll
         for (int t = 0; t < K * K; ++t) w[t] = __ldg(reinterpret_cast<const float2*>(p.w_dw + t * C + c0));
         const float2 b = __ldg(reinterpret_cast<const float2*>(p.b_dw + c0));
         tc::mbar_wait(&bar, 0);
-        for (int item = threadIdx.x; item < ITEMS; item += 256) {  // 256 % LANES_PX == 0: cl is loop invariant
-            const int rest = item / LANES_PX;
-            const int grp = rest % GROUPS, row = rest / GROUPS;
-            const int col0 = grp * COLS;
-            float2 acc[COLS];
+        for (int wi = warp; wi < WITEMS; wi += 8) {
+            const int col = (wi % CGROUPS) * CW + j, row0 = (wi / CGROUPS) * ROWS;
+            float2 acc[ROWS];
 #pragma unroll
-            for (int r = 0; r < COLS; ++r) acc[r] = b;
-            const uint32_t base = tc::smem_u32(tile) + (row * IWT + col0) * PITCH + cl * 4;
+            for (int r = 0; r < ROWS; ++r) acc[r] = b;
+            const uint32_t base = tc::smem_u32(tile) + (row0 * IWT + col) * PITCH + cl * 4;
 #pragma unroll
-            for (int ky = 0; ky < K; ++ky)
+            for (int sy = 0; sy < ROWS + K - 1; ++sy)
 #pragma unroll
-                for (int sx = 0; sx < COLS + K - 1; ++sx) {
+                for (int kx = 0; kx < K; ++kx) {
                     uint32_t raw;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(base + (ky * IWT + sx) * PITCH));
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(raw) : "r"(base + (sy * IWT + kx) * PITCH));
                     const float2 xv = make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
 #pragma unroll
-                    for (int r = 0; r < COLS; ++r) {
-                        const int kx = sx - r;
-                        if (kx >= 0 && kx < K) cab_ffma2(acc[r], xv, w[ky * K + kx]);
+                    for (int r = 0; r < ROWS; ++r) {
+                        const int ky = sy - r;
+                        if (ky >= 0 && ky < K) cab_ffma2(acc[r], xv, w[ky * K + kx]);
                     }
                 }
-            cab_act_vec<2 * COLS>(&acc[0].x, p.act);
+            cab_act_vec<2 * ROWS>(&acc[0].x, p.act);
             if constexpr (MMA) {
-                const uint32_t hb = tc::smem_u32(hs_raw) + ((row * MB_TW + col0) * C + c0) * 2;
+                const uint32_t hb = tc::smem_u32(hs_raw) + ((row0 * MB_TW + col) * C + c0) * 2;
 #pragma unroll
-                for (int r = 0; r < COLS; ++r) {
+                for (int r = 0; r < ROWS; ++r) {
                     const __nv_bfloat162 hv = __floats2bfloat162_rn(acc[r].x, acc[r].y);
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(hb + r * C * 2), "r"(*reinterpret_cast<const uint32_t*>(&hv)) : "memory");
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(hb + r * MB_TW * C * 2), "r"(*reinterpret_cast<const uint32_t*>(&hv)) : "memory");
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < COLS; ++r)
-                    *reinterpret_cast<float2*>(hs + (row * MB_TW + col0 + r) * C + c0) = acc[r];
+                for (int r = 0; r < ROWS; ++r)
+                    *reinterpret_cast<float2*>(hs + ((row0 + r) * MB_TW + col) * C + c0) = acc[r];
             }
         }
     }
