@@ -37,7 +37,7 @@ __device__ __forceinline__ void dw_row(const DwParams& p, const uint8_t* tile, u
     const int row = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lanes_px = cw >> 1;               // lanes per pixel (channel pairs of this chunk)
     const int grp = lane / lanes_px, cl = lane - grp * lanes_px;
-    const int c0 = chunk * 64 + cl * 2;
+    const int c0 = chunk * p.CB + cl * 2;
     const bool active = grp < TW / COLS;
     const int col0 = grp * COLS;
 
@@ -129,12 +129,12 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmX, const DwParams p) {
         tc::mbar_fence_init();
         tc::fence_proxy_async();
         tc::mbar_expect_tx(&bar, static_cast<uint32_t>(IWT * IHT * 128));
-        tc::tma_load_4d(tile, &tmX, &bar, chunk * 64, ow0 * S - PAD, oh0 * S - PAD, n);
+        tc::tma_load_4d(tile, &tmX, &bar, chunk * p.CB, ow0 * S - PAD, oh0 * S - PAD, n);
     }
     if (p.gap_sum && threadIdx.x < 64) s_gap[threadIdx.x] = 0.f;
     __syncthreads();
 
-    const int cw = min(64, p.C - chunk * 64);  // channels of this chunk (multiple of 8)
+    const int cw = min(p.CB, p.C - chunk * p.CB);  // channels of this chunk (multiple of 8)
     // columns per lane: as many column groups as fit into the 32 lanes (power of two)
     if (cw > 32) dw_row<K, S, 16>(p, tile, &bar, s_gap, cw, chunk, n, oh0, ow0);
     else if (cw > 16) dw_row<K, S, 8>(p, tile, &bar, s_gap, cw, chunk, n, oh0, ow0);
@@ -143,7 +143,7 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmX, const DwParams p) {
 
     if (p.gap_sum) {
         __syncthreads();
-        const int c = chunk * 64 + threadIdx.x;
+        const int c = chunk * p.CB + threadIdx.x;
         if (threadIdx.x < cw) atomicAdd(&p.gap_sum[static_cast<long long>(n) * p.C + c], s_gap[threadIdx.x]);
     }
 }
@@ -417,13 +417,16 @@ extern "C" int cabinet_dwconv_tma(const void* x, long long ldx, const float* w, 
     DwParams p;
     const int n_chunks = (C + 63) / 64;
     p.C = C; p.OH = OH; p.OW = OW; p.act = act; p.w = w; p.bias = bias;
-    p.CB = 64;  // TMA box = 64 channels; the last chunk may be narrower (zero filled)
+    // balanced chunks (multiples of 8 channels, <= 64): 72 -> 40 + 32, 200 -> 56 + 56 + 56 + 32.  A ragged 8-channel
+    // tail would pack 8 column groups into a warp whose rows sit a multiple of 128 B apart: an 8-way bank conflict
+    // that makes the tail cost more than a full chunk.  The TMA box stays 64 channels wide.
+    p.CB = ((C + n_chunks - 1) / n_chunks + 7) / 8 * 8;
     p.y = reinterpret_cast<bf16*>(y); p.ldy = ldy; p.gap_sum = gap_sum;
     const int IWT = (TW - 1) * stride + k, IHT = (TH - 1) * stride + k;
     CUtensorMap tm;
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     const uint64_t strides[3] = {(uint64_t)ldx * 2, (uint64_t)ldx * 2 * W, (uint64_t)ldx * 2 * W * H};
-    const uint32_t box[4] = {(uint32_t)p.CB, (uint32_t)IWT, (uint32_t)IHT, 1};
+    const uint32_t box[4] = {64, (uint32_t)IWT, (uint32_t)IHT, 1};
     int rc = cab_make_tmap_bf16(&tm, x, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
