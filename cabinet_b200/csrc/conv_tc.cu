@@ -30,7 +30,7 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int C_STAGE_BYTES = BLOCK_M * 128;  // one [128 rows x 64 ch] bf16 store box
 constexpr int MAX_STAGES = 8;
 constexpr int NUM_THREADS = 320;
-constexpr int B_RESIDENT_MAX = 64 * 1024;
+constexpr int B_RESIDENT_MAX = 80 * 1024;  // sb.conv2 (3x3, 64 -> 64: 72 KB) stays resident
 constexpr int SMEM_LIMIT = 220 * 1024;
 
 struct TcConvParams {
@@ -40,6 +40,7 @@ struct TcConvParams {
     int cin_blocks, num_k_blocks;
     int block_n, n_tiles, num_tiles, tmem_cols, stages, b_resident;
     int act, y_dtype, debug;
+    int c_bufs;               // store staging buffers per epilogue warpgroup: 2, or 1 when a tile is a single 64-column group
     int a_act, hw;            // A-operand prologue: x <- act(x * a_scale[image][channel]); hw = pixels per image
     const float* a_scale;     // [N][Cin] fp32 or nullptr
     const float* bias;
@@ -83,8 +84,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_stage_bytes = p.block_n * BLOCK_K * 2;
-    uint8_t* sC = smem;                                   // 4 x 16 KB store staging (2 per epilogue warpgroup)
-    uint8_t* sA = sC + 4 * C_STAGE_BYTES;                 // ring: stages x 16 KB
+    uint8_t* sC = smem;                                   // 2 x c_bufs x 16 KB store staging (c_bufs per epilogue warpgroup)
+    uint8_t* sA = sC + 2 * p.c_bufs * C_STAGE_BYTES;      // ring: stages x 16 KB
     uint8_t* sB = sA + p.stages * A_STAGE_BYTES;          // ring (stages x b_stage) or resident (num_k_blocks x b_stage)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -263,7 +264,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int row = q * 32 + lane;
         const int gtid = threadIdx.x - 64 - e * 128;  // 0..127 inside the warpgroup
         const bool leader = gtid == 0;
-        uint8_t* myC = sC + e * 2 * C_STAGE_BYTES;
+        uint8_t* myC = sC + e * p.c_bufs * C_STAGE_BYTES;
         float* myBias = s_bias[e];
         uint32_t store_seq = 0;
         int it = e, bias_n0 = -1;
@@ -283,7 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t taddr = tmem + e * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
             const int ngroups = (p.block_n + 63) >> 6;
             for (int grp = 0; grp < ngroups; ++grp) {
-                uint8_t* buf = myC + (store_seq & 1) * C_STAGE_BYTES;
+                uint8_t* buf = myC + (p.c_bufs == 2 ? (store_seq & 1) : 0) * C_STAGE_BYTES;
                 const int nch = min(4, (p.block_n - grp * 64) >> 4);  // 16-column chunks in this 64-column group
                 // issue all TMEM loads of the group, then one wait: 64 independent values per thread
                 uint32_t r[64];
@@ -299,7 +300,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
                 if constexpr (!OUT_F32) {
                     // the TMA store that used this staging buffer two groups ago must have finished reading it
-                    if (leader) tc::bulk_wait_read<1>();
+                    if (leader) {
+                        if (p.c_bufs == 2) tc::bulk_wait_read<1>();
+                        else tc::bulk_wait_read<0>();  // single buffer: its previous store (two tiles ago) must be done
+                    }
                     tc::named_bar_sync(1 + e, 128);
                 }
 #pragma unroll
@@ -488,7 +492,8 @@ extern "C" int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, in
     while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
     const int b_stage_bytes = p.block_n * BLOCK_K * 2;
     p.b_resident = (p.n_tiles == 1 && p.num_k_blocks * b_stage_bytes <= B_RESIDENT_MAX) ? 1 : 0;
-    const int fixed = 4 * C_STAGE_BYTES + (p.b_resident ? p.num_k_blocks * b_stage_bytes : 0) + 1024;
+    p.c_bufs = (y_dtype == CABINET_BF16 && p.block_n > 64) ? 2 : 1;
+    const int fixed = 2 * p.c_bufs * C_STAGE_BYTES + (p.b_resident ? p.num_k_blocks * b_stage_bytes : 0) + 1024;
     const int stage_bytes = A_STAGE_BYTES + (p.b_resident ? 0 : b_stage_bytes);
     // experiment hook: CAB_SMEM_CAP_KB caps the dynamic smem of kernels whose accumulators need <= 256 TMEM columns, so
     // that two CTAs (e.g. from two streams) can share an SM
@@ -565,7 +570,9 @@ extern "C" int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, in
     int dev = 0, sms = 148;
     CAB_CUDA(cudaGetDevice(&dev));
     CAB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = static_cast<int>(std::min<long long>(tiles, sms));
+    // experiment hook: CAB_TC_MAX_CTAS caps the persistent grid (leaves SMs to kernels of a concurrent stream)
+    static const int max_ctas = getenv("CAB_TC_MAX_CTAS") ? atoi(getenv("CAB_TC_MAX_CTAS")) : 0;
+    const int grid = static_cast<int>(std::min<long long>(tiles, max_ctas > 0 ? std::min(max_ctas, sms) : sms));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define CAB_TC_LAUNCH(ACT_, RES_, F32_, PRO_)                                                                        \
     do {                                                                                                             \
