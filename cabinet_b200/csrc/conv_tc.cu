@@ -40,6 +40,7 @@ struct TcConvParams {
     int cin_blocks, num_k_blocks;
     int block_n, n_tiles, num_tiles, tmem_cols, stages, b_resident;
     int act, y_dtype, debug;
+    int b_per_image;          // weights differ per image (cabinet_conv_tc_imgw): B tiles are fetched with the tile's image index
     int c_bufs;               // store staging buffers per epilogue warpgroup: 2, or 1 when a tile is a single 64-column group
     int a_act, hw;            // A-operand prologue: x <- act(x * a_scale[image][channel]); hw = pixels per image
     const float* a_scale;     // [N][Cin] fp32 or nullptr
@@ -120,7 +121,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (p.b_resident) {
                 tc::mbar_expect_tx(&bres_bar, p.num_k_blocks * b_stage_bytes);
                 for (int kb = 0; kb < p.num_k_blocks; ++kb)
-                    tc::tma_load_2d(sB + kb * b_stage_bytes, &tmB, &bres_bar, kb * BLOCK_K, 0);
+                    tc::tma_load_3d(sB + kb * b_stage_bytes, &tmB, &bres_bar, kb * BLOCK_K, 0, 0);
             }
             const uint32_t tx_bytes = A_STAGE_BYTES + (p.b_resident ? 0 : b_stage_bytes);
             int s = 0;
@@ -146,7 +147,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                     tc::tma_load_4d(sA + s * A_STAGE_BYTES, map, &full_bar[s], cb * BLOCK_K, tcd.ow0 + dx, tcd.oh0 + dy,
                                     tcd.img);
-                    if (!p.b_resident) tc::tma_load_2d(sB + s * b_stage_bytes, &tmB, &full_bar[s], kb * BLOCK_K, tcd.n0);
+                    if (!p.b_resident)
+                        tc::tma_load_3d(sB + s * b_stage_bytes, &tmB, &full_bar[s], kb * BLOCK_K, tcd.n0, p.b_per_image ? tcd.img : 0);
                     }
                     if (++cb == p.cin_blocks) {
                         cb = 0;
@@ -445,10 +447,28 @@ extern "C" int cabinet_debug_flags(int flags) {
     return old;
 }
 
+static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int Cin, const float* a_scale, int a_act,
+                        const void* w_packed, long long w_image_stride, int Cout, int KH, int KW, int stride, int pad,
+                        const float* bias, const void* res, long long ldres, void* y, int y_dtype, long long ldy,
+                        int OH, int OW, int act, cabinet_stream_t stream);
+
 extern "C" int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, int W, int Cin, const float* a_scale,
                                   int a_act, const void* w_packed, int Cout, int KH, int KW, int stride, int pad,
                                   const float* bias, const void* res, long long ldres, void* y, int y_dtype,
-                                  long long ldy, int OH, int OW, int act, cabinet_stream_t stream);
+                                  long long ldy, int OH, int OW, int act, cabinet_stream_t stream) {
+    return conv_tc_impl(x, ldx, N, H, W, Cin, a_scale, a_act, w_packed, 0, Cout, KH, KW, stride, pad, bias, res, ldres, y,
+                        y_dtype, ldy, OH, OW, act, stream);
+}
+
+extern "C" int cabinet_conv_tc_imgw(const void* x, long long ldx, int N, int H, int W, int Cin,
+                                    const void* w_packed_per_image, long long w_image_stride, int Cout, int KH, int KW,
+                                    int stride, int pad, const float* bias, const void* res, long long ldres, void* y,
+                                    int y_dtype, long long ldy, int OH, int OW, int act, cabinet_stream_t stream) {
+    CAB_REQUIRE(w_image_stride > 0 && w_image_stride % 8 == 0, "conv_tc_imgw: weight image stride must be a positive multiple of 8");
+    CAB_REQUIRE(!(KH == 1 && KW == 1 && stride == 1 && pad == 0), "conv_tc_imgw: built for spatial (k > 1) convolutions");
+    return conv_tc_impl(x, ldx, N, H, W, Cin, nullptr, CABINET_ACT_NONE, w_packed_per_image, w_image_stride, Cout, KH, KW,
+                        stride, pad, bias, res, ldres, y, y_dtype, ldy, OH, OW, act, stream);
+}
 
 extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_packed,
                                int Cout, int KH, int KW, int stride, int pad, const float* bias, const void* res,
@@ -458,10 +478,10 @@ extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W
                               res, ldres, y, y_dtype, ldy, OH, OW, act, stream);
 }
 
-extern "C" int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, int W, int Cin, const float* a_scale,
-                                  int a_act, const void* w_packed, int Cout, int KH, int KW, int stride, int pad,
-                                  const float* bias, const void* res, long long ldres, void* y, int y_dtype,
-                                  long long ldy, int OH, int OW, int act, cabinet_stream_t stream) {
+static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int Cin, const float* a_scale, int a_act,
+                        const void* w_packed, long long w_image_stride, int Cout, int KH, int KW, int stride, int pad,
+                        const float* bias, const void* res, long long ldres, void* y, int y_dtype, long long ldy,
+                        int OH, int OW, int act, cabinet_stream_t stream) {
     CAB_REQUIRE(x && w_packed && bias && y, "conv_tc: null pointer");
     CAB_REQUIRE(!a_scale || (Cin % 8 == 0 && (reinterpret_cast<uintptr_t>(a_scale) & 15) == 0),
                 "conv_tc: the A-operand scale needs Cin %% 8 == 0 and a 16-byte aligned pointer");
@@ -491,7 +511,8 @@ extern "C" int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, in
     p.tmem_cols = 32;
     while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
     const int b_stage_bytes = p.block_n * BLOCK_K * 2;
-    p.b_resident = (p.n_tiles == 1 && p.num_k_blocks * b_stage_bytes <= B_RESIDENT_MAX) ? 1 : 0;
+    p.b_per_image = w_image_stride > 0 ? 1 : 0;
+    p.b_resident = (!p.b_per_image && p.n_tiles == 1 && p.num_k_blocks * b_stage_bytes <= B_RESIDENT_MAX) ? 1 : 0;
     p.c_bufs = (y_dtype == CABINET_BF16 && p.block_n > 64) ? 2 : 1;
     const int fixed = 2 * p.c_bufs * C_STAGE_BYTES + (p.b_resident ? p.num_k_blocks * b_stage_bytes : 0) + 1024;
     const int stage_bytes = A_STAGE_BYTES + (p.b_resident ? 0 : b_stage_bytes);
@@ -545,10 +566,11 @@ extern "C" int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, in
     }
     {
         const uint64_t ktot = static_cast<uint64_t>(taps) * p.cin_blocks * BLOCK_K;
-        const uint64_t dims[2] = {ktot, (uint64_t)n16};
-        const uint64_t strides[1] = {ktot * es};
-        const uint32_t box[2] = {BLOCK_K, (uint32_t)p.block_n};
-        int rc = cab_make_tmap_bf16(&tmB, w_packed, 2, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        CAB_REQUIRE(!p.b_per_image || static_cast<uint64_t>(w_image_stride) >= ktot * n16, "conv_tc_imgw: weight image stride too small");
+        const uint64_t dims[3] = {ktot, (uint64_t)n16, (uint64_t)(p.b_per_image ? N : 1)};
+        const uint64_t strides[2] = {ktot * es, (p.b_per_image ? static_cast<uint64_t>(w_image_stride) : ktot * n16) * es};
+        const uint32_t box[3] = {BLOCK_K, (uint32_t)p.block_n, 1};
+        int rc = cab_make_tmap_bf16(&tmB, w_packed, 3, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
     }
     if (y_dtype == CABINET_BF16) {

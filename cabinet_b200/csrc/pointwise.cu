@@ -189,15 +189,17 @@ cab_combine_kernel(const T* __restrict__ g, const T* __restrict__ x, const T* __
 }
 
 // Per-(image, channel) sum over pixels: grid (chunks, N); smem accumulation then one atomic per channel per block.
+// Deterministic two-level sum: every block reduces its pixel range in a fixed order and writes partial[n][b][c]; the
+// block that arrives last (per-image ticket) adds the partials in block order -> out[n][c].  No floating-point atomics:
+// the FFM gate (and the per-image head weights derived from it) is bit-reproducible from run to run.
 template <typename T>
 __global__ void __launch_bounds__(256)
 channel_sum_kernel(const T* __restrict__ x, long long ldx, long long HW, int C, float* __restrict__ out,
-                   long long pix_per_block) {
+                   long long pix_per_block, float* __restrict__ partial, unsigned int* __restrict__ tickets) {
     constexpr int V = Vec16<T>::N;
-    extern __shared__ float s_sum[];
-    for (int i = threadIdx.x; i < C; i += blockDim.x) s_sum[i] = 0.f;
-    __syncthreads();
-    const int n = blockIdx.y;
+    extern __shared__ float s_red[];  // [rows][C]
+    __shared__ bool s_last;
+    const int n = blockIdx.y, nb = gridDim.x;
     const int CG = C / V;
     const long long p0 = blockIdx.x * pix_per_block;
     const long long p1 = min(p0 + pix_per_block, HW);
@@ -224,31 +226,60 @@ channel_sum_kernel(const T* __restrict__ x, long long ldx, long long HW, int C, 
             }
         }
 #pragma unroll
-        for (int i = 0; i < V; ++i) atomicAdd(&s_sum[cg * V + i], acc[i]);
+        for (int i = 0; i < V; ++i) s_red[pr * C + cg * V + i] = acc[i];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&out[static_cast<long long>(n) * C + i], s_sum[i]);
+    float* mine = partial + (static_cast<long long>(n) * nb + blockIdx.x) * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float sum = 0.f;
+        for (int r = 0; r < rows; ++r) sum += s_red[r * C + c];
+        mine[c] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&tickets[n], 1u) == static_cast<unsigned>(nb - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float* all = partial + static_cast<long long>(n) * nb * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float sum = 0.f;
+        for (int b = 0; b < nb; ++b) sum += __ldcg(all + static_cast<long long>(b) * C + c);
+        out[static_cast<long long>(n) * C + c] = sum;
+    }
+    if (threadIdx.x == 0) tickets[n] = 0;  // ready for the next launch
 }
 
 }  // namespace
 
 extern "C" int cabinet_channel_sum(const void* x, long long ldx, int dtype, int N, long long HW, int C, float* out,
-                                   cabinet_stream_t stream) {
-    CAB_REQUIRE(x && out, "channel_sum: null pointer");
+                                   float* scratch, long long scratch_bytes, cabinet_stream_t stream) {
+    CAB_REQUIRE(x && out && scratch, "channel_sum: null pointer");
     const int V = dtype == CABINET_F32 ? 4 : 8;
-    CAB_REQUIRE(C > 0 && C % V == 0 && ldx % V == 0 && ldx >= C && C / V <= 256 && C * sizeof(float) <= 48 * 1024,
+    CAB_REQUIRE(C > 0 && C % V == 0 && ldx % V == 0 && ldx >= C && C / V <= 256 && N <= 65535,
                 "channel_sum: unsupported C=%d ldx=%lld", C, ldx);
     if (N == 0 || HW == 0) return CABINET_OK;
-    // >= 256 pixels per block: the per-block tail is C global atomics, keep them rare next to the streaming part
-    const long long pix_per_block = std::max<long long>(256, cab_ceil_div(HW, 148 * 8));
-    dim3 grid(static_cast<unsigned>(cab_ceil_div(HW, pix_per_block)), N);
+    // >= 256 pixels per block and at most 64 blocks per image (the last block of an image adds their partial sums)
+    const long long pix_per_block = std::max<long long>(256, cab_ceil_div(HW, 64));
+    const int nb = static_cast<int>(cab_ceil_div(HW, pix_per_block));
+    const int rows = 256 / (C / V);
+    const size_t smem = static_cast<size_t>(rows) * C * sizeof(float);
+    CAB_REQUIRE(smem <= 48 * 1024, "channel_sum: C too large");
+    // scratch layout: [N] tickets (uint32, must be zero before the first launch; the kernel leaves them zero), then the
+    // partial sums [N][nb][C] fp32 at the next 256-byte boundary
+    const size_t off = (static_cast<size_t>(N) * sizeof(unsigned int) + 255) & ~size_t(255);
+    const size_t need = off + static_cast<size_t>(N) * nb * C * sizeof(float);
+    CAB_REQUIRE(static_cast<size_t>(scratch_bytes) >= need, "channel_sum: scratch needs %zu bytes", need);
+    unsigned int* tickets = reinterpret_cast<unsigned int*>(scratch);
+    float* partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + off);
+    dim3 grid(nb, N);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == CABINET_BF16)
-        channel_sum_kernel<bf16><<<grid, 256, C * sizeof(float), s>>>(reinterpret_cast<const bf16*>(x), ldx, HW, C, out,
-                                                                      pix_per_block);
+        channel_sum_kernel<bf16><<<grid, 256, smem, s>>>(reinterpret_cast<const bf16*>(x), ldx, HW, C, out, pix_per_block,
+                                                         partial, tickets);
     else
-        channel_sum_kernel<float><<<grid, 256, C * sizeof(float), s>>>(reinterpret_cast<const float*>(x), ldx, HW, C,
-                                                                       out, pix_per_block);
+        channel_sum_kernel<float><<<grid, 256, smem, s>>>(reinterpret_cast<const float*>(x), ldx, HW, C, out,
+                                                          pix_per_block, partial, tickets);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }
@@ -301,6 +332,43 @@ extern "C" int cabinet_scale_act(void* x, long long ldx, int dtype, const float*
     else
         scale_act_kernel<float><<<grid, threads, 0, s>>>(reinterpret_cast<float*>(x), ldx, scale, static_cast<int>(HW), C, act,
                                                          plus_one, pix_per_block);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+namespace {
+// out[n][r][k] = bf16(w[r][k] * (scale[n][k % cin_pad] + plus)) for k % cin_pad < Cin, 0 otherwise (the K padding)
+__global__ void __launch_bounds__(256)
+scale_weights_kernel(const bf16* __restrict__ w, const float* __restrict__ scale, bf16* __restrict__ out, long long per_image,
+                     int cin_pad, int Cin, float plus) {
+    const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
+    if (i >= per_image) return;
+    const int n = blockIdx.y;
+    const int ci = static_cast<int>(i % cin_pad);  // 8 consecutive k share the tap (cin_pad % 8 == 0)
+    Vec16<bf16> v;
+    v.load(w + i);
+    float f[8];
+    v.unpack(f);
+    const float* sc = scale + static_cast<long long>(n) * Cin;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (ci + j < Cin) ? f[j] * (sc[ci + j] + plus) : 0.f;
+    v.pack(f);
+    v.store(out + static_cast<long long>(n) * per_image + i);
+}
+}  // namespace
+
+extern "C" int cabinet_scale_weights(const void* w_packed, const float* scale, void* out, int N, int rows, int taps,
+                                     int cin_pad, int Cin, int plus_one, cabinet_stream_t stream) {
+    CAB_REQUIRE(w_packed && scale && out && rows > 0 && taps > 0 && cin_pad > 0 && cin_pad % 8 == 0 && Cin > 0 && Cin <= cin_pad,
+                "scale_weights: bad arguments");
+    CAB_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && N <= 65535,
+                "scale_weights: alignment / batch");
+    if (N == 0) return CABINET_OK;
+    const long long per_image = static_cast<long long>(rows) * taps * cin_pad;
+    dim3 grid(static_cast<unsigned>(cab_ceil_div(per_image / 8, 256)), N);
+    scale_weights_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const bf16*>(w_packed), scale, reinterpret_cast<bf16*>(out), per_image, cin_pad, Cin,
+        plus_one ? 1.f : 0.f);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

@@ -132,6 +132,7 @@ class Engine:
         self.stages = {}
         self.trace, self.trace_filter = None, None
         self.fuse_mbconv = True     # expand + depthwise (+ project) in one kernel for blocks with <= 64 input channels
+        self.fold_ffm = True        # FFM gate folded into per-image head-conv weights (no rewrite of the fused feature map)
         self.fuse_se = False        # SE apply as A-operand prologue of the project GEMM (slower than scale_act today)
         self.use_cuda_graph = False
         self.sub_batch = 0          # > 0: run the schedule over chunks of this many images
@@ -511,13 +512,31 @@ class Engine:
         # ---- feature fusion (reference: cabinet.py:142-153)
         ff = self.conv(cat_ffm, self.ffm_blk)
         gap = gap_all[n_se].view(-1)[: N * 256].view(N, 256)
+        scratch = torch.zeros(64 + N * 64 * 256 + 64, dtype=torch.float32, device=dev)  # tickets (zero) + partial sums
+        self.launches += 1
         self._run("channel_sum", "ffm.gap", 0, 0, self.lib.cabinet_channel_sum, ff.ptr, ff.ld, ff.dt, N, H8 * W8, 256,
-                  gap.data_ptr(), self.stream)
+                  gap.data_ptr(), scratch.data_ptr(), scratch.numel() * 4, self.stream)
         att = self.gate(gap, H8 * W8, self.ffm_gate, "ffm.gate")
-        self.scale_act(ff, att, ACT_NONE, "ffm.gate", plus_one=True)
+        hcl = self.head_conv
+        if (self.fold_ffm and self.use_tc and not self.debug and hcl.tc is not None and ff.dt == BF16
+                and hcl.kh * hcl.kw > 1):
+            # feat * atten + feat is a per-(image, channel) scale of the head conv's INPUT: fold it into per-image
+            # copies of the head weights (19 MB) instead of rewriting the 134 MB feature map
+            wimg = torch.empty((N,) + tuple(hcl.tc.shape), dtype=torch.bfloat16, device=dev)
+            self._run("scale_weights", "ffm.gate", wimg.numel() * 2, 0, self.lib.cabinet_scale_weights, hcl.tc.data_ptr(),
+                      att.data_ptr(), wimg.data_ptr(), N, hcl.tc.shape[0], hcl.tc.shape[1], hcl.tc.shape[2], hcl.cin, 1,
+                      self.stream)
+            hc = self.new(N, H8, W8, hcl.cout)
+            M = N * H8 * W8
+            self._run("conv_tc", hcl.name, (M * (hcl.cin + hcl.cout) + wimg.numel()) * 2,
+                      2 * M * hcl.cout * hcl.cin * hcl.kh * hcl.kw, self.lib.cabinet_conv_tc_imgw, ff.ptr, ff.ld, N, H8, W8,
+                      ff.C, wimg.data_ptr(), hcl.tc[0].numel() * hcl.tc.shape[0], hcl.cout, hcl.kh, hcl.kw, hcl.stride,
+                      hcl.pad, hcl.b.data_ptr(), None, 0, hc.ptr, hc.dt, hc.ld, H8, W8, hcl.act, self.stream)
+        else:
+            self.scale_act(ff, att, ACT_NONE, "ffm.gate", plus_one=True)
+            hc = self.conv(ff, hcl)
 
         # ---- head (reference: cabinet.py:162-172)
-        hc = self.conv(ff, self.head_conv)
         final8 = self.conv(hc, self.head_out, out_dtype=torch.float32)
         if self.debug:  # stage activations for the parity tests (keeps the buffers alive)
             self.stages = dict(feat_sb=cat_ffm.slice(0, 128), mobile_feat=mf, low=low, high=high, feat_fuse=ff,

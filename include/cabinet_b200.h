@@ -119,6 +119,20 @@ int cabinet_mbconv_noexpand_fused(const void* x, long long ldx, const float* w_d
                                   const float* w_pw, const float* b_pw, void* y, long long ldy, int N, int H, int W,
                                   int C, int act, cabinet_stream_t stream);
 
+/* cabinet_conv_tc with one weight matrix PER IMAGE (w_packed_per_image + n * w_image_stride elements, each in the
+ * cabinet_conv_tc packing), spatial kernels only (KH * KW > 1).  Used to fold a per-(image, input-channel) scale of
+ * the INPUT into the weights instead of rewriting the input tensor: FeatureFusionModule's feat * atten + feat
+ * (src/models/cabinet.py:152-153) feeding CABiNetOutput.conv (cabinet.py:166): W'_n = W * (1 + atten_n). */
+int cabinet_conv_tc_imgw(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_packed_per_image,
+                         long long w_image_stride, int Cout, int KH, int KW, int stride, int pad, const float* bias,
+                         const void* res, long long ldres, void* y, int y_dtype, long long ldy, int OH, int OW, int act,
+                         cabinet_stream_t stream);
+
+/* out[n][r][t][c] = bf16(w[r][t][c] * (scale[n][c] + plus_one)): per-image copies of a cabinet_conv_tc weight pack
+ * ([rows][taps][cin_pad] bf16, cin_pad % 8 == 0; channels >= Cin stay 0); scale is fp32 [N][Cin]. */
+int cabinet_scale_weights(const void* w_packed, const float* scale, void* out, int N, int rows, int taps, int cin_pad,
+                          int Cin, int plus_one, cabinet_stream_t stream);
+
 /* Fused inverted-residual block with expansion (src/models/mobilenetv3.py:126-159), bf16 NHWC, Cin <= 64:
  *   h = act_expand(W_e * x + b_e)            1x1 expand + BN + act          (mobilenetv3.py:128-131)
  *   d = act_dw(dw_kxk(h) + b_dw)             depthwise + BN                 (mobilenetv3.py:132-141)
@@ -182,10 +196,12 @@ int cabinet_attention_tc(const void* q, long long ldq, const void* k, long long 
 int cabinet_cab_combine(const void* g, const void* x, const void* r, void* out, long long ldo, const float* gamma,
                         int dtype, long long n_pixels, int C, cabinet_stream_t stream);
 
-/* out[n][c] += sum over pixels of x[n][p][c]  (out fp32, zeroed by the caller): the global average pool of
- * src/models/cabinet.py:146 when the producing GEMM did not already emit the partial sums. */
-int cabinet_channel_sum(const void* x, long long ldx, int dtype, int N, long long HW, int C, float* out,
-                        cabinet_stream_t stream);
+/* out[n][c] = sum over pixels of x[n][p][c]  (out fp32, overwritten): the global average pool of
+ * src/models/cabinet.py:146.  Deterministic (no floating-point atomics): blocks write partial sums, the last block of
+ * an image adds them in block order.  scratch: device memory, >= 256 + 4 * N (rounded up to 256) + N * 64 * C * 4 bytes,
+ * whose first 4 * N bytes (the per-image tickets) must be zero before the first call; the kernel leaves them zero. */
+int cabinet_channel_sum(const void* x, long long ldx, int dtype, int N, long long HW, int C, float* out, float* scratch,
+                        long long scratch_bytes, cabinet_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Bilinear resize, align_corners=False, NHWC -> NHWC (src/models/cabinet.py:228-233). */

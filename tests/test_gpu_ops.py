@@ -183,7 +183,11 @@ def test_channel_sum(dtype):
     x = q(gen(3, 256, 20, 13, seed=1), dtype)
     xm = to_map(x, dtype)
     out = torch.zeros(3, 256, device="cuda")
-    check(lib.cabinet_channel_sum(xm.ptr, xm.ld, xm.dt, 3, 260, 256, out.data_ptr(), stream()), "sum")
+    scratch = torch.zeros(256 + 3 * 64 * 256, device="cuda")
+    for _ in range(2):  # the second launch checks that the tickets were left at zero
+        out.fill_(-1.0)
+        check(lib.cabinet_channel_sum(xm.ptr, xm.ld, xm.dt, 3, 260, 256, out.data_ptr(), scratch.data_ptr(),
+                                      scratch.numel() * 4, stream()), "sum")
     torch.cuda.synchronize()
     assert rel_l2(out.cpu(), x.sum(dim=(2, 3))) < 1e-5
 
@@ -563,3 +567,30 @@ def test_mbconv_fused_dw_out(cin, cexp, k, s, H, W, act):
     print(f"mbconv_fused(dw out) {cin}->{cexp} k{k} s{s} {H}x{W}: rel_l2 {err:.3e} gap {gerr:.3e}")
     assert err < 6e-3 and gerr < 1e-3
     assert float((ym.t.float()[..., cexp:] - 7.0).abs().max()) == 0
+
+
+def test_conv_tc_per_image_weights():
+    """conv(x * (1 + a_n), W) == conv(x, W * (1 + a_n)): cabinet_scale_weights + cabinet_conv_tc_imgw vs torch."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    N, cin, cout, k, H, W = 3, 40, 24, 3, 19, 21
+    x = q(gen(N, cin, H, W, seed=1), dtype)
+    w = q(gen(cout, cin, k, k, seed=2, scale=(cin * k * k) ** -0.5), dtype)
+    b = gen(cout, seed=3, scale=0.1)
+    a = torch.rand(N, cin, generator=torch.Generator().manual_seed(4))
+    ref = torch.relu(F.conv2d(x * (1 + a)[:, :, None, None], w, b, 1, 1))
+    n16, c64 = -(-cout // 16) * 16, -(-cin // 64) * 64
+    pk = torch.zeros(n16, k * k, c64)
+    pk[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin)
+    pk = pk.to("cuda", dtype).contiguous()
+    wimg = torch.full((N, n16, k * k, c64), 7.0, dtype=dtype, device="cuda")
+    ad, bd = a.cuda(), b.cuda()
+    check(lib.cabinet_scale_weights(pk.data_ptr(), ad.data_ptr(), wimg.data_ptr(), N, n16, k * k, c64, cin, 1, stream()), "sw")
+    torch.cuda.synchronize()
+    exp = pk.float()[None] * torch.cat([1 + ad, torch.zeros(N, c64 - cin, device="cuda")], 1)[:, None, None, :]
+    assert float((wimg.float() - exp.to(dtype).float()).abs().max()) == 0
+    xm, ym = to_map(x, dtype), to_map(torch.zeros_like(ref), dtype)
+    check(lib.cabinet_conv_tc_imgw(xm.ptr, xm.ld, N, H, W, cin, wimg.data_ptr(), n16 * k * k * c64, cout, k, k, 1, 1,
+                                   bd.data_ptr(), None, 0, ym.ptr, ym.dt, ym.ld, H, W, ACT_RELU, stream()), "imgw")
+    torch.cuda.synchronize()
+    assert rel_l2(from_map(ym), ref) < 8e-3
