@@ -43,7 +43,7 @@ SIGNATURES = {
     "cabinet_gate_mlp": ([_p, _f, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),
     "cabinet_gate_fc": ([_p, _f, _p, _p, _p, _i, _i, _i, _i, _p], _i),
     "cabinet_scale_act": ([_p, _ll, _i, _p, _i, _ll, _i, _i, _i, _p], _i),
-    "cabinet_psp_pool": ([_p, _ll, _i, _p, _i, _i, _i, _i, _p], _i),
+    "cabinet_psp_pool": ([_p, _ll, _i, _p, _i, _i, _i, _i, _p, _ll, _p], _i),
     "cabinet_psp_concat": ([_p, _ll, _p, _p, _ll, _i, _i, _i, _i, _i, _p], _i),
     "cabinet_softmax_rows": ([_p, _p, _i, _ll, _i, _p], _i),
     "cabinet_attention_tc": ([_p, _ll, _p, _ll, _p, _ll, _p, _p, _ll, _i, _i, _i, _f, _p], _i),

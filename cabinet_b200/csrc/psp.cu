@@ -10,7 +10,8 @@ __device__ __constant__ int kPspOffset[4] = {0, 1, 10, 46};  // bin offsets insi
 constexpr int kPspBins = 110;
 
 // Work table of the pooling kernel: large bins (the 1x1 and 3x3 levels) are split into parts of <= `chunk` pixels so
-// that every block is short; parts of one bin are combined with atomicAdd (the output is zeroed first).
+// that every block is short; the parts of one bin go to a scratch area and the part that arrives last (per-bin ticket)
+// adds them in part order -- deterministic, no floating-point atomics.
 struct PspWork {
     unsigned short bin[256];
     unsigned char part[256], parts[256];
@@ -34,7 +35,7 @@ __host__ __device__ inline void psp_bin_rect(int bin, int H, int W, int& h0, int
 template <typename T>
 __global__ void __launch_bounds__(128)
 psp_pool_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ pooled, int H, int W, int C,
-                const __grid_constant__ PspWork wk) {
+                const __grid_constant__ PspWork wk, float* __restrict__ partial, unsigned int* __restrict__ tickets) {
     constexpr int VPT = Vec16<T>::N;  // channels per thread: 8 (bf16) or 4 (fp32)
     extern __shared__ float red[];    // [blockDim.x][VPT]
     const int bin = wk.bin[blockIdx.x], part = wk.part[blockIdx.x], parts = wk.parts[blockIdx.x];
@@ -84,17 +85,40 @@ psp_pool_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ pool
         }
         __syncthreads();
     }
-    if (pl == 0) {
-        const float inv = 1.f / static_cast<float>(npix);
-        float* out = pooled + (static_cast<long long>(n) * kPspBins + bin) * C + cq * VPT;
-        if (parts == 1) {
+    const float inv = 1.f / static_cast<float>(npix);
+    float* out = pooled + (static_cast<long long>(n) * kPspBins + bin) * C + cq * VPT;
+    if (parts == 1) {
+        if (pl == 0) {
 #pragma unroll
             for (int j = 0; j < VPT; ++j) out[j] = acc[j] * inv;
-        } else {
-#pragma unroll
-            for (int j = 0; j < VPT; ++j) atomicAdd(out + j, acc[j] * inv);
         }
+        return;
     }
+    // split bin: park this part, the last part to arrive adds all of them in part order
+    __shared__ bool s_last;
+    float* parked = partial + (static_cast<long long>(n) * wk.n + blockIdx.x) * C + cq * VPT;
+    if (pl == 0) {
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) parked[j] = acc[j];
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&tickets[n * kPspBins + bin], 1u) == static_cast<unsigned>(parts - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (pl == 0) {
+        const float* first = partial + (static_cast<long long>(n) * wk.n + (blockIdx.x - part)) * C + cq * VPT;
+        float sum[VPT];
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) sum[j] = 0.f;
+        for (int q = 0; q < parts; ++q)
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) sum[j] += __ldcg(first + static_cast<long long>(q) * C + j);
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) out[j] = sum[j] * inv;
+    }
+    if (threadIdx.x == 0) tickets[n * kPspBins + bin] = 0;  // ready for the next launch
 }
 
 // grid (ceil(W*CQ/256), H, N); thread per (column, channel vector): out[pix][0:C] = x, out[pix][C*(1+si) + c] =
@@ -146,7 +170,7 @@ psp_concat_kernel(const T* __restrict__ x, long long ldx, const float* __restric
 }  // namespace
 
 extern "C" int cabinet_psp_pool(const void* x, long long ldx, int dtype, float* pooled, int N, int H, int W, int C,
-                                cabinet_stream_t stream) {
+                                float* scratch, long long scratch_bytes, cabinet_stream_t stream) {
     const int vpt = dtype == CABINET_BF16 ? 8 : 4;
     CAB_REQUIRE(x && pooled && H > 0 && W > 0 && C > 0 && ldx >= C && C % vpt == 0 && C <= 1024 && ldx % vpt == 0 &&
                     (reinterpret_cast<uintptr_t>(x) & 15) == 0,
@@ -174,15 +198,20 @@ extern "C" int cabinet_psp_pool(const void* x, long long ldx, int dtype, float* 
         if (fits) break;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    CAB_CUDA(cudaMemsetAsync(pooled, 0, static_cast<size_t>(N) * kPspBins * C * sizeof(float), s));
+    // scratch: [N][110] tickets (uint32; zero before the first launch, left at zero) then [N][work items][C] partial sums
+    const size_t off = (static_cast<size_t>(N) * kPspBins * sizeof(unsigned int) + 255) & ~size_t(255);
+    const size_t need = off + static_cast<size_t>(N) * wk.n * C * sizeof(float);
+    CAB_REQUIRE(scratch && static_cast<size_t>(scratch_bytes) >= need, "psp_pool: scratch needs %zu bytes", need);
+    unsigned int* tickets = reinterpret_cast<unsigned int*>(scratch);
+    float* partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + off);
     dim3 grid(wk.n, N);
     const int cq = C / vpt;
     const int threads = std::max(cq, 128 / cq * cq);  // a multiple of the channel-vector count close to 128
     const size_t smem = static_cast<size_t>(threads) * vpt * sizeof(float);
     if (dtype == CABINET_BF16)
-        psp_pool_kernel<bf16><<<grid, threads, smem, s>>>(reinterpret_cast<const bf16*>(x), ldx, pooled, H, W, C, wk);
+        psp_pool_kernel<bf16><<<grid, threads, smem, s>>>(reinterpret_cast<const bf16*>(x), ldx, pooled, H, W, C, wk, partial, tickets);
     else
-        psp_pool_kernel<float><<<grid, threads, smem, s>>>(reinterpret_cast<const float*>(x), ldx, pooled, H, W, C, wk);
+        psp_pool_kernel<float><<<grid, threads, smem, s>>>(reinterpret_cast<const float*>(x), ldx, pooled, H, W, C, wk, partial, tickets);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

@@ -358,8 +358,11 @@ class Engine:
         """PSP encoder: pools -> 5C concat -> 1x1 project (reference: cab.py:65-76)."""
         pooled = torch.empty((x.N, 110, x.C), dtype=torch.float32, device=self.dev)
         es = x.t.element_size()
+        scratch = torch.empty(128 + x.N * (110 + 256 * x.C), dtype=torch.float32, device=self.dev)
+        scratch[: 64 + x.N * 110].zero_()  # per-bin tickets of the split bins (the partial sums behind them need no init)
+        self.launches += 1
         self._run("psp_pool", L.name, x.N * x.H * x.W * x.C * es, 0, self.lib.cabinet_psp_pool, x.ptr, x.ld, x.dt,
-                  pooled.data_ptr(), x.N, x.H, x.W, x.C, self.stream)
+                  pooled.data_ptr(), x.N, x.H, x.W, x.C, scratch.data_ptr(), scratch.numel() * 4, self.stream)
         cat = self.new(x.N, x.H, x.W, 5 * x.C)
         self._run("psp_concat", L.name, 0, 0, self.lib.cabinet_psp_concat, x.ptr, x.ld, pooled.data_ptr(), cat.ptr,
                   cat.ld, x.dt, x.N, x.H, x.W, x.C, self.stream)
@@ -512,7 +515,8 @@ class Engine:
         # ---- feature fusion (reference: cabinet.py:142-153)
         ff = self.conv(cat_ffm, self.ffm_blk)
         gap = gap_all[n_se].view(-1)[: N * 256].view(N, 256)
-        scratch = torch.zeros(64 + N * 64 * 256 + 64, dtype=torch.float32, device=dev)  # tickets (zero) + partial sums
+        scratch = torch.empty(64 + N * 64 * 256 + 64, dtype=torch.float32, device=dev)  # tickets + partial sums
+        scratch[: 64 + N].zero_()
         self.launches += 1
         self._run("channel_sum", "ffm.gap", 0, 0, self.lib.cabinet_channel_sum, ff.ptr, ff.ld, ff.dt, N, H8 * W8, 256,
                   gap.data_ptr(), scratch.data_ptr(), scratch.numel() * 4, self.stream)

@@ -173,9 +173,12 @@ int cabinet_scale_act(void* x, long long ldx, int dtype, const float* scale, int
  * PSP (src/models/cab.py:46-76).  psp_pool: adaptive average pools of sizes (1,3,6,8) -> pooled
  * [N][110][C] fp32 (bins floor(i*H/s) .. ceil((i+1)*H/s)).  psp_concat: writes the 5C-channel
  * tensor [x, up(pool1), up(pool3), up(pool6), up(pool8)] (bilinear, align_corners=False) that the
- * 1x1 `project` conv consumes. */
+ * 1x1 `project` conv consumes.  psp_pool is deterministic: bins larger than 128 pixels are split over several blocks
+ * whose partial sums are parked in `scratch` and added in a fixed order by the last block to arrive.  scratch: device
+ * memory, >= 256 + 440 * N (rounded up to 256) + N * 256 * C * 4 bytes; its first 440 * N bytes (per-bin tickets)
+ * must be zero before the first call, the kernel leaves them zero. */
 int cabinet_psp_pool(const void* x, long long ldx, int dtype, float* pooled, int N, int H, int W, int C,
-                     cabinet_stream_t stream);
+                     float* scratch, long long scratch_bytes, cabinet_stream_t stream);
 int cabinet_psp_concat(const void* x, long long ldx, const float* pooled, void* out, long long ldo, int dtype,
                        int N, int H, int W, int C, cabinet_stream_t stream);
 

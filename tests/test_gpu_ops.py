@@ -153,7 +153,11 @@ def test_psp_pool_and_concat(dtype, H, W):
     xm = to_map(x, dtype)
     pooled = torch.empty(N, 110, C, device="cuda")
     cat = to_map(torch.zeros(N, 5 * C, H, W), dtype)
-    check(lib.cabinet_psp_pool(xm.ptr, xm.ld, xm.dt, pooled.data_ptr(), N, H, W, C, stream()), "pool")
+    scratch = torch.zeros(128 + N * (110 + 256 * C), device="cuda")
+    for _ in range(2):  # the second launch checks that the tickets were left at zero
+        pooled.fill_(-1.0)
+        check(lib.cabinet_psp_pool(xm.ptr, xm.ld, xm.dt, pooled.data_ptr(), N, H, W, C, scratch.data_ptr(),
+                                   scratch.numel() * 4, stream()), "pool")
     check(lib.cabinet_psp_concat(xm.ptr, xm.ld, pooled.data_ptr(), cat.ptr, cat.ld, xm.dt, N, H, W, C, stream()), "cat")
     torch.cuda.synchronize()
     assert rel_l2(pooled.cpu(), ref_pooled) < 1e-5
