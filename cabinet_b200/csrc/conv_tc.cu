@@ -147,8 +147,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                     tc::tma_load_4d(sA + s * A_STAGE_BYTES, map, &full_bar[s], cb * BLOCK_K, tcd.ow0 + dx, tcd.oh0 + dy,
                                     tcd.img);
-                    if (!p.b_resident)
-                        tc::tma_load_3d(sB + s * b_stage_bytes, &tmB, &full_bar[s], kb * BLOCK_K, tcd.n0, p.b_per_image ? tcd.img : 0);
+                    if (!p.b_resident) {
+                        // per-image weights: spatial tiles carry the image index, flat (1x1) tiles cover 128 consecutive
+                        // pixels of ONE image (the host checks H * W % 128 == 0)
+                        const int bimg = !p.b_per_image ? 0 : (p.tiles_h == 1 && p.OH == 1 ? tcd.ow0 / p.hw : tcd.img);
+                        tc::tma_load_3d(sB + s * b_stage_bytes, &tmB, &full_bar[s], kb * BLOCK_K, tcd.n0, bimg);
+                    }
                     }
                     if (++cb == p.cin_blocks) {
                         cb = 0;
@@ -465,7 +469,8 @@ extern "C" int cabinet_conv_tc_imgw(const void* x, long long ldx, int N, int H, 
                                     int stride, int pad, const float* bias, const void* res, long long ldres, void* y,
                                     int y_dtype, long long ldy, int OH, int OW, int act, cabinet_stream_t stream) {
     CAB_REQUIRE(w_image_stride > 0 && w_image_stride % 8 == 0, "conv_tc_imgw: weight image stride must be a positive multiple of 8");
-    CAB_REQUIRE(!(KH == 1 && KW == 1 && stride == 1 && pad == 0), "conv_tc_imgw: built for spatial (k > 1) convolutions");
+    CAB_REQUIRE(!(KH == 1 && KW == 1 && stride == 1 && pad == 0) || (static_cast<long long>(H) * W) % 128 == 0,
+                "conv_tc_imgw: a 1x1 convolution needs H * W %% 128 == 0 (a 128-pixel tile must not straddle two images)");
     return conv_tc_impl(x, ldx, N, H, W, Cin, nullptr, CABINET_ACT_NONE, w_packed_per_image, w_image_stride, Cout, KH, KW,
                         stride, pad, bias, res, ldres, y, y_dtype, ldy, OH, OW, act, stream);
 }

@@ -166,8 +166,17 @@ __device__ __forceinline__ void dw_seg(const MbParams& p, uint32_t sE, uint32_t 
     // ReLU rides on the bf16 convert; other activations take the generic path (the SE pooling sums exist only in the
     // activation-free depthwise-output mode)
     const bool relu_pack = p.act_dw == CABINET_ACT_RELU;
-    if (!relu_pack) cab_act_vec<2 * COLS>(&acc[0].x, p.act_dw);
     float g0 = 0.f, g1 = 0.f;
+    if (want_gap && row_valid) {  // SE pools the BN output, i.e. the values BEFORE the activation (mobilenetv3.py:137-143)
+#pragma unroll
+        for (int r = 0; r < COLS; ++r) {
+            if (ow_base + col0 + r < p.OW) {
+                g0 += acc[r].x;
+                g1 += acc[r].y;
+            }
+        }
+    }
+    if (!relu_pack) cab_act_vec<2 * COLS>(&acc[0].x, p.act_dw);
     const int prow = row * TW + col0;
     const uint32_t a2row = sA2 + prow * 128 + ((cl & 3) << 2);
     const uint32_t cq = static_cast<uint32_t>(cl >> 2) << 4;
@@ -178,10 +187,6 @@ __device__ __forceinline__ void dw_seg(const MbParams& p, uint32_t sE, uint32_t 
         const uint32_t hv = relu_pack ? pack_act<CABINET_ACT_RELU>(acc[r].x, acc[r].y)
                                       : pack_act<CABINET_ACT_NONE>(acc[r].x, acc[r].y);
         sts32(a2row + r * 128 + (cq ^ (static_cast<uint32_t>(sw) << 4)), hv);
-        if (want_gap && row_valid && ow_base + col0 + r < p.OW) {
-            g0 += acc[r].x;
-            g1 += acc[r].y;
-        }
     }
     if (want_gap) {
         reds_f32(s_gap + (c0 << 2), g0);

@@ -132,6 +132,7 @@ class Engine:
         self.stages = {}
         self.trace, self.trace_filter = None, None
         self.fuse_mbconv = True     # expand + depthwise (+ project) in one kernel for blocks with <= 64 input channels
+        self.fold_se_relu = True    # ReLU SE blocks: gate folded into per-image project weights (relu(s*d) = s*relu(d))
         self.fold_ffm = True        # FFM gate folded into per-image head-conv weights (no rewrite of the fused feature map)
         self.fuse_se = False        # SE apply as A-operand prologue of the project GEMM (slower than scale_act today)
         self.use_cuda_graph = False
@@ -140,6 +141,7 @@ class Engine:
         self._graph_seen = {}
         self.dual_stream = False    # experimental: two half-batches on two streams
         self._side = None
+        self._scratch = []
         with torch.no_grad():
             self._pack(model)
 
@@ -313,7 +315,7 @@ class Engine:
                       self.stream)
         return out
 
-    def mbconv_fused(self, x: Map, e: dict, gap: Optional[torch.Tensor]) -> Map:
+    def mbconv_fused(self, x: Map, e: dict, gap: Optional[torch.Tensor], act_dw: Optional[int] = None) -> Map:
         """Inverted-residual block with the expanded activation kept on chip (reference: mobilenetv3.py:126-159).
         ``gap`` given (SE blocks): returns the pre-SE depthwise output and accumulates its pooling sums; else the
         block output (project + identity included)."""
@@ -330,7 +332,7 @@ class Engine:
             flops += 2 * x.N * OH * OW * dw.c * pw2.cout
         self._run("mbconv_fused", dw.name.replace(".dw", "") + ("" if project else ".expand+dw"), nbytes, flops,
                   self.lib.cabinet_mbconv_fused, x.ptr, x.ld, x.N, x.H, x.W, x.C, e["w1b"].data_ptr(), e["aux"].data_ptr(),
-                  dw.c, pw1.act, dw.k, dw.stride, dw.act,
+                  dw.c, pw1.act, dw.k, dw.stride, dw.act if act_dw is None else act_dw,
                   pw2.tc.data_ptr() if project else None, pw2.b.data_ptr() if project else None,
                   pw2.cout if project else 0, 1 if project and s["identity"] else 0, out.ptr, out.ld, OH, OW,
                   gap.data_ptr() if gap is not None else None, self.stream)
@@ -358,9 +360,12 @@ class Engine:
         """PSP encoder: pools -> 5C concat -> 1x1 project (reference: cab.py:65-76)."""
         pooled = torch.empty((x.N, 110, x.C), dtype=torch.float32, device=self.dev)
         es = x.t.element_size()
-        scratch = torch.empty(128 + x.N * (110 + 256 * x.C), dtype=torch.float32, device=self.dev)
-        scratch[: 64 + x.N * 110].zero_()  # per-bin tickets of the split bins (the partial sums behind them need no init)
-        self.launches += 1
+        need = 128 + x.N * (110 + 256 * x.C)
+        if self._scratch and self._scratch[-1].numel() >= need:
+            scratch = self._scratch.pop()  # zeroed with the per-forward memset (tickets must start at zero)
+        else:
+            scratch = torch.zeros(need, dtype=torch.float32, device=self.dev)
+            self.launches += 1
         self._run("psp_pool", L.name, x.N * x.H * x.W * x.C * es, 0, self.lib.cabinet_psp_pool, x.ptr, x.ld, x.dt,
                   pooled.data_ptr(), x.N, x.H, x.W, x.C, scratch.data_ptr(), scratch.numel() * 4, self.stream)
         cat = self.new(x.N, x.H, x.W, 5 * x.C)
@@ -412,7 +417,14 @@ class Engine:
         self.launches = 0
         dev, C = self.dev, self.n_classes
         n_se = sum(1 for b in self.blocks if "se" in b)
-        gap_all = torch.zeros((n_se + 1, N, 1024), dtype=torch.float32, device=dev)  # one memset per forward
+        # ONE memset per forward: the SE / FFM pooling sums, and the scratch areas (tickets + parked partial sums) of the
+        # deterministic reductions (cabinet_channel_sum, 2 x cabinet_psp_pool)
+        kc = self.key_ch
+        n_gap, n_psp, n_ffm = (n_se + 1) * N * 1024, 128 + N * (110 + 256 * kc), 128 + N * 64 * 256
+        zeros_all = torch.zeros(n_gap + 2 * n_psp + n_ffm, dtype=torch.float32, device=dev)
+        gap_all = zeros_all[:n_gap].view(n_se + 1, N, 1024)
+        self._scratch = [zeros_all[n_gap + i * n_psp: n_gap + (i + 1) * n_psp] for i in range(2)]
+        ffm_scratch = zeros_all[n_gap + 2 * n_psp:]
         self.launches += 1
 
         # ---- spatial branch (reference: cabinet.py:108-129) -> channels [0:128] of the FFM concat buffer
@@ -458,8 +470,14 @@ class Engine:
                 gap = None
                 if "se" in e:
                     gap = gap_all[gi].view(-1)[: N * s["exp"]].view(N, s["exp"])
+                # ReLU SE blocks: relu(s * d) = s * relu(d) (s = hard-sigmoid >= 0), so the kernel applies the ReLU and the
+                # gate is folded into per-image project weights -- no scale_act pass over the expanded tensor
+                pw2l = e["pw2"]
+                fold_se = (gap is not None and self.fold_se_relu and e["act"] == ACT_RELU and not self.debug
+                           and pw2l.tc is not None and pw2l.kh == 1 and (f.H // s["s"]) * (f.W // s["s"]) % 128 == 0
+                           and f.H % s["s"] == 0 and f.W % s["s"] == 0)
                 try:
-                    d = self.mbconv_fused(f, e, gap)
+                    d = self.mbconv_fused(f, e, gap, ACT_RELU if fold_se else None)
                 except ValueError as err:  # block shape outside the kernel's shared-memory / TMEM budget
                     if "budget" not in str(err):
                         raise
@@ -474,6 +492,22 @@ class Engine:
                 if not fuse:
                     d = self.dwconv(h, e["dw"], gap)
                 scale = self.gate(gap, d.H * d.W, e["se"], e["dw"].name)
+                if fuse and fold_se:
+                    pw2 = e["pw2"]
+                    wimg = torch.empty((N,) + tuple(pw2.tc.shape), dtype=torch.bfloat16, device=dev)
+                    self._run("scale_weights", e["dw"].name, wimg.numel() * 2, 0, self.lib.cabinet_scale_weights,
+                              pw2.tc.data_ptr(), scale.data_ptr(), wimg.data_ptr(), N, pw2.tc.shape[0], 1, pw2.tc.shape[2],
+                              pw2.cin, 0, self.stream)
+                    o = self.new(N, d.H, d.W, pw2.cout)
+                    M = N * d.H * d.W
+                    res = f if s["identity"] else None
+                    self._run("conv_tc", pw2.name, M * (pw2.cin + pw2.cout * (2 if res is not None else 1)) * 2 + wimg.numel() * 2,
+                              2 * M * pw2.cout * pw2.cin, self.lib.cabinet_conv_tc_imgw, d.ptr, d.ld, N, d.H, d.W, d.C,
+                              wimg.data_ptr(), pw2.tc[0].numel() * pw2.tc.shape[0], pw2.cout, 1, 1, 1, 0, pw2.b.data_ptr(),
+                              res.ptr if res is not None else None, res.ld if res is not None else 0, o.ptr, o.dt, o.ld,
+                              d.H, d.W, ACT_NONE, self.stream)
+                    f = o
+                    continue
                 # expand form: SE then activation; no-expand form: activation (already applied) then SE (F10)
                 se_act = e["act"] if s["expand"] else ACT_NONE
                 pw2 = e["pw2"]
@@ -515,9 +549,7 @@ class Engine:
         # ---- feature fusion (reference: cabinet.py:142-153)
         ff = self.conv(cat_ffm, self.ffm_blk)
         gap = gap_all[n_se].view(-1)[: N * 256].view(N, 256)
-        scratch = torch.empty(64 + N * 64 * 256 + 64, dtype=torch.float32, device=dev)  # tickets + partial sums
-        scratch[: 64 + N].zero_()
-        self.launches += 1
+        scratch = ffm_scratch
         self._run("channel_sum", "ffm.gap", 0, 0, self.lib.cabinet_channel_sum, ff.ptr, ff.ld, ff.dt, N, H8 * W8, 256,
                   gap.data_ptr(), scratch.data_ptr(), scratch.numel() * 4, self.stream)
         att = self.gate(gap, H8 * W8, self.ffm_gate, "ffm.gate")

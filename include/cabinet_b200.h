@@ -120,9 +120,11 @@ int cabinet_mbconv_noexpand_fused(const void* x, long long ldx, const float* w_d
                                   int C, int act, cabinet_stream_t stream);
 
 /* cabinet_conv_tc with one weight matrix PER IMAGE (w_packed_per_image + n * w_image_stride elements, each in the
- * cabinet_conv_tc packing), spatial kernels only (KH * KW > 1).  Used to fold a per-(image, input-channel) scale of
+ * cabinet_conv_tc packing); 1x1 convolutions need H * W % 128 == 0.  Used to fold a per-(image, input-channel) scale of
  * the INPUT into the weights instead of rewriting the input tensor: FeatureFusionModule's feat * atten + feat
- * (src/models/cabinet.py:152-153) feeding CABiNetOutput.conv (cabinet.py:166): W'_n = W * (1 + atten_n). */
+ * (src/models/cabinet.py:152-153) feeding CABiNetOutput.conv (cabinet.py:166): W'_n = W * (1 + atten_n); and the
+ * squeeze-excite scale of ReLU blocks, relu(s * d) = s * relu(d) for s >= 0 (src/models/mobilenetv3.py:83,143):
+ * W'_n = W_project * s_n. */
 int cabinet_conv_tc_imgw(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_packed_per_image,
                          long long w_image_stride, int Cout, int KH, int KW, int stride, int pad, const float* bias,
                          const void* res, long long ldres, void* y, int y_dtype, long long ldy, int OH, int OW, int act,
@@ -137,8 +139,11 @@ int cabinet_scale_weights(const void* w_packed, const float* scale, void* out, i
  *   h = act_expand(W_e * x + b_e)            1x1 expand + BN + act          (mobilenetv3.py:128-131)
  *   d = act_dw(dw_kxk(h) + b_dw)             depthwise + BN                 (mobilenetv3.py:132-141)
  *   w_project != NULL:  y = W_p * d + b_p (+ x when residual)                (mobilenetv3.py:145-159), y has Cout channels
- *   w_project == NULL:  y = d (Cexp channels) and gap_sum[n][c] += sum over pixels of d (blocks with squeeze-excite:
- *                       the SE gate needs the global mean before the project conv; act_dw is NONE there).
+ *   w_project == NULL:  y = d (Cexp channels) and gap_sum[n][c] += sum over pixels of (dw_kxk(h) + b_dw), i.e. of the
+ *                       values BEFORE act_dw (blocks with squeeze-excite: the gate needs the global mean of the BN
+ *                       output before the project conv).  act_dw = NONE leaves the activation to the SE apply;
+ *                       act_dw = RELU is for the identity relu(s * d) = s * relu(d), s >= 0, with the scale folded
+ *                       into per-image project weights (cabinet_scale_weights + cabinet_conv_tc_imgw).
  * The expanded activation h never reaches HBM (TMEM -> shared memory -> depthwise).
  * w_expand: bf16 [ceil16(Cexp)][64], row = expanded channel: columns 0..Cin-1 = W_e (BN folded), columns Cin, Cin+1 =
  *           b_e split into bf16 (hi, lo) -- the kernel feeds 1.0 into those two K slots, the bias is part of the GEMM --

@@ -538,13 +538,14 @@ def test_mbconv_fused_project(cin, cexp, cout, k, s, H, W, act, res):
     assert float((full[..., ym.off + cout:] - 7.0).abs().max()) == 0
 
 
+@pytest.mark.parametrize("act_dw", [ACT_NONE, ACT_RELU])
 @pytest.mark.parametrize("cin,cexp,k,s,H,W,act", [
     (24, 72, 5, 2, 40, 56, ACT_RELU),       # Large f4
     (40, 120, 5, 1, 24, 40, ACT_RELU),      # Large f5 / f6
     (40, 240, 3, 1, 11, 13, ACT_HSWISH),
     (16, 72, 3, 2, 17, 9, ACT_RELU),
 ])
-def test_mbconv_fused_dw_out(cin, cexp, k, s, H, W, act):
+def test_mbconv_fused_dw_out(cin, cexp, k, s, H, W, act, act_dw):
     """expand -> depthwise with the pre-SE output and its pooling sums (blocks with squeeze-excite)."""
     lib = _lib.load()
     dtype = torch.bfloat16
@@ -554,7 +555,8 @@ def test_mbconv_fused_dw_out(cin, cexp, k, s, H, W, act):
     wd, bd = gen(cexp, 1, k, k, seed=4, scale=1.0 / k), gen(cexp, seed=5, scale=0.1)
     pad = (k - 1) // 2
     h = q(act_ref(F.conv2d(x, we, be), act), dtype)
-    ref = F.conv2d(h, wd, bd, s, pad, 1, cexp)
+    pre = F.conv2d(h, wd, bd, s, pad, 1, cexp)   # the pooling sums are taken BEFORE act_dw (SE pools the BN output)
+    ref = act_ref(pre, act_dw)
     OH, OW = ref.shape[2:]
     xm = to_map(x, dtype)
     ym = to_map(torch.zeros_like(ref), dtype, ld=cexp + 8, off=0)
@@ -563,11 +565,11 @@ def test_mbconv_fused_dw_out(cin, cexp, k, s, H, W, act):
     aux = _pack_aux(wd, be, bd)
     pe = _pack_expand(we, be)
     check(lib.cabinet_mbconv_fused(xm.ptr, xm.ld, N, H, W, cin, pe.data_ptr(), aux.data_ptr(), cexp, act, k, s,
-                                   ACT_NONE, None, None, 0, 0, ym.ptr, ym.ld, OH, OW, gap.data_ptr(), stream()),
+                                   act_dw, None, None, 0, 0, ym.ptr, ym.ld, OH, OW, gap.data_ptr(), stream()),
           "mbconv_fused")
     torch.cuda.synchronize()
     err = rel_l2(from_map(ym), ref)
-    gerr = rel_l2(gap.cpu(), ref.sum(dim=(2, 3)))
+    gerr = rel_l2(gap.cpu(), pre.sum(dim=(2, 3)))
     print(f"mbconv_fused(dw out) {cin}->{cexp} k{k} s{s} {H}x{W}: rel_l2 {err:.3e} gap {gerr:.3e}")
     assert err < 6e-3 and gerr < 1e-3
     assert float((ym.t.float()[..., cexp:] - 7.0).abs().max()) == 0
