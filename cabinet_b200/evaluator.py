@@ -135,6 +135,13 @@ class MscEvalV0:
         cur = torch.cuda.current_stream(dev)
         st = self.__dict__.setdefault("_pipe", {"stream": torch.cuda.Stream(dev), "bufs": [None, None], "x32": None})
         copy_stream, bufs, x32 = st["stream"], st["bufs"], st["x32"]  # device buffers persist across evaluate() calls
+        # the fused forward + confusion-matrix call is replayed as a CUDA graph keyed by its buffer addresses: accumulate
+        # into a persistent matrix (the caller's `hist` is a fresh allocation per evaluate(), which would force a
+        # re-capture whenever the allocator hands out a different block -- it does under NCCL) and add it at the end
+        if st.get("hist") is None or st["hist"].shape != hist.shape:
+            st["hist"] = torch.zeros_like(hist)
+        user_hist, hist = hist, st["hist"]
+        hist.zero_()
         ready, consumed = [torch.cuda.Event(), torch.cuda.Event()], [None, None]
         copy_stream.wait_stream(cur)
         n_batches = 0
@@ -175,6 +182,7 @@ class MscEvalV0:
             consumed[b] = torch.cuda.Event()
             consumed[b].record(cur)
             n_batches += 1
+        user_hist.add_(hist)
         return n_batches
 
     @torch.no_grad()
