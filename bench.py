@@ -50,7 +50,10 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock / throttle reasons of this rank's GPU sampled WHILE the timed region runs.
+
+    NVML polled every ~2 ms from a thread (the timed region is only tens of milliseconds long: `nvidia-smi -lms`
+    cannot resolve it and its start-up alone is longer); falls back to an nvidia-smi loop if pynvml is missing."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -58,8 +61,45 @@ class ClockSampler:
 
     def __init__(self, gpu_id: str):
         self.gpu_id, self.proc, self.lines = gpu_id, None, []
+        self.samples, self.max_mhz, self.reasons, self.stop, self.nv = [], None, set(), False, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(gpu_id)
+            except (TypeError, AttributeError):
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(gpu_id.encode())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        names = {getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap"}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+            nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                if get_reasons is not None:
+                    mask = int(get_reasons(self.h))
+                    for bit, name in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpu_id, f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
@@ -71,12 +111,19 @@ class ClockSampler:
         return self
 
     def __exit__(self, *a):
+        if self.nv is not None:
+            self.stop = True
+            self.t.join(timeout=2)
+            return
         if self.proc is not None:
             time.sleep(0.25)
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
+        if self.nv is not None and self.samples:
+            return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml, 2 ms period"}
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
@@ -93,7 +140,8 @@ class ClockSampler:
                     reasons.add(n)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 200"}
 
 
 def cpu_forward_rate(mode, n_classes, size, batch, iters, warmup):
