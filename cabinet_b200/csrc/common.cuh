@@ -55,12 +55,12 @@ template <int N> __device__ __forceinline__ void cab_act_vec(float* v, int act) 
     if (act == CABINET_ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = fmaxf(v[i], 0.f);
-    } else if (act == CABINET_ACT_HSWISH) {
+    } else if (act == CABINET_ACT_HSWISH) {  // relu6(x + 3) / 6 == saturate(x / 6 + 0.5): one FFMA.SAT + one FMUL
 #pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = v[i] * (fminf(fmaxf(v[i] + 3.f, 0.f), 6.f) * (1.f / 6.f));
+        for (int i = 0; i < N; ++i) v[i] = v[i] * __saturatef(fmaf(v[i], 1.f / 6.f, 0.5f));
     } else if (act == CABINET_ACT_HSIGMOID) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = fminf(fmaxf(v[i] + 3.f, 0.f), 6.f) * (1.f / 6.f);
+        for (int i = 0; i < N; ++i) v[i] = __saturatef(fmaf(v[i], 1.f / 6.f, 0.5f));
     } else if (act == CABINET_ACT_SIGMOID) {
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = 1.f / (1.f + __expf(-v[i]));
