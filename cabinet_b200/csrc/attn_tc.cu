@@ -2,9 +2,10 @@
 //     ctx = softmax(Q K^T / sqrt(d)) V        per image, d = 128, L = H/32 * W/32 tokens (1024 ... 8160)
 // The L x L score matrix never exists in memory: one CTA owns 128 queries of one image and streams the keys in
 // blocks of 128.  Two passes over the keys (QK^T is recomputed; the tensor work here is negligible):
-//   pass A  S = Q K_j^T (TMEM) -> running row max m and row sum l (online, registers)
-//   pass B  S = Q K_j^T (TMEM) -> P = exp2(S*c - m) / l  (bf16, written in the K-major SWIZZLE_128B UMMA layout to
-//           shared memory) -> O += P V_j (TMEM accumulator over all key blocks) -> ctx rows (bf16)
+//   pass A  S = Q K_j^T (TMEM) -> row max m (registers; no exponentials)
+//   pass B  S = Q K_j^T (TMEM) -> P = exp2(S*c - m) <= 1, unnormalised (bf16, written in the K-major SWIZZLE_128B UMMA
+//           layout to shared memory; row sum l of the rounded values) -> O += P V_j (TMEM accumulator over all key
+//           blocks) -> ctx rows = O / l (bf16)
 // so no accumulator rescaling is needed.  V must be K-major (keys contiguous) for the P V product, hence the tiny
 // transpose pre-kernel v [L][128] -> vt [128][ceil8(L)].
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5 softmax / epilogue
@@ -137,43 +138,37 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int row = qd * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
         const float c = p.c;
-        float m = -INFINITY, l = 0.f;
-        // ---- pass A: row max / row sum
+        // ---- pass A: row max only (c > 0, so the scale is applied to the maximum).  No exponentials here: pass B
+        // writes UNNORMALISED probabilities exp2(s*c - m) <= 1, accumulates their row sum, and the output rows are
+        // scaled by 1 / l at the end.
+        float mraw = -INFINITY;
         for (int t = 0; t < nkb; ++t) {
             const int s = t & 1;
             tc::mbar_wait(&s_full[s], (t >> 1) & 1);
             tc::tc_fence_after();
             const uint32_t ta = tmem + s * 128 + lane_addr;
-            const int key0 = t * BKEY;
-            float bmax = -INFINITY;
+            const int nvalid = min(BKEY, p.L - t * BKEY);  // only the last key block can be partial
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 uint32_t r[32];
                 tc::tmem_ld32(ta + ch * 32, r);
                 tc::tmem_ld_wait();
+                if (nvalid == BKEY) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (key0 + ch * 32 + i < p.L) bmax = fmaxf(bmax, __uint_as_float(r[i]) * c);
+                    for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, __uint_as_float(r[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (ch * 32 + i < nvalid) mraw = fmaxf(mraw, __uint_as_float(r[i]));
+                }
             }
-            const float m_new = fmaxf(m, bmax);
-            float sum = 0.f;
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t r[32];
-                tc::tmem_ld32(ta + ch * 32, r);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (key0 + ch * 32 + i < p.L) sum += exp2f(fmaf(__uint_as_float(r[i]), c, -m_new));
-            }
-            l = l * exp2f(m - m_new) + sum;
-            m = m_new;
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s_empty[s]);
         }
-        const float inv_l = 1.f / l;
-        // ---- pass B: normalised probabilities -> smem (UMMA A operand)
+        const float m = mraw * c;
+        float l = 0.f;
+        // ---- pass B: probabilities -> smem (UMMA A operand), one MUFU.EX2 per element
         for (int t = nkb; t < T; ++t) {
             const int s = t & 1;
             const int kidx = t - nkb;
@@ -181,7 +176,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tc::tc_fence_after();
             tc::mbar_wait(&p_empty, (kidx & 1) ^ 1);
             const uint32_t ta = tmem + s * 128 + lane_addr;
-            const int key0 = kidx * BKEY;
+            const int nvalid = min(BKEY, p.L - kidx * BKEY);
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 uint32_t r[32];
@@ -189,12 +184,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 tc::tmem_ld_wait();
                 float pv[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    pv[i] = (key0 + ch * 32 + i < p.L) ? exp2f(fmaf(__uint_as_float(r[i]), c, -m)) * inv_l : 0.f;
+                for (int i = 0; i < 32; ++i) {
+                    float e;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(__uint_as_float(r[i]), c, -m)));
+                    pv[i] = e;
+                }
+                if (nvalid != BKEY) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (ch * 32 + i >= nvalid) pv[i] = 0.f;
+                }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {  // 4 chunks of 8 keys = 16 bytes each
                     Vec16<bf16> o;
                     o.pack(pv + 8 * g);
+                    // the row sum is taken over the ROUNDED probabilities the tensor core will multiply with
+                    float pr[8];
+                    o.unpack(pr);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) l += pr[i];
                     const int cidx = ch * 4 + g;  // 16-byte chunk index along the 128 keys
                     tc::sts128(tc::smem_u32(sP) + (cidx >> 3) * TILE_BYTES + row * 128 + (((cidx & 7) ^ (row & 7)) << 4), o.raw);
                 }
@@ -207,6 +215,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 tc::mbar_arrive(&s_empty[s]);
             }
         }
+        const float inv_l = 1.f / l;
         // ---- output rows
         tc::mbar_wait(&o_full, 0);
         tc::tc_fence_after();
@@ -222,7 +231,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 for (int g = 0; g < 4; ++g) {
                     float f[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[8 * g + i]);
+                    for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[8 * g + i]) * inv_l;
                     Vec16<bf16> o;
                     o.pack(f);
                     o.store(out + ch * 32 + g * 8);
