@@ -210,14 +210,16 @@ channel_sum_kernel(const T* __restrict__ x, long long ldx, long long HW, int C, 
 #pragma unroll
         for (int i = 0; i < V; ++i) acc[i] = 0.f;
         const T* base = x + static_cast<long long>(n) * HW * ldx + cg * V;
-        for (long long pb = p0 + pr; pb < p1; pb += 4LL * rows) {  // four independent 16-byte loads in flight
+        // 32-bit pixel / element offsets inside one image (the host checks HW * ldx < 2^31)
+        const unsigned q1 = static_cast<unsigned>(p1), step = static_cast<unsigned>(rows), ld = static_cast<unsigned>(ldx);
+        for (unsigned pb = static_cast<unsigned>(p0) + pr; pb < q1; pb += 4u * step) {  // four 16-byte loads in flight
             Vec16<T> v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (pb + u * rows < p1) v[u].load(base + (pb + u * rows) * ldx);
+                if (pb + u * step < q1) v[u].load(base + (pb + u * step) * ld);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (pb + u * rows < p1) {
+                if (pb + u * step < q1) {
                     float f[V];
                     v[u].unpack(f);
 #pragma unroll
@@ -256,7 +258,7 @@ extern "C" int cabinet_channel_sum(const void* x, long long ldx, int dtype, int 
                                    float* scratch, long long scratch_bytes, cabinet_stream_t stream) {
     CAB_REQUIRE(x && out && scratch, "channel_sum: null pointer");
     const int V = dtype == CABINET_F32 ? 4 : 8;
-    CAB_REQUIRE(C > 0 && C % V == 0 && ldx % V == 0 && ldx >= C && C / V <= 256 && N <= 65535,
+    CAB_REQUIRE(C > 0 && C % V == 0 && ldx % V == 0 && ldx >= C && C / V <= 256 && N <= 65535 && HW * ldx < (1LL << 31),
                 "channel_sum: unsupported C=%d ldx=%lld", C, ldx);
     if (N == 0 || HW == 0) return CABINET_OK;
     // >= 256 pixels per block and at most 64 blocks per image (the last block of an image adds their partial sums)
@@ -339,9 +341,9 @@ extern "C" int cabinet_scale_act(void* x, long long ldx, int dtype, const float*
 namespace {
 // out[n][r][k] = bf16(w[r][k] * (scale[n][k % cin_pad] + plus)) for k % cin_pad < Cin, 0 otherwise (the K padding)
 __global__ void __launch_bounds__(256)
-scale_weights_kernel(const bf16* __restrict__ w, const float* __restrict__ scale, bf16* __restrict__ out, long long per_image,
-                     int cin_pad, int Cin, float plus) {
-    const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
+scale_weights_kernel(const bf16* __restrict__ w, const float* __restrict__ scale, bf16* __restrict__ out, unsigned per_image,
+                     unsigned cin_pad, int Cin, float plus) {
+    const unsigned i = (blockIdx.x * 256u + threadIdx.x) * 8u;  // 32-bit index math (a 64-bit modulo costs ~100 instructions)
     if (i >= per_image) return;
     const int n = blockIdx.y;
     const int ci = static_cast<int>(i % cin_pad);  // 8 consecutive k share the tap (cin_pad % 8 == 0)
@@ -349,11 +351,17 @@ scale_weights_kernel(const bf16* __restrict__ w, const float* __restrict__ scale
     v.load(w + i);
     float f[8];
     v.unpack(f);
-    const float* sc = scale + static_cast<long long>(n) * Cin;
+    const float* sc = scale + static_cast<long long>(n) * Cin + ci;
+    if (ci + 8 <= Cin) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc)), s1 = __ldg(reinterpret_cast<const float4*>(sc) + 1);
+        f[0] *= s0.x + plus; f[1] *= s0.y + plus; f[2] *= s0.z + plus; f[3] *= s0.w + plus;
+        f[4] *= s1.x + plus; f[5] *= s1.y + plus; f[6] *= s1.z + plus; f[7] *= s1.w + plus;
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = (ci + j < Cin) ? f[j] * (sc[ci + j] + plus) : 0.f;
+        for (int j = 0; j < 8; ++j) f[j] = (ci + j < Cin) ? f[j] * (sc[j] + plus) : 0.f;
+    }
     v.pack(f);
-    v.store(out + static_cast<long long>(n) * per_image + i);
+    v.store(out + static_cast<size_t>(n) * per_image + i);
 }
 }  // namespace
 
@@ -365,10 +373,12 @@ extern "C" int cabinet_scale_weights(const void* w_packed, const float* scale, v
                 "scale_weights: alignment / batch");
     if (N == 0) return CABINET_OK;
     const long long per_image = static_cast<long long>(rows) * taps * cin_pad;
+    CAB_REQUIRE(per_image < (1LL << 31), "scale_weights: weight matrix too large");
+    CAB_REQUIRE(Cin % 4 == 0 && (reinterpret_cast<uintptr_t>(scale) & 15) == 0, "scale_weights: Cin %% 4 and a 16-byte aligned scale");
     dim3 grid(static_cast<unsigned>(cab_ceil_div(per_image / 8, 256)), N);
     scale_weights_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const bf16*>(w_packed), scale, reinterpret_cast<bf16*>(out), per_image, cin_pad, Cin,
-        plus_one ? 1.f : 0.f);
+        reinterpret_cast<const bf16*>(w_packed), scale, reinterpret_cast<bf16*>(out), static_cast<unsigned>(per_image),
+        static_cast<unsigned>(cin_pad), Cin, plus_one ? 1.f : 0.f);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }
