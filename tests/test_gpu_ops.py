@@ -600,3 +600,33 @@ def test_conv_tc_per_image_weights():
                                    bd.data_ptr(), None, 0, ym.ptr, ym.dt, ym.ld, H, W, ACT_RELU, stream()), "imgw")
     torch.cuda.synchronize()
     assert rel_l2(from_map(ym), ref) < 8e-3
+
+
+def test_conv_tc_per_image_weights_1x1_with_residual():
+    """Flat (1x1) tiles: every 128-pixel tile belongs to one image when H * W % 128 == 0 (SE gate folded into the
+    project weights, relu(s * d) = s * relu(d))."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    N, cin, cout, H, W = 4, 120, 40, 16, 24   # H * W = 384 = 3 tiles per image
+    d = q(torch.relu(gen(N, cin, H, W, seed=1)), dtype)
+    w = q(gen(cout, cin, 1, 1, seed=2, scale=cin ** -0.5), dtype)
+    b = gen(cout, seed=3, scale=0.1)
+    sgate = torch.rand(N, cin, generator=torch.Generator().manual_seed(4))
+    r = q(gen(N, cout, H, W, seed=5), dtype)
+    ref = F.conv2d(d * sgate[:, :, None, None], w, b) + r
+    n16, c64 = -(-cout // 16) * 16, -(-cin // 64) * 64
+    pk = torch.zeros(n16, 1, c64)
+    pk[:cout, 0, :cin] = w.reshape(cout, cin)
+    pk = pk.to("cuda", dtype).contiguous()
+    wimg = torch.empty((N, n16, 1, c64), dtype=dtype, device="cuda")
+    sd, bd = sgate.cuda(), b.cuda()
+    check(lib.cabinet_scale_weights(pk.data_ptr(), sd.data_ptr(), wimg.data_ptr(), N, n16, 1, c64, cin, 0, stream()), "sw")
+    xm, rm, ym = to_map(d, dtype), to_map(r, dtype), to_map(torch.zeros_like(ref), dtype)
+    check(lib.cabinet_conv_tc_imgw(xm.ptr, xm.ld, N, H, W, cin, wimg.data_ptr(), n16 * c64, cout, 1, 1, 1, 0,
+                                   bd.data_ptr(), rm.ptr, rm.ld, ym.ptr, ym.dt, ym.ld, H, W, ACT_NONE, stream()), "imgw")
+    torch.cuda.synchronize()
+    assert rel_l2(from_map(ym), ref) < 8e-3
+    # a map whose pixel count is not a multiple of 128 must be refused (a tile would straddle two images)
+    rc = lib.cabinet_conv_tc_imgw(xm.ptr, xm.ld, N, 5, 7, cin, wimg.data_ptr(), n16 * c64, cout, 1, 1, 1, 0, bd.data_ptr(),
+                                  None, 0, ym.ptr, ym.dt, ym.ld, 5, 7, ACT_NONE, stream())
+    assert rc != 0
