@@ -31,6 +31,7 @@ SIGNATURES = {
     "cabinet_conv_tc": ([_p, _ll, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _ll, _p, _i, _ll, _i, _i, _i, _p], _i),
     "cabinet_conv_tc_se": ([_p, _ll, _i, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _ll, _p, _i, _ll, _i, _i, _i,
                             _p], _i),
+    "cabinet_conv_tc_split_act": ([_p, _ll, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _ll, _i, _i, _i, _i, _p], _i),
     "cabinet_conv_tc_imgw": ([_p, _ll, _i, _i, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _p, _p, _ll, _p, _i, _ll, _i, _i, _i,
                               _p], _i),
     "cabinet_scale_weights": ([_p, _p, _p, _i, _i, _i, _i, _i, _i, _p], _i),

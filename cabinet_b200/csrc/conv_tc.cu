@@ -40,6 +40,7 @@ struct TcConvParams {
     int cin_blocks, num_k_blocks;
     int block_n, n_tiles, num_tiles, tmem_cols, stages, b_resident;
     int act, y_dtype, debug;
+    int act_cols;             // the activation applies to output channels < act_cols only (merged q|k|v projection)
     int b_per_image;          // weights differ per image (cabinet_conv_tc_imgw): B tiles are fetched with the tile's image index
     int c_bufs;               // store staging buffers per epilogue warpgroup: 2, or 1 when a tile is a single 64-column group
     int a_act, hw;            // A-operand prologue: x <- act(x * a_scale[image][channel]); hw = pixels per image
@@ -327,12 +328,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         v[4 * j4 + 3] = __uint_as_float(r[16 * c + 4 * j4 + 3]) + b.w;
                     }
                     constexpr bool RELU_ON_CVT = ACT == CABINET_ACT_RELU && !HAS_RES && !OUT_F32;  // cvt.rn.relu.bf16x2
+                    const bool do_act = co0 < p.act_cols;  // uniform per 16-column chunk (act_cols % 16 == 0)
                     if constexpr (ACT == CABINET_ACT_RELU && !RELU_ON_CVT) {
+                        if (do_act) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                        }
                     } else if constexpr (ACT == CABINET_ACT_HSWISH) {
+                        if (do_act) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] *= __saturatef(fmaf(v[j], 1.f / 6.f, 0.5f));  // relu6(v+3)/6
+                            for (int j = 0; j < 16; ++j) v[j] *= __saturatef(fmaf(v[j], 1.f / 6.f, 0.5f));  // relu6(v+3)/6
+                        }
                     }
                     if constexpr (HAS_RES) {
                         if (valid && co0 < p.Cout) {
@@ -355,7 +361,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                     if constexpr (!OUT_F32) {
                         Vec16<bf16> o0, o1;
-                        if constexpr (RELU_ON_CVT) {
+                        if (RELU_ON_CVT && do_act) {
                             uint32_t w[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
@@ -454,7 +460,7 @@ extern "C" int cabinet_debug_flags(int flags) {
 static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int Cin, const float* a_scale, int a_act,
                         const void* w_packed, long long w_image_stride, int Cout, int KH, int KW, int stride, int pad,
                         const float* bias, const void* res, long long ldres, void* y, int y_dtype, long long ldy,
-                        int OH, int OW, int act, cabinet_stream_t stream);
+                        int OH, int OW, int act, cabinet_stream_t stream, int act_cols = 1 << 30);
 
 extern "C" int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, int W, int Cin, const float* a_scale,
                                   int a_act, const void* w_packed, int Cout, int KH, int KW, int stride, int pad,
@@ -475,6 +481,15 @@ extern "C" int cabinet_conv_tc_imgw(const void* x, long long ldx, int N, int H, 
                         stride, pad, bias, res, ldres, y, y_dtype, ldy, OH, OW, act, stream);
 }
 
+extern "C" int cabinet_conv_tc_split_act(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_packed,
+                                         int Cout, int KH, int KW, int stride, int pad, const float* bias, void* y,
+                                         int y_dtype, long long ldy, int OH, int OW, int act, int act_cols,
+                                         cabinet_stream_t stream) {
+    CAB_REQUIRE(act_cols >= 0 && act_cols % 16 == 0, "conv_tc_split_act: act_cols must be a multiple of 16");
+    return conv_tc_impl(x, ldx, N, H, W, Cin, nullptr, CABINET_ACT_NONE, w_packed, 0, Cout, KH, KW, stride, pad, bias,
+                        nullptr, 0, y, y_dtype, ldy, OH, OW, act, stream, act_cols);
+}
+
 extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_packed,
                                int Cout, int KH, int KW, int stride, int pad, const float* bias, const void* res,
                                long long ldres, void* y, int y_dtype, long long ldy, int OH, int OW, int act,
@@ -486,7 +501,7 @@ extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W
 static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int Cin, const float* a_scale, int a_act,
                         const void* w_packed, long long w_image_stride, int Cout, int KH, int KW, int stride, int pad,
                         const float* bias, const void* res, long long ldres, void* y, int y_dtype, long long ldy,
-                        int OH, int OW, int act, cabinet_stream_t stream) {
+                        int OH, int OW, int act, cabinet_stream_t stream, int act_cols) {
     CAB_REQUIRE(x && w_packed && bias && y, "conv_tc: null pointer");
     CAB_REQUIRE(!a_scale || (Cin % 8 == 0 && (reinterpret_cast<uintptr_t>(a_scale) & 15) == 0),
                 "conv_tc: the A-operand scale needs Cin %% 8 == 0 and a 16-byte aligned pointer");
@@ -516,6 +531,7 @@ static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int C
     p.tmem_cols = 32;
     while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
     const int b_stage_bytes = p.block_n * BLOCK_K * 2;
+    p.act_cols = act_cols;
     p.b_per_image = w_image_stride > 0 ? 1 : 0;
     p.b_resident = (!p.b_per_image && p.n_tiles == 1 && p.num_k_blocks * b_stage_bytes <= B_RESIDENT_MAX) ? 1 : 0;
     p.c_bufs = (y_dtype == CABINET_BF16 && p.block_n > 64) ? 2 : 1;

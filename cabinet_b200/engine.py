@@ -225,6 +225,12 @@ class Engine:
         self.b1 = ConvLayer(ab.b1, ab.b2, ACT_RELU, wd, "ab.b1")
         self.b4 = ConvLayer(ab.b4, None, ACT_NONE, wd, "ab.b4")
         self.key_ch = self.to_k.cout
+        # to_query | to_key | to_value read the same tensor: one 256 -> 3 x 128 GEMM, ReLU on the first 2 x 128 outputs
+        self.qkv = None
+        if (self.precision == "bf16" and all(L.tc is not None and L.kh == 1 for L in (self.to_q, self.to_k, self.to_v))
+                and self.to_q.cout == self.to_k.cout == self.to_v.cout and self.to_q.cout % 16 == 0):
+            self.qkv = (torch.cat([L.tc[: L.cout] for L in (self.to_q, self.to_k, self.to_v)], 0).contiguous(),
+                        torch.cat([self.to_q.b, self.to_k.b, self.to_v.b]).contiguous())
 
         ffm = m.ffm
         self.ffm_blk = ConvLayer(ffm.convblk.conv, ffm.convblk.bn, ACT_RELU, wd, "ffm.convblk")
@@ -525,9 +531,21 @@ class Engine:
 
         # ---- attention branch (reference: cabinet.py:75-94, cab.py:131-162,175-184,213-216)
         feat = self.conv(mf, self.conva)
-        q = self.conv(feat, self.to_q)
-        k = self.psp(self.conv(feat, self.to_k), self.psp_k)
-        v = self.psp(self.conv(feat, self.to_v), self.psp_v)
+        if self.qkv is not None and self.use_tc and feat.dt == BF16:
+            kc = self.key_ch
+            qkv = self.new(N, h32, w32, 3 * kc)
+            M = N * h32 * w32
+            self._run("conv_tc", "cab.to_query|key|value", (M * (feat.C + 3 * kc) + self.qkv[0].numel()) * 2,
+                      2 * M * 3 * kc * feat.C, self.lib.cabinet_conv_tc_split_act, feat.ptr, feat.ld, N, h32, w32, feat.C,
+                      self.qkv[0].data_ptr(), 3 * kc, 1, 1, 1, 0, self.qkv[1].data_ptr(), qkv.ptr, qkv.dt, qkv.ld, h32, w32,
+                      ACT_RELU, 2 * kc, self.stream)
+            q = qkv.slice(0, kc)
+            k = self.psp(qkv.slice(kc, kc), self.psp_k)
+            v = self.psp(qkv.slice(2 * kc, kc), self.psp_v)
+        else:
+            q = self.conv(feat, self.to_q)
+            k = self.psp(self.conv(feat, self.to_k), self.psp_k)
+            v = self.psp(self.conv(feat, self.to_v), self.psp_v)
         ctx = self.attention(q, k, v)
         g = self.conv(ctx, self.proj_out)
         r = feat

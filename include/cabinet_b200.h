@@ -119,6 +119,13 @@ int cabinet_mbconv_noexpand_fused(const void* x, long long ldx, const float* w_d
                                   const float* w_pw, const float* b_pw, void* y, long long ldy, int N, int H, int W,
                                   int C, int act, cabinet_stream_t stream);
 
+/* cabinet_conv_tc whose activation applies to the first act_cols output channels only (act_cols % 16 == 0): several
+ * convolutions of the SAME input merged into one GEMM, e.g. GlobalContextAttention's to_query | to_key (Conv+BN+ReLU) |
+ * to_value (plain conv), src/models/cab.py:107-128, as one 256 -> 384 projection with act_cols = 256. */
+int cabinet_conv_tc_split_act(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_packed, int Cout,
+                              int KH, int KW, int stride, int pad, const float* bias, void* y, int y_dtype, long long ldy,
+                              int OH, int OW, int act, int act_cols, cabinet_stream_t stream);
+
 /* cabinet_conv_tc with one weight matrix PER IMAGE (w_packed_per_image + n * w_image_stride elements, each in the
  * cabinet_conv_tc packing); 1x1 convolutions need H * W % 128 == 0.  Used to fold a per-(image, input-channel) scale of
  * the INPUT into the weights instead of rewriting the input tensor: FeatureFusionModule's feat * atten + feat

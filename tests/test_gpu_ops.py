@@ -630,3 +630,26 @@ def test_conv_tc_per_image_weights_1x1_with_residual():
     rc = lib.cabinet_conv_tc_imgw(xm.ptr, xm.ld, N, 5, 7, cin, wimg.data_ptr(), n16 * c64, cout, 1, 1, 1, 0, bd.data_ptr(),
                                   None, 0, ym.ptr, ym.dt, ym.ld, 5, 7, ACT_NONE, stream())
     assert rc != 0
+
+
+def test_conv_tc_split_act():
+    """One GEMM for three projections of the same input: ReLU on the first 2 x 32 output channels only."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    N, cin, cout, H, W = 2, 48, 96, 12, 20
+    x = q(gen(N, cin, H, W, seed=1), dtype)
+    w = q(gen(cout, cin, 1, 1, seed=2, scale=cin ** -0.5), dtype)
+    b = gen(cout, seed=3, scale=0.3)
+    full = F.conv2d(x, w, b)
+    ref = torch.cat([torch.relu(full[:, :64]), full[:, 64:]], 1)
+    pk = torch.zeros(cout, 1, 64)
+    pk[:, 0, :cin] = w.reshape(cout, cin)
+    pk = pk.to("cuda", dtype).contiguous()
+    bd = b.cuda()
+    xm, ym = to_map(x, dtype), to_map(torch.zeros_like(ref), dtype)
+    check(lib.cabinet_conv_tc_split_act(xm.ptr, xm.ld, N, H, W, cin, pk.data_ptr(), cout, 1, 1, 1, 0, bd.data_ptr(), ym.ptr,
+                                        ym.dt, ym.ld, H, W, ACT_RELU, 64, stream()), "split_act")
+    torch.cuda.synchronize()
+    got = from_map(ym)
+    assert rel_l2(got, ref) < 6e-3
+    assert float(got[:, :64].min()) >= 0 and float(got[:, 64:].min()) < 0
