@@ -142,6 +142,9 @@ class Engine:
         self.dual_stream = False    # experimental: two half-batches on two streams
         self._side = None
         self._scratch = []
+        self.branch_overlap = True  # independent chains of the attention branch on side streams (fork / join by events)
+        self._branch_streams, self._branch_events = [], {}
+        self.sb_overlap = False     # experiment: spatial branch beside the backbone
         with torch.no_grad():
             self._pack(model)
 
@@ -321,6 +324,49 @@ class Engine:
                       self.stream)
         return out
 
+    # ------------------------------------------------------------------ independent branches on side streams
+    class _Branch:
+        """Kernels enqueued inside the block go to side stream `i` (forked from the current stream); `joined(t)` marks a
+        tensor that the main stream consumes after `_join(i)`.  The small kernels of the attention branch are latency
+        bound, so two independent chains side by side cost the longer one, not the sum.  Works eagerly and under CUDA
+        graph capture (fork / join by events)."""
+
+        def __init__(self, eng, i):
+            self.eng, self.i = eng, i
+
+        def __enter__(self):
+            eng = self.eng
+            if not eng.branch_overlap or eng.trace is not None or torch.device(eng.dev).type != "cuda":
+                self.ctx = None
+                return lambda t: None
+            self.main = torch.cuda.current_stream(eng.dev)
+            while len(eng._branch_streams) <= self.i:
+                eng._branch_streams.append(torch.cuda.Stream(eng.dev))
+            side = eng._branch_streams[self.i]
+            ev = torch.cuda.Event()
+            ev.record(self.main)
+            side.wait_event(ev)
+            self.ctx = torch.cuda.stream(side)
+            self.ctx.__enter__()
+            return lambda t: t.record_stream(self.main)
+
+        def __exit__(self, *a):
+            if self.ctx is not None:
+                eng = self.eng
+                ev = torch.cuda.Event()
+                ev.record(eng._branch_streams[self.i])
+                eng._branch_events[self.i] = ev
+                self.ctx.__exit__(*a)
+            return False
+
+    def _branch(self, i):
+        return Engine._Branch(self, i)
+
+    def _join(self, i):
+        ev = self._branch_events.pop(i, None)
+        if ev is not None:
+            torch.cuda.current_stream(self.dev).wait_event(ev)
+
     def mbconv_fused(self, x: Map, e: dict, gap: Optional[torch.Tensor], act_dw: Optional[int] = None) -> Map:
         """Inverted-residual block with the expanded activation kept on chip (reference: mobilenetv3.py:126-159).
         ``gap`` given (SE blocks): returns the pre-SE depthwise output and accumulates its pooling sums; else the
@@ -444,11 +490,19 @@ class Engine:
                       self.stem_tc[1].data_ptr(), s1.ptr, s1.ld, f0.ptr, f0.ld, OH2, OW2, self.stream)
         else:
             s1 = self.conv(None, self.sb1, nchw_input=x)
-        s2 = self.conv(s1, self.sb2)
-        s3 = self.conv(s2, self.sb3)
-        H8, W8 = s3.H, s3.W
+        H8, W8 = _out_size(_out_size(s1.H, 3, 2, 1), 3, 2, 1), _out_size(_out_size(s1.W, 3, 2, 1), 3, 2, 1)
         cat_ffm = self.new(N, H8, W8, 128 + 256)
-        self.conv(s3, self.sb4, out=cat_ffm.slice(0, 128))
+        if self.sb_overlap:  # experiment: the rest of the spatial branch beside the backbone (joined before the FFM)
+            with self._branch(2) as joined:
+                s2 = self.conv(s1, self.sb2)
+                s3 = self.conv(s2, self.sb3)
+                self.conv(s3, self.sb4, out=cat_ffm.slice(0, 128))
+                joined(s1.t)
+        else:
+            s2 = self.conv(s1, self.sb2)
+            s3 = self.conv(s2, self.sb3)
+            self.conv(s3, self.sb4, out=cat_ffm.slice(0, 128))
+        assert (s3.H, s3.W) == (H8, W8)
 
         # ---- backbone (reference: mobilenetv3.py:202-205)
         f = f0 if fused_stems else self.conv(None, self.stem, nchw_input=x)
@@ -540,31 +594,39 @@ class Engine:
                       self.qkv[0].data_ptr(), 3 * kc, 1, 1, 1, 0, self.qkv[1].data_ptr(), qkv.ptr, qkv.dt, qkv.ld, h32, w32,
                       ACT_RELU, 2 * kc, self.stream)
             q = qkv.slice(0, kc)
+            with self._branch(1) as joined:     # value PSP chain beside the key PSP chain
+                v = self.psp(qkv.slice(2 * kc, kc), self.psp_v)
+                joined(v.t)
             k = self.psp(qkv.slice(kc, kc), self.psp_k)
-            v = self.psp(qkv.slice(2 * kc, kc), self.psp_v)
         else:
             q = self.conv(feat, self.to_q)
             k = self.psp(self.conv(feat, self.to_k), self.psp_k)
             v = self.psp(self.conv(feat, self.to_v), self.psp_v)
+        with self._branch(0) as joined:         # local attention (three depthwise convs) beside the global attention
+            r = feat
+            for L in self.local:
+                r = self.dwconv(r, L)
+            joined(r.t)
+        self._join(1)
         ctx = self.attention(q, k, v)
         g = self.conv(ctx, self.proj_out)
-        r = feat
-        for L in self.local:
-            r = self.dwconv(r, L)
+        self._join(0)
         feat2 = cat_b1.slice(self.last.cout, 256)
         es = feat.t.element_size()
         self._run("cab_combine", "cab", 2 * N * h32 * w32 * 256 * es, 0, self.lib.cabinet_cab_combine, g.ptr, feat.ptr,
                   r.ptr, feat2.ptr, feat2.ld, self.gamma.data_ptr(), self.dt, N * h32 * w32, 256, self.stream)
-        low = self.conv(feat2, self.convb)
+        aux8 = self.new(N, H8, W8, C, torch.float32)
+        with self._branch(0) as joined:  # low-level path (convb + x4 upsample into the FFM concat) beside b1 / b4
+            low = self.conv(feat2, self.convb)
+            self.bilinear(low, cat_ffm.slice(128, 256), "low_up")   # 1/32 -> 1/8 (reference: cabinet.py:228-233)
+            joined(low.t)
         fused = self.conv(cat_b1, self.b1)
         high = self.conv(fused, self.b4, out_dtype=torch.float32)  # class logits stay fp32
-
-        # ---- 1/32 -> 1/8 (reference: cabinet.py:228-233)
-        self.bilinear(low, cat_ffm.slice(128, 256), "low_up")
-        aux8 = self.new(N, H8, W8, C, torch.float32)
         self.bilinear(high, aux8, "high_up")
+        self._join(0)
 
         # ---- feature fusion (reference: cabinet.py:142-153)
+        self._join(2)
         ff = self.conv(cat_ffm, self.ffm_blk)
         gap = gap_all[n_se].view(-1)[: N * 256].view(N, 256)
         scratch = ffm_scratch
