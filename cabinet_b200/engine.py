@@ -138,6 +138,7 @@ class Engine:
         self.use_cuda_graph = False
         self.sub_batch = 0          # > 0: run the schedule over chunks of this many images
         self._graphs = {}
+        self._pool = None
         self._graph_seen = {}
         self.dual_stream = False    # experimental: two half-batches on two streams
         self._side = None
@@ -710,26 +711,44 @@ class Engine:
         if not self.use_cuda_graph or self.trace is not None or self.debug or x.shape[0] == 0:
             return self._forward_eager(x, out_dtype)
         key = (tuple(x.shape), out_dtype, self.sub_batch, self.dual_stream)
-        g = self._graphs.get(key)
+        # A caller that keeps feeding the SAME buffer (an evaluator's device-side input slot, a benchmark) gets a graph
+        # captured on that address: no 2 x 201 MB staging copy per call.  Anything else goes through a static input
+        # buffer.  All graphs of the engine share one memory pool.
+        pkey = key + (x.data_ptr(),)
+        g = self._graphs.get(pkey)
         if g is None:
-            static_x = x.clone()
-            cur = torch.cuda.current_stream(self.dev)
-            side = torch.cuda.Stream(self.dev)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):  # warm-up outside capture (lazy function attributes, allocator)
-                self._forward_eager(static_x, out_dtype)
-            cur.wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                outs = self._forward_eager(static_x, out_dtype)
-            g = (graph, static_x, outs, self.launches)
-            self._graphs[key] = g
+            if len(self._graph_seen) > 4096:
+                self._graph_seen.clear()
+            seen = self._graph_seen.get(pkey, 0) + 1
+            self._graph_seen[pkey] = seen
+            if seen >= 3 and sum(1 for k in self._graphs if len(k) == len(pkey)) < 4:
+                g = self._capture_forward(x, out_dtype)
+                self._graphs[pkey] = g
+            else:
+                g = self._graphs.get(key)
+                if g is None:
+                    g = self._capture_forward(x.clone(), out_dtype)
+                    self._graphs[key] = g
         graph, static_x, outs, launches = g
         if x.data_ptr() != static_x.data_ptr():
             static_x.copy_(x, non_blocking=True)
         graph.replay()
         self.launches = launches
         return outs
+
+    def _capture_forward(self, static_x, out_dtype):
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):  # warm-up outside capture (lazy function attributes, allocator)
+            self._forward_eager(static_x, out_dtype)
+        cur.wait_stream(side)
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, pool=self._pool):
+            outs = self._forward_eager(static_x, out_dtype)
+        return (graph, static_x, outs, self.launches)
 
     def _argmax(self, final8: Map, N, H, W, labels=None, hist=None, ignore_label=255):
         mask = torch.empty((N, H, W), dtype=torch.uint8, device=self.dev)
@@ -748,12 +767,16 @@ class Engine:
             return fn()
         g = self._graphs.get(key)
         if g is None:
+            if len(self._graph_seen) > 4096:  # callers that never repeat a buffer: do not grow without bound
+                self._graph_seen.clear()
             seen = self._graph_seen.get(key, 0) + 1
             self._graph_seen[key] = seen
             if seen < 2 or len(self._graphs) >= 16:
                 return fn()
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, pool=self._pool):  # one activation pool for all graphs of this engine
                 out = fn()
             g = (graph, out, self.launches)
             self._graphs[key] = g
