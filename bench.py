@@ -213,6 +213,36 @@ def summarise_trace(rows, steps, peaks):
     return table
 
 
+def roofline_by_bound(fam_rows, peaks):
+    """The dominant family mixes HBM-bound and tensor-bound layers (conv_tc runs the 1x1 convs and the dense 3x3
+    convs): classify every launch by its own floor max(bytes / HBM peak, flops / tensor peak) and report each class
+    against its own peak, plus the share of the family's time that the per-launch floors explain."""
+    tf_peak, hbm = peaks["bf16_tflops_sustained"], peaks["hbm_gbs"]
+    cls = {"hbm": {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0, "floor_ms": 0.0},
+           "tensor": {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0, "floor_ms": 0.0}}
+    for r in fam_rows:
+        t_hbm, t_tc = r["bytes"] / (hbm * 1e9), r["flops"] / (tf_peak * 1e12)
+        c = cls["tensor" if t_tc > t_hbm else "hbm"]
+        c["ms"] += r["ms"]
+        c["bytes"] += r["bytes"]
+        c["flops"] += r["flops"]
+        c["launches"] += 1
+        c["floor_ms"] += 1e3 * max(t_hbm, t_tc)
+    out = {}
+    for name, c in cls.items():
+        if not c["launches"]:
+            continue
+        if name == "hbm":
+            ach, peak, unit = c["bytes"] / (c["ms"] * 1e-3) / 1e9, hbm, "GB/s"
+        else:
+            ach, peak, unit = c["flops"] / (c["ms"] * 1e-3) / 1e12, tf_peak, "TFLOP/s"
+        out[name] = {"achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "launches": c["launches"],
+                     "time_share_of_family": c["ms"] / sum(v["ms"] for v in cls.values())}
+    total = sum(v["ms"] for v in cls.values())
+    out["floor_frac"] = sum(v["floor_ms"] for v in cls.values()) / total if total else None
+    return out
+
+
 def ncu_traffic_per_launch(kernel, args):
     """dram read+write bytes per launch of a kernel family from the committed ncu capture of this workload
     (profiles/r01_ncu_dram_traffic_per_family.json: one forward, batch 16, Large, 1024x1024), else None."""
@@ -317,6 +347,7 @@ def run_ours(args):
         table = summarise_trace(rows, K, peaks)
         dom = table[0]
         roof = roofline_entry(dom, [r for r in rows if r["kernel"] == dom["kernel"]], peaks)
+        roof["by_bound"] = roofline_by_bound([r for r in rows if r["kernel"] == dom["kernel"]], peaks)
         roof["traffic"] = ncu_traffic_per_launch(dom["kernel"], args)
         roof["traffic_source"] = "profiles/r01_ncu_dram_traffic_per_family.json (ncu dram__bytes_read+write per launch)"
         traced_ms = sum(r["ms"] for r in rows) / K
@@ -364,6 +395,34 @@ def run_ours(args):
                 "input": "uint8 NHWC images + uint8 labels, normalised on the device (cabinet_normalize_u8)",
                 "hist_checksum_ok": (world > 1) or int(res8["confusion_matrix"].sum()) == valid}
 
+        # ---------------- the reference's default evaluation protocol (configs/train.yaml:65-66: six scales + flip TTA,
+        # sliding 1024^2 windows, stride 853): 30 class-map forwards per batch + the fused softmax / window / resize /
+        # argmax / confusion-matrix kernels, next to the same evaluator taking the reference's steps as torch ops.
+        msflip = None
+        if args.msflip and world == 1:
+            bm = min(B, args.msflip)
+            scales = (0.5, 0.75, 1.0, 1.25, 1.5, 1.75)
+            evm = MscEvalV0(model, [(x_host[:bm], lb_host[:bm])], C, 255, scales, True, cropsize=S)
+            msflip = {"unit": UNIT, "batch": bm, "scales": list(scales), "flip": True,
+                      "forwards_per_batch": 30, "h2d_bytes_per_step": bm * (3 * S * S * 4 + S * S)}
+            hists = {}
+            for name, fused in (("fused_kernels", True), ("torch_ops", False)):
+                evm.fused_general = fused
+                for _ in range(2):
+                    evm.evaluate()
+                barrier()
+                e0.record()
+                r = evm.evaluate()
+                e1.record()
+                barrier()
+                hists[name] = r["confusion_matrix"]
+                msflip[name] = {"value": bm / (e0.elapsed_time(e1) * 1e-3), "ms_per_batch": e0.elapsed_time(e1)}
+            msflip["value"] = msflip["fused_kernels"]["value"]
+            msflip["pixels_differing_between_paths"] = float(abs(hists["fused_kernels"] - hists["torch_ops"]).sum() / 2
+                                                             / max(hists["torch_ops"].sum(), 1))
+            del evm
+            torch.cuda.empty_cache()
+
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -380,7 +439,7 @@ def run_ours(args):
                        "upsample/argmax/confusion matrix, mask D2H, NCCL hist all-reduce, metrics read-back)",
                 "mIoU": float(res["mIoU"]),
                 "hist_checksum_ok": (world > 1) or hist_sum == valid, "hist_sum": hist_sum, "valid_pixels": valid},
-        "e2e_uint8": e2e8,
+        "e2e_uint8": e2e8, "e2e_multiscale_flip": msflip,
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         "kernels": table, "traced_ms_per_step": traced_ms, "peaks": peaks,
     }
@@ -405,6 +464,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--msflip", type=int, default=4, help="batch of the multi-scale + flip evaluation leg (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -55,6 +55,10 @@ SIGNATURES = {
     "cabinet_upsample_argmax": ([_p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p], _i),
     "cabinet_normalize_u8": ([_p, _p, _i, _i, _i, _f, _f, _f, _f, _f, _f, _p], _i),
     "cabinet_confusion_hist": ([_p, _i, _p, _i, _ll, _i, _i, _p, _p], _i),
+    "cabinet_upsample_softmax_accum": ([_p, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _ll, _ll, _i, _i, _i, _i, _p, _p, _f,
+                                        _p], _i),
+    "cabinet_prob_resize_accum": ([_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p], _i),
+    "cabinet_argmax_hist_nchw": ([_p, _i, _i, _ll, _p, _p, _i, _i, _p, _p], _i),
 }
 
 _lib = None

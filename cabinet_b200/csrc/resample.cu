@@ -343,7 +343,271 @@ normalize_u8_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, long l
                                                                (b[8] * k - m2) * i2, (b[11] * k - m2) * i2));
 }
 
+// ---------------------------------------------------------------------------------- evaluator tail (MscEvalV0)
+// eval_chip + the window accumulation of crop_eval (src/scripts/evaluate.py:74-87,139-146) in one pass over the
+// probability planes: x8 bilinear of the chip's class map -> softmax over classes -> (average with the softmax of the
+// horizontally flipped chip's map, read mirrored) -> weighted add into the window of the fp32 NCHW accumulator.
+// The full-resolution logits, the two softmax outputs, the flipped copy and the chip-sized sum never reach HBM.
+// Thread = 8 consecutive chip pixels of one row, all classes; the class map is evaluated twice (max + sum, then
+// write): it is <= 1/64 of the output and L1/L2 resident.
+template <bool EXACT8>
+__device__ __forceinline__ void softmax_stats8(const float* __restrict__ x, int n, int oh, int g, int IH, int IW, int C,
+                                               int OW, float sh, float sw, float* m, float* l) {
+#pragma unroll
+    for (int p = 0; p < PXG; ++p) {
+        m[p] = -INFINITY;
+        l[p] = 0.f;
+    }
+    upsample_group8<EXACT8>(x, n, oh, g, IH, IW, C, OW, sh, sw, [&](int, const float* v) {
+#pragma unroll
+        for (int p = 0; p < PXG; ++p) {  // online softmax: rescale the running sum when the maximum moves
+            const float mn = fmaxf(m[p], v[p]);
+            l[p] = l[p] * __expf(m[p] - mn) + __expf(v[p] - mn);
+            m[p] = mn;
+        }
+    });
+}
+
+template <bool EXACT8>
+__global__ void __launch_bounds__(128)
+upsample_softmax_accum_kernel(const float* __restrict__ x, const float* __restrict__ xf, int IH, int IW, int C, int OH,
+                              int OW, float sh, float sw, float* __restrict__ prob, long long sn, long long sc,
+                              long long sr, int dy0, int dx0, int dh, int dw, const float* __restrict__ wy,
+                              const float* __restrict__ wx, float weight) {
+    const int groups_w = (OW + PXG - 1) / PXG;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oh = blockIdx.y, n = blockIdx.z;
+    const int y = dy0 + oh;
+    if (g >= groups_w || y < 0 || y >= dh) return;
+    const int ow0 = g * PXG;
+    if (dx0 + ow0 >= dw || dx0 + ow0 + PXG <= 0) return;
+    float m[PXG], l[PXG], mf[PXG], lf[PXG], k[PXG], kf[PXG];
+    softmax_stats8<EXACT8>(x, n, oh, g, IH, IW, C, OW, sh, sw, m, l);
+    const float rowk = weight * (wy ? __ldg(wy + oh) : 1.f) * (xf ? 0.5f : 1.f);
+#pragma unroll
+    for (int p = 0; p < PXG; ++p) k[p] = rowk * (wx ? __ldg(wx + min(ow0 + p, OW - 1)) : 1.f) / l[p];
+    // mirrored group of the flipped chip's map: chip column ow <-> flipped column OW-1-ow.  With OW % 8 == 0 that
+    // is group (groups_w-1-g) read back to front; otherwise the mirrored pixels straddle two groups -> per-pixel path.
+    const bool mirror_fast = EXACT8 || (OW % PXG) == 0;
+    const int gf = groups_w - 1 - g;
+    if (xf && mirror_fast) {
+        softmax_stats8<EXACT8>(xf, n, oh, gf, IH, IW, C, OW, sh, sw, mf, lf);
+#pragma unroll
+        for (int p = 0; p < PXG; ++p) kf[p] = k[PXG - 1 - p] * l[PXG - 1 - p] / lf[p];  // weight of mirrored pixel p
+    }
+    float* orow = prob + static_cast<long long>(n) * sn + static_cast<long long>(y) * sr + dx0 + ow0;
+    const bool inside = dx0 + ow0 >= 0 && dx0 + ow0 + PXG <= dw && ow0 + PXG <= OW;
+    auto emit = [&](int c, const float* pv) {
+        float* o = orow + c * sc;
+        if (inside && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+            float4 a = *reinterpret_cast<const float4*>(o), b = *(reinterpret_cast<const float4*>(o) + 1);
+            a.x += pv[0]; a.y += pv[1]; a.z += pv[2]; a.w += pv[3];
+            b.x += pv[4]; b.y += pv[5]; b.z += pv[6]; b.w += pv[7];
+            *reinterpret_cast<float4*>(o) = a;
+            *(reinterpret_cast<float4*>(o) + 1) = b;
+        } else {
+#pragma unroll
+            for (int p = 0; p < PXG; ++p)
+                if (ow0 + p < OW && dx0 + ow0 + p >= 0 && dx0 + ow0 + p < dw) o[p] += pv[p];
+        }
+    };
+    if (!xf) {
+        upsample_group8<EXACT8>(x, n, oh, g, IH, IW, C, OW, sh, sw, [&](int c, const float* v) {
+            float pv[PXG];
+#pragma unroll
+            for (int p = 0; p < PXG; ++p) pv[p] = __expf(v[p] - m[p]) * k[p];
+            emit(c, pv);
+        });
+    } else if (mirror_fast) {
+        // two sweeps over the classes (plain, mirrored): the consumer interface hands out one class at a time, and the
+        // window is L1/L2-hot for the second read-modify-write
+        upsample_group8<EXACT8>(x, n, oh, g, IH, IW, C, OW, sh, sw, [&](int c, const float* v) {
+            float pv[PXG];
+#pragma unroll
+            for (int p = 0; p < PXG; ++p) pv[p] = __expf(v[p] - m[p]) * k[p];
+            emit(c, pv);
+        });
+        upsample_group8<EXACT8>(xf, n, oh, gf, IH, IW, C, OW, sh, sw, [&](int c, const float* v) {
+            float pv[PXG];
+#pragma unroll
+            for (int p = 0; p < PXG; ++p) pv[PXG - 1 - p] = __expf(v[p] - mf[p]) * kf[p];
+            emit(c, pv);
+        });
+    } else if constexpr (!EXACT8) {
+        upsample_group8<EXACT8>(x, n, oh, g, IH, IW, C, OW, sh, sw, [&](int c, const float* v) {
+            float pv[PXG];
+#pragma unroll
+            for (int p = 0; p < PXG; ++p) pv[p] = __expf(v[p] - m[p]) * k[p];
+            emit(c, pv);
+        });
+        // generic mirrored read: one flipped-map pixel at a time (chip widths that are not a multiple of 8)
+        int y0, y1;
+        float wyy;
+        cab_bilinear_tap(oh, sh, IH, y0, y1, wyy);
+        const float* r0 = xf + (static_cast<long long>(n) * IH + y0) * IW * C;
+        const float* r1 = xf + (static_cast<long long>(n) * IH + y1) * IW * C;
+#pragma unroll
+        for (int p = 0; p < PXG; ++p) {
+            const int ow = ow0 + p;
+            if (ow >= OW || dx0 + ow < 0 || dx0 + ow >= dw) continue;
+            int x0, x1;
+            float wxx;
+            cab_bilinear_tap(OW - 1 - ow, sw, IW, x0, x1, wxx);
+            float mm = -INFINITY, ll = 0.f;
+            for (int c = 0; c < C; ++c) {
+                const float t0 = __ldg(r0 + x0 * C + c), t1 = __ldg(r0 + x1 * C + c);
+                const float b0 = __ldg(r1 + x0 * C + c), b1 = __ldg(r1 + x1 * C + c);
+                const float top = t0 + wxx * (t1 - t0), bot = b0 + wxx * (b1 - b0);
+                const float v = top + wyy * (bot - top);
+                const float mn = fmaxf(mm, v);
+                ll = ll * __expf(mm - mn) + __expf(v - mn);
+                mm = mn;
+            }
+            const float kk = k[p] * l[p] / ll;
+            for (int c = 0; c < C; ++c) {
+                const float t0 = __ldg(r0 + x0 * C + c), t1 = __ldg(r0 + x1 * C + c);
+                const float b0 = __ldg(r1 + x0 * C + c), b1 = __ldg(r1 + x1 * C + c);
+                const float top = t0 + wxx * (t1 - t0), bot = b0 + wxx * (b1 - b0);
+                const float v = top + wyy * (bot - top);
+                orow[c * sc + p] += __expf(v - mm) * kk;
+            }
+        }
+    }
+}
+
+// dst[n][c][y][x] += bilinear(src[n][c][cy0 : cy0+ch][cx0 : cx0+cw] -> (H, W))   (align_corners=False): the un-pad crop
+// and the resize back to the image size of scale_crop_eval plus `probs += prob` of evaluate()
+// (src/scripts/evaluate.py:152-158,216-220) in one pass.  Thread = one output pixel, all classes (taps computed once).
+__global__ void __launch_bounds__(256)
+prob_resize_accum_kernel(const float* __restrict__ src, int C, int SH, int SW, int cy0, int cx0, int ch, int cw,
+                         float* __restrict__ dst, int H, int W, float sh, float sw) {
+    const int xo = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xo >= W) return;
+    const int yo = blockIdx.y, n = blockIdx.z;
+    int y0, y1, x0, x1;
+    float wy, wx;
+    cab_bilinear_tap(yo, sh, ch, y0, y1, wy);
+    cab_bilinear_tap(xo, sw, cw, x0, x1, wx);
+    const long long plane_s = static_cast<long long>(SH) * SW, plane_d = static_cast<long long>(H) * W;
+    const float* s = src + static_cast<long long>(n) * C * plane_s;
+    float* d = dst + static_cast<long long>(n) * C * plane_d + static_cast<long long>(yo) * W + xo;
+    const long long o00 = static_cast<long long>(cy0 + y0) * SW + cx0 + x0, o01 = static_cast<long long>(cy0 + y0) * SW + cx0 + x1;
+    const long long o10 = static_cast<long long>(cy0 + y1) * SW + cx0 + x0, o11 = static_cast<long long>(cy0 + y1) * SW + cx0 + x1;
+    for (int c = 0; c < C; ++c) {
+        const float* sp = s + c * plane_s;
+        // ATen's expression order: w00*a + w01*b + w10*c + w11*d with w = (1-wy)(1-wx) ... evaluated as
+        // h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d)
+        const float top = (1.f - wx) * __ldg(sp + o00) + wx * __ldg(sp + o01);
+        const float bot = (1.f - wx) * __ldg(sp + o10) + wx * __ldg(sp + o11);
+        d[c * plane_d] += (1.f - wy) * top + wy * bot;
+    }
+}
+
+// argmax over the class planes of an fp32 NCHW probability map (first maximum wins, torch.argmax) fused with the
+// confusion matrix (src/scripts/evaluate.py:222-228,162-191): the int64 prediction map is never written.
+template <typename TL>
+__global__ void __launch_bounds__(256)
+argmax_hist_nchw_kernel(const float* __restrict__ probs, int C, long long HW, uint8_t* __restrict__ mask,
+                        const TL* __restrict__ labels, int ignore_label, unsigned long long* __restrict__ hist) {
+    extern __shared__ unsigned int s_hist[];
+    if (hist) {
+        for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_hist[i] = 0u;
+        __syncthreads();
+    }
+    const int n = blockIdx.y;
+    const float* base = probs + static_cast<long long>(n) * C * HW;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < HW;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float best = __ldg(base + i);
+        int arg = 0;
+        for (int c = 1; c < C; ++c) {
+            const float v = __ldg(base + c * HW + i);
+            if (v > best) {
+                best = v;
+                arg = c;
+            }
+        }
+        const long long o = static_cast<long long>(n) * HW + i;
+        if (mask) mask[o] = static_cast<uint8_t>(arg);
+        if (hist) {
+            const long long lb = static_cast<long long>(labels[o]);
+            if (lb != ignore_label) {
+                const int lc = static_cast<int>(min(max(lb, 0LL), static_cast<long long>(C - 1)));
+                atomicAdd(&s_hist[arg * C + lc], 1u);
+            }
+        }
+    }
+    if (hist) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+            if (s_hist[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(s_hist[i]));
+    }
+}
+
 }  // namespace
+
+extern "C" int cabinet_upsample_softmax_accum(const float* x, const float* x_flip, int N, int IH, int IW, int C, int OH,
+                                              int OW, float* prob, long long stride_n, long long stride_c,
+                                              long long stride_row, int dst_y0, int dst_x0, int dst_h, int dst_w,
+                                              const float* weight_y, const float* weight_x, float weight,
+                                              cabinet_stream_t stream) {
+    CAB_REQUIRE(x && prob && IH > 0 && IW > 0 && OH > 0 && OW > 0 && C > 0 && dst_h > 0 && dst_w > 0,
+                "upsample_softmax_accum: bad arguments");
+    CAB_REQUIRE(OH <= 65535 && N <= 65535, "upsample_softmax_accum: OH/N exceed grid limits");
+    if (N == 0) return CABINET_OK;
+    const float sh = static_cast<float>(IH) / static_cast<float>(OH), sw = static_cast<float>(IW) / static_cast<float>(OW);
+    const bool exact8 = OH == 8 * IH && OW == 8 * IW;
+    const int groups = (OW + PXG - 1) / PXG;
+    dim3 grid((groups + 127) / 128, OH, N);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (exact8)
+        upsample_softmax_accum_kernel<true><<<grid, 128, 0, s>>>(x, x_flip, IH, IW, C, OH, OW, sh, sw, prob, stride_n,
+                                                                 stride_c, stride_row, dst_y0, dst_x0, dst_h, dst_w,
+                                                                 weight_y, weight_x, weight);
+    else
+        upsample_softmax_accum_kernel<false><<<grid, 128, 0, s>>>(x, x_flip, IH, IW, C, OH, OW, sh, sw, prob, stride_n,
+                                                                  stride_c, stride_row, dst_y0, dst_x0, dst_h, dst_w,
+                                                                  weight_y, weight_x, weight);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_prob_resize_accum(const float* src, int N, int C, int src_h, int src_w, int crop_y0, int crop_x0,
+                                         int crop_h, int crop_w, float* dst, int H, int W, cabinet_stream_t stream) {
+    CAB_REQUIRE(src && dst && C > 0 && crop_h > 0 && crop_w > 0 && H > 0 && W > 0 && crop_y0 >= 0 && crop_x0 >= 0 &&
+                    crop_y0 + crop_h <= src_h && crop_x0 + crop_w <= src_w,
+                "prob_resize_accum: bad arguments");
+    CAB_REQUIRE(H <= 65535 && N <= 65535, "prob_resize_accum: H/N exceed grid limits");
+    if (N == 0) return CABINET_OK;
+    const float sh = static_cast<float>(crop_h) / static_cast<float>(H), sw = static_cast<float>(crop_w) / static_cast<float>(W);
+    dim3 grid((W + 255) / 256, H, N);
+    prob_resize_accum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, C, src_h, src_w, crop_y0, crop_x0,
+                                                                                 crop_h, crop_w, dst, H, W, sh, sw);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_argmax_hist_nchw(const float* probs, int N, int C, long long HW, uint8_t* mask,
+                                        const void* labels, int label_dtype, int ignore_label, long long* hist,
+                                        cabinet_stream_t stream) {
+    CAB_REQUIRE(probs && (mask || hist) && C > 0 && C <= 255 && HW > 0, "argmax_hist_nchw: bad arguments (1 <= C <= 255)");
+    CAB_REQUIRE(!hist || labels, "argmax_hist_nchw: hist requested without labels");
+    CAB_REQUIRE(C * C * sizeof(unsigned) <= 48 * 1024, "argmax_hist_nchw: C*C histogram does not fit shared memory");
+    CAB_REQUIRE(N <= 65535, "argmax_hist_nchw: N exceeds grid limits");
+    if (N == 0) return CABINET_OK;
+    dim3 grid(static_cast<unsigned>(std::min<long long>(cab_ceil_div(HW, 256 * 4), 148 * 16)), N);
+    const size_t smem = hist ? sizeof(unsigned) * C * C : 0;
+    auto* h = reinterpret_cast<unsigned long long*>(hist);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (label_dtype == 0)
+        argmax_hist_nchw_kernel<long long><<<grid, 256, smem, s>>>(probs, C, HW, mask, reinterpret_cast<const long long*>(labels),
+                                                                   ignore_label, h);
+    else
+        argmax_hist_nchw_kernel<uint8_t><<<grid, 256, smem, s>>>(probs, C, HW, mask, reinterpret_cast<const uint8_t*>(labels),
+                                                                 ignore_label, h);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
 
 extern "C" int cabinet_normalize_u8(const uint8_t* x, float* y, int N, int H, int W, float mean0, float mean1,
                                     float mean2, float std0, float std1, float std2, cabinet_stream_t stream) {

@@ -460,8 +460,12 @@ class Engine:
                   out.dt, x.N, x.H, x.W, x.C, out.H, out.W, self.stream)
 
     # ------------------------------------------------------------------ the forward schedule
-    def _trunk(self, x: torch.Tensor):
-        """Everything up to the two fp32 class-logit maps: (final8 [N,H/8,W/8,C], aux8 [N,H/8,W/8,C])."""
+    def _trunk(self, x: torch.Tensor, need_aux: bool = True):
+        """Everything up to the two fp32 class-logit maps: (final8 [N,H/8,W/8,C], aux8 [N,H/8,W/8,C]).
+
+        ``need_aux=False`` (mask / confusion-matrix / probability callers, which only read ``model(x)[0]``,
+        evaluate.py:76-78): the auxiliary head ``b1 -> b4 -> x4 upsample`` (cabinet.py:88-93,234-239) is not launched
+        and ``aux8`` is None -- it feeds nothing but the second output."""
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
         if x.device != self.dev:
@@ -616,15 +620,20 @@ class Engine:
         es = feat.t.element_size()
         self._run("cab_combine", "cab", 2 * N * h32 * w32 * 256 * es, 0, self.lib.cabinet_cab_combine, g.ptr, feat.ptr,
                   r.ptr, feat2.ptr, feat2.ld, self.gamma.data_ptr(), self.dt, N * h32 * w32, 256, self.stream)
-        aux8 = self.new(N, H8, W8, C, torch.float32)
-        with self._branch(0) as joined:  # low-level path (convb + x4 upsample into the FFM concat) beside b1 / b4
+        aux8 = high = None
+        if need_aux or self.debug:
+            aux8 = self.new(N, H8, W8, C, torch.float32)
+            with self._branch(0) as joined:  # low-level path (convb + x4 upsample into the FFM concat) beside b1 / b4
+                low = self.conv(feat2, self.convb)
+                self.bilinear(low, cat_ffm.slice(128, 256), "low_up")   # 1/32 -> 1/8 (reference: cabinet.py:228-233)
+                joined(low.t)
+            fused = self.conv(cat_b1, self.b1)
+            high = self.conv(fused, self.b4, out_dtype=torch.float32)  # class logits stay fp32
+            self.bilinear(high, aux8, "high_up")
+            self._join(0)
+        else:
             low = self.conv(feat2, self.convb)
-            self.bilinear(low, cat_ffm.slice(128, 256), "low_up")   # 1/32 -> 1/8 (reference: cabinet.py:228-233)
-            joined(low.t)
-        fused = self.conv(cat_b1, self.b1)
-        high = self.conv(fused, self.b4, out_dtype=torch.float32)  # class logits stay fp32
-        self.bilinear(high, aux8, "high_up")
-        self._join(0)
+            self.bilinear(low, cat_ffm.slice(128, 256), "low_up")
 
         # ---- feature fusion (reference: cabinet.py:142-153)
         self._join(2)
@@ -790,8 +799,23 @@ class Engine:
         N, _, H, W = x.shape
         if N == 0:
             return torch.empty((0, H, W), dtype=torch.uint8, device=self.dev)
-        final8, _ = self._trunk(x)
+        final8, _ = self._trunk(x, need_aux=False)
         return self._argmax(final8, N, H, W)
+
+    @torch.no_grad()
+    def class_map8(self, x):
+        """(N,3,H,W) -> fp32 NHWC class map (N, H/8, W/8, C): ``conv_out(feat_fuse)`` before the final x8 bilinear
+        (reference: cabinet.py:236-243).  What the evaluator's fused softmax / accumulate tail consumes; the auxiliary
+        head is not computed.  A repeated input buffer (the evaluator's chip slots) is captured into a CUDA graph; the
+        returned tensor is then that graph's output buffer (overwritten by the next call with the same input buffer)."""
+        N, _, H, W = x.shape
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+
+        def run():
+            return self._trunk(x, need_aux=False)[0].t
+
+        return self._graphed(("cls8", tuple(x.shape), x.data_ptr()), run)
 
     @torch.no_grad()
     def forward_hist(self, x, labels, hist, ignore_label=255):
@@ -810,7 +834,7 @@ class Engine:
             x = x.float().contiguous()
 
         def run():
-            final8, _ = self._trunk(x)
+            final8, _ = self._trunk(x, need_aux=False)
             return self._argmax(final8, N, H, W, labels, hist, ignore_label)
 
         # static buffers (an evaluator's double-buffered device tensors) -> captured once, replayed afterwards

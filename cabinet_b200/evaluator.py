@@ -5,8 +5,13 @@ Same constructor and result dict.  Differences, all on the hot-path side of the 
     CPU and ships an int64 mask over PCIe per image); counts are integers < 2^53 so the values are identical;
   * the fast mode (``scales=(1.0,)``, ``flip=False``, image not larger than the crop) is ONE fused call per batch:
     forward -> bilinear x8 -> argmax -> ``hist[pred, label]`` (``CABiNet.accumulate_hist``), logits never reach HBM;
-  * the general mode (multi-scale / flip / sliding window) follows the reference step by step on the device and
-    finishes with the ``cabinet_confusion_hist`` kernel;
+  * the general mode (multi-scale / flip / sliding window) keeps the reference's control flow (pad, window grid,
+    scales) on the host and runs its arithmetic as three kernels on fp32 NCHW probability accumulators: per chip
+    ``cabinet_upsample_softmax_accum`` (x8 upsample of the 1/8 class map + softmax + flip average + overlap-count
+    weight + window add; full-resolution logits never exist), per scale ``cabinet_prob_resize_accum`` (un-pad +
+    resize back + sum over scales; also used to rescale the input), per batch ``cabinet_argmax_hist_nchw`` (argmax +
+    confusion matrix).  A model without ``class_map8`` (any ``nn.Module`` returning logits) takes the reference's
+    steps as torch ops on the device and shares the last kernel;
   * under ``torch.distributed`` every rank evaluates its own shard of the loader and the histograms are
     all-reduced once (the reference: ``dist.reduce(dst=0)``, ``evaluate.py:230-235``); every rank gets the result.
 """
@@ -116,15 +121,103 @@ class MscEvalV0:
         scaled = F.interpolate(image, [int(H * scale), int(W * scale)], mode="bilinear", align_corners=False)
         return F.interpolate(self.crop_eval(scaled), (H, W), mode="bilinear", align_corners=False)
 
-    def _hist_from_preds(self, preds, labels, hist):
+    def _hist_from_probs(self, probs, labels, hist):
+        """argmax over the class planes + ``hist[pred, label]`` in one kernel (reference: evaluate.py:222-228)."""
         from . import _lib
 
-        lib = _lib.load()
-        preds, labels = preds.contiguous(), labels.contiguous()
-        _lib.check(lib.cabinet_confusion_hist(preds.data_ptr(), 0 if preds.dtype == torch.int64 else 1, labels.data_ptr(),
-                                              0 if labels.dtype == torch.int64 else 1, preds.numel(), self.n_classes,
-                                              self.ignore_label, hist.data_ptr(),
-                                              torch.cuda.current_stream(hist.device).cuda_stream), "confusion_hist")
+        probs, labels = probs.contiguous(), labels.contiguous()
+        N, C, H, W = probs.shape
+        _lib.check(_lib.load().cabinet_argmax_hist_nchw(probs.data_ptr(), N, C, H * W, None, labels.data_ptr(),
+                                                         0 if labels.dtype == torch.int64 else 1, self.ignore_label,
+                                                         hist.data_ptr(), torch.cuda.current_stream(hist.device).cuda_stream),
+                   "argmax_hist_nchw")
+
+    # ---- general mode on the fused kernels (models exposing the 1/8-resolution class map)
+    @staticmethod
+    def window_grid(full: int, cs: int):
+        """Window starts along one axis and the per-pixel 1/overlap-count (reference: evaluate.py:127-146,149)."""
+        stride = int(cs * EVAL_STRIDE_RATE)
+        starts = [min(full, stride * i + cs) - cs for i in range(math.ceil((full - cs) / stride) + 1)]
+        count = np.zeros(full, dtype=np.float32)
+        for s0 in starts:
+            count[s0:s0 + cs] += 1
+        return starts, (1.0 / np.maximum(count, 1)).astype(np.float32)
+
+    def _resize_accum(self, src, crop, dst):
+        """dst (N,C,H,W) += bilinear(src[:, :, y0:y0+h, x0:x0+w] -> (H, W)), align_corners=False."""
+        from . import _lib
+
+        N, C, SH, SW = src.shape
+        _lib.check(_lib.load().cabinet_prob_resize_accum(src.data_ptr(), N, C, SH, SW, crop[0], crop[1], crop[2], crop[3],
+                                                          dst.data_ptr(), dst.shape[2], dst.shape[3],
+                                                          torch.cuda.current_stream(dst.device).cuda_stream),
+                   "prob_resize_accum")
+
+    def _crop_eval_into(self, image, dst):
+        """crop_eval (reference: evaluate.py:89-159) accumulating the normalised, un-padded probability map of
+        ``image`` (N,3,H,W) into ``dst`` (N,C,H,W) fp32: one class-map forward (two with flip) + one fused kernel per
+        window."""
+        from . import _lib
+
+        lib, cs = _lib.load(), self.cropsize
+        N, _, H, W = image.shape
+        hst = wst = 0
+        if H < cs or W < cs:  # centre zero-pad (reference: evaluate.py:60-72,102-111)
+            tgt = (cs, cs) if max(H, W) < cs else (cs if H < W else H, cs if W < H else W)
+            ph, pw = max(tgt[0] - H, 0), max(tgt[1] - W, 0)
+            hst, wst = ph // 2, pw // 2
+            padded = torch.zeros(N, 3, tgt[0], tgt[1], device=image.device)
+            padded[:, :, hst:hst + H, wst:wst + W] = image
+            image = padded
+        fh, fw = image.shape[2:]
+        if fh < cs or fw < cs:  # unreachable after padding, kept for parity with evaluate.py:121-124
+            ys, xs, ch, cw = [0], [0], fh, fw
+            inv_y = inv_x = None
+        else:
+            key = (fh, fw, cs, image.device)
+            cache = self.__dict__.setdefault("_grids", {})
+            if key not in cache:
+                (ys, iy), (xs, ix) = self.window_grid(fh, cs), self.window_grid(fw, cs)
+                cache[key] = (ys, xs, torch.from_numpy(iy).to(image.device), torch.from_numpy(ix).to(image.device))
+            ys, xs, inv_y, inv_x = cache[key]
+            ch = cw = cs
+        slots = self.__dict__.setdefault("_chips", {})
+        skey = (N, ch, cw, image.device)
+        if skey not in slots:  # static chip buffers: the class-map forward of a repeated buffer is a CUDA graph replay
+            slots[skey] = [torch.empty((N, 3, ch, cw), device=image.device) for _ in range(2)]
+        chip, chip_f = slots[skey]
+        stream = torch.cuda.current_stream(image.device).cuda_stream
+        C = self.n_classes
+        for y0 in ys:
+            for x0 in xs:
+                view = image[:, :, y0:y0 + ch, x0:x0 + cw]
+                chip.copy_(view)
+                m = self.model.class_map8(chip)
+                mf = None
+                if self.flip:
+                    chip_f.copy_(torch.flip(view, dims=(3,)))
+                    mf = self.model.class_map8(chip_f)
+                _lib.check(lib.cabinet_upsample_softmax_accum(
+                    m.data_ptr(), mf.data_ptr() if mf is not None else None, N, m.shape[1], m.shape[2], C, ch, cw,
+                    dst.data_ptr(), dst.stride(0), dst.stride(1), dst.stride(2), y0 - hst, x0 - wst, H, W,
+                    inv_y[y0:].data_ptr() if inv_y is not None else None,
+                    inv_x[x0:].data_ptr() if inv_x is not None else None, 1.0, stream), "upsample_softmax_accum")
+
+    def _probs_fused(self, images):
+        """sum over scales of scale_crop_eval (reference: evaluate.py:149-159,216-220) -> (N,C,H,W) fp32."""
+        N, _, H, W = images.shape
+        probs = torch.zeros((N, self.n_classes, H, W), device=images.device)
+        for s in self.scales:
+            hs, ws = int(H * s), int(W * s)
+            if (hs, ws) == (H, W):  # F.interpolate to the same size is the identity
+                self._crop_eval_into(images, probs)
+                continue
+            scaled = torch.zeros((N, 3, hs, ws), device=images.device)
+            self._resize_accum(images, (0, 0, H, W), scaled)
+            ps = torch.zeros((N, self.n_classes, hs, ws), device=images.device)
+            self._crop_eval_into(scaled, ps)
+            self._resize_accum(ps, (0, 0, hs, ws), probs)
+        return probs
 
     def _fast_pipelined(self, dev, hist, masks_out=None):
         """Fast mode over the whole loader with host->device copies one batch ahead of the fused forward.
@@ -213,10 +306,15 @@ class MscEvalV0:
             if fast and H == self.cropsize and W == self.cropsize:  # one chip == the image: argmax(softmax) == argmax
                 self.model.accumulate_hist(images.float().contiguous(), labels.contiguous(), hist, self.ignore_label)
                 continue
-            probs = torch.zeros((images.size(0), self.n_classes, H, W), device=dev)
-            for s in self.scales:
-                probs += self.scale_crop_eval(images.float(), s)
-            self._hist_from_preds(torch.argmax(probs, dim=1), labels, hist)
+            if images.size(0) == 0:
+                continue
+            if hasattr(self.model, "class_map8") and getattr(self, "fused_general", True):
+                probs = self._probs_fused(images.float().contiguous())
+            else:  # any other nn.Module: the reference's steps as device tensor ops
+                probs = torch.zeros((images.size(0), self.n_classes, H, W), device=dev)
+                for s in self.scales:
+                    probs += self.scale_crop_eval(images.float(), s)
+            self._hist_from_probs(probs, labels, hist)
         reduce_hist(hist)
         return metrics_from_hist(hist)
 

@@ -357,6 +357,15 @@ class CABiNet(nn.Module):
         self._check_input(x)
         return self.engine().forward_hist(x, labels, hist, ignore_label)
 
+    @torch.no_grad()
+    def class_map8(self, x: torch.Tensor) -> torch.Tensor:
+        """(N,3,H,W) -> fp32 NHWC (N, H/8, W/8, n_classes) class map of the head, i.e. ``final_logit`` before its
+        x8 bilinear upsample (reference: cabinet.py:236-243).  Input of ``cabinet_upsample_softmax_accum``."""
+        self._check_input(x)
+        if x.shape[0] == 0:
+            raise ValueError("class_map8 needs a non-empty batch")
+        return self.engine().class_map8(x)
+
     # ------------------------------------------------------------------ optimizer surface
     def get_params(self):
         """(wd, nowd, lr_mul_wd, lr_mul_nowd) with ``ab / ffm / conv_out`` as the x10-LR decoder.

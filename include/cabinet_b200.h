@@ -246,6 +246,29 @@ int cabinet_normalize_u8(const uint8_t* x, float* y, int N, int H, int W, float 
 int cabinet_confusion_hist(const void* pred, int pred_dtype, const void* labels, int label_dtype, long long n_pixels,
                            int C, int ignore_label, long long* hist, cabinet_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Evaluator tail (MscEvalV0, src/scripts/evaluate.py:74-159,216-228) on fp32 NCHW probability accumulators.
+ *
+ * _upsample_softmax_accum: eval_chip + the window accumulation of crop_eval (evaluate.py:74-87,139-146) for one chip:
+ *   prob[n][c][dst_y0+oh][dst_x0+ow] += weight * weight_y[oh] * weight_x[ow] * P[n][c][oh][ow],
+ *   P = softmax_c(bilinear(x -> OH x OW)), or with x_flip != NULL the mean of that and the mirrored softmax of the
+ *   upsampled class map of the horizontally flipped chip (flip TTA).  x, x_flip: fp32 NHWC class maps [N][IH][IW][C]
+ *   (the 1/8-resolution output of the head, src/models/cabinet.py:236-243); prob: plane strides in floats; chip
+ *   pixels whose destination falls outside [0,dst_h) x [0,dst_w) are dropped (the un-pad crop, evaluate.py:152-156);
+ *   weight_y [OH] / weight_x [OW] (NULL = 1) carry 1 / overlap count of the window's rows / columns (the count map of
+ *   a window grid is the outer product of per-axis counts, evaluate.py:149-150).
+ * _prob_resize_accum: dst[n][c] += bilinear(src[n][c][crop] -> H x W), align_corners=False (evaluate.py:157-158,218).
+ * _argmax_hist_nchw: uint8 mask = argmax_c probs (first maximum wins) and / or hist[pred*C + label] += 1 for labels !=
+ *   ignore_label, labels int64 (label_dtype 0) or uint8 (1), clipped to [0, C-1] (evaluate.py:222-228,162-191). */
+int cabinet_upsample_softmax_accum(const float* x, const float* x_flip, int N, int IH, int IW, int C, int OH, int OW,
+                                   float* prob, long long stride_n, long long stride_c, long long stride_row,
+                                   int dst_y0, int dst_x0, int dst_h, int dst_w, const float* weight_y,
+                                   const float* weight_x, float weight, cabinet_stream_t stream);
+int cabinet_prob_resize_accum(const float* src, int N, int C, int src_h, int src_w, int crop_y0, int crop_x0,
+                              int crop_h, int crop_w, float* dst, int H, int W, cabinet_stream_t stream);
+int cabinet_argmax_hist_nchw(const float* probs, int N, int C, long long HW, uint8_t* mask, const void* labels,
+                             int label_dtype, int ignore_label, long long* hist, cabinet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -653,3 +653,96 @@ def test_conv_tc_split_act():
     got = from_map(ym)
     assert rel_l2(got, ref) < 6e-3
     assert float(got[:, :64].min()) >= 0 and float(got[:, 64:].min()) < 0
+
+
+# ------------------------------------------------------------------ evaluator tail kernels (MscEvalV0 general mode)
+@pytest.mark.parametrize("N,IH,IW,C,OH,OW,flip,dy0,dx0,dh,dw,weights", [
+    (2, 8, 8, 8, 64, 64, False, 0, 0, 64, 64, False),      # exact x8, whole window
+    (2, 8, 16, 8, 64, 128, True, 5, 3, 80, 140, True),     # exact x8 + flip TTA + unaligned window + overlap weights
+    (1, 8, 8, 19, 64, 64, True, -7, -9, 50, 48, True),     # C % 4 != 0, padded chip: destination clipped on all sides
+    (2, 5, 7, 4, 37, 53, False, 2, 1, 40, 60, True),       # generic bilinear, OW % 8 != 0
+    (1, 5, 7, 5, 37, 53, True, -3, 0, 30, 50, True),       # generic + flip (per-pixel mirrored path) + clipping
+    (1, 6, 9, 8, 44, 72, True, 0, 4, 44, 80, False),       # generic rows, OW % 8 == 0: mirrored group path
+])
+def test_upsample_softmax_accum(N, IH, IW, C, OH, OW, flip, dy0, dx0, dh, dw, weights):
+    """eval_chip + window accumulation (reference: evaluate.py:74-87,139-146) against torch fp32 on the CPU."""
+    lib = _lib.load()
+    x = gen(N, IH, IW, C, seed=1, scale=2.0)
+    xf = gen(N, IH, IW, C, seed=2, scale=2.0) if flip else None
+    prob0 = torch.rand(N, C, dh, dw, generator=torch.Generator().manual_seed(3))
+    wy = 1.0 / torch.randint(1, 4, (OH,), generator=torch.Generator().manual_seed(4)).float() if weights else None
+    wx = 1.0 / torch.randint(1, 4, (OW,), generator=torch.Generator().manual_seed(5)).float() if weights else None
+    up = lambda t: F.interpolate(t.permute(0, 3, 1, 2), (OH, OW), mode="bilinear", align_corners=False)  # noqa: E731
+    p = F.softmax(up(x), dim=1)
+    if flip:
+        p = (p + F.softmax(torch.flip(up(xf), dims=(3,)), dim=1)) * 0.5
+    if weights:
+        p = p * wy.view(1, 1, OH, 1) * wx.view(1, 1, 1, OW)
+    want = prob0.clone()
+    ys = [y for y in range(OH) if 0 <= dy0 + y < dh]
+    xs = [c for c in range(OW) if 0 <= dx0 + c < dw]
+    want[:, :, dy0 + ys[0]:dy0 + ys[-1] + 1, dx0 + xs[0]:dx0 + xs[-1] + 1] += 0.75 * p[:, :, ys[0]:ys[-1] + 1, xs[0]:xs[-1] + 1]
+    xd, pd = x.cuda(), prob0.cuda()
+    xfd = xf.cuda() if flip else None
+    wyd, wxd = (wy.cuda(), wx.cuda()) if weights else (None, None)
+    check(lib.cabinet_upsample_softmax_accum(xd.data_ptr(), xfd.data_ptr() if flip else None, N, IH, IW, C, OH, OW,
+                                             pd.data_ptr(), pd.stride(0), pd.stride(1), pd.stride(2), dy0, dx0, dh, dw,
+                                             wyd.data_ptr() if weights else None, wxd.data_ptr() if weights else None,
+                                             0.75, stream()), "softmax_accum")
+    torch.cuda.synchronize()
+    got = pd.cpu()
+    assert rel_l2(got - prob0, want - prob0) < 2e-5
+    assert float((got - want).abs().max()) < 2e-5
+    untouched = torch.ones(dh, dw, dtype=torch.bool)
+    untouched[dy0 + ys[0]:dy0 + ys[-1] + 1, dx0 + xs[0]:dx0 + xs[-1] + 1] = False
+    assert torch.equal(got[:, :, untouched], prob0[:, :, untouched])  # nothing outside the window is written
+
+
+@pytest.mark.parametrize("N,C,SH,SW,crop,H,W", [
+    (2, 3, 40, 56, (0, 0, 40, 56), 80, 112),     # x2 up (input rescale of the 2.0 scale)
+    (1, 8, 48, 64, (4, 6, 36, 45), 72, 90),      # un-pad crop + resize back
+    (2, 5, 33, 47, (0, 0, 33, 47), 22, 31),      # down
+    (1, 4, 20, 24, (0, 0, 20, 24), 20, 24),      # identity
+])
+def test_prob_resize_accum(N, C, SH, SW, crop, H, W):
+    """un-pad + F.interpolate back + `probs +=` (reference: evaluate.py:152-158,218) against torch on the CPU."""
+    lib = _lib.load()
+    src = gen(N, C, SH, SW, seed=6)
+    dst0 = gen(N, C, H, W, seed=7)
+    y0, x0, ch, cw = crop
+    want = dst0 + F.interpolate(src[:, :, y0:y0 + ch, x0:x0 + cw], (H, W), mode="bilinear", align_corners=False)
+    sd, dd = src.cuda(), dst0.cuda()
+    check(lib.cabinet_prob_resize_accum(sd.data_ptr(), N, C, SH, SW, y0, x0, ch, cw, dd.data_ptr(), H, W, stream()), "resize")
+    torch.cuda.synchronize()
+    assert float((dd.cpu() - want).abs().max()) < 1e-5
+    with pytest.raises(ValueError):
+        check(lib.cabinet_prob_resize_accum(sd.data_ptr(), N, C, SH, SW, y0, x0, SH + 1, cw, dd.data_ptr(), H, W, stream()), "resize")
+
+
+@pytest.mark.parametrize("C,H,W", [(8, 37, 53), (19, 64, 64), (1, 5, 5)])
+def test_argmax_hist_nchw(C, H, W):
+    """torch.argmax(probs, 1) + compute_hist (reference: evaluate.py:222-228,162-191): bit-exact."""
+    from oracle.evaluator_oracle import compute_hist
+
+    lib = _lib.load()
+    N = 3
+    probs = torch.rand(N, C, H, W, generator=torch.Generator().manual_seed(8))
+    probs[:, :, ::3, ::5] = 0.25  # ties: the first maximum must win
+    labels = torch.randint(0, C + 2, (N, H, W), generator=torch.Generator().manual_seed(9))
+    labels[:, H // 2, :] = 255
+    want = torch.argmax(probs, dim=1)
+    h = sum(compute_hist(want[i].numpy(), labels[i].numpy(), C, 255) for i in range(N))
+    pd = probs.cuda()
+    for ldt, lab in ((0, labels.cuda()), (1, labels.to(torch.uint8).cuda())):
+        mask = torch.full((N, H, W), 77, dtype=torch.uint8, device="cuda")
+        hist = torch.zeros(C, C, dtype=torch.int64, device="cuda")
+        check(lib.cabinet_argmax_hist_nchw(pd.data_ptr(), N, C, H * W, mask.data_ptr(), lab.data_ptr(), ldt, 255,
+                                           hist.data_ptr(), stream()), "argmax_hist")
+        torch.cuda.synchronize()
+        assert torch.equal(mask.cpu().long(), want)
+        np.testing.assert_array_equal(hist.cpu().numpy(), h)
+    hist = torch.zeros(C, C, dtype=torch.int64, device="cuda")
+    check(lib.cabinet_argmax_hist_nchw(pd.data_ptr(), N, C, H * W, None, labels.cuda().data_ptr(), 0, 255,
+                                       hist.data_ptr(), stream()), "argmax_hist")  # hist only
+    np.testing.assert_array_equal(hist.cpu().numpy(), h)
+    check(lib.cabinet_argmax_hist_nchw(pd.data_ptr(), 0, C, H * W, None, 1, 0, 255, hist.data_ptr(), stream()), "empty")
