@@ -181,22 +181,30 @@ class MscEvalV0:
                 cache[key] = (ys, xs, torch.from_numpy(iy).to(image.device), torch.from_numpy(ix).to(image.device))
             ys, xs, inv_y, inv_x = cache[key]
             ch = cw = cs
+        # chips of one image batch are independent forwards: run several windows (and their flipped copies) as ONE
+        # class-map forward of up to `max_chip_batch` images -- the low-resolution layers of the network are latency
+        # bound at small batches.  Static chip buffers per group size: a repeated buffer replays a captured CUDA graph.
+        wins = [(y0, x0) for y0 in ys for x0 in xs]
+        per_win = N * (2 if self.flip else 1)
+        group = max(1, getattr(self, "max_chip_batch", 32) // per_win)
         slots = self.__dict__.setdefault("_chips", {})
-        skey = (N, ch, cw, image.device)
-        if skey not in slots:  # static chip buffers: the class-map forward of a repeated buffer is a CUDA graph replay
-            slots[skey] = [torch.empty((N, 3, ch, cw), device=image.device) for _ in range(2)]
-        chip, chip_f = slots[skey]
         stream = torch.cuda.current_stream(image.device).cuda_stream
         C = self.n_classes
-        for y0 in ys:
-            for x0 in xs:
+        for g0 in range(0, len(wins), group):
+            gw = wins[g0:g0 + group]
+            skey = (len(gw) * per_win, ch, cw, image.device)
+            if skey not in slots:
+                slots[skey] = torch.empty((len(gw) * per_win, 3, ch, cw), device=image.device)
+            chips = slots[skey]
+            for i, (y0, x0) in enumerate(gw):
                 view = image[:, :, y0:y0 + ch, x0:x0 + cw]
-                chip.copy_(view)
-                m = self.model.class_map8(chip)
-                mf = None
+                chips[i * per_win:i * per_win + N].copy_(view)
                 if self.flip:
-                    chip_f.copy_(torch.flip(view, dims=(3,)))
-                    mf = self.model.class_map8(chip_f)
+                    chips[i * per_win + N:(i + 1) * per_win].copy_(torch.flip(view, dims=(3,)))
+            maps = self.model.class_map8(chips)  # (len(gw) * per_win, h8, w8, C) fp32
+            for i, (y0, x0) in enumerate(gw):
+                m = maps[i * per_win:i * per_win + N]
+                mf = maps[i * per_win + N:(i + 1) * per_win] if self.flip else None
                 _lib.check(lib.cabinet_upsample_softmax_accum(
                     m.data_ptr(), mf.data_ptr() if mf is not None else None, N, m.shape[1], m.shape[2], C, ch, cw,
                     dst.data_ptr(), dst.stride(0), dst.stride(1), dst.stride(2), y0 - hst, x0 - wst, H, W,
