@@ -228,14 +228,17 @@ class MscEvalV0:
         return probs
 
     def _fast_pipelined(self, dev, hist, masks_out=None):
-        """Fast mode over the whole loader with host->device copies one batch ahead of the fused forward.
+        """Fast mode over the whole loader with host->device copies ahead of the fused forward.
 
-        Two device buffer sets; a copy stream uploads batch i+1 while the compute stream runs batch i
-        (forward + x8 upsample + argmax + confusion matrix in one fused tail).  ``masks_out``: optional list that
-        receives a pinned uint8 host tensor per batch (asynchronous D2H, valid after the final synchronise)."""
+        A ring of device buffer sets; a copy stream uploads work item i+1.. while the compute stream runs item i
+        (forward + x8 upsample + argmax + confusion matrix in one fused tail).  fp32 host batches are PCIe-bound
+        (12.6 MB per 1024^2 image against ~0.17 ms of compute), so they are cut into chunks of ``self.chunk`` images
+        (default 8): the forward of a chunk starts as soon as ITS images have landed, and only the last chunk's
+        forward is not hidden behind an upload.  ``masks_out``: optional list that receives a pinned uint8 host tensor
+        per batch (asynchronous D2H, valid after the final synchronise)."""
         cur = torch.cuda.current_stream(dev)
-        st = self.__dict__.setdefault("_pipe", {"stream": torch.cuda.Stream(dev), "bufs": [None, None], "x32": None})
-        copy_stream, bufs, x32 = st["stream"], st["bufs"], st["x32"]  # device buffers persist across evaluate() calls
+        st = self.__dict__.setdefault("_pipe", {"stream": torch.cuda.Stream(dev), "bufs": {}, "x32": None})
+        copy_stream, ring, x32 = st["stream"], st["bufs"], st["x32"]  # device buffers persist across evaluate() calls
         # the fused forward + confusion-matrix call is replayed as a CUDA graph keyed by its buffer addresses: accumulate
         # into a persistent matrix (the caller's `hist` is a fresh allocation per evaluate(), which would force a
         # re-capture whenever the allocator hands out a different block -- it does under NCCL) and add it at the end
@@ -243,11 +246,9 @@ class MscEvalV0:
             st["hist"] = torch.zeros_like(hist)
         user_hist, hist = hist, st["hist"]
         hist.zero_()
-        ready, consumed = [torch.cuda.Event(), torch.cuda.Event()], [None, None]
         copy_stream.wait_stream(cur)
-        n_batches = 0
+        n_batches, item = 0, 0
         for i, (images, labels) in enumerate(self.dl):
-            b = i & 1
             if labels.dim() == 4:
                 labels = labels.squeeze(1)
             if labels.dtype not in (torch.int64, torch.uint8):
@@ -256,32 +257,51 @@ class MscEvalV0:
             H, W = images.shape[1:3] if u8 else images.shape[2:]
             if H != self.cropsize or W != self.cropsize:
                 raise ValueError("fast pipelined mode needs images of exactly cropsize x cropsize")
-            if bufs[b] is None or bufs[b][0].shape != images.shape or bufs[b][1].dtype != labels.dtype:
-                bufs[b] = (torch.empty(images.shape, dtype=images.dtype if u8 else torch.float32, device=dev),
-                           torch.empty(labels.shape, dtype=labels.dtype, device=dev))
-                if u8 and (x32 is None or tuple(x32.shape) != (images.shape[0], 3, H, W)):
-                    x32 = st["x32"] = torch.empty((images.shape[0], 3, H, W), dtype=torch.float32, device=dev)
-                # the caching allocator may hand out memory that kernels already queued on the compute stream
-                # still touch: order the copy stream after them, and tell the allocator about the second stream
-                copy_stream.wait_stream(cur)
-                for t in bufs[b]:
-                    t.record_stream(copy_stream)
-            with torch.cuda.stream(copy_stream):
-                if consumed[b] is not None:
-                    copy_stream.wait_event(consumed[b])  # the forward that last read this buffer set is done
-                bufs[b][0].copy_(images, non_blocking=True)
-                bufs[b][1].copy_(labels, non_blocking=True)
-                ready[b].record(copy_stream)
-            cur.wait_event(ready[b])
-            xin = normalize_u8(bufs[b][0], x32, *self.u8_mean_std) if u8 else bufs[b][0]
-            mask = self.model.accumulate_hist(xin, bufs[b][1], hist, self.ignore_label)
+            N = images.shape[0]
+            chunk = getattr(self, "chunk", 8)
+            if u8 or chunk <= 0 or N <= chunk:  # uint8 uploads are compute-bound: one forward per batch
+                chunk = max(N, 1)
+            host = None
             if masks_out is not None:
-                host = torch.empty(mask.shape, dtype=torch.uint8, pin_memory=True) if len(masks_out) <= i else masks_out[i]
-                host.copy_(mask, non_blocking=True)
+                host = torch.empty((N, H, W), dtype=torch.uint8, pin_memory=True) if len(masks_out) <= i else masks_out[i]
                 if len(masks_out) <= i:
                     masks_out.append(host)
-            consumed[b] = torch.cuda.Event()
-            consumed[b].record(cur)
+            for c0 in range(0, N, chunk):
+                im, lb = images[c0:c0 + chunk], labels[c0:c0 + chunk]
+                n = im.shape[0]
+                # ring of 2 (whole batches) or 4 (chunks) slots per work-item shape
+                rkey = (tuple(im.shape), im.dtype, lb.dtype)
+                slots = ring.get(rkey)
+                if slots is None:
+                    nslot = 2 if chunk >= N else 4
+                    slots = ring[rkey] = {"next": 0, "sets": [], "n": nslot}
+                    # the caching allocator may hand out memory that kernels already queued on the compute stream
+                    # still touch: order the copy stream after them, and tell the allocator about the second stream
+                    copy_stream.wait_stream(cur)
+                    for _ in range(nslot):
+                        bi = torch.empty(im.shape, dtype=im.dtype if u8 else torch.float32, device=dev)
+                        bl = torch.empty(lb.shape, dtype=lb.dtype, device=dev)
+                        bi.record_stream(copy_stream)
+                        bl.record_stream(copy_stream)
+                        slots["sets"].append({"img": bi, "lab": bl, "ready": torch.cuda.Event(), "consumed": None})
+                    if u8 and (x32 is None or tuple(x32.shape) != (n, 3, H, W)):
+                        x32 = st["x32"] = torch.empty((n, 3, H, W), dtype=torch.float32, device=dev)
+                slot = slots["sets"][slots["next"]]
+                slots["next"] = (slots["next"] + 1) % slots["n"]
+                with torch.cuda.stream(copy_stream):
+                    if slot["consumed"] is not None:
+                        copy_stream.wait_event(slot["consumed"])  # the forward that last read this buffer set is done
+                    slot["img"].copy_(im, non_blocking=True)
+                    slot["lab"].copy_(lb, non_blocking=True)
+                    slot["ready"].record(copy_stream)
+                cur.wait_event(slot["ready"])
+                xin = normalize_u8(slot["img"], x32, *self.u8_mean_std) if u8 else slot["img"]
+                mask = self.model.accumulate_hist(xin, slot["lab"], hist, self.ignore_label)
+                if host is not None:
+                    host[c0:c0 + n].copy_(mask, non_blocking=True)
+                slot["consumed"] = torch.cuda.Event()
+                slot["consumed"].record(cur)
+                item += 1
             n_batches += 1
         user_hist.add_(hist)
         return n_batches
