@@ -132,6 +132,31 @@ bilinear_x4_bf16_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restr
 //   v = top + wy * (bot - top),  top/bot = a + wx * (b - a).
 constexpr int PXG = 8;
 
+// exact x8: 8 output pixels [8g, 8g+8) of one row for classes [c4, c4+4) from the 6 source vectors around them
+__device__ __forceinline__ void exact8_chunk4(const float* __restrict__ r0, const float* __restrict__ r1, int xa, int xb,
+                                              int xc, int C, int c4, float wy, float (&v)[4][PXG]) {
+    const float4 ta = __ldg(reinterpret_cast<const float4*>(r0 + xa * C + c4));
+    const float4 tb = __ldg(reinterpret_cast<const float4*>(r0 + xb * C + c4));
+    const float4 tcc = __ldg(reinterpret_cast<const float4*>(r0 + xc * C + c4));
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(r1 + xa * C + c4));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(r1 + xb * C + c4));
+    const float4 bc = __ldg(reinterpret_cast<const float4*>(r1 + xc * C + c4));
+    const float tav[4] = {ta.x, ta.y, ta.z, ta.w}, tbv[4] = {tb.x, tb.y, tb.z, tb.w};
+    const float tcv[4] = {tcc.x, tcc.y, tcc.z, tcc.w}, bav[4] = {ba.x, ba.y, ba.z, ba.w};
+    const float bbv[4] = {bb.x, bb.y, bb.z, bb.w}, bcv[4] = {bc.x, bc.y, bc.z, bc.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float va = tav[k] + wy * (bav[k] - tav[k]), vb = tbv[k] + wy * (bbv[k] - tbv[k]);
+        const float vc = tcv[k] + wy * (bcv[k] - tcv[k]);
+        const float d0 = vb - va, d1 = vc - vb;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[k][j] = va + ((j + 4.5f) * 0.125f) * d0;
+            v[k][j + 4] = vb + ((j + 0.5f) * 0.125f) * d1;
+        }
+    }
+}
+
 template <bool EXACT8, typename Consumer>
 __device__ __forceinline__ void upsample_group8(const float* __restrict__ x, int n, int oh, int g, int IH, int IW,
                                                 int C, int OW, float sh, float sw, Consumer&& consume) {
@@ -146,28 +171,10 @@ __device__ __forceinline__ void upsample_group8(const float* __restrict__ x, int
         if ((C & 3) == 0) {  // 4 classes per 16-byte load: 6 loads feed 32 outputs
             cstart = C;
             for (int c4 = 0; c4 < C; c4 += 4) {
-                const float4 ta = __ldg(reinterpret_cast<const float4*>(r0 + xa * C + c4));
-                const float4 tb = __ldg(reinterpret_cast<const float4*>(r0 + xb * C + c4));
-                const float4 tcc = __ldg(reinterpret_cast<const float4*>(r0 + xc * C + c4));
-                const float4 ba = __ldg(reinterpret_cast<const float4*>(r1 + xa * C + c4));
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(r1 + xb * C + c4));
-                const float4 bc = __ldg(reinterpret_cast<const float4*>(r1 + xc * C + c4));
-                const float tav[4] = {ta.x, ta.y, ta.z, ta.w}, tbv[4] = {tb.x, tb.y, tb.z, tb.w};
-                const float tcv[4] = {tcc.x, tcc.y, tcc.z, tcc.w}, bav[4] = {ba.x, ba.y, ba.z, ba.w};
-                const float bbv[4] = {bb.x, bb.y, bb.z, bb.w}, bcv[4] = {bc.x, bc.y, bc.z, bc.w};
+                float v[4][PXG];
+                exact8_chunk4(r0, r1, xa, xb, xc, C, c4, wy, v);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float va = tav[k] + wy * (bav[k] - tav[k]), vb = tbv[k] + wy * (bbv[k] - tbv[k]);
-                    const float vc = tcv[k] + wy * (bcv[k] - tcv[k]);
-                    const float d0 = vb - va, d1 = vc - vb;
-                    float v[PXG];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        v[j] = va + ((j + 4.5f) * 0.125f) * d0;
-                        v[j + 4] = vb + ((j + 0.5f) * 0.125f) * d1;
-                    }
-                    consume(c4 + k, v);
-                }
+                for (int k = 0; k < 4; ++k) consume(c4 + k, v[k]);
             }
         }
         for (int c = cstart; c < C; ++c) {
@@ -411,6 +418,34 @@ upsample_softmax_accum_kernel(const float* __restrict__ x, const float* __restri
                 if (ow0 + p < OW && dx0 + ow0 + p >= 0 && dx0 + ow0 + p < dw) o[p] += pv[p];
         }
     };
+    if constexpr (EXACT8) {
+        if (xf && (C & 3) == 0) {
+            // both class maps per 4-class chunk, ONE read-modify-write of the window
+            int y0, y1;
+            float wyy;
+            cab_bilinear_tap(oh, sh, IH, y0, y1, wyy);
+            const float* r0 = x + (static_cast<long long>(n) * IH + y0) * IW * C;
+            const float* r1 = x + (static_cast<long long>(n) * IH + y1) * IW * C;
+            const float* q0 = xf + (static_cast<long long>(n) * IH + y0) * IW * C;
+            const float* q1 = xf + (static_cast<long long>(n) * IH + y1) * IW * C;
+            const int xa = max(g - 1, 0), xc = min(g + 1, IW - 1), fa = max(gf - 1, 0), fc = min(gf + 1, IW - 1);
+            for (int c4 = 0; c4 < C; c4 += 4) {
+                float v[4][PXG], vf[4][PXG];
+                exact8_chunk4(r0, r1, xa, g, xc, C, c4, wyy, v);
+                exact8_chunk4(q0, q1, fa, gf, fc, C, c4, wyy, vf);
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    float pv[PXG];
+#pragma unroll
+                    for (int p = 0; p < PXG; ++p)
+                        pv[p] = __expf(v[k4][p] - m[p]) * k[p] +
+                                __expf(vf[k4][PXG - 1 - p] - mf[PXG - 1 - p]) * kf[PXG - 1 - p];
+                    emit(c4 + k4, pv);
+                }
+            }
+            return;
+        }
+    }
     if (!xf) {
         upsample_group8<EXACT8>(x, n, oh, g, IH, IW, C, OW, sh, sw, [&](int c, const float* v) {
             float pv[PXG];
@@ -481,25 +516,41 @@ upsample_softmax_accum_kernel(const float* __restrict__ x, const float* __restri
 __global__ void __launch_bounds__(256)
 prob_resize_accum_kernel(const float* __restrict__ src, int C, int SH, int SW, int cy0, int cx0, int ch, int cw,
                          float* __restrict__ dst, int H, int W, float sh, float sw) {
-    const int xo = blockIdx.x * blockDim.x + threadIdx.x;
-    if (xo >= W) return;
+    // thread = 4 consecutive output pixels of one row, all classes: taps once, one 16-byte read-modify-write per class
+    const int xq = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (xq >= W) return;
     const int yo = blockIdx.y, n = blockIdx.z;
-    int y0, y1, x0, x1;
-    float wy, wx;
+    int y0, y1, x0[4], x1[4];
+    float wy, wx[4];
     cab_bilinear_tap(yo, sh, ch, y0, y1, wy);
-    cab_bilinear_tap(xo, sw, cw, x0, x1, wx);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) cab_bilinear_tap(min(xq + p, W - 1), sw, cw, x0[p], x1[p], wx[p]);
     const long long plane_s = static_cast<long long>(SH) * SW, plane_d = static_cast<long long>(H) * W;
-    const float* s = src + static_cast<long long>(n) * C * plane_s;
-    float* d = dst + static_cast<long long>(n) * C * plane_d + static_cast<long long>(yo) * W + xo;
-    const long long o00 = static_cast<long long>(cy0 + y0) * SW + cx0 + x0, o01 = static_cast<long long>(cy0 + y0) * SW + cx0 + x1;
-    const long long o10 = static_cast<long long>(cy0 + y1) * SW + cx0 + x0, o11 = static_cast<long long>(cy0 + y1) * SW + cx0 + x1;
+    const float* s0 = src + static_cast<long long>(n) * C * plane_s + static_cast<long long>(cy0 + y0) * SW + cx0;
+    const float* s1 = src + static_cast<long long>(n) * C * plane_s + static_cast<long long>(cy0 + y1) * SW + cx0;
+    float* d = dst + static_cast<long long>(n) * C * plane_d + static_cast<long long>(yo) * W + xq;
+    const bool vec = xq + 4 <= W && (reinterpret_cast<uintptr_t>(d) & 15) == 0 && (plane_d & 3) == 0;
     for (int c = 0; c < C; ++c) {
-        const float* sp = s + c * plane_s;
-        // ATen's expression order: w00*a + w01*b + w10*c + w11*d with w = (1-wy)(1-wx) ... evaluated as
-        // h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d)
-        const float top = (1.f - wx) * __ldg(sp + o00) + wx * __ldg(sp + o01);
-        const float bot = (1.f - wx) * __ldg(sp + o10) + wx * __ldg(sp + o11);
-        d[c * plane_d] += (1.f - wy) * top + wy * bot;
+        const float* a = s0 + c * plane_s;
+        const float* b = s1 + c * plane_s;
+        float r[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            // ATen's expression: h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d)
+            const float top = (1.f - wx[p]) * __ldg(a + x0[p]) + wx[p] * __ldg(a + x1[p]);
+            const float bot = (1.f - wx[p]) * __ldg(b + x0[p]) + wx[p] * __ldg(b + x1[p]);
+            r[p] = (1.f - wy) * top + wy * bot;
+        }
+        float* o = d + c * plane_d;
+        if (vec) {
+            float4 t = *reinterpret_cast<const float4*>(o);
+            t.x += r[0]; t.y += r[1]; t.z += r[2]; t.w += r[3];
+            *reinterpret_cast<float4*>(o) = t;
+        } else {
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                if (xq + p < W) o[p] += r[p];
+        }
     }
 }
 
@@ -516,7 +567,37 @@ argmax_hist_nchw_kernel(const float* __restrict__ probs, int C, long long HW, ui
     }
     const int n = blockIdx.y;
     const float* base = probs + static_cast<long long>(n) * C * HW;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < HW;
+    const bool vec = (HW & 3) == 0 && (reinterpret_cast<uintptr_t>(probs) & 15) == 0 && (reinterpret_cast<uintptr_t>(mask) & 3) == 0;
+    const long long HWv = vec ? HW / 4 : 0;
+    for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < HWv;
+         q += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 f = __ldcs(reinterpret_cast<const float4*>(base) + q);
+        float best[4] = {f.x, f.y, f.z, f.w};
+        int arg[4] = {0, 0, 0, 0};
+        for (int c = 1; c < C; ++c) {
+            const float4 t = __ldcs(reinterpret_cast<const float4*>(base + c * HW) + q);
+            const float v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                if (v[p] > best[p]) {
+                    best[p] = v[p];
+                    arg[p] = c;
+                }
+        }
+        const long long o = static_cast<long long>(n) * HW + q * 4;
+        if (mask) *reinterpret_cast<uint32_t*>(mask + o) = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+        if (hist) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const long long lb = static_cast<long long>(labels[o + p]);
+                if (lb != ignore_label) {
+                    const int lc = static_cast<int>(min(max(lb, 0LL), static_cast<long long>(C - 1)));
+                    atomicAdd(&s_hist[arg[p] * C + lc], 1u);
+                }
+            }
+        }
+    }
+    for (long long i = (vec ? HW : 0) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < HW;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         float best = __ldg(base + i);
         int arg = 0;
@@ -580,7 +661,7 @@ extern "C" int cabinet_prob_resize_accum(const float* src, int N, int C, int src
     CAB_REQUIRE(H <= 65535 && N <= 65535, "prob_resize_accum: H/N exceed grid limits");
     if (N == 0) return CABINET_OK;
     const float sh = static_cast<float>(crop_h) / static_cast<float>(H), sw = static_cast<float>(crop_w) / static_cast<float>(W);
-    dim3 grid((W + 255) / 256, H, N);
+    dim3 grid((W + 1023) / 1024, H, N);
     prob_resize_accum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, C, src_h, src_w, crop_y0, crop_x0,
                                                                                  crop_h, crop_w, dst, H, W, sh, sw);
     CAB_LAUNCH_CHECK();
