@@ -113,7 +113,12 @@ def _out_size(n, k, s, p):
 
 
 class Engine:
-    def __init__(self, model, precision: str = "bf16"):
+    # everything ``_pack`` produces (what ``checkpoint.save_packed`` caches)
+    PACKED_ATTRS = ("stem", "blocks", "last", "stem_tc", "sb1", "sb2", "sb3", "sb4", "conva", "to_q", "to_k", "to_v",
+                    "psp_k", "psp_v", "proj_out", "local", "gamma", "convb", "b1", "b4", "key_ch", "qkv", "ffm_blk",
+                    "ffm_gate", "head_conv", "head_out")
+
+    def __init__(self, model, precision: str = "bf16", packed: Optional[dict] = None):
         if precision not in ("bf16", "fp32"):
             raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
         p0 = next(model.parameters())
@@ -146,8 +151,19 @@ class Engine:
         self.branch_overlap = True  # independent chains of the attention branch on side streams (fork / join by events)
         self._branch_streams, self._branch_events = [], {}
         self.sb_overlap = False     # experiment: spatial branch beside the backbone
-        with torch.no_grad():
-            self._pack(model)
+        if packed is not None:  # cached fold + pack of exactly these weights (checkpoint.load_packed verified the digest)
+            missing = [a for a in self.PACKED_ATTRS if a not in packed]
+            if missing:
+                raise ValueError(f"packed weights lack {missing}")
+            for a in self.PACKED_ATTRS:
+                setattr(self, a, packed[a])
+            self.gamma = model.ab.a2block.gamma.detach().float().contiguous()
+        else:
+            with torch.no_grad():
+                self._pack(model)
+
+    def packed_state(self) -> dict:
+        return {a: getattr(self, a) for a in self.PACKED_ATTRS}
 
     # ------------------------------------------------------------------ packing
     def _pack(self, m):
