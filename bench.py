@@ -291,6 +291,13 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = {"bound": False, "why": "--no-numa-bind" if args.no_numa_bind else "single rank: all host cores stay available "
+            "to the cpu_baseline leg"}
+    if not args.no_numa_bind and world > 1:
+        # before any pinned allocation: the rank's host buffers are first-touched on its GPU's NUMA node
+        from cabinet_b200.affinity import bind_to_gpu_numa
+
+        numa = bind_to_gpu_numa(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -440,7 +447,7 @@ def run_ours(args):
                 "mIoU": float(res["mIoU"]),
                 "hist_checksum_ok": (world > 1) or hist_sum == valid, "hist_sum": hist_sum, "valid_pixels": valid},
         "e2e_uint8": e2e8, "e2e_multiscale_flip": msflip,
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        "gpu_launches": launches, "clocks": clocks, "numa": numa, "roofline": roof,
         "kernels": table, "traced_ms_per_step": traced_ms, "peaks": peaks,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -464,6 +471,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--msflip", type=int, default=4, help="batch of the multi-scale + flip evaluation leg (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
