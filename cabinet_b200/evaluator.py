@@ -237,8 +237,10 @@ class MscEvalV0:
         forward is not hidden behind an upload.  ``masks_out``: optional list that receives a pinned uint8 host tensor
         per batch (asynchronous D2H, valid after the final synchronise)."""
         cur = torch.cuda.current_stream(dev)
-        st = self.__dict__.setdefault("_pipe", {"stream": torch.cuda.Stream(dev), "bufs": {}, "x32": None})
+        st = self.__dict__.setdefault("_pipe", {"stream": torch.cuda.Stream(dev), "d2h": torch.cuda.Stream(dev),
+                                                "bufs": {}, "x32": None})
         copy_stream, ring, x32 = st["stream"], st["bufs"], st["x32"]  # device buffers persist across evaluate() calls
+        d2h_stream = st["d2h"]  # mask read-back beside the next forward (on the compute stream it would serialise)
         # the fused forward + confusion-matrix call is replayed as a CUDA graph keyed by its buffer addresses: accumulate
         # into a persistent matrix (the caller's `hist` is a fresh allocation per evaluate(), which would force a
         # re-capture whenever the allocator hands out a different block -- it does under NCCL) and add it at the end
@@ -295,14 +297,24 @@ class MscEvalV0:
                     slot["lab"].copy_(lb, non_blocking=True)
                     slot["ready"].record(copy_stream)
                 cur.wait_event(slot["ready"])
+                if slot.get("d2h_done") is not None:
+                    cur.wait_event(slot["d2h_done"])  # this slot's mask buffer (a graph output) has been read back
                 xin = normalize_u8(slot["img"], x32, *self.u8_mean_std) if u8 else slot["img"]
                 mask = self.model.accumulate_hist(xin, slot["lab"], hist, self.ignore_label)
                 if host is not None:
-                    host[c0:c0 + n].copy_(mask, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(cur)
+                    mask.record_stream(d2h_stream)
+                    with torch.cuda.stream(d2h_stream):
+                        d2h_stream.wait_event(done)
+                        host[c0:c0 + n].copy_(mask, non_blocking=True)
+                        slot["d2h_done"] = torch.cuda.Event()
+                        slot["d2h_done"].record(d2h_stream)
                 slot["consumed"] = torch.cuda.Event()
                 slot["consumed"].record(cur)
                 item += 1
             n_batches += 1
+        cur.wait_stream(d2h_stream)  # the caller's stream order (and any event it records next) covers the read-backs
         user_hist.add_(hist)
         return n_batches
 
