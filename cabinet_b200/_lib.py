@@ -59,6 +59,9 @@ SIGNATURES = {
                                         _p], _i),
     "cabinet_prob_resize_accum": ([_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p], _i),
     "cabinet_argmax_hist_nchw": ([_p, _i, _i, _ll, _p, _p, _i, _i, _p, _p], _i),
+    "cabinet_ohem_workspace_bytes": ([], _ll),
+    "cabinet_ohem_ce_forward": ([_p, _i, _p, _i, _i, _i, _ll, _p, _i, _f, _ll, _p, _p, _p, _p], _i),
+    "cabinet_ohem_ce_backward": ([_p, _i, _p, _i, _i, _i, _ll, _p, _p, _p, _p, _p, _p], _i),
 }
 
 _lib = None

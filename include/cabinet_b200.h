@@ -269,6 +269,25 @@ int cabinet_prob_resize_accum(const float* src, int N, int C, int src_h, int src
 int cabinet_argmax_hist_nchw(const float* probs, int N, int C, long long HW, uint8_t* mask, const void* labels,
                              int label_dtype, int ignore_label, long long* hist, cabinet_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training-step loss (BASELINE config 5): OhemCELoss (src/utils/loss.py:38-80; src/scripts/train.py:344-349,435)
+ * forward + backward without the reference's full sort of the per-pixel losses.
+ *   loss_i = weight[label_i] * (logsumexp_c(logits_i) - logits_i[label_i]) for label_i != ignore_label;
+ *   k = min(n_min, #valid); if #(loss > thresh) >= k: mean of the losses above thresh, else mean of the k largest
+ *   (exact k-th value by a 3-level radix select over the float bit patterns); no valid pixel: 0.
+ * logits: NCHW [N][C][HW] fp32 or bf16 (`dtype`); labels int64 (label_dtype 0) or uint8 (1); weight: [C] fp32 or NULL;
+ * loss_px: fp32 [N*HW] scratch kept for the backward pass (-1 marks ignored pixels); workspace:
+ * cabinet_ohem_workspace_bytes() bytes of device memory, 8-byte aligned, zeroed by the call itself and read again by
+ * _backward; loss_out: one fp32 on the device.  Labels outside [0, C) other than ignore_label are treated as ignored.
+ * _backward: grad_logits (same dtype / shape as logits, fully overwritten) = *grad_out * d loss / d logits. */
+long long cabinet_ohem_workspace_bytes(void);
+int cabinet_ohem_ce_forward(const void* logits, int dtype, const void* labels, int label_dtype, int N, int C, long long HW,
+                            const float* weight, int ignore_label, float thresh, long long n_min, float* loss_px,
+                            void* workspace, float* loss_out, cabinet_stream_t stream);
+int cabinet_ohem_ce_backward(const void* logits, int dtype, const void* labels, int label_dtype, int N, int C,
+                             long long HW, const float* weight, const float* loss_px, const void* workspace,
+                             const float* grad_out, void* grad_logits, cabinet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,101 @@
+"""GPU: cabinet_b200.loss.OhemCELoss (C-ABI kernels, no sort) against the reference's golden outputs, the CPU oracle
+and the reference's own unit-test expectations (reference: src/utils/loss.py:11-83, tests/unit/test_loss.py:9-105)."""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from cabinet_b200.loss import OhemCELoss  # noqa: E402
+from oracle.loss_oracle import OHEM_CASES, make_case, ohem_ce_loss  # noqa: E402
+from tests.gpu_util import rel_l2  # noqa: E402
+
+
+def run_ours(logits, labels, thresh, n_min, weight, label_dtype=torch.int64):
+    x = logits.cuda().requires_grad_(True)
+    crit = OhemCELoss(thresh=thresh, n_min=n_min, ignore_lb=255, weight=weight).cuda()
+    loss = crit(x, labels.to(label_dtype).cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.detach().cpu(), x.grad.float().cpu()
+
+
+@pytest.mark.parametrize("label_dtype", [torch.int64, torch.uint8])
+@pytest.mark.parametrize("case", OHEM_CASES, ids=[c[0] for c in OHEM_CASES])
+def test_ohem_vs_reference_golden(golden_dir, case, label_dtype):
+    name, shape, thresh, n_min, ignore, weighted, scale, quant = case
+    g = np.load(golden_dir / f"ohem_{name}.npz")
+    logits, labels, weight = make_case(shape, ignore, weighted, scale, quant)
+    loss, grad = run_ours(logits, labels, thresh, n_min, weight, label_dtype)
+    assert loss.ndim == 0 and float(loss) == pytest.approx(float(g["loss"]), rel=2e-6, abs=1e-7)
+    ref_grad = torch.from_numpy(g["grad"])
+    if name == "ties_topk":
+        # equal losses at the k-th value: a sort keeps an arbitrary subset of them, the kernel spreads the same total
+        # weight over the tie group -- the selected mass and everything strictly above the tie agree
+        assert float(grad.sum()) == pytest.approx(float(ref_grad.sum()), abs=1e-5)
+        assert float(grad.abs().sum()) == pytest.approx(float(ref_grad.abs().sum()), rel=2e-2)
+    elif name == "all_ignored":
+        assert float(loss) == 0.0 and float(grad.abs().max()) == 0.0
+    else:
+        assert rel_l2(grad, ref_grad) < 1e-5
+        assert torch.equal(grad == 0, ref_grad == 0)  # the same pixels are selected
+
+
+@pytest.mark.parametrize("mode", ["thresh", "topk"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ohem_full_size_vs_sorted_torch(mode, dtype):
+    """BASELINE config-5 loss shape (8 x 8 x 1024 x 1024, n_min = N*H*W/16, thresh 0.7): the radix select picks exactly
+    the sorted prefix.  The comparison runs the oracle restatement (sort-based, plain torch) on the same device."""
+    N, C, H, W = 8, 8, 1024, 1024
+    g = torch.Generator(device="cuda").manual_seed(3)
+    logits = (torch.randn(N, C, H, W, device="cuda", generator=g) * (3.0 if mode == "thresh" else 0.05)).to(dtype)
+    labels = torch.randint(0, C, (N, H, W), device="cuda", generator=g)
+    labels[:, 100:140, :] = 255
+    if mode == "topk":  # confident, mostly right predictions: few losses above the threshold -> the k largest are used
+        logits.scatter_add_(1, labels.clamp(max=C - 1).unsqueeze(1), torch.full((N, 1, H, W), 6.0, device="cuda", dtype=dtype))
+    n_min = N * H * W // 16
+    x = logits.clone().requires_grad_(True)
+    ref = ohem_ce_loss(x, labels, 0.7, n_min, 255, None)
+    ref.backward()
+    y = logits.clone().requires_grad_(True)
+    loss = OhemCELoss(0.7, n_min, 255)(y, labels)
+    loss.backward()
+    n_gt = int((torch.nn.functional.cross_entropy(logits.float(), labels, ignore_index=255, reduction="none") > 0.7).sum())
+    assert (n_gt >= n_min) == (mode == "thresh")
+    assert float(loss) == pytest.approx(float(ref), rel=1e-5)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel_l2(y.grad.float().cpu(), x.grad.float().cpu()) < tol
+    assert y.grad.dtype == dtype
+    sel_ours, sel_ref = (y.grad.float().abs().sum(1) > 0), (x.grad.float().abs().sum(1) > 0)
+    assert float((sel_ours != sel_ref).float().mean()) < (5e-6 if dtype == torch.float32 else 1e-3)
+
+
+def test_reference_unit_test_expectations():
+    """tests/unit/test_loss.py:12-105 of the reference, on the device."""
+    gen = torch.Generator().manual_seed(15)
+    crit = OhemCELoss(thresh=0.7, n_min=100, ignore_lb=255).cuda()
+    loss = crit(torch.randn(4, 19, 64, 64, generator=gen).cuda(), torch.randint(0, 19, (4, 64, 64), generator=gen).cuda())
+    assert loss.ndim == 0 and loss.item() >= 0 and not torch.isnan(loss)
+    labels = torch.randint(0, 19, (2, 32, 32), generator=gen)
+    labels[0, :10, :10] = 255
+    loss = crit(torch.randn(2, 19, 32, 32, generator=gen).cuda(), labels.cuda())
+    assert loss.item() >= 0 and not torch.isnan(loss)
+    x = torch.randn(1, 19, 32, 32, generator=gen).cuda().requires_grad_(True)
+    loss = crit(x, torch.full((1, 32, 32), 255).cuda())  # all ignored
+    assert loss.item() == 0.0 and loss.requires_grad
+    loss.backward()
+    assert float(x.grad.abs().max()) == 0.0
+    w = torch.ones(19)
+    w[0] = 2.0
+    crit_w = OhemCELoss(thresh=0.7, n_min=100, ignore_lb=255, weight=w)
+    assert not hasattr(crit_w, "criteria")
+    crit_w = crit_w.cuda()  # the weight buffer follows .cuda()
+    assert crit_w.weight.is_cuda
+    x = torch.randn(2, 19, 32, 32, generator=gen).cuda().requires_grad_(True)
+    loss = crit_w(x, torch.randint(0, 19, (2, 32, 32), generator=gen).cuda())
+    loss.backward()
+    assert loss.item() >= 0 and not torch.isnan(loss) and not torch.isnan(x.grad).any()
+    with pytest.raises(RuntimeError):
+        crit(torch.randn(1, 19, 8, 8), torch.zeros(1, 8, 8, dtype=torch.long))  # no CPU path
+    assert "thresh=0.7" in repr(crit)

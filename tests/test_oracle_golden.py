@@ -65,3 +65,22 @@ def test_compute_hist_edge_cases():
     assert h.sum() == 7 and h[0, 0] == 1 and h[3, 3] == 2 and h[3, 2] == 1 and h[0, 1] == 1 and h[3, 0] == 1
     assert evaluator_oracle.compute_hist(np.zeros((0, 5)), np.zeros((0, 5)), C).sum() == 0
     assert evaluator_oracle.compute_hist(np.zeros((2, 2)), np.full((2, 2), 255), C).sum() == 0
+
+
+# ------------------------------------------------------------------ training loss (OhemCELoss)
+from oracle.loss_oracle import OHEM_CASES, make_case, ohem_ce_loss  # noqa: E402
+
+
+@pytest.mark.parametrize("case", OHEM_CASES, ids=[c[0] for c in OHEM_CASES])
+def test_loss_oracle_matches_reference_golden(golden_dir, case):
+    """oracle/loss_oracle.py against outputs of the imported reference OhemCELoss (oracle/make_golden_loss.py)."""
+    name, shape, thresh, n_min, ignore, weighted, scale, quant = case
+    g = np.load(golden_dir / f"ohem_{name}.npz")
+    logits, labels, weight = make_case(shape, ignore, weighted, scale, quant)
+    assert float(logits.double().sum()) == float(g["logits_sum"]) and int(labels.sum()) == int(g["labels_sum"])
+    x = logits.clone().requires_grad_(True)
+    loss = ohem_ce_loss(x, labels, thresh, n_min, 255, weight)
+    loss.backward()
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-6, abs=1e-7)
+    grad = x.grad if x.grad is not None else torch.zeros_like(x)
+    np.testing.assert_allclose(grad.numpy(), g["grad"], rtol=1e-5, atol=1e-8)
