@@ -15,7 +15,7 @@ HEADER = Path(__file__).resolve().parent.parent / "include" / "cabinet_b200.h"
 def header_prototypes():
     text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
     protos = {}
-    for m in re.finditer(r"(?:const\s+char\s*\*|int)\s+(cabinet_\w+)\s*\(([^)]*)\)\s*;", text):
+    for m in re.finditer(r"(?:const\s+char\s*\*|long\s+long|int)\s+(cabinet_\w+)\s*\(([^)]*)\)\s*;", text):
         name, args = m.group(1), m.group(2).strip()
         kinds = []
         if args and args != "void":
