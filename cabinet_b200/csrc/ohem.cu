@@ -42,6 +42,48 @@ template <> __device__ __forceinline__ float ld_logit<bf16>(const bf16* p) {
     return __uint_as_float(static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
 }
 
+// 4 consecutive pixels of one class plane (16-byte / 8-byte aligned)
+template <typename T> __device__ __forceinline__ void ld_logit4(const T* p, float* v);
+template <> __device__ __forceinline__ void ld_logit4<float>(const float* p, float* v) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void ld_logit4<bf16>(const bf16* p, float* v) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+template <typename T> __device__ __forceinline__ void st_grad4(T* p, const float* v);
+template <> __device__ __forceinline__ void st_grad4<float>(float* p, const float* v) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+}
+template <> __device__ __forceinline__ void st_grad4<bf16>(bf16* p, const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __stcs(reinterpret_cast<uint2*>(p), make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b)));
+}
+
+// max and sum(exp(x - max)) over the classes for 4 consecutive pixels (second sweep hits L1)
+template <typename T>
+__device__ __forceinline__ void softmax_stats4(const T* __restrict__ x, int C, long long HW, float* m, float* s) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        m[p] = -INFINITY;
+        s[p] = 0.f;
+    }
+    for (int c = 0; c < C; ++c) {
+        float v[4];
+        ld_logit4<T>(x + c * HW, v);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) m[p] = fmaxf(m[p], v[p]);
+    }
+    for (int c = 0; c < C; ++c) {
+        float v[4];
+        ld_logit4<T>(x + c * HW, v);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) s[p] += expf(v[p] - m[p]);
+    }
+}
+
 __device__ __forceinline__ long long ld_label(const void* labels, int label_dtype, long long i) {
     return label_dtype == 0 ? __ldg(reinterpret_cast<const long long*>(labels) + i)
                             : static_cast<long long>(__ldg(reinterpret_cast<const uint8_t*>(labels) + i));
@@ -81,7 +123,34 @@ ohem_ce_px_kernel(const T* __restrict__ logits, const void* __restrict__ labels,
     const T* base = logits + static_cast<long long>(n) * C * HW;
     unsigned long long nv = 0, ng = 0;
     double sg = 0.0;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < HW;
+    // 4 pixels per thread when every class plane is 16-byte aligned (HW % 8 == 0 covers bf16 too)
+    const bool vec = (HW & 7) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(loss_px) & 15) == 0;
+    const long long HWv = vec ? HW / 4 : 0;
+    for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < HWv;
+         q += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long i = q * 4, o = static_cast<long long>(n) * HW + i;
+        float m[4], s[4], l[4];
+        softmax_stats4<T>(base + i, C, HW, m, s);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const long long lb = ld_label(labels, label_dtype, o + p);
+            l[p] = -1.f;
+            if (lb != ignore_label && lb >= 0 && lb < C) {
+                const float w = weight ? __ldg(weight + lb) : 1.f;
+                const float v = fmaxf(w * (m[p] + logf(s[p]) - ld_logit<T>(base + lb * HW + i + p)), 0.f);
+                l[p] = __uint_as_float(__float_as_uint(v) & 0x7fffffffu);
+                ++nv;
+                if (l[p] > thresh) {
+                    ++ng;
+                    sg += l[p];
+                }
+                atomicAdd(&s_hist[__float_as_uint(l[p]) >> 20], 1u);
+            }
+        }
+        *reinterpret_cast<float4*>(loss_px + o) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+    for (long long i = (vec ? HW : 0) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < HW;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long o = static_cast<long long>(n) * HW + i;
         const long long lb = ld_label(labels, label_dtype, o);
@@ -251,7 +320,47 @@ ohem_ce_bwd_kernel(const T* __restrict__ logits, const void* __restrict__ labels
     const float g = __ldg(grad_out) * ws->inv_m;
     const T* base = logits + static_cast<long long>(n) * C * HW;
     T* gbase = grad_logits + static_cast<long long>(n) * C * HW;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < HW;
+    const bool vec = (HW & 7) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(grad_logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(loss_px) & 15) == 0;
+    const long long HWv = vec ? HW / 4 : 0;
+    for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < HWv;
+         q += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long i = q * 4, o = static_cast<long long>(n) * HW + i;
+        const float4 l4 = __ldg(reinterpret_cast<const float4*>(loss_px + o));
+        const float l[4] = {l4.x, l4.y, l4.z, l4.w};
+        float k[4];
+        long long lb[4];
+        bool any = false;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float coef = 0.f;
+            if (l[p] >= 0.f) coef = l[p] > sel ? 1.f : (l[p] == tie_v ? tie_f : 0.f);
+            lb[p] = -1;
+            k[p] = 0.f;
+            if (coef != 0.f) {
+                lb[p] = ld_label(labels, label_dtype, o + p);
+                k[p] = g * coef * (weight ? __ldg(weight + lb[p]) : 1.f);
+                any = true;
+            }
+        }
+        if (!any) {  // nothing selected among the 4 pixels: zero the gradient without reading the logits
+            const float z[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int c = 0; c < C; ++c) st_grad4<T>(gbase + c * HW + i, z);
+            continue;
+        }
+        float m[4], s[4];
+        softmax_stats4<T>(base + i, C, HW, m, s);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) s[p] = 1.f / s[p];
+        for (int c = 0; c < C; ++c) {
+            float v[4], r[4];
+            ld_logit4<T>(base + c * HW + i, v);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) r[p] = k[p] * (expf(v[p] - m[p]) * s[p] - (c == lb[p] ? 1.f : 0.f));
+            st_grad4<T>(gbase + c * HW + i, r);
+        }
+    }
+    for (long long i = (vec ? HW : 0) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < HW;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long o = static_cast<long long>(n) * HW + i;
         const float l = __ldg(loss_px + o);
@@ -320,7 +429,7 @@ extern "C" int cabinet_ohem_ce_backward(const void* logits, int dtype, const voi
     if (N == 0) return CABINET_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const OhemWs* ws = reinterpret_cast<const OhemWs*>(workspace);
-    dim3 grid(static_cast<unsigned>(std::min<long long>(cab_ceil_div(HW, 256), 148 * 16)), N);
+    dim3 grid(static_cast<unsigned>(std::min<long long>(cab_ceil_div(HW, 256 * 4), 148 * 16)), N);
     if (dtype == CABINET_F32)
         ohem_ce_bwd_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(logits), labels, label_dtype, C, HW,
                                                        weight, loss_px, ws, grad_out, reinterpret_cast<float*>(grad_logits));
