@@ -375,12 +375,15 @@ __device__ __forceinline__ void softmax_stats8(const float* __restrict__ x, int 
     });
 }
 
-template <bool EXACT8>
-__global__ void __launch_bounds__(128)
-upsample_softmax_accum_kernel(const float* __restrict__ x, const float* __restrict__ xf, int IH, int IW, int C, int OH,
+// FLIP is a template parameter: the plain variant keeps half the per-pixel state (64 instead of 126 registers,
+// twice the resident warps: the kernel is latency bound at 25 % occupancy)
+template <bool EXACT8, bool FLIP>
+__global__ void __launch_bounds__(128, EXACT8 ? (FLIP ? 4 : 6) : 3)
+upsample_softmax_accum_kernel(const float* __restrict__ x, const float* __restrict__ xf_arg, int IH, int IW, int C, int OH,
                               int OW, float sh, float sw, float* __restrict__ prob, long long sn, long long sc,
                               long long sr, int dy0, int dx0, int dh, int dw, const float* __restrict__ wy,
                               const float* __restrict__ wx, float weight) {
+    const float* __restrict__ xf = FLIP ? xf_arg : nullptr;
     const int groups_w = (OW + PXG - 1) / PXG;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int oh = blockIdx.y, n = blockIdx.z;
@@ -390,14 +393,14 @@ upsample_softmax_accum_kernel(const float* __restrict__ x, const float* __restri
     if (dx0 + ow0 >= dw || dx0 + ow0 + PXG <= 0) return;
     float m[PXG], l[PXG], mf[PXG], lf[PXG], k[PXG], kf[PXG];
     softmax_stats8<EXACT8>(x, n, oh, g, IH, IW, C, OW, sh, sw, m, l);
-    const float rowk = weight * (wy ? __ldg(wy + oh) : 1.f) * (xf ? 0.5f : 1.f);
+    const float rowk = weight * (wy ? __ldg(wy + oh) : 1.f) * (FLIP ? 0.5f : 1.f);
 #pragma unroll
     for (int p = 0; p < PXG; ++p) k[p] = rowk * (wx ? __ldg(wx + min(ow0 + p, OW - 1)) : 1.f) / l[p];
     // mirrored group of the flipped chip's map: chip column ow <-> flipped column OW-1-ow.  With OW % 8 == 0 that
     // is group (groups_w-1-g) read back to front; otherwise the mirrored pixels straddle two groups -> per-pixel path.
     const bool mirror_fast = EXACT8 || (OW % PXG) == 0;
     const int gf = groups_w - 1 - g;
-    if (xf && mirror_fast) {
+    if (FLIP && mirror_fast) {
         softmax_stats8<EXACT8>(xf, n, oh, gf, IH, IW, C, OW, sh, sw, mf, lf);
 #pragma unroll
         for (int p = 0; p < PXG; ++p) kf[p] = k[PXG - 1 - p] * l[PXG - 1 - p] / lf[p];  // weight of mirrored pixel p
@@ -419,7 +422,7 @@ upsample_softmax_accum_kernel(const float* __restrict__ x, const float* __restri
         }
     };
     if constexpr (EXACT8) {
-        if (xf && (C & 3) == 0) {
+        if (FLIP && (C & 3) == 0) {
             // both class maps per 4-class chunk, ONE read-modify-write of the window
             int y0, y1;
             float wyy;
@@ -446,7 +449,7 @@ upsample_softmax_accum_kernel(const float* __restrict__ x, const float* __restri
             return;
         }
     }
-    if (!xf) {
+    if constexpr (!FLIP) {
         upsample_group8<EXACT8>(x, n, oh, g, IH, IW, C, OW, sh, sw, [&](int c, const float* v) {
             float pv[PXG];
 #pragma unroll
@@ -641,14 +644,16 @@ extern "C" int cabinet_upsample_softmax_accum(const float* x, const float* x_fli
     const int groups = (OW + PXG - 1) / PXG;
     dim3 grid((groups + 127) / 128, OH, N);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (exact8)
-        upsample_softmax_accum_kernel<true><<<grid, 128, 0, s>>>(x, x_flip, IH, IW, C, OH, OW, sh, sw, prob, stride_n,
-                                                                 stride_c, stride_row, dst_y0, dst_x0, dst_h, dst_w,
-                                                                 weight_y, weight_x, weight);
-    else
-        upsample_softmax_accum_kernel<false><<<grid, 128, 0, s>>>(x, x_flip, IH, IW, C, OH, OW, sh, sw, prob, stride_n,
-                                                                  stride_c, stride_row, dst_y0, dst_x0, dst_h, dst_w,
-                                                                  weight_y, weight_x, weight);
+#define CAB_USA(E8, FL)                                                                                              \
+    upsample_softmax_accum_kernel<E8, FL><<<grid, 128, 0, s>>>(x, x_flip, IH, IW, C, OH, OW, sh, sw, prob, stride_n,    \
+                                                               stride_c, stride_row, dst_y0, dst_x0, dst_h, dst_w,      \
+                                                               weight_y, weight_x, weight)
+    if (exact8) {
+        if (x_flip) CAB_USA(true, true); else CAB_USA(true, false);
+    } else {
+        if (x_flip) CAB_USA(false, true); else CAB_USA(false, false);
+    }
+#undef CAB_USA
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }
