@@ -21,7 +21,7 @@ import torch
 
 from .synthetic import state_dict_digest
 
-PACK_FORMAT = 1
+PACK_FORMAT = 2
 
 
 def load_model_weights(checkpoint_path, device="cpu") -> Dict[str, Any]:

@@ -50,6 +50,10 @@ struct TcConvParams {
     long long ldres;
     void* y;
     long long ldy;
+    // UP4 epilogue: v += bilinear(up -> output size)[pixel] before the activation.  up: fp32 [N][up_h][up_w][Cout];
+    // img_h x img_w = true output size of one image (the tile walk of a 1x1 conv is flat over all pixels)
+    const float* up;
+    int up_h, up_w, img_h, img_w, up_flat;
 };
 
 __device__ long long g_dbg[8192];  // clock64 stamps of CTA 0's MMA warp when debug bit 8 is set
@@ -70,7 +74,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int tile
     return c;
 }
 
-template <int ACT, bool HAS_RES, bool OUT_F32, bool PRO>
+template <int ACT, bool HAS_RES, bool OUT_F32, bool PRO, bool UP4 = false>
 __global__ void __launch_bounds__(PRO ? NUM_THREADS + 256 : NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
@@ -280,6 +284,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int oh = tcd.oh0 + row / p.TW, ow = tcd.ow0 + row % p.TW;
             const bool valid = oh < p.OH && ow < p.OW;
             const long long pix = (static_cast<long long>(tcd.img) * p.OH + oh) * p.OW + ow;
+            [[maybe_unused]] const float* up00 = nullptr;
+            [[maybe_unused]] long long up_dx = 0, up_dy = 0;
+            [[maybe_unused]] float uw00 = 0.f, uw01 = 0.f, uw10 = 0.f, uw11 = 0.f;
+            if constexpr (UP4) {
+                if (valid) {  // bilinear taps of this thread's pixel in the low-resolution map (align_corners=False)
+                    int un = tcd.img, uoh = oh, uow = ow;
+                    if (p.up_flat) {
+                        un = static_cast<int>(pix / p.hw);
+                        const int rem = static_cast<int>(pix - static_cast<long long>(un) * p.hw);
+                        uoh = rem / p.img_w;
+                        uow = rem - uoh * p.img_w;
+                    }
+                    int y0, y1, x0, x1;
+                    float wy, wx;
+                    cab_bilinear_tap(uoh, static_cast<float>(p.up_h) / static_cast<float>(p.img_h), p.up_h, y0, y1, wy);
+                    cab_bilinear_tap(uow, static_cast<float>(p.up_w) / static_cast<float>(p.img_w), p.up_w, x0, x1, wx);
+                    up00 = p.up + ((static_cast<long long>(un) * p.up_h + y0) * p.up_w + x0) * p.Cout;
+                    up_dx = static_cast<long long>(x1 - x0) * p.Cout;
+                    up_dy = static_cast<long long>(y1 - y0) * p.up_w * p.Cout;
+                    uw00 = (1.f - wy) * (1.f - wx); uw01 = (1.f - wy) * wx; uw10 = wy * (1.f - wx); uw11 = wy * wx;
+                }
+            }
             if (tcd.n0 != bias_n0) {  // (re)load this cout tile's bias slice, zero padded
                 tc::named_bar_sync(1 + e, 128);  // everyone is done reading the previous slice
                 for (int i = gtid; i < p.block_n; i += 128) myBias[i] = (tcd.n0 + i < p.Cout) ? __ldg(p.bias + tcd.n0 + i) : 0.f;
@@ -326,6 +352,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         v[4 * j4 + 1] = __uint_as_float(r[16 * c + 4 * j4 + 1]) + b.y;
                         v[4 * j4 + 2] = __uint_as_float(r[16 * c + 4 * j4 + 2]) + b.z;
                         v[4 * j4 + 3] = __uint_as_float(r[16 * c + 4 * j4 + 3]) + b.w;
+                    }
+                    if constexpr (UP4) {
+                        if (valid && co0 + 16 <= p.Cout) {
+                            const float* t = up00 + co0;
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 a = __ldg(reinterpret_cast<const float4*>(t) + j4);
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(t + up_dx) + j4);
+                                const float4 c2 = __ldg(reinterpret_cast<const float4*>(t + up_dy) + j4);
+                                const float4 d = __ldg(reinterpret_cast<const float4*>(t + up_dy + up_dx) + j4);
+                                v[4 * j4 + 0] += uw00 * a.x + uw01 * b.x + uw10 * c2.x + uw11 * d.x;
+                                v[4 * j4 + 1] += uw00 * a.y + uw01 * b.y + uw10 * c2.y + uw11 * d.y;
+                                v[4 * j4 + 2] += uw00 * a.z + uw01 * b.z + uw10 * c2.z + uw11 * d.z;
+                                v[4 * j4 + 3] += uw00 * a.w + uw01 * b.w + uw10 * c2.w + uw11 * d.w;
+                            }
+                        }
                     }
                     constexpr bool RELU_ON_CVT = ACT == CABINET_ACT_RELU && !HAS_RES && !OUT_F32;  // cvt.rn.relu.bf16x2
                     const bool do_act = co0 < p.act_cols;  // uniform per 16-column chunk (act_cols % 16 == 0)
@@ -460,7 +502,8 @@ extern "C" int cabinet_debug_flags(int flags) {
 static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int Cin, const float* a_scale, int a_act,
                         const void* w_packed, long long w_image_stride, int Cout, int KH, int KW, int stride, int pad,
                         const float* bias, const void* res, long long ldres, void* y, int y_dtype, long long ldy,
-                        int OH, int OW, int act, cabinet_stream_t stream, int act_cols = 1 << 30);
+                        int OH, int OW, int act, cabinet_stream_t stream, int act_cols = 1 << 30,
+                        const float* up = nullptr, int up_h = 0, int up_w = 0);
 
 extern "C" int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, int W, int Cin, const float* a_scale,
                                   int a_act, const void* w_packed, int Cout, int KH, int KW, int stride, int pad,
@@ -498,11 +541,24 @@ extern "C" int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W
                               res, ldres, y, y_dtype, ldy, OH, OW, act, stream);
 }
 
+extern "C" int cabinet_conv_tc_up(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_packed,
+                                  int Cout, int KH, int KW, int stride, int pad, const float* bias, const float* up,
+                                  int up_h, int up_w, void* y, long long ldy, int OH, int OW, int act,
+                                  cabinet_stream_t stream) {
+    CAB_REQUIRE(up != nullptr, "conv_tc_up: null low-resolution map");
+    return conv_tc_impl(x, ldx, N, H, W, Cin, nullptr, CABINET_ACT_NONE, w_packed, 0, Cout, KH, KW, stride, pad, bias,
+                        nullptr, 0, y, CABINET_BF16, ldy, OH, OW, act, stream, 1 << 30, up, up_h, up_w);
+}
+
 static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int Cin, const float* a_scale, int a_act,
                         const void* w_packed, long long w_image_stride, int Cout, int KH, int KW, int stride, int pad,
                         const float* bias, const void* res, long long ldres, void* y, int y_dtype, long long ldy,
-                        int OH, int OW, int act, cabinet_stream_t stream, int act_cols) {
+                        int OH, int OW, int act, cabinet_stream_t stream, int act_cols, const float* up, int up_h,
+                        int up_w) {
     CAB_REQUIRE(x && w_packed && bias && y, "conv_tc: null pointer");
+    CAB_REQUIRE(!up || (up_h > 0 && up_w > 0 && Cout % 16 == 0 && (reinterpret_cast<uintptr_t>(up) & 15) == 0 && !res &&
+                        !a_scale && y_dtype == CABINET_BF16 && w_image_stride == 0),
+                "conv_tc_up: the upsample-add epilogue needs Cout %% 16 == 0, an aligned fp32 map, bf16 output, no residual");
     CAB_REQUIRE(!a_scale || (Cin % 8 == 0 && (reinterpret_cast<uintptr_t>(a_scale) & 15) == 0),
                 "conv_tc: the A-operand scale needs Cin %% 8 == 0 and a 16-byte aligned pointer");
     CAB_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && OH > 0 && OW > 0,
@@ -545,6 +601,7 @@ static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int C
     p.act = act; p.y_dtype = y_dtype; p.bias = bias; p.res = reinterpret_cast<const bf16*>(res); p.ldres = ldres;
     p.y = y; p.ldy = ldy; p.debug = g_debug;
     p.a_scale = a_scale; p.a_act = a_act; p.hw = H * W;
+    p.up = up; p.up_h = up_h; p.up_w = up_w; p.img_h = OH; p.img_w = OW; p.up_flat = 0;
 
     CUtensorMap tmA[4], tmB, tmY;
     const uint64_t es = 2;
@@ -552,7 +609,7 @@ static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int C
     if (flat) {
         const long long P = static_cast<long long>(N) * H * W;
         CAB_REQUIRE(P < (1LL << 31), "conv_tc: too many pixels");
-        Ng = 1; p.OH = 1; p.OW = static_cast<int>(P);
+        Ng = 1; p.OH = 1; p.OW = static_cast<int>(P); p.up_flat = 1;
         p.TW = BLOCK_M; p.TH = 1; p.tiles_w = static_cast<int>(cab_ceil_div(P, BLOCK_M)); p.tiles_h = 1;
         const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)P, 1, 1};
         const uint64_t strides[3] = {(uint64_t)ldx * es, (uint64_t)ldx * es * P, (uint64_t)ldx * es * P};
@@ -628,8 +685,26 @@ static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int C
         conv_tc_kernel<ACT_, RES_, F32_, PRO_><<<grid, (PRO_) ? NUM_THREADS + 256 : NUM_THREADS, smem, st>>>(        \
             tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmY, p);                                                            \
     } while (0)
+#define CAB_TC_LAUNCH_UP(ACT_)                                                                                       \
+    do {                                                                                                             \
+        static bool attr_done = false;                                                                               \
+        if (!attr_done) {                                                                                            \
+            CAB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_, false, false, false, true>,                           \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT + 1024));          \
+            attr_done = true;                                                                                        \
+        }                                                                                                            \
+        conv_tc_kernel<ACT_, false, false, false, true><<<grid, NUM_THREADS, smem, st>>>(tmA[0], tmA[1], tmA[2],     \
+                                                                                         tmA[3], tmB, tmY, p);       \
+    } while (0)
     const bool f32 = y_dtype == CABINET_F32;
-    if (a_scale) {
+    if (up) {
+        if (act == CABINET_ACT_RELU) CAB_TC_LAUNCH_UP(CABINET_ACT_RELU);
+        else if (act == CABINET_ACT_NONE) CAB_TC_LAUNCH_UP(CABINET_ACT_NONE);
+        else {
+            cabinet_set_error("conv_tc_up: activation %d not built (ReLU / none)", act);
+            return CABINET_ERR_INVALID;
+        }
+    } else if (a_scale) {
         CAB_REQUIRE(!f32 && act == CABINET_ACT_NONE, "conv_tc: the A-operand prologue is built for the linear project conv");
         if (res) CAB_TC_LAUNCH(CABINET_ACT_NONE, true, false, true);
         else CAB_TC_LAUNCH(CABINET_ACT_NONE, false, false, true);
@@ -644,6 +719,7 @@ static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int C
         return CABINET_ERR_INVALID;
     }
 #undef CAB_TC_LAUNCH
+#undef CAB_TC_LAUNCH_UP
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

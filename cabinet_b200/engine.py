@@ -69,11 +69,14 @@ def _fold(conv_w, conv_b, bn, eps=BN_EPS):
 class ConvLayer:
     """Dense conv (+folded BN) packed for the kernels: w [Cout][KH*KW*Cin] (c fastest), fp32 bias."""
 
-    def __init__(self, conv, bn, act, wdtype, name=""):
-        w, b = _fold(conv.weight, conv.bias, bn)
+    def __init__(self, conv, bn, act, wdtype, name="", folded=None):
+        if folded is not None:  # (w [Cout,Cin,KH,KW] fp32, b [Cout] fp32, stride, pad): weights derived at pack time
+            w, b, self.stride, self.pad = folded
+        else:
+            w, b = _fold(conv.weight, conv.bias, bn)
+            self.stride, self.pad = conv.stride[0], conv.padding[0]
         self.name = name
         self.cout, self.cin, self.kh, self.kw = w.shape
-        self.stride, self.pad = conv.stride[0], conv.padding[0]
         self.act = act
         self.w = w.permute(0, 2, 3, 1).reshape(self.cout, -1).contiguous().to(wdtype)
         self.b = b.contiguous()
@@ -116,7 +119,7 @@ class Engine:
     # everything ``_pack`` produces (what ``checkpoint.save_packed`` caches)
     PACKED_ATTRS = ("stem", "blocks", "last", "stem_tc", "sb1", "sb2", "sb3", "sb4", "conva", "to_q", "to_k", "to_v",
                     "psp_k", "psp_v", "proj_out", "local", "gamma", "convb", "b1", "b4", "key_ch", "qkv", "ffm_blk",
-                    "ffm_gate", "head_conv", "head_out")
+                    "ffm_gate", "head_conv", "head_out", "ffm_sb", "low_fold")
 
     def __init__(self, model, precision: str = "bf16", packed: Optional[dict] = None):
         if precision not in ("bf16", "fp32"):
@@ -139,6 +142,7 @@ class Engine:
         self.fuse_mbconv = True     # expand + depthwise (+ project) in one kernel for blocks with <= 64 input channels
         self.fold_se_relu = True    # ReLU SE blocks: gate folded into per-image project weights (relu(s*d) = s*relu(d))
         self.fold_ffm = True        # FFM gate folded into per-image head-conv weights (no rewrite of the fused feature map)
+        self.fold_low_up = True     # convb + x4 upsample + the low half of ffm.convblk as a 1/32-resolution conv + epilogue add
         self.fuse_se = False        # SE apply as A-operand prologue of the project GEMM (slower than scale_act today)
         self.use_cuda_graph = False
         self.sub_batch = 0          # > 0: run the schedule over chunks of this many images
@@ -255,6 +259,20 @@ class Engine:
         ffm = m.ffm
         self.ffm_blk = ConvLayer(ffm.convblk.conv, ffm.convblk.bn, ACT_RELU, wd, "ffm.convblk")
         self.ffm_gate = GateLayer(ffm.conv1.weight, None, ffm.conv2.weight, None, ACT_SIGMOID)
+        # A 1x1 conv commutes with bilinear interpolation: convblk(cat[sb, up(low)]) = W_sb sb + up(W_low low) + b, and
+        # low = convb(feat) is itself a 1x1 conv -> one 256 -> 256 conv at 1/32 resolution (W_low W_convb, bias
+        # W_low b_convb) whose fp32 output the convblk epilogue upsamples and adds (cabinet_conv_tc_up).  The x4-upsampled
+        # 256-channel tensor is never written and convblk's K shrinks from 384 to 128.
+        self.ffm_sb = self.low_fold = None
+        if self.precision == "bf16" and ffm.convblk.conv.kernel_size == (1, 1) and ab.convb.kernel_size == (1, 1):
+            wf, bf_ = _fold(ffm.convblk.conv.weight, ffm.convblk.conv.bias, ffm.convblk.bn)
+            n_sb = sb.conv_out.conv.out_channels
+            w_low = wf[:, n_sb:, 0, 0].double()
+            wb, bb = _fold(ab.convb.weight, ab.convb.bias, None)
+            self.ffm_sb = ConvLayer(None, None, ACT_RELU, wd, "ffm.convblk", folded=(wf[:, :n_sb].contiguous(), bf_, 1, 0))
+            self.low_fold = ConvLayer(None, None, ACT_NONE, wd, "ab.convb*ffm.low",
+                                      folded=((w_low @ wb[:, :, 0, 0].double()).float()[:, :, None, None].contiguous(),
+                                              (w_low @ bb.double()).float(), 1, 0))
         self.head_conv = ConvLayer(m.conv_out.conv.conv, m.conv_out.conv.bn, ACT_RELU, wd, "conv_out.conv")
         self.head_out = ConvLayer(m.conv_out.conv_out, None, ACT_NONE, wd, "conv_out.conv_out")
 
@@ -512,7 +530,9 @@ class Engine:
         else:
             s1 = self.conv(None, self.sb1, nchw_input=x)
         H8, W8 = _out_size(_out_size(s1.H, 3, 2, 1), 3, 2, 1), _out_size(_out_size(s1.W, 3, 2, 1), 3, 2, 1)
-        cat_ffm = self.new(N, H8, W8, 128 + 256)
+        fold_low = (self.fold_low_up and self.use_tc and not self.debug and self.ffm_sb is not None
+                    and self.ffm_sb.tc is not None and self.low_fold.tc is not None and self.sb4.cout == self.ffm_sb.cin)
+        cat_ffm = self.new(N, H8, W8, self.sb4.cout if fold_low else 128 + 256)
         if self.sb_overlap:  # experiment: the rest of the spatial branch beside the backbone (joined before the FFM)
             with self._branch(2) as joined:
                 s2 = self.conv(s1, self.sb2)
@@ -636,24 +656,39 @@ class Engine:
         es = feat.t.element_size()
         self._run("cab_combine", "cab", 2 * N * h32 * w32 * 256 * es, 0, self.lib.cabinet_cab_combine, g.ptr, feat.ptr,
                   r.ptr, feat2.ptr, feat2.ld, self.gamma.data_ptr(), self.dt, N * h32 * w32, 256, self.stream)
-        aux8 = high = None
+        aux8 = high = low = None
+
+        def low_path():
+            if fold_low:  # fp32 [N, h32, w32, 256] map that the convblk epilogue upsamples and adds
+                return self.conv(feat2, self.low_fold, out_dtype=torch.float32)
+            lo = self.conv(feat2, self.convb)
+            self.bilinear(lo, cat_ffm.slice(128, 256), "low_up")   # 1/32 -> 1/8 (reference: cabinet.py:228-233)
+            return lo
+
         if need_aux or self.debug:
             aux8 = self.new(N, H8, W8, C, torch.float32)
-            with self._branch(0) as joined:  # low-level path (convb + x4 upsample into the FFM concat) beside b1 / b4
-                low = self.conv(feat2, self.convb)
-                self.bilinear(low, cat_ffm.slice(128, 256), "low_up")   # 1/32 -> 1/8 (reference: cabinet.py:228-233)
+            with self._branch(0) as joined:  # low-level path beside b1 / b4
+                low = low_path()
                 joined(low.t)
             fused = self.conv(cat_b1, self.b1)
             high = self.conv(fused, self.b4, out_dtype=torch.float32)  # class logits stay fp32
             self.bilinear(high, aux8, "high_up")
             self._join(0)
         else:
-            low = self.conv(feat2, self.convb)
-            self.bilinear(low, cat_ffm.slice(128, 256), "low_up")
+            low = low_path()
 
         # ---- feature fusion (reference: cabinet.py:142-153)
         self._join(2)
-        ff = self.conv(cat_ffm, self.ffm_blk)
+        if fold_low:
+            L = self.ffm_sb
+            ff = self.new(N, H8, W8, L.cout)
+            M = N * H8 * W8
+            self._run("conv_tc", L.name, (M * (L.cin + L.cout) + L.w.numel()) * 2 + low.t.numel() * 4,
+                      2 * M * L.cout * L.cin, self.lib.cabinet_conv_tc_up, cat_ffm.ptr, cat_ffm.ld, N, H8, W8, L.cin,
+                      L.tc.data_ptr(), L.cout, 1, 1, 1, 0, L.b.data_ptr(), low.ptr, low.H, low.W, ff.ptr, ff.ld, H8, W8,
+                      L.act, self.stream)
+        else:
+            ff = self.conv(cat_ffm, self.ffm_blk)
         gap = gap_all[n_se].view(-1)[: N * 256].view(N, 256)
         scratch = ffm_scratch
         self._run("channel_sum", "ffm.gap", 0, 0, self.lib.cabinet_channel_sum, ff.ptr, ff.ld, ff.dt, N, H8 * W8, 256,

@@ -119,6 +119,16 @@ int cabinet_mbconv_noexpand_fused(const void* x, long long ldx, const float* w_d
                                   const float* w_pw, const float* b_pw, void* y, long long ldy, int N, int H, int W,
                                   int C, int act, cabinet_stream_t stream);
 
+/* conv_tc whose epilogue adds a bilinearly upsampled (align_corners=False) low-resolution fp32 map before the
+ * activation:  y = act(conv(x) + bias + bilinear(up [N][up_h][up_w][Cout] -> OH x OW)).
+ * A 1x1 convolution commutes with bilinear interpolation, so the part of `FeatureFusionModule.convblk` that reads the
+ * upsampled attention features (src/models/cabinet.py:228-231,143-144) is computed at 1/32 resolution (with
+ * `AttentionBranch.convb`, cabinet.py:86, folded into its weights) and added here: the x4-upsampled 256-channel
+ * tensor is never written and the GEMM's K shrinks from 384 to 128.  bf16 output, Cout % 16 == 0, act ReLU or none. */
+int cabinet_conv_tc_up(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_packed, int Cout,
+                       int KH, int KW, int stride, int pad, const float* bias, const float* up, int up_h, int up_w,
+                       void* y, long long ldy, int OH, int OW, int act, cabinet_stream_t stream);
+
 /* cabinet_conv_tc whose activation applies to the first act_cols output channels only (act_cols % 16 == 0): several
  * convolutions of the SAME input merged into one GEMM, e.g. GlobalContextAttention's to_query | to_key (Conv+BN+ReLU) |
  * to_value (plain conv), src/models/cab.py:107-128, as one 256 -> 384 projection with act_cols = 256. */

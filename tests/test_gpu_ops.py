@@ -746,3 +746,42 @@ def test_argmax_hist_nchw(C, H, W):
                                        hist.data_ptr(), stream()), "argmax_hist")  # hist only
     np.testing.assert_array_equal(hist.cpu().numpy(), h)
     check(lib.cabinet_argmax_hist_nchw(pd.data_ptr(), 0, C, H * W, None, 1, 0, 255, hist.data_ptr(), stream()), "empty")
+
+
+@pytest.mark.parametrize("cin,cout,k,p,H,W,UH,UW,act", [
+    (128, 256, 1, 0, 32, 32, 8, 8, ACT_RELU),      # the FFM case: flat 1x1 tile walk, exact x4
+    (128, 256, 1, 0, 9, 13, 3, 4, ACT_RELU),       # odd sizes: generic bilinear ratio, tiles straddle images
+    (64, 48, 1, 0, 20, 12, 5, 3, ACT_NONE),        # Cout = 48 (three 16-column chunks), no activation
+    (32, 64, 3, 1, 16, 24, 4, 6, ACT_RELU),        # 3x3: patch tile walk (per-image coordinates)
+])
+def test_conv_tc_upsample_add_epilogue(cin, cout, k, p, H, W, UH, UW, act):
+    """y = act(conv(x) + b + bilinear(up -> H x W)): the FFM convblk with the x4 upsample commuted behind the 1x1
+    conv (reference: cabinet.py:228-231,143-144), against fp32 torch on the CPU."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    N = 3
+    x = q(gen(N, cin, H, W, seed=1), dtype)
+    w = q(gen(cout, cin, k, k, seed=2, scale=(cin * k * k) ** -0.5), dtype)
+    b = gen(cout, seed=3, scale=0.1)
+    up = gen(N, cout, UH, UW, seed=4)
+    ref = act_ref(F.conv2d(x, w, b, 1, p) + F.interpolate(up, (H, W), mode="bilinear", align_corners=False), act)
+    xm = to_map(x, dtype, ld=cin + 16, off=8)
+    ym = to_map(torch.zeros(N, cout, H, W), dtype, ld=cout + 24, off=16)
+    ym.t.fill_(7.0)
+    upd = up.permute(0, 2, 3, 1).contiguous().cuda()
+    n16, c64 = -(-cout // 16) * 16, -(-cin // 64) * 64
+    pk = torch.zeros(n16, k * k, c64)
+    pk[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin)
+    pk = pk.to("cuda", dtype).contiguous()
+    bd = b.cuda()
+    check(lib.cabinet_conv_tc_up(xm.ptr, xm.ld, N, H, W, cin, pk.data_ptr(), cout, k, k, 1, p, bd.data_ptr(),
+                                 upd.data_ptr(), UH, UW, ym.ptr, ym.ld, H, W, act, stream()), "conv_tc_up")
+    torch.cuda.synchronize()
+    err = rel_l2(from_map(ym), ref)
+    print(f"conv_tc_up cin={cin} cout={cout} k={k} {H}x{W} <- {UH}x{UW}: rel_l2 {err:.3e}")
+    assert err < 6e-3
+    full = ym.t.float()
+    assert float((full[..., : ym.off] - 7.0).abs().max()) == 0 and float((full[..., ym.off + cout:] - 7.0).abs().max()) == 0
+    with pytest.raises(ValueError):  # Cout must be a multiple of 16
+        check(lib.cabinet_conv_tc_up(xm.ptr, xm.ld, N, H, W, cin, pk.data_ptr(), cout - 3, k, k, 1, p, bd.data_ptr(),
+                                     upd.data_ptr(), UH, UW, ym.ptr, ym.ld, H, W, act, stream()), "conv_tc_up")
