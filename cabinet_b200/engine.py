@@ -142,7 +142,10 @@ class Engine:
         self.fuse_mbconv = True     # expand + depthwise (+ project) in one kernel for blocks with <= 64 input channels
         self.fold_se_relu = True    # ReLU SE blocks: gate folded into per-image project weights (relu(s*d) = s*relu(d))
         self.fold_ffm = True        # FFM gate folded into per-image head-conv weights (no rewrite of the fused feature map)
-        self.fold_low_up = True     # convb + x4 upsample + the low half of ffm.convblk as a 1/32-resolution conv + epilogue add
+        # convb + x4 upsample + the low half of ffm.convblk as a 1/32-resolution conv + upsample-add in the convblk epilogue
+        # (cabinet_conv_tc_up).  Correct and parity-tested, but measured SLOWER (convblk 72 -> 146 us): every output
+        # element gathers 4 fp32 taps, 8x the bytes it writes, through a small L1 -> off by default
+        self.fold_low_up = False
         self.fuse_se = False        # SE apply as A-operand prologue of the project GEMM (slower than scale_act today)
         self.use_cuda_graph = False
         self.sub_batch = 0          # > 0: run the schedule over chunks of this many images
