@@ -370,7 +370,8 @@ def run_ours(args):
 
         masks = [torch.empty((B, S, S), dtype=torch.uint8).pin_memory() for _ in range(K)]  # D2H targets, allocated up front
         ev = MscEvalV0(model, [(x_host, lb_host)] * 4, C, 255, (1.0,), False, cropsize=S)
-        ev.evaluate(masks_out=masks)  # warm-up: device buffers + captured graphs of the fused forward/hist call
+        for _ in range(2):  # warm-up (8 batches): ring buffers, captured graphs of the fused forward/hist call, first replays
+            ev.evaluate(masks_out=masks)
         ev.dl = [(x_host, lb_host)] * K
         barrier()
         t0 = time.perf_counter()
@@ -391,7 +392,8 @@ def run_ours(args):
                                 generator=torch.Generator().manual_seed(21 + rank)).pin_memory()
         masks8 = masks
         ev8 = MscEvalV0(model, [(u8_host, lb_host)] * 4, C, 255, (1.0,), False, cropsize=S)
-        ev8.evaluate(masks_out=masks8)
+        for _ in range(2):
+            ev8.evaluate(masks_out=masks8)
         ev8.dl = [(u8_host, lb_host)] * K
         barrier()
         e0.record()

@@ -17,19 +17,21 @@ x = make_input(B, S, S, seed=7).pin_memory()
 lb = make_labels(B, S, S, C, seed=11).to(torch.uint8).pin_memory()
 masks = [torch.empty((B, S, S), dtype=torch.uint8).pin_memory() for _ in range(K)]
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for chunk in (16, 8, 4, 2):
+for chunk in (8, 16):
     ev = MscEvalV0(model, [(x, lb)] * 4, C, 255, (1.0,), False, cropsize=S)
     ev.chunk = chunk
     ev.evaluate(masks_out=masks)
     ev.dl = [(x, lb)] * K
-    best = 1e9
-    for _ in range(3):
+    ts = []
+    for _ in range(5):
         torch.cuda.synchronize()
         e0.record()
         ev.evaluate(masks_out=masks)
         e1.record()
         torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1))
-    print(f"chunk {chunk:2d}: {best / K:.3f} ms/step  {B * K / best * 1e3:.0f} img/s", flush=True)
+        ts.append(e0.elapsed_time(e1))
+    best = min(ts)
+    print(f"chunk {chunk:2d}: {best / K:.3f} ms/step  {B * K / best * 1e3:.0f} img/s   all runs (ms/step): "
+          + " ".join(f"{t / K:.3f}" for t in ts), flush=True)
     del ev
     model.engine()._graphs.clear()
