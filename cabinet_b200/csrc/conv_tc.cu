@@ -30,6 +30,9 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int C_STAGE_BYTES = BLOCK_M * 128;  // one [128 rows x 64 ch] bf16 store box
 constexpr int MAX_STAGES = 8;
 constexpr int NUM_THREADS = 320;
+constexpr int PRO_THREADS = 256;                 // A-operand prologue warps (PRO variants): 8 warps, 4 chunks of a row each
+// (16 warps were measured: 10 % faster without a residual, 30-40 % slower with one -- 72 registers per thread spill the epilogue)
+constexpr int PRO_CHUNKS = 8 * 128 / PRO_THREADS;  // 16-byte chunks of its A row per prologue thread
 constexpr int B_RESIDENT_MAX = 80 * 1024;  // sb.conv2 (3x3, 64 -> 64: 72 KB) stays resident
 constexpr int SMEM_LIMIT = 220 * 1024;
 
@@ -75,7 +78,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int tile
 }
 
 template <int ACT, bool HAS_RES, bool OUT_F32, bool PRO, bool UP4 = false>
-__global__ void __launch_bounds__(PRO ? NUM_THREADS + 256 : NUM_THREADS, 1)
+__global__ void __launch_bounds__(PRO ? NUM_THREADS + PRO_THREADS : NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
@@ -103,7 +106,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int s = 0; s < p.stages; ++s) {
             tc::mbar_init(&full_bar[s], 1);
             tc::mbar_init(&empty_bar[s], 1);
-            tc::mbar_init(&ready_bar[s], 8);
+            tc::mbar_init(&ready_bar[s], PRO_THREADS / 32);
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&acc_full[s], 1);
@@ -213,7 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // project 1x1 so the depthwise output is read from HBM once and never rewritten.
         // 8 warps: thread = (A row = pixel of the tile, half of its eight 16-byte chunks).  All shared / global loads of
         // a stage are issued before the first dependent instruction.
-        const int r = (threadIdx.x - NUM_THREADS) & 127, half = (threadIdx.x - NUM_THREADS) >> 7;
+        const int r = (threadIdx.x - NUM_THREADS) & 127, half = (threadIdx.x - NUM_THREADS) >> 7;  // half = part of the row
         int s = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -228,13 +231,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 tc::mbar_wait(&full_bar[s], ph);
                 const uint32_t rowa = tc::smem_u32(sA) + s * A_STAGE_BYTES + r * 128;
                 {
-                uint4 raw[4];
-                float4 s0[4], s1[4];
+                uint4 raw[PRO_CHUNKS];
+                float4 s0[PRO_CHUNKS], s1[PRO_CHUNKS];
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
+                for (int jj = 0; jj < PRO_CHUNKS; ++jj) {
                     // walk LOGICAL chunks: the 8 rows of a quarter-warp then touch 8 different physical chunks
                     // (conflict-free; walking physical chunks is an 8-way bank conflict) and share the scale address
-                    const int l = half * 4 + jj;
+                    const int l = half * PRO_CHUNKS + jj;
                     const int j = l ^ (r & 7);
                     const int c = cb * BLOCK_K + (l << 3);
                     if (c < p.Cin) {
@@ -244,8 +247,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                 }
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int l = half * 4 + jj;
+                for (int jj = 0; jj < PRO_CHUNKS; ++jj) {
+                    const int l = half * PRO_CHUNKS + jj;
                     const int j = l ^ (r & 7);
                     const int c = cb * BLOCK_K + (l << 3);
                     if (c < p.Cin) {
@@ -682,7 +685,7 @@ static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int C
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT + 1024));          \
             attr_done = true;                                                                                        \
         }                                                                                                            \
-        conv_tc_kernel<ACT_, RES_, F32_, PRO_><<<grid, (PRO_) ? NUM_THREADS + 256 : NUM_THREADS, smem, st>>>(        \
+        conv_tc_kernel<ACT_, RES_, F32_, PRO_><<<grid, (PRO_) ? NUM_THREADS + PRO_THREADS : NUM_THREADS, smem, st>>>( \
             tmA[0], tmA[1], tmA[2], tmA[3], tmB, tmY, p);                                                            \
     } while (0)
 #define CAB_TC_LAUNCH_UP(ACT_)                                                                                       \
