@@ -33,8 +33,10 @@ def main():
     fam = collections.OrderedDict()
     for r in rows:
         name = next(f for f, pat in FAMILIES if re.search(pat, r["name"]))
-        f = fam.setdefault(name, {"launches": 0, "time_ns": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0})
+        f = fam.setdefault(name, {"launches": 0, "time_ns": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0,
+                                  "per_launch_dram_bytes": []})  # in launch order (= schedule order of the forward)
         f["launches"] += 1
+        f["per_launch_dram_bytes"].append(r.get("dram__bytes_read.sum", 0.0) + r.get("dram__bytes_write.sum", 0.0))
         f["time_ns"] += r.get("gpu__time_duration.sum", 0.0)
         f["dram_read_bytes"] += r.get("dram__bytes_read.sum", 0.0)
         f["dram_write_bytes"] += r.get("dram__bytes_write.sum", 0.0)
