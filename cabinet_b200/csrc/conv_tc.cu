@@ -90,6 +90,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2], bres_bar;
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float s_bias[2][256];  // per epilogue warpgroup: bias slice of its current cout tile
+    __shared__ __align__(16) float s_ascale[PRO ? 1024 : 4];  // PRO: the A-operand scale row of the tile's image
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_stage_bytes = p.block_n * BLOCK_K * 2;
@@ -226,6 +227,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int img = p.tiles_h == 1 && p.OH == 1 ? static_cast<int>(min(pixrow, static_cast<long long>(p.OW) - 1) / p.hw)
                                                         : tcd.img;
             const float* sc = p.a_scale + static_cast<long long>(img) * p.Cin;
+            // The scale row is read once per tile into shared memory when all rows of the tile belong to one image
+            // (always, except flat tiles that straddle an image boundary): per-stage __ldg's of it were the dominant
+            // stall of this path (long scoreboard), 11 stages x 8 loads per thread and tile.
+            bool sc_smem = p.Cin <= 1024 && (p.Cin & 3) == 0;
+            if (p.tiles_h == 1 && p.OH == 1) {
+                const long long last = min(static_cast<long long>(tcd.ow0) + 127, static_cast<long long>(p.OW) - 1);
+                sc_smem = sc_smem && (tcd.ow0 / p.hw == last / p.hw);
+            }
+            tc::named_bar_sync(3, PRO_THREADS);  // the previous tile's stages no longer read s_ascale
+            if (sc_smem) {
+                const float* sc0 = p.a_scale + static_cast<long long>(p.tiles_h == 1 && p.OH == 1 ? tcd.ow0 / p.hw : tcd.img) * p.Cin;
+                for (int i = threadIdx.x - NUM_THREADS; i < (p.Cin >> 2); i += PRO_THREADS)
+                    reinterpret_cast<float4*>(s_ascale)[i] = __ldg(reinterpret_cast<const float4*>(sc0) + i);
+            }
+            tc::named_bar_sync(3, PRO_THREADS);
             int cb = 0;
             for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                 tc::mbar_wait(&full_bar[s], ph);
@@ -242,8 +258,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     const int c = cb * BLOCK_K + (l << 3);
                     if (c < p.Cin) {
                         raw[jj] = tc::lds128(rowa + (j << 4));
-                        s0[jj] = __ldg(reinterpret_cast<const float4*>(sc + c));
-                        s1[jj] = __ldg(reinterpret_cast<const float4*>(sc + c) + 1);
+                        if (sc_smem) {
+                            s0[jj] = *reinterpret_cast<const float4*>(s_ascale + c);
+                            s1[jj] = *reinterpret_cast<const float4*>(s_ascale + c + 4);
+                        } else {
+                            s0[jj] = __ldg(reinterpret_cast<const float4*>(sc + c));
+                            s1[jj] = __ldg(reinterpret_cast<const float4*>(sc + c) + 1);
+                        }
                     }
                 }
 #pragma unroll
@@ -600,7 +621,8 @@ static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int C
     // that two CTAs (e.g. from two streams) can share an SM
     static const int cap_kb = getenv("CAB_SMEM_CAP_KB") ? atoi(getenv("CAB_SMEM_CAP_KB")) : 0;
     const int limit = (cap_kb > 0 && p.tmem_cols <= 256) ? std::max(cap_kb * 1024, fixed + 2 * stage_bytes) : SMEM_LIMIT;
-    p.stages = std::max(2, std::min(MAX_STAGES, (std::min(limit, SMEM_LIMIT) - fixed) / stage_bytes));
+    // the prologue variants keep a 4 KB scale row in static shared memory: leave room for it under the 227 KB CTA limit
+    p.stages = std::max(2, std::min(MAX_STAGES, (std::min(limit, SMEM_LIMIT) - (a_scale ? 4096 : 0) - fixed) / stage_bytes));
     p.act = act; p.y_dtype = y_dtype; p.bias = bias; p.res = reinterpret_cast<const bf16*>(res); p.ldres = ldres;
     p.y = y; p.ldy = ldy; p.debug = g_debug;
     p.a_scale = a_scale; p.a_act = a_act; p.hw = H * W;
@@ -682,7 +704,8 @@ static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int C
         static bool attr_done = false;                                                                               \
         if (!attr_done) {                                                                                            \
             CAB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT_, RES_, F32_, PRO_>,                                    \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT + 1024));          \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,                               \
+                                          SMEM_LIMIT + 1024 - ((PRO_) ? 4096 : 0)));                                 \
             attr_done = true;                                                                                        \
         }                                                                                                            \
         conv_tc_kernel<ACT_, RES_, F32_, PRO_><<<grid, (PRO_) ? NUM_THREADS + PRO_THREADS : NUM_THREADS, smem, st>>>( \
