@@ -146,7 +146,9 @@ class Engine:
         # (cabinet_conv_tc_up).  Correct and parity-tested, but measured SLOWER (convblk 72 -> 146 us): every output
         # element gathers 4 fp32 taps, 8x the bytes it writes, through a small L1 -> off by default
         self.fold_low_up = False
-        self.fuse_se = False        # SE apply as A-operand prologue of the project GEMM (slower than scale_act today)
+        self.fuse_se = False        # SE apply as A-operand prologue of the project GEMM for every hard-swish SE block
+        # ... or only for the blocks where it measured faster than scale_act + plain GEMM (tools/trace_se.py)
+        self.fuse_se_blocks = frozenset({"mobile.f12", "mobile.f13"})
         self.use_cuda_graph = False
         self.sub_batch = 0          # > 0: run the schedule over chunks of this many images
         self._graphs = {}
@@ -615,7 +617,8 @@ class Engine:
                 # expand form: SE then activation; no-expand form: activation (already applied) then SE (F10)
                 se_act = e["act"] if s["expand"] else ACT_NONE
                 pw2 = e["pw2"]
-                if self.fuse_se and self.use_tc and pw2.tc is not None and d.dt == BF16 and d.C % 8 == 0:
+                if ((self.fuse_se or e["dw"].name[:-3] in self.fuse_se_blocks) and not self.debug and self.use_tc
+                        and pw2.tc is not None and d.dt == BF16 and d.C % 8 == 0):
                     # fused: the project GEMM applies act(x * scale) to its A tiles in shared memory
                     f = self.conv(d, pw2, res=f if s["identity"] else None, a_scale=scale, a_act=se_act)
                     continue

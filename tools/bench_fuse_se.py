@@ -5,10 +5,11 @@ model = build_model(8, "large").cuda()
 model.logits_dtype = torch.bfloat16
 model.use_cuda_graph = True
 x = make_input(16, 1024, 1024).cuda()
-for fuse in (False, True, False, True):
+for fuse in (False, "sel", True, False, "sel", True):
     model._engine = None if hasattr(model, "_engine") else None
     eng = model.engine()
-    eng.fuse_se = fuse
+    eng.fuse_se = fuse is True
+    eng.fuse_se_blocks = frozenset({"mobile.f12", "mobile.f13"}) if fuse == "sel" else frozenset()
     eng._graphs.clear(); eng._graph_seen.clear()
     for _ in range(4): model(x)
     torch.cuda.synchronize()
