@@ -114,7 +114,9 @@ __global__ void __launch_bounds__(256)
 scale_act_kernel(T* __restrict__ x, long long ldx, const float* __restrict__ scale, int HW, int C, int act,
                  int plus_one, int pix_per_block) {
     constexpr int V = Vec16<T>::N;
+    // (walking the tensor back to front, as channel_sum does, measured 10-15 % SLOWER here: these tensors fit L2 whole)
     const int n = blockIdx.y;
+    const int bx = blockIdx.x;
     const int CG = C / V;
     const int lanes = blockDim.x / CG;  // pixel lanes (CG <= 256 / 2 checked by the host)
     const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
@@ -122,7 +124,7 @@ scale_act_kernel(T* __restrict__ x, long long ldx, const float* __restrict__ sca
     float sc[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) sc[i] = __ldg(scale + static_cast<long long>(n) * C + cg * V + i);
-    const int p0 = blockIdx.x * pix_per_block;
+    const int p0 = bx * pix_per_block;
     const int p1 = min(p0 + pix_per_block, HW);
     T* base = x + (static_cast<long long>(n) * HW) * ldx + cg * V;
     for (int p = p0 + pl; p < p1; p += lanes) {
@@ -199,9 +201,12 @@ channel_sum_kernel(const T* __restrict__ x, long long ldx, long long HW, int C, 
     constexpr int V = Vec16<T>::N;
     extern __shared__ float s_red[];  // [rows][C]
     __shared__ bool s_last;
-    const int n = blockIdx.y, nb = gridDim.x;
+    // blocks are dispatched in (x, y) order: map them back to front, so the kernel starts on the part of the 134 MB
+    // tensor its producer wrote last (still L2 resident) instead of evicting it while streaming the evicted head
+    const int n = static_cast<int>(gridDim.y - 1 - blockIdx.y), nb = gridDim.x;
+    const int bxr = static_cast<int>(gridDim.x - 1 - blockIdx.x);
     const int CG = C / V;
-    const long long p0 = blockIdx.x * pix_per_block;
+    const long long p0 = bxr * pix_per_block;
     const long long p1 = min(p0 + pix_per_block, HW);
     const int rows = blockDim.x / CG;  // pixels processed per sweep (CG <= blockDim.x is checked by the host)
     const int cg = threadIdx.x % CG, pr = threadIdx.x / CG;
@@ -231,7 +236,7 @@ channel_sum_kernel(const T* __restrict__ x, long long ldx, long long HW, int C, 
         for (int i = 0; i < V; ++i) s_red[pr * C + cg * V + i] = acc[i];
     }
     __syncthreads();
-    float* mine = partial + (static_cast<long long>(n) * nb + blockIdx.x) * C;
+    float* mine = partial + (static_cast<long long>(n) * nb + bxr) * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float sum = 0.f;
         for (int r = 0; r < rows; ++r) sum += s_red[r * C + c];
