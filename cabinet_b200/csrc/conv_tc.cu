@@ -44,6 +44,7 @@ struct TcConvParams {
     int block_n, n_tiles, num_tiles, tmem_cols, stages, b_resident;
     int act, y_dtype, debug;
     int act_cols;             // the activation applies to output channels < act_cols only (merged q|k|v projection)
+    int reverse;              // walk the tiles back to front (start on the part of the input its producer left in L2)
     int b_per_image;          // weights differ per image (cabinet_conv_tc_imgw): B tiles are fetched with the tile's image index
     int c_bufs;               // store staging buffers per epilogue warpgroup: 2, or 1 when a tile is a single 64-column group
     int a_act, hw;            // A-operand prologue: x <- act(x * a_scale[image][channel]); hw = pixels per image
@@ -67,6 +68,7 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const TcConvParams& p, int tile) {
     TileCoord c;
+    if (p.reverse) tile = p.num_tiles - 1 - tile;
     const int m = tile / p.n_tiles;
     c.n0 = (tile - m * p.n_tiles) * p.block_n;
     const int tw_i = m % p.tiles_w;
@@ -580,6 +582,8 @@ static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int C
                         int OH, int OW, int act, cabinet_stream_t stream, int act_cols, const float* up, int up_h,
                         int up_w) {
     CAB_REQUIRE(x && w_packed && bias && y, "conv_tc: null pointer");
+    const int reverse = (act & CABINET_CONV_REVERSE_TILES) ? 1 : 0;
+    act &= ~CABINET_CONV_REVERSE_TILES;
     CAB_REQUIRE(!up || (up_h > 0 && up_w > 0 && Cout % 16 == 0 && (reinterpret_cast<uintptr_t>(up) & 15) == 0 && !res &&
                         !a_scale && y_dtype == CABINET_BF16 && w_image_stride == 0),
                 "conv_tc_up: the upsample-add epilogue needs Cout %% 16 == 0, an aligned fp32 map, bf16 output, no residual");
@@ -612,6 +616,7 @@ static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int C
     while (p.tmem_cols < 2 * p.block_n) p.tmem_cols *= 2;
     const int b_stage_bytes = p.block_n * BLOCK_K * 2;
     p.act_cols = act_cols;
+    p.reverse = reverse;
     p.b_per_image = w_image_stride > 0 ? 1 : 0;
     p.b_resident = (!p.b_per_image && p.n_tiles == 1 && p.num_k_blocks * b_stage_bytes <= B_RESIDENT_MAX) ? 1 : 0;
     p.c_bufs = (y_dtype == CABINET_BF16 && p.block_n > 64) ? 2 : 1;

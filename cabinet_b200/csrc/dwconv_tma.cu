@@ -15,7 +15,7 @@ namespace {
 constexpr int TH = 8, TW = 16, RUN = 4;
 
 struct DwParams {
-    int C, OH, OW, CB, act;
+    int C, OH, OW, CB, act, reverse;  // reverse: blocks walk (tile, image) back to front (CABINET_CONV_REVERSE_TILES)
     const float* w;
     const float* bias;
     bf16* y;
@@ -120,8 +120,9 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmX, const DwParams p) {
     __shared__ float s_gap[64];
 
     const int tiles_w = (p.OW + TW - 1) / TW;
-    const int ow0 = (blockIdx.x % tiles_w) * TW, oh0 = (blockIdx.x / tiles_w) * TH;
-    const int chunk = blockIdx.y, n = blockIdx.z;
+    const int bx = p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+    const int ow0 = (bx % tiles_w) * TW, oh0 = (bx / tiles_w) * TH;
+    const int chunk = blockIdx.y, n = p.reverse ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
     uint8_t* tile = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dw) + 127) & ~uintptr_t(127));
 
     if (threadIdx.x == 0) {
@@ -405,6 +406,8 @@ extern "C" int cabinet_dwconv_tma(const void* x, long long ldx, const float* w, 
                                   long long ldy, int N, int H, int W, int C, int k, int stride, int OH, int OW, int act,
                                   float* gap_sum, cabinet_stream_t stream) {
     CAB_REQUIRE(x && w && bias && y, "dwconv_tma: null pointer");
+    const int reverse = (act & CABINET_CONV_REVERSE_TILES) ? 1 : 0;
+    act &= ~CABINET_CONV_REVERSE_TILES;
     CAB_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2), "dwconv_tma: k must be 3|5 and stride 1|2");
     CAB_REQUIRE(C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C &&
                     (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
@@ -416,7 +419,7 @@ extern "C" int cabinet_dwconv_tma(const void* x, long long ldx, const float* w, 
     if (N == 0) return CABINET_OK;
     DwParams p;
     const int n_chunks = (C + 63) / 64;
-    p.C = C; p.OH = OH; p.OW = OW; p.act = act; p.w = w; p.bias = bias;
+    p.C = C; p.OH = OH; p.OW = OW; p.act = act; p.w = w; p.bias = bias; p.reverse = reverse;
     // balanced chunks (multiples of 8 channels, <= 64): 72 -> 40 + 32, 200 -> 56 + 56 + 56 + 32.  A ragged 8-channel
     // tail would pack 8 column groups into a warp whose rows sit a multiple of 128 B apart: an 8-way bank conflict
     // that makes the tail cost more than a full chunk.  The TMA box stays 64 channels wide.

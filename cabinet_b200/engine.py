@@ -146,6 +146,9 @@ class Engine:
         # (cabinet_conv_tc_up).  Correct and parity-tested, but measured SLOWER (convblk 72 -> 146 us): every output
         # element gathers 4 fp32 taps, 8x the bytes it writes, through a small L1 -> off by default
         self.fold_low_up = False
+        # layers that walk their tiles back to front: their input (> L2) was written by the previous kernel, whose tail
+        # is still L2 resident; the next layer then finds THIS layer's head in L2
+        self.reverse_layers = frozenset()
         self.fuse_se = False        # SE apply as A-operand prologue of the project GEMM for every hard-swish SE block
         # ... or only for the blocks where it measured faster than scale_act + plain GEMM (tools/trace_se.py)
         self.fuse_se_blocks = frozenset({"mobile.f12", "mobile.f13"})
@@ -340,12 +343,14 @@ class Engine:
                   1.0, self.stream)
         return out
 
+    REVERSE_TILES = 0x100  # CABINET_CONV_REVERSE_TILES
+
     def _conv_tc(self, x: Map, L: ConvLayer, out: Map, res: Optional[Map], OH, OW, nbytes, flops, a_scale=None, a_act=0):
         self._run("conv_tc", L.name, nbytes, flops, self.lib.cabinet_conv_tc_se, x.ptr, x.ld, x.N, x.H, x.W, x.C,
                   a_scale.data_ptr() if a_scale is not None else None, a_act,
                   L.tc.data_ptr(), L.cout, L.kh, L.kw, L.stride, L.pad, L.b.data_ptr(),
                   res.ptr if res is not None else None, res.ld if res is not None else 0, out.ptr, out.dt, out.ld,
-                  OH, OW, L.act, self.stream)
+                  OH, OW, L.act | (self.REVERSE_TILES if L.name in self.reverse_layers else 0), self.stream)
 
     def dwconv(self, x: Map, L: DwLayer, gap: Optional[torch.Tensor] = None) -> Map:
         p = (L.k - 1) // 2
@@ -357,7 +362,8 @@ class Engine:
         gp = gap.data_ptr() if gap is not None else None
         if self.use_tc and x.dt == BF16 and x.ld % 8 == 0 and x.off % 8 == 0:
             self._run("dwconv_tma", L.name, nbytes, flops, self.lib.cabinet_dwconv_tma, x.ptr, x.ld, L.w.data_ptr(),
-                      L.b.data_ptr(), out.ptr, out.ld, x.N, x.H, x.W, x.C, L.k, L.stride, OH, OW, L.act, gp, self.stream)
+                      L.b.data_ptr(), out.ptr, out.ld, x.N, x.H, x.W, x.C, L.k, L.stride, OH, OW,
+                      L.act | (self.REVERSE_TILES if L.name in self.reverse_layers else 0), gp, self.stream)
         else:
             self._run("dwconv", L.name, nbytes, flops, self.lib.cabinet_dwconv, x.ptr, x.ld, L.w.data_ptr(),
                       L.b.data_ptr(), out.ptr, out.ld, x.dt, x.N, x.H, x.W, x.C, L.k, L.stride, OH, OW, L.act, gp,

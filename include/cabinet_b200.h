@@ -33,6 +33,9 @@ enum {
     CABINET_ACT_HSIGMOID = 3, /* src/models/mobilenetv3.py:38-50 */
     CABINET_ACT_SIGMOID = 4   /* nn.Sigmoid */
 };
+/* OR into the `act` argument of the cabinet_conv_tc* entry points: walk the output tiles back to front, so a layer whose
+ * input is larger than L2 starts on the part its producer wrote last (still L2 resident).  Results are identical. */
+#define CABINET_CONV_REVERSE_TILES 0x100
 
 typedef void* cabinet_stream_t; /* cudaStream_t */
 
