@@ -7,9 +7,9 @@ model.use_cuda_graph = True
 x = make_input(16, 1024, 1024).cuda()
 ref = None
 for layers in ((), ("sb.conv2",), ("mobile.f4.dw",), ("ffm.convblk",), ("sb.conv2", "mobile.f4.dw"), (), ("sb.conv2", "mobile.f4.dw")):
+    model.repack()  # fresh engine (and graph pool) per configuration
     eng = model.engine()
     eng.reverse_layers = frozenset(layers)
-    eng._graphs.clear(); eng._graph_seen.clear()
     for _ in range(4): out = model(x)
     torch.cuda.synchronize()
     if ref is None: ref = out[0].clone()
