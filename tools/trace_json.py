@@ -1,8 +1,10 @@
-"""Per-launch trace of one forward (CUDA events around every kernel): python tools_trace.py [batch] [size] [out.json]"""
+"""Per-launch trace of one forward (CUDA events around every kernel): python tools/trace_json.py [batch] [size] [out.json]"""
 import json
 import sys
 
 import torch
+
+sys.path.insert(0, ".")
 
 from cabinet_b200.synthetic import build_model, make_input
 
