@@ -37,10 +37,15 @@ constexpr int W_KB_BYTES = NOUT * 128;                // 10240
 constexpr int ACC_STAGES = 2;
 constexpr int ACC_COLS = 128;                         // TMEM columns per accumulator stage (80 used)
 constexpr int NUM_THREADS = 448;
+constexpr int WINB_PITCH = 96;                        // bf16 copy of the window: row pitch in bytes (40 used + pad: rows 2
+                                                      // apart land 16 banks apart, so a warp's two pixel rows never collide)
+constexpr int WINB_BYTES = 3 * WIN_H * WINB_PITCH;    // 6048
+constexpr int WINB_STRIDE = 6144;
 constexpr int CSB_BYTES = 128 * 128;                  // staged [128 px x 64 ch] bf16 (swizzled)
 constexpr int CST_BYTES = 128 * 32;                   // staged [128 px x 16 ch] bf16 (dense)
 constexpr int SMEM_BYTES =
-    KBLOCKS * W_KB_BYTES + A_STAGES * A_STAGE_BYTES + WIN_STAGES * WIN_STRIDE + 2 * (CSB_BYTES + CST_BYTES) + 1024;
+    KBLOCKS * W_KB_BYTES + A_STAGES * A_STAGE_BYTES + WIN_STAGES * WIN_STRIDE + 2 * (CSB_BYTES + CST_BYTES) +
+    2 * WINB_STRIDE + 1024;
 
 struct StemParams {
     int N, OH, OW, tiles_w, tiles_h, num_tiles;
@@ -65,6 +70,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     uint8_t* sWin = sA + A_STAGES * A_STAGE_BYTES;         // 3 x [3][21][40] fp32
     uint8_t* sCsb = sWin + WIN_STAGES * WIN_STRIDE;        // 2 x staged sb output (1024-aligned: 30720 = 30 x 1024)
     uint8_t* sCst = sCsb + 2 * CSB_BYTES;                  // 2 x staged stem output
+    uint8_t* sWinB = sCst + 2 * CST_BYTES;                 // 2 x bf16 copy of the window
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -160,28 +166,41 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             const int ws = it % WIN_STAGES, as = it % A_STAGES;
             const uint32_t wph = (it / WIN_STAGES) & 1, aph = (it / A_STAGES) & 1;
             tc::mbar_wait(&win_full[ws], wph);
-            tc::mbar_wait(&a_empty[as], aph ^ 1);
             const uint32_t win = tc::smem_u32(sWin) + ws * WIN_STRIDE;
+            const uint32_t winb = tc::smem_u32(sWinB) + (it & 1) * WINB_STRIDE;
+            // pass 1: every window element is rounded to bf16 ONCE (it is used by ~12 im2col chunks); 1260 float2 pairs
+            // over 256 threads.  The im2col pass then moves 16 instead of 32 bytes per chunk and does no conversions:
+            // the kernel is shared-memory-bandwidth bound, this removes a third of the converter wavefronts.
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int pidx = ct + 256 * k;
+                if (pidx < 3 * WIN_H * (WIN_W / 2)) {
+                    const float2 f = tc::lds64f(win + pidx * 8);
+                    const int rowi = pidx / (WIN_W / 2), cp = pidx - rowi * (WIN_W / 2);
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(winb + rowi * WINB_PITCH + cp * 4), "r"(pack_bf16x2(f.x, f.y)));
+                }
+            }
+            tc::named_bar_sync(2, 256);  // the bf16 window is complete (and the fp32 stage is no longer needed)
+            if (lane == 0) tc::mbar_arrive(&win_empty[ws]);
+            tc::mbar_wait(&a_empty[as], aph ^ 1);
             const uint32_t arow = tc::smem_u32(sA) + as * A_STAGE_BYTES + r * 128;
 #pragma unroll
             for (int jj = 0; jj < 11; ++jj) {  // j = c*7 + ky; this thread takes j = half, half+2, ...
                 const int j = 2 * jj + half;
                 if (j >= 21) break;
                 const int c = j / 7, ky = j % 7;
-                const uint32_t src = win + ((c * WIN_H + 2 * oy + ky) * WIN_W + 2 * ox) * 4;
-                const float2 f0 = tc::lds64f(src), f1 = tc::lds64f(src + 8), f2 = tc::lds64f(src + 16),
-                             f3 = tc::lds64f(src + 24);
-                const uint4 v = make_uint4(pack_bf16x2(f0.x, f0.y), pack_bf16x2(f1.x, f1.y), pack_bf16x2(f2.x, f2.y),
-                                           pack_bf16x2(f3.x, f3.y));
+                const uint32_t src = winb + (c * WIN_H + 2 * oy + ky) * WINB_PITCH + ox * 4;
+                uint4 v;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.x) : "r"(src));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.y) : "r"(src + 4));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.z) : "r"(src + 8));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.w) : "r"(src + 12));
                 const int kb = j >> 3, cc = j & 7;
                 tc::sts128(arow + kb * A_KB_BYTES + ((cc ^ (r & 7)) << 4), v);
             }
             tc::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) {
-                tc::mbar_arrive(&a_full[as]);
-                tc::mbar_arrive(&win_empty[ws]);
-            }
+            if (lane == 0) tc::mbar_arrive(&a_full[as]);
         }
     } else {
         // ================= epilogue =================
