@@ -13,7 +13,7 @@
 // The folded-BN bias rides in the GEMM: K slots 168/169 of A hold 1.0 and the matching weight columns hold the bias
 // split into bf16 hi + lo parts (fp32-accurate to 2^-17), so the epilogue is activation + pack only.
 //
-// Persistent, warp specialised (448 threads):
+// Persistent, warp specialised (448 threads with CONV_WARPS = 8):
 //   warp 0      TMA producer: weights once; per tile one 3-D fp32 box {40 cols, 21 rows, 3 ch} (OOB = zero padding)
 //   warp 1      TMEM allocator + MMA issuer: 12 x tcgen05.mma (M128 N80 K16) per tile, 2 accumulator stages
 //   warps 2-9   converters (2 threads per A row): fp32 window -> bf16 im2col A tile in shared memory (2 stages)
@@ -36,7 +36,12 @@ constexpr int NOUT = 80;                              // 64 + 16
 constexpr int W_KB_BYTES = NOUT * 128;                // 10240
 constexpr int ACC_STAGES = 2;
 constexpr int ACC_COLS = 128;                         // TMEM columns per accumulator stage (80 used)
-constexpr int NUM_THREADS = 448;
+constexpr int CONV_WARPS = 8;                         // converter warps (CONV_WARPS / 4 threads per A row); 16 measured:
+                                                      // 230 -> 285 us (more shared-memory contention, 80-register cap spills)
+constexpr int CONV_THREADS = 32 * CONV_WARPS;
+constexpr int CONV_PARTS = CONV_THREADS / 128;        // threads sharing one A row
+constexpr int EPI_WARP0 = 2 + CONV_WARPS;             // first of the 4 epilogue warps
+constexpr int NUM_THREADS = 64 + CONV_THREADS + 128;
 constexpr int WINB_PITCH = 96;                        // bf16 copy of the window: row pitch in bytes (40 used + pad: rows 2
                                                       // apart land 16 banks apart, so a warp's two pixel rows never collide)
 constexpr int WINB_BYTES = 3 * WIN_H * WINB_PITCH;    // 6048
@@ -82,10 +87,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         tc::mbar_init(&w_bar, 1);
         for (int s = 0; s < WIN_STAGES; ++s) {
             tc::mbar_init(&win_full[s], 1);
-            tc::mbar_init(&win_empty[s], 8);
+            tc::mbar_init(&win_empty[s], CONV_WARPS);
         }
         for (int s = 0; s < A_STAGES; ++s) {
-            tc::mbar_init(&a_full[s], 8);
+            tc::mbar_init(&a_full[s], CONV_WARPS);
             tc::mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < ACC_STAGES; ++s) {
@@ -147,10 +152,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             tc::umma_commit_if(leader, &acc_full[cs]);
         }
         __syncwarp();
-    } else if (warp < 10) {
+    } else if (warp < EPI_WARP0) {
         // ================= converters: fp32 window -> swizzled bf16 im2col (2 threads per A row) =================
-        const int ct = threadIdx.x - 64;       // 0..255
-        const int r = ct & 127, half = ct >> 7;  // A row = output pixel of the patch; half = which chunks
+        const int ct = threadIdx.x - 64;       // 0..CONV_THREADS-1
+        const int r = ct & 127, half = ct >> 7;  // A row = output pixel of the patch; half = which chunks (j = half mod CONV_PARTS)
         const int oy = r / TW, ox = r % TW;
         if (half == 0) {
             // K padding chunks 21..23 of K-block 2 never change: chunk 21 = {1, 1, 0...} (the two bias slots), rest 0
@@ -172,21 +177,21 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             // over 256 threads.  The im2col pass then moves 16 instead of 32 bytes per chunk and does no conversions:
             // the kernel is shared-memory-bandwidth bound, this removes a third of the converter wavefronts.
 #pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                const int pidx = ct + 256 * k;
+            for (int k = 0; k < (3 * WIN_H * (WIN_W / 2) + CONV_THREADS - 1) / CONV_THREADS; ++k) {
+                const int pidx = ct + CONV_THREADS * k;
                 if (pidx < 3 * WIN_H * (WIN_W / 2)) {
                     const float2 f = tc::lds64f(win + pidx * 8);
                     const int rowi = pidx / (WIN_W / 2), cp = pidx - rowi * (WIN_W / 2);
                     asm volatile("st.shared.u32 [%0], %1;" ::"r"(winb + rowi * WINB_PITCH + cp * 4), "r"(pack_bf16x2(f.x, f.y)));
                 }
             }
-            tc::named_bar_sync(2, 256);  // the bf16 window is complete (and the fp32 stage is no longer needed)
+            tc::named_bar_sync(2, CONV_THREADS);  // the bf16 window is complete (and the fp32 stage is no longer needed)
             if (lane == 0) tc::mbar_arrive(&win_empty[ws]);
             tc::mbar_wait(&a_empty[as], aph ^ 1);
             const uint32_t arow = tc::smem_u32(sA) + as * A_STAGE_BYTES + r * 128;
 #pragma unroll
-            for (int jj = 0; jj < 11; ++jj) {  // j = c*7 + ky; this thread takes j = half, half+2, ...
-                const int j = 2 * jj + half;
+            for (int jj = 0; jj < (21 + CONV_PARTS - 1) / CONV_PARTS; ++jj) {  // j = c*7 + ky; j = half, half + CONV_PARTS, ...
+                const int j = CONV_PARTS * jj + half;
                 if (j >= 21) break;
                 const int c = j / 7, ky = j % 7;
                 const uint32_t src = winb + (c * WIN_H + 2 * oy + ky) * WINB_PITCH + ox * 4;
@@ -206,7 +211,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         // ================= epilogue =================
         const int q = warp & 3;
         const int r = q * 32 + lane;
-        const bool leader = warp == 10 && lane == 0;
+        const bool leader = warp == EPI_WARP0 && lane == 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int cs = it % ACC_STAGES;
