@@ -30,3 +30,30 @@ def test_shard_range_partitions_every_item_once():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+class _ConstantModel:
+    """Stand-in of the reference test's ConstantModel (tests/integration/test_training_pipeline.py:259-274)."""
+
+    def __init__(self, n_classes, value):
+        self.n_classes, self.value = n_classes, value
+
+    def __call__(self, x):
+        import torch
+
+        logits = torch.full((x.shape[0], self.n_classes, x.shape[2], x.shape[3]), -1e9)
+        logits[:, self.value] = 1e9
+        return logits, logits
+
+
+@pytest.mark.parametrize("n_classes,cropsize,size,value", [(4, 64, 100, 0), (3, 48, 96, 1)])
+def test_oracle_overlap_normalisation_is_uniform(n_classes, cropsize, size, value):
+    """reference tests/integration/test_training_pipeline.py:276-338: a constant model must give a spatially uniform
+    probability map whatever the window overlap (checks the oracle's count normalisation)."""
+    import torch
+
+    prob = evaluator_oracle.crop_eval(_ConstantModel(n_classes, value), torch.zeros(1, 3, size, size), n_classes,
+                                      cropsize, False)
+    assert (prob.argmax(dim=1) == value).all()
+    p = prob[0, value]
+    assert float(p.max() - p.min()) < 1e-5
