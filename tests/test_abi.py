@@ -68,3 +68,18 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     assert rc == 1 and b"null" in lib.cabinet_last_error()
     with pytest.raises(ValueError):
         _lib.check(rc, "dwconv")
+
+
+def test_header_constants_match_the_python_side():
+    """Enum / flag values the host side hard-codes must equal the header's."""
+    from cabinet_b200.engine import Engine
+
+    text = HEADER.read_text()
+    flag = re.search(r"#define\s+CABINET_CONV_REVERSE_TILES\s+(0x[0-9a-fA-F]+)", text)
+    assert flag and int(flag.group(1), 16) == Engine.REVERSE_TILES
+    enum = dict(re.findall(r"(CABINET_(?:ACT_\w+|F32|BF16))\s*=\s*(\d+)", text))
+    assert int(enum["CABINET_ACT_NONE"]) == _lib.ACT_NONE and int(enum["CABINET_ACT_RELU"]) == _lib.ACT_RELU
+    assert int(enum["CABINET_ACT_HSWISH"]) == _lib.ACT_HSWISH and int(enum["CABINET_ACT_HSIGMOID"]) == _lib.ACT_HSIGMOID
+    assert int(enum["CABINET_ACT_SIGMOID"]) == _lib.ACT_SIGMOID
+    assert int(enum["CABINET_F32"]) == _lib.F32 and int(enum["CABINET_BF16"]) == _lib.BF16
+    assert all(int(v) < 0x100 for k, v in enum.items() if k.startswith("CABINET_ACT_"))  # the flag bit stays free
