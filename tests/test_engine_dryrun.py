@@ -89,3 +89,95 @@ def test_dropin_refuses_cpu_and_train_mode():
         m(torch.zeros(1, 3, 64, 64))
     with pytest.raises(ValueError):
         m(torch.zeros(1, 4, 64, 64))
+
+
+@pytest.mark.parametrize("precision", ["bf16"])
+def test_mask_path_skips_aux_head_and_optional_schedules(cpu_engine, precision):
+    """Host logic of the schedule variants: mask / class-map callers do not launch the auxiliary head; the folded low
+    path calls cabinet_conv_tc_up; reverse_layers ORs CABINET_CONV_REVERSE_TILES into the layer's act argument."""
+    eng, rec = cpu_engine("large", 8, precision)
+    x = torch.zeros(2, 3, 64, 64)
+    eng.forward(x)
+    full = [c[0] for c in rec.calls]
+    rec.calls.clear()
+    eng.forward_mask(x)
+    mask = [c[0] for c in rec.calls]
+    assert full.count("cabinet_bilinear_nhwc") == 2 and mask.count("cabinet_bilinear_nhwc") == 1  # low_up only
+    assert mask.count("cabinet_upsample_argmax") == 1 and mask.count("cabinet_upsample_logits_nchw") == 0
+    n_conv = lambda names: sum(n.startswith("cabinet_conv_tc") or n == "cabinet_conv2d_simt" for n in names)  # noqa: E731
+    assert n_conv(full) - n_conv(mask) == 2  # b1 and b4
+    rec.calls.clear()
+    cm = eng.class_map8(x)
+    assert tuple(cm.shape) == (2, 8, 8, 8) and cm.dtype == torch.float32
+    assert [c[0] for c in rec.calls] == mask[:-1]  # the same trunk without the argmax tail
+    # folded low path
+    rec.calls.clear()
+    eng.fold_low_up = True
+    eng.forward_mask(x)
+    names = [c[0] for c in rec.calls]
+    assert names.count("cabinet_conv_tc_up") == 1 and names.count("cabinet_bilinear_nhwc") == 0
+    up = next(c[1] for c in rec.calls if c[0] == "cabinet_conv_tc_up")
+    assert up[5] == 128 and up[7] == 256 and (up[14], up[15]) == (2, 2) and (up[18], up[19]) == (8, 8)
+    eng.fold_low_up = False
+    # reversed tile walk
+    rec.calls.clear()
+    eng.reverse_layers = frozenset({"sb.conv2", "mobile.f4.dw"})
+    eng.fuse_mbconv = False
+    eng.forward_mask(x)
+    flagged = [c for c in rec.calls if c[0] in ("cabinet_conv_tc_se", "cabinet_dwconv_tma") and (c[1][-2 if c[0] == "cabinet_conv_tc_se" else -3] & 0x100)]
+    assert len(flagged) == 2
+
+
+def test_general_mode_window_geometry_matches_oracle(monkeypatch):
+    """Host glue of the fused multi-scale evaluator: for padded, exact and multi-window images the (window, destination
+    offset, clip extent, weight slice) arguments handed to cabinet_upsample_softmax_accum reproduce the oracle's
+    pad_tensor / chip_windows geometry (reference: evaluate.py:60-72,95-146)."""
+    from cabinet_b200 import evaluator as ev_mod
+    from oracle import evaluator_oracle
+
+    rec = RecordingLib()
+    monkeypatch.setattr(_lib, "load", lambda: rec)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: type("S", (), {"cuda_stream": 0})())
+
+    class FakeModel(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+            self.seen = []
+
+        def class_map8(self, x):
+            self.seen.append(tuple(x.shape))
+            return torch.zeros(x.shape[0], x.shape[2] // 8, x.shape[3] // 8, 4)
+
+    for (H, W), cs, flip in (((40, 56), 64, True), ((64, 64), 64, False), ((100, 150), 64, True), ((50, 200), 64, False)):
+        model = FakeModel()
+        ev = ev_mod.MscEvalV0(model, None, 4, 255, (1.0,), flip, cropsize=cs, device=torch.device("cpu"))
+        ev.max_chip_batch = 8
+        N = 2
+        image, dst = torch.zeros(N, 3, H, W), torch.zeros(N, 4, H, W)
+        rec.calls.clear()
+        ev._crop_eval_into(image, dst)
+        calls = [c[1] for c in rec.calls if c[0] == "cabinet_upsample_softmax_accum"]
+        # oracle geometry
+        if H < cs or W < cs:
+            tgt = (cs, cs) if max(H, W) < cs else (cs if H < W else H, cs if W < H else W)
+            _, (hst, hed, wst, wed) = evaluator_oracle.pad_tensor(image, tgt)
+            fh, fw = tgt
+        else:
+            hst = wst = 0
+            fh, fw = H, W
+        wins = evaluator_oracle.chip_windows(fh, fw, cs)
+        assert len(calls) == len(wins)
+        inv_base = {}
+        for a, (y0, y1, x0, x1) in zip(calls, wins):
+            assert (a[6], a[7]) == (cs, cs) and (a[2], a[3], a[4], a[5]) == (N, cs // 8, cs // 8, 4)
+            assert (a[12], a[13]) == (y0 - hst, x0 - wst) and (a[14], a[15]) == (H, W)
+            assert (a[9], a[10], a[11]) == (dst.stride(0), dst.stride(1), dst.stride(2))
+            assert (a[1] is not None) == flip
+            # weight slices start at the window origin of the per-axis inverse-count vectors
+            inv_base.setdefault("y", a[16] - 4 * y0)
+            inv_base.setdefault("x", a[17] - 4 * x0)
+            assert a[16] - 4 * y0 == inv_base["y"] and a[17] - 4 * x0 == inv_base["x"]
+        per_win = N * (2 if flip else 1)
+        assert sum(s[0] for s in model.seen) == len(wins) * per_win and all(s[2:] == (cs, cs) for s in model.seen)
+        assert all(s[0] <= max(8, per_win) for s in model.seen)
