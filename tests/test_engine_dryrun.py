@@ -181,3 +181,40 @@ def test_general_mode_window_geometry_matches_oracle(monkeypatch):
         per_win = N * (2 if flip else 1)
         assert sum(s[0] for s in model.seen) == len(wins) * per_win and all(s[2:] == (cs, cs) for s in model.seen)
         assert all(s[0] <= max(8, per_win) for s in model.seen)
+
+
+def test_packed_state_roundtrip_on_the_host(cpu_engine, tmp_path, monkeypatch):
+    """Engine.packed_state() -> torch.save -> torch.load -> Engine(packed=...) reproduces every packed tensor (the
+    device-side cache test lives in tests/test_checkpoint.py)."""
+    eng, rec = cpu_engine("large", 8, "bf16")
+    state = eng.packed_state()
+    assert set(state) == set(engine_mod.Engine.PACKED_ATTRS)
+    torch.save({"packed": state}, tmp_path / "w.pack")
+    loaded = torch.load(tmp_path / "w.pack", weights_only=False)["packed"]
+
+    def tensors(o, out):
+        if isinstance(o, torch.Tensor):
+            out.append(o)
+        elif isinstance(o, dict):
+            for k in sorted(o, key=str):
+                tensors(o[k], out)
+        elif isinstance(o, (list, tuple)):
+            for v in o:
+                tensors(v, out)
+        elif hasattr(o, "__dict__"):
+            tensors(vars(o), out)
+        return out
+
+    a, b = tensors(state, []), tensors(loaded, [])
+    assert len(a) == len(b) > 150 and all(torch.equal(x, y) for x, y in zip(a, b))
+
+    class P:
+        is_cuda = True
+        device = torch.device("cpu")
+
+    model = build_model(8, "large")
+    monkeypatch.setattr(engine_mod, "next", lambda it: P, raising=False)
+    eng2 = engine_mod.Engine(model, "bf16", packed=loaded)
+    assert eng2.qkv[0].shape == eng.qkv[0].shape and eng2.key_ch == eng.key_ch
+    with pytest.raises(ValueError):
+        engine_mod.Engine(model, "bf16", packed={k: v for k, v in loaded.items() if k != "stem"})
