@@ -41,8 +41,18 @@ def make_divisible(v, divisor=8, min_value=None):
     return new_v
 
 
+# Train-mode BatchNorm (oracle/train_oracle.py, the training step of BASELINE config 5): when this dict is not None,
+# ``bn`` normalises with the statistics of the batch (nn.BatchNorm2d in .train(), src/models/cabinet.py:30-31 etc.) and
+# records them so the caller can restate the running-statistics update.  None (the default) = inference.
+BATCH_STATS = None
+
+
 def bn(sd, prefix, x):
-    """Eval-mode BatchNorm2d: (x-mean)/sqrt(var+eps)*gamma+beta (ATen native_batch_norm, eval)."""
+    """BatchNorm2d.  Eval mode: (x-mean)/sqrt(var+eps)*gamma+beta (ATen native_batch_norm, eval)."""
+    if BATCH_STATS is not None:
+        BATCH_STATS[prefix] = (x.detach().mean(dim=(0, 2, 3)), x.detach().var(dim=(0, 2, 3), unbiased=True),
+                               x.shape[0] * x.shape[2] * x.shape[3])
+        return F.batch_norm(x, None, None, sd[prefix + ".weight"], sd[prefix + ".bias"], True, 0.0, BN_EPS)
     return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"],
                         sd[prefix + ".bias"], False, 0.0, BN_EPS)
 
@@ -200,6 +210,11 @@ def cabinet_forward(sd, x, cfgs, stages=None):
     """
     sd = {k: v.detach().to("cpu") for k, v in sd.items()}
     x = x.detach().to("cpu", torch.float32)
+    return cabinet_forward_graph(sd, x, cfgs, stages)
+
+
+def cabinet_forward_graph(sd, x, cfgs, stages=None):
+    """The same forward without ``no_grad`` / detach: differentiable w.r.t. the tensors of ``sd`` (train oracle)."""
     H, W = x.shape[2:]
     feat_sb = spatial_branch(sd, x)
     mobile_feat = mobilenet(sd, x, cfgs)

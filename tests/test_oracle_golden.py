@@ -84,3 +84,37 @@ def test_loss_oracle_matches_reference_golden(golden_dir, case):
     assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-6, abs=1e-7)
     grad = x.grad if x.grad is not None else torch.zeros_like(x)
     np.testing.assert_allclose(grad.numpy(), g["grad"], rtol=1e-5, atol=1e-8)
+
+
+# ------------------------------------------------------------------ training step (forward + backward, train-mode BN)
+from oracle.train_oracle import FULL_GRAD_KEYS, STAT_KEYS, TRAIN_CASES, train_step  # noqa: E402
+
+
+@pytest.mark.parametrize("case", TRAIN_CASES, ids=[c[0] for c in TRAIN_CASES])
+def test_train_step_oracle_matches_reference_golden(golden_dir, case):
+    """oracle/train_oracle.py (train-mode BN forward, OHEM loss on both outputs, autograd) against the imported
+    reference's loss, per-parameter gradient norms, four full gradients and updated BN running statistics
+    (oracle/make_golden_train.py; reference: src/scripts/train.py:430-436)."""
+    name, mode, C, (N, H, W), thresh, n_min = case
+    g = np.load(golden_dir / f"train_step_{name}.npz")
+    model = build_model(C, mode)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    assert state_dict_digest(sd) == str(g["digest"])
+    loss, grads, running = train_step(sd, make_input(N, H, W), make_labels(N, H, W, C), BACKBONE_CFGS[mode], thresh, n_min)
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-5)
+    want = dict(zip([str(k) for k in g["grad_keys"]], g["grad_norms"]))
+    assert set(want) == set(grads)
+    worst = 0.0
+    for k, ref_norm in want.items():
+        if ref_norm < 0:  # the backbone's unused classifier receives no gradient (SURVEY 8d, config 5)
+            assert grads[k] is None and k.startswith("mobile.classifier")
+            continue
+        got = float(grads[k].norm())
+        worst = max(worst, abs(got - ref_norm) / max(ref_norm, 1e-12))
+    assert worst < 1e-3, worst
+    for k in FULL_GRAD_KEYS:
+        ref = torch.from_numpy(g["grad__" + k])
+        assert float((grads[k] - ref).norm() / ref.norm()) < 1e-4, k
+    for k in STAT_KEYS:
+        np.testing.assert_allclose(running[k][0].numpy(), g["mean__" + k], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(running[k][1].numpy(), g["var__" + k], rtol=1e-5, atol=1e-6)
