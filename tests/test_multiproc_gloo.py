@@ -61,3 +61,55 @@ def test_two_rank_hist_allreduce_matches_single_process():
         np.testing.assert_array_equal(hist, want)  # integer counts: bit-exact on every rank
         assert miou == pytest.approx(float(metrics(want)["mIoU"]), abs=1e-12)
     assert out[0][2] == (0, 4) and out[1][2] == (4, 7)
+
+
+# ------------------------------------------------------------------ training config: bucketed gradient all-reduce
+def grad_worker(rank, world, port, out):
+    from cabinet_b200.grad_sync import GradBuckets
+    from cabinet_b200.synthetic import build_model
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = build_model(8, "small").train()
+    gb = GradBuckets(model.named_parameters(), bucket_bytes=1 << 20)
+    for i, (n, p) in enumerate(model.named_parameters()):
+        if p.grad is not None:
+            p.grad.add_(float(rank + 1) * (1 + i % 5))  # in place, like autograd's accumulation into the view
+    gb.all_reduce()
+    named = dict(model.named_parameters())
+    ok = all(torch.allclose(named[n].grad, torch.full_like(named[n], 1.5 * (1 + i % 5)))
+             for i, (n, p) in enumerate(model.named_parameters()) if p.grad is not None)
+    out[rank] = (ok, len(gb.buckets), gb.skipped, [len(x) for x in gb.names], gb.names[0][0],
+                 sum(b.numel() for b in gb.buckets))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_bucketed_gradient_allreduce():
+    """Config-5 plumbing: gradients live in flat buckets (reverse parameter order), one async all-reduce per bucket,
+    averaged over the ranks; the backbone's unused classifier is left out."""
+    from cabinet_b200.grad_sync import GradBuckets
+    from cabinet_b200.synthetic import build_model
+
+    world, port = 2, 31500 + os.getpid() % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(grad_worker, args=(world, port, out), nprocs=world, join=True)
+    model = build_model(8, "small")
+    n_all = sum(p.numel() for p in model.parameters())
+    n_cls = sum(p.numel() for n, p in model.named_parameters() if n.startswith("mobile.classifier"))
+    for r in range(world):
+        ok, n_buckets, skipped, sizes, first, total = out[r]
+        assert ok and n_buckets >= 2 and sum(sizes) == len(list(model.parameters())) - 4
+        assert sorted(skipped) == ["mobile.classifier.0.bias", "mobile.classifier.0.weight", "mobile.classifier.3.bias",
+                                   "mobile.classifier.3.weight"]
+        assert total == n_all - n_cls
+        assert first == list(dict(model.named_parameters()))[-1]  # the last parameter's gradient is ready first
+    # single process: views are installed, all_reduce is a no-op
+    gb = GradBuckets(model.named_parameters())
+    p = model.conv_out.conv_out.weight
+    p.grad.fill_(2.0)
+    gb.all_reduce()
+    assert float(p.grad.mean()) == 2.0 and p.grad.data_ptr() >= gb.buckets[0].data_ptr()
+    gb.zero_()
+    assert float(p.grad.abs().max()) == 0.0
