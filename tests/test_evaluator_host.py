@@ -57,3 +57,10 @@ def test_oracle_overlap_normalisation_is_uniform(n_classes, cropsize, size, valu
     assert (prob.argmax(dim=1) == value).all()
     p = prob[0, value]
     assert float(p.max() - p.min()) < 1e-5
+
+
+def test_cpulist_parser_of_the_numa_binding():
+    from cabinet_b200.affinity import _parse_cpulist
+
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("5") == {5} and _parse_cpulist("") == set()
