@@ -9,7 +9,8 @@
                            fused-block side tables, merged q|k|v, stem GEMM weights) cached next to the checkpoint, keyed
                            by a digest of the ``state_dict`` it was made from, the precision and the C-ABI version, so
                            that N evaluation processes (one per GPU) do not each redo it.  A stale or foreign cache is
-                           ignored, never trusted.
+                           ignored, never trusted: the file holds tensors and plain containers only and is read with
+                           ``weights_only=True`` (no unpickling of arbitrary objects), and the header is compared before use.
 """
 
 from __future__ import annotations
@@ -21,7 +22,7 @@ import torch
 
 from .synthetic import state_dict_digest
 
-PACK_FORMAT = 2
+PACK_FORMAT = 3
 
 
 def load_model_weights(checkpoint_path, device="cpu") -> Dict[str, Any]:
@@ -79,7 +80,7 @@ def load_packed(model, path) -> bool:
         return False
     dev = next(model.parameters()).device
     try:
-        blob = torch.load(path, map_location=dev, weights_only=False)
+        blob = torch.load(path, map_location=dev, weights_only=True)
     except Exception:
         return False
     if not isinstance(blob, dict) or blob.get("header") != _header(model):

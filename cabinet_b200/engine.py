@@ -111,6 +111,32 @@ class GateLayer:
         self.gate = gate
 
 
+_LAYER_TYPES = {c.__name__: c for c in (ConvLayer, DwLayer, GateLayer)}
+
+
+def _to_plain(o):
+    """Layer objects -> tagged dicts of their attributes (recursively); containers and tensors pass through."""
+    if type(o).__name__ in _LAYER_TYPES:
+        return {"__layer__": type(o).__name__, "vars": {k: _to_plain(v) for k, v in vars(o).items()}}
+    if isinstance(o, dict):
+        return {k: _to_plain(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return type(o)(_to_plain(v) for v in o)
+    return o
+
+
+def _from_plain(o):
+    if isinstance(o, dict):
+        if "__layer__" in o:
+            obj = object.__new__(_LAYER_TYPES[o["__layer__"]])
+            obj.__dict__.update({k: _from_plain(v) for k, v in o["vars"].items()})
+            return obj
+        return {k: _from_plain(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return type(o)(_from_plain(v) for v in o)
+    return o
+
+
 def _out_size(n, k, s, p):
     return (n + 2 * p - k) // s + 1
 
@@ -168,14 +194,16 @@ class Engine:
             if missing:
                 raise ValueError(f"packed weights lack {missing}")
             for a in self.PACKED_ATTRS:
-                setattr(self, a, packed[a])
+                setattr(self, a, _from_plain(packed[a]))
             self.gamma = model.ab.a2block.gamma.detach().float().contiguous()
         else:
             with torch.no_grad():
                 self._pack(model)
 
     def packed_state(self) -> dict:
-        return {a: getattr(self, a) for a in self.PACKED_ATTRS}
+        """Everything ``_pack`` produced as plain containers (dict / list / tuple / tensor / scalar / str): the cache
+        file holds no pickled classes and loads with ``torch.load(weights_only=True)``."""
+        return {a: _to_plain(getattr(self, a)) for a in self.PACKED_ATTRS}
 
     # ------------------------------------------------------------------ packing
     def _pack(self, m):
@@ -772,8 +800,19 @@ class Engine:
         self.launches = launches
         return outs[0], outs[1]
 
+    def _guard(self):
+        """The model's GPU as the current device while kernels are enqueued (a model on a non-current GPU would
+        otherwise launch in the wrong device context)."""
+        import contextlib
+
+        return torch.cuda.device(self.dev) if torch.device(self.dev).type == "cuda" else contextlib.nullcontext()
+
     @torch.no_grad()
     def forward(self, x, out_dtype=torch.float32):
+        with self._guard():
+            return self._forward(x, out_dtype)
+
+    def _forward(self, x, out_dtype=torch.float32):
         """-> (final_logit, high_res_logit_up) NCHW (reference: cabinet.py:240-247).
 
         With ``use_cuda_graph`` the whole kernel schedule of a given input shape is captured once and replayed; the
@@ -862,8 +901,9 @@ class Engine:
         N, _, H, W = x.shape
         if N == 0:
             return torch.empty((0, H, W), dtype=torch.uint8, device=self.dev)
-        final8, _ = self._trunk(x, need_aux=False)
-        return self._argmax(final8, N, H, W)
+        with self._guard():
+            final8, _ = self._trunk(x, need_aux=False)
+            return self._argmax(final8, N, H, W)
 
     @torch.no_grad()
     def class_map8(self, x):
@@ -878,7 +918,8 @@ class Engine:
         def run():
             return self._trunk(x, need_aux=False)[0].t
 
-        return self._graphed(("cls8", tuple(x.shape), x.data_ptr()), run)
+        with self._guard():
+            return self._graphed(("cls8", tuple(x.shape), x.data_ptr()), run)
 
     @torch.no_grad()
     def forward_hist(self, x, labels, hist, ignore_label=255):
@@ -901,8 +942,9 @@ class Engine:
             return self._argmax(final8, N, H, W, labels, hist, ignore_label)
 
         # static buffers (an evaluator's double-buffered device tensors) -> captured once, replayed afterwards
-        return self._graphed(("hist", tuple(x.shape), x.data_ptr(), labels.data_ptr(), labels.dtype, hist.data_ptr(),
-                              ignore_label), run)
+        with self._guard():
+            return self._graphed(("hist", tuple(x.shape), x.data_ptr(), labels.data_ptr(), labels.dtype, hist.data_ptr(),
+                                  ignore_label), run)
 
     # ------------------------------------------------------------------ tracing (bench / profiles)
     def start_trace(self, kernels=None):

@@ -18,6 +18,7 @@ Same constructor and result dict.  Differences, all on the hot-path side of the 
 
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Any, Dict, Sequence
 
@@ -31,6 +32,12 @@ try:
     import torch.distributed as dist
 except ImportError:  # pragma: no cover
     dist = None
+
+
+def _device_guard(dev):
+    """Make ``dev`` the current CUDA device while C-ABI calls are enqueued (streams are per device); no-op on CPU."""
+    dev = torch.device(dev)
+    return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
 
 
 def shard_range(n_items: int, rank: int, world: int):
@@ -65,8 +72,14 @@ def normalize_u8(images_u8: torch.Tensor, out: torch.Tensor, mean, std) -> torch
     N, H, W, C = images_u8.shape
     if C != 3 or images_u8.dtype != torch.uint8 or not images_u8.is_contiguous():
         raise ValueError("normalize_u8 expects a contiguous uint8 (N, H, W, 3) tensor")
-    _lib.check(_lib.load().cabinet_normalize_u8(images_u8.data_ptr(), out.data_ptr(), N, H, W, *mean, *std,
-                                                torch.cuda.current_stream(out.device).cuda_stream), "normalize_u8")
+    if (tuple(out.shape) != (N, 3, H, W) or out.dtype != torch.float32 or not out.is_contiguous()
+            or out.device != images_u8.device):
+        raise ValueError(f"normalize_u8: out must be a contiguous fp32 {(N, 3, H, W)} tensor on {images_u8.device}, got "
+                         f"{tuple(out.shape)} {out.dtype} on {out.device}")
+    with _device_guard(out.device):
+        rc = _lib.load().cabinet_normalize_u8(images_u8.data_ptr(), out.data_ptr(), N, H, W, *mean, *std,
+                                              torch.cuda.current_stream(out.device).cuda_stream)
+    _lib.check(rc, "normalize_u8")
     return out
 
 
@@ -238,8 +251,8 @@ class MscEvalV0:
         per batch (asynchronous D2H, valid after the final synchronise)."""
         cur = torch.cuda.current_stream(dev)
         st = self.__dict__.setdefault("_pipe", {"stream": torch.cuda.Stream(dev), "d2h": torch.cuda.Stream(dev),
-                                                "bufs": {}, "x32": None})
-        copy_stream, ring, x32 = st["stream"], st["bufs"], st["x32"]  # device buffers persist across evaluate() calls
+                                                "bufs": {}})
+        copy_stream, ring = st["stream"], st["bufs"]  # device buffers persist across evaluate() calls
         d2h_stream = st["d2h"]  # mask read-back beside the next forward (on the compute stream it would serialise)
         # the fused forward + confusion-matrix call is replayed as a CUDA graph keyed by its buffer addresses: accumulate
         # into a persistent matrix (the caller's `hist` is a fresh allocation per evaluate(), which would force a
@@ -257,9 +270,15 @@ class MscEvalV0:
                 labels = labels.long()
             u8 = images.dtype == torch.uint8
             H, W = images.shape[1:3] if u8 else images.shape[2:]
-            if H != self.cropsize or W != self.cropsize:
-                raise ValueError("fast pipelined mode needs images of exactly cropsize x cropsize")
             N = images.shape[0]
+            if H != self.cropsize or W != self.cropsize:
+                # not one chip == one image: this batch takes the general path (pad / sliding windows), in stream order
+                if u8:
+                    x32 = torch.empty((N, 3, H, W), dtype=torch.float32, device=dev)
+                    images = normalize_u8(images.to(dev, non_blocking=True).contiguous(), x32, *self.u8_mean_std)
+                self._general_batch(images.to(dev, non_blocking=True), labels.to(dev, non_blocking=True), hist, dev)
+                n_batches += 1
+                continue
             chunk = getattr(self, "chunk", 8)
             if u8 or chunk <= 0 or N <= chunk:  # uint8 uploads are compute-bound: one forward per batch
                 chunk = max(N, 1)
@@ -286,8 +305,9 @@ class MscEvalV0:
                         bi.record_stream(copy_stream)
                         bl.record_stream(copy_stream)
                         slots["sets"].append({"img": bi, "lab": bl, "ready": torch.cuda.Event(), "consumed": None})
-                    if u8 and (x32 is None or tuple(x32.shape) != (n, 3, H, W)):
-                        x32 = st["x32"] = torch.empty((n, 3, H, W), dtype=torch.float32, device=dev)
+                    # one fp32 staging buffer PER work-item shape (a short last batch must not shrink the buffer the
+                    # full-size batches of the next evaluate() normalise into)
+                    slots["x32"] = torch.empty((n, 3, H, W), dtype=torch.float32, device=dev) if u8 else None
                 slot = slots["sets"][slots["next"]]
                 slots["next"] = (slots["next"] + 1) % slots["n"]
                 with torch.cuda.stream(copy_stream):
@@ -299,7 +319,7 @@ class MscEvalV0:
                 cur.wait_event(slot["ready"])
                 if slot.get("d2h_done") is not None:
                     cur.wait_event(slot["d2h_done"])  # this slot's mask buffer (a graph output) has been read back
-                xin = normalize_u8(slot["img"], x32, *self.u8_mean_std) if u8 else slot["img"]
+                xin = normalize_u8(slot["img"], slots["x32"], *self.u8_mean_std) if u8 else slot["img"]
                 mask = self.model.accumulate_hist(xin, slot["lab"], hist, self.ignore_label)
                 if host is not None:
                     done = torch.cuda.Event()
@@ -324,38 +344,40 @@ class MscEvalV0:
         dev = next(self.model.parameters()).device
         hist = torch.zeros((self.n_classes, self.n_classes), dtype=torch.int64, device=dev)
         fast = self.scales == (1.0,) and not self.flip and hasattr(self.model, "accumulate_hist")
-        if fast and getattr(self, "pipelined", True):
-            try:
-                first = next(iter(self.dl))[0]
-                hw = first.shape[1:3] if first.dtype == torch.uint8 else first.shape[2:]
-                uniform = hw[0] == self.cropsize and hw[1] == self.cropsize
-            except StopIteration:
-                uniform = False
-            if uniform:
+        with _device_guard(dev):
+            if fast and getattr(self, "pipelined", True):
+                # fast vs general is decided per batch inside the loop (no peeking at the loader: a one-shot iterable
+                # would lose its first batch, a DataLoader would spin up its workers twice)
                 self._fast_pipelined(dev, hist, masks_out)
-                reduce_hist(hist)
-                return metrics_from_hist(hist)
-        for images, labels in self.dl:
-            images = images.to(dev, non_blocking=True)
-            labels = labels.to(dev, non_blocking=True)
-            if labels.dim() == 4:
-                labels = labels.squeeze(1)
-            if labels.dtype not in (torch.int64, torch.uint8):
-                labels = labels.long()
-            H, W = images.shape[2:]
-            if fast and H == self.cropsize and W == self.cropsize:  # one chip == the image: argmax(softmax) == argmax
-                self.model.accumulate_hist(images.float().contiguous(), labels.contiguous(), hist, self.ignore_label)
-                continue
-            if images.size(0) == 0:
-                continue
-            if hasattr(self.model, "class_map8") and getattr(self, "fused_general", True):
-                probs = self._probs_fused(images.float().contiguous())
-            else:  # any other nn.Module: the reference's steps as device tensor ops
-                probs = torch.zeros((images.size(0), self.n_classes, H, W), device=dev)
-                for s in self.scales:
-                    probs += self.scale_crop_eval(images.float(), s)
-            self._hist_from_probs(probs, labels, hist)
+            else:
+                for images, labels in self.dl:
+                    images = images.to(dev, non_blocking=True)
+                    labels = labels.to(dev, non_blocking=True)
+                    if images.dtype == torch.uint8:
+                        x32 = torch.empty((images.shape[0], 3) + tuple(images.shape[1:3]), dtype=torch.float32, device=dev)
+                        images = normalize_u8(images.contiguous(), x32, *self.u8_mean_std)
+                    self._general_batch(images, labels, hist, dev, fast)
         reduce_hist(hist)
         return metrics_from_hist(hist)
+
+    def _general_batch(self, images, labels, hist, dev, fast=False):
+        """One device-resident batch through the reference's control flow (evaluate.py:204-228)."""
+        if labels.dim() == 4:
+            labels = labels.squeeze(1)
+        if labels.dtype not in (torch.int64, torch.uint8):
+            labels = labels.long()
+        H, W = images.shape[2:]
+        if fast and H == self.cropsize and W == self.cropsize:  # one chip == the image: argmax(softmax) == argmax
+            self.model.accumulate_hist(images.float().contiguous(), labels.contiguous(), hist, self.ignore_label)
+            return
+        if images.size(0) == 0:
+            return
+        if hasattr(self.model, "class_map8") and getattr(self, "fused_general", True):
+            probs = self._probs_fused(images.float().contiguous())
+        else:  # any other nn.Module: the reference's steps as device tensor ops
+            probs = torch.zeros((images.size(0), self.n_classes, H, W), device=dev)
+            for s in self.scales:
+                probs += self.scale_crop_eval(images.float(), s)
+        self._hist_from_probs(probs, labels, hist)
 
     __call__ = evaluate

@@ -34,6 +34,8 @@ class GradBuckets:
         self.skipped = [n for n, p in named_params if p.requires_grad and skip(n)]
         self.names: List[List[str]] = []
         self.buckets: List[torch.Tensor] = []
+        self.params: List[List[torch.nn.Parameter]] = []
+        self._checked = False
         cur, cur_names, cur_elems = [], [], 0
         limit = max(1, bucket_bytes // 4)
         for n, p in reversed(items):  # backward produces gradients back to front
@@ -57,10 +59,38 @@ class GradBuckets:
             off += p.numel()
         self.buckets.append(flat)
         self.names.append(names)
+        self.params.append(list(params))
 
     def zero_(self):
+        """Zero the gradients IN PLACE.  Use this (or ``optimizer.zero_grad(set_to_none=False)``) instead of the default
+        ``optimizer.zero_grad()``: ``set_to_none=True`` detaches every ``p.grad`` from its bucket."""
+        self.attach()
         for b in self.buckets:
             b.zero_()
+
+    def attach(self, strict: bool = False) -> int:
+        """Make every ``p.grad`` a view into its bucket again.  A gradient that was replaced (``zero_grad(set_to_none=
+        True)`` followed by a backward that allocated a fresh tensor) is copied into the bucket first, so nothing is
+        lost; with ``strict`` a detached gradient raises instead.  -> number of gradients re-attached."""
+        fixed = 0
+        for flat, params in zip(self.buckets, self.params):
+            off = 0
+            for p in params:
+                view = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+                g = p.grad
+                if g is not None and g.data_ptr() == view.data_ptr() and g.shape == view.shape:
+                    continue
+                if strict:
+                    raise RuntimeError("GradBuckets: a .grad no longer aliases its bucket (optimizer.zero_grad() defaults to "
+                                       "set_to_none=True; use GradBuckets.zero_() or zero_grad(set_to_none=False))")
+                if g is None:
+                    view.zero_()
+                else:
+                    view.copy_(g)
+                p.grad = view
+                fixed += 1
+        return fixed
 
     @staticmethod
     def _world() -> int:
@@ -68,6 +98,11 @@ class GradBuckets:
 
     def reduce_bucket(self, i: int):
         """Start the all-reduce of bucket ``i``; -> a handle for ``finish`` (None in a single process)."""
+        if i == 0 or not self._checked:
+            # gradients produced after optimizer.zero_grad(set_to_none=True) live outside the buckets: fold them back in
+            # before anything is reduced (otherwise stale buckets would be averaged and the replicas diverge silently)
+            self.attach()
+            self._checked = True
         if self._world() == 1:
             return None
         return dist.all_reduce(self.buckets[i], op=dist.ReduceOp.SUM, async_op=True)
@@ -75,6 +110,7 @@ class GradBuckets:
     def finish(self, handles) -> None:
         """Wait for the collectives and turn the sums into means."""
         world = self._world()
+        self._checked = False
         for h in handles:
             if h is not None:
                 h.wait()

@@ -42,12 +42,14 @@ class _OhemCE(torch.autograd.Function):
             w = weight.to(device=dev, dtype=torch.float32).contiguous()
             if w.numel() != C:
                 raise ValueError(f"class weight has {w.numel()} entries for {C} classes")
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(lib.cabinet_ohem_ce_forward(x.data_ptr(), BF16 if x.dtype == torch.bfloat16 else F32, lb.data_ptr(),
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = (lib.cabinet_ohem_ce_forward(x.data_ptr(), BF16 if x.dtype == torch.bfloat16 else F32, lb.data_ptr(),
                                                0 if lb.dtype == torch.int64 else 1, N, C, H * W,
                                                w.data_ptr() if w is not None else None, int(ignore_lb), float(thresh),
                                                max(1, int(n_min)), loss_px.data_ptr(), ws.data_ptr(), out.data_ptr(),
-                                               stream), "ohem_ce_forward")
+                                               stream))
+        _lib.check(rc, "ohem_ce_forward")
         ctx.save_for_backward(x, lb, loss_px, ws, w if w is not None else torch.empty(0, device=dev))
         ctx.has_weight = w is not None
         ctx.in_dtype = logits.dtype
@@ -60,11 +62,13 @@ class _OhemCE(torch.autograd.Function):
         lib = _lib.load()
         g = grad_out.to(device=x.device, dtype=torch.float32).contiguous()
         grad = torch.empty_like(x)
-        stream = torch.cuda.current_stream(x.device).cuda_stream
-        _lib.check(lib.cabinet_ohem_ce_backward(x.data_ptr(), BF16 if x.dtype == torch.bfloat16 else F32, lb.data_ptr(),
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            rc = (lib.cabinet_ohem_ce_backward(x.data_ptr(), BF16 if x.dtype == torch.bfloat16 else F32, lb.data_ptr(),
                                                 0 if lb.dtype == torch.int64 else 1, N, C, H * W,
                                                 w.data_ptr() if ctx.has_weight else None, loss_px.data_ptr(),
-                                                ws.data_ptr(), g.data_ptr(), grad.data_ptr(), stream), "ohem_ce_backward")
+                                                ws.data_ptr(), g.data_ptr(), grad.data_ptr(), stream))
+        _lib.check(rc, "ohem_ce_backward")
         return grad, None, None, None, None, None
 
 

@@ -70,3 +70,26 @@ def test_packed_weight_cache_roundtrip(tmp_path, precision):
     with torch.no_grad():
         m2.ab.a2block.gamma.fill_(0.25)                   # a weight change after loading still invalidates the pack
     assert not torch.equal(m2(x)[0], want[0])
+
+
+def test_packed_state_is_plain_and_loads_with_weights_only(tmp_path):
+    """the pack cache must not need full unpickling.  Layer objects are stored as tagged dicts."""
+    from cabinet_b200.engine import ConvLayer, DwLayer, GateLayer, _from_plain, _to_plain
+
+    conv = torch.nn.Conv2d(8, 16, 3, stride=2, padding=1, bias=False)
+    bn = torch.nn.BatchNorm2d(16).eval()
+    dw = torch.nn.Conv2d(16, 16, 5, padding=2, groups=16, bias=False)
+    tree = {"blocks": [dict(spec={"k": 3, "se": True}, act=2, pw1=ConvLayer(conv, bn, 1, torch.bfloat16, "a"),
+                            dw=DwLayer(dw, bn, 0, "b"), fused_pw=(torch.ones(2), torch.zeros(2)))],
+            "gate": GateLayer(torch.randn(4, 16), None, torch.randn(16, 4), torch.randn(16), 3), "none": None}
+    plain = _to_plain(tree)
+    torch.save({"header": {"format": 3}, "packed": plain}, tmp_path / "p.pack")
+    back = _from_plain(torch.load(tmp_path / "p.pack", weights_only=True)["packed"])
+    b0, b1 = tree["blocks"][0], back["blocks"][0]
+    assert isinstance(b1["pw1"], ConvLayer) and isinstance(b1["dw"], DwLayer) and isinstance(back["gate"], GateLayer)
+    assert isinstance(b1["fused_pw"], tuple) and b1["spec"] == b0["spec"] and back["none"] is None
+    for a, b in ((b0["pw1"], b1["pw1"]), (b0["dw"], b1["dw"]), (tree["gate"], back["gate"])):
+        assert vars(a).keys() == vars(b).keys()
+        for k, v in vars(a).items():
+            w = vars(b)[k]
+            assert torch.equal(v, w) if isinstance(v, torch.Tensor) else v == w

@@ -113,3 +113,30 @@ def test_two_rank_bucketed_gradient_allreduce():
     assert float(p.grad.mean()) == 2.0 and p.grad.data_ptr() >= gb.buckets[0].data_ptr()
     gb.zero_()
     assert float(p.grad.abs().max()) == 0.0
+
+
+def test_grad_buckets_survive_optimizer_zero_grad():
+    """``optimizer.zero_grad()`` defaults to set_to_none=True, which detaches every ``p.grad`` from its flat
+    bucket; the next backward then allocates fresh gradients.  The buckets must pick those up again (two steps)."""
+    from cabinet_b200.grad_sync import GradBuckets
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+    gb = GradBuckets(net.named_parameters(), bucket_bytes=64, skip=lambda n: False)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    x = torch.randn(4, 5)
+    for step in range(2):
+        opt.zero_grad()  # set_to_none=True: the views are gone
+        net(x).square().sum().backward()
+        want = [p.grad.clone() for p in net.parameters()]
+        with pytest.raises(RuntimeError):
+            gb.attach(strict=True)
+        gb.all_reduce()  # re-attaches (copies the fresh gradients into the buckets) before reducing
+        flat = torch.cat([b for b in gb.buckets])
+        assert float(flat.abs().sum()) > 0
+        for p, w in zip(net.parameters(), want):
+            assert torch.equal(p.grad, w)
+            assert any(b.data_ptr() <= p.grad.data_ptr() < b.data_ptr() + b.numel() * 4 for b in gb.buckets)
+        opt.step()
+    gb.zero_()  # in place: the views stay
+    assert gb.attach(strict=True) == 0 and all(float(p.grad.abs().max()) == 0 for p in net.parameters())
