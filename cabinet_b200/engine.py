@@ -52,17 +52,23 @@ class Map:
         return self.t.view(self.N, self.H, self.W, self.ld)[..., self.off:self.off + self.C]
 
 
+def _host(t):
+    """Parameter -> fp32 CPU tensor.  Folding / packing is a few hundred tiny tensor ops: done once on the host (one
+    D2H per parameter) instead of ~900 elementwise kernel launches, then uploaded (`Engine._pack`)."""
+    return t.detach().float().cpu()
+
+
 def _fold(conv_w, conv_b, bn, eps=BN_EPS):
     """Conv + eval-BN -> (w', b') in fp32: y = conv(x, w') + b'  (fold before any rounding)."""
-    w = conv_w.detach().float()
+    w = _host(conv_w)
     cout = w.shape[0]
     if bn is None:
-        b = conv_b.detach().float().clone() if conv_b is not None else torch.zeros(cout, device=w.device)
+        b = _host(conv_b).clone() if conv_b is not None else torch.zeros(cout)
         return w, b
-    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + eps)
-    b = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    scale = _host(bn.weight) / torch.sqrt(_host(bn.running_var) + eps)
+    b = _host(bn.bias) - _host(bn.running_mean) * scale
     if conv_b is not None:
-        b = b + conv_b.detach().float() * scale
+        b = b + _host(conv_b) * scale
     return w * scale.view(-1, 1, 1, 1), b
 
 
@@ -103,10 +109,10 @@ class GateLayer:
     """SE (Linear/Linear + hard-sigmoid) or FFM (1x1/1x1 + sigmoid) channel gate, fp32."""
 
     def __init__(self, w1, b1, w2, b2, gate):
-        f = lambda t: None if t is None else t.detach().float().reshape(t.shape[0], -1).contiguous()  # noqa: E731
+        f = lambda t: None if t is None else _host(t).reshape(t.shape[0], -1).contiguous()  # noqa: E731
         self.w1, self.w2 = f(w1), f(w2)
-        self.b1 = None if b1 is None else b1.detach().float().contiguous()
-        self.b2 = None if b2 is None else b2.detach().float().contiguous()
+        self.b1 = None if b1 is None else _host(b1).contiguous()
+        self.b2 = None if b2 is None else _host(b2).contiguous()
         self.cmid, self.c = self.w1.shape
         self.gate = gate
 
@@ -122,6 +128,21 @@ def _to_plain(o):
         return {k: _to_plain(v) for k, v in o.items()}
     if isinstance(o, (list, tuple)):
         return type(o)(_to_plain(v) for v in o)
+    return o
+
+
+def _map_tensors(o, fn):
+    """Apply ``fn`` to every tensor inside layers / dicts / lists / tuples (layer objects are updated in place)."""
+    if isinstance(o, torch.Tensor):
+        return fn(o)
+    if type(o).__name__ in _LAYER_TYPES:
+        for k, v in vars(o).items():
+            setattr(o, k, _map_tensors(v, fn))
+        return o
+    if isinstance(o, dict):
+        return {k: _map_tensors(v, fn) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return type(o)(_map_tensors(v, fn) for v in o)
     return o
 
 
@@ -198,7 +219,9 @@ class Engine:
             self.gamma = model.ab.a2block.gamma.detach().float().contiguous()
         else:
             with torch.no_grad():
-                self._pack(model)
+                self._pack(model)  # on the host ...
+                for a in self.PACKED_ATTRS:  # ... then one upload per packed tensor
+                    setattr(self, a, _map_tensors(getattr(self, a), lambda t: t.to(self.dev)))
 
     def packed_state(self) -> dict:
         """Everything ``_pack`` produced as plain containers (dict / list / tuple / tensor / scalar / str): the cache
@@ -280,7 +303,7 @@ class Engine:
         self.proj_out = ConvLayer(ga.project_out, None, ACT_NONE, wd, "cab.project_out")
         self.local = [DwLayer(d.block[0], d.block[1], ACT_RELU, f"cab.local{i}")
                       for i, d in enumerate(ab.a2block.local_attn.refine)]
-        self.gamma = ab.a2block.gamma.detach().float().contiguous()
+        self.gamma = _host(ab.a2block.gamma).contiguous()
         self.convb = ConvLayer(ab.convb, None, ACT_NONE, wd, "ab.convb")
         self.b1 = ConvLayer(ab.b1, ab.b2, ACT_RELU, wd, "ab.b1")
         self.b4 = ConvLayer(ab.b4, None, ACT_NONE, wd, "ab.b4")
@@ -380,23 +403,39 @@ class Engine:
                   res.ptr if res is not None else None, res.ld if res is not None else 0, out.ptr, out.dt, out.ld,
                   OH, OW, L.act | (self.REVERSE_TILES if L.name in self.reverse_layers else 0), self.stream)
 
-    def dwconv(self, x: Map, L: DwLayer, gap: Optional[torch.Tensor] = None) -> Map:
+    def dwconv(self, x: Map, L: DwLayer, gap: Optional[torch.Tensor] = None, tickets: Optional[torch.Tensor] = None) -> Map:
+        """Depthwise conv + bias + act.  ``gap`` ([N, C] fp32): also the per-(image, channel) sums of the written values,
+        deterministic (per-CTA partials + fixed-order sum; ``tickets``: N zeroed 32-bit words from the per-forward
+        memset)."""
         p = (L.k - 1) // 2
         OH, OW = _out_size(x.H, L.k, L.stride, p), _out_size(x.W, L.k, L.stride, p)
         out = self.new(x.N, OH, OW, x.C)
         es = x.t.element_size()
         nbytes = x.N * x.C * (x.H * x.W + OH * OW) * es + L.w.numel() * 4
         flops = 2 * x.N * OH * OW * x.C * L.k * L.k
-        gp = gap.data_ptr() if gap is not None else None
         if self.use_tc and x.dt == BF16 and x.ld % 8 == 0 and x.off % 8 == 0:
+            gp = tk = part = None
+            if gap is not None:
+                parts = torch.empty((x.N, -(-OH // 8) * -(-OW // 16), x.C), dtype=torch.float32, device=self.dev)
+                gp, tk, part = gap.data_ptr(), tickets.data_ptr(), parts.data_ptr()
             self._run("dwconv_tma", L.name, nbytes, flops, self.lib.cabinet_dwconv_tma, x.ptr, x.ld, L.w.data_ptr(),
                       L.b.data_ptr(), out.ptr, out.ld, x.N, x.H, x.W, x.C, L.k, L.stride, OH, OW,
-                      L.act | (self.REVERSE_TILES if L.name in self.reverse_layers else 0), gp, self.stream)
+                      L.act | (self.REVERSE_TILES if L.name in self.reverse_layers else 0), gp, tk, part, self.stream)
         else:
             self._run("dwconv", L.name, nbytes, flops, self.lib.cabinet_dwconv, x.ptr, x.ld, L.w.data_ptr(),
-                      L.b.data_ptr(), out.ptr, out.ld, x.dt, x.N, x.H, x.W, x.C, L.k, L.stride, OH, OW, L.act, gp,
+                      L.b.data_ptr(), out.ptr, out.ld, x.dt, x.N, x.H, x.W, x.C, L.k, L.stride, OH, OW, L.act, None,
                       self.stream)
+            if gap is not None:  # parity mode: the deterministic two-level channel sum over the written tensor
+                self.channel_sum(out, gap, L.name)
         return out
+
+    def channel_sum(self, x: Map, out: torch.Tensor, name: str, scratch: Optional[torch.Tensor] = None):
+        """out[n][c] = sum over pixels of x (deterministic: per-block partials, fixed-order final sum)."""
+        if scratch is None:
+            scratch = torch.zeros(128 + x.N * 64 * x.C, dtype=torch.float32, device=self.dev)
+            self.launches += 1
+        self._run("channel_sum", name, 0, 0, self.lib.cabinet_channel_sum, x.ptr, x.ld, x.dt, x.N, x.H * x.W, x.C,
+                  out.data_ptr(), scratch.data_ptr(), scratch.numel() * 4, self.stream)
 
     # ------------------------------------------------------------------ independent branches on side streams
     class _Branch:
@@ -441,14 +480,18 @@ class Engine:
         if ev is not None:
             torch.cuda.current_stream(self.dev).wait_event(ev)
 
-    def mbconv_fused(self, x: Map, e: dict, gap: Optional[torch.Tensor], act_dw: Optional[int] = None) -> Map:
+    def mbconv_fused(self, x: Map, e: dict, want_gap: bool, act_dw: Optional[int] = None):
         """Inverted-residual block with the expanded activation kept on chip (reference: mobilenetv3.py:126-159).
-        ``gap`` given (SE blocks): returns the pre-SE depthwise output and accumulates its pooling sums; else the
-        block output (project + identity included)."""
+        ``want_gap`` (SE blocks): -> (pre-SE depthwise output, per-tile pooling partials [N, tiles, Cexp], tiles);
+        else -> the block output (project + identity included)."""
         s, pw1, dw, pw2 = e["spec"], e["pw1"], e["dw"], e["pw2"]
         pad = (dw.k - 1) // 2
         OH, OW = _out_size(x.H, dw.k, dw.stride, pad), _out_size(x.W, dw.k, dw.stride, pad)
-        project = gap is None
+        project = not want_gap
+        gap = tiles = None
+        if want_gap:  # upper bound of the tile count (the kernel picks the tile shape and reports it)
+            gap = torch.empty((x.N, -(-OH // 4) * -(-OW // 8), dw.c), dtype=torch.float32, device=self.dev)
+            tiles = _lib.C.c_int(0)
         cy = pw2.cout if project else dw.c
         out = self.new(x.N, OH, OW, cy)
         nbytes = (x.N * x.H * x.W * x.C + x.N * OH * OW * cy) * 2 + pw1.w.numel() * 2 + dw.w.numel() * 4
@@ -461,20 +504,24 @@ class Engine:
                   dw.c, pw1.act, dw.k, dw.stride, dw.act if act_dw is None else act_dw,
                   pw2.tc.data_ptr() if project else None, pw2.b.data_ptr() if project else None,
                   pw2.cout if project else 0, 1 if project and s["identity"] else 0, out.ptr, out.ld, OH, OW,
-                  gap.data_ptr() if gap is not None else None, self.stream)
+                  gap.data_ptr() if gap is not None else None, _lib.C.byref(tiles) if tiles is not None else None,
+                  self.stream)
+        if want_gap:
+            return out, gap, int(tiles.value)
         return out
 
-    def gate(self, gap: torch.Tensor, hw: int, G: GateLayer, name: str) -> torch.Tensor:
-        """Channel gate of SE / FFM: two batched tiny FC layers (mean -> ReLU hidden -> gate), fp32."""
+    def gate(self, gap: torch.Tensor, hw: int, G: GateLayer, name: str, n_parts: int = 1) -> torch.Tensor:
+        """Channel gate of SE / FFM: two batched tiny FC layers (mean -> ReLU hidden -> gate), fp32.  ``n_parts`` > 1:
+        ``gap`` is [N, n_parts, C] partial sums, added in index order by the first layer."""
         n = gap.shape[0]
         hidden = torch.empty((n, G.cmid), dtype=torch.float32, device=self.dev)
-        scale = torch.empty_like(gap)
+        scale = torch.empty((n, G.c), dtype=torch.float32, device=self.dev)
         self._run("gate_fc", name, G.w1.numel() * 4, 2 * n * G.c * G.cmid, self.lib.cabinet_gate_fc, gap.data_ptr(),
                   1.0 / hw, G.w1.data_ptr(), G.b1.data_ptr() if G.b1 is not None else None, hidden.data_ptr(), n, G.c,
-                  G.cmid, ACT_RELU, self.stream)
+                  G.cmid, ACT_RELU, n_parts, self.stream)
         self._run("gate_fc", name, G.w2.numel() * 4, 2 * n * G.c * G.cmid, self.lib.cabinet_gate_fc, hidden.data_ptr(),
                   1.0, G.w2.data_ptr(), G.b2.data_ptr() if G.b2 is not None else None, scale.data_ptr(), n, G.cmid,
-                  G.c, G.gate, self.stream)
+                  G.c, G.gate, 1, self.stream)
         return scale
 
     def scale_act(self, x: Map, scale: torch.Tensor, act: int, name: str, plus_one: bool = False):
@@ -550,9 +597,12 @@ class Engine:
         # ONE memset per forward: the SE / FFM pooling sums, and the scratch areas (tickets + parked partial sums) of the
         # deterministic reductions (cabinet_channel_sum, 2 x cabinet_psp_pool)
         kc = self.key_ch
-        n_gap, n_psp, n_ffm = (n_se + 1) * N * 1024, 128 + N * (110 + 256 * kc), 128 + N * 64 * 256
+        # (the SE pooling sums themselves need no zeroing any more: they are overwritten, not accumulated; the area also
+        # holds one row of N zeroed 32-bit arrival tickets per SE block)
+        n_gap, n_psp, n_ffm = (n_se + 1) * N * 1024 + n_se * N, 128 + N * (110 + 256 * kc), 128 + N * 64 * 256
         zeros_all = torch.zeros(n_gap + 2 * n_psp + n_ffm, dtype=torch.float32, device=dev)
-        gap_all = zeros_all[:n_gap].view(n_se + 1, N, 1024)
+        gap_all = zeros_all[:(n_se + 1) * N * 1024].view(n_se + 1, N, 1024)
+        tick_all = zeros_all[(n_se + 1) * N * 1024:n_gap].view(n_se, N) if n_se else None
         self._scratch = [zeros_all[n_gap + i * n_psp: n_gap + (i + 1) * n_psp] for i in range(2)]
         ffm_scratch = zeros_all[n_gap + 2 * n_psp:]
         self.launches += 1
@@ -605,19 +655,21 @@ class Engine:
                     # 5x5 stride-2 tiles are 4 x 8 outputs behind an 11 x 19 halo: measured slower than expand + dwconv_tma
                     and not (s["k"] == 5 and s["s"] == 2))
             d = None
+            n_parts = 1
             if fuse:
                 # expand -> depthwise (-> project + identity): the expanded activation never leaves the SM
                 gap = None
-                if "se" in e:
-                    gap = gap_all[gi].view(-1)[: N * s["exp"]].view(N, s["exp"])
                 # ReLU SE blocks: relu(s * d) = s * relu(d) (s = hard-sigmoid >= 0), so the kernel applies the ReLU and the
                 # gate is folded into per-image project weights -- no scale_act pass over the expanded tensor
                 pw2l = e["pw2"]
-                fold_se = (gap is not None and self.fold_se_relu and e["act"] == ACT_RELU and not self.debug
+                fold_se = ("se" in e and self.fold_se_relu and e["act"] == ACT_RELU and not self.debug
                            and pw2l.tc is not None and pw2l.kh == 1 and (f.H // s["s"]) * (f.W // s["s"]) % 128 == 0
                            and f.H % s["s"] == 0 and f.W % s["s"] == 0)
                 try:
-                    d = self.mbconv_fused(f, e, gap, ACT_RELU if fold_se else None)
+                    if "se" in e:
+                        d, gap, n_parts = self.mbconv_fused(f, e, True, ACT_RELU if fold_se else None)
+                    else:
+                        d = self.mbconv_fused(f, e, False)
                 except ValueError as err:  # block shape outside the kernel's shared-memory / TMEM budget
                     if "budget" not in str(err):
                         raise
@@ -627,11 +679,11 @@ class Engine:
                 continue
             h = self.conv(f, e["pw1"]) if s["expand"] and not fuse else f
             if "se" in e:
-                gap = gap_all[gi].view(-1)[: N * s["exp"]].view(N, s["exp"])
-                gi += 1
                 if not fuse:
-                    d = self.dwconv(h, e["dw"], gap)
-                scale = self.gate(gap, d.H * d.W, e["se"], e["dw"].name)
+                    gap = gap_all[gi].view(-1)[: N * s["exp"]].view(N, s["exp"])
+                    d = self.dwconv(h, e["dw"], gap, tick_all[gi])
+                gi += 1
+                scale = self.gate(gap, d.H * d.W, e["se"], e["dw"].name, n_parts)
                 if fuse and fold_se:
                     pw2 = e["pw2"]
                     wimg = torch.empty((N,) + tuple(pw2.tc.shape), dtype=torch.bfloat16, device=dev)
@@ -730,9 +782,7 @@ class Engine:
         else:
             ff = self.conv(cat_ffm, self.ffm_blk)
         gap = gap_all[n_se].view(-1)[: N * 256].view(N, 256)
-        scratch = ffm_scratch
-        self._run("channel_sum", "ffm.gap", 0, 0, self.lib.cabinet_channel_sum, ff.ptr, ff.ld, ff.dt, N, H8 * W8, 256,
-                  gap.data_ptr(), scratch.data_ptr(), scratch.numel() * 4, self.stream)
+        self.channel_sum(ff, gap, "ffm.gap", ffm_scratch)
         att = self.gate(gap, H8 * W8, self.ffm_gate, "ffm.gate")
         hcl = self.head_conv
         if (self.fold_ffm and self.use_tc and not self.debug and hcl.tc is not None and ff.dt == BF16

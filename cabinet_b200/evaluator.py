@@ -93,6 +93,12 @@ class MscEvalV0:
         # bytes (4x less PCIe traffic) and normalised on the device with these per-channel statistics
         self.u8_mean_std = u8_mean_std
 
+    def _crop_hw(self):
+        """``cropsize`` is an int (the reference: square chips) or an (h, w) pair: whole rectangular images as ONE chip
+        in the fast mode (BASELINE config 3 / 4 forward shapes).  The sliding-window general mode needs the int form."""
+        cs = self.cropsize
+        return (int(cs[0]), int(cs[1])) if isinstance(cs, (tuple, list)) else (int(cs), int(cs))
+
     # ---- general mode: the reference algorithm, tensors stay on the device
     def eval_chip(self, crop):
         prob = F.softmax(self.model(crop)[0].float(), dim=1)
@@ -172,6 +178,8 @@ class MscEvalV0:
         window."""
         from . import _lib
 
+        if isinstance(self.cropsize, (tuple, list)):
+            raise ValueError("the sliding-window mode needs an int cropsize (square chips, reference evaluate.py:97)")
         lib, cs = _lib.load(), self.cropsize
         N, _, H, W = image.shape
         hst = wst = 0
@@ -240,7 +248,7 @@ class MscEvalV0:
             self._resize_accum(ps, (0, 0, hs, ws), probs)
         return probs
 
-    def _fast_pipelined(self, dev, hist, masks_out=None):
+    def _fast_pipelined(self, dev, hist, masks_out=None, hist_trace=None):
         """Fast mode over the whole loader with host->device copies ahead of the fused forward.
 
         A ring of device buffer sets; a copy stream uploads work item i+1.. while the compute stream runs item i
@@ -248,7 +256,9 @@ class MscEvalV0:
         (12.6 MB per 1024^2 image against ~0.17 ms of compute), so they are cut into chunks of ``self.chunk`` images
         (default 8): the forward of a chunk starts as soon as ITS images have landed, and only the last chunk's
         forward is not hidden behind an upload.  ``masks_out``: optional list that receives a pinned uint8 host tensor
-        per batch (asynchronous D2H, valid after the final synchronise)."""
+        per batch (asynchronous D2H, valid after the final synchronise).  ``hist_trace``: optional pinned int64
+        (n_batches, C, C) host tensor that receives the running confusion matrix after every batch (asynchronous D2H
+        of the step's result on the read-back stream; 8 C^2 bytes per batch)."""
         cur = torch.cuda.current_stream(dev)
         st = self.__dict__.setdefault("_pipe", {"stream": torch.cuda.Stream(dev), "d2h": torch.cuda.Stream(dev),
                                                 "bufs": {}})
@@ -271,7 +281,7 @@ class MscEvalV0:
             u8 = images.dtype == torch.uint8
             H, W = images.shape[1:3] if u8 else images.shape[2:]
             N = images.shape[0]
-            if H != self.cropsize or W != self.cropsize:
+            if (H, W) != self._crop_hw():
                 # not one chip == one image: this batch takes the general path (pad / sliding windows), in stream order
                 if u8:
                     x32 = torch.empty((N, 3, H, W), dtype=torch.float32, device=dev)
@@ -333,13 +343,27 @@ class MscEvalV0:
                 slot["consumed"] = torch.cuda.Event()
                 slot["consumed"].record(cur)
                 item += 1
+            if hist_trace is not None and i < hist_trace.shape[0]:
+                snap = st.setdefault("snap", {}).get(i % 4)
+                if snap is None:  # device-side snapshots (the graph keeps adding to `hist` while the copy is in flight)
+                    snap = st["snap"][i % 4] = (torch.empty_like(hist), torch.cuda.Event())
+                    snap[0].record_stream(d2h_stream)
+                else:
+                    cur.wait_event(snap[1])  # its previous read-back has finished
+                snap[0].copy_(hist)
+                done = torch.cuda.Event()
+                done.record(cur)
+                with torch.cuda.stream(d2h_stream):
+                    d2h_stream.wait_event(done)
+                    hist_trace[i].copy_(snap[0], non_blocking=True)
+                    snap[1].record(d2h_stream)
             n_batches += 1
         cur.wait_stream(d2h_stream)  # the caller's stream order (and any event it records next) covers the read-backs
         user_hist.add_(hist)
         return n_batches
 
     @torch.no_grad()
-    def evaluate(self, masks_out=None) -> Dict[str, Any]:
+    def evaluate(self, masks_out=None, hist_trace=None) -> Dict[str, Any]:
         self.model.eval()
         dev = next(self.model.parameters()).device
         hist = torch.zeros((self.n_classes, self.n_classes), dtype=torch.int64, device=dev)
@@ -348,7 +372,7 @@ class MscEvalV0:
             if fast and getattr(self, "pipelined", True):
                 # fast vs general is decided per batch inside the loop (no peeking at the loader: a one-shot iterable
                 # would lose its first batch, a DataLoader would spin up its workers twice)
-                self._fast_pipelined(dev, hist, masks_out)
+                self._fast_pipelined(dev, hist, masks_out, hist_trace)
             else:
                 for images, labels in self.dl:
                     images = images.to(dev, non_blocking=True)
@@ -367,7 +391,7 @@ class MscEvalV0:
         if labels.dtype not in (torch.int64, torch.uint8):
             labels = labels.long()
         H, W = images.shape[2:]
-        if fast and H == self.cropsize and W == self.cropsize:  # one chip == the image: argmax(softmax) == argmax
+        if fast and (H, W) == self._crop_hw():  # one chip == the image: argmax(softmax) == argmax
             self.model.accumulate_hist(images.float().contiguous(), labels.contiguous(), hist, self.ignore_label)
             return
         if images.size(0) == 0:

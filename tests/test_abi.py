@@ -49,7 +49,7 @@ def test_library_builds_and_loads():
     if not _lib.LIB_PATH.is_file():
         _lib.build()
     lib = _lib.load()
-    assert lib.cabinet_abi_version() == 1
+    assert lib.cabinet_abi_version() == 2
 
 
 def test_header_symbols_exported_and_prototypes_agree():

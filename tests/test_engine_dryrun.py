@@ -72,7 +72,8 @@ def test_schedule_shapes_and_abi(cpu_engine, mode, C, shape, precision):
     assert names.count("cabinet_upsample_logits_nchw") == 2
     assert names.count("cabinet_psp_pool") == 2 and names.count("cabinet_softmax_rows") + names.count("cabinet_attention_tc") == 1
     # the single gap-sum / scratch memset (+ the V transpose inside attention_tc)
-    extra = 1 + names.count("cabinet_attention_tc")
+    # (+ one zeroed scratch per SE-block channel_sum of the fp32 parity mode; the FFM one shares the memset)
+    extra = 1 + names.count("cabinet_attention_tc") + names.count("cabinet_channel_sum") - 1
     assert eng.launches == len(rec.calls) + extra
     rec.calls.clear()
     mask = eng.forward_mask(x)
@@ -124,7 +125,7 @@ def test_mask_path_skips_aux_head_and_optional_schedules(cpu_engine, precision):
     eng.reverse_layers = frozenset({"sb.conv2", "mobile.f4.dw"})
     eng.fuse_mbconv = False
     eng.forward_mask(x)
-    flagged = [c for c in rec.calls if c[0] in ("cabinet_conv_tc_se", "cabinet_dwconv_tma") and (c[1][-2 if c[0] == "cabinet_conv_tc_se" else -3] & 0x100)]
+    flagged = [c for c in rec.calls if c[0] in ("cabinet_conv_tc_se", "cabinet_dwconv_tma") and (c[1][-2 if c[0] == "cabinet_conv_tc_se" else -5] & 0x100)]
     assert len(flagged) == 2
 
 
