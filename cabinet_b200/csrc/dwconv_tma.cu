@@ -20,9 +20,7 @@ struct DwParams {
     const float* bias;
     bf16* y;
     long long ldy;
-    float* gap_sum;          // [N][C] pooling sums of the written values (SE / GAP consumers), or nullptr
-    unsigned int* gap_tickets;  // [N], zero on entry, left zero: arrival counter of an image's CTAs
-    float* gap_part;         // [N][tiles][C] per-CTA partial sums (scratch, need not be initialised)
+    long long* gap_sum;      // [N][C] fixed-point (2^-24) pooling sums of the written values (SE consumers), or nullptr
 };
 
 // Warp = one output row of the 8 x 16 patch; lane = (column group, channel PAIR): one 32-bit word of the staged NHWC
@@ -120,7 +118,6 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmX, const DwParams p) {
     extern __shared__ __align__(128) uint8_t smem_dw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_gap[TH * 64];  // [output row = warp][lane][2]
-    __shared__ bool s_last;
 
     const int tiles_w = (p.OW + TW - 1) / TW;
     const int bx = p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
@@ -149,32 +146,19 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmX, const DwParams p) {
     else dw_row<K, S, 2>(p, tile, &bar, s_gap, cw, chunk, n, oh0, ow0);
 
     if (p.gap_sum) {
-        // Deterministic pooling sums (no floating-point atomics): fixed-order sum over the rows / column groups of this
-        // CTA -> partial[n][tile][c]; the CTA of an image that arrives last (ticket) adds the partials in tile order.
+        // Deterministic pooling sums: fixed-order fp32 sum over the rows / column groups of this CTA, then ONE 64-bit
+        // INTEGER atomic per channel (fixed point, 2^-24): integer addition is associative, so the total does not depend
+        // on the order in which the CTAs arrive -- bit-reproducible without tickets, fences or a second pass.
         __syncthreads();
-        const int T = gridDim.x;
         if (threadIdx.x < cw) {
             const int lanes_px = cw >> 1, ng = cw > 32 ? 1 : cw > 16 ? 2 : cw > 8 ? 4 : 8;
             const int cl = threadIdx.x >> 1, hi = threadIdx.x & 1;
             float sum = 0.f;
             for (int r = 0; r < TH; ++r)
                 for (int g = 0; g < ng; ++g) sum += s_gap[r * 64 + (g * lanes_px + cl) * 2 + hi];
-            p.gap_part[(static_cast<long long>(n) * T + bx) * p.C + chunk * p.CB + threadIdx.x] = sum;
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.gap_sum + static_cast<long long>(n) * p.C + chunk * p.CB + threadIdx.x),
+                      static_cast<unsigned long long>(__float2ll_rn(sum * CABINET_GAP_FIXED_ONE)));
         }
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) s_last = atomicAdd(&p.gap_tickets[n], 1u) == gridDim.x * gridDim.y - 1u;
-        __syncthreads();
-        if (!s_last) return;
-        __threadfence();
-        const float* all = p.gap_part + static_cast<long long>(n) * T * p.C;
-        for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-            float sum = 0.f;
-#pragma unroll 8
-            for (int t = 0; t < T; ++t) sum += __ldcg(all + static_cast<long long>(t) * p.C + c);
-            p.gap_sum[static_cast<long long>(n) * p.C + c] = sum;
-        }
-        if (threadIdx.x == 0) p.gap_tickets[n] = 0;  // ready for the next launch
     }
 }
 
@@ -433,9 +417,8 @@ extern "C" int cabinet_mbconv_noexpand_fused(const void* x, long long ldx, const
 
 extern "C" int cabinet_dwconv_tma(const void* x, long long ldx, const float* w, const float* bias, void* y,
                                   long long ldy, int N, int H, int W, int C, int k, int stride, int OH, int OW, int act,
-                                  float* gap_sum, unsigned int* gap_tickets, float* gap_partials, cabinet_stream_t stream) {
+                                  long long* gap_sum, cabinet_stream_t stream) {
     CAB_REQUIRE(x && w && bias && y, "dwconv_tma: null pointer");
-    CAB_REQUIRE(!gap_sum || (gap_tickets && gap_partials), "dwconv_tma: pooling sums need the ticket / partial-sum scratch");
     const int reverse = (act & CABINET_CONV_REVERSE_TILES) ? 1 : 0;
     act &= ~CABINET_CONV_REVERSE_TILES;
     CAB_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2), "dwconv_tma: k must be 3|5 and stride 1|2");
@@ -455,7 +438,6 @@ extern "C" int cabinet_dwconv_tma(const void* x, long long ldx, const float* w, 
     // that makes the tail cost more than a full chunk.  The TMA box stays 64 channels wide.
     p.CB = ((C + n_chunks - 1) / n_chunks + 7) / 8 * 8;
     p.y = reinterpret_cast<bf16*>(y); p.ldy = ldy; p.gap_sum = gap_sum;
-    p.gap_tickets = gap_tickets; p.gap_part = gap_partials;
     const int IWT = (TW - 1) * stride + k, IHT = (TH - 1) * stride + k;
     CUtensorMap tm;
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};

@@ -44,7 +44,7 @@ struct MbParams {
     const float* b2;
     const bf16* res;
     long long ldres;
-    float* gap;      // depthwise-output mode: [N][tiles_h * tiles_w][Cexp] per-tile pooling partials, or nullptr
+    long long* gap;  // depthwise-output mode: [N][Cexp] fixed-point (2^-24) pooling sums, or nullptr
     long long* dbg;  // clock64 stamps of CTA 0 / compute thread 0 (16 per chunk) in -DCAB_MB_DEBUG builds
 };
 
@@ -121,6 +121,12 @@ template <int ACT> __device__ __forceinline__ uint32_t pack_act(float lo, float 
     return d;
 }
 
+// Per-(warp, lane) pooling partial (two floats): parked in the 16 unused skew bytes behind the 128 channel bytes of the
+// staged E rows 0..127 (epilogue 1 never writes them; every tile shape stages >= 144 rows) -- no extra shared memory.
+__device__ __forceinline__ uint32_t gap_slot(uint32_t sE, int warp, int lane) {
+    return sE + (warp * 16 + (lane >> 1)) * E_PITCH + 128 + (lane & 1) * 8;
+}
+
 // Depthwise over one row segment: lane = (column group, channel pair).  COLS output columns per lane.
 template <int K, int S, int COLS, int IWT, int TW>
 __device__ __forceinline__ void dw_seg(const MbParams& p, uint32_t sE, uint32_t sA2, uint32_t s_gap, uint32_t s_aux,
@@ -131,7 +137,7 @@ __device__ __forceinline__ void dw_seg(const MbParams& p, uint32_t sE, uint32_t 
     const int grp = lane / lanes_px, cl = lane - grp * lanes_px;
     if (grp >= groups) {
         if (want_gap) {
-            const uint32_t a = s_gap + (((threadIdx.x >> 5) * 64 + lane * 2) << 2);
+            const uint32_t a = gap_slot(sE, threadIdx.x >> 5, lane);
             sts32f(a, 0.f);
             sts32f(a + 4, 0.f);
         }
@@ -194,8 +200,8 @@ __device__ __forceinline__ void dw_seg(const MbParams& p, uint32_t sE, uint32_t 
                                       : pack_act<CABINET_ACT_NONE>(acc[r].x, acc[r].y);
         sts32(a2row + r * 128 + (cq ^ (static_cast<uint32_t>(sw) << 4)), hv);
     }
-    if (want_gap) {  // [warp][lane][2]: summed over warps / column groups in a fixed order after the A2 barrier
-        const uint32_t a = s_gap + (((threadIdx.x >> 5) * 64 + lane * 2) << 2);
+    if (want_gap) {  // summed over warps / column groups in a fixed order after the A2 barrier
+        const uint32_t a = gap_slot(sE, threadIdx.x >> 5, lane);
         sts32f(a, g0);
         sts32f(a + 4, g1);
     }
@@ -246,7 +252,6 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const uint32_t sA1 = tc::smem_u32(smem);
     const uint32_t sE = sA1 + p.off_e, sA2 = sA1 + p.off_a2, sW = sA1 + p.off_w;
     const uint32_t s_b2 = sA1 + p.off_f32;                      // [cout_pad] fp32
-    const uint32_t s_gap = s_b2 + p.cout_pad * 4;               // [NCW][64] (depthwise-output mode; cout_pad = 0 there)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nc = p.n_chunks;
 
@@ -269,8 +274,6 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tc::fence_proxy_async();
     }
     if (warp == NCW) tc::tmem_alloc(&tmem_base_smem, TMEM_COLS);
-    if (!PROJECT)
-        for (int i = threadIdx.x; i < NCW * 64; i += NTHREADS) sts32f(s_gap + 4 * i, 0.f);
     if (PROJECT)
         for (int i = threadIdx.x; i < p.cout_pad; i += NTHREADS) sts32f(s_b2 + 4 * i, i < p.Cout ? __ldg(p.b2 + i) : 0.f);
     tc::tc_fence_before();
@@ -451,32 +454,33 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 {
                     const bool row_valid = oh0 + row_w < p.OH;
                     if (v16 > 32)
-                        dw_seg<K, S, WSEG, IWT, TW>(p, sE, sA2, s_gap, s_aux, c, v16 >> 1, 1, row_w, seg * WSEG, row_valid, ow0, want_gap);
+                        dw_seg<K, S, WSEG, IWT, TW>(p, sE, sA2, 0u, s_aux, c, v16 >> 1, 1, row_w, seg * WSEG, row_valid, ow0, want_gap);
                     else if (v16 > 16)
-                        dw_seg<K, S, WSEG / 2, IWT, TW>(p, sE, sA2, s_gap, s_aux, c, 16, 2, row_w, seg * WSEG, row_valid, ow0, want_gap);
+                        dw_seg<K, S, WSEG / 2, IWT, TW>(p, sE, sA2, 0u, s_aux, c, 16, 2, row_w, seg * WSEG, row_valid, ow0, want_gap);
                     else
-                        dw_seg<K, S, WSEG / 4, IWT, TW>(p, sE, sA2, s_gap, s_aux, c, 8, 4, row_w, seg * WSEG, row_valid, ow0, want_gap);
+                        dw_seg<K, S, WSEG / 4, IWT, TW>(p, sE, sA2, 0u, s_aux, c, 8, 4, row_w, seg * WSEG, row_valid, ow0, want_gap);
                 }
                 MB_STAMP(rec, 16 * g + 4);
                 tc::fence_proxy_async();
                 tc::named_bar_sync(1, NCW * 32);                // A2 complete, E free
                 MB_STAMP(rec, 16 * g + 5);
-                if (want_gap && threadIdx.x < 64) {
-                    // deterministic SE pooling partial of this (tile, chunk): fixed-order sum over the 8 warps and the
-                    // column groups -> gap[n][tile][channel] (no floating-point atomics); the consumer
-                    // (cabinet_gate_fc, n_parts = tiles per image) adds the tile rows in index order
-                    const int ch = c * 64 + threadIdx.x;
+                if (want_gap && threadIdx.x >= (NCW - 2) * 32) {
+                    // deterministic SE pooling sums: fixed-order fp32 sum over the 8 warps / column groups of this
+                    // (tile, chunk), then ONE 64-bit INTEGER atomic per channel (fixed point 2^-24; integer addition is
+                    // associative, so the total is independent of the CTA arrival order).  Warps 6-7 do it: thread 0
+                    // (dw_done arrive + TMA store issue) is not delayed.
+                    const int t = threadIdx.x - (NCW - 2) * 32;
+                    const int ch = c * 64 + t;
                     if (ch < p.Cexp) {
                         const int lanes_px = v16 > 32 ? (v16 >> 1) : v16 > 16 ? 16 : 8, ng = v16 > 32 ? 1 : v16 > 16 ? 2 : 4;
-                        const int cl = threadIdx.x >> 1, hi = threadIdx.x & 1;
+                        const int cl = t >> 1, hi = t & 1;
                         float sum = 0.f;
                         if (cl < lanes_px) {
                             for (int w8 = 0; w8 < NCW; ++w8)
-                                for (int gq = 0; gq < ng; ++gq)
-                                    sum += lds32f(s_gap + ((w8 * 64 + (gq * lanes_px + cl) * 2 + hi) << 2));
+                                for (int gq = 0; gq < ng; ++gq) sum += lds32f(gap_slot(sE, w8, gq * lanes_px + cl) + hi * 4);
                         }
-                        const long long trow = static_cast<long long>(n) * (p.tiles_w * p.tiles_h) + ti.th * p.tiles_w + ti.tw;
-                        p.gap[trow * p.Cexp + ch] = sum;
+                        atomicAdd(reinterpret_cast<unsigned long long*>(p.gap + static_cast<long long>(n) * p.Cexp + ch),
+                                  static_cast<unsigned long long>(__float2ll_rn(sum * CABINET_GAP_FIXED_ONE)));
                     }
                 }
                 if (threadIdx.x == 0) {
@@ -574,7 +578,7 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
 template <int K, int S, int TH, int TW, bool PROJECT>
 int launch_mb(const void* x, long long ldx, int N, const void* w1, const void* w2, void* y, long long ldy, int cy,
-              MbParams p, cudaStream_t st, bool probe, int* tiles_out) {
+              MbParams p, cudaStream_t st, bool probe) {
     constexpr int IWT = (TW - 1) * S + K, IHT = (TH - 1) * S + K, NPIX = IWT * IHT, NMT = (NPIX + 127) / 128;
     constexpr int NOUT = TH * TW;
     if (NMT * 64 + (PROJECT ? p.cout_pad : 0) > TMEM_COLS) {
@@ -586,7 +590,6 @@ int launch_mb(const void* x, long long ldx, int N, const void* w1, const void* w
     const long long tiles = static_cast<long long>(N) * p.tiles_w * p.tiles_h;
     CAB_REQUIRE(tiles < (1LL << 31), "mbconv_fused: too many tiles");
     p.num_tiles = static_cast<int>(tiles);
-    if (tiles_out) *tiles_out = p.tiles_w * p.tiles_h;
     const int a1_bytes = ((NPIX * 128 + 1023) / 1024) * 1024;
     int e_bytes = ((NPIX * E_PITCH + 1023) / 1024) * 1024;
     if (PROJECT && p.cout_pad > 64) e_bytes = std::max(e_bytes, ((p.cout_pad + 63) / 64 - 1) * A2_BYTES);
@@ -599,8 +602,7 @@ int launch_mb(const void* x, long long ldx, int N, const void* w1, const void* w
     p.w_buf_bytes = ((p.off_aux + p.aux_bytes + 1023) / 1024) * 1024;
     p.resident = p.n_chunks <= 2 ? 1 : 0;
     p.off_f32 = p.off_w + std::min(p.n_chunks, 2) * p.w_buf_bytes;
-    // fp32 tail: project bias [cout_pad] (PROJECT) or the per-warp pooling sums [NCW][64] (depthwise-output mode)
-    const size_t smem = static_cast<size_t>(std::max(p.off_f32, p.off_a2 + A2_BYTES)) + (PROJECT ? p.cout_pad : NCW * 64) * 4 + 1024;
+    const size_t smem = static_cast<size_t>(std::max(p.off_f32, p.off_a2 + A2_BYTES)) + p.cout_pad * 4 + 1024;
     if (smem > 113 * 1024) {
         cabinet_set_error("mbconv_fused: shared-memory budget (%zu bytes)", smem);
         return CABINET_ERR_INVALID;
@@ -668,9 +670,7 @@ extern "C" int cabinet_mbconv_debug(long long* device_stamps) {
 extern "C" int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_expand,
                                     const float* aux_packed, int Cexp, int act_expand, int k, int stride, int act_dw,
                                     const void* w_project, const float* b_project, int Cout, int residual, void* y,
-                                    long long ldy, int OH, int OW, float* gap_partials, int* gap_tiles_out,
-                                    cabinet_stream_t stream) {
-    float* gap_sum = gap_partials;
+                                    long long ldy, int OH, int OW, long long* gap_sum, cabinet_stream_t stream) {
     CAB_REQUIRE(x && w_expand && aux_packed && y, "mbconv_fused: null pointer");
     CAB_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2), "mbconv_fused: k must be 3|5 and stride 1|2");
     CAB_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cin <= 56 && Cin % 8 == 0 && Cexp > 0 && Cexp % 8 == 0 && Cexp <= 1024,
@@ -690,7 +690,6 @@ extern "C" int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, 
         CAB_REQUIRE(!gap_sum, "mbconv_fused: pooling sums exist in the depthwise-output mode only");
     } else {
         CAB_REQUIRE(ldy >= Cexp && !residual, "mbconv_fused: depthwise-output mode writes Cexp channels, no identity");
-        CAB_REQUIRE(!gap_partials || gap_tiles_out, "mbconv_fused: pooling partials need gap_tiles_out");
     }
     if (N == 0) return CABINET_OK;
     MbParams p;
@@ -704,8 +703,8 @@ extern "C" int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int cy = project ? Cout : Cexp;
 #define CAB_MB(K_, S_, TH_, TW_, PROBE_)                                                                           \
-    (project ? launch_mb<K_, S_, TH_, TW_, true>(x, ldx, N, w_expand, w_project, y, ldy, cy, p, st, PROBE_, gap_tiles_out)   \
-             : launch_mb<K_, S_, TH_, TW_, false>(x, ldx, N, w_expand, w_project, y, ldy, cy, p, st, PROBE_, gap_tiles_out))
+    (project ? launch_mb<K_, S_, TH_, TW_, true>(x, ldx, N, w_expand, w_project, y, ldy, cy, p, st, PROBE_)   \
+             : launch_mb<K_, S_, TH_, TW_, false>(x, ldx, N, w_expand, w_project, y, ldy, cy, p, st, PROBE_))
     if (k == 3 && stride == 1) return CAB_MB(3, 1, 8, 16, false);
     if (k == 5 && stride == 1) {
         if (CAB_MB(5, 1, 8, 16, true) == CABINET_OK) return CAB_MB(5, 1, 8, 16, false);

@@ -44,7 +44,7 @@ constexpr int FC_WMAX = 32;   // weights per lane kept in registers: rows of up 
 // staging barrier), so a launch pays ONE global round trip instead of one per 32 inputs.
 __global__ void __launch_bounds__(256)
 gate_fc_kernel(const float* __restrict__ in, float in_scale, const float* __restrict__ W, const float* __restrict__ b,
-               float* __restrict__ out, int N, int C, int J, int act, int n_parts) {
+               float* __restrict__ out, int N, int C, int J, int act, int in_fixed) {
     extern __shared__ float s_in[];  // [FC_NB][C]
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int j = blockIdx.x * 8 + warp;
@@ -58,19 +58,13 @@ gate_fc_kernel(const float* __restrict__ in, float in_scale, const float* __rest
     }
     // stage the inputs of this block's images: rows are contiguous, so it is one flat copy; all loads of a thread are
     // issued before the first store (C <= 1024, FC_NB = 8: at most 8 float4 per thread)
-    const float* src = in + static_cast<long long>(n0) * C * n_parts;
+    const float* src = in + static_cast<long long>(n0) * C;
     const int total = nb * C;
-    if (n_parts > 1) {
-        // in = [N][n_parts][C] partial sums (per-tile SE pooling partials of the fused block kernel): the rows of an image
-        // are added in index order -- the same order on every run, whatever the producer's CTA scheduling was
-        for (int i = threadIdx.x; i < total; i += blockDim.x) {
-            const int k = i / C, c = i - k * C;
-            const float* pp = src + static_cast<long long>(k) * n_parts * C + c;
-            float sum = 0.f;
-#pragma unroll 8
-            for (int t = 0; t < n_parts; ++t) sum += __ldg(pp + static_cast<long long>(t) * C);
-            s_in[i] = sum * in_scale;
-        }
+    if (in_fixed) {
+        // in = [N][C] 64-bit fixed-point sums (2^-24): the deterministic SE pooling sums of the depthwise kernels
+        const long long* fx = reinterpret_cast<const long long*>(in) + static_cast<long long>(n0) * C;
+        for (int i = threadIdx.x; i < total; i += blockDim.x)
+            s_in[i] = static_cast<float>(static_cast<double>(__ldg(fx + i)) * (1.0 / CABINET_GAP_FIXED_ONE)) * in_scale;
     } else if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
         float4 v[8];
 #pragma unroll
@@ -317,14 +311,13 @@ extern "C" int cabinet_gate_mlp(const float* gap_sum, float inv_hw, const float*
 }
 
 extern "C" int cabinet_gate_fc(const float* in, float in_scale, const float* W, const float* b, float* out, int N,
-                               int C, int J, int act, int n_parts, cabinet_stream_t stream) {
-    CAB_REQUIRE(in && W && out && C > 0 && J > 0 && C <= 32 * FC_WMAX && n_parts >= 1,
-                "gate_fc: bad arguments (C=%d J=%d n_parts=%d, C <= 1024)", C, J, n_parts);
+                               int C, int J, int act, int in_fixed, cabinet_stream_t stream) {
+    CAB_REQUIRE(in && W && out && C > 0 && J > 0 && C <= 32 * FC_WMAX, "gate_fc: bad arguments (C=%d J=%d, C <= 1024)", C, J);
     if (N == 0) return CABINET_OK;
     CAB_REQUIRE((N + FC_NB - 1) / FC_NB <= 65535, "gate_fc: N exceeds grid limits");
     gate_fc_kernel<<<dim3((J + 7) / 8, (N + FC_NB - 1) / FC_NB), 256, FC_NB * C * sizeof(float),
                      static_cast<cudaStream_t>(stream)>>>(
-        in, in_scale, W, b, out, N, C, J, act, n_parts);
+        in, in_scale, W, b, out, N, C, J, act, in_fixed);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

@@ -403,10 +403,11 @@ class Engine:
                   res.ptr if res is not None else None, res.ld if res is not None else 0, out.ptr, out.dt, out.ld,
                   OH, OW, L.act | (self.REVERSE_TILES if L.name in self.reverse_layers else 0), self.stream)
 
-    def dwconv(self, x: Map, L: DwLayer, gap: Optional[torch.Tensor] = None, tickets: Optional[torch.Tensor] = None) -> Map:
-        """Depthwise conv + bias + act.  ``gap`` ([N, C] fp32): also the per-(image, channel) sums of the written values,
-        deterministic (per-CTA partials + fixed-order sum; ``tickets``: N zeroed 32-bit words from the per-forward
-        memset)."""
+    def dwconv(self, x: Map, L: DwLayer, gap: Optional[torch.Tensor] = None):
+        """Depthwise conv + bias + act.  ``gap`` ([N, C], zeroed): also the per-(image, channel) sums of the written
+        values, deterministic.  bf16 path: int64 fixed-point accumulators (``cabinet_gate_fc(in_fixed=1)`` consumes
+        them); fp32 parity path: fp32 sums by the two-level ``channel_sum`` over the written tensor.
+        -> (out, gap_is_fixed_point)"""
         p = (L.k - 1) // 2
         OH, OW = _out_size(x.H, L.k, L.stride, p), _out_size(x.W, L.k, L.stride, p)
         out = self.new(x.N, OH, OW, x.C)
@@ -414,20 +415,17 @@ class Engine:
         nbytes = x.N * x.C * (x.H * x.W + OH * OW) * es + L.w.numel() * 4
         flops = 2 * x.N * OH * OW * x.C * L.k * L.k
         if self.use_tc and x.dt == BF16 and x.ld % 8 == 0 and x.off % 8 == 0:
-            gp = tk = part = None
-            if gap is not None:
-                parts = torch.empty((x.N, -(-OH // 8) * -(-OW // 16), x.C), dtype=torch.float32, device=self.dev)
-                gp, tk, part = gap.data_ptr(), tickets.data_ptr(), parts.data_ptr()
             self._run("dwconv_tma", L.name, nbytes, flops, self.lib.cabinet_dwconv_tma, x.ptr, x.ld, L.w.data_ptr(),
                       L.b.data_ptr(), out.ptr, out.ld, x.N, x.H, x.W, x.C, L.k, L.stride, OH, OW,
-                      L.act | (self.REVERSE_TILES if L.name in self.reverse_layers else 0), gp, tk, part, self.stream)
-        else:
-            self._run("dwconv", L.name, nbytes, flops, self.lib.cabinet_dwconv, x.ptr, x.ld, L.w.data_ptr(),
-                      L.b.data_ptr(), out.ptr, out.ld, x.dt, x.N, x.H, x.W, x.C, L.k, L.stride, OH, OW, L.act, None,
-                      self.stream)
-            if gap is not None:  # parity mode: the deterministic two-level channel sum over the written tensor
-                self.channel_sum(out, gap, L.name)
-        return out
+                      L.act | (self.REVERSE_TILES if L.name in self.reverse_layers else 0),
+                      gap.data_ptr() if gap is not None else None, self.stream)
+            return out, True
+        self._run("dwconv", L.name, nbytes, flops, self.lib.cabinet_dwconv, x.ptr, x.ld, L.w.data_ptr(),
+                  L.b.data_ptr(), out.ptr, out.ld, x.dt, x.N, x.H, x.W, x.C, L.k, L.stride, OH, OW, L.act, None,
+                  self.stream)
+        if gap is not None:  # parity mode: the deterministic two-level channel sum over the written tensor
+            self.channel_sum(out, gap, L.name)
+        return out, False
 
     def channel_sum(self, x: Map, out: torch.Tensor, name: str, scratch: Optional[torch.Tensor] = None):
         """out[n][c] = sum over pixels of x (deterministic: per-block partials, fixed-order final sum)."""
@@ -480,18 +478,14 @@ class Engine:
         if ev is not None:
             torch.cuda.current_stream(self.dev).wait_event(ev)
 
-    def mbconv_fused(self, x: Map, e: dict, want_gap: bool, act_dw: Optional[int] = None):
+    def mbconv_fused(self, x: Map, e: dict, gap: Optional[torch.Tensor], act_dw: Optional[int] = None) -> Map:
         """Inverted-residual block with the expanded activation kept on chip (reference: mobilenetv3.py:126-159).
-        ``want_gap`` (SE blocks): -> (pre-SE depthwise output, per-tile pooling partials [N, tiles, Cexp], tiles);
-        else -> the block output (project + identity included)."""
+        ``gap`` given (SE blocks; [N, Cexp] int64 fixed point, zeroed): returns the pre-SE depthwise output and
+        accumulates its pooling sums; else the block output (project + identity included)."""
         s, pw1, dw, pw2 = e["spec"], e["pw1"], e["dw"], e["pw2"]
         pad = (dw.k - 1) // 2
         OH, OW = _out_size(x.H, dw.k, dw.stride, pad), _out_size(x.W, dw.k, dw.stride, pad)
-        project = not want_gap
-        gap = tiles = None
-        if want_gap:  # upper bound of the tile count (the kernel picks the tile shape and reports it)
-            gap = torch.empty((x.N, -(-OH // 4) * -(-OW // 8), dw.c), dtype=torch.float32, device=self.dev)
-            tiles = _lib.C.c_int(0)
+        project = gap is None
         cy = pw2.cout if project else dw.c
         out = self.new(x.N, OH, OW, cy)
         nbytes = (x.N * x.H * x.W * x.C + x.N * OH * OW * cy) * 2 + pw1.w.numel() * 2 + dw.w.numel() * 4
@@ -504,24 +498,21 @@ class Engine:
                   dw.c, pw1.act, dw.k, dw.stride, dw.act if act_dw is None else act_dw,
                   pw2.tc.data_ptr() if project else None, pw2.b.data_ptr() if project else None,
                   pw2.cout if project else 0, 1 if project and s["identity"] else 0, out.ptr, out.ld, OH, OW,
-                  gap.data_ptr() if gap is not None else None, _lib.C.byref(tiles) if tiles is not None else None,
-                  self.stream)
-        if want_gap:
-            return out, gap, int(tiles.value)
+                  gap.data_ptr() if gap is not None else None, self.stream)
         return out
 
-    def gate(self, gap: torch.Tensor, hw: int, G: GateLayer, name: str, n_parts: int = 1) -> torch.Tensor:
-        """Channel gate of SE / FFM: two batched tiny FC layers (mean -> ReLU hidden -> gate), fp32.  ``n_parts`` > 1:
-        ``gap`` is [N, n_parts, C] partial sums, added in index order by the first layer."""
+    def gate(self, gap: torch.Tensor, hw: int, G: GateLayer, name: str, fixed: bool = False) -> torch.Tensor:
+        """Channel gate of SE / FFM: two batched tiny FC layers (mean -> ReLU hidden -> gate), fp32.  ``fixed``:
+        ``gap`` holds int64 fixed-point sums (the depthwise kernels' deterministic pooling accumulators)."""
         n = gap.shape[0]
         hidden = torch.empty((n, G.cmid), dtype=torch.float32, device=self.dev)
         scale = torch.empty((n, G.c), dtype=torch.float32, device=self.dev)
         self._run("gate_fc", name, G.w1.numel() * 4, 2 * n * G.c * G.cmid, self.lib.cabinet_gate_fc, gap.data_ptr(),
                   1.0 / hw, G.w1.data_ptr(), G.b1.data_ptr() if G.b1 is not None else None, hidden.data_ptr(), n, G.c,
-                  G.cmid, ACT_RELU, n_parts, self.stream)
+                  G.cmid, ACT_RELU, int(fixed), self.stream)
         self._run("gate_fc", name, G.w2.numel() * 4, 2 * n * G.c * G.cmid, self.lib.cabinet_gate_fc, hidden.data_ptr(),
                   1.0, G.w2.data_ptr(), G.b2.data_ptr() if G.b2 is not None else None, scale.data_ptr(), n, G.cmid,
-                  G.c, G.gate, 1, self.stream)
+                  G.c, G.gate, 0, self.stream)
         return scale
 
     def scale_act(self, x: Map, scale: torch.Tensor, act: int, name: str, plus_one: bool = False):
@@ -597,12 +588,11 @@ class Engine:
         # ONE memset per forward: the SE / FFM pooling sums, and the scratch areas (tickets + parked partial sums) of the
         # deterministic reductions (cabinet_channel_sum, 2 x cabinet_psp_pool)
         kc = self.key_ch
-        # (the SE pooling sums themselves need no zeroing any more: they are overwritten, not accumulated; the area also
-        # holds one row of N zeroed 32-bit arrival tickets per SE block)
-        n_gap, n_psp, n_ffm = (n_se + 1) * N * 1024 + n_se * N, 128 + N * (110 + 256 * kc), 128 + N * 64 * 256
+        # (every SE block owns N x 1024 8-byte slots: int64 fixed-point accumulators on the bf16 path, fp32 sums in the
+        # parity mode; the FFM pooling row sits behind them)
+        n_gap, n_psp, n_ffm = (2 * n_se + 1) * N * 1024, 128 + N * (110 + 256 * kc), 128 + N * 64 * 256
         zeros_all = torch.zeros(n_gap + 2 * n_psp + n_ffm, dtype=torch.float32, device=dev)
-        gap_all = zeros_all[:(n_se + 1) * N * 1024].view(n_se + 1, N, 1024)
-        tick_all = zeros_all[(n_se + 1) * N * 1024:n_gap].view(n_se, N) if n_se else None
+        gap_all = zeros_all[:n_gap].view(2 * n_se + 1, N * 1024)
         self._scratch = [zeros_all[n_gap + i * n_psp: n_gap + (i + 1) * n_psp] for i in range(2)]
         ffm_scratch = zeros_all[n_gap + 2 * n_psp:]
         self.launches += 1
@@ -655,10 +645,12 @@ class Engine:
                     # 5x5 stride-2 tiles are 4 x 8 outputs behind an 11 x 19 halo: measured slower than expand + dwconv_tma
                     and not (s["k"] == 5 and s["s"] == 2))
             d = None
-            n_parts = 1
+            gap_fixed = False
             if fuse:
                 # expand -> depthwise (-> project + identity): the expanded activation never leaves the SM
                 gap = None
+                if "se" in e:
+                    gap, gap_fixed = gap_all[2 * gi:2 * gi + 2].view(-1)[: 2 * N * s["exp"]], True
                 # ReLU SE blocks: relu(s * d) = s * relu(d) (s = hard-sigmoid >= 0), so the kernel applies the ReLU and the
                 # gate is folded into per-image project weights -- no scale_act pass over the expanded tensor
                 pw2l = e["pw2"]
@@ -666,10 +658,7 @@ class Engine:
                            and pw2l.tc is not None and pw2l.kh == 1 and (f.H // s["s"]) * (f.W // s["s"]) % 128 == 0
                            and f.H % s["s"] == 0 and f.W % s["s"] == 0)
                 try:
-                    if "se" in e:
-                        d, gap, n_parts = self.mbconv_fused(f, e, True, ACT_RELU if fold_se else None)
-                    else:
-                        d = self.mbconv_fused(f, e, False)
+                    d = self.mbconv_fused(f, e, gap, ACT_RELU if fold_se else None)
                 except ValueError as err:  # block shape outside the kernel's shared-memory / TMEM budget
                     if "budget" not in str(err):
                         raise
@@ -680,10 +669,10 @@ class Engine:
             h = self.conv(f, e["pw1"]) if s["expand"] and not fuse else f
             if "se" in e:
                 if not fuse:
-                    gap = gap_all[gi].view(-1)[: N * s["exp"]].view(N, s["exp"])
-                    d = self.dwconv(h, e["dw"], gap, tick_all[gi])
+                    gap = gap_all[2 * gi:2 * gi + 2].view(-1)[: 2 * N * s["exp"]]
+                    d, gap_fixed = self.dwconv(h, e["dw"], gap)
                 gi += 1
-                scale = self.gate(gap, d.H * d.W, e["se"], e["dw"].name, n_parts)
+                scale = self.gate(gap.view(N, -1), d.H * d.W, e["se"], e["dw"].name, gap_fixed)
                 if fuse and fold_se:
                     pw2 = e["pw2"]
                     wimg = torch.empty((N,) + tuple(pw2.tc.shape), dtype=torch.bfloat16, device=dev)
@@ -710,7 +699,7 @@ class Engine:
                     continue
                 self.scale_act(d, scale, se_act, e["dw"].name)
             else:
-                d = self.dwconv(h, e["dw"])
+                d, _ = self.dwconv(h, e["dw"])
             f = self.conv(d, e["pw2"], res=f if s["identity"] else None)
         h32, w32 = f.H, f.W
         cat_b1 = self.new(N, h32, w32, self.last.cout + 256)  # [mobile_feat | CAB feat] (reference: cabinet.py:87)
@@ -738,7 +727,7 @@ class Engine:
         with self._branch(0) as joined:         # local attention (three depthwise convs) beside the global attention
             r = feat
             for L in self.local:
-                r = self.dwconv(r, L)
+                r, _ = self.dwconv(r, L)
             joined(r.t)
         self._join(1)
         ctx = self.attention(q, k, v)
@@ -781,7 +770,7 @@ class Engine:
                       L.act, self.stream)
         else:
             ff = self.conv(cat_ffm, self.ffm_blk)
-        gap = gap_all[n_se].view(-1)[: N * 256].view(N, 256)
+        gap = gap_all[2 * n_se].view(-1)[: N * 256].view(N, 256)
         self.channel_sum(ff, gap, "ffm.gap", ffm_scratch)
         att = self.gate(gap, H8 * W8, self.ffm_gate, "ffm.gate")
         hcl = self.head_conv

@@ -37,6 +37,11 @@ enum {
  * input is larger than L2 starts on the part its producer wrote last (still L2 resident).  Results are identical. */
 #define CABINET_CONV_REVERSE_TILES 0x100
 
+/* One unit of the 64-bit fixed-point per-(image, channel) pooling sums that the depthwise kernels accumulate for the
+ * squeeze-excite gate: value = raw * 2^-24.  Integer accumulation is associative, which makes the sums (and everything
+ * downstream) bit-reproducible whatever the order in which the thread blocks finish. */
+#define CABINET_GAP_FIXED_ONE 16777216.0f
+
 typedef void* cabinet_stream_t; /* cudaStream_t */
 
 const char* cabinet_last_error(void);
@@ -111,13 +116,11 @@ int cabinet_dwconv(const void* x, long long ldx, const float* w, const float* bi
 
 /* The same depthwise convolution for bf16 with the input patch (+halo) staged in shared memory by one TMA box per
  * CTA (zero padding = TMA out-of-bounds fill).  Same arguments / semantics as cabinet_dwconv (bf16 only), except that
- * the pooling sums are DETERMINISTIC (no floating-point atomics): every CTA writes a partial row, the CTA of an image
- * that arrives last adds them in tile order and OVERWRITES gap_sum[n][0..C) (no zeroing needed).  With gap_sum:
- *   gap_tickets  [N] uint32, zero on entry, left zero;
- *   gap_partials [N][ceil(OH/8) * ceil(OW/16)][C] fp32 scratch (need not be initialised). */
+ * the pooling sums are DETERMINISTIC: gap_sum is [N][C] int64 fixed point (CABINET_GAP_FIXED_ONE), zeroed by the caller;
+ * every CTA adds its fixed-order fp32 partial sum with one 64-bit integer atomic per channel. */
 int cabinet_dwconv_tma(const void* x, long long ldx, const float* w, const float* bias, void* y, long long ldy, int N,
-                       int H, int W, int C, int k, int stride, int OH, int OW, int act, float* gap_sum,
-                       unsigned int* gap_tickets, float* gap_partials, cabinet_stream_t stream);
+                       int H, int W, int C, int k, int stride, int OH, int OW, int act, long long* gap_sum,
+                       cabinet_stream_t stream);
 
 /* Whole no-expand inverted-residual block in one kernel (inp == hidden, no SE, stride 1, identity):
  *   y = x + W_pw * act(dw3x3(x) + b_dw) + b_pw     (src/models/mobilenetv3.py:110-125,154-159; Large f1)
@@ -163,12 +166,10 @@ int cabinet_scale_weights(const void* w_packed, const float* scale, void* out, i
  *   h = act_expand(W_e * x + b_e)            1x1 expand + BN + act          (mobilenetv3.py:128-131)
  *   d = act_dw(dw_kxk(h) + b_dw)             depthwise + BN                 (mobilenetv3.py:132-141)
  *   w_project != NULL:  y = W_p * d + b_p (+ x when residual)                (mobilenetv3.py:145-159), y has Cout channels
- *   w_project == NULL:  y = d (Cexp channels) and gap_partials[n][tile][c] = sum over the tile's pixels of
- *                       (dw_kxk(h) + b_dw), i.e. of the values BEFORE act_dw (blocks with squeeze-excite: the gate needs
- *                       the global mean of the BN output before the project conv).  Deterministic: fixed summation
- *                       order inside a tile, no atomics; *gap_tiles_out (HOST int) receives the tiles per image and
- *                       the consumer (cabinet_gate_fc, n_parts = that count) adds the tile rows in index order.
- *                       The buffer needs [N][ceil(OH/4) * ceil(OW/8)][Cexp] floats at most, uninitialised.  act_dw = NONE leaves the activation to the SE apply;
+ *   w_project == NULL:  y = d (Cexp channels) and gap_sum[n][c] += sum over pixels of (dw_kxk(h) + b_dw), i.e. of the
+ *                       values BEFORE act_dw (blocks with squeeze-excite: the gate needs the global mean of the BN
+ *                       output before the project conv); gap_sum is [N][Cexp] int64 fixed point (CABINET_GAP_FIXED_ONE),
+ *                       zeroed by the caller: fixed-order fp32 sum per tile, then 64-bit integer atomics (deterministic).  act_dw = NONE leaves the activation to the SE apply;
  *                       act_dw = RELU is for the identity relu(s * d) = s * relu(d), s >= 0, with the scale folded
  *                       into per-image project weights (cabinet_scale_weights + cabinet_conv_tc_imgw).
  * The expanded activation h never reaches HBM (TMEM -> shared memory -> depthwise).
@@ -178,11 +179,11 @@ int cabinet_scale_weights(const void* w_packed, const float* scale, void* out, i
  * w_project: the cabinet_conv_tc packing (bf16 [ceil16(Cout)][1][ceil64(Cexp)]); b_project fp32 [Cout].
  * aux_packed: fp32 [ceil(Cexp/64)][k*k + 2][64], zero padded, BN folded: rows 0..k*k-1 = depthwise taps of the chunk's
  *           64 channels, row k*k = reserved (0), row k*k+1 = depthwise bias (one bulk copy per chunk).
- * k in {3,5}, stride in {1,2}, pad (k-1)/2; Cexp % 8 == 0; Cout <= 128; gap_partials may be NULL. */
+ * k in {3,5}, stride in {1,2}, pad (k-1)/2; Cexp % 8 == 0; Cout <= 128; gap_sum may be NULL. */
 int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_expand,
                          const float* aux_packed, int Cexp, int act_expand, int k, int stride, int act_dw,
                          const void* w_project, const float* b_project, int Cout, int residual, void* y, long long ldy,
-                         int OH, int OW, float* gap_partials, int* gap_tiles_out, cabinet_stream_t stream);
+                         int OH, int OW, long long* gap_sum, cabinet_stream_t stream);
 
 /* Squeeze-excite / FFM channel gate: scale[n][c] = gate(b2 + W2 * relu(b1 + W1 * (sum[n]/HW))).
  * Replaces src/models/mobilenetv3.py:68-83 (gate = CABINET_ACT_HSIGMOID, biases present) and
@@ -192,11 +193,11 @@ int cabinet_gate_mlp(const float* gap_sum, float inv_hw, const float* w1, const 
 
 /* One layer of that gate for the whole batch at once (each weight is read once for all images):
  *   out[n][j] = act(b[j] + sum_c W[j][c] * in[n][c] * in_scale),  in [N][C], W [J][C], out [N][J], all fp32.
- * n_parts > 1: in is [N][n_parts][C] and in[n][c] = sum_t in[n][t][c], added in index order (the per-tile pooling
- * partials of cabinet_mbconv_fused).
+ * in_fixed != 0: in is [N][C] int64 fixed point (CABINET_GAP_FIXED_ONE): the pooling sums of cabinet_dwconv_tma /
+ * cabinet_mbconv_fused.
  * The engine runs the SE / FFM gate as gate_fc(ReLU, in_scale = 1/HW) -> gate_fc(hard-sigmoid | sigmoid). */
 int cabinet_gate_fc(const float* in, float in_scale, const float* W, const float* b, float* out, int N, int C, int J,
-                    int act, int n_parts, cabinet_stream_t stream);
+                    int act, int in_fixed, cabinet_stream_t stream);
 
 /* In place: x[n][p][c] = act(x * scale[n][c])            (plus_one = 0; SE apply, mobilenetv3.py:83 + act)
  *           x[n][p][c] = x * scale[n][c] + x             (plus_one = 1; FFM, src/models/cabinet.py:152-153) */

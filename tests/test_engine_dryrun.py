@@ -125,7 +125,7 @@ def test_mask_path_skips_aux_head_and_optional_schedules(cpu_engine, precision):
     eng.reverse_layers = frozenset({"sb.conv2", "mobile.f4.dw"})
     eng.fuse_mbconv = False
     eng.forward_mask(x)
-    flagged = [c for c in rec.calls if c[0] in ("cabinet_conv_tc_se", "cabinet_dwconv_tma") and (c[1][-2 if c[0] == "cabinet_conv_tc_se" else -5] & 0x100)]
+    flagged = [c for c in rec.calls if c[0] in ("cabinet_conv_tc_se", "cabinet_dwconv_tma") and (c[1][-2 if c[0] == "cabinet_conv_tc_se" else -3] & 0x100)]
     assert len(flagged) == 2
 
 
