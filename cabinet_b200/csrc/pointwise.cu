@@ -62,9 +62,25 @@ gate_fc_kernel(const float* __restrict__ in, float in_scale, const float* __rest
     const int total = nb * C;
     if (in_fixed) {
         // in = [N][C] 64-bit fixed-point sums (2^-24): the deterministic SE pooling sums of the depthwise kernels
-        const long long* fx = reinterpret_cast<const long long*>(in) + static_cast<long long>(n0) * C;
-        for (int i = threadIdx.x; i < total; i += blockDim.x)
-            s_in[i] = static_cast<float>(static_cast<double>(__ldg(fx + i)) * (1.0 / CABINET_GAP_FIXED_ONE)) * in_scale;
+        // (int64 -> fp32 with ONE rounding, then an exact power-of-two scale: no double-precision arithmetic)
+        const longlong2* fx = reinterpret_cast<const longlong2*>(reinterpret_cast<const long long*>(in) + static_cast<long long>(n0) * C);
+        const float sc = in_scale * (1.0f / CABINET_GAP_FIXED_ONE);
+        if ((C & 1) == 0) {  // 16-byte loads, all of a thread's loads in flight before the first use
+            longlong2 v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int i = threadIdx.x + u * 256;
+                if (2 * i < total) v[u] = __ldg(fx + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int i = threadIdx.x + u * 256;
+                if (2 * i < total) *reinterpret_cast<float2*>(s_in + 2 * i) = make_float2(__ll2float_rn(v[u].x) * sc, __ll2float_rn(v[u].y) * sc);
+            }
+        } else {
+            const long long* f1 = reinterpret_cast<const long long*>(fx);
+            for (int i = threadIdx.x; i < total; i += blockDim.x) s_in[i] = __ll2float_rn(__ldg(f1 + i)) * sc;
+        }
     } else if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
         float4 v[8];
 #pragma unroll
