@@ -61,6 +61,27 @@ SIGNATURES = {
     "cabinet_prob_resize_accum": ([_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p], _i),
     "cabinet_argmax_hist_nchw": ([_p, _i, _i, _ll, _p, _p, _i, _i, _p, _p], _i),
     "cabinet_ohem_workspace_bytes": ([], _ll),
+    "cabinet_train_scratch_floats": ([_ll, _i, _i], _ll),
+    "cabinet_pack_conv_weight": ([_p, _i, _i, _i, _i, _p, _i, _i, _i, _p], _i),
+    "cabinet_pack_dw_weight": ([_p, _i, _i, _p, _p], _i),
+    "cabinet_bn_train_stats": ([_p, _ll, _i, _ll, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p], _i),
+    "cabinet_affine_act": ([_p, _ll, _i, _p, _p, _p, _f, _p, _ll, _p, _ll, _i, _ll, _ll, _i, _i, _p], _i),
+    "cabinet_bn_train_backward": ([_p, _ll, _p, _ll, _i, _p, _i, _p, _p, _p, _ll, _ll, _i, _i, _p, _p], _i),
+    "cabinet_gate_scale_backward": ([_p, _ll, _p, _ll, _i, _p, _f, _i, _p, _i, _ll, _i, _p, _p], _i),
+    "cabinet_gate_apply_backward": ([_p, _ll, _p, _ll, _i, _p, _f, _p, _f, _i, _p, _ll, _i, _ll, _i, _i, _p], _i),
+    "cabinet_gate_mlp_backward": ([_p, _f, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p], _i),
+    "cabinet_col_sum": ([_p, _ll, _i, _ll, _i, _p, _i, _p, _p], _i),
+    "cabinet_conv_dgrad": ([_p, _ll, _i, _p, _i, _ll, _ll, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
+    "cabinet_conv_wgrad_scratch_floats": ([_i, _i, _i, _i, _i, _i, _i], _ll),
+    "cabinet_conv_wgrad": ([_p, _ll, _i, _p, _i, _ll, _ll, _ll, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p,
+                            _p], _i),
+    "cabinet_dwconv_dgrad": ([_p, _ll, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
+    "cabinet_dwconv_wgrad": ([_p, _ll, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p], _i),
+    "cabinet_resample_sep": ([_p, _i, _ll, _ll, _ll, _ll, _p, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p,
+                              _i, _p], _i),
+    "cabinet_softmax_backward": ([_p, _p, _p, _ll, _i, _f, _p], _i),
+    "cabinet_cab_combine_backward": ([_p, _ll, _p, _p, _p, _p, _i, _p, _p, _p, _p, _ll, _i, _i, _p, _p], _i),
+    "cabinet_add": ([_p, _ll, _p, _ll, _p, _ll, _i, _ll, _i, _p], _i),
     "cabinet_ohem_ce_forward": ([_p, _i, _p, _i, _i, _i, _ll, _p, _i, _f, _ll, _p, _p, _p, _p], _i),
     "cabinet_ohem_ce_backward": ([_p, _i, _p, _i, _i, _i, _ll, _p, _p, _p, _p, _p, _p], _i),
 }

@@ -1,0 +1,1053 @@
+// Training-step kernels (BASELINE config 5; reference: src/scripts/train.py:429-441 = autocast forward in .train() mode,
+// two OHEM losses, backward).  Everything the inference path does not have:
+//   * train-mode BatchNorm: batch statistics (shifted single pass, deterministic two-level sums), running-statistics
+//     update (momentum 0.1, unbiased variance), normalise + activation, and its backward (two reductions + apply);
+//   * data gradients and weight gradients of the dense and depthwise convolutions (CUDA-core implicit GEMM with
+//     fp32 accumulation; split over the pixel dimension with a fixed-order second-level sum for the weight gradients);
+//   * squeeze-excite / FFM gate backward, CAB combine backward, softmax backward, the adjoints of every bilinear
+//     resize / adaptive average pool as ONE separable sparse resampling kernel, small helpers.
+// All reductions have a fixed summation order (no floating-point atomics): a training step is bit-reproducible.
+// Activations are NHWC (fp32 or bf16), statistics / gradients of parameters fp32.
+#include "common.cuh"
+
+namespace {
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p) { return to_f32<T>(*p); }
+
+// derivative of the activation with respect to its input u
+__device__ __forceinline__ float act_grad(float u, int act) {
+    switch (act) {
+        case CABINET_ACT_RELU: return u > 0.f ? 1.f : 0.f;
+        case CABINET_ACT_HSWISH:  // d/du [u * relu6(u + 3) / 6]
+            return u <= -3.f ? 0.f : (u >= 3.f ? 1.f : (2.f * u + 3.f) * (1.f / 6.f));
+        case CABINET_ACT_HSIGMOID: return (u > -3.f && u < 3.f) ? (1.f / 6.f) : 0.f;
+        case CABINET_ACT_SIGMOID: {
+            const float s = 1.f / (1.f + __expf(-u));
+            return s * (1.f - s);
+        }
+        default: return 1.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Column reductions over the pixel dimension: out[q][c] = sum over rows m of f_q(m, c), q < NQ.
+// Level 1: block b reduces rows [b * rows_per_block, ...) -> partial[b][q][c] (fixed order inside the block);
+// level 2 (the *_finalize kernels) adds the blocks in index order.
+constexpr int RED_THREADS = 256;
+
+template <int NQ, typename F>
+__device__ __forceinline__ void col_reduce_block(long long M, int C, long long rows_per_block, float* __restrict__ partial,
+                                                 F f) {
+    extern __shared__ float s_red[];  // [lanes][NQ][cw]
+    const long long m0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+    const long long m1 = min(m0 + rows_per_block, M);
+    for (int c0 = 0; c0 < C; c0 += RED_THREADS) {
+        const int cw = min(RED_THREADS, C - c0);
+        const int lanes = RED_THREADS / cw;          // pixel lanes working on this channel chunk
+        const int cl = threadIdx.x % cw, lane = threadIdx.x / cw;
+        float acc[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
+        if (lane < lanes)
+            for (long long m = m0 + lane; m < m1; m += lanes) f(m, c0 + cl, acc);
+        __syncthreads();
+        if (lane < lanes)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) s_red[(lane * NQ + q) * cw + cl] = acc[q];
+        __syncthreads();
+        if (threadIdx.x < cw) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                float sum = 0.f;
+                for (int l = 0; l < lanes; ++l) sum += s_red[(l * NQ + q) * cw + threadIdx.x];
+                partial[(static_cast<long long>(blockIdx.x) * NQ + q) * C + c0 + threadIdx.x] = sum;
+            }
+        }
+    }
+}
+
+inline int red_blocks(long long M, long long* rows_per_block) {
+    long long nb = std::min<long long>(1024, std::max<long long>(1, M / 64));
+    *rows_per_block = cab_ceil_div(M, nb);
+    return static_cast<int>(cab_ceil_div(M, *rows_per_block));
+}
+constexpr size_t RED_SMEM = RED_THREADS * 3 * sizeof(float);
+
+// ---- BN statistics: shifted sums (k = the value at row 0) keep E[(x-k)^2] - E[x-k]^2 well conditioned in fp32
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS)
+bn_stats_kernel(const T* __restrict__ x, long long ldx, long long M, int C, long long rpb, float* __restrict__ partial) {
+    col_reduce_block<2>(M, C, rpb, partial, [&](long long m, int c, float* acc) {
+        const float d = ldf(x + m * ldx + c) - ldf(x + c);
+        acc[0] += d;
+        acc[1] = fmaf(d, d, acc[1]);
+    });
+}
+
+template <typename T>
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nb, long long M, int C, const T* __restrict__ x,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ run_mean, float* __restrict__ run_var,
+                                   float* __restrict__ stats /* [4][C]: mean, invstd, scale, shift */) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < nb; ++b) {
+        s1 += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
+        s2 += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
+    }
+    const double k = ldf(x + c), inv_m = 1.0 / static_cast<double>(M);
+    const double d = s1 * inv_m;
+    const double mean = k + d;
+    const double var = fmax(s2 * inv_m - d * d, 0.0);  // biased (normalisation)
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+    stats[c] = static_cast<float>(mean);
+    stats[C + c] = invstd;
+    stats[2 * C + c] = g * invstd;
+    stats[3 * C + c] = bt - static_cast<float>(mean) * g * invstd;
+    if (run_mean) {  // nn.BatchNorm2d: running = (1 - momentum) * running + momentum * batch (unbiased variance)
+        const double unb = M > 1 ? var * static_cast<double>(M) / static_cast<double>(M - 1) : var;
+        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * static_cast<float>(mean);
+        run_var[c] = (1.f - momentum) * run_var[c] + momentum * static_cast<float>(unb);
+    }
+}
+
+// y = act((z * scale[c] + shift[c]) * gate[n][c]) + res     (scale/shift/gate/res optional)
+template <typename TZ, typename TY>
+__global__ void __launch_bounds__(256)
+affine_act_kernel(const TZ* __restrict__ z, long long ldz, const float* __restrict__ scale, const float* __restrict__ shift,
+                  const float* __restrict__ gate, float gate_plus, const TY* __restrict__ res, long long ldres,
+                  TY* __restrict__ y, long long ldy, long long M, long long HW, int C, int act) {
+    const long long total = M * C;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long m = i / C;
+        const int c = static_cast<int>(i - m * C);
+        float u = ldf(z + m * ldz + c);
+        if (scale) u = fmaf(u, scale[c], shift[c]);
+        if (gate) u *= gate[(m / HW) * C + c] + gate_plus;
+        u = cab_act(u, act);
+        if (res) u += ldf(res + m * ldres + c);
+        y[m * ldy + c] = from_f32<TY>(u);
+    }
+}
+
+// ---- BN (+activation) backward.  g = dy * act'(u), u = z * scale + shift, xhat = (z - mean) * invstd.
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS)
+bn_bwd_reduce_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ z, long long ldz,
+                     const float* __restrict__ stats, int act, long long M, int C, long long rpb,
+                     float* __restrict__ partial) {
+    col_reduce_block<2>(M, C, rpb, partial, [&](long long m, int c, float* acc) {
+        const float zv = ldf(z + m * ldz + c);
+        const float u = fmaf(zv, stats[2 * C + c], stats[3 * C + c]);
+        const float g = ldf(dy + m * lddy + c) * act_grad(u, act);
+        acc[0] += g;
+        acc[1] = fmaf(g, (zv - stats[c]) * stats[C + c], acc[1]);
+    });
+}
+
+// sums the block partials in order; dgamma / dbeta accumulate into the parameter gradients; coef[2][C] = the two
+// per-channel means the apply kernel subtracts
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb, long long M, int C,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s1 = 0.f, s2 = 0.f;
+    for (int b = 0; b < nb; ++b) {
+        s1 += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
+        s2 += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
+    }
+    if (dbeta) dbeta[c] += s1;
+    if (dgamma) dgamma[c] += s2;
+    coef[c] = s1 / static_cast<float>(M);
+    coef[C + c] = s2 / static_cast<float>(M);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ z, long long ldz,
+                    const float* __restrict__ stats, const float* __restrict__ coef, int act, T* __restrict__ dz,
+                    long long lddz, long long M, int C, int accumulate) {
+    const long long total = M * C;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long m = i / C;
+        const int c = static_cast<int>(i - m * C);
+        const float zv = ldf(z + m * ldz + c);
+        const float u = fmaf(zv, stats[2 * C + c], stats[3 * C + c]);
+        const float g = ldf(dy + m * lddy + c) * act_grad(u, act);
+        const float xhat = (zv - stats[c]) * stats[C + c];
+        float v = stats[2 * C + c] * (g - coef[c] - xhat * coef[C + c]);
+        T* o = dz + m * lddz + c;
+        if (accumulate) v += ldf(o);
+        *o = from_f32<T>(v);
+    }
+}
+
+// ---- plain activation / bias-free elementwise backward: dx = dy * act'(x)   (layers without BN)
+// and the gated form y = act(v * (s[n][c] + plus)): dv = dy * act'(v * s') * s' + dm[n][c] * inv_hw
+template <typename T>
+__global__ void __launch_bounds__(256)
+gate_bwd_apply_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ v, long long ldv,
+                      const float* __restrict__ s, float plus, const float* __restrict__ dm, float inv_hw, int act,
+                      T* __restrict__ dv, long long lddv, long long M, long long HW, int C, int accumulate) {
+    const long long total = M * C;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long m = i / C;
+        const int c = static_cast<int>(i - m * C);
+        const long long nc = (m / HW) * C + c;
+        const float sv = s ? s[nc] + plus : 1.f;
+        const float x = ldf(v + m * ldv + c);
+        float r = ldf(dy + m * lddy + c) * act_grad(x * sv, act) * sv;
+        if (dm) r = fmaf(dm[nc], inv_hw, r);
+        T* o = dv + m * lddv + c;
+        if (accumulate) r += ldf(o);
+        *o = from_f32<T>(r);
+    }
+}
+
+// ds[n][c] = sum over the pixels of image n of dy * act'(v * s') * v : one block per (pixel chunk, image); two-level
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS)
+gate_bwd_reduce_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ v, long long ldv,
+                       const float* __restrict__ s, float plus, int act, long long HW, int C, long long rpb,
+                       float* __restrict__ partial /* [N][nb][C] */) {
+    const int n = blockIdx.y, nb = gridDim.x;
+    const T* dyn = dy + static_cast<long long>(n) * HW * lddy;
+    const T* vn = v + static_cast<long long>(n) * HW * ldv;
+    const float* sn = s + static_cast<long long>(n) * C;
+    col_reduce_block<1>(HW, C, rpb, partial + static_cast<long long>(n) * nb * C, [&](long long m, int c, float* acc) {
+        const float x = ldf(vn + m * ldv + c);
+        acc[0] = fmaf(ldf(dyn + m * lddy + c) * act_grad(x * (sn[c] + plus), act), x, acc[0]);
+    });
+}
+
+// out[n][c] (+)= alpha * sum_b partial[n][b][c]  (fixed order)
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int nb, long long count, long long group_stride,
+                                    float* __restrict__ out, float alpha, int accumulate) {
+    // partial is [groups][nb][count]; blockIdx.y = group
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float* p = partial + static_cast<long long>(blockIdx.y) * group_stride + i;
+    float sum = 0.f;
+    for (int b = 0; b < nb; ++b) sum += p[static_cast<long long>(b) * count];
+    float* o = out + static_cast<long long>(blockIdx.y) * count + i;
+    *o = (accumulate ? *o : 0.f) + alpha * sum;
+}
+
+// column sums of a [M][C] tensor (bias gradients, per-image channel sums use cabinet_channel_sum)
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS)
+col_sum_kernel(const T* __restrict__ x, long long ldx, long long M, int C, long long rpb, float* __restrict__ partial) {
+    col_reduce_block<1>(M, C, rpb, partial, [&](long long m, int c, float* acc) { acc[0] += ldf(x + m * ldx + c); });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight packing: PyTorch OIHW fp32 -> [cout_pad][KH*KW][cin_pad] (ci fastest, zero padded) in fp32 or bf16: the layout
+// cabinet_conv2d_simt / cabinet_conv_tc consume and the data-gradient kernel reads.  transposed_1 = depthwise
+// ([C][1][k][k] -> [k*k][C]).
+template <typename TO>
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int cout_pad,
+                                        int cin_pad, TO* __restrict__ out) {
+    const long long total = static_cast<long long>(cout_pad) * taps * cin_pad;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ci = static_cast<int>(i % cin_pad);
+        const long long t = i / cin_pad;
+        const int tap = static_cast<int>(t % taps), co = static_cast<int>(t / taps);
+        float v = 0.f;
+        if (co < Cout && ci < Cin) v = w[(static_cast<long long>(co) * Cin + ci) * taps + tap];
+        out[i] = from_f32<TO>(v);
+    }
+}
+
+__global__ void pack_dw_weight_kernel(const float* __restrict__ w, int C, int taps, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * taps) return;
+    const int c = i % C, t = i / C;
+    out[i] = w[c * taps + t];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dense convolution, data gradient (implicit GEMM over (ky, kx, co)):
+//   dx[n][iy][ix][ci] (+)= sum_{ky,kx,co} dy[n][oy][ox][co] * w[co][ky*KW+kx][ci],  oy = (iy + pad - ky) / stride (exact)
+constexpr int GBM = 64, GBN = 64, GBK = 16;
+
+struct DgradArgs {
+    const void* dy; long long lddy;
+    const void* w; long long w_sco, w_stap;  // element strides of the packed weights ([co][tap][ci], ci contiguous)
+    void* dx; long long lddx;
+    int N, H, W, Cin, Cout, KH, KW, stride, pad, OH, OW, accumulate;
+    long long M;  // N*H*W
+    int K;        // KH*KW*Cout
+};
+
+template <typename T, typename TW>
+__global__ void __launch_bounds__(256) conv_dgrad_kernel(DgradArgs a) {
+    __shared__ __align__(16) float As[GBK][GBM];
+    __shared__ __align__(16) float Bs[GBK][GBN + 4];
+    __shared__ int pix_n[GBM], pix_y[GBM], pix_x[GBM];
+    const int tid = threadIdx.x;
+    const long long m0 = static_cast<long long>(blockIdx.x) * GBM;
+    const int n0 = blockIdx.y * GBN;
+    const T* __restrict__ dy = reinterpret_cast<const T*>(a.dy);
+    const TW* __restrict__ w = reinterpret_cast<const TW*>(a.w);
+    if (tid < GBM) {
+        const long long m = m0 + tid;
+        if (m < a.M) {
+            pix_x[tid] = static_cast<int>(m % a.W);
+            const long long t = m / a.W;
+            pix_y[tid] = static_cast<int>(t % a.H);
+            pix_n[tid] = static_cast<int>(t / a.H);
+        } else {
+            pix_n[tid] = -1;
+            pix_y[tid] = pix_x[tid] = 0;
+        }
+    }
+    __syncthreads();
+    const int ty = tid / 16, tx = tid % 16;
+    float acc[4][4] = {};
+    const int a_pix = tid % GBM, a_kq = tid / GBM;
+    const int b_ci = tid % GBN, b_kq = tid / GBN;
+    const int pn = pix_n[a_pix], py = pix_y[a_pix], px = pix_x[a_pix];
+    for (int k0 = 0; k0 < a.K; k0 += GBK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + a_kq * 4 + j;
+            float v = 0.f;
+            if (k < a.K && pn >= 0) {
+                const int tap = k / a.Cout, co = k - tap * a.Cout;
+                const int ky = tap / a.KW, kx = tap - ky * a.KW;
+                const int ty2 = py + a.pad - ky, tx2 = px + a.pad - kx;
+                if (ty2 >= 0 && tx2 >= 0 && ty2 % a.stride == 0 && tx2 % a.stride == 0) {
+                    const int oy = ty2 / a.stride, ox = tx2 / a.stride;
+                    if (oy < a.OH && ox < a.OW)
+                        v = ldf(dy + ((static_cast<long long>(pn) * a.OH + oy) * a.OW + ox) * a.lddy + co);
+                }
+            }
+            As[a_kq * 4 + j][a_pix] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + b_kq * 4 + j;
+            const int ci = n0 + b_ci;
+            float v = 0.f;
+            if (k < a.K && ci < a.Cin) {
+                const int tap = k / a.Cout, co = k - tap * a.Cout;
+                v = to_f32<TW>(w[co * a.w_sco + tap * a.w_stap + ci]);
+            }
+            Bs[b_kq * 4 + j][b_ci] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GBK; ++kk) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float af[4] = {av.x, av.y, av.z, av.w};
+            const float bf[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(af[i], bf[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    T* __restrict__ dx = reinterpret_cast<T*>(a.dx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= a.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ci = n0 + tx * 4 + j;
+            if (ci >= a.Cin) continue;
+            T* o = dx + m * a.lddx + ci;
+            float v = acc[i][j];
+            if (a.accumulate) v += ldf(o);
+            *o = from_f32<T>(v);
+        }
+    }
+}
+
+// Dense convolution, weight gradient, split over the pixel dimension (blockIdx.z):
+//   partial[z][co][tap*Cin + ci] = sum over the split's output pixels of dy[pix][co] * x[n][oy*s-p+ky][ox*s-p+kx][ci]
+struct WgradArgs {
+    const void* dy; long long lddy;
+    const void* x; long long sxn, sxh, sxw, sxc;
+    float* partial;
+    int N, H, W, Cin, Cout, KH, KW, stride, pad, OH, OW;
+    long long M, rows_per_split;  // M = N*OH*OW
+    int Kn;                       // KH*KW*Cin
+};
+
+template <typename T, typename TX>
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
+    __shared__ __align__(16) float As[GBK][GBM];       // dy^T : [pixel][co]
+    __shared__ __align__(16) float Bs[GBK][GBN + 4];   // x    : [pixel][(tap, ci)]
+    const int tid = threadIdx.x;
+    const int co0 = blockIdx.x * GBM, kn0 = blockIdx.y * GBN;
+    const long long r0 = static_cast<long long>(blockIdx.z) * a.rows_per_split;
+    const long long r1 = min(r0 + a.rows_per_split, a.M);
+    const T* __restrict__ dy = reinterpret_cast<const T*>(a.dy);
+    const TX* __restrict__ x = reinterpret_cast<const TX*>(a.x);
+    const int ty = tid / 16, tx = tid % 16;
+    float acc[4][4] = {};
+    // loaders: A: thread -> (pixel row kk = tid / 16, 4 consecutive co); B: thread -> (kk = tid / 16, 4 consecutive kn)
+    const int l_kk = tid / 16, l_q = (tid % 16) * 4;
+    // the (tap, ci) decomposition of this thread's four B columns is loop invariant
+    int b_ky[4], b_kx[4], b_ci[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int kn = kn0 + l_q + j;
+        if (kn < a.Kn) {
+            const int tap = kn / a.Cin;
+            b_ci[j] = kn - tap * a.Cin;
+            b_ky[j] = tap / a.KW;
+            b_kx[j] = tap - b_ky[j] * a.KW;
+        } else {
+            b_ci[j] = -1;
+            b_ky[j] = b_kx[j] = 0;
+        }
+    }
+    for (long long p0 = r0; p0 < r1; p0 += GBK) {
+        const long long m = p0 + l_kk;
+        int n = 0, oy = 0, ox = 0;
+        const bool valid = m < r1;
+        if (valid) {
+            ox = static_cast<int>(m % a.OW);
+            const long long t = m / a.OW;
+            oy = static_cast<int>(t % a.OH);
+            n = static_cast<int>(t / a.OH);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = co0 + l_q + j;
+            As[l_kk][l_q + j] = (valid && co < a.Cout) ? ldf(dy + m * a.lddy + co) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = 0.f;
+            if (valid && b_ci[j] >= 0) {
+                const int iy = oy * a.stride - a.pad + b_ky[j], ix = ox * a.stride - a.pad + b_kx[j];
+                if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+                    v = to_f32<TX>(x[n * a.sxn + iy * a.sxh + ix * a.sxw + b_ci[j] * a.sxc]);
+            }
+            Bs[l_kk][l_q + j] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GBK; ++kk) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float af[4] = {av.x, av.y, av.z, av.w};
+            const float bf[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(af[i], bf[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* out = a.partial + static_cast<long long>(blockIdx.z) * a.Cout * a.Kn;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + ty * 4 + i;
+        if (co >= a.Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kn = kn0 + tx * 4 + j;
+            if (kn < a.Kn) out[static_cast<long long>(co) * a.Kn + kn] = acc[i][j];
+        }
+    }
+}
+
+// dW (OIHW) += sum over splits of partial[z][co][tap*Cin + ci]
+__global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin, int taps,
+                                      float* __restrict__ dw) {
+    const long long total = static_cast<long long>(Cout) * Cin * taps;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ci = static_cast<int>(i % Cin);
+    const long long t = i / Cin;
+    const int tap = static_cast<int>(t % taps), co = static_cast<int>(t / taps);
+    float sum = 0.f;
+    for (int z = 0; z < splits; ++z) sum += partial[static_cast<long long>(z) * total + i];
+    dw[(static_cast<long long>(co) * Cin + ci) * taps + tap] += sum;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Depthwise convolution gradients.
+template <typename T>
+__global__ void __launch_bounds__(256)
+dw_dgrad_kernel(const T* __restrict__ dy, long long lddy, const float* __restrict__ w /* [k*k][C] */, T* __restrict__ dx,
+                long long lddx, int N, int H, int W, int C, int K, int stride, int OH, int OW, int accumulate) {
+    const int pad = (K - 1) / 2;
+    const long long total = static_cast<long long>(N) * H * W * C;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        long long t = i / C;
+        const int ix = static_cast<int>(t % W);
+        t /= W;
+        const int iy = static_cast<int>(t % H), n = static_cast<int>(t / H);
+        float acc = 0.f;
+        for (int ky = 0; ky < K; ++ky) {
+            const int ty = iy + pad - ky;
+            if (ty < 0 || ty % stride) continue;
+            const int oy = ty / stride;
+            if (oy >= OH) continue;
+            for (int kx = 0; kx < K; ++kx) {
+                const int tx = ix + pad - kx;
+                if (tx < 0 || tx % stride) continue;
+                const int ox = tx / stride;
+                if (ox >= OW) continue;
+                acc = fmaf(ldf(dy + ((static_cast<long long>(n) * OH + oy) * OW + ox) * lddy + c), w[(ky * K + kx) * C + c], acc);
+            }
+        }
+        T* o = dx + ((static_cast<long long>(n) * H + iy) * W + ix) * lddx + c;
+        if (accumulate) acc += ldf(o);
+        *o = from_f32<T>(acc);
+    }
+}
+
+// partial[b][tap][c] = sum over the block's output pixels of dy[pix][c] * x[pix shifted by tap][c]
+template <typename T, int KK>
+__global__ void __launch_bounds__(RED_THREADS)
+dw_wgrad_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx, int H, int W, int C,
+                int stride, int OH, int OW, long long M, long long rpb, float* __restrict__ partial) {
+    constexpr int K = KK;
+    const int pad = (K - 1) / 2;
+    col_reduce_block<K * K>(M, C, rpb, partial, [&](long long m, int c, float* acc) {
+        const int ox = static_cast<int>(m % OW);
+        const long long t = m / OW;
+        const int oy = static_cast<int>(t % OH), n = static_cast<int>(t / OH);
+        const float g = ldf(dy + m * lddy + c);
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const int iy = oy * stride - pad + ky;
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const int ix = ox * stride - pad + kx;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                    acc[ky * K + kx] = fmaf(g, ldf(x + ((static_cast<long long>(n) * H + iy) * W + ix) * ldx + c), acc[ky * K + kx]);
+            }
+        }
+    });
+}
+
+// dW ([C][1][k][k]) += sum_b partial[b][tap][c]
+__global__ void dw_wgrad_finalize_kernel(const float* __restrict__ partial, int nb, int C, int taps, float* __restrict__ dw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * taps) return;
+    const int c = i % C, t = i / C;
+    float sum = 0.f;
+    for (int b = 0; b < nb; ++b) sum += partial[(static_cast<long long>(b) * taps + t) * C + c];
+    dw[c * taps + t] += sum;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Separable sparse resampling: out[n][oy][ox][c] (+)= sum_{iy in Ry[oy]} sum_{ix in Rx[ox]} wy * wx * in[n][iy][ix][c].
+// The row operators come as CSR tables (start[o], start[o+1]) -> (index, weight).  With the forward matrices of a
+// bilinear resize / adaptive average pool this is the forward op; with their transposes it is the exact adjoint, which
+// is what the backward of every F.interpolate / AdaptiveAvgPool2d of the network needs.  Generic element strides on
+// both sides (NHWC maps and the NCHW logit gradients).
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+resample_sep_kernel(const TI* __restrict__ in, long long isn, long long isy, long long isx, long long isc,
+                    TO* __restrict__ out, long long osn, long long osy, long long osx, long long osc, int N, int OH, int OW,
+                    int C, const int* __restrict__ ys, const int* __restrict__ yi, const float* __restrict__ yw,
+                    const int* __restrict__ xs, const int* __restrict__ xi, const float* __restrict__ xw, int accumulate) {
+    const long long total = static_cast<long long>(N) * OH * OW * C;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        // c fastest when the output is channel-contiguous, x fastest otherwise (coalesced stores either way)
+        int c, ox, oy, n;
+        long long t = i;
+        if (osc == 1) {
+            c = static_cast<int>(t % C); t /= C;
+            ox = static_cast<int>(t % OW); t /= OW;
+            oy = static_cast<int>(t % OH); n = static_cast<int>(t / OH);
+        } else {
+            ox = static_cast<int>(t % OW); t /= OW;
+            oy = static_cast<int>(t % OH); t /= OH;
+            c = static_cast<int>(t % C); n = static_cast<int>(t / C);
+        }
+        float acc = 0.f;
+        const TI* base = in + n * isn + c * isc;
+        for (int a = ys[oy]; a < ys[oy + 1]; ++a) {
+            const TI* row = base + yi[a] * isy;
+            float r = 0.f;
+            for (int b = xs[ox]; b < xs[ox + 1]; ++b) r = fmaf(xw[b], ldf(row + xi[b] * isx), r);
+            acc = fmaf(yw[a], r, acc);
+        }
+        TO* o = out + n * osn + oy * osy + ox * osx + c * osc;
+        if (accumulate) acc += ldf(o);
+        *o = from_f32<TO>(acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// softmax backward over rows: ds = p * (dp - sum_j dp_j p_j) * alpha
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ ds, long long rows,
+                   int cols, float alpha) {
+    const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= rows) return;
+    const float* pr = p + row * cols;
+    const float* dr = dp + row * cols;
+    float dot = 0.f;
+    for (int c = lane; c < cols; c += 32) dot = fmaf(pr[c], dr[c], dot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    float* out = ds + row * cols;
+    for (int c = lane; c < cols; c += 32) out[c] = pr[c] * (dr[c] - dot) * alpha;
+}
+
+// CAB combine backward: out = gamma * g + x + x * sigmoid(r)
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS)
+cab_combine_bwd_kernel(const T* __restrict__ dout, long long ldo, const T* __restrict__ g, const T* __restrict__ x,
+                       const T* __restrict__ r, const float* __restrict__ gamma, T* __restrict__ dg, T* __restrict__ dx,
+                       T* __restrict__ dr, long long M, int C, long long rpb, float* __restrict__ partial, int accumulate_dx) {
+    const float gm = *gamma;
+    // column-reduction helper doubles as the elementwise pass: acc[0] collects dout * g per channel (dgamma = its total)
+    col_reduce_block<1>(M, C, rpb, partial, [&](long long m, int c, float* acc) {
+        const long long i = m * C + c;
+        const float d = ldf(dout + m * ldo + c), xv = ldf(x + i), gv = ldf(g + i);
+        const float s = 1.f / (1.f + __expf(-ldf(r + i)));
+        acc[0] = fmaf(d, gv, acc[0]);
+        dg[i] = from_f32<T>(gm * d);
+        float v = d * (1.f + s);
+        if (accumulate_dx) v += ldf(dx + i);
+        dx[i] = from_f32<T>(v);
+        dr[i] = from_f32<T>(d * xv * s * (1.f - s));
+    });
+}
+
+// total of a [nb][C] partial buffer -> one scalar accumulated into out (dgamma)
+__global__ void sum_all_kernel(const float* __restrict__ partial, long long count, float* __restrict__ out) {
+    __shared__ float s[256];
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < count; i += 256) acc += partial[i];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out += s[0];
+}
+
+// out = a + b  (gradient fan-in / residual add), any mix of pixel strides
+template <typename T>
+__global__ void __launch_bounds__(256)
+add_kernel(const T* __restrict__ a, long long lda, const T* __restrict__ b, long long ldb, T* __restrict__ out,
+           long long ldo, long long M, int C) {
+    const long long total = M * C;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long m = i / C;
+        const int c = static_cast<int>(i - m * C);
+        out[m * ldo + c] = from_f32<T>(ldf(a + m * lda + c) + ldf(b + m * ldb + c));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gate MLP backward (SE: Linear + ReLU + Linear + hard-sigmoid; FFM: 1x1 + ReLU + 1x1 + sigmoid), tiny matrices:
+//   a2 = W2 h + b2, s = gate(a2);  h = relu(W1 m + b1)
+// phase 0: da2[n][c] = ds[n][c] * gate'(.) (from s); phase 1: dW2, db2; phase 2: da1 = (da2 W2) * (h > 0);
+// phase 3: dW1, db1; phase 4: dm = da1 W1.  One launch per phase (the phases depend on each other).
+__global__ void gate_bwd_phase_kernel(int phase, int N, int C, int J, int gate, float m_scale, const float* __restrict__ m,
+                                      const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ h,
+                                      const float* __restrict__ s, const float* __restrict__ ds, float* __restrict__ da2,
+                                      float* __restrict__ da1, float* __restrict__ dW1, float* __restrict__ db1,
+                                      float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ dm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (phase == 0) {
+        if (i >= N * C) return;
+        const float sv = s[i];
+        const float d = gate == CABINET_ACT_SIGMOID ? sv * (1.f - sv) : ((sv > 0.f && sv < 1.f) ? (1.f / 6.f) : 0.f);
+        da2[i] = ds[i] * d;
+    } else if (phase == 1) {
+        if (i >= C * J) return;
+        const int c = i / J, j = i - c * J;
+        float acc = 0.f;
+        for (int n = 0; n < N; ++n) acc = fmaf(da2[n * C + c], h[n * J + j], acc);
+        dW2[i] += acc;
+        if (j == 0 && db2) {
+            float b = 0.f;
+            for (int n = 0; n < N; ++n) b += da2[n * C + c];
+            db2[c] += b;
+        }
+    } else if (phase == 2) {
+        if (i >= N * J) return;
+        const int n = i / J, j = i - n * J;
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) acc = fmaf(da2[n * C + c], W2[c * J + j], acc);
+        da1[i] = h[i] > 0.f ? acc : 0.f;
+    } else if (phase == 3) {
+        if (i >= J * C) return;
+        const int j = i / C, c = i - j * C;
+        float acc = 0.f;
+        for (int n = 0; n < N; ++n) acc = fmaf(da1[n * J + j], m[n * C + c] * m_scale, acc);
+        dW1[i] += acc;
+        if (c == 0 && db1) {
+            float b = 0.f;
+            for (int n = 0; n < N; ++n) b += da1[n * J + j];
+            db1[j] += b;
+        }
+    } else {
+        if (i >= N * C) return;
+        const int n = i / C, c = i - n * C;
+        float acc = 0.f;
+        for (int j = 0; j < J; ++j) acc = fmaf(da1[n * J + j], W1[j * C + c], acc);
+        dm[i] = acc;
+    }
+}
+
+inline unsigned ew_grid(long long total) { return static_cast<unsigned>(std::min<long long>(cab_ceil_div(total, 256), 148LL * 16)); }
+
+}  // namespace
+
+#define CAB_DT2(dt, CALL_F, CALL_B)          \
+    do {                                     \
+        if ((dt) == CABINET_F32) { CALL_F; } \
+        else { CALL_B; }                     \
+    } while (0)
+
+extern "C" int cabinet_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int KW, void* out, int out_dtype,
+                                        int cout_pad, int cin_pad, cabinet_stream_t stream) {
+    CAB_REQUIRE(w_oihw && out && Cout > 0 && Cin > 0 && KH > 0 && KW > 0 && cout_pad >= Cout && cin_pad >= Cin,
+                "pack_conv_weight: bad arguments");
+    const long long total = static_cast<long long>(cout_pad) * KH * KW * cin_pad;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (out_dtype == CABINET_F32)
+        pack_conv_weight_kernel<float><<<ew_grid(total), 256, 0, s>>>(w_oihw, Cout, Cin, KH * KW, cout_pad, cin_pad,
+                                                                       reinterpret_cast<float*>(out));
+    else
+        pack_conv_weight_kernel<bf16><<<ew_grid(total), 256, 0, s>>>(w_oihw, Cout, Cin, KH * KW, cout_pad, cin_pad,
+                                                                      reinterpret_cast<bf16*>(out));
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_pack_dw_weight(const float* w, int C, int k, float* out, cabinet_stream_t stream) {
+    CAB_REQUIRE(w && out && C > 0 && k > 0, "pack_dw_weight: bad arguments");
+    pack_dw_weight_kernel<<<static_cast<unsigned>(cab_ceil_div(C * k * k, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, C, k * k, out);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" long long cabinet_train_scratch_floats(long long M, int C, int nq) {
+    long long rpb;
+    const int nb = red_blocks(std::max<long long>(M, 1), &rpb);
+    return static_cast<long long>(nb) * nq * C;
+}
+
+extern "C" int cabinet_bn_train_stats(const void* x, long long ldx, int dtype, long long M, int C, const float* gamma,
+                                      const float* beta, float eps, float momentum, float* running_mean,
+                                      float* running_var, float* stats, float* scratch, cabinet_stream_t stream) {
+    CAB_REQUIRE(x && stats && scratch && M > 0 && C > 0 && ldx >= C, "bn_train_stats: bad arguments");
+    long long rpb;
+    const int nb = red_blocks(M, &rpb);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CAB_DT2(dtype,
+            (bn_stats_kernel<float><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const float*>(x), ldx, M, C, rpb, scratch)),
+            (bn_stats_kernel<bf16><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const bf16*>(x), ldx, M, C, rpb, scratch)));
+    CAB_LAUNCH_CHECK();
+    const unsigned g = static_cast<unsigned>(cab_ceil_div(C, 128));
+    CAB_DT2(dtype,
+            (bn_finalize_kernel<float><<<g, 128, 0, s>>>(scratch, nb, M, C, reinterpret_cast<const float*>(x), gamma, beta, eps,
+                                                        momentum, running_mean, running_var, stats)),
+            (bn_finalize_kernel<bf16><<<g, 128, 0, s>>>(scratch, nb, M, C, reinterpret_cast<const bf16*>(x), gamma, beta, eps,
+                                                       momentum, running_mean, running_var, stats)));
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_affine_act(const void* z, long long ldz, int z_dtype, const float* scale, const float* shift,
+                                  const float* gate, float gate_plus, const void* res, long long ldres, void* y,
+                                  long long ldy, int y_dtype, long long M, long long HW, int C, int act,
+                                  cabinet_stream_t stream) {
+    CAB_REQUIRE(z && y && M >= 0 && C > 0 && HW > 0 && (!scale || shift), "affine_act: bad arguments");
+    if (M == 0) return CABINET_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const unsigned g = ew_grid(M * C);
+#define CAB_AA(TZ, TY)                                                                                                \
+    affine_act_kernel<TZ, TY><<<g, 256, 0, s>>>(reinterpret_cast<const TZ*>(z), ldz, scale, shift, gate, gate_plus,   \
+                                                reinterpret_cast<const TY*>(res), ldres, reinterpret_cast<TY*>(y), ldy, \
+                                                M, HW, C, act)
+    if (z_dtype == CABINET_F32 && y_dtype == CABINET_F32) CAB_AA(float, float);
+    else if (z_dtype == CABINET_F32) CAB_AA(float, bf16);
+    else if (y_dtype == CABINET_F32) CAB_AA(bf16, float);
+    else CAB_AA(bf16, bf16);
+#undef CAB_AA
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_bn_train_backward(const void* dy, long long lddy, const void* z, long long ldz, int dtype,
+                                         const float* stats, int act, float* dgamma, float* dbeta, void* dz,
+                                         long long lddz, long long M, int C, int accumulate, float* scratch,
+                                         cabinet_stream_t stream) {
+    CAB_REQUIRE(dy && z && stats && dz && scratch && M > 0 && C > 0, "bn_train_backward: bad arguments");
+    long long rpb;
+    const int nb = red_blocks(M, &rpb);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float* coef = scratch + static_cast<long long>(nb) * 2 * C;
+    CAB_DT2(dtype,
+            (bn_bwd_reduce_kernel<float><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const float*>(dy), lddy,
+                                                                         reinterpret_cast<const float*>(z), ldz, stats, act, M, C, rpb, scratch)),
+            (bn_bwd_reduce_kernel<bf16><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const bf16*>(dy), lddy,
+                                                                        reinterpret_cast<const bf16*>(z), ldz, stats, act, M, C, rpb, scratch)));
+    CAB_LAUNCH_CHECK();
+    bn_bwd_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(C, 128)), 128, 0, s>>>(scratch, nb, M, C, dgamma, dbeta, coef);
+    CAB_LAUNCH_CHECK();
+    const unsigned g = ew_grid(M * C);
+    CAB_DT2(dtype,
+            (bn_bwd_apply_kernel<float><<<g, 256, 0, s>>>(reinterpret_cast<const float*>(dy), lddy, reinterpret_cast<const float*>(z), ldz,
+                                                         stats, coef, act, reinterpret_cast<float*>(dz), lddz, M, C, accumulate)),
+            (bn_bwd_apply_kernel<bf16><<<g, 256, 0, s>>>(reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(z), ldz,
+                                                        stats, coef, act, reinterpret_cast<bf16*>(dz), lddz, M, C, accumulate)));
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_gate_apply_backward(const void* dy, long long lddy, const void* v, long long ldv, int dtype,
+                                           const float* s, float plus, const float* dm, float inv_hw, int act, void* dv,
+                                           long long lddv, int N, long long HW, int C, int accumulate,
+                                           cabinet_stream_t stream) {
+    CAB_REQUIRE(dy && v && dv && N >= 0 && HW > 0 && C > 0, "gate_apply_backward: bad arguments");
+    if (N == 0) return CABINET_OK;
+    const long long M = static_cast<long long>(N) * HW;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CAB_DT2(dtype,
+            (gate_bwd_apply_kernel<float><<<ew_grid(M * C), 256, 0, st>>>(reinterpret_cast<const float*>(dy), lddy, reinterpret_cast<const float*>(v), ldv, s, plus,
+                                                                         dm, inv_hw, act, reinterpret_cast<float*>(dv), lddv, M, HW, C, accumulate)),
+            (gate_bwd_apply_kernel<bf16><<<ew_grid(M * C), 256, 0, st>>>(reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(v), ldv, s, plus,
+                                                                        dm, inv_hw, act, reinterpret_cast<bf16*>(dv), lddv, M, HW, C, accumulate)));
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_gate_scale_backward(const void* dy, long long lddy, const void* v, long long ldv, int dtype,
+                                           const float* s, float plus, int act, float* ds, int N, long long HW, int C,
+                                           float* scratch, cabinet_stream_t stream) {
+    CAB_REQUIRE(dy && v && s && ds && scratch && N > 0 && HW > 0 && C > 0 && N <= 65535, "gate_scale_backward: bad arguments");
+    long long rpb;
+    const int nb = red_blocks(HW, &rpb);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid(nb, N);
+    CAB_DT2(dtype,
+            (gate_bwd_reduce_kernel<float><<<grid, RED_THREADS, RED_SMEM, st>>>(reinterpret_cast<const float*>(dy), lddy, reinterpret_cast<const float*>(v), ldv,
+                                                                               s, plus, act, HW, C, rpb, scratch)),
+            (gate_bwd_reduce_kernel<bf16><<<grid, RED_THREADS, RED_SMEM, st>>>(reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(v), ldv,
+                                                                              s, plus, act, HW, C, rpb, scratch)));
+    CAB_LAUNCH_CHECK();
+    sum_partials_kernel<<<dim3(static_cast<unsigned>(cab_ceil_div(C, 128)), N), 128, 0, st>>>(scratch, nb, C, static_cast<long long>(nb) * C, ds,
+                                                                                               1.f, 0);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_col_sum(const void* x, long long ldx, int dtype, long long M, int C, float* out, int accumulate,
+                               float* scratch, cabinet_stream_t stream) {
+    CAB_REQUIRE(x && out && scratch && M > 0 && C > 0, "col_sum: bad arguments");
+    long long rpb;
+    const int nb = red_blocks(M, &rpb);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CAB_DT2(dtype,
+            (col_sum_kernel<float><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const float*>(x), ldx, M, C, rpb, scratch)),
+            (col_sum_kernel<bf16><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const bf16*>(x), ldx, M, C, rpb, scratch)));
+    CAB_LAUNCH_CHECK();
+    sum_partials_kernel<<<dim3(static_cast<unsigned>(cab_ceil_div(C, 128)), 1), 128, 0, s>>>(scratch, nb, C, 0, out, 1.f, accumulate);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_conv_dgrad(const void* dy, long long lddy, int dtype, const void* w_packed, int w_dtype,
+                                  long long w_sco, long long w_stap, void* dx, long long lddx, int N, int H, int W, int Cin,
+                                  int Cout, int KH, int KW, int stride, int pad, int OH, int OW, int accumulate,
+                                  cabinet_stream_t stream) {
+    CAB_REQUIRE(dy && w_packed && dx && N >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && stride >= 1, "conv_dgrad: bad arguments");
+    if (N == 0) return CABINET_OK;
+    DgradArgs a;
+    a.dy = dy; a.lddy = lddy; a.w = w_packed; a.w_sco = w_sco; a.w_stap = w_stap; a.dx = dx; a.lddx = lddx;
+    a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad;
+    a.OH = OH; a.OW = OW; a.accumulate = accumulate;
+    a.M = static_cast<long long>(N) * H * W;
+    a.K = KH * KW * Cout;
+    dim3 grid(static_cast<unsigned>(cab_ceil_div(a.M, GBM)), static_cast<unsigned>(cab_ceil_div(Cin, GBN)));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == CABINET_F32 && w_dtype == CABINET_F32) conv_dgrad_kernel<float, float><<<grid, 256, 0, s>>>(a);
+    else if (dtype == CABINET_F32) conv_dgrad_kernel<float, bf16><<<grid, 256, 0, s>>>(a);
+    else if (w_dtype == CABINET_F32) conv_dgrad_kernel<bf16, float><<<grid, 256, 0, s>>>(a);
+    else conv_dgrad_kernel<bf16, bf16><<<grid, 256, 0, s>>>(a);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" long long cabinet_conv_wgrad_scratch_floats(int N, int OH, int OW, int Cin, int Cout, int KH, int KW) {
+    const long long M = static_cast<long long>(N) * OH * OW;
+    const long long tiles = cab_ceil_div(Cout, GBM) * cab_ceil_div(static_cast<long long>(KH) * KW * Cin, GBN);
+    long long splits = std::max<long long>(1, std::min<long long>(cab_ceil_div(148LL * 4, tiles), cab_ceil_div(M, 256)));
+    splits = std::min<long long>(splits, 512);
+    return splits * Cout * KH * KW * Cin;
+}
+
+extern "C" int cabinet_conv_wgrad(const void* dy, long long lddy, int dtype, const void* x, int x_dtype, long long sxn,
+                                  long long sxh, long long sxw, long long sxc, float* dw_oihw, int N, int H, int W, int Cin,
+                                  int Cout, int KH, int KW, int stride, int pad, int OH, int OW, float* scratch,
+                                  cabinet_stream_t stream) {
+    CAB_REQUIRE(dy && x && dw_oihw && scratch && N > 0 && Cin > 0 && Cout > 0, "conv_wgrad: bad arguments");
+    WgradArgs a;
+    a.dy = dy; a.lddy = lddy; a.x = x; a.sxn = sxn; a.sxh = sxh; a.sxw = sxw; a.sxc = sxc; a.partial = scratch;
+    a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad;
+    a.OH = OH; a.OW = OW;
+    a.M = static_cast<long long>(N) * OH * OW;
+    a.Kn = KH * KW * Cin;
+    const long long total = static_cast<long long>(Cout) * a.Kn;
+    const long long splits = cabinet_conv_wgrad_scratch_floats(N, OH, OW, Cin, Cout, KH, KW) / total;
+    a.rows_per_split = cab_ceil_div(cab_ceil_div(a.M, splits), GBK) * GBK;
+    const int nz = static_cast<int>(cab_ceil_div(a.M, a.rows_per_split));
+    dim3 grid(static_cast<unsigned>(cab_ceil_div(Cout, GBM)), static_cast<unsigned>(cab_ceil_div(a.Kn, GBN)), nz);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == CABINET_F32 && x_dtype == CABINET_F32) conv_wgrad_kernel<float, float><<<grid, 256, 0, s>>>(a);
+    else if (dtype == CABINET_F32) conv_wgrad_kernel<float, bf16><<<grid, 256, 0, s>>>(a);
+    else if (x_dtype == CABINET_F32) conv_wgrad_kernel<bf16, float><<<grid, 256, 0, s>>>(a);
+    else conv_wgrad_kernel<bf16, bf16><<<grid, 256, 0, s>>>(a);
+    CAB_LAUNCH_CHECK();
+    wgrad_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(total, 256)), 256, 0, s>>>(scratch, nz, Cout, Cin, KH * KW, dw_oihw);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_dwconv_dgrad(const void* dy, long long lddy, int dtype, const float* w_packed, void* dx,
+                                    long long lddx, int N, int H, int W, int C, int k, int stride, int OH, int OW,
+                                    int accumulate, cabinet_stream_t stream) {
+    CAB_REQUIRE(dy && w_packed && dx && C > 0 && (k == 3 || k == 5) && stride >= 1, "dwconv_dgrad: bad arguments");
+    if (N == 0) return CABINET_OK;
+    const long long total = static_cast<long long>(N) * H * W * C;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CAB_DT2(dtype,
+            (dw_dgrad_kernel<float><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const float*>(dy), lddy, w_packed, reinterpret_cast<float*>(dx), lddx, N, H, W,
+                                                                  C, k, stride, OH, OW, accumulate)),
+            (dw_dgrad_kernel<bf16><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const bf16*>(dy), lddy, w_packed, reinterpret_cast<bf16*>(dx), lddx, N, H, W,
+                                                                 C, k, stride, OH, OW, accumulate)));
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_dwconv_wgrad(const void* dy, long long lddy, const void* x, long long ldx, int dtype, float* dw,
+                                    int N, int H, int W, int C, int k, int stride, int OH, int OW, float* scratch,
+                                    cabinet_stream_t stream) {
+    CAB_REQUIRE(dy && x && dw && scratch && N > 0 && C > 0 && (k == 3 || k == 5), "dwconv_wgrad: bad arguments");
+    const long long M = static_cast<long long>(N) * OH * OW;
+    long long rpb;
+    const int nb = red_blocks(M, &rpb);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t smem = RED_THREADS * k * k * sizeof(float);
+#define CAB_DWW(T, KK)                                                                                                   \
+    dw_wgrad_kernel<T, KK><<<nb, RED_THREADS, smem, s>>>(reinterpret_cast<const T*>(dy), lddy, reinterpret_cast<const T*>(x), \
+                                                         ldx, H, W, C, stride, OH, OW, M, rpb, scratch)
+    if (dtype == CABINET_F32) { if (k == 3) CAB_DWW(float, 3); else CAB_DWW(float, 5); }
+    else { if (k == 3) CAB_DWW(bf16, 3); else CAB_DWW(bf16, 5); }
+#undef CAB_DWW
+    CAB_LAUNCH_CHECK();
+    dw_wgrad_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(C * k * k, 256)), 256, 0, s>>>(scratch, nb, C, k * k, dw);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_resample_sep(const void* in, int in_dtype, long long isn, long long isy, long long isx,
+                                    long long isc, void* out, int out_dtype, long long osn, long long osy, long long osx,
+                                    long long osc, int N, int OH, int OW, int C, const int* y_start, const int* y_index,
+                                    const float* y_weight, const int* x_start, const int* x_index, const float* x_weight,
+                                    int accumulate, cabinet_stream_t stream) {
+    CAB_REQUIRE(in && out && y_start && y_index && y_weight && x_start && x_index && x_weight && OH > 0 && OW > 0 && C > 0,
+                "resample_sep: bad arguments");
+    if (N == 0) return CABINET_OK;
+    const long long total = static_cast<long long>(N) * OH * OW * C;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define CAB_RS(TI, TO)                                                                                                   \
+    resample_sep_kernel<TI, TO><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const TI*>(in), isn, isy, isx, isc,      \
+                                                               reinterpret_cast<TO*>(out), osn, osy, osx, osc, N, OH, OW, C, \
+                                                               y_start, y_index, y_weight, x_start, x_index, x_weight, accumulate)
+    if (in_dtype == CABINET_F32 && out_dtype == CABINET_F32) CAB_RS(float, float);
+    else if (in_dtype == CABINET_F32) CAB_RS(float, bf16);
+    else if (out_dtype == CABINET_F32) CAB_RS(bf16, float);
+    else CAB_RS(bf16, bf16);
+#undef CAB_RS
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_softmax_backward(const float* p, const float* dp, float* ds, long long rows, int cols, float alpha,
+                                        cabinet_stream_t stream) {
+    CAB_REQUIRE(p && dp && ds && cols > 0, "softmax_backward: bad arguments");
+    if (rows == 0) return CABINET_OK;
+    softmax_bwd_kernel<<<static_cast<unsigned>(cab_ceil_div(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, dp, ds, rows, cols, alpha);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_cab_combine_backward(const void* dout, long long ldo, const void* g, const void* x, const void* r,
+                                            const float* gamma, int dtype, void* dg, void* dx, void* dr, float* dgamma,
+                                            long long n_pixels, int C, int accumulate_dx, float* scratch,
+                                            cabinet_stream_t stream) {
+    CAB_REQUIRE(dout && g && x && r && gamma && dg && dx && dr && dgamma && scratch && n_pixels > 0 && C > 0,
+                "cab_combine_backward: bad arguments");
+    long long rpb;
+    const int nb = red_blocks(n_pixels, &rpb);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CAB_DT2(dtype,
+            (cab_combine_bwd_kernel<float><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const float*>(dout), ldo, reinterpret_cast<const float*>(g),
+                                                                           reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(r), gamma,
+                                                                           reinterpret_cast<float*>(dg), reinterpret_cast<float*>(dx), reinterpret_cast<float*>(dr),
+                                                                           n_pixels, C, rpb, scratch, accumulate_dx)),
+            (cab_combine_bwd_kernel<bf16><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const bf16*>(dout), ldo, reinterpret_cast<const bf16*>(g),
+                                                                          reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(r), gamma,
+                                                                          reinterpret_cast<bf16*>(dg), reinterpret_cast<bf16*>(dx), reinterpret_cast<bf16*>(dr),
+                                                                          n_pixels, C, rpb, scratch, accumulate_dx)));
+    CAB_LAUNCH_CHECK();
+    sum_all_kernel<<<1, 256, 0, s>>>(scratch, static_cast<long long>(nb) * C, dgamma);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_add(const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo, int dtype,
+                           long long M, int C, cabinet_stream_t stream) {
+    CAB_REQUIRE(a && b && out && C > 0, "add: bad arguments");
+    if (M == 0) return CABINET_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CAB_DT2(dtype,
+            (add_kernel<float><<<ew_grid(M * C), 256, 0, s>>>(reinterpret_cast<const float*>(a), lda, reinterpret_cast<const float*>(b), ldb,
+                                                             reinterpret_cast<float*>(out), ldo, M, C)),
+            (add_kernel<bf16><<<ew_grid(M * C), 256, 0, s>>>(reinterpret_cast<const bf16*>(a), lda, reinterpret_cast<const bf16*>(b), ldb,
+                                                            reinterpret_cast<bf16*>(out), ldo, M, C)));
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_gate_mlp_backward(const float* mean, float mean_scale, const float* w1, const float* w2, const float* hidden,
+                                         const float* s, const float* ds, int gate, int N, int C, int J, float* dw1,
+                                         float* db1, float* dw2, float* db2, float* dmean, float* scratch,
+                                         cabinet_stream_t stream) {
+    CAB_REQUIRE(mean && w1 && w2 && hidden && s && ds && dw1 && dw2 && dmean && scratch && N > 0 && C > 0 && J > 0,
+                "gate_mlp_backward: bad arguments");
+    float* da2 = scratch;
+    float* da1 = scratch + static_cast<long long>(N) * C;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int sizes[5] = {N * C, C * J, N * J, J * C, N * C};
+    for (int ph = 0; ph < 5; ++ph) {
+        gate_bwd_phase_kernel<<<static_cast<unsigned>(cab_ceil_div(sizes[ph], 128)), 128, 0, st>>>(ph, N, C, J, gate, mean_scale, mean, w1, w2, hidden, s, ds, da2, da1,
+                                                                                                    dw1, db1, dw2, db2, dmean);
+        CAB_LAUNCH_CHECK();
+    }
+    return CABINET_OK;
+}

@@ -275,9 +275,11 @@ class CABiNet(nn.Module):
         self.conv_out = CABiNetOutput(256, 256, n_classes)
         self.precision = "bf16"
         self.logits_dtype = torch.float32
+        self.train_precision = "fp32"   # activation dtype of the training step: "fp32" | "bf16"
         self.use_cuda_graph = False  # replay a captured kernel schedule per input shape (static output buffers)
         self.sub_batch = 0           # > 0: run the schedule over chunks of this many images (L2-resident activations)
         self.__dict__["_engine"] = None
+        self.__dict__["_train_engine"] = None
 
     # ------------------------------------------------------------------ engine plumbing
     def _weights_stamp(self):
@@ -302,40 +304,61 @@ class CABiNet(nn.Module):
 
     def _apply(self, fn, *a, **kw):
         self.__dict__["_engine"] = None
+        self.__dict__["_train_engine"] = None
         return super()._apply(fn, *a, **kw)
 
     def __deepcopy__(self, memo):  # EMA deep-copies the model (reference: src/utils/ema.py:44)
-        eng = self.__dict__.pop("_engine", None)
+        eng, teng = self.__dict__.pop("_engine", None), self.__dict__.pop("_train_engine", None)
         try:
             cls = self.__class__
             new = cls.__new__(cls)
             memo[id(self)] = new
             new.__dict__.update({k: copy.deepcopy(v, memo) for k, v in self.__dict__.items()})
-            new.__dict__["_engine"] = None
+            new.__dict__["_engine"] = new.__dict__["_train_engine"] = None
         finally:
-            self.__dict__["_engine"] = eng
+            self.__dict__["_engine"], self.__dict__["_train_engine"] = eng, teng
         return new
 
     def __getstate__(self):
         d = dict(self.__dict__)
-        d["_engine"] = None
+        d["_engine"] = d["_train_engine"] = None
         return d
 
     # ------------------------------------------------------------------ forward surface
-    def _check_input(self, x):
+    def _check_input(self, x, inference_only=True):
         if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.shape[1] != 3:
             raise ValueError(f"expected an (N, 3, H, W) tensor, got {getattr(x, 'shape', type(x))}")
         if not x.is_cuda:
             raise RuntimeError("cabinet_b200.CABiNet has no CPU path: move the model and the input to a CUDA device")
-        if self.training:
-            raise RuntimeError("cabinet_b200.CABiNet implements the inference forward only (eval-mode BN); "
+        if self.training and inference_only:
+            raise RuntimeError("the fused mask / confusion-matrix / class-map calls are inference paths (eval-mode BN); "
                                "call .eval() first")
+
+    def train_engine(self):
+        """The training-step engine (train-mode forward + backward kernels) for the current device / precision."""
+        from .train_engine import TrainEngine
+
+        eng = self.__dict__.get("_train_engine")
+        dev = next(self.parameters()).device
+        if eng is None or eng.dev != dev or eng.precision != self.train_precision:
+            eng = self.__dict__["_train_engine"] = TrainEngine(self, precision=self.train_precision)
+        return eng
 
     def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """(N,3,H,W) -> (final_logit, high_res_logit_up), each (N, n_classes, H, W) NCHW.
 
-        reference: cabinet.py:207-247 (the aux head is upsampled in two stages, F8).
+        reference: cabinet.py:207-247 (the aux head is upsampled in two stages, F8).  ``.eval()``: the inference
+        schedule (BN folded into the weights).  ``.train()``: batch-statistics BatchNorm (running statistics updated) and a
+        differentiable result -- ``loss.backward()`` fills ``p.grad`` of every parameter on the forward path
+        (reference: src/scripts/train.py:429-441); ``torch.no_grad()`` in train mode gives the same forward without a tape
+        kept alive (``val_step``, train.py:443-456).
         """
+        if self.training:
+            self._check_input(x, inference_only=False)
+            from .train_engine import TrainStep
+
+            params = [p for n, p in self.named_parameters() if not n.startswith("mobile.classifier")]
+            return TrainStep.apply(self.train_engine(), self.logits_dtype, x, *params)
         self._check_input(x)
         return self.engine().forward(x, out_dtype=self.logits_dtype)
 

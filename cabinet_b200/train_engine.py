@@ -1,0 +1,544 @@
+"""Training step of the drop-in model (BASELINE config 5): train-mode forward + backward on the C-ABI kernels.
+
+reference: ``src/scripts/train.py:429-441`` -- ``out, out16 = net(im)`` with the model in ``.train()`` (batch-statistics
+BatchNorm, running statistics updated), two ``OhemCELoss`` terms, ``loss.backward()``.  ``cabinet_b200.CABiNet`` in
+train mode routes ``forward`` through :class:`TrainStep` (a ``torch.autograd.Function``): its forward runs the schedule
+below and keeps a tape of the tensors the backward kernels need; its backward receives the gradients of the two logit
+tensors and returns one fp32 gradient per parameter, so ``loss.backward()``, ``GradScaler`` and optimizers work as with
+the reference module.  PyTorch supplies memory, streams and the autograd hand-off only: every arithmetic step is a
+kernel of ``libcabinet_b200.so`` (``csrc/train.cu`` + the forward kernels of the inference path).
+
+Layout: NHWC activations (fp32 in ``precision='fp32'``, bf16 in ``'bf16'``), class-logit maps / statistics / parameter
+gradients fp32.  All reductions are deterministic (fixed summation order), so a step is bit-reproducible.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT_HSIGMOID, ACT_HSWISH, ACT_NONE, ACT_RELU, ACT_SIGMOID, BF16, F32, check
+from .constants import BN_EPS
+from .engine import Map, _out_size
+
+BN_MOMENTUM = 0.1  # nn.BatchNorm2d default (the reference never overrides it)
+PSP_SIZES = (1, 3, 6, 8)  # reference: src/models/cab.py:49
+
+
+# ----------------------------------------------------------------------------- separable resampling operators (host)
+def bilinear_matrix(n_in: int, n_out: int) -> np.ndarray:
+    """[n_out][n_in] row operator of F.interpolate(mode='bilinear', align_corners=False) along one axis
+    (ATen area_pixel_compute_source_index; reference call sites cabinet.py:228-245, cab.py:70-72)."""
+    m = np.zeros((n_out, n_in), dtype=np.float64)
+    scale = np.float32(n_in) / np.float32(n_out)
+    for o in range(n_out):
+        src = max(np.float32((np.float32(o) + np.float32(0.5)) * scale - np.float32(0.5)), np.float32(0.0))
+        i0 = min(int(src), n_in - 1)
+        i1 = min(i0 + 1, n_in - 1)
+        w1 = np.float32(src - np.float32(i0))
+        m[o, i0] += float(np.float32(1.0) - w1)
+        m[o, i1] += float(w1)
+    return m
+
+
+def adaptive_pool_matrix(n_in: int, n_out: int) -> np.ndarray:
+    """[n_out][n_in] row operator of nn.AdaptiveAvgPool2d along one axis (bins floor(b*in/out) .. ceil((b+1)*in/out))."""
+    m = np.zeros((n_out, n_in), dtype=np.float64)
+    for b in range(n_out):
+        lo, hi = (b * n_in) // n_out, -((-(b + 1) * n_in) // n_out)
+        m[b, lo:hi] = 1.0 / (hi - lo)
+    return m
+
+
+def csr(mat: np.ndarray):
+    """dense [O][I] -> (start int32 [O+1], index int32 [nnz], weight fp32 [nnz])."""
+    start, idx, w = [0], [], []
+    for row in mat:
+        nz = np.nonzero(row)[0]
+        idx.extend(nz.tolist())
+        w.extend(row[nz].tolist())
+        start.append(len(idx))
+    return (np.asarray(start, np.int32), np.asarray(idx if idx else [0], np.int32), np.asarray(w if w else [0.0], np.float32))
+
+
+class _Tables:
+    def __init__(self, dev):
+        self.dev, self.cache = dev, {}
+
+    def get(self, kind: str, n_in: int, n_out: int, transpose: bool):
+        key = (kind, n_in, n_out, transpose)
+        if key not in self.cache:
+            m = bilinear_matrix(n_in, n_out) if kind == "bilinear" else adaptive_pool_matrix(n_in, n_out)
+            s, i, w = csr(m.T if transpose else m)
+            self.cache[key] = tuple(torch.from_numpy(a).to(self.dev) for a in (s, i, w))
+        return self.cache[key]
+
+
+class _Grads:
+    """Gradient buffers mirror the geometry of the activation buffers (same base tensor shape, so channel slices of a
+    concat buffer address the same way); a region written for the first time is overwritten, later writers accumulate."""
+
+    def __init__(self, eng):
+        self.eng, self.buf, self.written = eng, {}, {}
+
+    def _base(self, m: Map) -> torch.Tensor:
+        k = id(m.t)
+        if k not in self.buf:
+            self.buf[k] = torch.empty_like(m.t)
+            self.written[k] = []
+        return self.buf[k]
+
+    def out(self, m: Map) -> Tuple[Map, int]:
+        """-> (gradient view of ``m``, accumulate flag) and marks the region written."""
+        b = self._base(m)
+        spans = self.written[id(m.t)]
+        lo, hi = m.off, m.off + m.C
+        covered = any(a <= lo and hi <= z for a, z in spans)
+        if not covered:
+            assert not any(a < hi and lo < z for a, z in spans), "partially overlapping gradient regions"
+            spans.append((lo, hi))
+        return Map(b, m.N, m.H, m.W, m.C, m.ld, m.off), int(covered)
+
+    def get(self, m: Map) -> Optional[Map]:
+        """gradient view of ``m`` if any consumer wrote it."""
+        k = id(m.t)
+        if k not in self.buf or not any(a <= m.off and m.off + m.C <= z for a, z in self.written[k]):
+            return None
+        return Map(self.buf[k], m.N, m.H, m.W, m.C, m.ld, m.off)
+
+
+class TrainEngine:
+    def __init__(self, model, precision: str = "fp32"):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        p0 = next(model.parameters())
+        if not p0.is_cuda:
+            raise RuntimeError("cabinet_b200 training needs the model on a CUDA device (no CPU path)")
+        self.lib = _lib.load()
+        self.model, self.dev, self.precision = model, p0.device, precision
+        self.tdt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.dt = BF16 if precision == "bf16" else F32
+        self.n_classes = model.n_classes
+        self.tables = _Tables(self.dev)
+        self.tape: List = []
+        self.pgrads: Dict[int, torch.Tensor] = {}
+        self.launches = 0
+        self._keep: List[torch.Tensor] = []
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _call(self, name: str, *args):
+        check(getattr(self.lib, name)(*args, self.stream), name)
+        self.launches += 1
+
+    def new(self, N, H, W, C, dtype=None) -> Map:
+        return Map(torch.empty((N, H, W, C), dtype=dtype or self.tdt, device=self.dev), N, H, W, C, C)
+
+    def scratch(self, M: int, C: int, nq: int) -> torch.Tensor:
+        n = int(self.lib.cabinet_train_scratch_floats(int(M), int(C), int(nq)))
+        return torch.empty(max(n, 1), dtype=torch.float32, device=self.dev)
+
+    def pgrad(self, p: torch.nn.Parameter) -> torch.Tensor:
+        """fp32 gradient accumulator of a parameter (zeroed on first use in a backward)."""
+        g = self.pgrads.get(id(p))
+        if g is None:
+            g = self.pgrads[id(p)] = torch.zeros(p.shape, dtype=torch.float32, device=self.dev)
+        return g
+
+    @staticmethod
+    def _dt(t: torch.Tensor) -> int:
+        return BF16 if t.dtype == torch.bfloat16 else F32
+
+    # ------------------------------------------------------------------ ops (forward + tape entry)
+    def conv(self, x: Optional[Map], conv, out: Optional[Map] = None, out_dtype=None, nchw: Optional[torch.Tensor] = None,
+             need_dx: bool = True) -> Map:
+        """nn.Conv2d (bias optional) on an NHWC map or the fp32 NCHW network input."""
+        w, b = conv.weight, conv.bias
+        cout, cin, kh, kw = w.shape
+        stride, pad = conv.stride[0], conv.padding[0]
+        if nchw is not None:
+            N, _, H, W = nchw.shape
+            xptr, xdt, strides = nchw.data_ptr(), F32, (3 * H * W, W, 1, H * W)
+        else:
+            N, H, W = x.N, x.H, x.W
+            xptr, xdt, strides = x.ptr, x.dt, (H * W * x.ld, W * x.ld, x.ld, 1)
+            assert x.C == cin, (x.C, cin)
+        OH, OW = _out_size(H, kh, stride, pad), _out_size(W, kw, stride, pad)
+        if out is None:
+            out = self.new(N, OH, OW, cout, out_dtype)
+        wp = torch.empty((cout, kh * kw, cin), dtype=torch.float32, device=self.dev)
+        self._call("cabinet_pack_conv_weight", w.data_ptr(), cout, cin, kh, kw, wp.data_ptr(), F32, cout, cin)
+        bias = b.detach().float().contiguous() if b is not None else None
+        self._call("cabinet_conv2d_simt", xptr, xdt, *strides, 0, wp.data_ptr(), F32, kh * kw * cin, 1, 0,
+                   bias.data_ptr() if bias is not None else None, None, 0, out.ptr, out.dt, out.ld, 0, 1, N, H, W, cin, cout,
+                   kh, kw, stride, pad, OH, OW, ACT_NONE, 1.0)
+
+        def backward(g: _Grads):
+            dy = g.get(out)
+            if dy is None:
+                return
+            if b is not None:
+                sc = self.scratch(N * OH * OW, cout, 1)
+                self._call("cabinet_col_sum", dy.ptr, dy.ld, dy.dt, N * OH * OW, cout, self.pgrad(b).data_ptr(), 1,
+                           sc.data_ptr())
+            n = int(self.lib.cabinet_conv_wgrad_scratch_floats(N, OH, OW, cin, cout, kh, kw))
+            sc = torch.empty(n, dtype=torch.float32, device=self.dev)
+            self._call("cabinet_conv_wgrad", dy.ptr, dy.ld, dy.dt, xptr, xdt, *strides, self.pgrad(w).data_ptr(), N, H, W,
+                       cin, cout, kh, kw, stride, pad, OH, OW, sc.data_ptr())
+            if nchw is None and need_dx:
+                if dy.dt != x.dt:  # fp32 class-logit gradients into a bf16 activation gradient
+                    dyc = self.new(N, OH, OW, cout, x.t.dtype)
+                    self._call("cabinet_affine_act", dy.ptr, dy.ld, dy.dt, None, None, None, 0.0, None, 0, dyc.ptr, dyc.ld,
+                               dyc.dt, N * OH * OW, OH * OW, cout, ACT_NONE)
+                    dy = dyc
+                dx, acc = g.out(x)
+                self._call("cabinet_conv_dgrad", dy.ptr, dy.ld, dy.dt, wp.data_ptr(), F32, kh * kw * cin, cin, dx.ptr, dx.ld,
+                           N, H, W, cin, cout, kh, kw, stride, pad, OH, OW, acc)
+
+        self.tape.append(backward)
+        return out
+
+    def dwconv(self, x: Map, conv) -> Map:
+        """Depthwise nn.Conv2d (groups = C, no bias)."""
+        w = conv.weight
+        C, k, stride = w.shape[0], w.shape[2], conv.stride[0]
+        p = (k - 1) // 2
+        OH, OW = _out_size(x.H, k, stride, p), _out_size(x.W, k, stride, p)
+        out = self.new(x.N, OH, OW, C)
+        wp = torch.empty((k * k, C), dtype=torch.float32, device=self.dev)
+        zero = torch.zeros(C, dtype=torch.float32, device=self.dev)
+        self.launches += 1
+        self._call("cabinet_pack_dw_weight", w.data_ptr(), C, k, wp.data_ptr())
+        self._call("cabinet_dwconv", x.ptr, x.ld, wp.data_ptr(), zero.data_ptr(), out.ptr, out.ld, x.dt, x.N, x.H, x.W, C, k,
+                   stride, OH, OW, ACT_NONE, None)
+
+        def backward(g: _Grads):
+            dy = g.get(out)
+            if dy is None:
+                return
+            sc = self.scratch(x.N * OH * OW, C, k * k)
+            self._call("cabinet_dwconv_wgrad", dy.ptr, dy.ld, x.ptr, x.ld, x.dt, self.pgrad(w).data_ptr(), x.N, x.H, x.W, C, k,
+                       stride, OH, OW, sc.data_ptr())
+            dx, acc = g.out(x)
+            self._call("cabinet_dwconv_dgrad", dy.ptr, dy.ld, dy.dt, wp.data_ptr(), dx.ptr, dx.ld, x.N, x.H, x.W, C, k, stride,
+                       OH, OW, acc)
+
+        self.tape.append(backward)
+        return out
+
+    def bn(self, z: Map, bn, act: int, res: Optional[Map] = None, out: Optional[Map] = None) -> Map:
+        """Train-mode BatchNorm2d (+activation) (+ residual add)."""
+        M, C = z.N * z.H * z.W, z.C
+        stats = torch.empty((4, C), dtype=torch.float32, device=self.dev)
+        sc = self.scratch(M, C, 2)
+        self._call("cabinet_bn_train_stats", z.ptr, z.ld, z.dt, M, C, bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps),
+                   BN_MOMENTUM if bn.momentum is None else float(bn.momentum), bn.running_mean.data_ptr(),
+                   bn.running_var.data_ptr(), stats.data_ptr(), sc.data_ptr())
+        bn.num_batches_tracked.add_(1)
+        if out is None:
+            out = self.new(z.N, z.H, z.W, C)
+        self._call("cabinet_affine_act", z.ptr, z.ld, z.dt, stats[2].data_ptr(), stats[3].data_ptr(), None, 0.0,
+                   res.ptr if res is not None else None, res.ld if res is not None else 0, out.ptr, out.ld, out.dt, M,
+                   z.H * z.W, C, act)
+
+        def backward(g: _Grads):
+            dy = g.get(out)
+            if dy is None:
+                return
+            if res is not None:  # identity branch: d res += dy
+                self.add_grad(g, res, dy)
+            dz, acc = g.out(z)
+            sc2 = self.scratch(M, C, 4)
+            self._call("cabinet_bn_train_backward", dy.ptr, dy.ld, z.ptr, z.ld, z.dt, stats.data_ptr(), act,
+                       self.pgrad(bn.weight).data_ptr(), self.pgrad(bn.bias).data_ptr(), dz.ptr, dz.ld, M, C, acc,
+                       sc2.data_ptr())
+
+        self.tape.append(backward)
+        return out
+
+    def add_grad(self, g: _Grads, target: Map, dy: Map):
+        """grad(target) += dy (or = dy for the first writer)."""
+        dt, acc = g.out(target)
+        M = target.N * target.H * target.W
+        if acc:
+            self._call("cabinet_add", dt.ptr, dt.ld, dy.ptr, dy.ld, dt.ptr, dt.ld, dt.dt, M, target.C)
+        else:
+            self._call("cabinet_affine_act", dy.ptr, dy.ld, dy.dt, None, None, None, 0.0, None, 0, dt.ptr, dt.ld, dt.dt, M,
+                       target.H * target.W, target.C, ACT_NONE)
+
+    def channel_mean_sum(self, v: Map) -> torch.Tensor:
+        """[N][C] fp32 sums over the pixels of every image (deterministic two-level sum)."""
+        out = torch.empty((v.N, v.C), dtype=torch.float32, device=self.dev)
+        scratch = torch.zeros(128 + v.N * 64 * v.C, dtype=torch.float32, device=self.dev)
+        self.launches += 1
+        self._call("cabinet_channel_sum", v.ptr, v.ld, v.dt, v.N, v.H * v.W, v.C, out.data_ptr(), scratch.data_ptr(),
+                   scratch.numel() * 4)
+        return out
+
+    def gate(self, v: Map, w1, b1, w2, b2, gate_act: int, act: int, plus: float, out: Optional[Map] = None) -> Map:
+        """y = act(v * (s + plus)), s = gate(W2 relu(W1 mean(v) + b1) + b2): SELayer (mobilenetv3.py:68-83) followed by the
+        block activation, or the FFM attention (cabinet.py:146-153, plus = 1)."""
+        N, C, HW = v.N, v.C, v.H * v.W
+        J = w1.shape[0]
+        sums = self.channel_mean_sum(v)
+        hidden = torch.empty((N, J), dtype=torch.float32, device=self.dev)
+        s = torch.empty((N, C), dtype=torch.float32, device=self.dev)
+        w1f, w2f = w1.detach().reshape(J, C), w2.detach().reshape(C, J)
+        self._call("cabinet_gate_fc", sums.data_ptr(), 1.0 / HW, w1f.data_ptr(), b1.data_ptr() if b1 is not None else None,
+                   hidden.data_ptr(), N, C, J, ACT_RELU, 0)
+        self._call("cabinet_gate_fc", hidden.data_ptr(), 1.0, w2f.data_ptr(), b2.data_ptr() if b2 is not None else None,
+                   s.data_ptr(), N, J, C, gate_act, 0)
+        if out is None:
+            out = self.new(v.N, v.H, v.W, C)
+        self._call("cabinet_affine_act", v.ptr, v.ld, v.dt, None, None, s.data_ptr(), plus, None, 0, out.ptr, out.ld, out.dt,
+                   N * HW, HW, C, act)
+
+        def backward(g: _Grads):
+            dy = g.get(out)
+            if dy is None:
+                return
+            ds = torch.empty((N, C), dtype=torch.float32, device=self.dev)
+            sc = torch.empty(N * int(self.lib.cabinet_train_scratch_floats(HW, C, 1)), dtype=torch.float32, device=self.dev)
+            self._call("cabinet_gate_scale_backward", dy.ptr, dy.ld, v.ptr, v.ld, v.dt, s.data_ptr(), plus, act, ds.data_ptr(), N,
+                       HW, C, sc.data_ptr())
+            dm = torch.empty((N, C), dtype=torch.float32, device=self.dev)
+            sc2 = torch.empty(N * (C + J), dtype=torch.float32, device=self.dev)
+            self._call("cabinet_gate_mlp_backward", sums.data_ptr(), 1.0 / HW, w1f.data_ptr(), w2f.data_ptr(), hidden.data_ptr(),
+                       s.data_ptr(), ds.data_ptr(), gate_act, N, C, J, self.pgrad(w1).data_ptr(),
+                       self.pgrad(b1).data_ptr() if b1 is not None else None, self.pgrad(w2).data_ptr(),
+                       self.pgrad(b2).data_ptr() if b2 is not None else None, dm.data_ptr(), sc2.data_ptr())
+            dv, acc = g.out(v)
+            self._call("cabinet_gate_apply_backward", dy.ptr, dy.ld, v.ptr, v.ld, v.dt, s.data_ptr(), plus, dm.data_ptr(), 1.0 / HW,
+                       act, dv.ptr, dv.ld, N, HW, C, acc)
+
+        self.tape.append(backward)
+        return out
+
+    def resample(self, src: Map, kind: str, OH: int, OW: int, out: Optional[Map] = None, out_dtype=None) -> Map:
+        """Bilinear resize (align_corners=False) or adaptive average pool of an NHWC map, + its adjoint on the tape."""
+        if out is None:
+            out = self.new(src.N, OH, OW, src.C, out_dtype or src.t.dtype)
+        ty, tx = self.tables.get(kind, src.H, OH, False), self.tables.get(kind, src.W, OW, False)
+        self._call("cabinet_resample_sep", src.ptr, src.dt, src.H * src.W * src.ld, src.W * src.ld, src.ld, 1, out.ptr, out.dt,
+                   OH * OW * out.ld, OW * out.ld, out.ld, 1, src.N, OH, OW, src.C, *(t.data_ptr() for t in ty),
+                   *(t.data_ptr() for t in tx), 0)
+
+        def backward(g: _Grads):
+            dy = g.get(out)
+            if dy is None:
+                return
+            dx, acc = g.out(src)
+            ay, ax = self.tables.get(kind, src.H, OH, True), self.tables.get(kind, src.W, OW, True)
+            self._call("cabinet_resample_sep", dy.ptr, dy.dt, OH * OW * dy.ld, OW * dy.ld, dy.ld, 1, dx.ptr, dx.dt,
+                       src.H * src.W * dx.ld, src.W * dx.ld, dx.ld, 1, src.N, src.H, src.W, src.C,
+                       *(t.data_ptr() for t in ay), *(t.data_ptr() for t in ax), acc)
+
+        self.tape.append(backward)
+        return out
+
+    def psp(self, x: Map, project) -> Map:
+        """PSPModule (cab.py:46-76): cat[x, up(pool_s(x)) for s in (1,3,6,8)] -> 1x1 project."""
+        cat = self.new(x.N, x.H, x.W, 5 * x.C)
+        ident = cat.slice(0, x.C)
+        self._call("cabinet_affine_act", x.ptr, x.ld, x.dt, None, None, None, 0.0, None, 0, ident.ptr, ident.ld, ident.dt,
+                   x.N * x.H * x.W, x.H * x.W, x.C, ACT_NONE)
+
+        def ident_bwd(g: _Grads):
+            dy = g.get(ident)
+            if dy is not None:
+                self.add_grad(g, x, dy)
+
+        self.tape.append(ident_bwd)
+        for i, s in enumerate(PSP_SIZES):
+            pooled = self.resample(x, "pool", s, s)
+            self.resample(pooled, "bilinear", x.H, x.W, out=cat.slice((i + 1) * x.C, x.C))
+        return self.conv(cat, project)
+
+    def attention(self, q: Map, k: Map, v: Map) -> Map:
+        """softmax(q k^T / sqrt(d)) v per image with the probabilities kept for the backward (cab.py:149-153)."""
+        N, L, d = q.N, q.H * q.W, q.C
+        alpha = float(d) ** -0.5
+        s = torch.empty((N, L, L), dtype=torch.float32, device=self.dev)
+        p = torch.empty((N, L, L), dtype=torch.float32, device=self.dev)
+        ctx = self.new(q.N, q.H, q.W, d)
+
+        def gemm(xp, xdt, sxw, sxc, xbs, wpt, wdt, w_sco, w_sk, wbs, yp, ydt, ldy, ybs, Mr, Kd, Nc, al=1.0):
+            # out[b][m][co] = al * sum_k x[b][m][k] w[b][co][k]
+            self._call("cabinet_conv2d_simt", xp, xdt, 0, 0, sxw, sxc, xbs, wpt, wdt, w_sco, w_sk, wbs, None, None, 0, yp, ydt,
+                       ldy, ybs, N, 1, 1, Mr, Kd, Nc, 1, 1, 1, 0, 1, Mr, ACT_NONE, al)
+
+        gemm(q.ptr, q.dt, q.ld, 1, L * q.ld, k.ptr, k.dt, k.ld, 1, L * k.ld, s.data_ptr(), F32, L, L * L, L, d, L, alpha)
+        self._call("cabinet_softmax_rows", s.data_ptr(), p.data_ptr(), F32, N * L, L)
+        gemm(p.data_ptr(), F32, L, 1, L * L, v.ptr, v.dt, 1, v.ld, L * v.ld, ctx.ptr, ctx.dt, ctx.ld, L * ctx.ld, L, L, d)
+
+        def backward(g: _Grads):
+            do = g.get(ctx)
+            if do is None:
+                return
+            dp = s  # the raw scores are not needed any more: reuse their buffer
+            ds = torch.empty((N, L, L), dtype=torch.float32, device=self.dev)
+            dq, dk, dv = (self.new(q.N, q.H, q.W, d) for _ in range(3))
+            # dV[j][c] = sum_i P[i][j] dO[i][c]
+            gemm(p.data_ptr(), F32, 1, L, L * L, do.ptr, do.dt, 1, do.ld, L * do.ld, dv.ptr, dv.dt, d, L * d, L, L, d)
+            # dP[i][j] = sum_c dO[i][c] V[j][c]
+            gemm(do.ptr, do.dt, do.ld, 1, L * do.ld, v.ptr, v.dt, v.ld, 1, L * v.ld, dp.data_ptr(), F32, L, L * L, L, d, L)
+            self._call("cabinet_softmax_backward", p.data_ptr(), dp.data_ptr(), ds.data_ptr(), N * L, L, alpha)
+            # dQ[i][c] = sum_j dS[i][j] K[j][c];  dK[j][c] = sum_i dS[i][j] Q[i][c]
+            gemm(ds.data_ptr(), F32, L, 1, L * L, k.ptr, k.dt, 1, k.ld, L * k.ld, dq.ptr, dq.dt, d, L * d, L, L, d)
+            gemm(ds.data_ptr(), F32, 1, L, L * L, q.ptr, q.dt, 1, q.ld, L * q.ld, dk.ptr, dk.dt, d, L * d, L, L, d)
+            for tgt, src in ((q, dq), (k, dk), (v, dv)):
+                self.add_grad(g, tgt, src)
+
+        self.tape.append(backward)
+        return ctx
+
+    def cab_combine(self, gmap: Map, x: Map, r: Map, gamma, out: Map):
+        """out = gamma * global + x + x * sigmoid(r) (cab.py:175-184,213-216)."""
+        M = x.N * x.H * x.W
+        gm = gamma.detach().float().contiguous()
+        self._call("cabinet_cab_combine", gmap.ptr, x.ptr, r.ptr, out.ptr, out.ld, gm.data_ptr(), self.dt, M, x.C)
+
+        def backward(g: _Grads):
+            dy = g.get(out)
+            if dy is None:
+                return
+            dg, _ = g.out(gmap)
+            dr, _ = g.out(r)
+            dx, acc = g.out(x)
+            sc = self.scratch(M, x.C, 1)
+            self._call("cabinet_cab_combine_backward", dy.ptr, dy.ld, gmap.ptr, x.ptr, r.ptr, gm.data_ptr(), self.dt, dg.ptr,
+                       dx.ptr, dr.ptr, self.pgrad(gamma).data_ptr(), M, x.C, acc, sc.data_ptr())
+
+        self.tape.append(backward)
+
+    def logits_up(self, src: Map, H: int, W: int, odt: torch.dtype) -> torch.Tensor:
+        """x8 bilinear of the fp32 class map -> NCHW logits (cabinet.py:240-245) + its adjoint."""
+        N, C = src.N, src.C
+        y = torch.empty((N, C, H, W), dtype=odt, device=self.dev)
+        self._call("cabinet_upsample_logits_nchw", src.ptr, N, src.H, src.W, C, y.data_ptr(), self._dt(y), H, W)
+
+        def backward(g: _Grads, dy_nchw: torch.Tensor):
+            dy_nchw = dy_nchw.contiguous()
+            dx, acc = g.out(src)
+            ay, ax = self.tables.get("bilinear", src.H, H, True), self.tables.get("bilinear", src.W, W, True)
+            self._call("cabinet_resample_sep", dy_nchw.data_ptr(), self._dt(dy_nchw), C * H * W, W, 1, H * W, dx.ptr, dx.dt,
+                       src.H * src.W * dx.ld, src.W * dx.ld, dx.ld, 1, N, src.H, src.W, C, *(t.data_ptr() for t in ay),
+                       *(t.data_ptr() for t in ax), acc)
+
+        return y, backward
+
+    # ------------------------------------------------------------------ the step
+    def forward(self, x: torch.Tensor, logits_dtype=torch.float32):
+        """Train-mode ``CABiNet.forward`` (cabinet.py:207-247) -> (final_logit, high_res_logit_up), NCHW."""
+        m = self.model
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        N, _, H, W = x.shape
+        self.tape, self.launches, self.pgrads = [], 0, {}
+        mob, sb, ab, ffm, head = m.mobile, m.sb, m.ab, m.ffm, m.conv_out
+        ga, cab = ab.a2block.global_attn, ab.a2block
+
+        # ---- spatial branch (cabinet.py:108-129)
+        s1 = self.bn(self.conv(None, sb.conv1.conv, nchw=x), sb.conv1.bn, ACT_RELU)
+        s2 = self.bn(self.conv(s1, sb.conv2.conv), sb.conv2.bn, ACT_RELU)
+        s3 = self.bn(self.conv(s2, sb.conv3.conv), sb.conv3.bn, ACT_RELU)
+        H8, W8 = s3.H, s3.W
+        n_sb = sb.conv_out.conv.out_channels
+        cat_ffm = self.new(N, H8, W8, n_sb + ab.convb.out_channels)
+        self.bn(self.conv(s3, sb.conv_out.conv), sb.conv_out.bn, ACT_RELU, out=cat_ffm.slice(0, n_sb))
+
+        # ---- backbone (mobilenetv3.py:102-159,202-205)
+        f = self.bn(self.conv(None, mob.features[0][0], nchw=x), mob.features[0][1], ACT_HSWISH)
+        for blk in list(mob.features)[1:]:
+            s, c = blk.spec, blk.conv
+            act = ACT_HSWISH if s["hs"] else ACT_RELU
+            res = f if s["identity"] else None
+            if s["expand"]:
+                h = self.bn(self.conv(f, c[0]), c[1], act)
+                z = self.dwconv(h, c[3])
+                if s["se"]:
+                    u = self.bn(z, c[4], ACT_NONE)
+                    se = c[5]
+                    y = self.gate(u, se.fc[0].weight, se.fc[0].bias, se.fc[2].weight, se.fc[2].bias, ACT_HSIGMOID, act, 0.0)
+                else:
+                    y = self.bn(z, c[4], act)
+                f = self.bn(self.conv(y, c[7]), c[8], ACT_NONE, res=res)
+            else:
+                y = self.bn(self.dwconv(f, c[0]), c[1], act)
+                if s["se"]:  # no-expand form: activation first, then SE
+                    se = c[3]
+                    y = self.gate(y, se.fc[0].weight, se.fc[0].bias, se.fc[2].weight, se.fc[2].bias, ACT_HSIGMOID, ACT_NONE, 0.0)
+                f = self.bn(self.conv(y, c[4]), c[5], ACT_NONE, res=res)
+        h32, w32 = f.H, f.W
+        n_mf = mob.conv[0].out_channels
+        cat_b1 = self.new(N, h32, w32, n_mf + 256)
+        mf = self.bn(self.conv(f, mob.conv[0]), mob.conv[1], ACT_HSWISH, out=cat_b1.slice(0, n_mf))
+
+        # ---- attention branch (cabinet.py:75-94, cab.py:131-162,175-184,213-216)
+        feat = self.bn(self.conv(mf, ab.conva[0]), ab.conva[1], ACT_RELU)
+        q = self.bn(self.conv(feat, ga.to_query[0]), ga.to_query[1], ACT_RELU)
+        k = self.psp(self.bn(self.conv(feat, ga.to_key[0]), ga.to_key[1], ACT_RELU), ga.psp_key.project)
+        v = self.psp(self.conv(feat, ga.to_value), ga.psp_value.project)
+        ctx = self.attention(q, k, v)
+        gl = self.conv(ctx, ga.project_out)
+        r = feat
+        for dwb in cab.local_attn.refine:
+            r = self.bn(self.dwconv(r, dwb.block[0]), dwb.block[1], ACT_RELU)
+        feat2 = cat_b1.slice(n_mf, 256)
+        self.cab_combine(gl, feat, r, cab.gamma, feat2)
+        low = self.conv(feat2, ab.convb)
+        self.resample(low, "bilinear", H8, W8, out=cat_ffm.slice(n_sb, low.C))                  # cabinet.py:228-233
+        fused = self.bn(self.conv(cat_b1, ab.b1), ab.b2, ACT_RELU)
+        high = self.conv(fused, ab.b4, out_dtype=torch.float32)
+        aux8 = self.resample(high, "bilinear", H8, W8)                                          # cabinet.py:234-239
+
+        # ---- feature fusion + head (cabinet.py:142-153,162-172)
+        ff = self.bn(self.conv(cat_ffm, ffm.convblk.conv), ffm.convblk.bn, ACT_RELU)
+        ffo = self.gate(ff, ffm.conv1.weight, None, ffm.conv2.weight, None, ACT_SIGMOID, ACT_NONE, 1.0)
+        hc = self.bn(self.conv(ffo, head.conv.conv), head.conv.bn, ACT_RELU)
+        final8 = self.conv(hc, head.conv_out, out_dtype=torch.float32)
+        final, bwd_final = self.logits_up(final8, H, W, logits_dtype)
+        aux, bwd_aux = self.logits_up(aux8, H, W, logits_dtype)
+        self._out_bwd = (bwd_final, bwd_aux)
+        return final, aux
+
+    def backward(self, d_final: Optional[torch.Tensor], d_aux: Optional[torch.Tensor]) -> Dict[int, torch.Tensor]:
+        """Gradients of the two logit tensors -> {id(parameter): fp32 gradient}."""
+        g = _Grads(self)
+        self.pgrads = {}
+        for dy, bwd in ((d_final, self._out_bwd[0]), (d_aux, self._out_bwd[1])):
+            if dy is not None:
+                bwd(g, dy)
+        for fn in reversed(self.tape):
+            fn(g)
+        self.tape = []
+        return self.pgrads
+
+
+class TrainStep(torch.autograd.Function):
+    """Autograd hand-off: inputs = (engine, logits dtype, x, *parameters); outputs = the two logit tensors."""
+
+    @staticmethod
+    def forward(ctx, eng: TrainEngine, logits_dtype, x, *params):
+        with torch.no_grad(), torch.cuda.device(eng.dev):
+            final, aux = eng.forward(x, logits_dtype)
+        ctx.eng, ctx.params = eng, params
+        return final, aux
+
+    @staticmethod
+    def backward(ctx, d_final, d_aux):
+        eng = ctx.eng
+        with torch.no_grad(), torch.cuda.device(eng.dev):
+            grads = eng.backward(d_final, d_aux)
+        out = []
+        for p in ctx.params:
+            gp = grads.get(id(p))
+            out.append(gp.to(p.dtype) if gp is not None else None)
+        return (None, None, None, *out)

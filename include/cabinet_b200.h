@@ -311,6 +311,102 @@ int cabinet_ohem_ce_backward(const void* logits, int dtype, const void* labels, 
                              long long HW, const float* weight, const float* loss_px, const void* workspace,
                              const float* grad_out, void* grad_logits, cabinet_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training step (BASELINE config 5; src/scripts/train.py:429-441: net(im) in .train() mode -> 2 x OhemCELoss ->
+ * backward).  NHWC activations (fp32 or bf16), fp32 statistics and parameter gradients.  Every reduction has a fixed
+ * summation order (two-level sums, no floating-point atomics).  Scratch buffers are uninitialised device memory of
+ * cabinet_train_scratch_floats(rows, C, quantities) floats unless stated otherwise.
+ */
+long long cabinet_train_scratch_floats(long long M, int C, int nq);
+
+/* PyTorch OIHW fp32 weight -> [cout_pad][KH*KW][cin_pad] (ci fastest, zero padded), fp32 or bf16: the layout of
+ * cabinet_conv2d_simt (w_sco = KH*KW*cin_pad, w_sk = 1), cabinet_conv_tc (cout_pad = ceil16, cin_pad = ceil64, bf16)
+ * and cabinet_conv_dgrad.  Depthwise [C][1][k][k] -> [k*k][C] fp32 (cabinet_dwconv / cabinet_dwconv_dgrad). */
+int cabinet_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int KW, void* out, int out_dtype,
+                             int cout_pad, int cin_pad, cabinet_stream_t stream);
+int cabinet_pack_dw_weight(const float* w, int C, int k, float* out, cabinet_stream_t stream);
+
+/* Train-mode BatchNorm2d statistics (nn.BatchNorm2d in .train(): src/models/cabinet.py:30-31, mobilenetv3.py:88-98,
+ * cab.py:26-27) of x [M][C] (M = N*H*W): stats[4][C] = batch mean, 1/sqrt(biased var + eps), scale = gamma * invstd,
+ * shift = beta - mean * scale; running_mean / running_var (may be NULL) are updated in place with `momentum` and the
+ * unbiased variance.  scratch: (M, C, 2). */
+int cabinet_bn_train_stats(const void* x, long long ldx, int dtype, long long M, int C, const float* gamma,
+                           const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                           float* stats, float* scratch, cabinet_stream_t stream);
+
+/* y[m][c] = act((z * scale[c] + shift[c]) * (gate[n][c] + gate_plus)) + res[m][c]; scale/shift, gate ([N][C], n = m / HW)
+ * and res are optional.  BN apply (+activation), SE / FFM scale (+activation), residual add. */
+int cabinet_affine_act(const void* z, long long ldz, int z_dtype, const float* scale, const float* shift, const float* gate,
+                       float gate_plus, const void* res, long long ldres, void* y, long long ldy, int y_dtype, long long M,
+                       long long HW, int C, int act, cabinet_stream_t stream);
+
+/* Backward of y = act(BN_train(z)): g = dy * act'(u), dgamma += sum g * xhat, dbeta += sum g,
+ * dz (+)= scale * (g - mean(g) - xhat * mean(g * xhat)).  stats as written by cabinet_bn_train_stats.  scratch: (M, C, 4). */
+int cabinet_bn_train_backward(const void* dy, long long lddy, const void* z, long long ldz, int dtype, const float* stats,
+                              int act, float* dgamma, float* dbeta, void* dz, long long lddz, long long M, int C,
+                              int accumulate, float* scratch, cabinet_stream_t stream);
+
+/* Backward of y = act(v * (s[n][c] + plus)) (SE apply, mobilenetv3.py:83,143; FFM feat * atten + feat, cabinet.py:152):
+ *   _scale_backward: ds[n][c] = sum_p dy * act'(v s') * v          (scratch: (HW, C, 1) * N floats)
+ *   _apply_backward: dv (+)= dy * act'(v s') * s' + dm[n][c] * inv_hw  (dm = gradient of the pooled mean, may be NULL;
+ *                    s may be NULL: plain activation backward) */
+int cabinet_gate_scale_backward(const void* dy, long long lddy, const void* v, long long ldv, int dtype, const float* s,
+                                float plus, int act, float* ds, int N, long long HW, int C, float* scratch,
+                                cabinet_stream_t stream);
+int cabinet_gate_apply_backward(const void* dy, long long lddy, const void* v, long long ldv, int dtype, const float* s,
+                                float plus, const float* dm, float inv_hw, int act, void* dv, long long lddv, int N,
+                                long long HW, int C, int accumulate, cabinet_stream_t stream);
+/* Backward of the gate MLP s = gate(W2 relu(W1 m + b1) + b2), m = mean * mean_scale (SELayer.fc, FFM conv1/conv2; pass
+ * the pooling SUMS and mean_scale = 1/HW): parameter gradients are accumulated (+=), dmean [N][C] (gradient with respect
+ * to m) is overwritten.  scratch: N * (C + J) floats. */
+int cabinet_gate_mlp_backward(const float* mean, float mean_scale, const float* w1, const float* w2, const float* hidden, const float* s,
+                              const float* ds, int gate, int N, int C, int J, float* dw1, float* db1, float* dw2,
+                              float* db2, float* dmean, float* scratch, cabinet_stream_t stream);
+
+/* out[c] (+)= sum over the M rows of x[m][c] (bias gradients).  scratch: (M, C, 1). */
+int cabinet_col_sum(const void* x, long long ldx, int dtype, long long M, int C, float* out, int accumulate, float* scratch,
+                    cabinet_stream_t stream);
+
+/* Dense convolution gradients (nn.Conv2d backward).  w_packed: cabinet_pack_conv_weight layout, element strides w_sco
+ * (per output channel) and w_stap (per tap).  _dgrad: dx [N][H][W][Cin] (+)= conv_transpose(dy, w).  _wgrad: dw (OIHW
+ * fp32) += dy^T * im2col(x), split over the pixels with a fixed-order second-level sum; x is addressed with element
+ * strides (NHWC maps and the fp32 NCHW network input); scratch: cabinet_conv_wgrad_scratch_floats(...) floats. */
+int cabinet_conv_dgrad(const void* dy, long long lddy, int dtype, const void* w_packed, int w_dtype, long long w_sco,
+                       long long w_stap, void* dx, long long lddx, int N, int H, int W, int Cin, int Cout, int KH, int KW,
+                       int stride, int pad, int OH, int OW, int accumulate, cabinet_stream_t stream);
+long long cabinet_conv_wgrad_scratch_floats(int N, int OH, int OW, int Cin, int Cout, int KH, int KW);
+int cabinet_conv_wgrad(const void* dy, long long lddy, int dtype, const void* x, int x_dtype, long long sxn, long long sxh,
+                       long long sxw, long long sxc, float* dw_oihw, int N, int H, int W, int Cin, int Cout, int KH, int KW,
+                       int stride, int pad, int OH, int OW, float* scratch, cabinet_stream_t stream);
+/* Depthwise convolution gradients; w_packed [k*k][C] fp32; dw ([C][1][k][k] fp32) +=; scratch: (N*OH*OW, C, k*k). */
+int cabinet_dwconv_dgrad(const void* dy, long long lddy, int dtype, const float* w_packed, void* dx, long long lddx, int N,
+                         int H, int W, int C, int k, int stride, int OH, int OW, int accumulate, cabinet_stream_t stream);
+int cabinet_dwconv_wgrad(const void* dy, long long lddy, const void* x, long long ldx, int dtype, float* dw, int N, int H,
+                         int W, int C, int k, int stride, int OH, int OW, float* scratch, cabinet_stream_t stream);
+
+/* Separable sparse resampling  out[n][oy][ox][c] (+)= sum_{iy, ix} Ry[oy][iy] Rx[ox][ix] in[n][iy][ix][c]  with the row
+ * operators as CSR tables (start[O+1], index[], weight[]).  Given the TRANSPOSED matrices of a bilinear resize
+ * (align_corners=False) or an adaptive average pool it is the exact adjoint: the backward of F.interpolate
+ * (src/models/cabinet.py:228-245, cab.py:70-72) and nn.AdaptiveAvgPool2d (cab.py:55-57).  Element strides on both
+ * sides (NHWC maps, NCHW logit gradients). */
+int cabinet_resample_sep(const void* in, int in_dtype, long long isn, long long isy, long long isx, long long isc,
+                         void* out, int out_dtype, long long osn, long long osy, long long osx, long long osc, int N, int OH,
+                         int OW, int C, const int* y_start, const int* y_index, const float* y_weight, const int* x_start,
+                         const int* x_index, const float* x_weight, int accumulate, cabinet_stream_t stream);
+
+/* ds = p * (dp - rowsum(dp * p)) * alpha over rows of `cols` fp32 (softmax backward, cab.py:150-151). */
+int cabinet_softmax_backward(const float* p, const float* dp, float* ds, long long rows, int cols, float alpha,
+                             cabinet_stream_t stream);
+/* Backward of out = gamma * g + x + x * sigmoid(r) (cab.py:175-184,213-216), dense [n_pixels][C] operands:
+ * dg = gamma * dout, dx (+)= dout * (1 + sigmoid(r)), dr = dout * x * sigmoid'(r), *dgamma += sum dout * g.
+ * scratch: (n_pixels, C, 1). */
+int cabinet_cab_combine_backward(const void* dout, long long ldo, const void* g, const void* x, const void* r,
+                                 const float* gamma, int dtype, void* dg, void* dx, void* dr, float* dgamma,
+                                 long long n_pixels, int C, int accumulate_dx, float* scratch, cabinet_stream_t stream);
+/* out[m][c] = a[m][c] + b[m][c] (gradient fan-in). */
+int cabinet_add(const void* a, long long lda, const void* b, long long ldb, void* out, long long ldo, int dtype, long long M,
+                int C, cabinet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -219,3 +219,43 @@ def test_packed_state_roundtrip_on_the_host(cpu_engine, tmp_path, monkeypatch):
     assert eng2.qkv[0].shape == eng.qkv[0].shape and eng2.key_ch == eng.key_ch
     with pytest.raises(ValueError):
         engine_mod.Engine(model, "bf16", packed={k: v for k, v in loaded.items() if k != "stem"})
+
+
+@pytest.mark.parametrize("mode,C,shape,precision", [("small", 8, (2, 3, 64, 96), "fp32"), ("large", 5, (2, 3, 64, 64), "bf16")])
+def test_train_engine_schedule_and_abi(monkeypatch, mode, C, shape, precision):
+    """Host logic of the training step against the recording double: every ctypes call of the forward and of the
+    backward tape has the ABI's argument count / types, every trained parameter gets a gradient buffer, the gradient
+    regions of the concat buffers are covered before they are read."""
+    from cabinet_b200 import train_engine as te
+
+    rec = RecordingLib()
+    rec.cabinet_train_scratch_floats = lambda M, Cc, nq: 16
+    rec.cabinet_conv_wgrad_scratch_floats = lambda *a: 16
+    monkeypatch.setattr(_lib, "load", lambda: rec)
+    monkeypatch.setattr(te.TrainEngine, "stream", property(lambda self: None))
+    model = build_model(C, mode).train()
+
+    class P:
+        is_cuda = True
+        device = torch.device("cpu")
+
+    real_next = next
+    monkeypatch.setattr(te, "next", lambda it: P, raising=False)
+    eng = te.TrainEngine(model, precision)
+    monkeypatch.setattr(te, "next", real_next, raising=False)
+    x = torch.zeros(shape)
+    final, aux = eng.forward(x)
+    assert final.shape == (shape[0], C, shape[2], shape[3]) and aux.shape == final.shape
+    n_fwd = len(rec.calls)
+    names = [c[0] for c in rec.calls]
+    n_bn = sum(1 for m in model.modules() if isinstance(m, torch.nn.BatchNorm2d))
+    assert names.count("cabinet_bn_train_stats") == n_bn
+    grads = eng.backward(torch.zeros_like(final), torch.zeros_like(aux))
+    bwd = [c[0] for c in rec.calls[n_fwd:]]
+    assert bwd.count("cabinet_bn_train_backward") == n_bn
+    n_conv = names.count("cabinet_conv2d_simt") - 2   # minus the two attention GEMMs
+    assert bwd.count("cabinet_conv_wgrad") == n_conv
+    assert bwd.count("cabinet_conv_dgrad") == n_conv - 2   # the two stems read the network input: no data gradient
+    trained = {id(p): n for n, p in model.named_parameters() if not n.startswith("mobile.classifier")}
+    assert set(grads) == set(trained), [trained[i] for i in set(trained) - set(grads)]
+    assert all(grads[id(p)].shape == p.shape for p in model.parameters() if id(p) in grads)

@@ -1,0 +1,356 @@
+"""GPU: the training step (BASELINE config 5) -- train-mode forward + backward kernels of ``csrc/train.cu`` behind
+``cabinet_b200.CABiNet.train()``.
+
+* per-kernel checks against torch autograd on the CPU (fp32 reference of the same op);
+* one whole step (loss, every parameter gradient, updated BN statistics) against the goldens of the imported reference
+  (``tests/golden/train_step_*.npz``, ``oracle/make_golden_train.py``) and against ``oracle/train_oracle.py`` run live.
+Tolerances: fp32 mode 2e-4 relative on the loss, 2e-3 rel-L2 on gradients (fp32 reductions in a different order than
+ATen over up to 1e5 terms); bf16 activations 5e-2.
+"""
+
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from cabinet_b200 import _lib  # noqa: E402
+from cabinet_b200._lib import ACT_HSIGMOID, ACT_HSWISH, ACT_NONE, ACT_RELU, ACT_SIGMOID, BF16, F32, check  # noqa: E402
+from cabinet_b200.constants import BACKBONE_CFGS  # noqa: E402
+from cabinet_b200.loss import OhemCELoss  # noqa: E402
+from cabinet_b200.synthetic import build_model, make_input, make_labels, state_dict_digest  # noqa: E402
+from cabinet_b200.train_engine import adaptive_pool_matrix, bilinear_matrix, csr  # noqa: E402
+from oracle.train_oracle import FULL_GRAD_KEYS, STAT_KEYS, TRAIN_CASES, train_step  # noqa: E402
+from tests.gpu_util import rel_l2  # noqa: E402
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def gen(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def act_ref(x, act):
+    return {ACT_NONE: lambda t: t, ACT_RELU: F.relu, ACT_HSWISH: F.hardswish, ACT_HSIGMOID: F.hardsigmoid,
+            ACT_SIGMOID: torch.sigmoid}[act](x)
+
+
+def nhwc(t):  # NCHW cpu -> NHWC cuda contiguous
+    return t.permute(0, 2, 3, 1).contiguous().cuda()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).cpu()
+
+
+def scratch(lib, M, C, nq):
+    return torch.empty(max(int(lib.cabinet_train_scratch_floats(M, C, nq)), 1), device="cuda")
+
+
+@pytest.mark.parametrize("N,C,H,W,act", [(2, 16, 9, 7, ACT_RELU), (3, 72, 5, 5, ACT_HSWISH), (1, 960, 2, 2, ACT_NONE),
+                                         (2, 300, 17, 13, ACT_RELU)])
+def test_bn_train_forward_backward(N, C, H, W, act):
+    lib = _lib.load()
+    x = (gen(N, C, H, W, seed=1) * 2 + 5).requires_grad_(True)   # mean >> std: the shifted sums must not cancel
+    gamma, beta = (gen(C, seed=2) * 0.3 + 1).requires_grad_(True), gen(C, seed=3, scale=0.2).requires_grad_(True)
+    rm, rv = gen(C, seed=4, scale=0.1), gen(C, seed=5).abs() + 0.5
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    y_ref = act_ref(F.batch_norm(x, rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5), act)
+    dy = gen(N, C, H, W, seed=6)
+    y_ref.backward(dy)
+    M = N * H * W
+    xd, dyd = nhwc(x.detach()), nhwc(dy)
+    stats = torch.empty(4, C, device="cuda")
+    rmd, rvd, gd, bd = rm.cuda(), rv.cuda(), gamma.detach().cuda(), beta.detach().cuda()
+    check(lib.cabinet_bn_train_stats(xd.data_ptr(), C, F32, M, C, gd.data_ptr(), bd.data_ptr(), 1e-5, 0.1, rmd.data_ptr(),
+                                     rvd.data_ptr(), stats.data_ptr(), scratch(lib, M, C, 2).data_ptr(), stream()), "stats")
+    y = torch.empty_like(xd)
+    check(lib.cabinet_affine_act(xd.data_ptr(), C, F32, stats[2].data_ptr(), stats[3].data_ptr(), None, 0.0, None, 0,
+                                 y.data_ptr(), C, F32, M, H * W, C, act, stream()), "affine_act")
+    dz = torch.empty_like(xd)
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    check(lib.cabinet_bn_train_backward(dyd.data_ptr(), C, xd.data_ptr(), C, F32, stats.data_ptr(), act, dg.data_ptr(),
+                                        db.data_ptr(), dz.data_ptr(), C, M, C, 0, scratch(lib, M, C, 4).data_ptr(), stream()),
+          "bn_bwd")
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(y), y_ref.detach()) < 1e-5
+    assert rel_l2(rmd.cpu(), rm_ref) < 1e-5 and rel_l2(rvd.cpu(), rv_ref) < 1e-5
+    assert rel_l2(nchw(dz), x.grad) < 1e-4
+    assert rel_l2(dg.cpu(), gamma.grad) < 1e-4 and rel_l2(db.cpu(), beta.grad) < 1e-4
+
+
+@pytest.mark.parametrize("N,cin,cout,k,s,p,H,W,nchw_in", [
+    (2, 16, 24, 1, 1, 0, 9, 7, False), (1, 24, 40, 3, 1, 1, 8, 11, False), (2, 64, 64, 3, 2, 1, 16, 12, False),
+    (2, 3, 64, 7, 2, 3, 20, 24, True), (1, 130, 70, 3, 1, 1, 5, 5, False), (2, 8, 5, 1, 1, 0, 33, 17, False)])
+def test_conv_gradients(N, cin, cout, k, s, p, H, W, nchw_in):
+    lib = _lib.load()
+    x = gen(N, cin, H, W, seed=1).requires_grad_(True)
+    w = gen(cout, cin, k, k, seed=2, scale=(cin * k * k) ** -0.5).requires_grad_(True)
+    y = F.conv2d(x, w, None, s, p)
+    dy = gen(*y.shape, seed=3)
+    y.backward(dy)
+    OH, OW = y.shape[2:]
+    wd = w.detach().cuda()
+    wp = torch.empty(cout, k * k, cin, device="cuda")
+    check(lib.cabinet_pack_conv_weight(wd.data_ptr(), cout, cin, k, k, wp.data_ptr(), F32, cout, cin, stream()), "pack")
+    assert torch.equal(wp.cpu(), w.detach().permute(0, 2, 3, 1).reshape(cout, k * k, cin))
+    dyd = nhwc(dy)
+    if nchw_in:
+        xd = x.detach().cuda().contiguous()
+        strides = (cin * H * W, W, 1, H * W)
+    else:
+        xd = nhwc(x.detach())
+        strides = (H * W * cin, W * cin, cin, 1)
+    dw = torch.zeros(cout, cin, k, k, device="cuda")
+    n = int(lib.cabinet_conv_wgrad_scratch_floats(N, OH, OW, cin, cout, k, k))
+    sc = torch.empty(n, device="cuda")
+    check(lib.cabinet_conv_wgrad(dyd.data_ptr(), cout, F32, xd.data_ptr(), F32, *strides, dw.data_ptr(), N, H, W, cin, cout, k,
+                                 k, s, p, OH, OW, sc.data_ptr(), stream()), "wgrad")
+    dx = torch.full((N, H, W, cin), 3.0, device="cuda")
+    check(lib.cabinet_conv_dgrad(dyd.data_ptr(), cout, F32, wp.data_ptr(), F32, k * k * cin, cin, dx.data_ptr(), cin, N, H, W,
+                                 cin, cout, k, k, s, p, OH, OW, 0, stream()), "dgrad")
+    dx2 = torch.full((N, H, W, cin), 3.0, device="cuda")
+    check(lib.cabinet_conv_dgrad(dyd.data_ptr(), cout, F32, wp.data_ptr(), F32, k * k * cin, cin, dx2.data_ptr(), cin, N, H, W,
+                                 cin, cout, k, k, s, p, OH, OW, 1, stream()), "dgrad")
+    torch.cuda.synchronize()
+    assert rel_l2(dw.cpu(), w.grad) < 1e-5
+    assert rel_l2(nchw(dx), x.grad) < 1e-5
+    assert rel_l2(nchw(dx2) - 3.0, x.grad) < 1e-4   # accumulate flag
+
+
+@pytest.mark.parametrize("N,C,k,s,H,W", [(2, 16, 3, 1, 9, 7), (1, 72, 5, 2, 11, 13), (2, 240, 3, 2, 8, 8), (1, 960, 5, 1, 4, 4)])
+def test_dwconv_gradients(N, C, k, s, H, W):
+    lib = _lib.load()
+    x = gen(N, C, H, W, seed=1).requires_grad_(True)
+    w = gen(C, 1, k, k, seed=2, scale=1.0 / k).requires_grad_(True)
+    p = (k - 1) // 2
+    y = F.conv2d(x, w, None, s, p, 1, C)
+    dy = gen(*y.shape, seed=3)
+    y.backward(dy)
+    OH, OW = y.shape[2:]
+    wd = w.detach().cuda()
+    wp = torch.empty(k * k, C, device="cuda")
+    check(lib.cabinet_pack_dw_weight(wd.data_ptr(), C, k, wp.data_ptr(), stream()), "pack_dw")
+    xd, dyd = nhwc(x.detach()), nhwc(dy)
+    dw = torch.zeros(C, 1, k, k, device="cuda")
+    check(lib.cabinet_dwconv_wgrad(dyd.data_ptr(), C, xd.data_ptr(), C, F32, dw.data_ptr(), N, H, W, C, k, s, OH, OW,
+                                   scratch(lib, N * OH * OW, C, k * k).data_ptr(), stream()), "dw_wgrad")
+    dx = torch.empty(N, H, W, C, device="cuda")
+    check(lib.cabinet_dwconv_dgrad(dyd.data_ptr(), C, F32, wp.data_ptr(), dx.data_ptr(), C, N, H, W, C, k, s, OH, OW, 0,
+                                   stream()), "dw_dgrad")
+    torch.cuda.synchronize()
+    assert rel_l2(dw.cpu(), w.grad) < 1e-5 and rel_l2(nchw(dx), x.grad) < 1e-5
+
+
+@pytest.mark.parametrize("kind,n_in,n_out", [("bilinear", 4, 16), ("bilinear", 17, 68), ("bilinear", 3, 5),
+                                              ("bilinear", 8, 5), ("pool", 7, 3), ("pool", 2, 6), ("pool", 32, 8)])
+def test_resample_operator_and_adjoint(kind, n_in, n_out):
+    """forward == F.interpolate / adaptive_avg_pool2d; transposed tables == their autograd backward."""
+    lib = _lib.load()
+    N, C, W_in, W_out = 2, 8, n_in + 1, n_out + (1 if kind == "bilinear" else 0)
+    if kind == "pool":
+        W_out = max(1, n_out - 1)
+    x = gen(N, C, n_in, W_in, seed=1).requires_grad_(True)
+    y_ref = (F.interpolate(x, (n_out, W_out), mode="bilinear", align_corners=False) if kind == "bilinear"
+             else F.adaptive_avg_pool2d(x, (n_out, W_out)))
+    dy = gen(*y_ref.shape, seed=2)
+    y_ref.backward(dy)
+    mat = bilinear_matrix if kind == "bilinear" else adaptive_pool_matrix
+    my, mx = mat(n_in, n_out), mat(W_in, W_out)
+    up = lambda a: [torch.from_numpy(t).cuda() for t in csr(a)]  # noqa: E731
+    (ys, yi, yw), (xs, xi, xw) = up(my), up(mx)
+    xd = nhwc(x.detach())
+    y = torch.empty(N, n_out, W_out, C, device="cuda")
+    check(lib.cabinet_resample_sep(xd.data_ptr(), F32, n_in * W_in * C, W_in * C, C, 1, y.data_ptr(), F32, n_out * W_out * C,
+                                   W_out * C, C, 1, N, n_out, W_out, C, ys.data_ptr(), yi.data_ptr(), yw.data_ptr(),
+                                   xs.data_ptr(), xi.data_ptr(), xw.data_ptr(), 0, stream()), "resample")
+    (ys, yi, yw), (xs, xi, xw) = up(my.T), up(mx.T)
+    # adjoint, fed with an NCHW gradient (as the logit gradients arrive)
+    dyd = dy.cuda().contiguous()
+    dx = torch.empty(N, n_in, W_in, C, device="cuda")
+    check(lib.cabinet_resample_sep(dyd.data_ptr(), F32, C * n_out * W_out, W_out, 1, n_out * W_out, dx.data_ptr(), F32,
+                                   n_in * W_in * C, W_in * C, C, 1, N, n_in, W_in, C, ys.data_ptr(), yi.data_ptr(), yw.data_ptr(),
+                                   xs.data_ptr(), xi.data_ptr(), xw.data_ptr(), 0, stream()), "resample_adj")
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(y), y_ref.detach()) < 1e-6
+    assert rel_l2(nchw(dx), x.grad) < 1e-6
+
+
+@pytest.mark.parametrize("gate,plus,act,bias", [(ACT_HSIGMOID, 0.0, ACT_HSWISH, True), (ACT_HSIGMOID, 0.0, ACT_NONE, True),
+                                                (ACT_SIGMOID, 1.0, ACT_NONE, False), (ACT_HSIGMOID, 0.0, ACT_RELU, True)])
+def test_gate_backward(gate, plus, act, bias):
+    """y = act(v * (s + plus)), s = gate(W2 relu(W1 mean(v) + b1) + b2): SE block / FFM attention backward."""
+    lib = _lib.load()
+    N, C, J, H, W = 3, 24, 8, 6, 5
+    v = gen(N, C, H, W, seed=1).requires_grad_(True)
+    w1, w2 = gen(J, C, seed=2, scale=0.4).requires_grad_(True), gen(C, J, seed=3, scale=0.6).requires_grad_(True)
+    b1 = gen(J, seed=4, scale=0.3).requires_grad_(True) if bias else None
+    b2 = gen(C, seed=5, scale=0.3).requires_grad_(True) if bias else None
+    m = v.mean(dim=(2, 3))
+    h = F.relu(F.linear(m, w1, b1))
+    s = act_ref(F.linear(h, w2, b2), gate)
+    y = act_ref(v * (s + plus).view(N, C, 1, 1), act)
+    dy = gen(*y.shape, seed=6)
+    y.backward(dy)
+    HW = H * W
+    vd, dyd = nhwc(v.detach()), nhwc(dy)
+    sums = (m.detach() * HW).cuda()
+    hd, sd = h.detach().cuda(), s.detach().cuda()
+    ds = torch.empty(N, C, device="cuda")
+    sc = torch.empty(N * int(lib.cabinet_train_scratch_floats(HW, C, 1)), device="cuda")
+    check(lib.cabinet_gate_scale_backward(dyd.data_ptr(), C, vd.data_ptr(), C, F32, sd.data_ptr(), plus, act, ds.data_ptr(), N,
+                                          HW, C, sc.data_ptr(), stream()), "gate_scale_bwd")
+    w1d, w2d = w1.detach().cuda(), w2.detach().cuda()
+    dw1, dw2 = torch.zeros_like(w1d), torch.zeros_like(w2d)
+    db1, db2 = torch.zeros(J, device="cuda"), torch.zeros(C, device="cuda")
+    dm = torch.empty(N, C, device="cuda")
+    sc2 = torch.empty(N * (C + J), device="cuda")
+    check(lib.cabinet_gate_mlp_backward(sums.data_ptr(), 1.0 / HW, w1d.data_ptr(), w2d.data_ptr(), hd.data_ptr(), sd.data_ptr(),
+                                        ds.data_ptr(), gate, N, C, J, dw1.data_ptr(), db1.data_ptr() if bias else None,
+                                        dw2.data_ptr(), db2.data_ptr() if bias else None, dm.data_ptr(), sc2.data_ptr(),
+                                        stream()), "gate_mlp_bwd")
+    dv = torch.empty_like(vd)
+    check(lib.cabinet_gate_apply_backward(dyd.data_ptr(), C, vd.data_ptr(), C, F32, sd.data_ptr(), plus, dm.data_ptr(), 1.0 / HW,
+                                          act, dv.data_ptr(), C, N, HW, C, 0, stream()), "gate_apply_bwd")
+    torch.cuda.synchronize()
+    assert rel_l2(nchw(dv), v.grad) < 1e-5
+    assert rel_l2(dw1.cpu(), w1.grad) < 1e-5 and rel_l2(dw2.cpu(), w2.grad) < 1e-5
+    if bias:
+        assert rel_l2(db1.cpu(), b1.grad) < 1e-5 and rel_l2(db2.cpu(), b2.grad) < 1e-5
+
+
+def test_softmax_and_cab_combine_backward():
+    lib = _lib.load()
+    rows, cols = 37, 50
+    s = gen(rows, cols, seed=1).requires_grad_(True)
+    p = F.softmax(s * 0.3, dim=-1)
+    dp = gen(rows, cols, seed=2)
+    p.backward(dp)
+    pd, dpd = p.detach().cuda(), dp.cuda()
+    ds = torch.empty_like(pd)
+    check(lib.cabinet_softmax_backward(pd.data_ptr(), dpd.data_ptr(), ds.data_ptr(), rows, cols, 0.3, stream()), "softmax_bwd")
+    M, C = 45, 16
+    g, x, r = (gen(M, C, seed=i).requires_grad_(True) for i in (3, 4, 5))
+    gamma = torch.tensor([0.7], requires_grad=True)
+    out = gamma * g + x + x * torch.sigmoid(r)
+    do = gen(M, C, seed=6)
+    out.backward(do)
+    gd, xd, rd, dod = g.detach().cuda(), x.detach().cuda(), r.detach().cuda(), do.cuda()
+    dg, dx, dr = torch.empty_like(gd), torch.empty_like(gd), torch.empty_like(gd)
+    dgamma = torch.zeros(1, device="cuda")
+    gm = gamma.detach().cuda()
+    check(lib.cabinet_cab_combine_backward(dod.data_ptr(), C, gd.data_ptr(), xd.data_ptr(), rd.data_ptr(), gm.data_ptr(), F32,
+                                           dg.data_ptr(), dx.data_ptr(), dr.data_ptr(), dgamma.data_ptr(), M, C, 0,
+                                           scratch(lib, M, C, 1).data_ptr(), stream()), "cab_bwd")
+    torch.cuda.synchronize()
+    assert rel_l2(ds.cpu(), s.grad) < 1e-5
+    assert rel_l2(dg.cpu(), g.grad) < 1e-6 and rel_l2(dx.cpu(), x.grad) < 1e-6 and rel_l2(dr.cpu(), r.grad) < 1e-5
+    assert abs(float(dgamma) - float(gamma.grad)) < 1e-4 * abs(float(gamma.grad)) + 1e-6
+
+
+def _run_step(model, x, labels, thresh, n_min):
+    crit_p, crit_16 = OhemCELoss(thresh, n_min, 255), OhemCELoss(thresh, n_min, 255)
+    model.zero_grad(set_to_none=True)
+    out, out16 = model(x)
+    loss = crit_p(out, labels) + crit_16(out16, labels)
+    loss.backward()
+    return loss.detach(), out, out16
+
+
+@pytest.mark.parametrize("case", TRAIN_CASES, ids=[c[0] for c in TRAIN_CASES])
+def test_train_step_vs_reference_golden(golden_dir, case):
+    """One training step in fp32 mode against the imported reference's outputs (oracle/make_golden_train.py): loss, the
+    gradient norm of EVERY parameter, four full gradients, four updated BN running statistics."""
+    name, mode, C, (N, H, W), thresh, n_min = case
+    g = np.load(golden_dir / f"train_step_{name}.npz")
+    model = build_model(C, mode)
+    assert state_dict_digest(model.state_dict()) == str(g["digest"])
+    model = model.cuda().train()
+    model.train_precision = "fp32"
+    x, lb = make_input(N, H, W).cuda(), make_labels(N, H, W, C).cuda()
+    loss, out, out16 = _run_step(model, x, lb, thresh, n_min)
+    assert out.requires_grad and out.shape == (N, C, H, W)
+    print(f"{name}: loss {float(loss):.6f} (reference {float(g['loss']):.6f})")
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=2e-4)
+    named = dict(model.named_parameters())
+    worst = 0.0
+    for k, want in zip(g["grad_keys"], g["grad_norms"]):
+        p = named[str(k)]
+        if want < 0:
+            assert p.grad is None, k   # mobile.classifier: not on the forward path
+            continue
+        assert p.grad is not None, k
+        got = float(p.grad.norm())
+        rel = abs(got - want) / max(want, 1e-6)
+        worst = max(worst, rel)
+        assert rel < 5e-3 or abs(got - want) < 1e-5, (str(k), got, float(want))
+    print(f"{name}: worst relative gradient-norm error {worst:.2e}")
+    for k in FULL_GRAD_KEYS:
+        e = rel_l2(named[k].grad.cpu(), torch.from_numpy(g["grad__" + k]))
+        print(f"  grad {k}: rel_l2 {e:.2e}")
+        assert e < 2e-3, (k, e)
+    sd = model.state_dict()
+    for k in STAT_KEYS:
+        assert rel_l2(sd[k + ".running_mean"].cpu(), torch.from_numpy(g["mean__" + k])) < 1e-4, k
+        assert rel_l2(sd[k + ".running_var"].cpu(), torch.from_numpy(g["var__" + k])) < 1e-4, k
+        assert int(sd[k + ".num_batches_tracked"]) == 1
+
+
+def test_train_step_all_gradients_vs_oracle_and_determinism():
+    """Every gradient tensor against oracle/train_oracle.py run live (Large, odd size), bit-reproducible across runs,
+    and the bf16-activation mode within its tolerance."""
+    mode, C, N, H, W = "large", 6, 2, 96, 80
+    thresh, n_min = 0.7, N * H * W // 16
+    base = build_model(C, mode)
+    sd = {k: v.clone() for k, v in base.state_dict().items()}
+    x, lb = make_input(N, H, W), make_labels(N, H, W, C)
+    loss_ref, grads_ref, running_ref = train_step(sd, x, lb, BACKBONE_CFGS[mode], thresh, n_min)
+    runs = []
+    for precision in ("fp32", "fp32", "bf16"):
+        model = build_model(C, mode).cuda().train()
+        model.train_precision = precision
+        loss, _, _ = _run_step(model, x.cuda(), lb.cuda(), thresh, n_min)
+        named = dict(model.named_parameters())
+        tol_l, tol_g = (2e-4, 3e-3) if precision == "fp32" else (2e-2, 8e-2)
+        assert float(loss) == pytest.approx(float(loss_ref), rel=tol_l)
+        worst = ("", 0.0)
+        for k, gr in grads_ref.items():
+            if gr is None:
+                assert named[k].grad is None
+                continue
+            e = rel_l2(named[k].grad.cpu(), gr)
+            if e > worst[1]:
+                worst = (k, e)
+            assert e < tol_g or float((named[k].grad.cpu() - gr).abs().max()) < 1e-6, (precision, k, e)
+        print(f"{precision}: loss {float(loss):.6f} vs {float(loss_ref):.6f}; worst gradient {worst[0]} rel_l2 {worst[1]:.2e}")
+        msd = model.state_dict()
+        for prefix, (rm, rv) in running_ref.items():
+            assert rel_l2(msd[prefix + ".running_mean"].cpu(), rm) < (1e-4 if precision == "fp32" else 2e-2), prefix
+            assert rel_l2(msd[prefix + ".running_var"].cpu(), rv) < (1e-4 if precision == "fp32" else 3e-2), prefix
+        runs.append({k: p.grad.clone() for k, p in named.items() if p.grad is not None})
+    assert all(torch.equal(runs[0][k], runs[1][k]) for k in runs[0])   # bit-reproducible
+
+
+def test_train_mode_surface():
+    """no_grad in train mode (val_step, train.py:443-456), eval after train, GradScaler-style scaled backward."""
+    model = build_model(8, "small").cuda()
+    x = make_input(2, 64, 64).cuda()
+    f_eval = model(x)[0].clone()
+    model.train()
+    with torch.no_grad():
+        f_tr, a_tr = model(x)
+    assert not f_tr.requires_grad and torch.isfinite(f_tr).all()
+    out, out16 = model(x)
+    (out.float().mean() * 1024.0 + out16.float().mean()).backward()   # a scaled loss, as torch.amp.GradScaler produces
+    g = model.conv_out.conv_out.weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
+    assert model.mobile.classifier[0].weight.grad is None
+    model.eval()
+    f2 = model(x)[0]
+    assert not torch.equal(f2, f_eval)   # the running statistics moved: the inference pack was rebuilt from them
+    assert torch.isfinite(f2).all()
