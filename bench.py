@@ -198,10 +198,11 @@ def run_reference(args):
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0}))
 
 
-CONFIGS = {  # BASELINE.json configs[1..3]
+CONFIGS = {  # BASELINE.json configs[1..4]
     2: dict(mode="large", height=1024, width=1024, batch=16, classes=8, name="BASELINE configs[1]"),
     3: dict(mode="large", height=1024, width=2048, batch=8, classes=19, name="BASELINE configs[2], Cityscapes shape"),
     4: dict(mode="small", height=2160, width=3840, batch=4, classes=8, name="BASELINE configs[3], UAVid native 4K"),
+    5: dict(mode="large", height=1024, width=1024, batch=8, classes=8, name="BASELINE configs[4], training step fwd+bwd"),
 }
 
 
@@ -617,6 +618,125 @@ def run_ours(args):
     print(json.dumps(line))
 
 
+def run_train(args):
+    """BASELINE configs[4]: Large training step (train-mode forward, 2 x OhemCELoss, backward, bucketed gradient
+    all-reduce over NCCL), batch 8 per GPU.  ``value`` = images/s with inputs resident in HBM; ``e2e`` = the same step
+    fed from pinned host memory (H2D of images + labels, D2H of the loss) every step."""
+    import torch
+    import torch.distributed as dist
+
+    from cabinet_b200.grad_sync import GradBuckets
+    from cabinet_b200.loss import OhemCELoss
+    from cabinet_b200.synthetic import build_model, make_input, make_labels
+
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm, B, C, H, W = args.steps, args.warmup, args.batch, args.classes, args.height, args.width
+    model = build_model(C, args.mode).to(dev).train()
+    model.train_precision = args.train_precision
+    model.logits_dtype = torch.bfloat16 if args.train_precision == "bf16" else torch.float32
+    crit_p, crit_16 = OhemCELoss(0.7, B * H * W // 16, 255), OhemCELoss(0.7, B * H * W // 16, 255)  # configs/train.yaml
+    gb = GradBuckets(model.named_parameters())
+    x_host = make_input(B, H, W, seed=7 + rank).pin_memory()
+    lb_host = make_labels(B, H, W, C, seed=11 + rank).pin_memory()
+    x, lb = x_host.to(dev), lb_host.to(dev)
+    eng = model.train_engine()
+
+    def step(xd, ld):
+        gb.zero_()
+        out, out16 = model(xd)
+        loss = crit_p(out, ld) + crit_16(out16, ld)
+        loss.backward()
+        gb.all_reduce()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    uuid = str(torch.cuda.get_device_properties(local).uuid)
+    gpu_id = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+    for _ in range(Wm):
+        step(x, lb)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    with ClockSampler(gpu_id) as clk:
+        e0.record()
+        for _ in range(K):
+            loss = step(x, lb)
+            launches += eng.launches
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    value = world * B * K / (ms * 1e-3)
+    # end to end: host batch in, loss out, every step
+    barrier()
+    e0.record()
+    for _ in range(K):
+        xd, ld = x_host.to(dev, non_blocking=True), lb_host.to(dev, non_blocking=True)
+        lv = float(step(xd, ld).item())
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    # per-kernel shares of one traced step
+    eng.start_trace()
+    step(x, lb)
+    rows = eng.stop_trace()
+    fam = {}
+    for n, ph, t in rows:
+        f = fam.setdefault((n.replace("cabinet_", ""), ph), [0.0, 0])
+        f[0] += t
+        f[1] += 1
+    table = [{"kernel": k, "phase": ph, "ms_per_step": v[0], "launches_per_step": v[1]}
+             for (k, ph), v in sorted(fam.items(), key=lambda kv: -kv[1][0])]
+    # roofline of the dominant kernel: the convolution gradients (and the forward convolutions of this mode) are
+    # implicit GEMMs; their algorithmic FLOPs are ~3x the forward's (SURVEY 8d config 5)
+    peaks = load_peaks()
+    fwd_flops = 54.31e9 * B if (args.mode, H, W) == ("large", 1024, 1024) else None
+    dom = table[0]
+    conv_ms = sum(r["ms_per_step"] for r in table if r["kernel"] in ("conv_wgrad", "conv_dgrad", "conv2d_simt", "conv_tc"))
+    roof = {"kernel": dom["kernel"], "bound": "tensor", "unit": "TFLOP/s", "peak": peaks["bf16_tflops_sustained"],
+            "peak_source": peaks["source"], "traffic": None,
+            "achieved": (3 * fwd_flops / (conv_ms * 1e-3) / 1e12) if fwd_flops and conv_ms else None,
+            "note": "dense convolution forward + data + weight gradients (3 x 54.31 GFLOP / image) over their summed device time; "
+                    "fp32 mode runs them as CUDA-core implicit GEMMs"}
+    roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    n_grad = sum(b.numel() for b in gb.buckets)
+    print(json.dumps({
+        "metric": "training images/sec at 1024x1024 (MNv3-L), fwd+bwd" if (H, W, args.mode) == (1024, 1024, "large")
+        else f"training images/sec at {H}x{W} (MNv3-{args.mode[0].upper()}), fwd+bwd",
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.train_precision == "bf16" else "f32", "data": "synthetic",
+        "config": dict(workload_config(args), outputs="loss + gradients of 398 parameter tensors",
+                       launch="eager kernel launches through the C-ABI (train engine)",
+                       cache="activations of a step far exceed the 126 MB L2",
+                       loss="2 x OhemCELoss(thresh 0.7, n_min = pixels / 16)", grad_elements=n_grad,
+                       grad_sync=f"{len(gb.buckets)} flat fp32 buckets, one async NCCL all-reduce each"),
+        "e2e": {"value": world * B * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
+                "h2d_bytes_per_step": x_host.numel() * 4 + lb_host.numel() * 8, "d2h_bytes_per_step": 4,
+                "api": "model.train()(x) -> OhemCELoss x 2 -> loss.backward() -> GradBuckets.all_reduce()", "loss": lv},
+        "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "kernels": table[:14],
+        "traced_ms_per_step": sum(t for _, _, t in rows)}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -633,6 +753,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=0, help="--impl reference: images per step (default: --batch)")
     ap.add_argument("--cpu-iters", type=int, default=None, help="timed forwards of the cpu_baseline leg")
     ap.add_argument("--no-gpu-eager", action="store_true")
+    ap.add_argument("--train-precision", default="fp32", choices=["fp32", "bf16"], help="--config 5: activation dtype")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
@@ -653,6 +774,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == 5:
+        run_train(args)
     else:
         run_ours(args)
 

@@ -127,7 +127,7 @@ class TrainEngine:
         self.tape: List = []
         self.pgrads: Dict[int, torch.Tensor] = {}
         self.launches = 0
-        self._keep: List[torch.Tensor] = []
+        self.trace, self.phase = None, "fwd"
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -135,8 +135,27 @@ class TrainEngine:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def _call(self, name: str, *args):
-        check(getattr(self.lib, name)(*args, self.stream), name)
+        tr = self.trace
+        if tr is not None:  # bench / profiling: bracket the call with CUDA events on the launching stream
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = getattr(self.lib, name)(*args, self.stream)
+            e1.record()
+            tr.append((name, self.phase, e0, e1))
+        else:
+            rc = getattr(self.lib, name)(*args, self.stream)
+        check(rc, name)
         self.launches += 1
+
+    def start_trace(self):
+        self.trace = []
+
+    def stop_trace(self):
+        """-> [(kernel entry point, 'fwd' | 'bwd', ms)]; synchronises."""
+        torch.cuda.synchronize(self.dev)
+        rows = [(n, ph, e0.elapsed_time(e1)) for n, ph, e0, e1 in self.trace]
+        self.trace = None
+        return rows
 
     def new(self, N, H, W, C, dtype=None) -> Map:
         return Map(torch.empty((N, H, W, C), dtype=dtype or self.tdt, device=self.dev), N, H, W, C, C)
@@ -441,7 +460,7 @@ class TrainEngine:
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
         N, _, H, W = x.shape
-        self.tape, self.launches, self.pgrads = [], 0, {}
+        self.tape, self.launches, self.pgrads, self.phase = [], 0, {}, "fwd"
         mob, sb, ab, ffm, head = m.mobile, m.sb, m.ab, m.ffm, m.conv_out
         ga, cab = ab.a2block.global_attn, ab.a2block
 
@@ -512,7 +531,7 @@ class TrainEngine:
     def backward(self, d_final: Optional[torch.Tensor], d_aux: Optional[torch.Tensor]) -> Dict[int, torch.Tensor]:
         """Gradients of the two logit tensors -> {id(parameter): fp32 gradient}."""
         g = _Grads(self)
-        self.pgrads = {}
+        self.pgrads, self.phase = {}, "bwd"
         for dy, bwd in ((d_final, self._out_bwd[0]), (d_aux, self._out_bwd[1])):
             if dy is not None:
                 bwd(g, dy)
