@@ -249,26 +249,29 @@ col_sum_kernel(const T* __restrict__ x, long long ldx, long long M, int C, long 
 // Weight packing: PyTorch OIHW fp32 -> [cout_pad][KH*KW][cin_pad] (ci fastest, zero padded) in fp32 or bf16: the layout
 // cabinet_conv2d_simt / cabinet_conv_tc consume and the data-gradient kernel reads.  transposed_1 = depthwise
 // ([C][1][k][k] -> [k*k][C]).
+// transpose_flip: the weights of the data-gradient convolution (rows = input channels, taps mirrored, K = output channels)
 template <typename TO>
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int cout_pad,
-                                        int cin_pad, TO* __restrict__ out) {
-    const long long total = static_cast<long long>(cout_pad) * taps * cin_pad;
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int rows_pad,
+                                        int k_pad, int transpose_flip, TO* __restrict__ out) {
+    const long long total = static_cast<long long>(rows_pad) * taps * k_pad;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int ci = static_cast<int>(i % cin_pad);
-        const long long t = i / cin_pad;
-        const int tap = static_cast<int>(t % taps), co = static_cast<int>(t / taps);
+        const int kk = static_cast<int>(i % k_pad);
+        const long long t = i / k_pad;
+        const int tap = static_cast<int>(t % taps), r = static_cast<int>(t / taps);
+        const int co = transpose_flip ? kk : r, ci = transpose_flip ? r : kk;
+        const int src_tap = transpose_flip ? taps - 1 - tap : tap;
         float v = 0.f;
-        if (co < Cout && ci < Cin) v = w[(static_cast<long long>(co) * Cin + ci) * taps + tap];
+        if (co < Cout && ci < Cin) v = w[(static_cast<long long>(co) * Cin + ci) * taps + src_tap];
         out[i] = from_f32<TO>(v);
     }
 }
 
-__global__ void pack_dw_weight_kernel(const float* __restrict__ w, int C, int taps, float* __restrict__ out) {
+__global__ void pack_dw_weight_kernel(const float* __restrict__ w, int C, int taps, int flip, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C * taps) return;
     const int c = i % C, t = i / C;
-    out[i] = w[c * taps + t];
+    out[i] = w[c * taps + (flip ? taps - 1 - t : t)];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -720,25 +723,26 @@ inline unsigned ew_grid(long long total) { return static_cast<unsigned>(std::min
     } while (0)
 
 extern "C" int cabinet_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int KW, void* out, int out_dtype,
-                                        int cout_pad, int cin_pad, cabinet_stream_t stream) {
-    CAB_REQUIRE(w_oihw && out && Cout > 0 && Cin > 0 && KH > 0 && KW > 0 && cout_pad >= Cout && cin_pad >= Cin,
+                                        int rows_pad, int k_pad, int transpose_flip, cabinet_stream_t stream) {
+    CAB_REQUIRE(w_oihw && out && Cout > 0 && Cin > 0 && KH > 0 && KW > 0 && rows_pad >= (transpose_flip ? Cin : Cout) &&
+                    k_pad >= (transpose_flip ? Cout : Cin),
                 "pack_conv_weight: bad arguments");
-    const long long total = static_cast<long long>(cout_pad) * KH * KW * cin_pad;
+    const long long total = static_cast<long long>(rows_pad) * KH * KW * k_pad;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (out_dtype == CABINET_F32)
-        pack_conv_weight_kernel<float><<<ew_grid(total), 256, 0, s>>>(w_oihw, Cout, Cin, KH * KW, cout_pad, cin_pad,
+        pack_conv_weight_kernel<float><<<ew_grid(total), 256, 0, s>>>(w_oihw, Cout, Cin, KH * KW, rows_pad, k_pad, transpose_flip,
                                                                        reinterpret_cast<float*>(out));
     else
-        pack_conv_weight_kernel<bf16><<<ew_grid(total), 256, 0, s>>>(w_oihw, Cout, Cin, KH * KW, cout_pad, cin_pad,
+        pack_conv_weight_kernel<bf16><<<ew_grid(total), 256, 0, s>>>(w_oihw, Cout, Cin, KH * KW, rows_pad, k_pad, transpose_flip,
                                                                       reinterpret_cast<bf16*>(out));
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }
 
-extern "C" int cabinet_pack_dw_weight(const float* w, int C, int k, float* out, cabinet_stream_t stream) {
+extern "C" int cabinet_pack_dw_weight(const float* w, int C, int k, int flip, float* out, cabinet_stream_t stream) {
     CAB_REQUIRE(w && out && C > 0 && k > 0, "pack_dw_weight: bad arguments");
     pack_dw_weight_kernel<<<static_cast<unsigned>(cab_ceil_div(C * k * k, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        w, C, k * k, out);
+        w, C, k * k, flip, out);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

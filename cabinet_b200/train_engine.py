@@ -128,6 +128,8 @@ class TrainEngine:
         self.pgrads: Dict[int, torch.Tensor] = {}
         self.launches = 0
         self.trace, self.phase = None, "fwd"
+        self.use_tc = precision == "bf16"   # tcgen05 / TMA kernels for the GEMM-shaped and depthwise layers
+        self._zero_cache: Dict[int, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -176,11 +178,24 @@ class TrainEngine:
         return BF16 if t.dtype == torch.bfloat16 else F32
 
     # ------------------------------------------------------------------ ops (forward + tape entry)
+    def _zeros(self, n: int) -> torch.Tensor:
+        z = self._zero_cache.get(n)
+        if z is None:
+            z = self._zero_cache[n] = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        return z
+
+    @staticmethod
+    def _tc_ok(m: Map) -> bool:
+        return m.dt == BF16 and m.ld % 8 == 0 and m.off % 8 == 0 and m.t.data_ptr() % 16 == 0
+
     def conv(self, x: Optional[Map], conv, out: Optional[Map] = None, out_dtype=None, nchw: Optional[torch.Tensor] = None,
              need_dx: bool = True) -> Map:
-        """nn.Conv2d (bias optional) on an NHWC map or the fp32 NCHW network input."""
+        """nn.Conv2d (bias optional) on an NHWC map or the fp32 NCHW network input.  bf16 mode: forward and the stride-1
+        data gradient run on the tensor cores (cabinet_conv_tc; the data gradient of a stride-1 convolution is the
+        convolution of dy with the transposed, mirrored weights); fp32 mode and the remaining cases: CUDA-core kernels."""
         w, b = conv.weight, conv.bias
         cout, cin, kh, kw = w.shape
+        taps = kh * kw
         stride, pad = conv.stride[0], conv.padding[0]
         if nchw is not None:
             N, _, H, W = nchw.shape
@@ -192,12 +207,24 @@ class TrainEngine:
         OH, OW = _out_size(H, kh, stride, pad), _out_size(W, kw, stride, pad)
         if out is None:
             out = self.new(N, OH, OW, cout, out_dtype)
-        wp = torch.empty((cout, kh * kw, cin), dtype=torch.float32, device=self.dev)
-        self._call("cabinet_pack_conv_weight", w.data_ptr(), cout, cin, kh, kw, wp.data_ptr(), F32, cout, cin)
-        bias = b.detach().float().contiguous() if b is not None else None
-        self._call("cabinet_conv2d_simt", xptr, xdt, *strides, 0, wp.data_ptr(), F32, kh * kw * cin, 1, 0,
-                   bias.data_ptr() if bias is not None else None, None, 0, out.ptr, out.dt, out.ld, 0, 1, N, H, W, cin, cout,
-                   kh, kw, stride, pad, OH, OW, ACT_NONE, 1.0)
+        bias = b.detach() if b is not None else None
+        tc = (self.use_tc and nchw is None and self._tc_ok(x) and stride in (1, 2) and (stride == 1 or (H >= 2 and W >= 2))
+              and (out.dt == F32 or self._tc_ok(out)))
+        if tc:
+            r16, k64 = -(-cout // 16) * 16, -(-cin // 64) * 64
+            wp = torch.empty((r16, taps, k64), dtype=torch.bfloat16, device=self.dev)
+            self._call("cabinet_pack_conv_weight", w.data_ptr(), cout, cin, kh, kw, wp.data_ptr(), BF16, r16, k64, 0)
+            self._call("cabinet_conv_tc", x.ptr, x.ld, N, H, W, cin, wp.data_ptr(), cout, kh, kw, stride, pad,
+                       (bias if bias is not None else self._zeros(cout)).data_ptr(), None, 0, out.ptr, out.dt, out.ld, OH, OW,
+                       ACT_NONE)
+            wdt, w_sco, w_stap = BF16, taps * k64, k64
+        else:
+            wp = torch.empty((cout, taps, cin), dtype=torch.float32, device=self.dev)
+            self._call("cabinet_pack_conv_weight", w.data_ptr(), cout, cin, kh, kw, wp.data_ptr(), F32, cout, cin, 0)
+            self._call("cabinet_conv2d_simt", xptr, xdt, *strides, 0, wp.data_ptr(), F32, taps * cin, 1, 0,
+                       bias.data_ptr() if bias is not None else None, None, 0, out.ptr, out.dt, out.ld, 0, 1, N, H, W, cin,
+                       cout, kh, kw, stride, pad, OH, OW, ACT_NONE, 1.0)
+            wdt, w_sco, w_stap = F32, taps * cin, cin
 
         def backward(g: _Grads):
             dy = g.get(out)
@@ -211,32 +238,46 @@ class TrainEngine:
             sc = torch.empty(n, dtype=torch.float32, device=self.dev)
             self._call("cabinet_conv_wgrad", dy.ptr, dy.ld, dy.dt, xptr, xdt, *strides, self.pgrad(w).data_ptr(), N, H, W,
                        cin, cout, kh, kw, stride, pad, OH, OW, sc.data_ptr())
-            if nchw is None and need_dx:
-                if dy.dt != x.dt:  # fp32 class-logit gradients into a bf16 activation gradient
-                    dyc = self.new(N, OH, OW, cout, x.t.dtype)
-                    self._call("cabinet_affine_act", dy.ptr, dy.ld, dy.dt, None, None, None, 0.0, None, 0, dyc.ptr, dyc.ld,
-                               dyc.dt, N * OH * OW, OH * OW, cout, ACT_NONE)
-                    dy = dyc
-                dx, acc = g.out(x)
-                self._call("cabinet_conv_dgrad", dy.ptr, dy.ld, dy.dt, wp.data_ptr(), F32, kh * kw * cin, cin, dx.ptr, dx.ld,
-                           N, H, W, cin, cout, kh, kw, stride, pad, OH, OW, acc)
+            if nchw is not None or not need_dx:
+                return
+            if dy.dt != x.dt:  # fp32 class-logit gradients into a bf16 activation gradient (pixel stride padded to 8)
+                dyc = Map(torch.empty((N, OH, OW, -(-cout // 8) * 8), dtype=x.t.dtype, device=self.dev), N, OH, OW, cout,
+                          -(-cout // 8) * 8)
+                self._call("cabinet_affine_act", dy.ptr, dy.ld, dy.dt, None, None, None, 0.0, None, 0, dyc.ptr, dyc.ld,
+                           dyc.dt, N * OH * OW, OH * OW, cout, ACT_NONE)
+                dy = dyc
+            dx, acc = g.out(x)
+            if self.use_tc and stride == 1 and self._tc_ok(dy) and self._tc_ok(dx) and (OH, OW) == (H, W):
+                r16, k64 = -(-cin // 16) * 16, -(-cout // 64) * 64
+                wt = torch.empty((r16, taps, k64), dtype=torch.bfloat16, device=self.dev)
+                self._call("cabinet_pack_conv_weight", w.data_ptr(), cout, cin, kh, kw, wt.data_ptr(), BF16, r16, k64, 1)
+                self._call("cabinet_conv_tc", dy.ptr, dy.ld, N, H, W, cout, wt.data_ptr(), cin, kh, kw, 1, kh - 1 - pad,
+                           self._zeros(cin).data_ptr(), dx.ptr if acc else None, dx.ld if acc else 0, dx.ptr, dx.dt, dx.ld,
+                           H, W, ACT_NONE)
+                return
+            self._call("cabinet_conv_dgrad", dy.ptr, dy.ld, dy.dt, wp.data_ptr(), wdt, w_sco, w_stap, dx.ptr, dx.ld, N, H, W,
+                       cin, cout, kh, kw, stride, pad, OH, OW, acc)
 
         self.tape.append(backward)
         return out
 
     def dwconv(self, x: Map, conv) -> Map:
-        """Depthwise nn.Conv2d (groups = C, no bias)."""
+        """Depthwise nn.Conv2d (groups = C, no bias).  bf16 mode: the TMA-staged kernel forward, and for stride 1 also
+        backward (the data gradient is the depthwise convolution of dy with the mirrored filter)."""
         w = conv.weight
         C, k, stride = w.shape[0], w.shape[2], conv.stride[0]
         p = (k - 1) // 2
         OH, OW = _out_size(x.H, k, stride, p), _out_size(x.W, k, stride, p)
         out = self.new(x.N, OH, OW, C)
         wp = torch.empty((k * k, C), dtype=torch.float32, device=self.dev)
-        zero = torch.zeros(C, dtype=torch.float32, device=self.dev)
-        self.launches += 1
-        self._call("cabinet_pack_dw_weight", w.data_ptr(), C, k, wp.data_ptr())
-        self._call("cabinet_dwconv", x.ptr, x.ld, wp.data_ptr(), zero.data_ptr(), out.ptr, out.ld, x.dt, x.N, x.H, x.W, C, k,
-                   stride, OH, OW, ACT_NONE, None)
+        self._call("cabinet_pack_dw_weight", w.data_ptr(), C, k, 0, wp.data_ptr())
+        tma = self.use_tc and self._tc_ok(x) and self._tc_ok(out) and C % 8 == 0
+        if tma:
+            self._call("cabinet_dwconv_tma", x.ptr, x.ld, wp.data_ptr(), self._zeros(C).data_ptr(), out.ptr, out.ld, x.N, x.H,
+                       x.W, C, k, stride, OH, OW, ACT_NONE, None)
+        else:
+            self._call("cabinet_dwconv", x.ptr, x.ld, wp.data_ptr(), self._zeros(C).data_ptr(), out.ptr, out.ld, x.dt, x.N, x.H,
+                       x.W, C, k, stride, OH, OW, ACT_NONE, None)
 
         def backward(g: _Grads):
             dy = g.get(out)
@@ -246,6 +287,15 @@ class TrainEngine:
             self._call("cabinet_dwconv_wgrad", dy.ptr, dy.ld, x.ptr, x.ld, x.dt, self.pgrad(w).data_ptr(), x.N, x.H, x.W, C, k,
                        stride, OH, OW, sc.data_ptr())
             dx, acc = g.out(x)
+            if tma and stride == 1 and self._tc_ok(dy):
+                wf = torch.empty((k * k, C), dtype=torch.float32, device=self.dev)
+                self._call("cabinet_pack_dw_weight", w.data_ptr(), C, k, 1, wf.data_ptr())
+                tgt = self.new(x.N, x.H, x.W, C) if acc else dx
+                self._call("cabinet_dwconv_tma", dy.ptr, dy.ld, wf.data_ptr(), self._zeros(C).data_ptr(), tgt.ptr, tgt.ld, x.N,
+                           x.H, x.W, C, k, 1, x.H, x.W, ACT_NONE, None)
+                if acc:
+                    self._call("cabinet_add", dx.ptr, dx.ld, tgt.ptr, tgt.ld, dx.ptr, dx.ld, dx.dt, x.N * x.H * x.W, C)
+                return
             self._call("cabinet_dwconv_dgrad", dy.ptr, dy.ld, dy.dt, wp.data_ptr(), dx.ptr, dx.ld, x.N, x.H, x.W, C, k, stride,
                        OH, OW, acc)
 

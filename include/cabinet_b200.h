@@ -319,12 +319,16 @@ int cabinet_ohem_ce_backward(const void* logits, int dtype, const void* labels, 
  */
 long long cabinet_train_scratch_floats(long long M, int C, int nq);
 
-/* PyTorch OIHW fp32 weight -> [cout_pad][KH*KW][cin_pad] (ci fastest, zero padded), fp32 or bf16: the layout of
- * cabinet_conv2d_simt (w_sco = KH*KW*cin_pad, w_sk = 1), cabinet_conv_tc (cout_pad = ceil16, cin_pad = ceil64, bf16)
- * and cabinet_conv_dgrad.  Depthwise [C][1][k][k] -> [k*k][C] fp32 (cabinet_dwconv / cabinet_dwconv_dgrad). */
+/* PyTorch OIHW fp32 weight -> [rows_pad][KH*KW][k_pad] (k fastest, zero padded), fp32 or bf16.
+ *   transpose_flip = 0: rows = output channels, k = input channels: the layout of cabinet_conv2d_simt (w_sco =
+ *     KH*KW*k_pad, w_sk = 1), cabinet_conv_tc (rows_pad = ceil16(Cout), k_pad = ceil64(Cin), bf16), cabinet_conv_dgrad;
+ *   transpose_flip = 1: rows = input channels, taps mirrored, k = output channels: the weights with which the data
+ *     gradient of a stride-1 convolution is itself a cabinet_conv_tc call (pad' = K - 1 - pad).
+ * Depthwise [C][1][k][k] -> [k*k][C] fp32 (cabinet_dwconv / cabinet_dwconv_tma / cabinet_dwconv_dgrad); flip = 1 mirrors
+ * the taps (stride-1 data gradient = the depthwise convolution of dy with the mirrored filter). */
 int cabinet_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int KW, void* out, int out_dtype,
-                             int cout_pad, int cin_pad, cabinet_stream_t stream);
-int cabinet_pack_dw_weight(const float* w, int C, int k, float* out, cabinet_stream_t stream);
+                             int rows_pad, int k_pad, int transpose_flip, cabinet_stream_t stream);
+int cabinet_pack_dw_weight(const float* w, int C, int k, int flip, float* out, cabinet_stream_t stream);
 
 /* Train-mode BatchNorm2d statistics (nn.BatchNorm2d in .train(): src/models/cabinet.py:30-31, mobilenetv3.py:88-98,
  * cab.py:26-27) of x [M][C] (M = N*H*W): stats[4][C] = batch mean, 1/sqrt(biased var + eps), scale = gamma * invstd,

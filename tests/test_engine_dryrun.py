@@ -253,9 +253,13 @@ def test_train_engine_schedule_and_abi(monkeypatch, mode, C, shape, precision):
     grads = eng.backward(torch.zeros_like(final), torch.zeros_like(aux))
     bwd = [c[0] for c in rec.calls[n_fwd:]]
     assert bwd.count("cabinet_bn_train_backward") == n_bn
-    n_conv = names.count("cabinet_conv2d_simt") - 2   # minus the two attention GEMMs
+    n_conv = names.count("cabinet_conv2d_simt") + names.count("cabinet_conv_tc") - 2   # minus the two attention GEMMs
     assert bwd.count("cabinet_conv_wgrad") == n_conv
-    assert bwd.count("cabinet_conv_dgrad") == n_conv - 2   # the two stems read the network input: no data gradient
+    # the two stems read the network input: no data gradient; bf16 mode: stride-1 data gradients are conv_tc calls
+    assert bwd.count("cabinet_conv_dgrad") + bwd.count("cabinet_conv_tc") == n_conv - 2
+    if precision == "bf16":
+        assert names.count("cabinet_conv_tc") >= n_conv - 4 and bwd.count("cabinet_conv_tc") >= n_conv - 6
+        assert names.count("cabinet_dwconv_tma") > 0 and bwd.count("cabinet_dwconv_tma") > 0
     trained = {id(p): n for n, p in model.named_parameters() if not n.startswith("mobile.classifier")}
     assert set(grads) == set(trained), [trained[i] for i in set(trained) - set(grads)]
     assert all(grads[id(p)].shape == p.shape for p in model.parameters() if id(p) in grads)

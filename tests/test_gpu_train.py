@@ -110,7 +110,7 @@ def test_conv_gradients(N, cin, cout, k, s, p, H, W, nchw_in, dtype):
     OH, OW = y.shape[2:]
     wd = w.detach().cuda()
     wp = torch.empty(cout, k * k, cin, device="cuda")
-    check(lib.cabinet_pack_conv_weight(wd.data_ptr(), cout, cin, k, k, wp.data_ptr(), F32, cout, cin, stream()), "pack")
+    check(lib.cabinet_pack_conv_weight(wd.data_ptr(), cout, cin, k, k, wp.data_ptr(), F32, cout, cin, 0, stream()), "pack")
     assert torch.equal(wp.cpu(), w.detach().permute(0, 2, 3, 1).reshape(cout, k * k, cin))
     dyd = nhwc(dy, dtype)
     if nchw_in:
@@ -150,7 +150,7 @@ def test_dwconv_gradients(N, C, k, s, H, W, dtype):
     OH, OW = y.shape[2:]
     wd = w.detach().cuda()
     wp = torch.empty(k * k, C, device="cuda")
-    check(lib.cabinet_pack_dw_weight(wd.data_ptr(), C, k, wp.data_ptr(), stream()), "pack_dw")
+    check(lib.cabinet_pack_dw_weight(wd.data_ptr(), C, k, 0, wp.data_ptr(), stream()), "pack_dw")
     xd, dyd = nhwc(x.detach(), dtype), nhwc(dy, dtype)
     dw = torch.zeros(C, 1, k, k, device="cuda")
     check(lib.cabinet_dwconv_wgrad(dyd.data_ptr(), C, xd.data_ptr(), C, dt, dw.data_ptr(), N, H, W, C, k, s, OH, OW,
@@ -341,14 +341,18 @@ def test_train_step_all_gradients_vs_oracle_and_determinism():
         tol_l, tol_g = (2e-4, 1e-2) if precision == "fp32" else (2e-2, 0.8)
         assert float(loss) == pytest.approx(float(loss_ref), rel=tol_l)
         worst = ("", 0.0)
+        # gradients that are analytically ~0 (the bias of a BN whose output only feeds another BN: its shift is removed
+        # again) are compared on an absolute scale: a small fraction of the typical gradient norm of the network
+        typical = float(torch.tensor([float(gr.norm()) for gr in grads_ref.values() if gr is not None]).median())
         for k, gr in grads_ref.items():
             if gr is None:
                 assert named[k].grad is None
                 continue
             e = rel_l2(named[k].grad.cpu(), gr)
-            if e > worst[1]:
+            small = float((named[k].grad.cpu() - gr).norm()) < (1e-5 if precision == "fp32" else 2e-3) * typical
+            if e > worst[1] and not small:
                 worst = (k, e)
-            assert e < tol_g or float((named[k].grad.cpu() - gr).abs().max()) < 1e-6, (precision, k, e)
+            assert e < tol_g or small, (precision, k, e, float(gr.norm()), typical)
         print(f"{precision}: loss {float(loss):.6f} vs {float(loss_ref):.6f}; worst gradient {worst[0]} rel_l2 {worst[1]:.2e}")
         if precision == "bf16":  # the layer next to the loss is only one bf16 rounding away from the fp32 result
             assert rel_l2(named["conv_out.conv_out.weight"].grad.cpu(), grads_ref["conv_out.conv_out.weight"]) < 0.08
