@@ -8,6 +8,8 @@
 //     resize / adaptive average pool as ONE separable sparse resampling kernel, small helpers.
 // All reductions have a fixed summation order (no floating-point atomics): a training step is bit-reproducible.
 // Activations are NHWC (fp32 or bf16), statistics / gradients of parameters fp32.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -65,6 +67,56 @@ __device__ __forceinline__ void col_reduce_block(long long M, int C, long long r
         }
     }
 }
+
+// 16-byte vector accessors (8 bf16 / 4 fp32 per access)
+template <typename T> __device__ __forceinline__ void ldv(const T* p, float* f) {
+    Vec16<T> v;
+    v.load(p);
+    v.unpack(f);
+}
+template <typename T> __device__ __forceinline__ void stv(T* p, const float* f) {
+    Vec16<T> v;
+    v.pack(f);
+    v.store(p);
+}
+template <typename T> __host__ __device__ constexpr int vec_n() { return sizeof(T) == 4 ? 4 : 8; }
+
+// Vectorised form of col_reduce_block: a thread owns one 16-byte channel vector (V channels) of a pixel lane.
+// f(m, c0, acc[NQ * V]) accumulates quantity q of channel c0 + v into acc[q * V + v].  C % V == 0.
+template <int NQ, int V, typename F>
+__device__ __forceinline__ void col_reduce_block_v(long long M, int C, long long rows_per_block, float* __restrict__ partial,
+                                                   F f) {
+    extern __shared__ float s_red[];  // [lanes][NQ][cw]
+    const long long m0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+    const long long m1 = min(m0 + rows_per_block, M);
+    const int CV = C / V;
+    for (int v0 = 0; v0 < CV; v0 += RED_THREADS) {
+        const int cwv = min(RED_THREADS, CV - v0), cw = cwv * V;
+        const int lanes = RED_THREADS / cwv;
+        const int cv = threadIdx.x % cwv, lane = threadIdx.x / cwv;
+        float acc[NQ * V];
+#pragma unroll
+        for (int q = 0; q < NQ * V; ++q) acc[q] = 0.f;
+        if (lane < lanes)
+            for (long long m = m0 + lane; m < m1; m += lanes) f(m, (v0 + cv) * V, acc);
+        __syncthreads();
+        if (lane < lanes)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                for (int v = 0; v < V; ++v) s_red[(lane * NQ + q) * cw + cv * V + v] = acc[q * V + v];
+        __syncthreads();
+        for (int c = threadIdx.x; c < cw; c += RED_THREADS) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                float sum = 0.f;
+                for (int l = 0; l < lanes; ++l) sum += s_red[(l * NQ + q) * cw + c];
+                partial[(static_cast<long long>(blockIdx.x) * NQ + q) * C + v0 * V + c] = sum;
+            }
+        }
+    }
+}
+template <typename T> constexpr size_t red_smem_v(int nq) { return static_cast<size_t>(RED_THREADS) * vec_n<T>() * nq * sizeof(float); }
 
 inline int red_blocks(long long M, long long* rows_per_block) {
     long long nb = std::min<long long>(1024, std::max<long long>(1, M / 64));
@@ -146,6 +198,120 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, long long lddy, const T* __restri
         acc[0] += g;
         acc[1] = fmaf(g, (zv - stats[c]) * stats[C + c], acc[1]);
     });
+}
+
+// ---- 16-byte vectorised variants (C and every pixel stride a multiple of the vector width, 16-byte aligned bases)
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS)
+bn_stats_v_kernel(const T* __restrict__ x, long long ldx, long long M, int C, long long rpb, float* __restrict__ partial) {
+    constexpr int V = vec_n<T>();
+    col_reduce_block_v<2, V>(M, C, rpb, partial, [&](long long m, int c0, float* acc) {
+        float xv[V], kv[V];
+        ldv(x + m * ldx + c0, xv);
+        ldv(x + c0, kv);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const float d = xv[v] - kv[v];
+            acc[v] += d;
+            acc[V + v] = fmaf(d, d, acc[V + v]);
+        }
+    });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS)
+bn_bwd_reduce_v_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ z, long long ldz,
+                       const float* __restrict__ stats, int act, long long M, int C, long long rpb,
+                       float* __restrict__ partial) {
+    constexpr int V = vec_n<T>();
+    col_reduce_block_v<2, V>(M, C, rpb, partial, [&](long long m, int c0, float* acc) {
+        float zv[V], dv[V];
+        ldv(z + m * ldz + c0, zv);
+        ldv(dy + m * lddy + c0, dv);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int c = c0 + v;
+            const float u = fmaf(zv[v], __ldg(stats + 2 * C + c), __ldg(stats + 3 * C + c));
+            const float g = dv[v] * act_grad(u, act);
+            acc[v] += g;
+            acc[V + v] = fmaf(g, (zv[v] - __ldg(stats + c)) * __ldg(stats + C + c), acc[V + v]);
+        }
+    });
+}
+
+// one thread = one channel vector, walking pixels with a fixed stride: the per-channel constants stay in registers
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_v_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ z, long long ldz,
+                      const float* __restrict__ stats, const float* __restrict__ coef, int act, T* __restrict__ dz,
+                      long long lddz, long long M, int C, int accumulate) {
+    constexpr int V = vec_n<T>();
+    const int CV = C / V;
+    const int cv = threadIdx.x % CV, lane = threadIdx.x / CV, lanes = blockDim.x / CV;
+    if (lane >= lanes) return;
+    const int c0 = cv * V;
+    float mean[V], invstd[V], scale[V], shift[V], k1[V], k2[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        mean[v] = stats[c0 + v]; invstd[v] = stats[C + c0 + v]; scale[v] = stats[2 * C + c0 + v]; shift[v] = stats[3 * C + c0 + v];
+        k1[v] = coef[c0 + v]; k2[v] = coef[C + c0 + v];
+    }
+    for (long long m = static_cast<long long>(blockIdx.x) * lanes + lane; m < M; m += static_cast<long long>(gridDim.x) * lanes) {
+        float zv[V], dv[V], o[V];
+        ldv(z + m * ldz + c0, zv);
+        ldv(dy + m * lddy + c0, dv);
+        if (accumulate) ldv(dz + m * lddz + c0, o);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const float g = dv[v] * act_grad(fmaf(zv[v], scale[v], shift[v]), act);
+            const float r = scale[v] * (g - k1[v] - (zv[v] - mean[v]) * invstd[v] * k2[v]);
+            o[v] = accumulate ? o[v] + r : r;
+        }
+        stv(dz + m * lddz + c0, o);
+    }
+}
+
+template <typename TZ, typename TY>
+__global__ void __launch_bounds__(256)
+affine_act_v_kernel(const TZ* __restrict__ z, long long ldz, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ gate, float gate_plus, const TY* __restrict__ res, long long ldres,
+                    TY* __restrict__ y, long long ldy, long long M, long long HW, int C, int act) {
+    constexpr int V = 8;  // 8 channels per thread: one or two 16-byte accesses per tensor
+    const int CV = C / V;
+    const int cv = threadIdx.x % CV, lane = threadIdx.x / CV, lanes = blockDim.x / CV;
+    if (lane >= lanes) return;
+    const int c0 = cv * V;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        sc[v] = scale ? scale[c0 + v] : 1.f;
+        sh[v] = scale ? shift[c0 + v] : 0.f;
+    }
+    auto ld8 = [](auto* p, float* f) {
+        using TT = std::remove_cv_t<std::remove_pointer_t<decltype(p)>>;
+        if constexpr (sizeof(TT) == 2) ldv(p, f);
+        else { ldv(p, f); ldv(p + 4, f + 4); }
+    };
+    for (long long m = static_cast<long long>(blockIdx.x) * lanes + lane; m < M; m += static_cast<long long>(gridDim.x) * lanes) {
+        float u[V], r[V];
+        ld8(z + m * ldz + c0, u);
+        if (res) ld8(res + m * ldres + c0, r);
+        const float* gp = gate ? gate + (m / HW) * C + c0 : nullptr;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            float t = fmaf(u[v], sc[v], sh[v]);
+            if (gp) t *= __ldg(gp + v) + gate_plus;
+            u[v] = t;
+        }
+        cab_act_vec<V>(u, act);
+        if (res) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) u[v] += r[v];
+        }
+        TY* o = y + m * ldy + c0;
+        if constexpr (sizeof(TY) == 2) stv(o, u);
+        else { stv(o, u); stv(o + 4, u + 4); }
+    }
 }
 
 // sums the block partials in order; dgamma / dbeta accumulate into the parameter gradients; coef[2][C] = the two
@@ -712,6 +878,8 @@ __global__ void gate_bwd_phase_kernel(int phase, int N, int C, int J, int gate, 
     }
 }
 
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline unsigned row_grid(long long M, int lanes) { return static_cast<unsigned>(std::max<long long>(1, std::min<long long>(cab_ceil_div(M, lanes), 148LL * 8))); }
 inline unsigned ew_grid(long long total) { return static_cast<unsigned>(std::min<long long>(cab_ceil_div(total, 256), 148LL * 16)); }
 
 }  // namespace
@@ -760,9 +928,16 @@ extern "C" int cabinet_bn_train_stats(const void* x, long long ldx, int dtype, l
     long long rpb;
     const int nb = red_blocks(M, &rpb);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    CAB_DT2(dtype,
-            (bn_stats_kernel<float><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const float*>(x), ldx, M, C, rpb, scratch)),
-            (bn_stats_kernel<bf16><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const bf16*>(x), ldx, M, C, rpb, scratch)));
+    const int V = dtype == CABINET_F32 ? 4 : 8;
+    if (C % V == 0 && ldx % V == 0 && al16(x)) {
+        CAB_DT2(dtype,
+                (bn_stats_v_kernel<float><<<nb, RED_THREADS, red_smem_v<float>(2), s>>>(reinterpret_cast<const float*>(x), ldx, M, C, rpb, scratch)),
+                (bn_stats_v_kernel<bf16><<<nb, RED_THREADS, red_smem_v<bf16>(2), s>>>(reinterpret_cast<const bf16*>(x), ldx, M, C, rpb, scratch)));
+    } else {
+        CAB_DT2(dtype,
+                (bn_stats_kernel<float><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const float*>(x), ldx, M, C, rpb, scratch)),
+                (bn_stats_kernel<bf16><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const bf16*>(x), ldx, M, C, rpb, scratch)));
+    }
     CAB_LAUNCH_CHECK();
     const unsigned g = static_cast<unsigned>(cab_ceil_div(C, 128));
     CAB_DT2(dtype,
@@ -781,6 +956,21 @@ extern "C" int cabinet_affine_act(const void* z, long long ldz, int z_dtype, con
     CAB_REQUIRE(z && y && M >= 0 && C > 0 && HW > 0 && (!scale || shift), "affine_act: bad arguments");
     if (M == 0) return CABINET_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (C % 8 == 0 && C <= 2048 && ldz % 8 == 0 && ldy % 8 == 0 && (!res || ldres % 8 == 0) && al16(z) && al16(y) && al16(res)) {
+        const int lanes = 256 / (C / 8);
+        const unsigned gv = row_grid(M, lanes);
+#define CAB_AAV(TZ, TY)                                                                                                  \
+    affine_act_v_kernel<TZ, TY><<<gv, 256, 0, s>>>(reinterpret_cast<const TZ*>(z), ldz, scale, shift, gate, gate_plus,   \
+                                                   reinterpret_cast<const TY*>(res), ldres, reinterpret_cast<TY*>(y), ldy, \
+                                                   M, HW, C, act)
+        if (z_dtype == CABINET_F32 && y_dtype == CABINET_F32) CAB_AAV(float, float);
+        else if (z_dtype == CABINET_F32) CAB_AAV(float, bf16);
+        else if (y_dtype == CABINET_F32) CAB_AAV(bf16, float);
+        else CAB_AAV(bf16, bf16);
+#undef CAB_AAV
+        CAB_LAUNCH_CHECK();
+        return CABINET_OK;
+    }
     const unsigned g = ew_grid(M * C);
 #define CAB_AA(TZ, TY)                                                                                                \
     affine_act_kernel<TZ, TY><<<g, 256, 0, s>>>(reinterpret_cast<const TZ*>(z), ldz, scale, shift, gate, gate_plus,   \
@@ -804,20 +994,39 @@ extern "C" int cabinet_bn_train_backward(const void* dy, long long lddy, const v
     const int nb = red_blocks(M, &rpb);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     float* coef = scratch + static_cast<long long>(nb) * 2 * C;
-    CAB_DT2(dtype,
-            (bn_bwd_reduce_kernel<float><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const float*>(dy), lddy,
-                                                                         reinterpret_cast<const float*>(z), ldz, stats, act, M, C, rpb, scratch)),
-            (bn_bwd_reduce_kernel<bf16><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const bf16*>(dy), lddy,
-                                                                        reinterpret_cast<const bf16*>(z), ldz, stats, act, M, C, rpb, scratch)));
+    const int V = dtype == CABINET_F32 ? 4 : 8;
+    const bool vec = C % V == 0 && C / V <= 256 && lddy % V == 0 && ldz % V == 0 && lddz % V == 0 && al16(dy) && al16(z) && al16(dz);
+    if (vec) {
+        CAB_DT2(dtype,
+                (bn_bwd_reduce_v_kernel<float><<<nb, RED_THREADS, red_smem_v<float>(2), s>>>(reinterpret_cast<const float*>(dy), lddy,
+                                                                                          reinterpret_cast<const float*>(z), ldz, stats, act, M, C, rpb, scratch)),
+                (bn_bwd_reduce_v_kernel<bf16><<<nb, RED_THREADS, red_smem_v<bf16>(2), s>>>(reinterpret_cast<const bf16*>(dy), lddy,
+                                                                                        reinterpret_cast<const bf16*>(z), ldz, stats, act, M, C, rpb, scratch)));
+    } else {
+        CAB_DT2(dtype,
+                (bn_bwd_reduce_kernel<float><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const float*>(dy), lddy,
+                                                                             reinterpret_cast<const float*>(z), ldz, stats, act, M, C, rpb, scratch)),
+                (bn_bwd_reduce_kernel<bf16><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const bf16*>(dy), lddy,
+                                                                            reinterpret_cast<const bf16*>(z), ldz, stats, act, M, C, rpb, scratch)));
+    }
     CAB_LAUNCH_CHECK();
     bn_bwd_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(C, 128)), 128, 0, s>>>(scratch, nb, M, C, dgamma, dbeta, coef);
     CAB_LAUNCH_CHECK();
-    const unsigned g = ew_grid(M * C);
-    CAB_DT2(dtype,
-            (bn_bwd_apply_kernel<float><<<g, 256, 0, s>>>(reinterpret_cast<const float*>(dy), lddy, reinterpret_cast<const float*>(z), ldz,
-                                                         stats, coef, act, reinterpret_cast<float*>(dz), lddz, M, C, accumulate)),
-            (bn_bwd_apply_kernel<bf16><<<g, 256, 0, s>>>(reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(z), ldz,
-                                                        stats, coef, act, reinterpret_cast<bf16*>(dz), lddz, M, C, accumulate)));
+    if (vec) {
+        const unsigned gv = row_grid(M, 256 / (C / V));
+        CAB_DT2(dtype,
+                (bn_bwd_apply_v_kernel<float><<<gv, 256, 0, s>>>(reinterpret_cast<const float*>(dy), lddy, reinterpret_cast<const float*>(z), ldz,
+                                                                stats, coef, act, reinterpret_cast<float*>(dz), lddz, M, C, accumulate)),
+                (bn_bwd_apply_v_kernel<bf16><<<gv, 256, 0, s>>>(reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(z), ldz,
+                                                               stats, coef, act, reinterpret_cast<bf16*>(dz), lddz, M, C, accumulate)));
+    } else {
+        const unsigned g = ew_grid(M * C);
+        CAB_DT2(dtype,
+                (bn_bwd_apply_kernel<float><<<g, 256, 0, s>>>(reinterpret_cast<const float*>(dy), lddy, reinterpret_cast<const float*>(z), ldz,
+                                                             stats, coef, act, reinterpret_cast<float*>(dz), lddz, M, C, accumulate)),
+                (bn_bwd_apply_kernel<bf16><<<g, 256, 0, s>>>(reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(z), ldz,
+                                                            stats, coef, act, reinterpret_cast<bf16*>(dz), lddz, M, C, accumulate)));
+    }
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

@@ -129,6 +129,7 @@ class TrainEngine:
         self.launches = 0
         self.trace, self.phase = None, "fwd"
         self.use_tc = precision == "bf16"   # tcgen05 / TMA kernels for the GEMM-shaped and depthwise layers
+        self.wgrad_tc = True                # tcgen05 weight gradients (stride-1 "same" convolutions)
         self._zero_cache: Dict[int, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ plumbing
@@ -234,10 +235,17 @@ class TrainEngine:
                 sc = self.scratch(N * OH * OW, cout, 1)
                 self._call("cabinet_col_sum", dy.ptr, dy.ld, dy.dt, N * OH * OW, cout, self.pgrad(b).data_ptr(), 1,
                            sc.data_ptr())
-            n = int(self.lib.cabinet_conv_wgrad_scratch_floats(N, OH, OW, cin, cout, kh, kw))
-            sc = torch.empty(n, dtype=torch.float32, device=self.dev)
-            self._call("cabinet_conv_wgrad", dy.ptr, dy.ld, dy.dt, xptr, xdt, *strides, self.pgrad(w).data_ptr(), N, H, W,
-                       cin, cout, kh, kw, stride, pad, OH, OW, sc.data_ptr())
+            if (self.use_tc and self.wgrad_tc and nchw is None and stride == 1 and kh == kw and 2 * pad == kh - 1
+                    and self._tc_ok(x) and self._tc_ok(dy)):
+                n = int(self.lib.cabinet_conv_wgrad_tc_scratch_floats(N, H, W, cin, cout, kh, kw))
+                sc = torch.empty(n, dtype=torch.float32, device=self.dev)
+                self._call("cabinet_conv_wgrad_tc", dy.ptr, dy.ld, x.ptr, x.ld, self.pgrad(w).data_ptr(), N, H, W, cin, cout,
+                           kh, kw, pad, sc.data_ptr())
+            else:
+                n = int(self.lib.cabinet_conv_wgrad_scratch_floats(N, OH, OW, cin, cout, kh, kw))
+                sc = torch.empty(n, dtype=torch.float32, device=self.dev)
+                self._call("cabinet_conv_wgrad", dy.ptr, dy.ld, dy.dt, xptr, xdt, *strides, self.pgrad(w).data_ptr(), N, H,
+                           W, cin, cout, kh, kw, stride, pad, OH, OW, sc.data_ptr())
             if nchw is not None or not need_dx:
                 return
             if dy.dt != x.dt:  # fp32 class-logit gradients into a bf16 activation gradient (pixel stride padded to 8)

@@ -231,6 +231,7 @@ def test_train_engine_schedule_and_abi(monkeypatch, mode, C, shape, precision):
     rec = RecordingLib()
     rec.cabinet_train_scratch_floats = lambda M, Cc, nq: 16
     rec.cabinet_conv_wgrad_scratch_floats = lambda *a: 16
+    rec.cabinet_conv_wgrad_tc_scratch_floats = lambda *a: 16
     monkeypatch.setattr(_lib, "load", lambda: rec)
     monkeypatch.setattr(te.TrainEngine, "stream", property(lambda self: None))
     model = build_model(C, mode).train()
@@ -254,12 +255,13 @@ def test_train_engine_schedule_and_abi(monkeypatch, mode, C, shape, precision):
     bwd = [c[0] for c in rec.calls[n_fwd:]]
     assert bwd.count("cabinet_bn_train_backward") == n_bn
     n_conv = names.count("cabinet_conv2d_simt") + names.count("cabinet_conv_tc") - 2   # minus the two attention GEMMs
-    assert bwd.count("cabinet_conv_wgrad") == n_conv
+    assert bwd.count("cabinet_conv_wgrad") + bwd.count("cabinet_conv_wgrad_tc") == n_conv
     # the two stems read the network input: no data gradient; bf16 mode: stride-1 data gradients are conv_tc calls
     assert bwd.count("cabinet_conv_dgrad") + bwd.count("cabinet_conv_tc") == n_conv - 2
     if precision == "bf16":
         assert names.count("cabinet_conv_tc") >= n_conv - 4 and bwd.count("cabinet_conv_tc") >= n_conv - 6
         assert names.count("cabinet_dwconv_tma") > 0 and bwd.count("cabinet_dwconv_tma") > 0
+        assert bwd.count("cabinet_conv_wgrad_tc") >= n_conv - 8   # all but the stems, the stride-2 and the class-logit convs
     trained = {id(p): n for n, p in model.named_parameters() if not n.startswith("mobile.classifier")}
     assert set(grads) == set(trained), [trained[i] for i in set(trained) - set(grads)]
     assert all(grads[id(p)].shape == p.shape for p in model.parameters() if id(p) in grads)
