@@ -136,7 +136,6 @@ def test_conv_gradients(N, cin, cout, k, s, p, H, W, nchw_in, dtype):
     assert rel_l2(nchw(dx2) - 3.0, x.grad) < 1e-4 * tm   # accumulate flag
 
 
-@pytest.mark.parametrize("N,C,k,s,H,W", [(2, 16, 3, 1, 9, 7), (1, 72, 5, 2, 11, 13), (2, 240, 3, 2, 8, 8), (1, 960, 5, 1, 4, 4)])
 @pytest.mark.parametrize("N,cin,cout,k,H,W,ldx_extra", [
     (2, 16, 64, 1, 16, 24, 0), (1, 72, 24, 1, 9, 7, 8), (2, 256, 256, 3, 16, 16, 0), (1, 960, 256, 3, 4, 4, 256),
     (2, 384, 256, 1, 12, 20, 0), (3, 64, 160, 1, 33, 17, 0), (1, 1216, 256, 3, 6, 5, 0), (2, 40, 8, 1, 64, 64, 0)])
@@ -165,6 +164,7 @@ def test_conv_wgrad_tensor_core(N, cin, cout, k, H, W, ldx_extra):
     assert e < 1e-5   # exact products of bf16 values, fp32 accumulation
 
 
+@pytest.mark.parametrize("N,C,k,s,H,W", [(2, 16, 3, 1, 9, 7), (1, 72, 5, 2, 11, 13), (2, 240, 3, 2, 8, 8), (1, 960, 5, 1, 4, 4)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_dwconv_gradients(N, C, k, s, H, W, dtype):
     lib = _lib.load()
