@@ -450,11 +450,29 @@ struct DgradArgs {
     const void* w; long long w_sco, w_stap;  // element strides of the packed weights ([co][tap][ci], ci contiguous)
     void* dx; long long lddx;
     int N, H, W, Cin, Cout, KH, KW, stride, pad, OH, OW, accumulate;
-    long long M;  // N*H*W
+    long long M;  // N*H*W (stride 1) or the pixels of the largest parity class (stride 2)
     int K;        // KH*KW*Cout
 };
 
-template <typename T, typename TW>
+// Stride 2: the input pixels split into four parity classes (iy & 1, ix & 1) = blockIdx.z; a pixel of class (py, px) only
+// meets the taps with ky = (py + pad) mod 2 (+2, +4, ...), kx likewise -- a quarter of the (pixel, tap) pairs.  Each class
+// is its own dense GEMM over its valid taps (no multiplications by structural zeros).
+struct ParityTaps {
+    int ky0, nky, kx0, nkx, hc, wc;  // first valid ky / kx, their counts, pixel grid of the class
+};
+__device__ __forceinline__ ParityTaps parity_taps(const DgradArgs& a, int cls) {
+    ParityTaps t;
+    const int py = cls >> 1, px = cls & 1;
+    t.ky0 = (py + a.pad) & 1;
+    t.kx0 = (px + a.pad) & 1;
+    t.nky = (a.KH - t.ky0 + 1) / 2;
+    t.nkx = (a.KW - t.kx0 + 1) / 2;
+    t.hc = (a.H - py + 1) / 2;
+    t.wc = (a.W - px + 1) / 2;
+    return t;
+}
+
+template <typename T, typename TW, bool S2>
 __global__ void __launch_bounds__(256) conv_dgrad_kernel(DgradArgs a) {
     __shared__ __align__(16) float As[GBK][GBM];
     __shared__ __align__(16) float Bs[GBK][GBN + 4];
@@ -464,13 +482,28 @@ __global__ void __launch_bounds__(256) conv_dgrad_kernel(DgradArgs a) {
     const int n0 = blockIdx.y * GBN;
     const T* __restrict__ dy = reinterpret_cast<const T*>(a.dy);
     const TW* __restrict__ w = reinterpret_cast<const TW*>(a.w);
+    ParityTaps pt;
+    int py = 0, px = 0, nkx = a.KW, Kc = a.K;
+    long long Mc = a.M;
+    if (S2) {
+        pt = parity_taps(a, blockIdx.z);
+        py = blockIdx.z >> 1; px = blockIdx.z & 1;
+        nkx = pt.nkx;
+        Kc = pt.nky * pt.nkx * a.Cout;
+        Mc = static_cast<long long>(a.N) * pt.hc * pt.wc;
+        if (m0 >= Mc || Kc == 0) {
+            if (Kc != 0 || m0 >= Mc || a.accumulate) return;  // (no valid tap: the class gets zeros unless it accumulates)
+        }
+    }
     if (tid < GBM) {
         const long long m = m0 + tid;
-        if (m < a.M) {
-            pix_x[tid] = static_cast<int>(m % a.W);
-            const long long t = m / a.W;
-            pix_y[tid] = static_cast<int>(t % a.H);
-            pix_n[tid] = static_cast<int>(t / a.H);
+        if (m < Mc) {
+            const int wc = S2 ? pt.wc : a.W, hc = S2 ? pt.hc : a.H;
+            const int xx = static_cast<int>(m % wc);
+            const long long t = m / wc;
+            pix_x[tid] = S2 ? 2 * xx + px : xx;
+            pix_y[tid] = S2 ? 2 * static_cast<int>(t % hc) + py : static_cast<int>(t % hc);
+            pix_n[tid] = static_cast<int>(t / hc);
         } else {
             pix_n[tid] = -1;
             pix_y[tid] = pix_x[tid] = 0;
@@ -481,17 +514,18 @@ __global__ void __launch_bounds__(256) conv_dgrad_kernel(DgradArgs a) {
     float acc[4][4] = {};
     const int a_pix = tid % GBM, a_kq = tid / GBM;
     const int b_ci = tid % GBN, b_kq = tid / GBN;
-    const int pn = pix_n[a_pix], py = pix_y[a_pix], px = pix_x[a_pix];
-    for (int k0 = 0; k0 < a.K; k0 += GBK) {
+    const int pn = pix_n[a_pix], iy = pix_y[a_pix], ix = pix_x[a_pix];
+    for (int k0 = 0; k0 < Kc; k0 += GBK) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int k = k0 + a_kq * 4 + j;
             float v = 0.f;
-            if (k < a.K && pn >= 0) {
+            if (k < Kc && pn >= 0) {
                 const int tap = k / a.Cout, co = k - tap * a.Cout;
-                const int ky = tap / a.KW, kx = tap - ky * a.KW;
-                const int ty2 = py + a.pad - ky, tx2 = px + a.pad - kx;
-                if (ty2 >= 0 && tx2 >= 0 && ty2 % a.stride == 0 && tx2 % a.stride == 0) {
+                int ky = tap / nkx, kx = tap - ky * nkx;
+                if (S2) { ky = pt.ky0 + 2 * ky; kx = pt.kx0 + 2 * kx; }
+                const int ty2 = iy + a.pad - ky, tx2 = ix + a.pad - kx;
+                if (ty2 >= 0 && tx2 >= 0 && (S2 || (ty2 % a.stride == 0 && tx2 % a.stride == 0))) {
                     const int oy = ty2 / a.stride, ox = tx2 / a.stride;
                     if (oy < a.OH && ox < a.OW)
                         v = ldf(dy + ((static_cast<long long>(pn) * a.OH + oy) * a.OW + ox) * a.lddy + co);
@@ -504,9 +538,14 @@ __global__ void __launch_bounds__(256) conv_dgrad_kernel(DgradArgs a) {
             const int k = k0 + b_kq * 4 + j;
             const int ci = n0 + b_ci;
             float v = 0.f;
-            if (k < a.K && ci < a.Cin) {
+            if (k < Kc && ci < a.Cin) {
                 const int tap = k / a.Cout, co = k - tap * a.Cout;
-                v = to_f32<TW>(w[co * a.w_sco + tap * a.w_stap + ci]);
+                int wtap = tap;
+                if (S2) {
+                    const int ky = tap / nkx, kx = tap - ky * nkx;
+                    wtap = (pt.ky0 + 2 * ky) * a.KW + pt.kx0 + 2 * kx;
+                }
+                v = to_f32<TW>(w[co * a.w_sco + wtap * a.w_stap + ci]);
             }
             Bs[b_kq * 4 + j][b_ci] = v;
         }
@@ -527,13 +566,14 @@ __global__ void __launch_bounds__(256) conv_dgrad_kernel(DgradArgs a) {
     T* __restrict__ dx = reinterpret_cast<T*>(a.dx);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const long long m = m0 + ty * 4 + i;
-        if (m >= a.M) continue;
+        const int r = ty * 4 + i;
+        if (m0 + r >= Mc) continue;
+        const long long pix = (static_cast<long long>(pix_n[r]) * a.H + pix_y[r]) * a.W + pix_x[r];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int ci = n0 + tx * 4 + j;
             if (ci >= a.Cin) continue;
-            T* o = dx + m * a.lddx + ci;
+            T* o = dx + pix * a.lddx + ci;
             float v = acc[i][j];
             if (a.accumulate) v += ldf(o);
             *o = from_f32<T>(v);
@@ -679,6 +719,52 @@ dw_dgrad_kernel(const T* __restrict__ dy, long long lddy, const float* __restric
         T* o = dx + ((static_cast<long long>(n) * H + iy) * W + ix) * lddx + c;
         if (accumulate) acc += ldf(o);
         *o = from_f32<T>(acc);
+    }
+}
+
+// vectorised: one thread = one input pixel x one 16-byte channel vector; only the taps whose parity meets the pixel
+template <typename T>
+__global__ void __launch_bounds__(256)
+dw_dgrad_v_kernel(const T* __restrict__ dy, long long lddy, const float* __restrict__ w, T* __restrict__ dx, long long lddx,
+                  int N, int H, int W, int C, int K, int stride, int OH, int OW, int accumulate) {
+    constexpr int V = vec_n<T>();
+    const int pad = (K - 1) / 2, CV = C / V;
+    const long long total = static_cast<long long>(N) * H * W * CV;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c0 = static_cast<int>(i % CV) * V;
+        long long t = i / CV;
+        const int ix = static_cast<int>(t % W);
+        t /= W;
+        const int iy = static_cast<int>(t % H), n = static_cast<int>(t / H);
+        float acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = 0.f;
+        for (int ky = (iy + pad) % stride; ky < K; ky += stride) {
+            const int ty = iy + pad - ky;
+            if (ty < 0) break;
+            const int oy = ty / stride;
+            if (oy >= OH) continue;
+            for (int kx = (ix + pad) % stride; kx < K; kx += stride) {
+                const int tx = ix + pad - kx;
+                if (tx < 0) break;
+                const int ox = tx / stride;
+                if (ox >= OW) continue;
+                float g[V];
+                ldv(dy + ((static_cast<long long>(n) * OH + oy) * OW + ox) * lddy + c0, g);
+                const float* wp = w + (ky * K + kx) * C + c0;
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] = fmaf(g[v], __ldg(wp + v), acc[v]);
+            }
+        }
+        T* o = dx + ((static_cast<long long>(n) * H + iy) * W + ix) * lddx + c0;
+        if (accumulate) {
+            float old[V];
+            ldv(o, old);
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] += old[v];
+        }
+        stv(o, acc);
     }
 }
 
@@ -1095,12 +1181,20 @@ extern "C" int cabinet_conv_dgrad(const void* dy, long long lddy, int dtype, con
     a.OH = OH; a.OW = OW; a.accumulate = accumulate;
     a.M = static_cast<long long>(N) * H * W;
     a.K = KH * KW * Cout;
-    dim3 grid(static_cast<unsigned>(cab_ceil_div(a.M, GBM)), static_cast<unsigned>(cab_ceil_div(Cin, GBN)));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (dtype == CABINET_F32 && w_dtype == CABINET_F32) conv_dgrad_kernel<float, float><<<grid, 256, 0, s>>>(a);
-    else if (dtype == CABINET_F32) conv_dgrad_kernel<float, bf16><<<grid, 256, 0, s>>>(a);
-    else if (w_dtype == CABINET_F32) conv_dgrad_kernel<bf16, float><<<grid, 256, 0, s>>>(a);
-    else conv_dgrad_kernel<bf16, bf16><<<grid, 256, 0, s>>>(a);
+    const bool s2 = stride == 2;
+    if (s2) a.M = static_cast<long long>(N) * ((H + 1) / 2) * ((W + 1) / 2);  // the largest parity class
+    dim3 grid(static_cast<unsigned>(cab_ceil_div(a.M, GBM)), static_cast<unsigned>(cab_ceil_div(Cin, GBN)), s2 ? 4 : 1);
+#define CAB_DG(T, TW)                                                      \
+    do {                                                                   \
+        if (s2) conv_dgrad_kernel<T, TW, true><<<grid, 256, 0, s>>>(a);    \
+        else conv_dgrad_kernel<T, TW, false><<<grid, 256, 0, s>>>(a);      \
+    } while (0)
+    if (dtype == CABINET_F32 && w_dtype == CABINET_F32) CAB_DG(float, float);
+    else if (dtype == CABINET_F32) CAB_DG(float, bf16);
+    else if (w_dtype == CABINET_F32) CAB_DG(bf16, float);
+    else CAB_DG(bf16, bf16);
+#undef CAB_DG
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }
@@ -1145,8 +1239,19 @@ extern "C" int cabinet_dwconv_dgrad(const void* dy, long long lddy, int dtype, c
                                     int accumulate, cabinet_stream_t stream) {
     CAB_REQUIRE(dy && w_packed && dx && C > 0 && (k == 3 || k == 5) && stride >= 1, "dwconv_dgrad: bad arguments");
     if (N == 0) return CABINET_OK;
-    const long long total = static_cast<long long>(N) * H * W * C;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int V = dtype == CABINET_F32 ? 4 : 8;
+    if (C % V == 0 && lddy % V == 0 && lddx % V == 0 && al16(dy) && al16(dx) && al16(w_packed) && C % 4 == 0) {
+        const long long tv = static_cast<long long>(N) * H * W * (C / V);
+        CAB_DT2(dtype,
+                (dw_dgrad_v_kernel<float><<<ew_grid(tv), 256, 0, s>>>(reinterpret_cast<const float*>(dy), lddy, w_packed, reinterpret_cast<float*>(dx), lddx, N, H,
+                                                                     W, C, k, stride, OH, OW, accumulate)),
+                (dw_dgrad_v_kernel<bf16><<<ew_grid(tv), 256, 0, s>>>(reinterpret_cast<const bf16*>(dy), lddy, w_packed, reinterpret_cast<bf16*>(dx), lddx, N, H,
+                                                                    W, C, k, stride, OH, OW, accumulate)));
+        CAB_LAUNCH_CHECK();
+        return CABINET_OK;
+    }
+    const long long total = static_cast<long long>(N) * H * W * C;
     CAB_DT2(dtype,
             (dw_dgrad_kernel<float><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const float*>(dy), lddy, w_packed, reinterpret_cast<float*>(dx), lddx, N, H, W,
                                                                   C, k, stride, OH, OW, accumulate)),
