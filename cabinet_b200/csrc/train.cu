@@ -97,8 +97,20 @@ __device__ __forceinline__ void col_reduce_block_v(long long M, int C, long long
         float acc[NQ * V];
 #pragma unroll
         for (int q = 0; q < NQ * V; ++q) acc[q] = 0.f;
-        if (lane < lanes)
-            for (long long m = m0 + lane; m < m1; m += lanes) f(m, (v0 + cv) * V, acc);
+        if (lane < lanes) {
+            // two independent accumulator sets / rows in flight per thread (fixed pairing: still deterministic)
+            float acc2[NQ * V];
+#pragma unroll
+            for (int q = 0; q < NQ * V; ++q) acc2[q] = 0.f;
+            long long m = m0 + lane;
+            for (; m + lanes < m1; m += 2 * lanes) {
+                f(m, (v0 + cv) * V, acc);
+                f(m + lanes, (v0 + cv) * V, acc2);
+            }
+            if (m < m1) f(m, (v0 + cv) * V, acc);
+#pragma unroll
+            for (int q = 0; q < NQ * V; ++q) acc[q] += acc2[q];
+        }
         __syncthreads();
         if (lane < lanes)
 #pragma unroll
@@ -141,13 +153,20 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nb, lo
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ run_mean, float* __restrict__ run_var,
                                    float* __restrict__ stats /* [4][C]: mean, invstd, scale, shift */) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    // one WARP per channel: lane l adds blocks l, l + 32, ... in order, then a fixed butterfly (deterministic)
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
     double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < nb; ++b) {
+    for (int b = lane; b < nb; b += 32) {
         s1 += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
         s2 += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane != 0) return;
     const double k = ldf(x + c), inv_m = 1.0 / static_cast<double>(M);
     const double d = s1 * inv_m;
     const double mean = k + d;
@@ -318,13 +337,19 @@ affine_act_v_kernel(const TZ* __restrict__ z, long long ldz, const float* __rest
 // per-channel means the apply kernel subtracts
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb, long long M, int C,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;  // one warp per channel
     if (c >= C) return;
     float s1 = 0.f, s2 = 0.f;
-    for (int b = 0; b < nb; ++b) {
+    for (int b = lane; b < nb; b += 32) {
         s1 += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
         s2 += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane != 0) return;
     if (dbeta) dbeta[c] += s1;
     if (dgamma) dgamma[c] += s2;
     coef[c] = s1 / static_cast<float>(M);
@@ -793,14 +818,17 @@ dw_wgrad_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ 
     });
 }
 
-// dW ([C][1][k][k]) += sum_b partial[b][tap][c]
+// dW ([C][1][k][k]) += sum_b partial[b][tap][c]: one warp per output (lane l adds blocks l, l + 32, ... then a fixed
+// butterfly: deterministic)
 __global__ void dw_wgrad_finalize_kernel(const float* __restrict__ partial, int nb, int C, int taps, float* __restrict__ dw) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= C * taps) return;
     const int c = i % C, t = i / C;
     float sum = 0.f;
-    for (int b = 0; b < nb; ++b) sum += partial[(static_cast<long long>(b) * taps + t) * C + c];
-    dw[c * taps + t] += sum;
+    for (int b = lane; b < nb; b += 32) sum += partial[(static_cast<long long>(b) * taps + t) * C + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) dw[c * taps + t] += sum;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1025,7 +1053,7 @@ extern "C" int cabinet_bn_train_stats(const void* x, long long ldx, int dtype, l
                 (bn_stats_kernel<bf16><<<nb, RED_THREADS, RED_SMEM, s>>>(reinterpret_cast<const bf16*>(x), ldx, M, C, rpb, scratch)));
     }
     CAB_LAUNCH_CHECK();
-    const unsigned g = static_cast<unsigned>(cab_ceil_div(C, 128));
+    const unsigned g = static_cast<unsigned>(cab_ceil_div(C, 4));  // 4 warps = 4 channels per block
     CAB_DT2(dtype,
             (bn_finalize_kernel<float><<<g, 128, 0, s>>>(scratch, nb, M, C, reinterpret_cast<const float*>(x), gamma, beta, eps,
                                                         momentum, running_mean, running_var, stats)),
@@ -1096,7 +1124,7 @@ extern "C" int cabinet_bn_train_backward(const void* dy, long long lddy, const v
                                                                             reinterpret_cast<const bf16*>(z), ldz, stats, act, M, C, rpb, scratch)));
     }
     CAB_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(C, 128)), 128, 0, s>>>(scratch, nb, M, C, dgamma, dbeta, coef);
+    bn_bwd_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(C, 4)), 128, 0, s>>>(scratch, nb, M, C, dgamma, dbeta, coef);
     CAB_LAUNCH_CHECK();
     if (vec) {
         const unsigned gv = row_grid(M, 256 / (C / V));
@@ -1277,7 +1305,7 @@ extern "C" int cabinet_dwconv_wgrad(const void* dy, long long lddy, const void* 
     else { if (k == 3) CAB_DWW(bf16, 3); else CAB_DWW(bf16, 5); }
 #undef CAB_DWW
     CAB_LAUNCH_CHECK();
-    dw_wgrad_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(C * k * k, 256)), 256, 0, s>>>(scratch, nb, C, k * k, dw);
+    dw_wgrad_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(C * k * k, 8)), 256, 0, s>>>(scratch, nb, C, k * k, dw);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }
