@@ -275,11 +275,22 @@ bn_bwd_apply_v_kernel(const T* __restrict__ dy, long long lddy, const T* __restr
         mean[v] = stats[c0 + v]; invstd[v] = stats[C + c0 + v]; scale[v] = stats[2 * C + c0 + v]; shift[v] = stats[3 * C + c0 + v];
         k1[v] = coef[c0 + v]; k2[v] = coef[C + c0 + v];
     }
-    for (long long m = static_cast<long long>(blockIdx.x) * lanes + lane; m < M; m += static_cast<long long>(gridDim.x) * lanes) {
-        float zv[V], dv[V], o[V];
+    const long long step = static_cast<long long>(gridDim.x) * lanes;
+    for (long long m = static_cast<long long>(blockIdx.x) * lanes + lane; m < M; m += 2 * step) {
+        // two rows in flight per thread
+        const long long m2 = m + step;
+        const bool two = m2 < M;
+        float zv[V], dv[V], o[V], zv2[V], dv2[V], o2[V];
         ldv(z + m * ldz + c0, zv);
         ldv(dy + m * lddy + c0, dv);
-        if (accumulate) ldv(dz + m * lddz + c0, o);
+        if (two) {
+            ldv(z + m2 * ldz + c0, zv2);
+            ldv(dy + m2 * lddy + c0, dv2);
+        }
+        if (accumulate) {
+            ldv(dz + m * lddz + c0, o);
+            if (two) ldv(dz + m2 * lddz + c0, o2);
+        }
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             const float g = dv[v] * act_grad(fmaf(zv[v], scale[v], shift[v]), act);
@@ -287,6 +298,15 @@ bn_bwd_apply_v_kernel(const T* __restrict__ dy, long long lddy, const T* __restr
             o[v] = accumulate ? o[v] + r : r;
         }
         stv(dz + m * lddz + c0, o);
+        if (two) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float g = dv2[v] * act_grad(fmaf(zv2[v], scale[v], shift[v]), act);
+                const float r = scale[v] * (g - k1[v] - (zv2[v] - mean[v]) * invstd[v] * k2[v]);
+                o2[v] = accumulate ? o2[v] + r : r;
+            }
+            stv(dz + m2 * lddz + c0, o2);
+        }
     }
 }
 
@@ -818,6 +838,41 @@ dw_wgrad_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ 
     });
 }
 
+// channel-pair variant (4-byte bf16x2 / 8-byte float2 accesses: a warp reads 128 / 256 contiguous bytes per tap)
+template <typename T> __device__ __forceinline__ float2 ld2(const T* p);
+template <> __device__ __forceinline__ float2 ld2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 ld2<bf16>(const bf16* p) {
+    const uint32_t r = *reinterpret_cast<const uint32_t*>(p);
+    return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u));
+}
+
+template <typename T, int KK>
+__global__ void __launch_bounds__(RED_THREADS)
+dw_wgrad_v2_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx, int H, int W, int C,
+                   int stride, int OH, int OW, long long M, long long rpb, float* __restrict__ partial) {
+    constexpr int K = KK;
+    const int pad = (K - 1) / 2;
+    col_reduce_block_v<K * K, 2>(M, C, rpb, partial, [&](long long m, int c0, float* acc) {
+        const int ox = static_cast<int>(m % OW);
+        const long long t = m / OW;
+        const int oy = static_cast<int>(t % OH), n = static_cast<int>(t / OH);
+        const float2 g = ld2(dy + m * lddy + c0);
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const int iy = oy * stride - pad + ky;
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const int ix = ox * stride - pad + kx;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+                    const float2 xv = ld2(x + ((static_cast<long long>(n) * H + iy) * W + ix) * ldx + c0);
+                    acc[(ky * K + kx) * 2] = fmaf(g.x, xv.x, acc[(ky * K + kx) * 2]);
+                    acc[(ky * K + kx) * 2 + 1] = fmaf(g.y, xv.y, acc[(ky * K + kx) * 2 + 1]);
+                }
+            }
+        }
+    });
+}
+
 // dW ([C][1][k][k]) += sum_b partial[b][tap][c]: one warp per output (lane l adds blocks l, l + 32, ... then a fixed
 // butterfly: deterministic)
 __global__ void dw_wgrad_finalize_kernel(const float* __restrict__ partial, int nb, int C, int taps, float* __restrict__ dw) {
@@ -1297,6 +1352,25 @@ extern "C" int cabinet_dwconv_wgrad(const void* dy, long long lddy, const void* 
     long long rpb;
     const int nb = red_blocks(M, &rpb);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (C % 2 == 0 && lddy % 2 == 0 && ldx % 2 == 0 && (reinterpret_cast<uintptr_t>(dy) & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0) {
+        const size_t smem2 = RED_THREADS * 2 * k * k * sizeof(float);
+        static bool attr_done = false;
+        if (!attr_done) {
+            CAB_CUDA(cudaFuncSetAttribute(dw_wgrad_v2_kernel<float, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            CAB_CUDA(cudaFuncSetAttribute(dw_wgrad_v2_kernel<bf16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            attr_done = true;
+        }
+#define CAB_DWV(T, KK)                                                                                                       \
+    dw_wgrad_v2_kernel<T, KK><<<nb, RED_THREADS, smem2, s>>>(reinterpret_cast<const T*>(dy), lddy, reinterpret_cast<const T*>(x), \
+                                                            ldx, H, W, C, stride, OH, OW, M, rpb, scratch)
+        if (dtype == CABINET_F32) { if (k == 3) CAB_DWV(float, 3); else CAB_DWV(float, 5); }
+        else { if (k == 3) CAB_DWV(bf16, 3); else CAB_DWV(bf16, 5); }
+#undef CAB_DWV
+        CAB_LAUNCH_CHECK();
+        dw_wgrad_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(C * k * k, 8)), 256, 0, s>>>(scratch, nb, C, k * k, dw);
+        CAB_LAUNCH_CHECK();
+        return CABINET_OK;
+    }
     const size_t smem = RED_THREADS * k * k * sizeof(float);
 #define CAB_DWW(T, KK)                                                                                                   \
     dw_wgrad_kernel<T, KK><<<nb, RED_THREADS, smem, s>>>(reinterpret_cast<const T*>(dy), lddy, reinterpret_cast<const T*>(x), \

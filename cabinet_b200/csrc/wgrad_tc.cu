@@ -1,4 +1,4 @@
-// Weight gradient of a stride-1 "same" convolution on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulation in TMEM):
+// Weight gradient of a stride-1 "same" (or any stride-2) convolution on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulation in TMEM):
 //
 //     dW[co][ky][kx][ci] = sum over pixels (n, oy, ox)  dy[n][oy][ox][co] * x[n][oy + ky - pad][ox + kx - pad][ci]
 //
@@ -9,6 +9,8 @@
 // 128-byte-swizzled layout, which is exactly the canonical MN-major SWIZZLE_128B atom (64 MN elements x 8 K rows);
 // descriptors: LBO = bytes between 64-channel blocks, SBO = 1024 (8 K rows), instruction descriptor a_major = b_major = 1.
 // No transposition pass, no im2col: the tap shift is a shifted box coordinate and the zero padding TMA's out-of-bounds fill.
+// Stride 2: one tensor map per input parity (py, px): map(py,px)[h][w] = x[2h+py][2w+px]; tap (ky, kx) reads the map of
+// parity ((ky - pad) & 1, (kx - pad) & 1) at the box shifted by (ky - pad) >> 1 -- again a plain box.
 //
 // Grid: (cout tiles of 128, taps x cin tiles of NB, pixel splits).  Warp 0 = TMA producer, warp 1 = TMEM allocator +
 // MMA issuer, warps 2-5 = epilogue (TMEM -> fp32 partial[split][co][tap * Cin + ci]).  The splits are added in index
@@ -23,7 +25,7 @@ constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_STAGES = 8;
 
 struct WgParams {
-    int Cin, Cout, taps, KW, pad;
+    int Cin, Cout, taps, KW, pad, stride;
     int TW, TH, tiles_w, tiles_h, n_k_tiles, tiles_per_split, flat;
     int NB, n_blocks, n_tiles, stages, stage_bytes;
     float* partial;
@@ -41,7 +43,9 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgParams p) {
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                     const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+                     const __grid_constant__ CUtensorMap tmX3, const WgParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[WG_MAX_STAGES], empty_bar[WG_MAX_STAGES], acc_bar;
     __shared__ uint32_t tmem_base_smem;
@@ -57,6 +61,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
     if (threadIdx.x == 0) {
         tc::prefetch_tmap(&tmDY);
         tc::prefetch_tmap(&tmX);
+        if (p.stride == 2) {
+            tc::prefetch_tmap(&tmX1);
+            tc::prefetch_tmap(&tmX2);
+            tc::prefetch_tmap(&tmX3);
+        }
         for (int s = 0; s < p.stages; ++s) {
             tc::mbar_init(&full_bar[s], 1);
             tc::mbar_init(&empty_bar[s], 1);
@@ -74,6 +83,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
     if (warp == 0) {
         // ---------------- TMA producer
         if (lane == 0) {
+            // stride 2: this tap's input parity map and box shift
+            const int dy_ = ky - p.pad, dx_ = kx - p.pad;
+            const int par = p.stride == 2 ? ((dy_ & 1) * 2 + (dx_ & 1)) : 0;
+            const int shy = p.stride == 2 ? (dy_ - (dy_ & 1)) / 2 : dy_, shx = p.stride == 2 ? (dx_ - (dx_ & 1)) / 2 : dx_;
+            const CUtensorMap* tmx = par == 0 ? &tmX : (par == 1 ? &tmX1 : (par == 2 ? &tmX2 : &tmX3));
             for (int t = t0; t < t1; ++t) {
                 const int it = t - t0, s = it % p.stages;
                 if (it >= p.stages) tc::mbar_wait(&empty_bar[s], ((it / p.stages) - 1) & 1);
@@ -88,9 +102,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
                 tc::mbar_expect_tx(&full_bar[s], static_cast<uint32_t>(p.stage_bytes));
                 tc::tma_load_4d(st, &tmDY, &full_bar[s], co0, c1, c2, c3);
                 tc::tma_load_4d(st + BOX_BYTES, &tmDY, &full_bar[s], co0 + 64, c1, c2, c3);
-                const int xs = p.flat ? c1 : c1 + kx - p.pad, ys = p.flat ? 0 : c2 + ky - p.pad;
+                const int xs = p.flat ? c1 : c1 + shx, ys = p.flat ? 0 : c2 + shy;
                 for (int j = 0; j < p.n_blocks; ++j)
-                    tc::tma_load_4d(st + (2 + j) * BOX_BYTES, &tmX, &full_bar[s], ci0 + 64 * j, xs, ys, c3);
+                    tc::tma_load_4d(st + (2 + j) * BOX_BYTES, tmx, &full_bar[s], ci0 + 64 * j, xs, ys, c3);
             }
         }
     } else if (warp == 1) {
@@ -160,9 +174,10 @@ struct WgPlan {
     long long n_k_tiles;
 };
 
-WgPlan wg_plan(int N, int H, int W, int Cin, int Cout, int KH, int KW) {
+WgPlan wg_plan(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride = 1) {
+    // H, W: the OUTPUT (dy) grid
     WgPlan g;
-    g.flat = (KH == 1 && KW == 1) ? 1 : 0;
+    g.flat = (KH == 1 && KW == 1 && stride == 1) ? 1 : 0;
     if (g.flat) {
         g.TW = KT; g.TH = 1; g.tiles_h = 1;
         g.n_k_tiles = cab_ceil_div(static_cast<long long>(N) * H * W, KT);
@@ -191,50 +206,67 @@ WgPlan wg_plan(int N, int H, int W, int Cin, int Cout, int KH, int KW) {
 
 }  // namespace
 
-extern "C" long long cabinet_conv_wgrad_tc_scratch_floats(int N, int H, int W, int Cin, int Cout, int KH, int KW) {
-    const WgPlan g = wg_plan(N, H, W, Cin, Cout, KH, KW);
+extern "C" long long cabinet_conv_wgrad_tc_scratch_floats(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
+                                                          int pad) {
+    const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
+    const WgPlan g = wg_plan(N, OH, OW, Cin, Cout, KH, KW, stride);
     return static_cast<long long>(g.splits) * Cout * KH * KW * Cin;
 }
 
 extern "C" int cabinet_conv_wgrad_tc(const void* dy, long long lddy, const void* x, long long ldx, float* dw_oihw, int N,
-                                     int H, int W, int Cin, int Cout, int KH, int KW, int pad, float* scratch,
+                                     int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, float* scratch,
                                      cabinet_stream_t stream) {
     CAB_REQUIRE(dy && x && dw_oihw && scratch, "conv_wgrad_tc: null pointer");
-    CAB_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && 2 * pad == KH - 1 && KH == KW,
-                "conv_wgrad_tc: stride-1 'same' convolutions only (2 * pad == k - 1)");
+    CAB_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && KH == KW && pad >= 0 &&
+                    ((stride == 1 && 2 * pad == KH - 1) || (stride == 2 && H >= 2 && W >= 2)),
+                "conv_wgrad_tc: stride-1 'same' (2 * pad == k - 1) or stride-2 convolutions only");
+    const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
     CAB_REQUIRE(lddy % 8 == 0 && ldx % 8 == 0 && lddy >= Cout && ldx >= Cin && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(x) & 15) == 0,
                 "conv_wgrad_tc: pixel strides must be multiples of 8 and the bases 16-byte aligned");
-    const WgPlan g = wg_plan(N, H, W, Cin, Cout, KH, KW);
+    const WgPlan g = wg_plan(N, OH, OW, Cin, Cout, KH, KW, stride);
     CAB_REQUIRE(g.n_k_tiles < (1LL << 31) && static_cast<long long>(N) * H * W < (1LL << 31), "conv_wgrad_tc: too many pixels");
     WgParams p;
-    p.Cin = Cin; p.Cout = Cout; p.taps = KH * KW; p.KW = KW; p.pad = pad;
+    p.Cin = Cin; p.Cout = Cout; p.taps = KH * KW; p.KW = KW; p.pad = pad; p.stride = stride;
     p.TW = g.TW; p.TH = g.TH; p.tiles_w = g.tiles_w; p.tiles_h = g.tiles_h; p.n_k_tiles = static_cast<int>(g.n_k_tiles);
     p.tiles_per_split = g.tiles_per_split; p.flat = g.flat;
     p.NB = g.NB; p.n_blocks = g.NB / 64; p.n_tiles = g.n_tiles;
     p.stage_bytes = (2 + p.n_blocks) * BOX_BYTES;
     p.stages = std::max(2, std::min(WG_MAX_STAGES, (200 * 1024) / p.stage_bytes));
     p.partial = scratch;
-    CUtensorMap tmDY, tmX;
+    CUtensorMap tmDY, tmX[4];
     const uint64_t es = 2;
-    for (int which = 0; which < 2; ++which) {
-        const void* base = which ? x : dy;
-        const long long ld = which ? ldx : lddy;
-        const int C = which ? Cin : Cout;
-        int rc;
-        if (g.flat) {
-            const uint64_t P = static_cast<uint64_t>(N) * H * W;
-            const uint64_t dims[4] = {(uint64_t)C, P, 1, 1};
+    if (g.flat) {
+        const uint64_t P = static_cast<uint64_t>(N) * H * W;
+        const uint32_t box[4] = {64, KT, 1, 1};
+        for (int which = 0; which < 2; ++which) {
+            const long long ld = which ? ldx : lddy;
+            const uint64_t dims[4] = {(uint64_t)(which ? Cin : Cout), P, 1, 1};
             const uint64_t strides[3] = {(uint64_t)ld * es, (uint64_t)ld * es * P, (uint64_t)ld * es * P};
-            const uint32_t box[4] = {64, KT, 1, 1};
-            rc = cab_make_tmap_bf16(which ? &tmX : &tmDY, base, 4, dims, strides, box);
-        } else {
-            const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-            const uint64_t strides[3] = {(uint64_t)ld * es, (uint64_t)ld * es * W, (uint64_t)ld * es * W * H};
-            const uint32_t box[4] = {64, (uint32_t)g.TW, (uint32_t)g.TH, 1};
-            rc = cab_make_tmap_bf16(which ? &tmX : &tmDY, base, 4, dims, strides, box);
+            int rc = cab_make_tmap_bf16(which ? &tmX[0] : &tmDY, which ? x : dy, 4, dims, strides, box);
+            if (rc) return rc;
         }
-        if (rc) return rc;
+        tmX[1] = tmX[2] = tmX[3] = tmX[0];
+    } else {
+        const uint32_t box[4] = {64, (uint32_t)g.TW, (uint32_t)g.TH, 1};
+        {
+            const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)OW, (uint64_t)OH, (uint64_t)N};
+            const uint64_t strides[3] = {(uint64_t)lddy * es, (uint64_t)lddy * es * OW, (uint64_t)lddy * es * OW * OH};
+            int rc = cab_make_tmap_bf16(&tmDY, dy, 4, dims, strides, box);
+            if (rc) return rc;
+        }
+        const bf16* xb = reinterpret_cast<const bf16*>(x);
+        for (int py = 0; py < stride; ++py)
+            for (int px = 0; px < stride; ++px) {
+                const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)((W - px + stride - 1) / stride),
+                                          (uint64_t)((H - py + stride - 1) / stride), (uint64_t)N};
+                const uint64_t strides[3] = {(uint64_t)ldx * es * stride, (uint64_t)ldx * es * W * stride,
+                                             (uint64_t)ldx * es * W * H};
+                int rc = cab_make_tmap_bf16(&tmX[py * stride + px], xb + (static_cast<long long>(py) * W + px) * ldx, 4, dims,
+                                            strides, box);
+                if (rc) return rc;
+            }
+        if (stride == 1) tmX[1] = tmX[2] = tmX[3] = tmX[0];
     }
     const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
     static bool attr_done = false;
@@ -244,7 +276,7 @@ extern "C" int cabinet_conv_wgrad_tc(const void* dy, long long lddy, const void*
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     dim3 grid(g.m_tiles, p.taps * g.n_tiles, g.splits);
-    conv_wgrad_tc_kernel<<<grid, WG_THREADS, smem, s>>>(tmDY, tmX, p);
+    conv_wgrad_tc_kernel<<<grid, WG_THREADS, smem, s>>>(tmDY, tmX[0], tmX[1], tmX[2], tmX[3], p);
     CAB_LAUNCH_CHECK();
     const long long total = static_cast<long long>(Cout) * Cin * p.taps;
     wgrad_tc_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(total, 256)), 256, 0, s>>>(scratch, g.splits, Cout, Cin, p.taps,

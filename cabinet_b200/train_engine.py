@@ -235,12 +235,12 @@ class TrainEngine:
                 sc = self.scratch(N * OH * OW, cout, 1)
                 self._call("cabinet_col_sum", dy.ptr, dy.ld, dy.dt, N * OH * OW, cout, self.pgrad(b).data_ptr(), 1,
                            sc.data_ptr())
-            if (self.use_tc and self.wgrad_tc and nchw is None and stride == 1 and kh == kw and 2 * pad == kh - 1
-                    and self._tc_ok(x) and self._tc_ok(dy)):
-                n = int(self.lib.cabinet_conv_wgrad_tc_scratch_floats(N, H, W, cin, cout, kh, kw))
+            if (self.use_tc and self.wgrad_tc and nchw is None and kh == kw and self._tc_ok(x) and self._tc_ok(dy)
+                    and ((stride == 1 and 2 * pad == kh - 1) or (stride == 2 and H >= 2 and W >= 2))):
+                n = int(self.lib.cabinet_conv_wgrad_tc_scratch_floats(N, H, W, cin, cout, kh, kw, stride, pad))
                 sc = torch.empty(n, dtype=torch.float32, device=self.dev)
                 self._call("cabinet_conv_wgrad_tc", dy.ptr, dy.ld, x.ptr, x.ld, self.pgrad(w).data_ptr(), N, H, W, cin, cout,
-                           kh, kw, pad, sc.data_ptr())
+                           kh, kw, stride, pad, sc.data_ptr())
             else:
                 n = int(self.lib.cabinet_conv_wgrad_scratch_floats(N, OH, OW, cin, cout, kh, kw))
                 sc = torch.empty(n, dtype=torch.float32, device=self.dev)

@@ -382,14 +382,14 @@ long long cabinet_conv_wgrad_scratch_floats(int N, int OH, int OW, int Cin, int 
 int cabinet_conv_wgrad(const void* dy, long long lddy, int dtype, const void* x, int x_dtype, long long sxn, long long sxh,
                        long long sxw, long long sxc, float* dw_oihw, int N, int H, int W, int Cin, int Cout, int KH, int KW,
                        int stride, int pad, int OH, int OW, float* scratch, cabinet_stream_t stream);
-/* The weight gradient of a stride-1 "same" convolution (2 * pad == k - 1; every 1x1 and the 3x3 stride-1 layers) on the
- * tensor cores: per tap a GEMM over the pixel index with both bf16 NHWC operands consumed as MN-major UMMA tiles
+/* The weight gradient of a stride-1 "same" convolution (2 * pad == k - 1; every 1x1 and the 3x3 stride-1 layers) or a
+ * stride-2 convolution (one tensor map per input parity) on the tensor cores: per tap a GEMM over the pixel index with both bf16 NHWC operands consumed as MN-major UMMA tiles
  * straight from TMA boxes (tcgen05.mma, fp32 accumulation in TMEM), split over the pixels, fixed-order second-level
- * sum.  dy [N][H][W][Cout], x [N][H][W][Cin] bf16 (pixel strides multiples of 8); dw (OIHW fp32) +=;
+ * sum.  dy [N][OH][OW][Cout], x [N][H][W][Cin] bf16 (pixel strides multiples of 8); dw (OIHW fp32) +=;
  * scratch: cabinet_conv_wgrad_tc_scratch_floats(...) floats. */
-long long cabinet_conv_wgrad_tc_scratch_floats(int N, int H, int W, int Cin, int Cout, int KH, int KW);
+long long cabinet_conv_wgrad_tc_scratch_floats(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
 int cabinet_conv_wgrad_tc(const void* dy, long long lddy, const void* x, long long ldx, float* dw_oihw, int N, int H, int W,
-                          int Cin, int Cout, int KH, int KW, int pad, float* scratch, cabinet_stream_t stream);
+                          int Cin, int Cout, int KH, int KW, int stride, int pad, float* scratch, cabinet_stream_t stream);
 /* Depthwise convolution gradients; w_packed [k*k][C] fp32; dw ([C][1][k][k] fp32) +=; scratch: (N*OH*OW, C, k*k). */
 int cabinet_dwconv_dgrad(const void* dy, long long lddy, int dtype, const float* w_packed, void* dx, long long lddx, int N,
                          int H, int W, int C, int k, int stride, int OH, int OW, int accumulate, cabinet_stream_t stream);

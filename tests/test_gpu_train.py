@@ -136,16 +136,17 @@ def test_conv_gradients(N, cin, cout, k, s, p, H, W, nchw_in, dtype):
     assert rel_l2(nchw(dx2) - 3.0, x.grad) < 1e-4 * tm   # accumulate flag
 
 
-@pytest.mark.parametrize("N,cin,cout,k,H,W,ldx_extra", [
-    (2, 16, 64, 1, 16, 24, 0), (1, 72, 24, 1, 9, 7, 8), (2, 256, 256, 3, 16, 16, 0), (1, 960, 256, 3, 4, 4, 256),
-    (2, 384, 256, 1, 12, 20, 0), (3, 64, 160, 1, 33, 17, 0), (1, 1216, 256, 3, 6, 5, 0), (2, 40, 8, 1, 64, 64, 0)])
-def test_conv_wgrad_tensor_core(N, cin, cout, k, H, W, ldx_extra):
+@pytest.mark.parametrize("N,cin,cout,k,H,W,ldx_extra,stride", [
+    (2, 16, 64, 1, 16, 24, 0, 1), (1, 72, 24, 1, 9, 7, 8, 1), (2, 256, 256, 3, 16, 16, 0, 1), (1, 960, 256, 3, 4, 4, 256, 1),
+    (2, 384, 256, 1, 12, 20, 0, 1), (3, 64, 160, 1, 33, 17, 0, 1), (1, 1216, 256, 3, 6, 5, 0, 1), (2, 40, 8, 1, 64, 64, 0, 1),
+    (2, 64, 64, 3, 32, 24, 0, 2), (1, 64, 64, 3, 17, 13, 0, 2), (2, 24, 40, 5, 20, 20, 8, 2)])
+def test_conv_wgrad_tensor_core(N, cin, cout, k, H, W, ldx_extra, stride):
     """tcgen05 weight gradient (MN-major operands straight from TMA boxes) against torch autograd on the same bf16 values."""
     lib = _lib.load()
     p = (k - 1) // 2
     x = q(gen(N, cin, H, W, seed=1), torch.bfloat16).requires_grad_(False)
     w = gen(cout, cin, k, k, seed=2, scale=0.1).requires_grad_(True)
-    y = F.conv2d(x, w, None, 1, p)
+    y = F.conv2d(x, w, None, stride, p)
     dy = q(gen(*y.shape, seed=3), torch.bfloat16)
     y.backward(dy)
     ldx = cin + ldx_extra   # the input may be a channel slice of a wider (concat) buffer
@@ -153,14 +154,14 @@ def test_conv_wgrad_tensor_core(N, cin, cout, k, H, W, ldx_extra):
     xb[..., ldx_extra:] = nhwc(x, torch.bfloat16)
     xv = xb[..., ldx_extra:]
     dyd = nhwc(dy, torch.bfloat16)
-    n = int(lib.cabinet_conv_wgrad_tc_scratch_floats(N, H, W, cin, cout, k, k))
+    n = int(lib.cabinet_conv_wgrad_tc_scratch_floats(N, H, W, cin, cout, k, k, stride, p))
     sc = torch.full((n,), float("nan"), device="cuda")
     dw = torch.zeros(cout, cin, k, k, device="cuda")
-    check(lib.cabinet_conv_wgrad_tc(dyd.data_ptr(), cout, xv.data_ptr(), ldx, dw.data_ptr(), N, H, W, cin, cout, k, k, p,
-                                    sc.data_ptr(), stream()), "wgrad_tc")
+    check(lib.cabinet_conv_wgrad_tc(dyd.data_ptr(), cout, xv.data_ptr(), ldx, dw.data_ptr(), N, H, W, cin, cout, k, k, stride,
+                                    p, sc.data_ptr(), stream()), "wgrad_tc")
     torch.cuda.synchronize()
     e = rel_l2(dw.cpu(), w.grad)
-    print(f"wgrad_tc {cin}->{cout} k{k} {N}x{H}x{W}: rel_l2 {e:.2e}")
+    print(f"wgrad_tc {cin}->{cout} k{k} s{stride} {N}x{H}x{W}: rel_l2 {e:.2e}")
     assert e < 1e-5   # exact products of bf16 values, fp32 accumulation
 
 
