@@ -42,7 +42,7 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
     return d;
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 2)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                      const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
                      const __grid_constant__ CUtensorMap tmX3, const WgParams p) {
@@ -196,11 +196,14 @@ WgPlan wg_plan(int N, int H, int W, int Cin, int Cout, int KH, int KW, int strid
     g.NB = Cin <= 64 ? 64 : (Cin <= 128 ? 128 : 256);
     g.n_tiles = static_cast<int>(cab_ceil_div(Cin, g.NB));
     g.m_tiles = static_cast<int>(cab_ceil_div(Cout, 128));
+    // ONE wave: NB <= 128 leaves room for two CTAs per SM (<= 100 KB of pipeline stages, 2 x NB <= 512 TMEM columns),
+    // NB = 256 runs one CTA per SM with a deeper ring; the pixel range is cut so that the grid does not exceed that
     const long long base = static_cast<long long>(g.m_tiles) * g.n_tiles * KH * KW;
-    long long splits = std::max<long long>(1, std::min<long long>(cab_ceil_div(148LL * 2, base), g.n_k_tiles));
+    const long long slots = 148LL * (g.NB <= 128 ? 2 : 1);
+    long long splits = std::max<long long>(1, std::min<long long>(slots / base, g.n_k_tiles));
     splits = std::min<long long>(splits, 1024);
     g.tiles_per_split = static_cast<int>(cab_ceil_div(g.n_k_tiles, splits));
-    g.splits = static_cast<int>(cab_ceil_div(g.n_k_tiles, g.tiles_per_split));
+    g.splits = static_cast<int>(cab_ceil_div(g.n_k_tiles, g.tiles_per_split));  // <= splits
     return g;
 }
 
@@ -232,7 +235,7 @@ extern "C" int cabinet_conv_wgrad_tc(const void* dy, long long lddy, const void*
     p.tiles_per_split = g.tiles_per_split; p.flat = g.flat;
     p.NB = g.NB; p.n_blocks = g.NB / 64; p.n_tiles = g.n_tiles;
     p.stage_bytes = (2 + p.n_blocks) * BOX_BYTES;
-    p.stages = std::max(2, std::min(WG_MAX_STAGES, (200 * 1024) / p.stage_bytes));
+    p.stages = std::max(2, std::min(WG_MAX_STAGES, ((p.NB <= 128 ? 100 : 200) * 1024) / p.stage_bytes));
     p.partial = scratch;
     CUtensorMap tmDY, tmX[4];
     const uint64_t es = 2;
