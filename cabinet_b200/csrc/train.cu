@@ -777,11 +777,12 @@ dw_dgrad_v_kernel(const T* __restrict__ dy, long long lddy, const float* __restr
     const long long total = static_cast<long long>(N) * H * W * CV;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>(i % CV) * V;
-        long long t = i / CV;
-        const int ix = static_cast<int>(t % W);
-        t /= W;
-        const int iy = static_cast<int>(t % H), n = static_cast<int>(t / H);
+        const unsigned iu = static_cast<unsigned>(i);  // (the host checks the vector count < 2^31)
+        const int c0 = static_cast<int>(iu % static_cast<unsigned>(CV)) * V;
+        unsigned t = iu / static_cast<unsigned>(CV);
+        const int ix = static_cast<int>(t % static_cast<unsigned>(W));
+        t /= static_cast<unsigned>(W);
+        const int iy = static_cast<int>(t % static_cast<unsigned>(H)), n = static_cast<int>(t / static_cast<unsigned>(H));
         float acc[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] = 0.f;
@@ -821,9 +822,11 @@ dw_wgrad_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ 
     constexpr int K = KK;
     const int pad = (K - 1) / 2;
     col_reduce_block<K * K>(M, C, rpb, partial, [&](long long m, int c, float* acc) {
-        const int ox = static_cast<int>(m % OW);
-        const long long t = m / OW;
-        const int oy = static_cast<int>(t % OH), n = static_cast<int>(t / OH);
+        // 32-bit index arithmetic (the host checks N*OH*OW < 2^31): a 64-bit division costs ~100 instructions
+        const unsigned mu = static_cast<unsigned>(m);
+        const int ox = static_cast<int>(mu % static_cast<unsigned>(OW));
+        const unsigned t = mu / static_cast<unsigned>(OW);
+        const int oy = static_cast<int>(t % static_cast<unsigned>(OH)), n = static_cast<int>(t / static_cast<unsigned>(OH));
         const float g = ldf(dy + m * lddy + c);
 #pragma unroll
         for (int ky = 0; ky < K; ++ky) {
@@ -853,9 +856,11 @@ dw_wgrad_v2_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict
     constexpr int K = KK;
     const int pad = (K - 1) / 2;
     col_reduce_block_v<K * K, 2>(M, C, rpb, partial, [&](long long m, int c0, float* acc) {
-        const int ox = static_cast<int>(m % OW);
-        const long long t = m / OW;
-        const int oy = static_cast<int>(t % OH), n = static_cast<int>(t / OH);
+        // 32-bit index arithmetic (the host checks N*OH*OW < 2^31): a 64-bit division costs ~100 instructions
+        const unsigned mu = static_cast<unsigned>(m);
+        const int ox = static_cast<int>(mu % static_cast<unsigned>(OW));
+        const unsigned t = mu / static_cast<unsigned>(OW);
+        const int oy = static_cast<int>(t % static_cast<unsigned>(OH)), n = static_cast<int>(t / static_cast<unsigned>(OH));
         const float2 g = ld2(dy + m * lddy + c0);
 #pragma unroll
         for (int ky = 0; ky < K; ++ky) {
@@ -902,16 +907,18 @@ resample_sep_kernel(const TI* __restrict__ in, long long isn, long long isy, lon
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         // c fastest when the output is channel-contiguous, x fastest otherwise (coalesced stores either way)
+        // (32-bit index arithmetic: the host checks total < 2^31)
         int c, ox, oy, n;
-        long long t = i;
+        unsigned t = static_cast<unsigned>(i);
+        const unsigned uC = C, uW = OW, uH = OH;
         if (osc == 1) {
-            c = static_cast<int>(t % C); t /= C;
-            ox = static_cast<int>(t % OW); t /= OW;
-            oy = static_cast<int>(t % OH); n = static_cast<int>(t / OH);
+            c = static_cast<int>(t % uC); t /= uC;
+            ox = static_cast<int>(t % uW); t /= uW;
+            oy = static_cast<int>(t % uH); n = static_cast<int>(t / uH);
         } else {
-            ox = static_cast<int>(t % OW); t /= OW;
-            oy = static_cast<int>(t % OH); t /= OH;
-            c = static_cast<int>(t % C); n = static_cast<int>(t / C);
+            ox = static_cast<int>(t % uW); t /= uW;
+            oy = static_cast<int>(t % uH); t /= uH;
+            c = static_cast<int>(t % uC); n = static_cast<int>(t / uC);
         }
         float acc = 0.f;
         const TI* base = in + n * isn + c * isc;
@@ -1324,7 +1331,8 @@ extern "C" int cabinet_dwconv_dgrad(const void* dy, long long lddy, int dtype, c
     if (N == 0) return CABINET_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int V = dtype == CABINET_F32 ? 4 : 8;
-    if (C % V == 0 && lddy % V == 0 && lddx % V == 0 && al16(dy) && al16(dx) && al16(w_packed) && C % 4 == 0) {
+    if (C % V == 0 && lddy % V == 0 && lddx % V == 0 && al16(dy) && al16(dx) && al16(w_packed) && C % 4 == 0 &&
+        static_cast<long long>(N) * H * W * (C / V) < (1LL << 31)) {
         const long long tv = static_cast<long long>(N) * H * W * (C / V);
         CAB_DT2(dtype,
                 (dw_dgrad_v_kernel<float><<<ew_grid(tv), 256, 0, s>>>(reinterpret_cast<const float*>(dy), lddy, w_packed, reinterpret_cast<float*>(dx), lddx, N, H,
@@ -1349,6 +1357,7 @@ extern "C" int cabinet_dwconv_wgrad(const void* dy, long long lddy, const void* 
                                     cabinet_stream_t stream) {
     CAB_REQUIRE(dy && x && dw && scratch && N > 0 && C > 0 && (k == 3 || k == 5), "dwconv_wgrad: bad arguments");
     const long long M = static_cast<long long>(N) * OH * OW;
+    CAB_REQUIRE(M < (1LL << 31), "dwconv_wgrad: too many pixels");
     long long rpb;
     const int nb = red_blocks(M, &rpb);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1393,6 +1402,7 @@ extern "C" int cabinet_resample_sep(const void* in, int in_dtype, long long isn,
                 "resample_sep: bad arguments");
     if (N == 0) return CABINET_OK;
     const long long total = static_cast<long long>(N) * OH * OW * C;
+    CAB_REQUIRE(total < (1LL << 31), "resample_sep: too many output elements");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define CAB_RS(TI, TO)                                                                                                   \
     resample_sep_kernel<TI, TO><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const TI*>(in), isn, isy, isx, isc,      \
