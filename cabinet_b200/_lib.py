@@ -64,6 +64,8 @@ SIGNATURES = {
     "cabinet_train_scratch_floats": ([_ll, _i, _i], _ll),
     "cabinet_pack_conv_weight": ([_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p], _i),
     "cabinet_pack_dw_weight": ([_p, _i, _i, _i, _p, _p], _i),
+    "cabinet_im2col_nchw": ([_p, _i, _i, _i, _i, _i, _i, _i, _p, _ll, _p], _i),
+    "cabinet_embed_filter": ([_p, _i, _i, _i, _i, _p, _ll, _i, _p], _i),
     "cabinet_bn_train_stats": ([_p, _ll, _i, _ll, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p], _i),
     "cabinet_affine_act": ([_p, _ll, _i, _p, _p, _p, _f, _p, _ll, _p, _ll, _i, _ll, _ll, _i, _i, _p], _i),
     "cabinet_bn_train_backward": ([_p, _ll, _p, _ll, _i, _p, _i, _p, _p, _p, _ll, _ll, _i, _i, _p, _p], _i),

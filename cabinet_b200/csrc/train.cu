@@ -486,6 +486,56 @@ __global__ void pack_dw_weight_kernel(const float* __restrict__ w, int C, int ta
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// im2col of the fp32 NCHW network input for the two stem convolutions (7x7 s2 p3 and, embedded in its centre, 3x3 s2 p1):
+// out[n*OH*OW + oy*OW + ox][ci*K*K + ky*K + kx] = bf16(x[n][ci][oy*S - P + ky][ox*S - P + kx]) (0 outside the image and in
+// the padding columns >= Cin*K*K).  The column order is the OIHW flattening of the filter, so the stem convolutions and
+// their weight gradients become plain 1x1 GEMMs on the tensor cores with the parameter / gradient tensors used in place.
+__global__ void __launch_bounds__(256)
+im2col_nchw_kernel(const float* __restrict__ x, int N, int Cin, int H, int W, int K, int S, int P, int OH, int OW,
+                   bf16* __restrict__ out, int ld) {
+    // one thread = one output pixel x one 16-byte chunk (8 columns): consecutive threads write consecutive chunks of a row
+    const unsigned chunks = ld / 8, cols = Cin * K * K, KK = K * K;
+    const long long total = static_cast<long long>(N) * OH * OW * chunks;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const unsigned iu = static_cast<unsigned>(i);
+        const unsigned ch = iu % chunks, pix = iu / chunks;
+        const int ox = pix % OW;
+        const unsigned t = pix / OW;
+        const int oy = t % OH, n = t / OH;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned col = ch * 8 + j;
+            v[j] = 0.f;
+            if (col < cols) {
+                const unsigned ci = col / KK, rem = col - ci * KK;
+                const int ky = rem / K, kx = rem - ky * K;
+                const int iy = oy * S - P + ky, ix = ox * S - P + kx;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[j] = __ldg(x + ((static_cast<long long>(n) * Cin + ci) * H + iy) * W + ix);
+            }
+        }
+        Vec16<bf16> o;
+        o.pack(v);
+        o.store(out + static_cast<long long>(pix) * ld + ch * 8);
+    }
+}
+
+// dst[r][c0 + c] (+)= src[r][c] for a [rows][cols] block (embedding a 3x3 filter / its gradient in the 7x7 footprint)
+__global__ void embed_filter_kernel(const float* __restrict__ w_small, int Cout, int Cin, int k, int K, float* __restrict__ w_big,
+                                    int ld_big, int extract_add) {
+    // w_small [Cout][Cin][k][k]  <->  w_big [Cout][ld_big], column ci*K*K + (ky + off)*K + kx + off, off = (K - k) / 2
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = Cout * Cin * k * k;
+    if (i >= total) return;
+    const int kx = i % k, ky = (i / k) % k, ci = (i / (k * k)) % Cin, co = i / (k * k * Cin);
+    const int off = (K - k) / 2;
+    float* big = w_big + static_cast<long long>(co) * ld_big + ci * K * K + (ky + off) * K + kx + off;
+    if (extract_add) const_cast<float*>(w_small)[i] += *big;   // gradient of the embedded filter back into the small one
+    else *big = w_small[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Dense convolution, data gradient (implicit GEMM over (ky, kx, co)):
 //   dx[n][iy][ix][ci] (+)= sum_{ky,kx,co} dy[n][oy][ox][co] * w[co][ky*KW+kx][ci],  oy = (iy + pad - ky) / stride (exact)
 constexpr int GBM = 64, GBN = 64, GBK = 16;
@@ -1087,6 +1137,32 @@ extern "C" int cabinet_pack_dw_weight(const float* w, int C, int k, int flip, fl
     CAB_REQUIRE(w && out && C > 0 && k > 0, "pack_dw_weight: bad arguments");
     pack_dw_weight_kernel<<<static_cast<unsigned>(cab_ceil_div(C * k * k, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         w, C, k * k, flip, out);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_im2col_nchw(const float* x, int N, int Cin, int H, int W, int k, int stride, int pad, void* out,
+                                   long long ld, cabinet_stream_t stream) {
+    CAB_REQUIRE(x && out && N >= 0 && Cin > 0 && H > 0 && W > 0 && k > 0 && stride > 0 && ld >= static_cast<long long>(Cin) * k * k &&
+                    ld % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "im2col_nchw: bad arguments (ld must be a multiple of 8 >= Cin*k*k, out 16-byte aligned)");
+    if (N == 0) return CABINET_OK;
+    const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
+    const long long total = static_cast<long long>(N) * OH * OW;
+    CAB_REQUIRE(total * (ld / 8) < (1LL << 31), "im2col_nchw: too many pixels");
+    im2col_nchw_kernel<<<ew_grid(total * (ld / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, N, Cin, H, W, k, stride, pad, OH, OW, reinterpret_cast<bf16*>(out), static_cast<int>(ld));
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_embed_filter(float* w_small, int Cout, int Cin, int k, int K, float* w_big, long long ld_big,
+                                    int extract_add, cabinet_stream_t stream) {
+    CAB_REQUIRE(w_small && w_big && Cout > 0 && Cin > 0 && k > 0 && K >= k && (K - k) % 2 == 0 && ld_big >= static_cast<long long>(Cin) * K * K,
+                "embed_filter: bad arguments");
+    const int total = Cout * Cin * k * k;
+    embed_filter_kernel<<<static_cast<unsigned>(cab_ceil_div(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w_small, Cout, Cin, k, K, w_big, static_cast<int>(ld_big), extract_add);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

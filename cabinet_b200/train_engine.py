@@ -129,7 +129,8 @@ class TrainEngine:
         self.launches = 0
         self.trace, self.phase = None, "fwd"
         self.use_tc = precision == "bf16"   # tcgen05 / TMA kernels for the GEMM-shaped and depthwise layers
-        self.wgrad_tc = True                # tcgen05 weight gradients (stride-1 "same" convolutions)
+        self.wgrad_tc = True                # tcgen05 weight gradients (stride-1 "same" and stride-2 convolutions)
+        self.stem_gemm = True               # both stems as 1x1 GEMMs on one bf16 im2col of the input
         self._zero_cache: Dict[int, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ plumbing
@@ -265,6 +266,50 @@ class TrainEngine:
                 return
             self._call("cabinet_conv_dgrad", dy.ptr, dy.ld, dy.dt, wp.data_ptr(), wdt, w_sco, w_stap, dx.ptr, dx.ld, N, H, W,
                        cin, cout, kh, kw, stride, pad, OH, OW, acc)
+
+        self.tape.append(backward)
+        return out
+
+    STEM_K, STEM_LD = 7, 152   # im2col footprint of the stems: 3 x 7 x 7 = 147 columns, pixel stride padded to 8
+
+    def stem_im2col(self, x: torch.Tensor) -> Map:
+        """bf16 im2col [N, H/2, W/2, 152] of the fp32 NCHW input over the 7x7 / stride-2 / pad-3 footprint shared by both
+        stem convolutions (the 3x3 / pad-1 backbone stem is its centre): read once, used by two forward GEMMs and two
+        weight-gradient GEMMs on the tensor cores."""
+        N, _, H, W = x.shape
+        OH, OW = _out_size(H, 7, 2, 3), _out_size(W, 7, 2, 3)
+        xcol = Map(torch.empty((N, OH, OW, self.STEM_LD), dtype=torch.bfloat16, device=self.dev), N, OH, OW, self.STEM_LD,
+                   self.STEM_LD)
+        self._call("cabinet_im2col_nchw", x.data_ptr(), N, 3, H, W, 7, 2, 3, xcol.ptr, xcol.ld)
+        return xcol
+
+    def conv_stem(self, xcol: Map, conv) -> Map:
+        """A stem convolution (7x7 s2 p3, or 3x3 s2 p1 embedded in the same footprint) as a 1x1 GEMM on the im2col matrix."""
+        w = conv.weight
+        cout, cin, k, _ = w.shape
+        assert cin == 3 and conv.stride[0] == 2 and (k, conv.padding[0]) in ((7, 3), (3, 1)) and conv.bias is None
+        N, OH, OW, LD = xcol.N, xcol.H, xcol.W, self.STEM_LD
+        out = self.new(N, OH, OW, cout)
+        r16, k64 = -(-cout // 16) * 16, -(-LD // 64) * 64
+        wbig = torch.zeros((cout, LD), dtype=torch.float32, device=self.dev)
+        self.launches += 1
+        wp = torch.empty((r16, 1, k64), dtype=torch.bfloat16, device=self.dev)
+        self._call("cabinet_embed_filter", w.data_ptr(), cout, 3, k, self.STEM_K, wbig.data_ptr(), LD, 0)
+        self._call("cabinet_pack_conv_weight", wbig.data_ptr(), cout, LD, 1, 1, wp.data_ptr(), BF16, r16, k64, 0)
+        self._call("cabinet_conv_tc", xcol.ptr, xcol.ld, N, OH, OW, LD, wp.data_ptr(), cout, 1, 1, 1, 0,
+                   self._zeros(cout).data_ptr(), None, 0, out.ptr, out.dt, out.ld, OH, OW, ACT_NONE)
+
+        def backward(g: _Grads):
+            dy = g.get(out)
+            if dy is None:
+                return
+            dwbig = torch.zeros((cout, LD), dtype=torch.float32, device=self.dev)
+            self.launches += 1
+            n = int(self.lib.cabinet_conv_wgrad_tc_scratch_floats(N, OH, OW, LD, cout, 1, 1, 1, 0))
+            sc = torch.empty(n, dtype=torch.float32, device=self.dev)
+            self._call("cabinet_conv_wgrad_tc", dy.ptr, dy.ld, xcol.ptr, xcol.ld, dwbig.data_ptr(), N, OH, OW, LD, cout, 1, 1, 1,
+                       0, sc.data_ptr())
+            self._call("cabinet_embed_filter", self.pgrad(w).data_ptr(), cout, 3, k, self.STEM_K, dwbig.data_ptr(), LD, 1)
 
         self.tape.append(backward)
         return out
@@ -523,7 +568,9 @@ class TrainEngine:
         ga, cab = ab.a2block.global_attn, ab.a2block
 
         # ---- spatial branch (cabinet.py:108-129)
-        s1 = self.bn(self.conv(None, sb.conv1.conv, nchw=x), sb.conv1.bn, ACT_RELU)
+        xcol = self.stem_im2col(x) if (self.use_tc and self.stem_gemm) else None
+        s1 = self.bn(self.conv_stem(xcol, sb.conv1.conv) if xcol is not None else self.conv(None, sb.conv1.conv, nchw=x),
+                     sb.conv1.bn, ACT_RELU)
         s2 = self.bn(self.conv(s1, sb.conv2.conv), sb.conv2.bn, ACT_RELU)
         s3 = self.bn(self.conv(s2, sb.conv3.conv), sb.conv3.bn, ACT_RELU)
         H8, W8 = s3.H, s3.W
@@ -532,7 +579,8 @@ class TrainEngine:
         self.bn(self.conv(s3, sb.conv_out.conv), sb.conv_out.bn, ACT_RELU, out=cat_ffm.slice(0, n_sb))
 
         # ---- backbone (mobilenetv3.py:102-159,202-205)
-        f = self.bn(self.conv(None, mob.features[0][0], nchw=x), mob.features[0][1], ACT_HSWISH)
+        f = self.bn(self.conv_stem(xcol, mob.features[0][0]) if xcol is not None
+                    else self.conv(None, mob.features[0][0], nchw=x), mob.features[0][1], ACT_HSWISH)
         for blk in list(mob.features)[1:]:
             s, c = blk.spec, blk.conv
             act = ACT_HSWISH if s["hs"] else ACT_RELU

@@ -330,6 +330,17 @@ int cabinet_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int
                              int rows_pad, int k_pad, int transpose_flip, cabinet_stream_t stream);
 int cabinet_pack_dw_weight(const float* w, int C, int k, int flip, float* out, cabinet_stream_t stream);
 
+/* im2col of the fp32 NCHW network input for the stem convolutions (sb.conv1 7x7 s2 p3, src/models/cabinet.py:111; backbone
+ * stem 3x3 s2 p1 = the centre of the same footprint, src/models/mobilenetv3.py:86-91): out bf16 [N*OH*OW][ld], column
+ * ci*k*k + ky*k + kx (the OIHW flattening of the filter; columns >= Cin*k*k are zeroed).  Both stems and their weight
+ * gradients then run as 1x1 GEMMs on the tensor cores (cabinet_conv_tc / cabinet_conv_wgrad_tc) on this matrix.
+ * cabinet_embed_filter: w_big[co][ci*K*K + (ky+o)*K + kx+o] = w_small[co][ci][ky][kx], o = (K-k)/2 (extract_add = 0), or
+ * w_small += that slice of w_big (extract_add = 1: the gradient of the embedded filter). */
+int cabinet_im2col_nchw(const float* x, int N, int Cin, int H, int W, int k, int stride, int pad, void* out, long long ld,
+                        cabinet_stream_t stream);
+int cabinet_embed_filter(float* w_small, int Cout, int Cin, int k, int K, float* w_big, long long ld_big, int extract_add,
+                         cabinet_stream_t stream);
+
 /* Train-mode BatchNorm2d statistics (nn.BatchNorm2d in .train(): src/models/cabinet.py:30-31, mobilenetv3.py:88-98,
  * cab.py:26-27) of x [M][C] (M = N*H*W): stats[4][C] = batch mean, 1/sqrt(biased var + eps), scale = gamma * invstd,
  * shift = beta - mean * scale; running_mean / running_var (may be NULL) are updated in place with `momentum` and the

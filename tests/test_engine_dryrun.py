@@ -258,6 +258,7 @@ def test_train_engine_schedule_and_abi(monkeypatch, mode, C, shape, precision):
     assert bwd.count("cabinet_conv_wgrad") + bwd.count("cabinet_conv_wgrad_tc") == n_conv
     # the two stems read the network input: no data gradient; bf16 mode: stride-1 data gradients are conv_tc calls
     assert bwd.count("cabinet_conv_dgrad") + bwd.count("cabinet_conv_tc") == n_conv - 2
+    assert names.count("cabinet_im2col_nchw") == (1 if precision == "bf16" else 0)
     if precision == "bf16":
         assert names.count("cabinet_conv_tc") >= n_conv - 4 and bwd.count("cabinet_conv_tc") >= n_conv - 6
         assert names.count("cabinet_dwconv_tma") > 0 and bwd.count("cabinet_dwconv_tma") > 0

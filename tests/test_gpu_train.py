@@ -165,6 +165,33 @@ def test_conv_wgrad_tensor_core(N, cin, cout, k, H, W, ldx_extra, stride):
     assert e < 1e-5   # exact products of bf16 values, fp32 accumulation
 
 
+@pytest.mark.parametrize("N,H,W", [(2, 20, 24), (1, 17, 13), (2, 64, 48)])
+def test_stem_im2col_and_embedded_filter(N, H, W):
+    """im2col of the NCHW input over the 7x7/s2/p3 footprint: the 7x7 stem AND the 3x3/s2/p1 stem (centre of the footprint)
+    are row-times-matrix products on it."""
+    lib = _lib.load()
+    x = gen(N, 3, H, W, seed=1)
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    LD = 152
+    xd = x.cuda()
+    col = torch.full((N * OH * OW, LD), 9.0, dtype=torch.bfloat16, device="cuda")
+    check(lib.cabinet_im2col_nchw(xd.data_ptr(), N, 3, H, W, 7, 2, 3, col.data_ptr(), LD, stream()), "im2col")
+    ref = F.unfold(x.to(torch.bfloat16).float(), 7, padding=3, stride=2).transpose(1, 2).reshape(N * OH * OW, 147)
+    torch.cuda.synchronize()
+    assert torch.equal(col[:, :147].float().cpu(), ref) and float(col[:, 147:].abs().max()) == 0
+    for k, p, cout in ((7, 3, 64), (3, 1, 16)):
+        w = gen(cout, 3, k, k, seed=2 + k)
+        big = torch.zeros(cout, LD, device="cuda")
+        wd = w.cuda()
+        check(lib.cabinet_embed_filter(wd.data_ptr(), cout, 3, k, 7, big.data_ptr(), LD, 0, stream()), "embed")
+        y = (col.float() @ big.t()).view(N, OH, OW, cout).permute(0, 3, 1, 2).cpu()
+        assert rel_l2(y, F.conv2d(x.to(torch.bfloat16).float(), w, None, 2, p)) < 1e-5
+        g = torch.ones_like(wd)
+        check(lib.cabinet_embed_filter(g.data_ptr(), cout, 3, k, 7, big.data_ptr(), LD, 1, stream()), "extract")
+        torch.cuda.synchronize()
+        assert torch.allclose(g.cpu(), 1.0 + w)   # extract_add: small += the embedded slice of big
+
+
 @pytest.mark.parametrize("N,C,k,s,H,W", [(2, 16, 3, 1, 9, 7), (1, 72, 5, 2, 11, 13), (2, 240, 3, 2, 8, 8), (1, 960, 5, 1, 4, 4)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_dwconv_gradients(N, C, k, s, H, W, dtype):
