@@ -29,6 +29,7 @@ SIGNATURES = {
     "cabinet_conv2d_simt": ([_p, _i, _ll, _ll, _ll, _ll, _ll, _p, _i, _ll, _ll, _ll, _p, _p, _ll, _p, _i, _ll, _ll,
                              _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p], _i),
     "cabinet_conv_tc": ([_p, _ll, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _ll, _p, _i, _ll, _i, _i, _i, _p], _i),
+    "cabinet_conv_tc_view": ([_p, _ll, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _ll, _i, _i, _ll, _ll, _ll, _p], _i),
     "cabinet_conv_tc_se": ([_p, _ll, _i, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p, _ll, _p, _i, _ll, _i, _i, _i,
                             _p], _i),
     "cabinet_conv_tc_split_act": ([_p, _ll, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _ll, _i, _i, _i, _i, _p], _i),
@@ -63,6 +64,7 @@ SIGNATURES = {
     "cabinet_ohem_workspace_bytes": ([], _ll),
     "cabinet_train_scratch_floats": ([_ll, _i, _i], _ll),
     "cabinet_pack_conv_weight": ([_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p], _i),
+    "cabinet_pack_conv_weight_parity": ([_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p], _i),
     "cabinet_pack_dw_weight": ([_p, _i, _i, _i, _p, _p], _i),
     "cabinet_im2col_nchw": ([_p, _i, _i, _i, _i, _i, _i, _i, _p, _ll, _p], _i),
     "cabinet_embed_filter": ([_p, _i, _i, _i, _i, _p, _ll, _i, _p], _i),

@@ -529,7 +529,15 @@ static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int C
                         const void* w_packed, long long w_image_stride, int Cout, int KH, int KW, int stride, int pad,
                         const float* bias, const void* res, long long ldres, void* y, int y_dtype, long long ldy,
                         int OH, int OW, int act, cabinet_stream_t stream, int act_cols = 1 << 30,
-                        const float* up = nullptr, int up_h = 0, int up_w = 0);
+                        const float* up = nullptr, int up_h = 0, int up_w = 0, long long y_sw = 1, long long y_sh = 0,
+                        long long y_sn = 0);
+
+extern "C" int cabinet_conv_tc_view(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_packed,
+                                    int Cout, int KH, int KW, int pad, const float* bias, void* y, long long ldy, int OH,
+                                    int OW, long long y_sw, long long y_sh, long long y_sn, cabinet_stream_t stream) {
+    return conv_tc_impl(x, ldx, N, H, W, Cin, nullptr, CABINET_ACT_NONE, w_packed, 0, Cout, KH, KW, 1, pad, bias, nullptr, 0,
+                        y, CABINET_BF16, ldy, OH, OW, CABINET_ACT_NONE, stream, 1 << 30, nullptr, 0, 0, y_sw, y_sh, y_sn);
+}
 
 extern "C" int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, int W, int Cin, const float* a_scale,
                                   int a_act, const void* w_packed, int Cout, int KH, int KW, int stride, int pad,
@@ -580,8 +588,13 @@ static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int C
                         const void* w_packed, long long w_image_stride, int Cout, int KH, int KW, int stride, int pad,
                         const float* bias, const void* res, long long ldres, void* y, int y_dtype, long long ldy,
                         int OH, int OW, int act, cabinet_stream_t stream, int act_cols, const float* up, int up_h,
-                        int up_w) {
+                        int up_w, long long y_sw, long long y_sh, long long y_sn) {
+    // y_sw / y_sh / y_sn (pixels): the output is a strided VIEW (pixel, row, image pitch) of a larger NHWC tensor -- e.g.
+    // one input-parity class of the data gradient of a stride-2 convolution.  Defaults: a dense [N][OH][OW] tensor.
     CAB_REQUIRE(x && w_packed && bias && y, "conv_tc: null pointer");
+    const bool out_view = y_sw != 1 || y_sh != 0 || y_sn != 0;
+    CAB_REQUIRE(!out_view || (y_dtype == CABINET_BF16 && !res && !up && y_sw >= 1 && y_sh >= OW && y_sn >= OH),
+                "conv_tc: a strided output view needs bf16 output and no residual");
     const int reverse = (act & CABINET_CONV_REVERSE_TILES) ? 1 : 0;
     act &= ~CABINET_CONV_REVERSE_TILES;
     CAB_REQUIRE(!up || (up_h > 0 && up_w > 0 && Cout % 16 == 0 && (reinterpret_cast<uintptr_t>(up) & 15) == 0 && !res &&
@@ -602,7 +615,7 @@ static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int C
     if (N == 0) return CABINET_OK;
 
     TcConvParams p;
-    const bool flat = KH == 1 && KW == 1 && stride == 1 && pad == 0;
+    const bool flat = KH == 1 && KW == 1 && stride == 1 && pad == 0 && !out_view;
     const int taps = KH * KW;
     p.Cin = Cin; p.Cout = Cout; p.KW = KW; p.stride = stride; p.pad = pad;
     p.cin_blocks = (Cin + BLOCK_K - 1) / BLOCK_K;
@@ -684,7 +697,8 @@ static int conv_tc_impl(const void* x, long long ldx, int N, int H, int W, int C
     if (y_dtype == CABINET_BF16) {
         // store map: {Cout (true extent: clips padded / foreign channels), OW, OH, N}, 64-channel boxes
         const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)p.OW, (uint64_t)p.OH, (uint64_t)Ng};
-        const uint64_t strides[3] = {(uint64_t)ldy * es, (uint64_t)ldy * es * p.OW, (uint64_t)ldy * es * p.OW * p.OH};
+        const uint64_t strides[3] = {(uint64_t)ldy * es * (uint64_t)y_sw, (uint64_t)ldy * es * (uint64_t)(y_sh ? y_sh : p.OW),
+                                     (uint64_t)ldy * es * (uint64_t)(y_sn ? y_sn : (long long)p.OW * p.OH)};
         const uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
         int rc = cab_make_tmap_bf16(&tmY, y, 4, dims, strides, box);
         if (rc) return rc;

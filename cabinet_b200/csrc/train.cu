@@ -224,10 +224,15 @@ template <typename T>
 __global__ void __launch_bounds__(RED_THREADS)
 bn_stats_v_kernel(const T* __restrict__ x, long long ldx, long long M, int C, long long rpb, float* __restrict__ partial) {
     constexpr int V = vec_n<T>();
+    float kv[V];      // the shift (row 0) of this thread's channel vector: loaded once per channel chunk
+    int kc = -1;
     col_reduce_block_v<2, V>(M, C, rpb, partial, [&](long long m, int c0, float* acc) {
-        float xv[V], kv[V];
+        if (c0 != kc) {
+            ldv(x + c0, kv);
+            kc = c0;
+        }
+        float xv[V];
         ldv(x + m * ldx + c0, xv);
-        ldv(x + c0, kv);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             const float d = xv[v] - kv[v];
@@ -243,17 +248,24 @@ bn_bwd_reduce_v_kernel(const T* __restrict__ dy, long long lddy, const T* __rest
                        const float* __restrict__ stats, int act, long long M, int C, long long rpb,
                        float* __restrict__ partial) {
     constexpr int V = vec_n<T>();
+    float mean[V], invstd[V], scale[V], shift[V];   // per-channel constants of this thread's vector, loaded once
+    int kc = -1;
     col_reduce_block_v<2, V>(M, C, rpb, partial, [&](long long m, int c0, float* acc) {
+        if (c0 != kc) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                mean[v] = stats[c0 + v]; invstd[v] = stats[C + c0 + v]; scale[v] = stats[2 * C + c0 + v]; shift[v] = stats[3 * C + c0 + v];
+            }
+            kc = c0;
+        }
         float zv[V], dv[V];
         ldv(z + m * ldz + c0, zv);
         ldv(dy + m * lddy + c0, dv);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            const int c = c0 + v;
-            const float u = fmaf(zv[v], __ldg(stats + 2 * C + c), __ldg(stats + 3 * C + c));
-            const float g = dv[v] * act_grad(u, act);
+            const float g = dv[v] * act_grad(fmaf(zv[v], scale[v], shift[v]), act);
             acc[v] += g;
-            acc[V + v] = fmaf(g, (zv[v] - __ldg(stats + c)) * __ldg(stats + C + c), acc[V + v]);
+            acc[V + v] = fmaf(g, (zv[v] - mean[v]) * invstd[v], acc[V + v]);
         }
     });
 }
@@ -475,6 +487,26 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
         float v = 0.f;
         if (co < Cout && ci < Cin) v = w[(static_cast<long long>(co) * Cin + ci) * taps + src_tap];
         out[i] = from_f32<TO>(v);
+    }
+}
+
+// Sub-filter of one input-parity class (py, px) of a stride-2 convolution's data gradient, transposed for cabinet_conv_tc:
+//   dx[2a+py][2b+px][ci] = sum_{jy, jx, co} dy[a - pad2 + jy][b - pad2 + jx][co] * w[co][ci][ky(jy)][kx(jx)],
+//   ky(j) = py + pad - 2 (j - pad2)   (taps outside [0, K) are zero)
+// out [rows_pad >= Cin][KH2 * KW2][k_pad >= Cout] bf16, zero padded.
+__global__ void pack_conv_weight_parity_kernel(const float* __restrict__ w, int Cout, int Cin, int K, int pad, int py, int px,
+                                               int KH2, int KW2, int pad2, int rows_pad, int k_pad, bf16* __restrict__ out) {
+    const long long total = static_cast<long long>(rows_pad) * KH2 * KW2 * k_pad;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(i % k_pad);
+        const long long t = i / k_pad;
+        const int tap = static_cast<int>(t % (KH2 * KW2)), ci = static_cast<int>(t / (KH2 * KW2));
+        const int jy = tap / KW2, jx = tap - jy * KW2;
+        const int ky = py + pad - 2 * (jy - pad2), kx = px + pad - 2 * (jx - pad2);
+        float v = 0.f;
+        if (co < Cout && ci < Cin && ky >= 0 && ky < K && kx >= 0 && kx < K) v = w[((static_cast<long long>(co) * Cin + ci) * K + ky) * K + kx];
+        out[i] = __float2bfloat16_rn(v);
     }
 }
 
@@ -1129,6 +1161,18 @@ extern "C" int cabinet_pack_conv_weight(const float* w_oihw, int Cout, int Cin, 
     else
         pack_conv_weight_kernel<bf16><<<ew_grid(total), 256, 0, s>>>(w_oihw, Cout, Cin, KH * KW, rows_pad, k_pad, transpose_flip,
                                                                       reinterpret_cast<bf16*>(out));
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_pack_conv_weight_parity(const float* w_oihw, int Cout, int Cin, int K, int pad, int py, int px, int KH2,
+                                               int KW2, int pad2, void* out, int rows_pad, int k_pad, cabinet_stream_t stream) {
+    CAB_REQUIRE(w_oihw && out && Cout > 0 && Cin > 0 && K > 0 && KH2 > 0 && KW2 > 0 && rows_pad >= Cin && k_pad >= Cout &&
+                    (py == 0 || py == 1) && (px == 0 || px == 1),
+                "pack_conv_weight_parity: bad arguments");
+    const long long total = static_cast<long long>(rows_pad) * KH2 * KW2 * k_pad;
+    pack_conv_weight_parity_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w_oihw, Cout, Cin, K, pad, py, px, KH2, KW2, pad2, rows_pad, k_pad, reinterpret_cast<bf16*>(out));
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

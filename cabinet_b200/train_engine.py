@@ -131,6 +131,7 @@ class TrainEngine:
         self.use_tc = precision == "bf16"   # tcgen05 / TMA kernels for the GEMM-shaped and depthwise layers
         self.wgrad_tc = True                # tcgen05 weight gradients (stride-1 "same" and stride-2 convolutions)
         self.stem_gemm = True               # both stems as 1x1 GEMMs on one bf16 im2col of the input
+        self.dgrad_s2_tc = True             # stride-2 data gradients as four parity-class conv_tc calls
         self._zero_cache: Dict[int, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ plumbing
@@ -264,11 +265,45 @@ class TrainEngine:
                            self._zeros(cin).data_ptr(), dx.ptr if acc else None, dx.ld if acc else 0, dx.ptr, dx.dt, dx.ld,
                            H, W, ACT_NONE)
                 return
+            if (self.use_tc and self.dgrad_s2_tc and stride == 2 and kh == kw and not acc and self._tc_ok(dy)
+                    and self._tc_ok(dx) and H >= 2 and W >= 2 and self._parity_pads(kh, pad) is not None):
+                # stride 2: four input-parity classes, each the stride-1 convolution of dy with a sub-filter, written
+                # through a strided view of dx (cabinet_conv_tc_view)
+                r16, k64 = -(-cin // 16) * 16, -(-cout // 64) * 64
+                for py in range(2):
+                    for px in range(2):
+                        (kh2, pad2), (kw2, padx2) = self._parity_geom(kh, pad, py), self._parity_geom(kw, pad, px)
+                        hc, wc = (H - py + 1) // 2, (W - px + 1) // 2
+                        if hc == 0 or wc == 0:
+                            continue
+                        wt = torch.empty((r16, kh2 * kw2, k64), dtype=torch.bfloat16, device=self.dev)
+                        self._call("cabinet_pack_conv_weight_parity", w.data_ptr(), cout, cin, kh, pad, py, px, kh2, kw2, pad2,
+                                   wt.data_ptr(), r16, k64)
+                        view = dx.ptr + (py * W + px) * dx.ld * 2
+                        self._call("cabinet_conv_tc_view", dy.ptr, dy.ld, N, OH, OW, cout, wt.data_ptr(), cin, kh2, kw2, pad2,
+                                   self._zeros(cin).data_ptr(), view, dx.ld, hc, wc, 2, 2 * W, H * W)
+                return
             self._call("cabinet_conv_dgrad", dy.ptr, dy.ld, dy.dt, wp.data_ptr(), wdt, w_sco, w_stap, dx.ptr, dx.ld, N, H, W,
                        cin, cout, kh, kw, stride, pad, OH, OW, acc)
 
         self.tape.append(backward)
         return out
+
+    @staticmethod
+    def _parity_geom(k: int, pad: int, par: int):
+        """(taps, pad) of the stride-1 sub-convolution that yields the input rows of parity ``par`` of a stride-2
+        convolution's data gradient: row 2a + par meets ky = par + pad - 2 off, off = dy row - a."""
+        offs = [(par + pad - ky) // 2 for ky in range(k) if (par + pad - ky) % 2 == 0]
+        if not offs:
+            return 1, 0   # no tap of this parity: a 1-tap sub-filter of zeros
+        return max(offs) - min(offs) + 1, -min(offs)
+
+    @classmethod
+    def _parity_pads(cls, k: int, pad: int):
+        """cabinet_conv_tc takes ONE padding for both axes: usable when both parities need the same one (3x3 / pad 1 and
+        7x7 / pad 3 do; 5x5 / pad 2 does not) -> that padding, else None."""
+        p0, p1 = cls._parity_geom(k, pad, 0)[1], cls._parity_geom(k, pad, 1)[1]
+        return p0 if p0 == p1 else None
 
     STEM_K, STEM_LD = 7, 152   # im2col footprint of the stems: 3 x 7 x 7 = 147 columns, pixel stride padded to 8
 

@@ -85,6 +85,14 @@ int cabinet_conv_tc(const void* x, long long ldx, int N, int H, int W, int Cin, 
                     int KH, int KW, int stride, int pad, const float* bias, const void* res, long long ldres,
                     void* y, int y_dtype, long long ldy, int OH, int OW, int act, cabinet_stream_t stream);
 
+/* cabinet_conv_tc (stride 1, no activation / residual, bf16) writing a strided VIEW of a larger NHWC tensor: output pixel
+ * (n, oh, ow) lands at y + ((n * y_sn) + oh * y_sh + ow * y_sw) * ldy (pitches in pixels).  With the sub-filters of
+ * cabinet_pack_conv_weight_parity, four calls (one per input parity) are the data gradient of a stride-2 convolution
+ * on the tensor cores (backward of sb.conv2 / sb.conv3, src/models/cabinet.py:112-113). */
+int cabinet_conv_tc_view(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_packed, int Cout, int KH,
+                         int KW, int pad, const float* bias, void* y, long long ldy, int OH, int OW, long long y_sw,
+                         long long y_sh, long long y_sn, cabinet_stream_t stream);
+
 /* cabinet_conv_tc with the squeeze-excite apply fused in front (A-operand prologue): the GEMM consumes
  * act(x[n][p][c] * a_scale[n][c]) (a_scale fp32 [N][Cin]) without that tensor ever being written:
  * SELayer's x * y (src/models/mobilenetv3.py:83) and the activation that follows it (:143) run in shared memory
@@ -329,6 +337,11 @@ long long cabinet_train_scratch_floats(long long M, int C, int nq);
 int cabinet_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int KH, int KW, void* out, int out_dtype,
                              int rows_pad, int k_pad, int transpose_flip, cabinet_stream_t stream);
 int cabinet_pack_dw_weight(const float* w, int C, int k, int flip, float* out, cabinet_stream_t stream);
+/* Sub-filter of the input-parity class (py, px) of a stride-2 convolution's data gradient, transposed for cabinet_conv_tc:
+ * out bf16 [rows_pad >= Cin][KH2*KW2][k_pad >= Cout]; tap (jy, jx) holds w[co][ci][py + pad - 2 (jy - pad2)][px + pad - 2 (jx - pad2)]
+ * (zero outside the filter): dx[2a+py][2b+px] = conv(dy, out, pad2)[a][b]. */
+int cabinet_pack_conv_weight_parity(const float* w_oihw, int Cout, int Cin, int K, int pad, int py, int px, int KH2, int KW2,
+                                    int pad2, void* out, int rows_pad, int k_pad, cabinet_stream_t stream);
 
 /* im2col of the fp32 NCHW network input for the stem convolutions (sb.conv1 7x7 s2 p3, src/models/cabinet.py:111; backbone
  * stem 3x3 s2 p1 = the centre of the same footprint, src/models/mobilenetv3.py:86-91): out bf16 [N*OH*OW][ld], column

@@ -165,6 +165,40 @@ def test_conv_wgrad_tensor_core(N, cin, cout, k, H, W, ldx_extra, stride):
     assert e < 1e-5   # exact products of bf16 values, fp32 accumulation
 
 
+@pytest.mark.parametrize("N,cin,cout,k,pad,H,W", [(2, 64, 64, 3, 1, 32, 24), (1, 64, 64, 3, 1, 17, 13), (2, 24, 40, 7, 3, 20, 22)])
+def test_stride2_dgrad_as_parity_conv_tc(N, cin, cout, k, pad, H, W):
+    """Data gradient of a stride-2 convolution = four stride-1 tensor-core convolutions of dy (one per input parity) with
+    sub-filters, each written through a strided view of dx."""
+    from cabinet_b200.train_engine import TrainEngine
+
+    lib = _lib.load()
+    x = gen(N, cin, H, W, seed=1).requires_grad_(True)
+    w = q(gen(cout, cin, k, k, seed=2, scale=(cin * k * k) ** -0.5), torch.bfloat16).requires_grad_(True)
+    y = F.conv2d(x, w, None, 2, pad)
+    dy = q(gen(*y.shape, seed=3), torch.bfloat16)
+    y.backward(dy)
+    OH, OW = y.shape[2:]
+    assert TrainEngine._parity_pads(k, pad) is not None
+    dyd, wd = nhwc(dy, torch.bfloat16), w.detach().cuda()
+    dx = torch.full((N, H, W, cin), 5.0, dtype=torch.bfloat16, device="cuda")
+    zeros = torch.zeros(cin, device="cuda")
+    r16, k64 = -(-cin // 16) * 16, -(-cout // 64) * 64
+    for py in range(2):
+        for px in range(2):
+            (kh2, pad2), (kw2, _) = TrainEngine._parity_geom(k, pad, py), TrainEngine._parity_geom(k, pad, px)
+            hc, wc = (H - py + 1) // 2, (W - px + 1) // 2
+            wt = torch.empty(r16, kh2 * kw2, k64, dtype=torch.bfloat16, device="cuda")
+            check(lib.cabinet_pack_conv_weight_parity(wd.data_ptr(), cout, cin, k, pad, py, px, kh2, kw2, pad2, wt.data_ptr(),
+                                                      r16, k64, stream()), "pack_parity")
+            check(lib.cabinet_conv_tc_view(dyd.data_ptr(), cout, N, OH, OW, cout, wt.data_ptr(), cin, kh2, kw2, pad2,
+                                           zeros.data_ptr(), dx.data_ptr() + (py * W + px) * cin * 2, cin, hc, wc, 2, 2 * W,
+                                           H * W, stream()), "conv_tc_view")
+    torch.cuda.synchronize()
+    e = rel_l2(nchw(dx), x.grad)
+    print(f"stride-2 dgrad {cout}->{cin} k{k} {N}x{H}x{W}: rel_l2 {e:.2e}")
+    assert e < 4e-3   # bf16 output rounding
+
+
 @pytest.mark.parametrize("N,H,W", [(2, 20, 24), (1, 17, 13), (2, 64, 48)])
 def test_stem_im2col_and_embedded_filter(N, H, W):
     """im2col of the NCHW input over the 7x7/s2/p3 footprint: the 7x7 stem AND the 3x3/s2/p1 stem (centre of the footprint)
