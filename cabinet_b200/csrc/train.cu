@@ -83,7 +83,7 @@ template <typename T> __host__ __device__ constexpr int vec_n() { return sizeof(
 
 // Vectorised form of col_reduce_block: a thread owns one 16-byte channel vector (V channels) of a pixel lane.
 // f(m, c0, acc[NQ * V]) accumulates quantity q of channel c0 + v into acc[q * V + v].  C % V == 0.
-template <int NQ, int V, typename F>
+template <int NQ, int V, bool UNROLL2 = true, typename F>
 __device__ __forceinline__ void col_reduce_block_v(long long M, int C, long long rows_per_block, float* __restrict__ partial,
                                                    F f) {
     extern __shared__ float s_red[];  // [lanes][NQ][cw]
@@ -97,7 +97,10 @@ __device__ __forceinline__ void col_reduce_block_v(long long M, int C, long long
         float acc[NQ * V];
 #pragma unroll
         for (int q = 0; q < NQ * V; ++q) acc[q] = 0.f;
-        if (lane < lanes) {
+        if (!UNROLL2) {
+            if (lane < lanes)
+                for (long long m = m0 + lane; m < m1; m += lanes) f(m, (v0 + cv) * V, acc);
+        } else if (lane < lanes) {
             // two independent accumulator sets / rows in flight per thread (fixed pairing: still deterministic)
             float acc2[NQ * V];
 #pragma unroll
@@ -960,6 +963,60 @@ dw_wgrad_v2_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict
     });
 }
 
+// Line-walking variant: one thread = one output line (n, oy) x one channel pair; it slides a K x K register window of x
+// along the line, so a step costs K * S new 4-byte loads instead of K * K (and no per-pixel index arithmetic).
+template <typename T, int KK, int S>
+__global__ void __launch_bounds__(RED_THREADS)
+dw_wgrad_line_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx, int H, int W, int C,
+                     int OH, int OW, long long n_lines, long long rpb, float* __restrict__ partial) {
+    constexpr int K = KK;
+    constexpr int pad = (K - 1) / 2;
+    col_reduce_block_v<K * K, 2, false>(n_lines, C, rpb, partial, [&](long long line, int c0, float* acc) {
+        const unsigned lu = static_cast<unsigned>(line);
+        const int oy = static_cast<int>(lu % static_cast<unsigned>(OH)), n = static_cast<int>(lu / static_cast<unsigned>(OH));
+        const T* xrow[K];
+        bool rv[K];
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const int iy = oy * S - pad + ky;
+            rv[ky] = iy >= 0 && iy < H;
+            xrow[ky] = x + (static_cast<long long>(n) * H + (rv[ky] ? iy : 0)) * W * ldx + c0;
+        }
+        float2 win[K][K];
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const int ix = kx - pad;
+                win[ky][kx] = (rv[ky] && ix >= 0 && ix < W) ? ld2(xrow[ky] + static_cast<long long>(ix) * ldx) : make_float2(0.f, 0.f);
+            }
+        const T* dyp = dy + line * OW * lddy + c0;
+        for (int ox = 0; ox < OW; ++ox) {
+            const float2 g = ld2(dyp + static_cast<long long>(ox) * lddy);
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    acc[(ky * K + kx) * 2] = fmaf(g.x, win[ky][kx].x, acc[(ky * K + kx) * 2]);
+                    acc[(ky * K + kx) * 2 + 1] = fmaf(g.y, win[ky][kx].y, acc[(ky * K + kx) * 2 + 1]);
+                }
+            if (ox + 1 < OW) {
+#pragma unroll
+                for (int ky = 0; ky < K; ++ky) {
+#pragma unroll
+                    for (int kx = 0; kx + S < K; ++kx) win[ky][kx] = win[ky][kx + S];
+#pragma unroll
+                    for (int j = 0; j < S; ++j) {
+                        if (K - S + j < 0) continue;
+                        const int ix = (ox + 1) * S - pad + K - S + j;
+                        win[ky][K - S + j] = (rv[ky] && ix >= 0 && ix < W) ? ld2(xrow[ky] + static_cast<long long>(ix) * ldx) : make_float2(0.f, 0.f);
+                    }
+                }
+            }
+        }
+    });
+}
+
 // dW ([C][1][k][k]) += sum_b partial[b][tap][c]: one warp per output (lane l adds blocks l, l + 32, ... then a fixed
 // butterfly: deterministic)
 __global__ void dw_wgrad_finalize_kernel(const float* __restrict__ partial, int nb, int C, int taps, float* __restrict__ dw) {
@@ -1481,6 +1538,39 @@ extern "C" int cabinet_dwconv_wgrad(const void* dy, long long lddy, const void* 
     long long rpb;
     const int nb = red_blocks(M, &rpb);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (C % 2 == 0 && lddy % 2 == 0 && ldx % 2 == 0 && (reinterpret_cast<uintptr_t>(dy) & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
+        (stride == 1 || stride == 2) && OW >= 8 &&
+        cab_ceil_div(static_cast<long long>(N) * OH, 2LL * (RED_THREADS / std::min(RED_THREADS, C / 2))) <= nb) {
+        // line walker: a block reduces 2 lines per pixel lane (its partial rows fit the scratch sized for `nb` blocks)
+        const long long n_lines = static_cast<long long>(N) * OH;
+        const int cwv = std::min(RED_THREADS, C / 2), lanes = RED_THREADS / cwv;
+        const long long rpb2 = 2LL * lanes;
+        const int nb2 = static_cast<int>(cab_ceil_div(n_lines, rpb2));
+        const size_t smem2 = RED_THREADS * 2 * k * k * sizeof(float);
+        static bool attr_done = false;
+        if (!attr_done) {
+            CAB_CUDA(cudaFuncSetAttribute(dw_wgrad_line_kernel<float, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            CAB_CUDA(cudaFuncSetAttribute(dw_wgrad_line_kernel<float, 5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            CAB_CUDA(cudaFuncSetAttribute(dw_wgrad_line_kernel<bf16, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            CAB_CUDA(cudaFuncSetAttribute(dw_wgrad_line_kernel<bf16, 5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            attr_done = true;
+        }
+#define CAB_DWL(T, KK, SS)                                                                                                     \
+    dw_wgrad_line_kernel<T, KK, SS><<<nb2, RED_THREADS, smem2, s>>>(reinterpret_cast<const T*>(dy), lddy, reinterpret_cast<const T*>(x), \
+                                                                    ldx, H, W, C, OH, OW, n_lines, rpb2, scratch)
+#define CAB_DWL2(T)                                                                                 \
+    do {                                                                                            \
+        if (k == 3 && stride == 1) CAB_DWL(T, 3, 1); else if (k == 3) CAB_DWL(T, 3, 2);             \
+        else if (stride == 1) CAB_DWL(T, 5, 1); else CAB_DWL(T, 5, 2);                              \
+    } while (0)
+        if (dtype == CABINET_F32) CAB_DWL2(float); else CAB_DWL2(bf16);
+#undef CAB_DWL2
+#undef CAB_DWL
+        CAB_LAUNCH_CHECK();
+        dw_wgrad_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(C * k * k, 8)), 256, 0, s>>>(scratch, nb2, C, k * k, dw);
+        CAB_LAUNCH_CHECK();
+        return CABINET_OK;
+    }
     if (C % 2 == 0 && lddy % 2 == 0 && ldx % 2 == 0 && (reinterpret_cast<uintptr_t>(dy) & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0) {
         const size_t smem2 = RED_THREADS * 2 * k * k * sizeof(float);
         static bool attr_done = false;
