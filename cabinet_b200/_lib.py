@@ -36,6 +36,7 @@ SIGNATURES = {
     "cabinet_conv_tc_imgw": ([_p, _ll, _i, _i, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _p, _p, _ll, _p, _i, _ll, _i, _i, _i,
                               _p], _i),
     "cabinet_conv_tc_up": ([_p, _ll, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _ll, _i, _i, _i, _p], _i),
+    "cabinet_gate_scale_weights": ([_p, _i, _f, _p, _p, _p, _p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p], _i),
     "cabinet_scale_weights": ([_p, _p, _p, _i, _i, _i, _i, _i, _i, _p], _i),
     "cabinet_stem_tc": ([_p, _i, _i, _i, _p, _p, _p, _ll, _p, _ll, _i, _i, _p], _i),
     "cabinet_dwconv": ([_p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p], _i),

@@ -391,6 +391,83 @@ scale_weights_kernel(const bf16* __restrict__ w, const float* __restrict__ scale
 }
 }  // namespace
 
+namespace {
+// Gate MLP + per-image weight scaling in ONE launch (the squeeze-excite gate of a ReLU block folded into its project conv,
+// the FFM attention folded into the head conv): every block recomputes the (tiny) two-layer gate of its image in shared
+// memory -- C x J multiply-adds, a few microseconds hidden behind the other blocks -- then scales its slice of the weights:
+//   out[n][r][k] = bf16(w[r][k] * (gate[n][k % cin_pad] + plus)),  gate = act(W2 relu(W1 mean + b1) + b2)
+// Replaces gate_fc -> gate_fc -> scale_weights (three dependent launches on the critical path).
+constexpr int GSW_ELEMS = 8192;  // weight elements per block
+__global__ void __launch_bounds__(256)
+gate_scale_weights_kernel(const void* __restrict__ gap, int in_fixed, float inv_hw, const float* __restrict__ w1,
+                          const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int gate,
+                          int C, int J, const bf16* __restrict__ w, bf16* __restrict__ out, unsigned per_image, unsigned cin_pad,
+                          float plus) {
+    extern __shared__ float sm[];  // mean[C] | hidden[J] | gate[C]
+    float* mean = sm;
+    float* hidden = sm + C;
+    float* g = hidden + J;
+    const int n = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (in_fixed) {
+        const long long* fx = reinterpret_cast<const long long*>(gap) + static_cast<long long>(n) * C;
+        for (int c = threadIdx.x; c < C; c += 256) mean[c] = __ll2float_rn(__ldg(fx + c)) * (inv_hw * (1.0f / CABINET_GAP_FIXED_ONE));
+    } else {
+        const float* fp = reinterpret_cast<const float*>(gap) + static_cast<long long>(n) * C;
+        for (int c = threadIdx.x; c < C; c += 256) mean[c] = __ldg(fp + c) * inv_hw;
+    }
+    __syncthreads();
+    for (int j = warp; j < J; j += 8) {
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(w1 + static_cast<long long>(j) * C + c), mean[c], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) hidden[j] = fmaxf(acc + (b1 ? b1[j] : 0.f), 0.f);
+    }
+    __syncthreads();
+    for (int c = warp; c < C; c += 8) {
+        float acc = 0.f;
+        for (int j = lane; j < J; j += 32) acc = fmaf(__ldg(w2 + static_cast<long long>(c) * J + j), hidden[j], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) g[c] = cab_act(acc + (b2 ? b2[c] : 0.f), gate) + plus;
+    }
+    __syncthreads();
+    const unsigned base = blockIdx.x * GSW_ELEMS;
+    for (unsigned i = base + threadIdx.x * 8u; i < min(base + GSW_ELEMS, per_image); i += 256u * 8u) {
+        const int ci = static_cast<int>(i % cin_pad);
+        Vec16<bf16> v;
+        v.load(w + i);
+        float f[8];
+        v.unpack(f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = (ci + k < C) ? f[k] * g[ci + k] : 0.f;
+        v.pack(f);
+        v.store(out + static_cast<size_t>(n) * per_image + i);
+    }
+}
+}  // namespace
+
+extern "C" int cabinet_gate_scale_weights(const void* gap_sum, int in_fixed, float inv_hw, const float* w1, const float* b1,
+                                          const float* w2, const float* b2, int gate, int C, int Cmid, const void* w_packed,
+                                          void* out, int N, int rows, int taps, int cin_pad, int plus_one,
+                                          cabinet_stream_t stream) {
+    CAB_REQUIRE(gap_sum && w1 && w2 && w_packed && out && C > 0 && Cmid > 0 && rows > 0 && taps > 0 && cin_pad % 8 == 0 &&
+                    C <= cin_pad && C <= 1024 && Cmid <= 1024 && N <= 65535,
+                "gate_scale_weights: bad arguments");
+    CAB_REQUIRE((reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "gate_scale_weights: alignment");
+    if (N == 0) return CABINET_OK;
+    const long long per_image = static_cast<long long>(rows) * taps * cin_pad;
+    CAB_REQUIRE(per_image < (1LL << 31), "gate_scale_weights: weight matrix too large");
+    dim3 grid(static_cast<unsigned>(cab_ceil_div(per_image, GSW_ELEMS)), N);
+    gate_scale_weights_kernel<<<grid, 256, (2 * C + Cmid) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        gap_sum, in_fixed, inv_hw, w1, b1, w2, b2, gate, C, Cmid, reinterpret_cast<const bf16*>(w_packed),
+        reinterpret_cast<bf16*>(out), static_cast<unsigned>(per_image), static_cast<unsigned>(cin_pad), plus_one ? 1.f : 0.f);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
 extern "C" int cabinet_scale_weights(const void* w_packed, const float* scale, void* out, int N, int rows, int taps,
                                      int cin_pad, int Cin, int plus_one, cabinet_stream_t stream) {
     CAB_REQUIRE(w_packed && scale && out && rows > 0 && taps > 0 && cin_pad > 0 && cin_pad % 8 == 0 && Cin > 0 && Cin <= cin_pad,

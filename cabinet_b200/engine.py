@@ -515,6 +515,16 @@ class Engine:
                   G.c, G.gate, 0, self.stream)
         return scale
 
+    def gate_scale_weights(self, gap: torch.Tensor, fixed: bool, hw: int, G: GateLayer, w_tc: torch.Tensor, wimg: torch.Tensor,
+                           cin: int, plus_one: bool, name: str):
+        """Gate MLP + per-image copies of a conv_tc weight pack scaled by (gate + plus_one), one launch."""
+        n = wimg.shape[0]
+        self._run("gate_scale_weights", name, wimg.numel() * 2 + (G.w1.numel() + G.w2.numel()) * 4, 4 * n * G.c * G.cmid,
+                  self.lib.cabinet_gate_scale_weights, gap.data_ptr(), int(fixed), 1.0 / hw, G.w1.data_ptr(),
+                  G.b1.data_ptr() if G.b1 is not None else None, G.w2.data_ptr(),
+                  G.b2.data_ptr() if G.b2 is not None else None, G.gate, G.c, G.cmid, w_tc.data_ptr(), wimg.data_ptr(), n,
+                  w_tc.shape[0], w_tc.shape[1], w_tc.shape[2], int(plus_one), self.stream)
+
     def scale_act(self, x: Map, scale: torch.Tensor, act: int, name: str, plus_one: bool = False):
         # not in the per-layer-fusion byte model (SE scale / FFM gate are "free riders" there): counted as 0 algorithmic
         self._run("scale_act", name, 0, 0, self.lib.cabinet_scale_act, x.ptr, x.ld, x.dt, scale.data_ptr(), x.N,
@@ -672,13 +682,10 @@ class Engine:
                     gap = gap_all[2 * gi:2 * gi + 2].view(-1)[: 2 * N * s["exp"]]
                     d, gap_fixed = self.dwconv(h, e["dw"], gap)
                 gi += 1
-                scale = self.gate(gap.view(N, -1), d.H * d.W, e["se"], e["dw"].name, gap_fixed)
                 if fuse and fold_se:
                     pw2 = e["pw2"]
                     wimg = torch.empty((N,) + tuple(pw2.tc.shape), dtype=torch.bfloat16, device=dev)
-                    self._run("scale_weights", e["dw"].name, wimg.numel() * 2, 0, self.lib.cabinet_scale_weights,
-                              pw2.tc.data_ptr(), scale.data_ptr(), wimg.data_ptr(), N, pw2.tc.shape[0], 1, pw2.tc.shape[2],
-                              pw2.cin, 0, self.stream)
+                    self.gate_scale_weights(gap, gap_fixed, d.H * d.W, e["se"], pw2.tc, wimg, pw2.cin, False, e["dw"].name)
                     o = self.new(N, d.H, d.W, pw2.cout)
                     M = N * d.H * d.W
                     res = f if s["identity"] else None
@@ -689,6 +696,7 @@ class Engine:
                               d.H, d.W, ACT_NONE, self.stream)
                     f = o
                     continue
+                scale = self.gate(gap.view(N, -1), d.H * d.W, e["se"], e["dw"].name, gap_fixed)
                 # expand form: SE then activation; no-expand form: activation (already applied) then SE (F10)
                 se_act = e["act"] if s["expand"] else ACT_NONE
                 pw2 = e["pw2"]
@@ -772,16 +780,14 @@ class Engine:
             ff = self.conv(cat_ffm, self.ffm_blk)
         gap = gap_all[2 * n_se].view(-1)[: N * 256].view(N, 256)
         self.channel_sum(ff, gap, "ffm.gap", ffm_scratch)
-        att = self.gate(gap, H8 * W8, self.ffm_gate, "ffm.gate")
         hcl = self.head_conv
         if (self.fold_ffm and self.use_tc and not self.debug and hcl.tc is not None and ff.dt == BF16
                 and hcl.kh * hcl.kw > 1):
             # feat * atten + feat is a per-(image, channel) scale of the head conv's INPUT: fold it into per-image
-            # copies of the head weights (19 MB) instead of rewriting the 134 MB feature map
+            # copies of the head weights (19 MB) instead of rewriting the 134 MB feature map; the gate MLP runs inside
+            # the same launch
             wimg = torch.empty((N,) + tuple(hcl.tc.shape), dtype=torch.bfloat16, device=dev)
-            self._run("scale_weights", "ffm.gate", wimg.numel() * 2, 0, self.lib.cabinet_scale_weights, hcl.tc.data_ptr(),
-                      att.data_ptr(), wimg.data_ptr(), N, hcl.tc.shape[0], hcl.tc.shape[1], hcl.tc.shape[2], hcl.cin, 1,
-                      self.stream)
+            self.gate_scale_weights(gap, False, H8 * W8, self.ffm_gate, hcl.tc, wimg, hcl.cin, True, "ffm.gate")
             hc = self.new(N, H8, W8, hcl.cout)
             M = N * H8 * W8
             self._run("conv_tc", hcl.name, (M * (hcl.cin + hcl.cout) + wimg.numel()) * 2,
@@ -789,6 +795,7 @@ class Engine:
                       ff.C, wimg.data_ptr(), hcl.tc[0].numel() * hcl.tc.shape[0], hcl.cout, hcl.kh, hcl.kw, hcl.stride,
                       hcl.pad, hcl.b.data_ptr(), None, 0, hc.ptr, hc.dt, hc.ld, H8, W8, hcl.act, self.stream)
         else:
+            att = self.gate(gap, H8 * W8, self.ffm_gate, "ffm.gate")
             self.scale_act(ff, att, ACT_NONE, "ffm.gate", plus_one=True)
             hc = self.conv(ff, hcl)
 

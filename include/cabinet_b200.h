@@ -170,6 +170,15 @@ int cabinet_conv_tc_imgw(const void* x, long long ldx, int N, int H, int W, int 
 int cabinet_scale_weights(const void* w_packed, const float* scale, void* out, int N, int rows, int taps, int cin_pad,
                           int Cin, int plus_one, cabinet_stream_t stream);
 
+/* cabinet_gate_fc x 2 + cabinet_scale_weights in ONE launch: every block recomputes the gate of its image
+ *   gate[n][c] = act(b2 + W2 relu(b1 + W1 (sum[n] * inv_hw)))     (SELayer.fc, mobilenetv3.py:68-83; FFM conv1/conv2,
+ *                                                                    cabinet.py:146-150)
+ * in shared memory and writes out[n][r][t][c] = bf16(w[r][t][c] * (gate[n][c] + plus_one)).  gap_sum: fp32 [N][C], or the
+ * int64 fixed-point sums of the depthwise kernels (in_fixed != 0).  C <= cin_pad, C, Cmid <= 1024. */
+int cabinet_gate_scale_weights(const void* gap_sum, int in_fixed, float inv_hw, const float* w1, const float* b1,
+                               const float* w2, const float* b2, int gate, int C, int Cmid, const void* w_packed, void* out,
+                               int N, int rows, int taps, int cin_pad, int plus_one, cabinet_stream_t stream);
+
 /* Fused inverted-residual block with expansion (src/models/mobilenetv3.py:126-159), bf16 NHWC, Cin <= 64:
  *   h = act_expand(W_e * x + b_e)            1x1 expand + BN + act          (mobilenetv3.py:128-131)
  *   d = act_dw(dw_kxk(h) + b_dw)             depthwise + BN                 (mobilenetv3.py:132-141)

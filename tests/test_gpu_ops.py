@@ -590,6 +590,34 @@ def test_mbconv_fused_dw_out(cin, cexp, k, s, H, W, act, act_dw):
     assert float((ym.t.float()[..., cexp:] - 7.0).abs().max()) == 0
 
 
+@pytest.mark.parametrize("C,J,gate,bias,fixed,plus,taps", [(120, 32, ACT_HSIGMOID, True, True, False, 1),
+                                                          (256, 64, ACT_SIGMOID, False, False, True, 9),
+                                                          (72, 24, ACT_HSIGMOID, True, True, False, 1)])
+def test_gate_scale_weights(C, J, gate, bias, fixed, plus, taps):
+    """gate MLP + per-image weight scaling in one launch == gate_fc x 2 + scale_weights."""
+    lib = _lib.load()
+    N, HW, rows = 3, 77, 48
+    cin_pad = -(-C // 64) * 64
+    sums = gen(N, C, seed=1) * HW
+    w1, w2 = gen(J, C, seed=2, scale=C ** -0.5), gen(C, J, seed=3, scale=J ** -0.5)
+    b1, b2 = (gen(J, seed=4, scale=0.1), gen(C, seed=5, scale=0.5)) if bias else (None, None)
+    g = act_ref(F.linear(F.relu(F.linear(sums / HW, w1, b1)), w2, b2), gate) + (1.0 if plus else 0.0)
+    w = torch.zeros(rows, taps, cin_pad)
+    w[:, :, :C] = gen(rows, taps, C, seed=6)
+    wq = w.to(torch.bfloat16)
+    ref = (wq.float()[None] * F.pad(g, (0, cin_pad - C))[:, None, None, :]).to(torch.bfloat16)
+    d = lambda t: None if t is None else t.cuda()  # noqa: E731
+    gap = (sums.double() * 2.0 ** 24).round().to(torch.int64).cuda() if fixed else sums.cuda()
+    w1d, w2d, b1d, b2d, wd = d(w1), d(w2), d(b1), d(b2), wq.cuda()
+    out = torch.full((N, rows, taps, cin_pad), 3.0, dtype=torch.bfloat16, device="cuda")
+    check(lib.cabinet_gate_scale_weights(gap.data_ptr(), int(fixed), 1.0 / HW, w1d.data_ptr(), b1d.data_ptr() if bias else None,
+                                         w2d.data_ptr(), b2d.data_ptr() if bias else None, gate, C, J, wd.data_ptr(),
+                                         out.data_ptr(), N, rows, taps, cin_pad, int(plus), stream()), "gate_scale_weights")
+    torch.cuda.synchronize()
+    assert rel_l2(out.float().cpu(), ref.float()) < 3e-3
+    assert float(out[..., C:].abs().max()) == 0
+
+
 def test_conv_tc_per_image_weights():
     """conv(x * (1 + a_n), W) == conv(x, W * (1 + a_n)): cabinet_scale_weights + cabinet_conv_tc_imgw vs torch."""
     lib = _lib.load()
