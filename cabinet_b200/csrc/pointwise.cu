@@ -397,18 +397,45 @@ namespace {
 // memory -- C x J multiply-adds, a few microseconds hidden behind the other blocks -- then scales its slice of the weights:
 //   out[n][r][k] = bf16(w[r][k] * (gate[n][k % cin_pad] + plus)),  gate = act(W2 relu(W1 mean + b1) + b2)
 // Replaces gate_fc -> gate_fc -> scale_weights (three dependent launches on the critical path).
-constexpr int GSW_ELEMS = 8192;  // weight elements per block
+constexpr int GSW_ELEMS = 65536;  // weight elements per block (each block re-reads the gate weights: keep the grid small)
+
+// out[o] = act(b[o] + sum_i W[o][i] * in[i]) + plus for one block of 256 threads, inputs / outputs in shared memory.
+// 256 / O threads share an output (interleaved i, so a group reads consecutive weights), every thread's loads are
+// independent of each other (all in flight at once: the layer costs about one L2 round trip); the group's partial sums are
+// added in a fixed order.  Ends with a barrier.
+__device__ __forceinline__ void fc_block(const float* __restrict__ W, const float* __restrict__ b, const float* in, float* out,
+                                         float* red, int O, int I, int act, float plus) {
+    int parts = 1;
+    while (parts * 2 * O <= 256 && parts * 2 <= 32) parts *= 2;
+    for (int o0 = 0; o0 < O; o0 += 256 / parts) {
+        const int o = o0 + threadIdx.x / parts, part = threadIdx.x % parts;
+        float acc = 0.f;
+        if (o < O) {
+            const float* wr = W + static_cast<long long>(o) * I;
+#pragma unroll 8
+            for (int i = part; i < I; i += parts) acc = fmaf(__ldg(wr + i), in[i], acc);
+        }
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        if (o < O && part == 0) {
+            float sum = 0.f;
+            for (int k = 0; k < parts; ++k) sum += red[threadIdx.x + k];
+            out[o] = cab_act(sum + (b ? b[o] : 0.f), act) + plus;
+        }
+        __syncthreads();
+    }
+}
 __global__ void __launch_bounds__(256)
 gate_scale_weights_kernel(const void* __restrict__ gap, int in_fixed, float inv_hw, const float* __restrict__ w1,
                           const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int gate,
                           int C, int J, const bf16* __restrict__ w, bf16* __restrict__ out, unsigned per_image, unsigned cin_pad,
                           float plus) {
-    extern __shared__ float sm[];  // mean[C] | hidden[J] | gate[C]
+    extern __shared__ float sm[];  // mean[C] | hidden[J] | gate[C] | red[256]
     float* mean = sm;
     float* hidden = sm + C;
     float* g = hidden + J;
+    float* red = g + C;
     const int n = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (in_fixed) {
         const long long* fx = reinterpret_cast<const long long*>(gap) + static_cast<long long>(n) * C;
         for (int c = threadIdx.x; c < C; c += 256) mean[c] = __ll2float_rn(__ldg(fx + c)) * (inv_hw * (1.0f / CABINET_GAP_FIXED_ONE));
@@ -417,22 +444,8 @@ gate_scale_weights_kernel(const void* __restrict__ gap, int in_fixed, float inv_
         for (int c = threadIdx.x; c < C; c += 256) mean[c] = __ldg(fp + c) * inv_hw;
     }
     __syncthreads();
-    for (int j = warp; j < J; j += 8) {
-        float acc = 0.f;
-        for (int c = lane; c < C; c += 32) acc = fmaf(__ldg(w1 + static_cast<long long>(j) * C + c), mean[c], acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) hidden[j] = fmaxf(acc + (b1 ? b1[j] : 0.f), 0.f);
-    }
-    __syncthreads();
-    for (int c = warp; c < C; c += 8) {
-        float acc = 0.f;
-        for (int j = lane; j < J; j += 32) acc = fmaf(__ldg(w2 + static_cast<long long>(c) * J + j), hidden[j], acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) g[c] = cab_act(acc + (b2 ? b2[c] : 0.f), gate) + plus;
-    }
-    __syncthreads();
+    fc_block(w1, b1, mean, hidden, red, J, C, CABINET_ACT_RELU, 0.f);
+    fc_block(w2, b2, hidden, g, red, C, J, gate, plus);
     const unsigned base = blockIdx.x * GSW_ELEMS;
     for (unsigned i = base + threadIdx.x * 8u; i < min(base + GSW_ELEMS, per_image); i += 256u * 8u) {
         const int ci = static_cast<int>(i % cin_pad);
@@ -461,7 +474,7 @@ extern "C" int cabinet_gate_scale_weights(const void* gap_sum, int in_fixed, flo
     const long long per_image = static_cast<long long>(rows) * taps * cin_pad;
     CAB_REQUIRE(per_image < (1LL << 31), "gate_scale_weights: weight matrix too large");
     dim3 grid(static_cast<unsigned>(cab_ceil_div(per_image, GSW_ELEMS)), N);
-    gate_scale_weights_kernel<<<grid, 256, (2 * C + Cmid) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+    gate_scale_weights_kernel<<<grid, 256, (2 * C + Cmid + 256) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
         gap_sum, in_fixed, inv_hw, w1, b1, w2, b2, gate, C, Cmid, reinterpret_cast<const bf16*>(w_packed),
         reinterpret_cast<bf16*>(out), static_cast<unsigned>(per_image), static_cast<unsigned>(cin_pad), plus_one ? 1.f : 0.f);
     CAB_LAUNCH_CHECK();
