@@ -33,6 +33,10 @@ jobs = {
     "f5.dw": lambda: eng.dwconv(rnd(B, 128, 128, 120), blk[5]["dw"]),
     "f12.dw": lambda: eng.dwconv(rnd(B, 64, 64, 672), blk[12]["dw"]),
     "f14.dw": lambda: eng.dwconv(rnd(B, 32, 32, 960), blk[14]["dw"]),
+    "f2.fused": lambda: eng.mbconv_fused(rnd(B, 512, 512, 16), blk[2], None),
+    "f3.fused": lambda: eng.mbconv_fused(rnd(B, 256, 256, 24), blk[3], None),
+    "f5.fused": lambda: eng.mbconv_fused(rnd(B, 128, 128, 40), blk[5], torch.zeros(B * 120, dtype=torch.int64, device="cuda")),
+    "f7.fused": lambda: eng.mbconv_fused(rnd(B, 128, 128, 40), blk[7], None),
 }
 for name, fn in jobs.items():
     if which and name not in which:
