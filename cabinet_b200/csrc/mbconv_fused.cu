@@ -7,7 +7,8 @@
 //
 //   per output tile (TH x TW pixels of one image), per chunk of <= 64 expanded channels
 //     1. MMA1 (tcgen05, TMEM):  D1[input pixels incl. halo][64] = A1[pixels][Cin + 2] * W1_chunk^T
-//        A1 is ONE 4-D TMA box {64 ch, IWT, IHT, 1} of the block input (OOB zero fill = conv padding of the input).
+//        A1 is one 4-D TMA box {64 ch, IWT, IHT, 1} of the block input per 64-channel K block (OOB zero fill = conv
+//        padding of the input, and the zero tail of the last K block); Cin <= 248 -> up to 4 K blocks.
 //        The expand bias rides in the GEMM: the control warp writes 1.0 into K slots Cin, Cin+1 of every A1 row and
 //        W1 carries (bias_hi, bias_lo) there, so epilogue 1 needs no per-element add.
 //     2. epilogue 1 (CUDA cores):  TMEM -> act -> 0 outside the image (the depthwise conv pads the EXPANDED
@@ -30,13 +31,14 @@ constexpr int NCW = 8;                      // compute warps
 constexpr int NTHREADS = (NCW + 1) * 32;    // + control warp
 constexpr int E_PITCH = 144;                // bytes per staged expanded pixel (64 ch bf16 + 16 B skew)
 constexpr int A2_BYTES = 128 * 128;
-constexpr int W1_CHUNK = 64 * 128;
+constexpr int W1_KB = 64 * 128;              // one K block (64 input channels) of a 64-channel expand-weight chunk
 constexpr int TMEM_COLS = 256;
 
 struct MbParams {
     int H, W, OH, OW, Cin, Cexp, Cout, cout_pad;
     int n_chunks, resident, tiles_w, tiles_h, num_tiles;
     int act_e, act_dw, has_res, ksteps1;
+    int kb, a1_kb_bytes, w1_bytes;  // K blocks of MMA1, bytes of one staged A1 K block / of one W1 chunk
     int off_e, off_a2, off_w, w_buf_bytes, off_f32;
     int off_aux, aux_bytes, a2_bytes;
     int step[3];       // gridDim.x split into (tile column, tile row, image) steps
@@ -122,7 +124,7 @@ template <int ACT> __device__ __forceinline__ uint32_t pack_act(float lo, float 
 }
 
 // Per-(warp, lane) pooling partial (two floats): parked in the 16 unused skew bytes behind the 128 channel bytes of the
-// staged E rows 0..127 (epilogue 1 never writes them; every tile shape stages >= 144 rows) -- no extra shared memory.
+// staged E rows 0..127 (epilogue 1 never writes them; the E region holds >= 128 rows in this mode) -- no extra shared memory.
 __device__ __forceinline__ uint32_t gap_slot(uint32_t sE, int warp, int lane) {
     return sE + (warp * 16 + (lane >> 1)) * E_PITCH + 128 + (lane & 1) * 8;
 }
@@ -294,8 +296,10 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         lt.init(blockIdx.x, p.tiles_w, p.tiles_h);
         auto load_a1 = [&](int) {
             if (lane == 0) {
-                tc::mbar_expect_tx(&a1_full, NPIX * 128);
-                tc::tma_load_4d(smem, &tmX, &a1_full, 0, lt.tw * TW * S - PAD, lt.th * TH * S - PAD, lt.n);
+                tc::mbar_expect_tx(&a1_full, NPIX * 128 * p.kb);
+                for (int kb = 0; kb < p.kb; ++kb)
+                    tc::tma_load_4d(smem + kb * p.a1_kb_bytes, &tmX, &a1_full, kb * 64, lt.tw * TW * S - PAD,
+                                    lt.th * TH * S - PAD, lt.n);
             }
             lt.next(p.step, p.tiles_w, p.tiles_h);
             __syncwarp();
@@ -303,9 +307,9 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         auto load_w = [&](int c, int buf) {
             if (lane == 0) {
                 uint8_t* dst = smem + p.off_w + buf * p.w_buf_bytes;
-                tc::mbar_expect_tx(&w_full[buf], W1_CHUNK + (PROJECT ? p.cout_pad * 128 : 0) + p.aux_bytes);
-                tc::tma_load_2d(dst, &tmW1, &w_full[buf], 0, c * 64);
-                if (PROJECT) tc::tma_load_2d(dst + W1_CHUNK, &tmW2, &w_full[buf], c * 64, 0);
+                tc::mbar_expect_tx(&w_full[buf], p.w1_bytes + (PROJECT ? p.cout_pad * 128 : 0) + p.aux_bytes);
+                for (int kb = 0; kb < p.kb; ++kb) tc::tma_load_2d(dst + kb * W1_KB, &tmW1, &w_full[buf], kb * 64, c * 64);
+                if (PROJECT) tc::tma_load_2d(dst + p.w1_bytes, &tmW2, &w_full[buf], c * 64, 0);
                 bulk_load_1d(dst + p.off_aux, reinterpret_cast<const uint8_t*>(p.aux) + static_cast<size_t>(c) * p.aux_bytes,
                              p.aux_bytes, &w_full[buf]);
             }
@@ -319,7 +323,9 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 // bias slots: K columns Cin, Cin+1 of every staged pixel <- 1.0 (one 4-byte store per row, in the row's
                 // swizzled 16-byte chunk); this warp also issues the MMAs, so a proxy fence is all the ordering needed
                 const uint32_t ones = 0x3F803F80u;
-                for (int r = lane; r < NPIX; r += 32) sts32(sA1 + r * 128 + ((((p.Cin >> 3) ^ (r & 7))) << 4), ones);
+                const uint32_t s_ones = sA1 + (p.Cin >> 6) * p.a1_kb_bytes;
+                const int cq = (p.Cin & 63) >> 3;
+                for (int r = lane; r < NPIX; r += 32) sts32(s_ones + r * 128 + ((cq ^ (r & 7)) << 4), ones);
                 tc::fence_proxy_async();
                 __syncwarp();
             }
@@ -334,6 +340,11 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 if (p.ksteps1 > 1) tc::umma_bf16_if(leader, tmem + m * 64, ad + 2, b_desc + 2, idesc1, 1u);
                 if (p.ksteps1 > 2) tc::umma_bf16_if(leader, tmem + m * 64, ad + 4, b_desc + 4, idesc1, 1u);
                 if (p.ksteps1 > 3) tc::umma_bf16_if(leader, tmem + m * 64, ad + 6, b_desc + 6, idesc1, 1u);
+                for (int ks = 4; ks < p.ksteps1; ++ks) {  // further K blocks (Cin > 56)
+                    const uint64_t ko = static_cast<uint64_t>((ks & 3) * 2);
+                    tc::umma_bf16_if(leader, tmem + m * 64, ad + static_cast<uint64_t>(((ks >> 2) * p.a1_kb_bytes) >> 4) + ko,
+                                     b_desc + static_cast<uint64_t>(((ks >> 2) * W1_KB) >> 4) + ko, idesc1, 1u);
+                }
             }
             tc::umma_commit_if(leader, &d1_full);
             if (c == nc - 1) tc::umma_commit_if(leader, &a1_free);
@@ -361,7 +372,7 @@ mbconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     if (c == 0) tc::mbar_wait(&d2_free, (it & 1) ^ 1);
                     tc::tc_fence_after();
                     const int buf = p.resident ? c : (g & 1);
-                    const uint64_t b_desc = tc::make_desc_sw128(sW + buf * p.w_buf_bytes + W1_CHUNK);
+                    const uint64_t b_desc = tc::make_desc_sw128(sW + buf * p.w_buf_bytes + p.w1_bytes);
                     const int ks2 = min(64, exp16 - c * 64) >> 4;
                     tc::umma_bf16_if(leader, tmem + D2COL, a2_desc, b_desc, idesc2, c > 0 ? 1u : 0u);
                     if (ks2 > 1) tc::umma_bf16_if(leader, tmem + D2COL, a2_desc + 2, b_desc + 2, idesc2, 1u);
@@ -590,15 +601,18 @@ int launch_mb(const void* x, long long ldx, int N, const void* w1, const void* w
     const long long tiles = static_cast<long long>(N) * p.tiles_w * p.tiles_h;
     CAB_REQUIRE(tiles < (1LL << 31), "mbconv_fused: too many tiles");
     p.num_tiles = static_cast<int>(tiles);
-    const int a1_bytes = ((NPIX * 128 + 1023) / 1024) * 1024;
+    p.a1_kb_bytes = ((NPIX * 128 + 1023) / 1024) * 1024;
+    p.w1_bytes = p.kb * W1_KB;
+    const int a1_bytes = p.kb * p.a1_kb_bytes;
     int e_bytes = ((NPIX * E_PITCH + 1023) / 1024) * 1024;
     if (PROJECT && p.cout_pad > 64) e_bytes = std::max(e_bytes, ((p.cout_pad + 63) / 64 - 1) * A2_BYTES);
+    if (!PROJECT) e_bytes = std::max(e_bytes, ((128 * E_PITCH + 1023) / 1024) * 1024);  // gap_slot parks partials behind rows 0..127
     p.a2_bytes = ((NOUT * 128 + 1023) / 1024) * 1024;  // MMA2 reads 128 rows: the tail runs into the weight buffers
     p.off_e = a1_bytes;
     p.off_a2 = p.off_e + e_bytes;
     p.off_w = p.off_a2 + p.a2_bytes;
     p.aux_bytes = (K * K + 2) * 256;
-    p.off_aux = W1_CHUNK + (PROJECT ? p.cout_pad * 128 : 0);
+    p.off_aux = p.w1_bytes + (PROJECT ? p.cout_pad * 128 : 0);
     p.w_buf_bytes = ((p.off_aux + p.aux_bytes + 1023) / 1024) * 1024;
     p.resident = p.n_chunks <= 2 ? 1 : 0;
     p.off_f32 = p.off_w + std::min(p.n_chunks, 2) * p.w_buf_bytes;
@@ -618,8 +632,8 @@ int launch_mb(const void* x, long long ldx, int N, const void* w1, const void* w
         if (rc) return rc;
     }
     {
-        const uint64_t dims[2] = {64, (uint64_t)((p.Cexp + 15) / 16 * 16)};
-        const uint64_t strides[1] = {128};
+        const uint64_t dims[2] = {(uint64_t)p.kb * 64, (uint64_t)((p.Cexp + 15) / 16 * 16)};
+        const uint64_t strides[1] = {(uint64_t)p.kb * 128};
         const uint32_t box[2] = {64, 64};
         int rc = cab_make_tmap_bf16(&tmW1, w1, 2, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (rc) return rc;
@@ -673,8 +687,10 @@ extern "C" int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, 
                                     long long ldy, int OH, int OW, long long* gap_sum, cabinet_stream_t stream) {
     CAB_REQUIRE(x && w_expand && aux_packed && y, "mbconv_fused: null pointer");
     CAB_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2), "mbconv_fused: k must be 3|5 and stride 1|2");
-    CAB_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cin <= 56 && Cin % 8 == 0 && Cexp > 0 && Cexp % 8 == 0 && Cexp <= 1024,
-                "mbconv_fused: needs Cin %% 8 == 0, Cin <= 56 and Cexp %% 8 == 0 (got Cin %d, Cexp %d)", Cin, Cexp);
+    // the expand bias rides in K slots Cin, Cin + 1 of the last K block: that block must have two free slots
+    CAB_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cin <= 248 && Cin % 8 == 0 && Cin % 64 <= 56 && Cexp > 0 &&
+                    Cexp % 8 == 0 && Cexp <= 1024,
+                "mbconv_fused: needs Cin %% 8 == 0, Cin %% 64 <= 56, Cin <= 248 and Cexp %% 8 == 0 (got Cin %d, Cexp %d)", Cin, Cexp);
     const int pad = (k - 1) / 2;
     CAB_REQUIRE(OH == (H + 2 * pad - k) / stride + 1 && OW == (W + 2 * pad - k) / stride + 1,
                 "mbconv_fused: inconsistent output size");
@@ -684,8 +700,8 @@ extern "C" int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, 
                 "mbconv_fused: alignment");
     const bool project = w_project != nullptr;
     if (project) {
-        CAB_REQUIRE(b_project && Cout > 0 && Cout <= 128 && ldy >= Cout && (reinterpret_cast<uintptr_t>(w_project) & 15) == 0,
-                    "mbconv_fused: project needs a bias and Cout <= 128");
+        CAB_REQUIRE(b_project && Cout > 0 && Cout <= 160 && ldy >= Cout && (reinterpret_cast<uintptr_t>(w_project) & 15) == 0,
+                    "mbconv_fused: project needs a bias and Cout <= 160");
         CAB_REQUIRE(!residual || (stride == 1 && Cin == Cout && Cin % 8 == 0), "mbconv_fused: identity needs stride 1, Cin == Cout");
         CAB_REQUIRE(!gap_sum, "mbconv_fused: pooling sums exist in the depthwise-output mode only");
     } else {
@@ -698,6 +714,7 @@ extern "C" int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, 
     p.n_chunks = (Cexp + 63) / 64;
     p.act_e = act_expand; p.act_dw = act_dw; p.has_res = residual ? 1 : 0;
     p.ksteps1 = (Cin + 2 + 15) / 16;  // + the two bias slots
+    p.kb = Cin / 64 + 1;
     p.aux = aux_packed; p.b2 = b_project;
     p.res = reinterpret_cast<const bf16*>(x); p.ldres = ldx; p.gap = gap_sum; p.dbg = g_mb_dbg;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -705,7 +722,10 @@ extern "C" int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, 
 #define CAB_MB(K_, S_, TH_, TW_, PROBE_)                                                                           \
     (project ? launch_mb<K_, S_, TH_, TW_, true>(x, ldx, N, w_expand, w_project, y, ldy, cy, p, st, PROBE_)   \
              : launch_mb<K_, S_, TH_, TW_, false>(x, ldx, N, w_expand, w_project, y, ldy, cy, p, st, PROBE_))
-    if (k == 3 && stride == 1) return CAB_MB(3, 1, 8, 16, false);
+    if (k == 3 && stride == 1) {
+        if (CAB_MB(3, 1, 8, 16, true) == CABINET_OK) return CAB_MB(3, 1, 8, 16, false);
+        return CAB_MB(3, 1, 8, 8, false);  // 10 x 10 input patch = one M tile: what fits beside several K blocks of A1 / W1
+    }
     if (k == 5 && stride == 1) {
         if (CAB_MB(5, 1, 8, 16, true) == CABINET_OK) return CAB_MB(5, 1, 8, 16, false);
         return CAB_MB(5, 1, 8, 8, false);  // narrow tile: 12 x 12 input patch, fits next to streamed project weights

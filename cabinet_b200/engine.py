@@ -186,7 +186,7 @@ class Engine:
         self.debug = False
         self.stages = {}
         self.trace, self.trace_filter = None, None
-        self.fuse_mbconv = True     # expand + depthwise (+ project) in one kernel for blocks with <= 64 input channels
+        self.fuse_mbconv = True     # expand + depthwise (+ project) in one kernel (blocks whose tiles fit the shared memory)
         self.fold_se_relu = True    # ReLU SE blocks: gate folded into per-image project weights (relu(s*d) = s*relu(d))
         self.fold_ffm = True        # FFM gate folded into per-image head-conv weights (no rewrite of the fused feature map)
         # convb + x4 upsample + the low half of ffm.convblk as a 1/32-resolution conv + upsample-add in the convblk epilogue
@@ -252,9 +252,10 @@ class Engine:
                     aux[: dwl.c, kk + 1] = dwl.b
                     e["aux"] = aux.view(nc, 64, kk + 2).permute(0, 2, 1).contiguous()
                     p1 = e["pw1"]
-                    if p1.cin % 8 == 0 and p1.cin <= 56:
-                        # expand weights with the bias as two extra K columns (bf16 hi + lo; the kernel feeds 1.0 there)
-                        wb = torch.zeros((-(-p1.cout // 16) * 16, 64), dtype=f32, device=dwl.w.device)
+                    if p1.cin % 8 == 0 and p1.cin % 64 <= 56 and p1.cin <= 248:
+                        # expand weights with the bias as two extra K columns (bf16 hi + lo; the kernel feeds 1.0 there);
+                        # K = Cin + 2 padded to whole 64-channel K blocks
+                        wb = torch.zeros((-(-p1.cout // 16) * 16, (p1.cin // 64 + 1) * 64), dtype=f32, device=dwl.w.device)
                         wb[: p1.cout, : p1.cin] = p1.tc[: p1.cout, 0, : p1.cin].float()
                         hi = p1.b.to(torch.bfloat16).float()
                         wb[: p1.cout, p1.cin], wb[: p1.cout, p1.cin + 1] = hi, p1.b - hi
@@ -650,7 +651,7 @@ class Engine:
                 f = o
                 continue
             fuse = (s["expand"] and self.fuse_mbconv and self.use_tc and f.dt == BF16 and f.ld % 8 == 0
-                    and f.off % 8 == 0 and s["exp"] % 8 == 0 and ("se" in e or s["out"] <= 128) and "w1b" in e
+                    and f.off % 8 == 0 and s["exp"] % 8 == 0 and ("se" in e or s["out"] <= 160) and "w1b" in e
                     and not e.get("nofuse")
                     # 5x5 stride-2 tiles are 4 x 8 outputs behind an 11 x 19 halo: measured slower than expand + dwconv_tma
                     and not (s["k"] == 5 and s["s"] == 2))

@@ -179,7 +179,7 @@ int cabinet_gate_scale_weights(const void* gap_sum, int in_fixed, float inv_hw, 
                                const float* w2, const float* b2, int gate, int C, int Cmid, const void* w_packed, void* out,
                                int N, int rows, int taps, int cin_pad, int plus_one, cabinet_stream_t stream);
 
-/* Fused inverted-residual block with expansion (src/models/mobilenetv3.py:126-159), bf16 NHWC, Cin <= 64:
+/* Fused inverted-residual block with expansion (src/models/mobilenetv3.py:126-159), bf16 NHWC, Cin <= 248:
  *   h = act_expand(W_e * x + b_e)            1x1 expand + BN + act          (mobilenetv3.py:128-131)
  *   d = act_dw(dw_kxk(h) + b_dw)             depthwise + BN                 (mobilenetv3.py:132-141)
  *   w_project != NULL:  y = W_p * d + b_p (+ x when residual)                (mobilenetv3.py:145-159), y has Cout channels
@@ -190,13 +190,14 @@ int cabinet_gate_scale_weights(const void* gap_sum, int in_fixed, float inv_hw, 
  *                       act_dw = RELU is for the identity relu(s * d) = s * relu(d), s >= 0, with the scale folded
  *                       into per-image project weights (cabinet_scale_weights + cabinet_conv_tc_imgw).
  * The expanded activation h never reaches HBM (TMEM -> shared memory -> depthwise).
- * w_expand: bf16 [ceil16(Cexp)][64], row = expanded channel: columns 0..Cin-1 = W_e (BN folded), columns Cin, Cin+1 =
- *           b_e split into bf16 (hi, lo) -- the kernel feeds 1.0 into those two K slots, the bias is part of the GEMM --
- *           remaining columns 0.  Needs Cin % 8 == 0 and Cin <= 56.
+ * w_expand: bf16 [ceil16(Cexp)][64 * KB], KB = Cin / 64 + 1 K blocks, row = expanded channel: columns 0..Cin-1 = W_e (BN
+ *           folded), columns Cin, Cin+1 = b_e split into bf16 (hi, lo) -- the kernel feeds 1.0 into those two K slots,
+ *           the bias is part of the GEMM -- remaining columns 0.  Needs Cin % 8 == 0, Cin % 64 <= 56 and Cin <= 248.
  * w_project: the cabinet_conv_tc packing (bf16 [ceil16(Cout)][1][ceil64(Cexp)]); b_project fp32 [Cout].
  * aux_packed: fp32 [ceil(Cexp/64)][k*k + 2][64], zero padded, BN folded: rows 0..k*k-1 = depthwise taps of the chunk's
  *           64 channels, row k*k = reserved (0), row k*k+1 = depthwise bias (one bulk copy per chunk).
- * k in {3,5}, stride in {1,2}, pad (k-1)/2; Cexp % 8 == 0; Cout <= 128; gap_sum may be NULL. */
+ * k in {3,5}, stride in {1,2}, pad (k-1)/2; Cexp % 8 == 0; Cout <= 160; gap_sum may be NULL.  Shapes whose tiles do not
+ * fit 113 KB of shared memory / 256 TMEM columns (two CTAs per SM) return CABINET_ERR_INVALID ("budget"). */
 int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_expand,
                          const float* aux_packed, int Cexp, int act_expand, int k, int stride, int act_dw,
                          const void* w_project, const float* b_project, int Cout, int residual, void* y, long long ldy,

@@ -487,9 +487,10 @@ def _pack_aux(wd, be, bd):
 
 
 def _pack_expand(we, be):
-    """[ceil16(Cexp)][64] bf16: expand weights + the bias as two extra K columns (hi, lo) -- include/cabinet_b200.h."""
+    """[ceil16(Cexp)][64 * (Cin // 64 + 1)] bf16: expand weights + the bias as two extra K columns (hi, lo) --
+    include/cabinet_b200.h."""
     cexp, cin = we.shape[:2]
-    pk = torch.zeros(-(-cexp // 16) * 16, 64)
+    pk = torch.zeros(-(-cexp // 16) * 16, 64 * (cin // 64 + 1))
     pk[:cexp, :cin] = we.reshape(cexp, cin)
     hi = be.to(torch.bfloat16).float()
     pk[:cexp, cin], pk[:cexp, cin + 1] = hi, be - hi
@@ -514,6 +515,10 @@ def _pack_tc(w, dtype=torch.bfloat16):
     (56, 128, 56, 3, 1, 16, 16, ACT_HSWISH, True),
     (16, 72, 24, 3, 2, 30, 34, ACT_RELU, False),      # Small f2: two chunks at stride 2 (narrow-tile fallback)
     (40, 240, 40, 5, 1, 14, 18, ACT_HSWISH, True),    # Small f5-like: four k5 chunks, streamed taps
+    (80, 200, 80, 3, 1, 20, 28, ACT_HSWISH, True),    # Large f8: two K blocks of input channels, 8 x 8 tiles
+    (80, 184, 80, 3, 1, 64, 64, ACT_HSWISH, True),    # Large f9 / f10 at their config-2 size
+    (72, 136, 72, 3, 1, 13, 9, ACT_RELU, True),       # odd size, ragged last chunk with two K blocks
+    (64, 128, 64, 3, 1, 16, 16, ACT_RELU, True),      # Cin a multiple of 64: the bias slots open a K block of their own
 ])
 def test_mbconv_fused_project(cin, cexp, cout, k, s, H, W, act, res):
     """expand -> depthwise -> project (+identity) in one kernel vs the torch ops with the same bf16 roundings."""
@@ -554,6 +559,11 @@ def test_mbconv_fused_project(cin, cexp, cout, k, s, H, W, act, res):
     (40, 120, 5, 1, 24, 40, ACT_RELU),      # Large f5 / f6
     (40, 240, 3, 1, 11, 13, ACT_HSWISH),
     (16, 72, 3, 2, 17, 9, ACT_RELU),
+    (80, 480, 3, 1, 64, 64, ACT_HSWISH),    # Large f11
+    (112, 672, 3, 1, 21, 35, ACT_HSWISH),   # Large f12, odd size
+    (48, 144, 5, 1, 17, 23, ACT_HSWISH),    # Small f7-like
+    (96, 128, 5, 1, 12, 20, ACT_HSWISH),    # k5 with two K blocks
+    (160, 64, 3, 1, 16, 24, ACT_HSWISH),    # three K blocks
 ])
 def test_mbconv_fused_dw_out(cin, cexp, k, s, H, W, act, act_dw):
     """expand -> depthwise with the pre-SE output and its pooling sums (blocks with squeeze-excite)."""
