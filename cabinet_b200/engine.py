@@ -187,6 +187,7 @@ class Engine:
         self.stages = {}
         self.trace, self.trace_filter = None, None
         self.fuse_mbconv = True     # expand + depthwise (+ project) in one kernel (blocks whose tiles fit the shared memory)
+        self.use_mbconv_t = True    # ... in the channel-major formulation (cabinet_mbconv_t) where it supports the block
         self.fold_se_relu = True    # ReLU SE blocks: gate folded into per-image project weights (relu(s*d) = s*relu(d))
         self.fold_ffm = True        # FFM gate folded into per-image head-conv weights (no rewrite of the fused feature map)
         # convb + x4 upsample + the low half of ffm.convblk as a 1/32-resolution conv + upsample-add in the convblk epilogue
@@ -260,6 +261,18 @@ class Engine:
                         hi = p1.b.to(torch.bfloat16).float()
                         wb[: p1.cout, p1.cin], wb[: p1.cout, p1.cin + 1] = hi, p1.b - hi
                         e["w1b"] = wb.to(torch.bfloat16).contiguous()
+                        # channel-major kernel (cabinet_mbconv_t): chunks of 128 TMEM lanes; widths <= 64 are replicated
+                        # twice along the lanes.  Same columns as w1b; taps + depthwise bias in the same row order.
+                        ch = 64 if dwl.c <= 64 else 128
+                        nct = 1 if dwl.c <= 64 else -(-dwl.c // 128)
+                        flat = torch.zeros((nct * ch, wb.shape[1]), dtype=f32, device=dwl.w.device)
+                        flat[: dwl.c] = wb[: dwl.c]
+                        e["w1t"] = (flat.view(nct, ch, -1).repeat(1, 128 // ch, 1).reshape(nct * 128, -1)
+                                    .to(torch.bfloat16).contiguous())
+                        fa = torch.zeros((nct * ch, kk + 1), dtype=f32, device=dwl.w.device)
+                        fa[: dwl.c, :kk] = dwl.w.t()
+                        fa[: dwl.c, kk] = dwl.b
+                        e["auxt"] = fa.view(nct, ch, kk + 1).repeat(1, 128 // ch, 1).permute(0, 2, 1).contiguous()
             else:
                 e["dw"] = DwLayer(c[0], c[1], act, f"mobile.f{bi}.dw")
                 se, pw2, bn2 = c[3], c[4], c[5]
@@ -494,6 +507,24 @@ class Engine:
         if project:
             nbytes += pw2.w.numel() * 2 + (x.N * OH * OW * cy * 2 if s["identity"] else 0)
             flops += 2 * x.N * OH * OW * dw.c * pw2.cout
+        # (stride-2 blocks with <= 64 expanded channels -- Large f2 -- have 32-pixel tiles with four outputs per thread
+        # there: latency bound, 0.33 ms against 0.18 ms for the pixel-major kernel)
+        use_t = (self.use_mbconv_t and "w1t" in e and not e.get("no_t") and not (dw.stride == 2 and dw.c <= 64)
+                 and ((dw.k == 3 and (not project or (pw2.cout <= 128 and pw2.cout % 8 == 0)))
+                      or (dw.k == 5 and dw.stride == 1 and not project)))
+        if use_t:
+            try:
+                self._run("mbconv_t", dw.name.replace(".dw", "") + ("" if project else ".expand+dw"), nbytes, flops,
+                          self.lib.cabinet_mbconv_t, x.ptr, x.ld, x.N, x.H, x.W, x.C, e["w1t"].data_ptr(),
+                          e["auxt"].data_ptr(), dw.c, pw1.act, dw.k, dw.stride, dw.act if act_dw is None else act_dw,
+                          pw2.tc.data_ptr() if project else None, pw2.b.data_ptr() if project else None,
+                          pw2.cout if project else 0, 1 if project and s["identity"] else 0, out.ptr, out.ld, OH, OW,
+                          gap.data_ptr() if gap is not None else None, self.stream)
+                return out
+            except ValueError as err:  # outside the kernel's shared-memory / TMEM budget: the pixel-major kernel
+                if "budget" not in str(err):
+                    raise
+                e["no_t"] = True
         self._run("mbconv_fused", dw.name.replace(".dw", "") + ("" if project else ".expand+dw"), nbytes, flops,
                   self.lib.cabinet_mbconv_fused, x.ptr, x.ld, x.N, x.H, x.W, x.C, e["w1b"].data_ptr(), e["aux"].data_ptr(),
                   dw.c, pw1.act, dw.k, dw.stride, dw.act if act_dw is None else act_dw,

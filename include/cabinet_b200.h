@@ -203,6 +203,21 @@ int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, int W, int 
                          const void* w_project, const float* b_project, int Cout, int residual, void* y, long long ldy,
                          int OH, int OW, long long* gap_sum, cabinet_stream_t stream);
 
+/* The same block (same semantics, arguments and modes as cabinet_mbconv_fused) in the channel-major formulation: the
+ * expand GEMM is computed transposed (TMEM lane = expanded channel, TMEM column = pixel of the input patch), so the
+ * depthwise conv reads its rows straight from TMEM into fp32 registers -- the expanded activation is neither staged in
+ * shared memory nor rounded to bf16.  One persistent CTA per SM (16 compute warps + TMA warp + MMA warp).
+ * w_expand_t: bf16 [nc * 128][64 * KB], KB = Cin / 64 + 1: chunk c, row l = expanded channel c * CH + (l % CH) with
+ *           CH = 64 (Cexp <= 64: one chunk, rows 64..127 repeat rows 0..63) or 128; columns as in cabinet_mbconv_fused
+ *           (W_e, then the bias as bf16 hi / lo in columns Cin, Cin + 1); rows of channels >= Cexp are 0.
+ * aux_t:    fp32 [nc][k*k + 1][128]: rows 0..k*k-1 = depthwise taps, row k*k = depthwise bias, same row -> channel map.
+ * Supported: k = 3 with stride 1 | 2, k = 5 with stride 1 in the depthwise-output mode; Cout <= 128, Cout % 8 == 0.
+ * Everything else returns CABINET_ERR_INVALID (the caller falls back to cabinet_mbconv_fused / the unfused kernels). */
+int cabinet_mbconv_t(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_expand_t, const float* aux_t,
+                     int Cexp, int act_expand, int k, int stride, int act_dw, const void* w_project,
+                     const float* b_project, int Cout, int residual, void* y, long long ldy, int OH, int OW,
+                     long long* gap_sum, cabinet_stream_t stream);
+
 /* Squeeze-excite / FFM channel gate: scale[n][c] = gate(b2 + W2 * relu(b1 + W1 * (sum[n]/HW))).
  * Replaces src/models/mobilenetv3.py:68-83 (gate = CABINET_ACT_HSIGMOID, biases present) and
  * src/models/cabinet.py:146-150 (gate = CABINET_ACT_SIGMOID, b1 = b2 = NULL).  All fp32. */

@@ -68,7 +68,8 @@ def test_schedule_shapes_and_abi(cpu_engine, mode, C, shape, precision):
     names = [c[0] for c in rec.calls]
     n_blocks = 15 if mode == "large" else 11
     assert (names.count("cabinet_dwconv") + names.count("cabinet_dwconv_tma")
-            + names.count("cabinet_mbconv_noexpand_fused") + names.count("cabinet_mbconv_fused")) == n_blocks + 3
+            + names.count("cabinet_mbconv_noexpand_fused") + names.count("cabinet_mbconv_fused")
+            + names.count("cabinet_mbconv_t")) == n_blocks + 3
     assert names.count("cabinet_upsample_logits_nchw") == 2
     assert names.count("cabinet_psp_pool") == 2 and names.count("cabinet_softmax_rows") + names.count("cabinet_attention_tc") == 1
     # the single gap-sum / scratch memset (+ the V transpose inside attention_tc)

@@ -600,6 +600,123 @@ def test_mbconv_fused_dw_out(cin, cexp, k, s, H, W, act, act_dw):
     assert float((ym.t.float()[..., cexp:] - 7.0).abs().max()) == 0
 
 
+def _pack_expand_t(we, be):
+    """[nc * 128][64 * (Cin // 64 + 1)] bf16, row (c, l) = channel c * CH + l % CH (include/cabinet_b200.h: cabinet_mbconv_t)."""
+    cexp, cin = we.shape[:2]
+    ch = 64 if cexp <= 64 else 128
+    nc = 1 if cexp <= 64 else -(-cexp // 128)
+    flat = torch.zeros(nc * ch, 64 * (cin // 64 + 1))
+    flat[:cexp, :cin] = we.reshape(cexp, cin)
+    hi = be.to(torch.bfloat16).float()
+    flat[:cexp, cin], flat[:cexp, cin + 1] = hi, be - hi
+    pk = flat.view(nc, ch, -1).repeat(1, 128 // ch, 1).reshape(nc * 128, -1)
+    return pk.to("cuda", torch.bfloat16).contiguous()
+
+
+def _pack_aux_t(wd, bd):
+    """[nc][k*k + 1][128] fp32: depthwise taps + bias, rows mapped like _pack_expand_t."""
+    cexp, kk = wd.shape[0], wd.shape[2] * wd.shape[3]
+    ch = 64 if cexp <= 64 else 128
+    nc = 1 if cexp <= 64 else -(-cexp // 128)
+    flat = torch.zeros(nc * ch, kk + 1)
+    flat[:cexp, :kk] = wd.reshape(cexp, kk)
+    flat[:cexp, kk] = bd
+    return flat.view(nc, ch, kk + 1).repeat(1, 128 // ch, 1).permute(0, 2, 1).contiguous().cuda()
+
+
+@pytest.mark.parametrize("cin,cexp,cout,k,s,H,W,act,res", [
+    (16, 64, 24, 3, 2, 40, 56, ACT_RELU, False),      # Large f2 (64 channels replicated over the 128 lanes)
+    (24, 72, 24, 3, 1, 24, 40, ACT_RELU, True),       # Large f3
+    (40, 240, 80, 3, 2, 20, 36, ACT_HSWISH, False),   # Large f7 (two chunks)
+    (16, 16, 16, 3, 1, 9, 7, ACT_RELU, True),         # tile larger than the image
+    (56, 128, 56, 3, 1, 16, 16, ACT_HSWISH, True),
+    (16, 72, 24, 3, 2, 30, 34, ACT_RELU, False),      # Small f2
+    (80, 200, 80, 3, 1, 20, 28, ACT_HSWISH, True),    # Large f8: two K blocks
+    (80, 184, 80, 3, 1, 64, 64, ACT_HSWISH, True),    # Large f9 / f10 at their config-2 size
+    (72, 392, 72, 3, 1, 13, 9, ACT_RELU, True),       # four chunks: streamed weights, odd size
+    (64, 128, 64, 3, 1, 16, 16, ACT_RELU, True),      # Cin a multiple of 64: the bias slots open a K block of their own
+    (24, 48, 128, 3, 1, 33, 17, ACT_HSWISH, False),   # 128 output channels
+])
+def test_mbconv_t_project(cin, cexp, cout, k, s, H, W, act, res):
+    """Channel-major fused block (expand -> depthwise from TMEM -> project) vs torch ops; the expanded activation stays
+    fp32 here, so only d and y carry bf16 roundings."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    N = 3
+    x = q(gen(N, cin, H, W, seed=1), dtype)
+    we, be = q(gen(cexp, cin, 1, 1, seed=2, scale=cin ** -0.5), dtype), gen(cexp, seed=3, scale=0.2)
+    wd, bd = gen(cexp, 1, k, k, seed=4, scale=1.0 / k), gen(cexp, seed=5, scale=0.1)
+    wp, bp = q(gen(cout, cexp, 1, 1, seed=6, scale=cexp ** -0.5), dtype), gen(cout, seed=7, scale=0.1)
+    pad = (k - 1) // 2
+    h = act_ref(F.conv2d(x, we, be), act)
+    d = q(act_ref(F.conv2d(h, wd, bd, s, pad, 1, cexp), act), dtype)
+    ref = F.conv2d(d, wp, bp)
+    if res:
+        ref = ref + x
+    OH, OW = ref.shape[2:]
+    xm = to_map(x, dtype, ld=cin + 8, off=8)
+    ym = to_map(torch.zeros_like(ref), dtype, ld=cout + 24, off=16)
+    ym.t.fill_(7.0)
+    aux, bpd = _pack_aux_t(wd, bd), bp.cuda()
+    pe, pp = _pack_expand_t(we, be), _pack_tc(wp)
+    check(lib.cabinet_mbconv_t(xm.ptr, xm.ld, N, H, W, cin, pe.data_ptr(), aux.data_ptr(), cexp, act, k, s, act,
+                               pp.data_ptr(), bpd.data_ptr(), cout, 1 if res else 0, ym.ptr, ym.ld, OH, OW, None,
+                               stream()), "mbconv_t")
+    torch.cuda.synchronize()
+    err = rel_l2(from_map(ym), ref)
+    print(f"mbconv_t {cin}->{cexp}->{cout} k{k} s{s} {H}x{W}: rel_l2 {err:.3e}")
+    assert err < 6e-3
+    full = ym.t.float()
+    assert float((full[..., : ym.off] - 7.0).abs().max()) == 0
+    assert float((full[..., ym.off + cout:] - 7.0).abs().max()) == 0
+
+
+@pytest.mark.parametrize("act_dw", [ACT_NONE, ACT_RELU])
+@pytest.mark.parametrize("cin,cexp,k,s,H,W,act", [
+    (40, 120, 5, 1, 24, 40, ACT_RELU),      # Large f5 / f6
+    (40, 240, 3, 1, 11, 13, ACT_HSWISH),
+    (16, 72, 3, 2, 17, 9, ACT_RELU),
+    (80, 480, 3, 1, 64, 64, ACT_HSWISH),    # Large f11
+    (112, 672, 3, 1, 21, 35, ACT_HSWISH),   # Large f12, odd size
+    (160, 960, 5, 1, 32, 32, ACT_HSWISH),   # Large f14 / f15: three K blocks, eight chunks
+    (48, 144, 5, 1, 17, 23, ACT_HSWISH),    # Small f7-like
+    (16, 64, 5, 1, 12, 20, ACT_RELU),       # k5 with replicated lanes
+    (16, 48, 3, 2, 22, 14, ACT_RELU),       # stride 2 with replicated lanes, 48 of 64 channels
+])
+def test_mbconv_t_dw_out(cin, cexp, k, s, H, W, act, act_dw):
+    """Channel-major expand -> depthwise with the pre-SE output and its pooling sums (squeeze-excite blocks)."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    N = 2
+    x = q(gen(N, cin, H, W, seed=1), dtype)
+    we, be = q(gen(cexp, cin, 1, 1, seed=2, scale=cin ** -0.5), dtype), gen(cexp, seed=3, scale=0.2)
+    wd, bd = gen(cexp, 1, k, k, seed=4, scale=1.0 / k), gen(cexp, seed=5, scale=0.1)
+    pad = (k - 1) // 2
+    h = act_ref(F.conv2d(x, we, be), act)
+    pre = F.conv2d(h, wd, bd, s, pad, 1, cexp)
+    ref = act_ref(pre, act_dw)
+    OH, OW = ref.shape[2:]
+    xm = to_map(x, dtype)
+    ym = to_map(torch.zeros_like(ref), dtype, ld=cexp + 8, off=0)
+    ym.t.fill_(7.0)
+    aux, pe = _pack_aux_t(wd, bd), _pack_expand_t(we, be)
+    sums = []
+    for _ in range(2):
+        acc = torch.zeros((N, cexp), dtype=torch.int64, device="cuda")
+        check(lib.cabinet_mbconv_t(xm.ptr, xm.ld, N, H, W, cin, pe.data_ptr(), aux.data_ptr(), cexp, act, k, s,
+                                   act_dw, None, None, 0, 0, ym.ptr, ym.ld, OH, OW, acc.data_ptr(), stream()),
+              "mbconv_t")
+        torch.cuda.synchronize()
+        sums.append(acc)
+    assert torch.equal(sums[0], sums[1])   # deterministic
+    gap = sums[0].double().mul(2.0 ** -24).float()
+    err = rel_l2(from_map(ym), ref)
+    gerr = rel_l2(gap.cpu(), pre.sum(dim=(2, 3)))
+    print(f"mbconv_t(dw out) {cin}->{cexp} k{k} s{s} {H}x{W}: rel_l2 {err:.3e} gap {gerr:.3e}")
+    assert err < 4e-3 and gerr < 1e-3
+    assert float((ym.t.float()[..., cexp:] - 7.0).abs().max()) == 0
+
+
 @pytest.mark.parametrize("C,J,gate,bias,fixed,plus,taps", [(120, 32, ACT_HSIGMOID, True, True, False, 1),
                                                           (256, 64, ACT_SIGMOID, False, False, True, 9),
                                                           (72, 24, ACT_HSIGMOID, True, True, False, 1)])
