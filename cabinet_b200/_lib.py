@@ -44,7 +44,9 @@ SIGNATURES = {
     "cabinet_mbconv_noexpand_fused": ([_p, _ll, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _p], _i),
     "cabinet_mbconv_fused": ([_p, _ll, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _ll, _i, _i, _p,
                               _p], _i),
-    "cabinet_mbconv_t": ([_p, _ll, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _ll, _i, _i, _p, _p], _i),
+    "cabinet_mbconv_t": ([_p, _ll, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _ll, _i, _i, _p, _p,
+                          _p], _i),
+    "cabinet_expand_sums": ([_p, _ll, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p], _i),
     "cabinet_gate_mlp": ([_p, _f, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),
     "cabinet_gate_fc": ([_p, _f, _p, _p, _p, _i, _i, _i, _i, _i, _p], _i),
     "cabinet_scale_act": ([_p, _ll, _i, _p, _i, _ll, _i, _i, _i, _p], _i),

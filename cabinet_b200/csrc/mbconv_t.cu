@@ -50,6 +50,7 @@ struct MtParams {
     int ns, a1_stage_bytes;   // A1 ring: stages, bytes per stage (= kb K blocks)
     int ncols, nd, d2col;     // D1 ring in TMEM: columns per stage (= stride), stages; first column of D2
     int nd2, d2_stride;       // D2 buffers (1 | 2) and their column stride
+    int nw2;                  // W2 chunk buffers (2, or 1 when shared memory is short)
     int step[3];
     const float* aux;   // [nc][K*K + 1][128] fp32: depthwise taps, depthwise bias (row layout = TMEM lanes)
     const float* b2;
@@ -58,6 +59,7 @@ struct MtParams {
     bf16* y;
     long long ldy;
     long long* gap;
+    const float* scale;  // project mode: [N][Cexp] squeeze-excite gate applied to the BN output before act_dw, or nullptr
 };
 
 struct TileIter {
@@ -163,14 +165,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi, bool relu) {
     return d;
 }
 
-template <int K, int S, int REP, bool PROJECT>
+template <int K, int S, int REP, bool PROJECT, int TW>
 __global__ void __launch_bounds__(NTHREADS, 1)
 mbconv_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                 const __grid_constant__ CUtensorMap tmW2, const MtParams p) {
     constexpr int PAD = (K - 1) / 2;
-    constexpr int TH = S == 1 ? 8 : 4, TW = S == 1 ? 16 : 8;
+    constexpr int TH = S == 1 ? 8 : 4;
     constexpr int NR = (S == 1 && REP == 1) ? 2 : 1;                   // output rows per thread
-    constexpr int NC = S == 1 ? 16 : (REP == 1 ? 8 : 4);               // output columns per thread
+    constexpr int NC = S == 1 ? TW : (REP == 1 ? 8 : 4);               // output columns per thread
+    static_assert(TW == 8 || (TW == 16 && S == 1), "tiles: 8 x 16 or 8 x 8 (stride 1), 4 x 8 (stride 2)");
     constexpr int IWT = (TW - 1) * S + K, IHT = (TH - 1) * S + K, NPIX = IWT * IHT;
     constexpr int NIN = (NC - 1) * S + K, NROWS = (NR - 1) * S + K;    // input window of one thread
     constexpr int CH = 128 / REP;                                      // distinct channels per chunk
@@ -299,9 +302,9 @@ mbconv_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 }
             }
             if (PROJECT && !p.resident && e >= 1) {  // W2 of chunk e - 1: one step behind W1, it is needed a phase later
-                const int g = e - 1;
-                if (g >= 2) tc::mbar_wait(&w2_free[g & 1], ((g >> 1) - 1) & 1);
-                load_w2(g % nc, g & 1);
+                const int g = e - 1, wb = g % p.nw2;
+                if (g >= p.nw2) tc::mbar_wait(&w2_free[wb], ((g / p.nw2) - 1) & 1);
+                load_w2(g % nc, wb);
             }
         }
         __syncwarp();
@@ -335,8 +338,8 @@ mbconv_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             if (g + p.nd - 1 < G) mma1(g + p.nd - 1);
             if (PROJECT) {
                 const int it = g / nc, c = g - it * nc;
-                const int buf = g & 1, wbuf = p.resident ? c : buf;
-                tc::mbar_wait(&w2_full[wbuf], p.resident ? 0 : ((g >> 1) & 1));
+                const int buf = g & 1, wbuf = p.resident ? c : g % p.nw2;
+                tc::mbar_wait(&w2_full[wbuf], p.resident ? 0 : ((g / p.nw2) & 1));
                 tc::mbar_wait(&a2_full[buf], (g >> 1) & 1);
                 const int db = it % p.nd2;
                 if (c == 0 && it >= p.nd2) tc::mbar_wait(&d2_free[db], ((it / p.nd2) - 1) & 1);
@@ -350,7 +353,7 @@ mbconv_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                                          static_cast<uint64_t>((ks & 3) * 2),
                                      idesc2, (c > 0 || ks > 0) ? 1u : 0u);
                 tc::umma_commit_if(leader, &a2_free[buf]);
-                if (!p.resident) tc::umma_commit_if(leader, &w2_free[buf]);
+                if (!p.resident) tc::umma_commit_if(leader, &w2_free[wbuf]);
                 if (c == nc - 1) tc::umma_commit_if(leader, &d2_full[db]);
             }
         }
@@ -527,6 +530,13 @@ mbconv_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                                   static_cast<unsigned long long>(__float2ll_rn(gsum * CABINET_GAP_FIXED_ONE)));
                 } else {
                     // ---- A2 (M-major SWIZZLE_128B): row = channel, 128 B = 64 consecutive output pixels
+                    if (p.scale) {  // squeeze-excite: act(gate * BN output), mobilenetv3.py:137-143 (gate >= 0)
+                        const float sc = cg < p.Cexp ? __ldg(p.scale + static_cast<long long>(n) * p.Cexp + cg) : 0.f;
+#pragma unroll
+                        for (int a = 0; a < NR; ++a)
+#pragma unroll
+                            for (int j = 0; j < NC; ++j) acc[a][j] *= sc;
+                    }
                     if (!relu_dw) {
 #pragma unroll
                         for (int a = 0; a < NR; ++a) act3<NC>(acc[a], p.act_dw);
@@ -578,9 +588,9 @@ mbconv_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
 }
 
-template <int K, int S, int REP, bool PROJECT>
+template <int K, int S, int REP, bool PROJECT, int TW>
 int launch_mt(const void* x, long long ldx, int N, const void* w1, const void* w2, MtParams p, cudaStream_t st) {
-    constexpr int TH = S == 1 ? 8 : 4, TW = S == 1 ? 16 : 8;
+    constexpr int TH = S == 1 ? 8 : 4;
     constexpr int IWT = (TW - 1) * S + K, IHT = (TH - 1) * S + K, NPIX = IWT * IHT;
     constexpr int CH = 128 / REP;
     p.ncols = (NPIX + 15) / 16 * 16;
@@ -605,7 +615,12 @@ int launch_mt(const void* x, long long ldx, int N, const void* w1, const void* w
     p.resident = p.nc <= 2 ? 1 : 0;
     p.a1_stage_bytes = p.kb * p.a1_kb_bytes;
     // everything but the A1 ring; the ring takes what is left of 226 KB (static shared memory shares the 227 KB)
-    const int fixed = 2 * p.w1_buf_bytes + 2 * p.w2_buf_bytes + (PROJECT ? 2 * A2_BUF : 0) + 1024 + p.cout_pad * 4 + 1024;
+    p.nw2 = 2;
+    int fixed = 2 * p.w1_buf_bytes + 2 * p.w2_buf_bytes + (PROJECT ? 2 * A2_BUF : 0) + 1024 + p.cout_pad * 4 + 1024;
+    if (PROJECT && !p.resident && (226 * 1024 - fixed) / p.a1_stage_bytes < 2) {  // W2 single buffered: one more patch stage
+        p.nw2 = 1;
+        fixed -= p.w2_buf_bytes;
+    }
     p.ns = std::min(MAX_STAGES, (226 * 1024 - fixed) / p.a1_stage_bytes);
     if (p.ns < 1) {
         cabinet_set_error("mbconv_t: shared-memory budget (%d bytes + the input patch)", fixed);
@@ -613,7 +628,7 @@ int launch_mt(const void* x, long long ldx, int N, const void* w1, const void* w
     }
     p.off_w1 = p.ns * p.a1_stage_bytes;
     p.off_w2 = p.off_w1 + 2 * p.w1_buf_bytes;
-    p.off_a2 = ((p.off_w2 + 2 * p.w2_buf_bytes + 1023) / 1024) * 1024;
+    p.off_a2 = ((p.off_w2 + p.nw2 * p.w2_buf_bytes + 1023) / 1024) * 1024;
     p.off_b2 = p.off_a2 + (PROJECT ? 2 * A2_BUF : 0);
     const size_t smem = static_cast<size_t>(p.off_b2) + p.cout_pad * 4 + 1024;
     CUtensorMap tmX, tmW1, tmW2;
@@ -650,10 +665,10 @@ int launch_mt(const void* x, long long ldx, int N, const void* w1, const void* w
     p.step[2] = grid / (p.tiles_w * p.tiles_h);
     static bool attr_done = false;
     if (!attr_done) {
-        CAB_CUDA(cudaFuncSetAttribute(mbconv_t_kernel<K, S, REP, PROJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        CAB_CUDA(cudaFuncSetAttribute(mbconv_t_kernel<K, S, REP, PROJECT, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_done = true;
     }
-    mbconv_t_kernel<K, S, REP, PROJECT><<<grid, NTHREADS, smem, st>>>(tmX, tmW1, tmW2, p);
+    mbconv_t_kernel<K, S, REP, PROJECT, TW><<<grid, NTHREADS, smem, st>>>(tmX, tmW1, tmW2, p);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }
@@ -663,9 +678,10 @@ int launch_mt(const void* x, long long ldx, int N, const void* w1, const void* w
 extern "C" int cabinet_mbconv_t(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_expand_t,
                                 const float* aux_t, int Cexp, int act_expand, int k, int stride, int act_dw,
                                 const void* w_project, const float* b_project, int Cout, int residual, void* y,
-                                long long ldy, int OH, int OW, long long* gap_sum, cabinet_stream_t stream) {
+                                long long ldy, int OH, int OW, long long* gap_sum, const float* se_scale,
+                                cabinet_stream_t stream) {
     CAB_REQUIRE(x && w_expand_t && aux_t && y, "mbconv_t: null pointer");
-    CAB_REQUIRE((k == 3 && (stride == 1 || stride == 2)) || (k == 5 && stride == 1), "mbconv_t: k3 s1|s2 or k5 s1");
+    CAB_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2), "mbconv_t: k must be 3|5 and stride 1|2");
     CAB_REQUIRE(N >= 0 && H > 0 && W > 0 && Cin > 0 && Cin <= 248 && Cin % 8 == 0 && Cin % 64 <= 56 && Cexp > 0 &&
                     Cexp % 8 == 0 && Cexp <= 1024,
                 "mbconv_t: needs Cin %% 8 == 0, Cin %% 64 <= 56, Cin <= 248 and Cexp %% 8 == 0 (got Cin %d, Cexp %d)", Cin, Cexp);
@@ -682,11 +698,10 @@ extern "C" int cabinet_mbconv_t(const void* x, long long ldx, int N, int H, int 
         CAB_REQUIRE(b_project && Cout > 0 && Cout <= 128 && Cout % 8 == 0 && ldy >= Cout && ldy % 8 == 0 &&
                         (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_project) & 15) == 0,
                     "mbconv_t: project needs a bias, Cout %% 8 == 0, Cout <= 128 and 16-byte aligned output pixels");
-        CAB_REQUIRE(k == 3, "mbconv_t: project mode is k = 3 only (TMEM budget)");
         CAB_REQUIRE(!residual || (stride == 1 && Cin == Cout), "mbconv_t: identity needs stride 1, Cin == Cout");
         CAB_REQUIRE(!gap_sum, "mbconv_t: pooling sums exist in the depthwise-output mode only");
     } else {
-        CAB_REQUIRE(ldy >= Cexp && !residual, "mbconv_t: depthwise-output mode writes Cexp channels, no identity");
+        CAB_REQUIRE(ldy >= Cexp && !residual && !se_scale, "mbconv_t: depthwise-output mode writes Cexp channels, no identity, no gate");
     }
     if (N == 0) return CABINET_OK;
     MtParams p;
@@ -699,14 +714,18 @@ extern "C" int cabinet_mbconv_t(const void* x, long long ldx, int N, int H, int 
     p.kb = Cin / 64 + 1;
     p.aux = aux_t; p.b2 = b_project;
     p.res = reinterpret_cast<const bf16*>(x); p.ldres = ldx;
-    p.y = reinterpret_cast<bf16*>(y); p.ldy = ldy; p.gap = gap_sum;
+    p.y = reinterpret_cast<bf16*>(y); p.ldy = ldy; p.gap = gap_sum; p.scale = se_scale;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define CAB_MT(K_, S_, R_)                                                                   \
-    (project ? launch_mt<K_, S_, R_, true>(x, ldx, N, w_expand_t, w_project, p, st)       \
-             : launch_mt<K_, S_, R_, false>(x, ldx, N, w_expand_t, w_project, p, st))
-    if (k == 3 && stride == 1) return rep == 2 ? CAB_MT(3, 1, 2) : CAB_MT(3, 1, 1);
-    if (k == 3 && stride == 2) return rep == 2 ? CAB_MT(3, 2, 2) : CAB_MT(3, 2, 1);
-    return rep == 2 ? launch_mt<5, 1, 2, false>(x, ldx, N, w_expand_t, w_project, p, st)
-                    : launch_mt<5, 1, 1, false>(x, ldx, N, w_expand_t, w_project, p, st);
+#define CAB_MT(K_, S_, R_, TWP_, TWD_)                                                          \
+    (project ? launch_mt<K_, S_, R_, true, TWP_>(x, ldx, N, w_expand_t, w_project, p, st)       \
+             : launch_mt<K_, S_, R_, false, TWD_>(x, ldx, N, w_expand_t, w_project, p, st))
+    if (k == 3 && stride == 1) return rep == 2 ? CAB_MT(3, 1, 2, 16, 16) : CAB_MT(3, 1, 1, 16, 16);
+    if (k == 3 && stride == 2) return rep == 2 ? CAB_MT(3, 2, 2, 8, 8) : CAB_MT(3, 2, 1, 8, 8);
+    // k = 5: 8 x 16 tiles (12 x 20 patch = 240 TMEM columns) leave no room for D2 -> 8 x 8 tiles in project mode
+    if (k == 5 && stride == 1) return rep == 2 ? CAB_MT(5, 1, 2, 8, 16) : CAB_MT(5, 1, 1, 8, 16);
+    // k = 5 stride 2: 4 x 8 tiles behind an 11 x 19 patch (224 TMEM columns): depthwise-output mode only
+    CAB_REQUIRE(!project, "mbconv_t: k5 stride 2 exists in the depthwise-output mode only (TMEM budget)");
+    return rep == 2 ? launch_mt<5, 2, 2, false, 8>(x, ldx, N, w_expand_t, w_project, p, st)
+                    : launch_mt<5, 2, 1, false, 8>(x, ldx, N, w_expand_t, w_project, p, st);
 #undef CAB_MT
 }

@@ -187,6 +187,8 @@ class Engine:
         self.stages = {}
         self.trace, self.trace_filter = None, None
         self.fuse_mbconv = True     # expand + depthwise (+ project) in one kernel (blocks whose tiles fit the shared memory)
+        self.se_from_sums = True    # stride-1 SE blocks: gate from sums of the expanded activation, whole block in one kernel
+        self.t_k5s2 = True          # k5 stride-2 SE blocks (Large f4, f13) through cabinet_mbconv_t as well
         self.use_mbconv_t = True    # ... in the channel-major formulation (cabinet_mbconv_t) where it supports the block
         self.fold_se_relu = True    # ReLU SE blocks: gate folded into per-image project weights (relu(s*d) = s*relu(d))
         self.fold_ffm = True        # FFM gate folded into per-image head-conv weights (no rewrite of the fused feature map)
@@ -492,7 +494,8 @@ class Engine:
         if ev is not None:
             torch.cuda.current_stream(self.dev).wait_event(ev)
 
-    def mbconv_fused(self, x: Map, e: dict, gap: Optional[torch.Tensor], act_dw: Optional[int] = None) -> Map:
+    def mbconv_fused(self, x: Map, e: dict, gap: Optional[torch.Tensor], act_dw: Optional[int] = None,
+                     se_scale: Optional[torch.Tensor] = None) -> Map:
         """Inverted-residual block with the expanded activation kept on chip (reference: mobilenetv3.py:126-159).
         ``gap`` given (SE blocks; [N, Cexp] int64 fixed point, zeroed): returns the pre-SE depthwise output and
         accumulates its pooling sums; else the block output (project + identity included)."""
@@ -500,6 +503,7 @@ class Engine:
         pad = (dw.k - 1) // 2
         OH, OW = _out_size(x.H, dw.k, dw.stride, pad), _out_size(x.W, dw.k, dw.stride, pad)
         project = gap is None
+        assert se_scale is None or project
         cy = pw2.cout if project else dw.c
         out = self.new(x.N, OH, OW, cy)
         nbytes = (x.N * x.H * x.W * x.C + x.N * OH * OW * cy) * 2 + pw1.w.numel() * 2 + dw.w.numel() * 4
@@ -510,8 +514,7 @@ class Engine:
         # (stride-2 blocks with <= 64 expanded channels -- Large f2 -- have 32-pixel tiles with four outputs per thread
         # there: latency bound, 0.33 ms against 0.18 ms for the pixel-major kernel)
         use_t = (self.use_mbconv_t and "w1t" in e and not e.get("no_t") and not (dw.stride == 2 and dw.c <= 64)
-                 and ((dw.k == 3 and (not project or (pw2.cout <= 128 and pw2.cout % 8 == 0)))
-                      or (dw.k == 5 and dw.stride == 1 and not project)))
+                 and (not project or (pw2.cout <= 128 and pw2.cout % 8 == 0 and (dw.k == 3 or dw.stride == 1))))
         if use_t:
             try:
                 self._run("mbconv_t", dw.name.replace(".dw", "") + ("" if project else ".expand+dw"), nbytes, flops,
@@ -519,12 +522,15 @@ class Engine:
                           e["auxt"].data_ptr(), dw.c, pw1.act, dw.k, dw.stride, dw.act if act_dw is None else act_dw,
                           pw2.tc.data_ptr() if project else None, pw2.b.data_ptr() if project else None,
                           pw2.cout if project else 0, 1 if project and s["identity"] else 0, out.ptr, out.ld, OH, OW,
-                          gap.data_ptr() if gap is not None else None, self.stream)
+                          gap.data_ptr() if gap is not None else None,
+                          se_scale.data_ptr() if se_scale is not None else None, self.stream)
                 return out
             except ValueError as err:  # outside the kernel's shared-memory / TMEM budget: the pixel-major kernel
                 if "budget" not in str(err):
                     raise
                 e["no_t"] = True
+        if se_scale is not None:
+            raise ValueError("budget: the squeeze-excite gate input exists in cabinet_mbconv_t only")
         self._run("mbconv_fused", dw.name.replace(".dw", "") + ("" if project else ".expand+dw"), nbytes, flops,
                   self.lib.cabinet_mbconv_fused, x.ptr, x.ld, x.N, x.H, x.W, x.C, e["w1b"].data_ptr(), e["aux"].data_ptr(),
                   dw.c, pw1.act, dw.k, dw.stride, dw.act if act_dw is None else act_dw,
@@ -532,6 +538,31 @@ class Engine:
                   pw2.cout if project else 0, 1 if project and s["identity"] else 0, out.ptr, out.ld, OH, OW,
                   gap.data_ptr() if gap is not None else None, self.stream)
         return out
+
+    def _se_from_sums_ok(self, x: Map, e: dict) -> bool:
+        s, dw, pw2 = e["spec"], e["dw"], e["pw2"]
+        p = (dw.k - 1) // 2
+        if isinstance(self.se_from_sums, (set, frozenset)) and dw.name[:-3] not in self.se_from_sums:
+            return False
+        elif self.se_from_sums is True and dw.k != 3:
+            return False  # k5: the 8 x 8-tile project kernel + the sums pass measured no faster than the three-kernel path
+        return (self.use_mbconv_t and not self.debug and not e.get("no_sums") and not e.get("no_t") and "w1t" in e
+                and s["s"] == 1 and dw.c > 64 and 2 * p <= min(x.H, x.W) and max(x.H, x.W) <= 256
+                and pw2.tc is not None and pw2.cout <= 128 and pw2.cout % 8 == 0)
+
+    def se_block_one_kernel(self, x: Map, e: dict, gap: torch.Tensor) -> Map:
+        """expand_sums -> gate layers -> mbconv_t(se_scale): reference mobilenetv3.py:126-159 with SELayer :68-83.
+        ``gap``: this block's zeroed [N, Cexp] int64 fixed-point pooling accumulator."""
+        dw, pw1 = e["dw"], e["pw1"]
+        N = x.N
+        nsplit = 0  # automatic: about two (image, part) units per persistent CTA
+        name = dw.name.replace(".dw", "")
+        self._run("expand_sums", name + ".sums", N * x.H * x.W * x.C * 2, 2 * N * x.H * x.W * x.C * dw.c,
+                  self.lib.cabinet_expand_sums, x.ptr, x.ld, N, x.H, x.W, x.C, e["w1t"].data_ptr(), e["auxt"].data_ptr(),
+                  dw.c, pw1.act, dw.k, nsplit, gap.data_ptr(), self.stream)
+        scale = self.gate(gap.view(N, -1), x.H * x.W, e["se"], dw.name, True)
+        # expand form: SE on the BN output, then the activation (F10)
+        return self.mbconv_fused(x, e, None, act_dw=e["act"], se_scale=scale)
 
     def gate(self, gap: torch.Tensor, hw: int, G: GateLayer, name: str, fixed: bool = False) -> torch.Tensor:
         """Channel gate of SE / FFM: two batched tiny FC layers (mean -> ReLU hidden -> gate), fp32.  ``fixed``:
@@ -684,10 +715,22 @@ class Engine:
             fuse = (s["expand"] and self.fuse_mbconv and self.use_tc and f.dt == BF16 and f.ld % 8 == 0
                     and f.off % 8 == 0 and s["exp"] % 8 == 0 and ("se" in e or s["out"] <= 160) and "w1b" in e
                     and not e.get("nofuse")
-                    # 5x5 stride-2 tiles are 4 x 8 outputs behind an 11 x 19 halo: measured slower than expand + dwconv_tma
-                    and not (s["k"] == 5 and s["s"] == 2))
+                    # 5x5 stride-2 tiles are 4 x 8 outputs behind an 11 x 19 halo: the pixel-major kernel measured slower
+                    # than expand + dwconv_tma there; the channel-major one takes SE blocks (depthwise-output mode)
+                    and not (s["k"] == 5 and s["s"] == 2 and not (self.use_mbconv_t and self.t_k5s2 and "se" in e)))
             d = None
             gap_fixed = False
+            if fuse and "se" in e and self.se_from_sums and self._se_from_sums_ok(f, e):
+                # stride-1 squeeze-excite block: the gate from border-corrected sums of the expanded activation (its mean
+                # after the depthwise conv is linear in them), then the WHOLE block as one kernel
+                try:
+                    f = self.se_block_one_kernel(f, e, gap_all[2 * gi:2 * gi + 2].view(-1)[: 2 * N * s["exp"]])
+                    gi += 1
+                    continue
+                except ValueError as err:
+                    if "budget" not in str(err):
+                        raise
+                    e["no_sums"] = True
             if fuse:
                 # expand -> depthwise (-> project + identity): the expanded activation never leaves the SM
                 gap = None

@@ -211,12 +211,30 @@ int cabinet_mbconv_fused(const void* x, long long ldx, int N, int H, int W, int 
  *           CH = 64 (Cexp <= 64: one chunk, rows 64..127 repeat rows 0..63) or 128; columns as in cabinet_mbconv_fused
  *           (W_e, then the bias as bf16 hi / lo in columns Cin, Cin + 1); rows of channels >= Cexp are 0.
  * aux_t:    fp32 [nc][k*k + 1][128]: rows 0..k*k-1 = depthwise taps, row k*k = depthwise bias, same row -> channel map.
- * Supported: k = 3 with stride 1 | 2, k = 5 with stride 1 in the depthwise-output mode; Cout <= 128, Cout % 8 == 0.
+ * se_scale (project mode only, may be NULL): fp32 [N][Cexp] squeeze-excite gate; the block then computes
+ *           d = act_dw(se_scale[n][c] * (dw_kxk(h) + b_dw)) -- a whole SE block in one launch once the gate is known
+ *           (cabinet_expand_sums + cabinet_gate_fc obtain it without running the depthwise conv).
+ * Supported: k = 3 with stride 1 | 2, k = 5 with stride 1; Cout <= 128, Cout % 8 == 0.
  * Everything else returns CABINET_ERR_INVALID (the caller falls back to cabinet_mbconv_fused / the unfused kernels). */
 int cabinet_mbconv_t(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_expand_t, const float* aux_t,
                      int Cexp, int act_expand, int k, int stride, int act_dw, const void* w_project,
                      const float* b_project, int Cout, int residual, void* y, long long ldy, int OH, int OW,
-                     long long* gap_sum, cabinet_stream_t stream);
+                     long long* gap_sum, const float* se_scale, cabinet_stream_t stream);
+
+/* Squeeze-excite pooling sums without the depthwise conv (stride-1 blocks; src/models/mobilenetv3.py:68-83,126-143): the
+ * sum of d = dw_kxk(h) + b_dw over the pixels is linear in the expanded activation h = act_expand(W_e x + b_e):
+ *   sum d = HW b_dw + sum_taps w_dw[ky][kx] * R(ky - p, kx - p),  R(dy, dx) = T - (border rows the tap never reads)
+ *   - (border columns it never reads) + (their corner overlap),  p = (k - 1) / 2,
+ * i.e. it only takes the total T of h, the sums of its first / last p rows and columns and 2p x 2p corner values.
+ * The expand GEMM runs on tcgen05, channel-major (TMEM lane = channel): a thread adds up the columns of its lane.
+ * gap_sum: [N][Cexp] int64 fixed point (CABINET_GAP_FIXED_ONE), zeroed by the caller: receives sum d exactly like the
+ *          pooling output of cabinet_dwconv_tma / cabinet_mbconv_fused (nsplit + 1 integer atomics per entry:
+ *          deterministic) -> cabinet_gate_fc(in_fixed = 1) -> cabinet_mbconv_t(se_scale) runs the block in one launch.
+ * w_expand_t, aux_t as in cabinet_mbconv_t; needs 64 < Cexp, 2p <= H, W <= 256; nsplit in [1, ceil(H / max(1, 256 / W))]
+ * = parts of an image that are added up as separate work units (<= 0: chosen by the library). */
+int cabinet_expand_sums(const void* x, long long ldx, int N, int H, int W, int Cin, const void* w_expand_t,
+                        const float* aux_t, int Cexp, int act_expand, int k, int nsplit, long long* gap_sum,
+                        cabinet_stream_t stream);
 
 /* Squeeze-excite / FFM channel gate: scale[n][c] = gate(b2 + W2 * relu(b1 + W1 * (sum[n]/HW))).
  * Replaces src/models/mobilenetv3.py:68-83 (gate = CABINET_ACT_HSIGMOID, biases present) and

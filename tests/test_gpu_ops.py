@@ -661,7 +661,7 @@ def test_mbconv_t_project(cin, cexp, cout, k, s, H, W, act, res):
     pe, pp = _pack_expand_t(we, be), _pack_tc(wp)
     check(lib.cabinet_mbconv_t(xm.ptr, xm.ld, N, H, W, cin, pe.data_ptr(), aux.data_ptr(), cexp, act, k, s, act,
                                pp.data_ptr(), bpd.data_ptr(), cout, 1 if res else 0, ym.ptr, ym.ld, OH, OW, None,
-                               stream()), "mbconv_t")
+                               None, stream()), "mbconv_t")
     torch.cuda.synchronize()
     err = rel_l2(from_map(ym), ref)
     print(f"mbconv_t {cin}->{cexp}->{cout} k{k} s{s} {H}x{W}: rel_l2 {err:.3e}")
@@ -682,6 +682,9 @@ def test_mbconv_t_project(cin, cexp, cout, k, s, H, W, act, res):
     (48, 144, 5, 1, 17, 23, ACT_HSWISH),    # Small f7-like
     (16, 64, 5, 1, 12, 20, ACT_RELU),       # k5 with replicated lanes
     (16, 48, 3, 2, 22, 14, ACT_RELU),       # stride 2 with replicated lanes, 48 of 64 channels
+    (24, 72, 5, 2, 40, 56, ACT_RELU),       # Large f4 (k5 stride 2)
+    (112, 672, 5, 2, 23, 31, ACT_HSWISH),   # Large f13, odd size
+    (16, 64, 5, 2, 18, 10, ACT_HSWISH),     # k5 stride 2 with replicated lanes
 ])
 def test_mbconv_t_dw_out(cin, cexp, k, s, H, W, act, act_dw):
     """Channel-major expand -> depthwise with the pre-SE output and its pooling sums (squeeze-excite blocks)."""
@@ -704,7 +707,7 @@ def test_mbconv_t_dw_out(cin, cexp, k, s, H, W, act, act_dw):
     for _ in range(2):
         acc = torch.zeros((N, cexp), dtype=torch.int64, device="cuda")
         check(lib.cabinet_mbconv_t(xm.ptr, xm.ld, N, H, W, cin, pe.data_ptr(), aux.data_ptr(), cexp, act, k, s,
-                                   act_dw, None, None, 0, 0, ym.ptr, ym.ld, OH, OW, acc.data_ptr(), stream()),
+                                   act_dw, None, None, 0, 0, ym.ptr, ym.ld, OH, OW, acc.data_ptr(), None, stream()),
               "mbconv_t")
         torch.cuda.synchronize()
         sums.append(acc)
@@ -715,6 +718,79 @@ def test_mbconv_t_dw_out(cin, cexp, k, s, H, W, act, act_dw):
     print(f"mbconv_t(dw out) {cin}->{cexp} k{k} s{s} {H}x{W}: rel_l2 {err:.3e} gap {gerr:.3e}")
     assert err < 4e-3 and gerr < 1e-3
     assert float((ym.t.float()[..., cexp:] - 7.0).abs().max()) == 0
+
+
+@pytest.mark.parametrize("cin,cexp,k,H,W,act,nsplit", [
+    (40, 120, 5, 128, 128, ACT_RELU, 8),     # Large f5 / f6 at their config-2 size
+    (80, 480, 3, 64, 64, ACT_HSWISH, 2),     # Large f11
+    (112, 672, 3, 21, 35, ACT_HSWISH, 3),    # Large f12, odd size (ragged last flat box, ragged 16-column pieces)
+    (160, 960, 5, 32, 32, ACT_HSWISH, 1),    # Large f14 / f15: three K blocks
+    (24, 72, 5, 9, 4, ACT_RELU, 1),          # image as narrow as the border (W = 2p)
+    (48, 144, 3, 200, 13, ACT_HSWISH, 5),    # tall image: one row per flat box would be too few pixels -> 19 rows per box
+])
+def test_expand_sums(cin, cexp, k, H, W, act, nsplit):
+    """Pooling sums of the depthwise BN output from border-corrected sums of the expanded activation (no depthwise conv
+    is run) vs the sum over the real depthwise output (mobilenetv3.py:68-83,137-143); deterministic."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    N = 3
+    x = q(gen(N, cin, H, W, seed=1), dtype)
+    we, be = q(gen(cexp, cin, 1, 1, seed=2, scale=cin ** -0.5), dtype), gen(cexp, seed=3, scale=0.2)
+    wd, bd = gen(cexp, 1, k, k, seed=4, scale=1.0 / k), gen(cexp, seed=5, scale=0.1)
+    pad = (k - 1) // 2
+    h = act_ref(F.conv2d(x, we, be), act)
+    ref = F.conv2d(h, wd, bd, 1, pad, 1, cexp).sum(dim=(2, 3))
+    xm = to_map(x, dtype, ld=cin + 8, off=8)
+    pe, aux = _pack_expand_t(we, be), _pack_aux_t(wd, bd)
+    sums = []
+    for _ in range(2):
+        acc = torch.zeros((N, cexp), dtype=torch.int64, device="cuda")
+        check(lib.cabinet_expand_sums(xm.ptr, xm.ld, N, H, W, cin, pe.data_ptr(), aux.data_ptr(), cexp, act, k, nsplit,
+                                      acc.data_ptr(), stream()), "expand_sums")
+        torch.cuda.synchronize()
+        sums.append(acc)
+    assert torch.equal(sums[0], sums[1])
+    gap = sums[0].double().mul(2.0 ** -24).float().cpu()
+    err = float((gap - ref).abs().max() / ref.abs().max())
+    print(f"expand_sums {cin}->{cexp} k{k} {H}x{W}: max err / max |sum| {err:.3e}")
+    assert err < 2e-5
+
+
+@pytest.mark.parametrize("cin,cexp,cout,k,H,W,act,res", [
+    (40, 120, 40, 5, 24, 40, ACT_RELU, True),        # Large f5 / f6 (k5 project mode: 8 x 8 tiles)
+    (80, 480, 112, 3, 20, 28, ACT_HSWISH, False),    # Large f11
+    (112, 672, 112, 3, 21, 35, ACT_HSWISH, True),    # Large f12
+    (16, 64, 24, 5, 13, 9, ACT_HSWISH, False),       # k5 with replicated lanes
+])
+def test_mbconv_t_se_block(cin, cexp, cout, k, H, W, act, res):
+    """Whole squeeze-excite block in one launch once the gate is known: project(act(gate * (dw(h) + b))) (+ x)."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    N = 2
+    x = q(gen(N, cin, H, W, seed=1), dtype)
+    we, be = q(gen(cexp, cin, 1, 1, seed=2, scale=cin ** -0.5), dtype), gen(cexp, seed=3, scale=0.2)
+    wd, bd = gen(cexp, 1, k, k, seed=4, scale=1.0 / k), gen(cexp, seed=5, scale=0.1)
+    wp, bp = q(gen(cout, cexp, 1, 1, seed=6, scale=cexp ** -0.5), dtype), gen(cout, seed=7, scale=0.1)
+    gate = torch.rand((N, cexp), generator=torch.Generator().manual_seed(8))
+    pad = (k - 1) // 2
+    h = act_ref(F.conv2d(x, we, be), act)
+    d = q(act_ref(F.conv2d(h, wd, bd, 1, pad, 1, cexp) * gate[:, :, None, None], act), dtype)
+    ref = F.conv2d(d, wp, bp)
+    if res:
+        ref = ref + x
+    xm = to_map(x, dtype)
+    ym = to_map(torch.zeros_like(ref), dtype, ld=cout + 8, off=0)
+    ym.t.fill_(7.0)
+    aux, bpd, gd = _pack_aux_t(wd, bd), bp.cuda(), gate.cuda()
+    pe, pp = _pack_expand_t(we, be), _pack_tc(wp)
+    check(lib.cabinet_mbconv_t(xm.ptr, xm.ld, N, H, W, cin, pe.data_ptr(), aux.data_ptr(), cexp, act, k, 1, act,
+                               pp.data_ptr(), bpd.data_ptr(), cout, 1 if res else 0, ym.ptr, ym.ld, H, W, None,
+                               gd.data_ptr(), stream()), "mbconv_t")
+    torch.cuda.synchronize()
+    err = rel_l2(from_map(ym), ref)
+    print(f"mbconv_t SE block {cin}->{cexp}->{cout} k{k} {H}x{W}: rel_l2 {err:.3e}")
+    assert err < 6e-3
+    assert float((ym.t.float()[..., cout:] - 7.0).abs().max()) == 0
 
 
 @pytest.mark.parametrize("C,J,gate,bias,fixed,plus,taps", [(120, 32, ACT_HSIGMOID, True, True, False, 1),
