@@ -166,7 +166,7 @@ class Engine:
     # everything ``_pack`` produces (what ``checkpoint.save_packed`` caches)
     PACKED_ATTRS = ("stem", "blocks", "last", "stem_tc", "sb1", "sb2", "sb3", "sb4", "conva", "to_q", "to_k", "to_v",
                     "psp_k", "psp_v", "proj_out", "local", "gamma", "convb", "b1", "b4", "key_ch", "qkv", "ffm_blk",
-                    "ffm_gate", "head_conv", "head_out", "ffm_sb", "low_fold")
+                    "ffm_gate", "head_conv", "head_out", "ffm_sb", "low_fold", "stem_tc2")
 
     def __init__(self, model, precision: str = "bf16", packed: Optional[dict] = None):
         if precision not in ("bf16", "fp32"):
@@ -188,6 +188,7 @@ class Engine:
         self.trace, self.trace_filter = None, None
         self.fuse_mbconv = True     # expand + depthwise (+ project) in one kernel (blocks whose tiles fit the shared memory)
         self.se_from_sums = True    # stride-1 SE blocks: gate from sums of the expanded activation, whole block in one kernel
+        self.use_stem2 = True       # stems without the im2col tile (cabinet_stem_tc2)
         self.t_k5s2 = True          # k5 stride-2 SE blocks (Large f4, f13) through cabinet_mbconv_t as well
         self.use_mbconv_t = True    # ... in the channel-major formulation (cabinet_mbconv_t) where it supports the block
         self.fold_se_relu = True    # ReLU SE blocks: gate folded into per-image project weights (relu(s*d) = s*relu(d))
@@ -289,7 +290,7 @@ class Engine:
         self.last = ConvLayer(mob.conv[0], mob.conv[1], ACT_HSWISH, wd, "mobile.conv")
 
         sb = m.sb
-        self.stem_tc = None
+        self.stem_tc = self.stem_tc2 = None
         if self.precision == "bf16":
             # fused stems: [80][192] bf16, k = (c*7 + ky)*8 + kx; the 3x3 stem sits in the centre of a 7x7 footprint
             w7, b7 = _fold(sb.conv1.conv.weight, None, sb.conv1.bn)
@@ -304,6 +305,12 @@ class Engine:
             b_hi = bias.to(torch.bfloat16).float()
             wk[:, 168], wk[:, 169] = b_hi, bias - b_hi  # bias rides in two spare K slots (A feeds 1.0 there)
             self.stem_tc = (wk.to(torch.bfloat16).contiguous(), bias)
+            # cabinet_stem_tc2: W[o][ky][kx][c] (c = 3: the constant-1 channel, carrying the bias at the centre pixel) as
+            # UMMA core matrices [ky][K half][k chunk][o][8]
+            wn = torch.zeros((80, 7, 8, 4), dtype=torch.float32, device=w7.device)
+            wn[..., :3] = pk.permute(0, 2, 3, 1)
+            wn[:, 3, 4, 3], wn[:, 3, 5, 3] = b_hi, bias - b_hi
+            self.stem_tc2 = wn.view(80, 7, 2, 2, 8).permute(1, 2, 3, 0, 4).contiguous().to(torch.bfloat16)
         self.sb1 = ConvLayer(sb.conv1.conv, sb.conv1.bn, ACT_RELU, f32, "sb.conv1")
         self.sb2 = ConvLayer(sb.conv2.conv, sb.conv2.bn, ACT_RELU, wd, "sb.conv2")
         self.sb3 = ConvLayer(sb.conv3.conv, sb.conv3.bn, ACT_RELU, wd, "sb.conv3")
@@ -676,9 +683,14 @@ class Engine:
             OH2, OW2 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
             s1, f0 = self.new(N, OH2, OW2, 64), self.new(N, OH2, OW2, 16)
             nbytes = x.numel() * 4 + (s1.t.numel() + f0.t.numel()) * 2 + 80 * 192 * 2
-            self._run("stem_tc", "sb.conv1+mobile.stem", nbytes, 2 * N * OH2 * OW2 * (64 * 147 + 16 * 27),
-                      self.lib.cabinet_stem_tc, x.data_ptr(), N, H, W, self.stem_tc[0].data_ptr(),
-                      self.stem_tc[1].data_ptr(), s1.ptr, s1.ld, f0.ptr, f0.ld, OH2, OW2, self.stream)
+            if self.use_stem2 and self.stem_tc2 is not None:
+                self._run("stem_tc", "sb.conv1+mobile.stem", nbytes, 2 * N * OH2 * OW2 * (64 * 147 + 16 * 27),
+                          self.lib.cabinet_stem_tc2, x.data_ptr(), N, H, W, self.stem_tc2.data_ptr(), s1.ptr, s1.ld,
+                          f0.ptr, f0.ld, OH2, OW2, self.stream)
+            else:
+                self._run("stem_tc", "sb.conv1+mobile.stem", nbytes, 2 * N * OH2 * OW2 * (64 * 147 + 16 * 27),
+                          self.lib.cabinet_stem_tc, x.data_ptr(), N, H, W, self.stem_tc[0].data_ptr(),
+                          self.stem_tc[1].data_ptr(), s1.ptr, s1.ld, f0.ptr, f0.ld, OH2, OW2, self.stream)
         else:
             s1 = self.conv(None, self.sb1, nchw_input=x)
         H8, W8 = _out_size(_out_size(s1.H, 3, 2, 1), 3, 2, 1), _out_size(_out_size(s1.W, 3, 2, 1), 3, 2, 1)

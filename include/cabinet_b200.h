@@ -111,6 +111,15 @@ int cabinet_conv_tc_se(const void* x, long long ldx, int N, int H, int W, int Ci
 int cabinet_stem_tc(const float* x, int N, int H, int W, const void* w_packed, const float* bias, void* y_sb,
                     long long ld_sb, void* y_stem, long long ld_stem, int OH, int OW, cabinet_stream_t stream);
 
+/* The same two stems without an im2col tile: the converter warps write a pixel-interleaved bf16 copy (r, g, b, 1.0) of
+ * the fp32 window and the tensor core reads the overlapping stride-2 rows of the implicit GEMM straight out of it (no-
+ * swizzle K-major descriptor, rows 16 bytes = two pixels apart).  16 x 8 output patches.
+ * w_packed2: bf16 [7 ky][2 K halves][2 k chunks][80 out][8] = UMMA core matrices of W[o][ky][kx][c] (kx = 0..7 with
+ *            kx = 0 zero, c = 0..3 with c = 3 zero except the bias: hi part at (ky 3, kx 4), lo part at (ky 3, kx 5);
+ *            element e = (kx % 2) * 4 + c of chunk (kx / 2) % 2 of half kx / 4); BN folded, rows 64..79 = backbone stem. */
+int cabinet_stem_tc2(const float* x, int N, int H, int W, const void* w_packed2, void* y_sb, long long ld_sb, void* y_stem,
+                     long long ld_stem, int OH, int OW, cabinet_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Depthwise k x k (k in {3,5}, stride in {1,2}, pad (k-1)/2) + folded-BN bias + activation,
  * optional per-(image, channel) sum of the written values for the SE / GAP consumers.

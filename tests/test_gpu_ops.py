@@ -312,6 +312,38 @@ def test_conv_tc(cin, cout, k, s, p, H, W, act, res, out_fp32):
 
 
 @pytest.mark.parametrize("N,H,W", [(2, 64, 64), (1, 37, 52), (3, 128, 96), (1, 21, 8)])
+def test_stem_tc2(N, H, W):
+    """Stems without the im2col tile (overlapping-row UMMA descriptor over the interleaved bf16 window) vs torch."""
+    lib = _lib.load()
+    x = gen(N, 3, H, W, seed=1)
+    w7, b7 = gen(64, 3, 7, 7, seed=2, scale=0.1), gen(64, seed=3, scale=0.1)
+    w3, b3 = gen(16, 3, 3, 3, seed=4, scale=0.2), gen(16, seed=5, scale=0.1)
+    xq = q(x, torch.bfloat16)
+    ref_sb = F.relu(F.conv2d(xq, q(w7, torch.bfloat16), b7, 2, 3))
+    t = F.conv2d(xq, q(w3, torch.bfloat16), b3, 2, 1)
+    ref_st = t * F.relu6(t + 3) / 6
+    OH, OW = ref_sb.shape[2:]
+    pk = torch.zeros(80, 3, 7, 8)
+    pk[:64, :, :, 1:8] = w7
+    pk[64:, :, 2:5, 3:6] = w3
+    bias = torch.cat([b7, b3])
+    wn = torch.zeros(80, 7, 8, 4)               # W[o][ky][kx][c]; c = 3 is the constant-1 channel
+    wn[..., :3] = pk.permute(0, 2, 3, 1)
+    hi = bias.to(torch.bfloat16).float()
+    wn[:, 3, 4, 3], wn[:, 3, 5, 3] = hi, bias - hi
+    wk = wn.view(80, 7, 2, 2, 8).permute(1, 2, 3, 0, 4).contiguous().to("cuda", torch.bfloat16)
+    xd = x.cuda()
+    y_sb = to_map(torch.zeros(N, 64, OH, OW), torch.bfloat16)
+    y_st = to_map(torch.zeros(N, 16, OH, OW), torch.bfloat16)
+    check(lib.cabinet_stem_tc2(xd.data_ptr(), N, H, W, wk.data_ptr(), y_sb.ptr, y_sb.ld, y_st.ptr, y_st.ld, OH, OW,
+                               stream()), "stem_tc2")
+    torch.cuda.synchronize()
+    e1, e2 = rel_l2(from_map(y_sb), ref_sb), rel_l2(from_map(y_st), ref_st)
+    print(f"stem_tc2 {N}x{H}x{W}: sb {e1:.3e} stem {e2:.3e}")
+    assert e1 < 6e-3 and e2 < 6e-3
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 64, 64), (1, 37, 52), (3, 128, 96), (1, 21, 8)])
 def test_stem_tc(N, H, W):
     """Fused 7x7/3x3 stems on tcgen05 vs the two fp32 torch convolutions."""
     lib = _lib.load()
