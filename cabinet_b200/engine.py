@@ -365,14 +365,16 @@ class Engine:
 
     def _run(self, kernel: str, layer: str, nbytes: int, flops: int, fn, *args):
         """Enqueue one kernel.  With tracing on, bracket it with CUDA events on the launching stream and keep
-        its ALGORITHMIC bytes/flops (each operand once) for the roofline report."""
+        its ALGORITHMIC bytes/flops (each operand once) for the roofline report.  ``nbytes`` may be a pair
+        (per-layer-fusion model bytes of SURVEY 8d, bytes the block-fused kernel itself has to move)."""
+        nbytes, fused_bytes = nbytes if isinstance(nbytes, tuple) else (nbytes, nbytes)
         tr = self.trace
         if tr is not None and (self.trace_filter is None or kernel in self.trace_filter):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             rc = fn(*args)
             e1.record()
-            tr.append((kernel, layer, nbytes, flops, e0, e1))
+            tr.append((kernel, layer, nbytes, flops, e0, e1, fused_bytes))
         else:
             rc = fn(*args)
         check(rc, f"{kernel}[{layer}]")
@@ -515,9 +517,15 @@ class Engine:
         out = self.new(x.N, OH, OW, cy)
         nbytes = (x.N * x.H * x.W * x.C + x.N * OH * OW * cy) * 2 + pw1.w.numel() * 2 + dw.w.numel() * 4
         flops = 2 * x.N * x.H * x.W * x.C * dw.c + 2 * x.N * OH * OW * dw.c * dw.k * dw.k
+        # SURVEY 8(d)'s per-layer-fusion model: the expand conv writes / the depthwise conv reads the expanded tensor, the
+        # depthwise conv writes / the project conv reads its output -- traffic this kernel keeps on chip
+        model = nbytes + 2 * x.N * x.H * x.W * dw.c * 2 + (2 * x.N * OH * OW * dw.c * 2 if project else 0)
         if project:
-            nbytes += pw2.w.numel() * 2 + (x.N * OH * OW * cy * 2 if s["identity"] else 0)
+            extra = pw2.w.numel() * 2 + (x.N * OH * OW * cy * 2 if s["identity"] else 0)
+            nbytes += extra
+            model += extra
             flops += 2 * x.N * OH * OW * dw.c * pw2.cout
+        nbytes = (model, nbytes)
         # (stride-2 blocks with <= 64 expanded channels -- Large f2 -- have 32-pixel tiles with four outputs per thread
         # there: latency bound, 0.33 ms against 0.18 ms for the pixel-major kernel)
         use_t = (self.use_mbconv_t and "w1t" in e and not e.get("no_t") and not (dw.stride == 2 and dw.c <= 64)
@@ -1087,6 +1095,7 @@ class Engine:
     def stop_trace(self):
         """-> list of dict(kernel, layer, bytes, flops, ms); synchronises."""
         torch.cuda.synchronize(self.dev)
-        rows = [dict(kernel=k, layer=l, bytes=b, flops=f, ms=e0.elapsed_time(e1)) for k, l, b, f, e0, e1 in self.trace]
+        rows = [dict(kernel=k, layer=l, bytes=b, flops=f, ms=e0.elapsed_time(e1), fused_bytes=fb)
+                for k, l, b, f, e0, e1, fb in self.trace]
         self.trace = None
         return rows

@@ -10,7 +10,8 @@ import json
 import re
 import sys
 
-FAMILIES = [("conv_tc", r"conv_tc"), ("mbconv_fused", r"mbconv_fused_kernel"), ("mbconv_noexpand_fused", r"mbconv1_fused"),
+FAMILIES = [("conv_tc", r"conv_tc"), ("mbconv_t", r"mbconv_t_kernel"), ("expand_sums", r"expand_sums"),
+            ("mbconv_fused", r"mbconv_fused_kernel"), ("mbconv_noexpand_fused", r"mbconv1_fused"),
             ("dwconv_tma", r"dwconv_tma"), ("stem_tc", r"stem_tc"), ("gate_fc", r"gate_fc"), ("scale_act", r"scale_act"),
             ("scale_weights", r"scale_weights"), ("upsample_logits_nchw", r"upsample_logits_nchw"),
             ("upsample_argmax", r"upsample_argmax"), ("bilinear_nhwc", r"bilinear"), ("channel_sum", r"channel_sum"),
