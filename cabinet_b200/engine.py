@@ -189,6 +189,7 @@ class Engine:
         self.fuse_mbconv = True     # expand + depthwise (+ project) in one kernel (blocks whose tiles fit the shared memory)
         self.se_from_sums = True    # stride-1 SE blocks: gate from sums of the expanded activation, whole block in one kernel
         self.use_stem2 = True       # stems without the im2col tile (cabinet_stem_tc2)
+        self.t_small_s2 = False     # stride-2 blocks with <= 64 expanded channels (Large f2) through cabinet_mbconv_t too
         self.t_k5s2 = True          # k5 stride-2 SE blocks (Large f4, f13) through cabinet_mbconv_t as well
         self.use_mbconv_t = True    # ... in the channel-major formulation (cabinet_mbconv_t) where it supports the block
         self.fold_se_relu = True    # ReLU SE blocks: gate folded into per-image project weights (relu(s*d) = s*relu(d))
@@ -528,7 +529,8 @@ class Engine:
         nbytes = (model, nbytes)
         # (stride-2 blocks with <= 64 expanded channels -- Large f2 -- have 32-pixel tiles with four outputs per thread
         # there: latency bound, 0.33 ms against 0.18 ms for the pixel-major kernel)
-        use_t = (self.use_mbconv_t and "w1t" in e and not e.get("no_t") and not (dw.stride == 2 and dw.c <= 64)
+        use_t = (self.use_mbconv_t and "w1t" in e and not e.get("no_t")
+                 and not (dw.stride == 2 and dw.c <= 64 and not self.t_small_s2)
                  and (not project or (pw2.cout <= 128 and pw2.cout % 8 == 0 and (dw.k == 3 or dw.stride == 1))))
         if use_t:
             try:

@@ -1,0 +1,41 @@
+"""Per-call trace of one bf16 training step (Large, batch 8, 1024x1024): python tools/trace_train.py [min_ms]"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from cabinet_b200.loss import OhemCELoss  # noqa: E402
+from cabinet_b200.synthetic import build_model, make_input, make_labels  # noqa: E402
+
+MIN_MS = float(sys.argv[1]) if len(sys.argv) > 1 else 0.12
+B, S, C = 8, 1024, 8
+model = build_model(C, "large").cuda().train()
+model.train_precision = "bf16"
+model.logits_dtype = torch.bfloat16
+x, lb = make_input(B, S, S).cuda(), make_labels(B, S, S, C).cuda()
+crit = OhemCELoss(0.7, B * S * S // 16, 255)
+
+
+def step():
+    model.zero_grad(set_to_none=True)
+    out, out16 = model(x)
+    (crit(out, lb) + crit(out16, lb)).backward()
+
+
+for _ in range(2):
+    step()
+eng = model.train_engine()
+eng.start_trace()
+step()
+rows = eng.stop_trace()
+tot = sum(r[2] for r in rows)
+print(f"{len(rows)} calls, {tot:.2f} ms traced")
+fam = {}
+for i, (n, ph, ms) in enumerate(rows):
+    fam.setdefault((n, ph), [0, 0.0])
+    fam[(n, ph)][0] += 1
+    fam[(n, ph)][1] += ms
+    if ms >= MIN_MS:
+        print(f"{i:5d} {ph} {n:34s} {ms:7.3f} ms")
+for (n, ph), (c, ms) in sorted(fam.items(), key=lambda kv: -kv[1][1])[:20]:
+    print(f"{ph} {n:34s} x{c:3d} {ms:7.2f} ms")
