@@ -34,6 +34,7 @@ struct OhemWs {
     float sel_thresh;          // select l > sel_thresh ...
     float tie_value, tie_frac; // ... plus tie_frac of the pixels with l == tie_value
     float inv_m, loss;
+    unsigned int n_nonfinite;  // valid pixels whose loss is NaN / Inf (overflowed logits): the loss and the gradients become NaN
 };
 
 template <typename T> __device__ __forceinline__ float ld_logit(const T* p);
@@ -122,6 +123,7 @@ ohem_ce_px_kernel(const T* __restrict__ logits, const void* __restrict__ labels,
     const int n = blockIdx.y;
     const T* base = logits + static_cast<long long>(n) * C * HW;
     unsigned long long nv = 0, ng = 0;
+    unsigned int bad = 0;
     double sg = 0.0;
     // 4 pixels per thread when every class plane is 16-byte aligned (HW % 8 == 0 covers bf16 too)
     const bool vec = (HW & 7) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
@@ -138,7 +140,9 @@ ohem_ce_px_kernel(const T* __restrict__ logits, const void* __restrict__ labels,
             l[p] = -1.f;
             if (lb != ignore_label && lb >= 0 && lb < C) {
                 const float w = weight ? __ldg(weight + lb) : 1.f;
-                const float v = fmaxf(w * (m[p] + logf(s[p]) - ld_logit<T>(base + lb * HW + i + p)), 0.f);
+                const float raw = w * (m[p] + logf(s[p]) - ld_logit<T>(base + lb * HW + i + p));
+                if (!isfinite(raw)) ++bad;  // fmaxf would turn a NaN into 0: the reference propagates it (GradScaler then skips the step)
+                const float v = fmaxf(raw, 0.f);
                 l[p] = __uint_as_float(__float_as_uint(v) & 0x7fffffffu);
                 ++nv;
                 if (l[p] > thresh) {
@@ -155,7 +159,11 @@ ohem_ce_px_kernel(const T* __restrict__ logits, const void* __restrict__ labels,
         const long long o = static_cast<long long>(n) * HW + i;
         const long long lb = ld_label(labels, label_dtype, o);
         float l = -1.f;
-        if (lb != ignore_label) l = pixel_ce<T>(base + i, C, HW, lb, weight, nullptr, nullptr);
+        if (lb != ignore_label) {
+            float mm, ss;
+            l = pixel_ce<T>(base + i, C, HW, lb, weight, &mm, &ss);
+            if (l >= 0.f && !(isfinite(l) && isfinite(mm) && isfinite(ss) && ss > 0.f)) ++bad;
+        }
         loss_px[o] = l;
         if (l >= 0.f) {
             ++nv;
@@ -166,6 +174,7 @@ ohem_ce_px_kernel(const T* __restrict__ logits, const void* __restrict__ labels,
             atomicAdd(&s_hist[__float_as_uint(l) >> 20], 1u);
         }
     }
+    if (bad) atomicAdd(&ws->n_nonfinite, bad);
     // block reduction of the three scalars (warp shuffles, then one shared atomic per warp)
     for (int d = 16; d > 0; d >>= 1) {
         nv += __shfl_down_sync(0xffffffffu, nv, d);
@@ -237,6 +246,14 @@ __global__ void ohem_finish_kernel(OhemWs* __restrict__ ws, float* __restrict__ 
     const double k = static_cast<double>(ws->k);
     ws->loss = static_cast<float>((ws->sum_above + static_cast<double>(ws->k_rem) * static_cast<double>(ws->tie_value)) / k);
     *loss_out = ws->loss;
+}
+
+// Non-finite per-pixel losses (NaN / Inf logits): the loss becomes NaN, as with the reference's F.cross_entropy.
+__global__ void ohem_nonfinite_kernel(OhemWs* __restrict__ ws, float* __restrict__ loss_out) {
+    if (ws->n_nonfinite) {
+        ws->loss = __int_as_float(0x7fc00000);
+        *loss_out = ws->loss;
+    }
 }
 
 // One block of 1024 threads.  level 0 also decides the mode; level 2 finishes the selection and writes the loss.
@@ -317,7 +334,7 @@ ohem_ce_bwd_kernel(const T* __restrict__ logits, const void* __restrict__ labels
                    const float* __restrict__ grad_out, T* __restrict__ grad_logits) {
     const int n = blockIdx.y;
     const float sel = ws->sel_thresh, tie_v = ws->tie_value, tie_f = ws->tie_frac;
-    const float g = __ldg(grad_out) * ws->inv_m;
+    const float g = ws->n_nonfinite ? __int_as_float(0x7fc00000) : __ldg(grad_out) * ws->inv_m;  // NaN loss -> NaN gradients
     const T* base = logits + static_cast<long long>(n) * C * HW;
     T* gbase = grad_logits + static_cast<long long>(n) * C * HW;
     const bool vec = (HW & 7) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
@@ -416,6 +433,7 @@ extern "C" int cabinet_ohem_ce_forward(const void* logits, int dtype, const void
     ohem_pick_kernel<<<1, 1024, 0, s>>>(2, thresh, n_min, ws, loss_out);
     ohem_sum_above_kernel<<<hgrid, 256, 0, s>>>(loss_px, total, ws);
     ohem_finish_kernel<<<1, 1, 0, s>>>(ws, loss_out);
+    ohem_nonfinite_kernel<<<1, 1, 0, s>>>(ws, loss_out);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

@@ -113,3 +113,18 @@ def test_reference_unit_test_expectations():
     with pytest.raises(RuntimeError):
         crit(torch.randn(1, 19, 8, 8), torch.zeros(1, 8, 8, dtype=torch.long))  # no CPU path
     assert "thresh=0.7" in repr(crit)
+
+
+@pytest.mark.parametrize("hw", [(16, 24), (7, 9)])  # vectorised and scalar pixel paths
+@pytest.mark.parametrize("bad", [float("nan"), float("inf")])
+def test_nonfinite_logits_give_a_nan_loss(hw, bad):
+    """Overflowed / NaN logits must not turn into a finite loss with zero gradient: the reference's F.cross_entropy
+    propagates them (GradScaler then skips the step and backs off, src/scripts/train.py:436-441)."""
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn((2, 5) + hw, generator=g)
+    labels = torch.randint(0, 5, (2,) + hw, generator=g)
+    ref_ok, _ = run_ours(logits, labels, 0.7, 8, None)
+    assert torch.isfinite(ref_ok)
+    logits[1, int(labels[1, 3, 4]), 3, 4] = bad if bad != bad else -bad  # the target logit of one valid pixel
+    loss, grad = run_ours(logits, labels, 0.7, 8, None)
+    assert torch.isnan(loss) and torch.isnan(grad).any()
