@@ -31,6 +31,24 @@ __device__ __forceinline__ float act_grad(float u, int act) {
     }
 }
 
+// ... over a small register array: ONE uniform branch per call, straight-line code per case (a switch per element is an
+// indirect branch per element: it made the BN backward passes instruction bound)
+template <int N> __device__ __forceinline__ void act_grad_vec(const float* u, int act, float* d) {
+    if (act == CABINET_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) d[i] = u[i] > 0.f ? 1.f : 0.f;
+    } else if (act == CABINET_ACT_HSWISH) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) d[i] = u[i] <= -3.f ? 0.f : (u[i] >= 3.f ? 1.f : fmaf(u[i], 1.f / 3.f, 0.5f));
+    } else if (act == CABINET_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) d[i] = 1.f;
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) d[i] = act_grad(u[i], act);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Column reductions over the pixel dimension: out[q][c] = sum over rows m of f_q(m, c), q < NQ.
 // Level 1: block b reduces rows [b * rows_per_block, ...) -> partial[b][q][c] (fixed order inside the block);
@@ -261,12 +279,15 @@ bn_bwd_reduce_v_kernel(const T* __restrict__ dy, long long lddy, const T* __rest
             }
             kc = c0;
         }
-        float zv[V], dv[V];
+        float zv[V], dv[V], u[V], ag[V];
         ldv(z + m * ldz + c0, zv);
         ldv(dy + m * lddy + c0, dv);
 #pragma unroll
+        for (int v = 0; v < V; ++v) u[v] = fmaf(zv[v], scale[v], shift[v]);
+        act_grad_vec<V>(u, act, ag);
+#pragma unroll
         for (int v = 0; v < V; ++v) {
-            const float g = dv[v] * act_grad(fmaf(zv[v], scale[v], shift[v]), act);
+            const float g = dv[v] * ag[v];
             acc[v] += g;
             acc[V + v] = fmaf(g, (zv[v] - mean[v]) * invstd[v], acc[V + v]);
         }
@@ -306,17 +327,24 @@ bn_bwd_apply_v_kernel(const T* __restrict__ dy, long long lddy, const T* __restr
             ldv(dz + m * lddz + c0, o);
             if (two) ldv(dz + m2 * lddz + c0, o2);
         }
+        float u[V], ag[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) u[v] = fmaf(zv[v], scale[v], shift[v]);
+        act_grad_vec<V>(u, act, ag);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            const float g = dv[v] * act_grad(fmaf(zv[v], scale[v], shift[v]), act);
+            const float g = dv[v] * ag[v];
             const float r = scale[v] * (g - k1[v] - (zv[v] - mean[v]) * invstd[v] * k2[v]);
             o[v] = accumulate ? o[v] + r : r;
         }
         stv(dz + m * lddz + c0, o);
         if (two) {
 #pragma unroll
+            for (int v = 0; v < V; ++v) u[v] = fmaf(zv2[v], scale[v], shift[v]);
+            act_grad_vec<V>(u, act, ag);
+#pragma unroll
             for (int v = 0; v < V; ++v) {
-                const float g = dv2[v] * act_grad(fmaf(zv2[v], scale[v], shift[v]), act);
+                const float g = dv2[v] * ag[v];
                 const float r = scale[v] * (g - k1[v] - (zv2[v] - mean[v]) * invstd[v] * k2[v]);
                 o2[v] = accumulate ? o2[v] + r : r;
             }
@@ -963,16 +991,21 @@ dw_wgrad_v2_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict
     });
 }
 
-// Line-walking variant: one thread = one output line (n, oy) x one channel pair; it slides a K x K register window of x
-// along the line, so a step costs K * S new 4-byte loads instead of K * K (and no per-pixel index arithmetic).
+// Line-walking variant: one thread = one segment of an output line (n, oy) x one channel pair; it slides a K x K
+// register window of x along the segment, so a step costs K * S new 4-byte loads instead of K * K (and no per-pixel
+// index arithmetic).  Lines are cut into `nseg` segments of `seg_len` pixels so that even a 256-line layer fills the
+// machine (whole lines left 128 blocks of dependent 256-step walks: latency bound, 13x the HBM floor).
 template <typename T, int KK, int S>
 __global__ void __launch_bounds__(RED_THREADS)
 dw_wgrad_line_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx, int H, int W, int C,
-                     int OH, int OW, long long n_lines, long long rpb, float* __restrict__ partial) {
+                     int OH, int OW, long long n_items, int nseg, int seg_len, long long rpb, float* __restrict__ partial) {
     constexpr int K = KK;
     constexpr int pad = (K - 1) / 2;
-    col_reduce_block_v<K * K, 2, false>(n_lines, C, rpb, partial, [&](long long line, int c0, float* acc) {
-        const unsigned lu = static_cast<unsigned>(line);
+    col_reduce_block_v<K * K, 2, false>(n_items, C, rpb, partial, [&](long long item, int c0, float* acc) {
+        const unsigned iu = static_cast<unsigned>(item);
+        const unsigned lu = iu / static_cast<unsigned>(nseg);
+        const int ox0 = static_cast<int>(iu - lu * static_cast<unsigned>(nseg)) * seg_len, ox1 = min(OW, ox0 + seg_len);
+        const long long line = lu;
         const int oy = static_cast<int>(lu % static_cast<unsigned>(OH)), n = static_cast<int>(lu / static_cast<unsigned>(OH));
         const T* xrow[K];
         bool rv[K];
@@ -987,11 +1020,11 @@ dw_wgrad_line_kernel(const T* __restrict__ dy, long long lddy, const T* __restri
         for (int ky = 0; ky < K; ++ky)
 #pragma unroll
             for (int kx = 0; kx < K; ++kx) {
-                const int ix = kx - pad;
+                const int ix = ox0 * S + kx - pad;
                 win[ky][kx] = (rv[ky] && ix >= 0 && ix < W) ? ld2(xrow[ky] + static_cast<long long>(ix) * ldx) : make_float2(0.f, 0.f);
             }
         const T* dyp = dy + line * OW * lddy + c0;
-        for (int ox = 0; ox < OW; ++ox) {
+        for (int ox = ox0; ox < ox1; ++ox) {
             const float2 g = ld2(dyp + static_cast<long long>(ox) * lddy);
 #pragma unroll
             for (int ky = 0; ky < K; ++ky)
@@ -1000,7 +1033,7 @@ dw_wgrad_line_kernel(const T* __restrict__ dy, long long lddy, const T* __restri
                     acc[(ky * K + kx) * 2] = fmaf(g.x, win[ky][kx].x, acc[(ky * K + kx) * 2]);
                     acc[(ky * K + kx) * 2 + 1] = fmaf(g.y, win[ky][kx].y, acc[(ky * K + kx) * 2 + 1]);
                 }
-            if (ox + 1 < OW) {
+            if (ox + 1 < ox1) {
 #pragma unroll
                 for (int ky = 0; ky < K; ++ky) {
 #pragma unroll
@@ -1541,11 +1574,16 @@ extern "C" int cabinet_dwconv_wgrad(const void* dy, long long lddy, const void* 
     if (C % 2 == 0 && lddy % 2 == 0 && ldx % 2 == 0 && (reinterpret_cast<uintptr_t>(dy) & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
         (stride == 1 || stride == 2) && OW >= 8 &&
         cab_ceil_div(static_cast<long long>(N) * OH, 2LL * (RED_THREADS / std::min(RED_THREADS, C / 2))) <= nb) {
-        // line walker: a block reduces 2 lines per pixel lane (its partial rows fit the scratch sized for `nb` blocks)
+        // line walker: a block reduces 2 line segments per pixel lane; as many segments per line as the scratch (sized
+        // for `nb` blocks of partial rows) allows, at least 8 pixels each
         const long long n_lines = static_cast<long long>(N) * OH;
         const int cwv = std::min(RED_THREADS, C / 2), lanes = RED_THREADS / cwv;
         const long long rpb2 = 2LL * lanes;
-        const int nb2 = static_cast<int>(cab_ceil_div(n_lines, rpb2));
+        int nseg = static_cast<int>(std::max<long long>(1, std::min<long long>(OW / 8, nb * rpb2 / n_lines)));
+        const int seg_len = (OW + nseg - 1) / nseg;
+        nseg = (OW + seg_len - 1) / seg_len;
+        const long long n_items = n_lines * nseg;
+        const int nb2 = static_cast<int>(cab_ceil_div(n_items, rpb2));
         const size_t smem2 = RED_THREADS * 2 * k * k * sizeof(float);
         static bool attr_done = false;
         if (!attr_done) {
@@ -1557,7 +1595,7 @@ extern "C" int cabinet_dwconv_wgrad(const void* dy, long long lddy, const void* 
         }
 #define CAB_DWL(T, KK, SS)                                                                                                     \
     dw_wgrad_line_kernel<T, KK, SS><<<nb2, RED_THREADS, smem2, s>>>(reinterpret_cast<const T*>(dy), lddy, reinterpret_cast<const T*>(x), \
-                                                                    ldx, H, W, C, OH, OW, n_lines, rpb2, scratch)
+                                                                    ldx, H, W, C, OH, OW, n_items, nseg, seg_len, rpb2, scratch)
 #define CAB_DWL2(T)                                                                                 \
     do {                                                                                            \
         if (k == 3 && stride == 1) CAB_DWL(T, 3, 1); else if (k == 3) CAB_DWL(T, 3, 2);             \
