@@ -463,6 +463,71 @@ gate_bwd_apply_kernel(const T* __restrict__ dy, long long lddy, const T* __restr
     }
 }
 
+// 16-byte vectorised forms (one thread = one channel vector of a pixel lane of image blockIdx.y: the per-(image, channel)
+// constants stay in registers, no per-element index division, no per-element activation switch)
+template <typename T>
+__global__ void __launch_bounds__(256)
+gate_bwd_apply_v_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ v, long long ldvs,
+                        const float* __restrict__ s, float plus, const float* __restrict__ dm, float inv_hw, int act,
+                        T* __restrict__ dv, long long lddv, long long HW, int C, int accumulate) {
+    constexpr int V = vec_n<T>();
+    const int CV = C / V;
+    const int cv = threadIdx.x % CV, lane = threadIdx.x / CV, lanes = blockDim.x / CV;
+    if (lane >= lanes) return;
+    const int n = blockIdx.y, c0 = cv * V;
+    float sv[V], dmv[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        sv[k] = s ? s[static_cast<long long>(n) * C + c0 + k] + plus : 1.f;
+        dmv[k] = dm ? dm[static_cast<long long>(n) * C + c0 + k] * inv_hw : 0.f;
+    }
+    const long long base = static_cast<long long>(n) * HW;
+    for (long long m = static_cast<long long>(blockIdx.x) * lanes + lane; m < HW; m += static_cast<long long>(gridDim.x) * lanes) {
+        float x[V], g[V], u[V], ag[V], o[V];
+        ldv(v + (base + m) * ldvs + c0, x);
+        ldv(dy + (base + m) * lddy + c0, g);
+        if (accumulate) ldv(dv + (base + m) * lddv + c0, o);
+#pragma unroll
+        for (int k = 0; k < V; ++k) u[k] = x[k] * sv[k];
+        act_grad_vec<V>(u, act, ag);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const float r = fmaf(g[k] * ag[k], sv[k], dmv[k]);
+            o[k] = accumulate ? o[k] + r : r;
+        }
+        stv(dv + (base + m) * lddv + c0, o);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS)
+gate_bwd_reduce_v_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ v, long long ldvs,
+                         const float* __restrict__ s, float plus, int act, long long HW, int C, long long rpb,
+                         float* __restrict__ partial /* [N][nb][C] */) {
+    constexpr int V = vec_n<T>();
+    const int n = blockIdx.y, nb = gridDim.x;
+    const T* dyn = dy + static_cast<long long>(n) * HW * lddy;
+    const T* vn = v + static_cast<long long>(n) * HW * ldvs;
+    const float* sn = s + static_cast<long long>(n) * C;
+    float sv[V];
+    int kc = -1;
+    col_reduce_block_v<1, V>(HW, C, rpb, partial + static_cast<long long>(n) * nb * C, [&](long long m, int c0, float* acc) {
+        if (c0 != kc) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) sv[k] = sn[c0 + k] + plus;
+            kc = c0;
+        }
+        float x[V], g[V], u[V], ag[V];
+        ldv(vn + m * ldvs + c0, x);
+        ldv(dyn + m * lddy + c0, g);
+#pragma unroll
+        for (int k = 0; k < V; ++k) u[k] = x[k] * sv[k];
+        act_grad_vec<V>(u, act, ag);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = fmaf(g[k] * ag[k], x[k], acc[k]);
+    });
+}
+
 // ds[n][c] = sum over the pixels of image n of dy * act'(v * s') * v : one block per (pixel chunk, image); two-level
 template <typename T>
 __global__ void __launch_bounds__(RED_THREADS)
@@ -1425,6 +1490,19 @@ extern "C" int cabinet_gate_apply_backward(const void* dy, long long lddy, const
     if (N == 0) return CABINET_OK;
     const long long M = static_cast<long long>(N) * HW;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int V = dtype == CABINET_F32 ? 4 : 8;
+    if (C % V == 0 && C / V <= 256 && lddy % V == 0 && ldv % V == 0 && lddv % V == 0 && al16(dy) && al16(v) && al16(dv) && N <= 65535) {
+        const int lanes = 256 / (C / V);
+        const unsigned gx = static_cast<unsigned>(std::max<long long>(1, std::min<long long>(cab_ceil_div(HW, 4LL * lanes), 148LL * 16 / N + 1)));
+        dim3 grid(gx, N);
+        CAB_DT2(dtype,
+                (gate_bwd_apply_v_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(dy), lddy, reinterpret_cast<const float*>(v), ldv, s, plus, dm,
+                                                                     inv_hw, act, reinterpret_cast<float*>(dv), lddv, HW, C, accumulate)),
+                (gate_bwd_apply_v_kernel<bf16><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(v), ldv, s, plus, dm,
+                                                                    inv_hw, act, reinterpret_cast<bf16*>(dv), lddv, HW, C, accumulate)));
+        CAB_LAUNCH_CHECK();
+        return CABINET_OK;
+    }
     CAB_DT2(dtype,
             (gate_bwd_apply_kernel<float><<<ew_grid(M * C), 256, 0, st>>>(reinterpret_cast<const float*>(dy), lddy, reinterpret_cast<const float*>(v), ldv, s, plus,
                                                                          dm, inv_hw, act, reinterpret_cast<float*>(dv), lddv, M, HW, C, accumulate)),
@@ -1442,6 +1520,19 @@ extern "C" int cabinet_gate_scale_backward(const void* dy, long long lddy, const
     const int nb = red_blocks(HW, &rpb);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid(nb, N);
+    const int V = dtype == CABINET_F32 ? 4 : 8;
+    if (C % V == 0 && lddy % V == 0 && ldv % V == 0 && al16(dy) && al16(v)) {
+        CAB_DT2(dtype,
+                (gate_bwd_reduce_v_kernel<float><<<grid, RED_THREADS, red_smem_v<float>(1), st>>>(reinterpret_cast<const float*>(dy), lddy,
+                                                                                                 reinterpret_cast<const float*>(v), ldv, s, plus, act, HW, C, rpb, scratch)),
+                (gate_bwd_reduce_v_kernel<bf16><<<grid, RED_THREADS, red_smem_v<bf16>(1), st>>>(reinterpret_cast<const bf16*>(dy), lddy,
+                                                                                               reinterpret_cast<const bf16*>(v), ldv, s, plus, act, HW, C, rpb, scratch)));
+        CAB_LAUNCH_CHECK();
+        sum_partials_kernel<<<dim3(static_cast<unsigned>(cab_ceil_div(C, 128)), N), 128, 0, st>>>(scratch, nb, C, static_cast<long long>(nb) * C, ds,
+                                                                                                   1.f, 0);
+        CAB_LAUNCH_CHECK();
+        return CABINET_OK;
+    }
     CAB_DT2(dtype,
             (gate_bwd_reduce_kernel<float><<<grid, RED_THREADS, RED_SMEM, st>>>(reinterpret_cast<const float*>(dy), lddy, reinterpret_cast<const float*>(v), ldv,
                                                                                s, plus, act, HW, C, rpb, scratch)),
