@@ -1139,16 +1139,19 @@ __global__ void __launch_bounds__(256)
 resample_sep_kernel(const TI* __restrict__ in, long long isn, long long isy, long long isx, long long isc,
                     TO* __restrict__ out, long long osn, long long osy, long long osx, long long osc, int N, int OH, int OW,
                     int C, const int* __restrict__ ys, const int* __restrict__ yi, const float* __restrict__ yw,
-                    const int* __restrict__ xs, const int* __restrict__ xi, const float* __restrict__ xw, int accumulate) {
+                    const int* __restrict__ xs, const int* __restrict__ xi, const float* __restrict__ xw, int accumulate,
+                    int x_fastest) {
     const long long total = static_cast<long long>(N) * OH * OW * C;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        // c fastest when the output is channel-contiguous, x fastest otherwise (coalesced stores either way)
+        // c fastest when the output is channel-contiguous, x fastest otherwise (coalesced stores either way) -- or x
+        // fastest on request: a gather of many taps from a planar (NCHW) input wants neighbouring threads on
+        // neighbouring x (the x8 adjoint of the logit gradients reads 256 taps per output)
         // (32-bit index arithmetic: the host checks total < 2^31)
         int c, ox, oy, n;
         unsigned t = static_cast<unsigned>(i);
         const unsigned uC = C, uW = OW, uH = OH;
-        if (osc == 1) {
+        if (osc == 1 && !x_fastest) {
             c = static_cast<int>(t % uC); t /= uC;
             ox = static_cast<int>(t % uW); t /= uW;
             oy = static_cast<int>(t % uH); n = static_cast<int>(t / uH);
@@ -1168,6 +1171,63 @@ resample_sep_kernel(const TI* __restrict__ in, long long isn, long long isy, lon
         TO* o = out + n * osn + oy * osy + ox * osx + c * osc;
         if (accumulate) acc += ldf(o);
         *o = from_f32<TO>(acc);
+    }
+}
+
+// Channel-contiguous (NHWC -> NHWC) form: one thread = 8 channels of one output pixel, 16-byte loads per tap.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+resample_sep_v_kernel(const TI* __restrict__ in, long long isn, long long isy, long long isx, TO* __restrict__ out,
+                      long long osn, long long osy, long long osx, int N, int OH, int OW, int C, const int* __restrict__ ys,
+                      const int* __restrict__ yi, const float* __restrict__ yw, const int* __restrict__ xs,
+                      const int* __restrict__ xi, const float* __restrict__ xw, int accumulate) {
+    const unsigned CV = C / 8;
+    const long long total = static_cast<long long>(N) * OH * OW * CV;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        unsigned t = static_cast<unsigned>(i);
+        const int cv = static_cast<int>(t % CV); t /= CV;
+        const int ox = static_cast<int>(t % static_cast<unsigned>(OW)); t /= static_cast<unsigned>(OW);
+        const int oy = static_cast<int>(t % static_cast<unsigned>(OH)), n = static_cast<int>(t / static_cast<unsigned>(OH));
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        const TI* base = in + n * isn + cv * 8;
+        const int xb0 = xs[ox], xb1 = xs[ox + 1];
+        for (int a = ys[oy]; a < ys[oy + 1]; ++a) {
+            const TI* row = base + yi[a] * isy;
+            const float wy = yw[a];
+            for (int b = xb0; b < xb1; ++b) {
+                const float w = wy * xw[b];
+                float v[8];
+                if constexpr (sizeof(TI) == 2) {
+                    ldv(row + xi[b] * isx, v);
+                } else {
+                    ldv(row + xi[b] * isx, v);
+                    ldv(row + xi[b] * isx + 4, v + 4);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(w, v[k], acc[k]);
+            }
+        }
+        TO* o = out + n * osn + oy * osy + ox * osx + cv * 8;
+        if (accumulate) {
+            float p[8];
+            if constexpr (sizeof(TO) == 2) {
+                ldv(o, p);
+            } else {
+                ldv(o, p);
+                ldv(o + 4, p + 4);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += p[k];
+        }
+        if constexpr (sizeof(TO) == 2) {
+            stv(o, acc);
+        } else {
+            stv(o, acc);
+            stv(o + 4, acc + 4);
+        }
     }
 }
 
@@ -1743,10 +1803,27 @@ extern "C" int cabinet_resample_sep(const void* in, int in_dtype, long long isn,
     const long long total = static_cast<long long>(N) * OH * OW * C;
     CAB_REQUIRE(total < (1LL << 31), "resample_sep: too many output elements");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int x_fastest = (accumulate >> 1) & 1;  // bit 1: gather-friendly thread order (see the kernel)
+    const int few_taps = (accumulate >> 2) & 1;   // bit 2: few taps per output (an upsample, the adjoint of a pool): the
+    accumulate &= 1;                              //        8-channel vector kernel pays (with many taps it starves: 8x fewer threads)
+    if (few_taps && isc == 1 && osc == 1 && C % 8 == 0 && isn % 8 == 0 && isy % 8 == 0 && isx % 8 == 0 && osn % 8 == 0 && osy % 8 == 0 &&
+        osx % 8 == 0 && al16(in) && al16(out)) {
+#define CAB_RSV(TI, TO)                                                                                                        \
+    resample_sep_v_kernel<TI, TO><<<ew_grid(total / 8), 256, 0, s>>>(reinterpret_cast<const TI*>(in), isn, isy, isx,             \
+                                                                     reinterpret_cast<TO*>(out), osn, osy, osx, N, OH, OW, C,    \
+                                                                     y_start, y_index, y_weight, x_start, x_index, x_weight, accumulate)
+        if (in_dtype == CABINET_F32 && out_dtype == CABINET_F32) CAB_RSV(float, float);
+        else if (in_dtype == CABINET_F32) CAB_RSV(float, bf16);
+        else if (out_dtype == CABINET_F32) CAB_RSV(bf16, float);
+        else CAB_RSV(bf16, bf16);
+#undef CAB_RSV
+        CAB_LAUNCH_CHECK();
+        return CABINET_OK;
+    }
 #define CAB_RS(TI, TO)                                                                                                   \
     resample_sep_kernel<TI, TO><<<ew_grid(total), 256, 0, s>>>(reinterpret_cast<const TI*>(in), isn, isy, isx, isc,      \
                                                                reinterpret_cast<TO*>(out), osn, osy, osx, osc, N, OH, OW, C, \
-                                                               y_start, y_index, y_weight, x_start, x_index, x_weight, accumulate)
+                                                               y_start, y_index, y_weight, x_start, x_index, x_weight, accumulate, x_fastest)
     if (in_dtype == CABINET_F32 && out_dtype == CABINET_F32) CAB_RS(float, float);
     else if (in_dtype == CABINET_F32) CAB_RS(float, bf16);
     else if (out_dtype == CABINET_F32) CAB_RS(bf16, float);

@@ -483,9 +483,10 @@ class TrainEngine:
         if out is None:
             out = self.new(src.N, OH, OW, src.C, out_dtype or src.t.dtype)
         ty, tx = self.tables.get(kind, src.H, OH, False), self.tables.get(kind, src.W, OW, False)
+        up = OH * OW >= src.H * src.W  # an upsample reads <= 2 x 2 taps per output, its adjoint many (and vice versa for a pool)
         self._call("cabinet_resample_sep", src.ptr, src.dt, src.H * src.W * src.ld, src.W * src.ld, src.ld, 1, out.ptr, out.dt,
                    OH * OW * out.ld, OW * out.ld, out.ld, 1, src.N, OH, OW, src.C, *(t.data_ptr() for t in ty),
-                   *(t.data_ptr() for t in tx), 0)
+                   *(t.data_ptr() for t in tx), 4 if up else 0)  # bit 2: few taps per output -> vector kernel
 
         def backward(g: _Grads):
             dy = g.get(out)
@@ -495,7 +496,7 @@ class TrainEngine:
             ay, ax = self.tables.get(kind, src.H, OH, True), self.tables.get(kind, src.W, OW, True)
             self._call("cabinet_resample_sep", dy.ptr, dy.dt, OH * OW * dy.ld, OW * dy.ld, dy.ld, 1, dx.ptr, dx.dt,
                        src.H * src.W * dx.ld, src.W * dx.ld, dx.ld, 1, src.N, src.H, src.W, src.C,
-                       *(t.data_ptr() for t in ay), *(t.data_ptr() for t in ax), acc)
+                       *(t.data_ptr() for t in ay), *(t.data_ptr() for t in ax), acc | (0 if up else 4))
 
         self.tape.append(backward)
         return out
