@@ -267,3 +267,37 @@ def test_train_engine_schedule_and_abi(monkeypatch, mode, C, shape, precision):
     trained = {id(p): n for n, p in model.named_parameters() if not n.startswith("mobile.classifier")}
     assert set(grads) == set(trained), [trained[i] for i in set(trained) - set(grads)]
     assert all(grads[id(p)].shape == p.shape for p in model.parameters() if id(p) in grads)
+
+
+def test_fused_block_routing(cpu_engine):
+    """Host logic of the round-2 block kernels: which Large blocks go to the channel-major kernel, the one-kernel SE path
+    (expand_sums -> two gate layers -> mbconv_t with the gate as input) for the stride-1 3x3 SE blocks, and the fall-backs
+    when the flags are off."""
+    eng, rec = cpu_engine("large", 8, "bf16")
+    x = torch.zeros(1, 3, 128, 128)
+    eng.forward_mask(x)
+    calls = [(c[0], c[1]) for c in rec.calls]
+    names = [c[0] for c in calls]
+    assert names.count("cabinet_stem_tc2") == 1 and names.count("cabinet_stem_tc") == 0
+    # f2 (stride 2, 64 expanded channels) stays on the pixel-major kernel, f3 .. f15 are channel-major
+    assert names.count("cabinet_mbconv_fused") == 1 and names.count("cabinet_mbconv_t") == 13
+    assert names.count("cabinet_expand_sums") == 2          # f11, f12
+    with_gate = [a for n, a in calls if n == "cabinet_mbconv_t" and a[-2] is not None]
+    assert len(with_gate) == 2 and all(a[13] is not None for a in with_gate)   # project mode with se_scale
+    assert sorted(a[8] for a in with_gate) == [480, 672]                       # Cexp of f11 / f12
+    # a sums pass is followed by the two gate layers on the fixed-point accumulator it filled
+    i = names.index("cabinet_expand_sums")
+    assert names[i + 1:i + 4] == ["cabinet_gate_fc", "cabinet_gate_fc", "cabinet_mbconv_t"]
+    assert calls[i + 1][1][0] == calls[i][1][-2] and calls[i + 1][1][-2] == 1     # in = gap_sum, in_fixed = 1
+    rec.calls.clear()
+    eng.se_from_sums = False
+    eng.use_stem2 = False
+    eng.forward_mask(x)
+    names = [c[0] for c in rec.calls]
+    assert names.count("cabinet_expand_sums") == 0 and names.count("cabinet_stem_tc") == 1
+    assert names.count("cabinet_mbconv_t") == 13            # f11 / f12: expand + depthwise, then scale / project kernels
+    rec.calls.clear()
+    eng.use_mbconv_t = False
+    eng.forward_mask(x)
+    names = [c[0] for c in rec.calls]
+    assert names.count("cabinet_mbconv_t") == 0 and names.count("cabinet_mbconv_fused") >= 8
