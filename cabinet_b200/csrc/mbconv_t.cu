@@ -30,8 +30,6 @@
 // MMA1 of the next chunks and MMA2 of the previous one all run under the depthwise phase; the warps only meet on
 // mbarriers (no CTA-wide barrier in the steady state).  Expanded widths <= 64 are replicated
 // twice along the TMEM lanes (rows 64..127 of W1 repeat rows 0..63) so that all 128 lanes have a channel to work on.
-#include <cstdlib>
-
 #include "tc_common.cuh"
 
 namespace {
@@ -600,7 +598,6 @@ int launch_mt(const void* x, long long ldx, int N, const void* w1, const void* w
     // of one tile and MMA2 of the next stop serialising), then more D1 stages.
     p.d2_stride = (p.cout_pad + 31) / 32 * 32;
     p.nd2 = PROJECT && 2 * p.ncols + 2 * p.d2_stride <= TMEM_COLS ? 2 : 1;
-    if (const char* e = getenv("CABINET_MT_ND2")) p.nd2 = std::min(p.nd2, std::max(1, atoi(e)));  // experiments
     p.d2col = PROJECT ? TMEM_COLS - p.nd2 * p.d2_stride : TMEM_COLS;
     p.nd = std::min(MAX_STAGES, p.d2col / p.ncols);
     if (p.ncols > 256 || p.nd < 2) {
