@@ -25,9 +25,28 @@ def step():
 for _ in range(2):
     step()
 eng = model.train_engine()
+# keep (M, C) of the BatchNorm calls: achieved bandwidth per call (backward = 5 tensor passes, statistics 1, apply 2)
+shapes = []
+orig_call = eng._call
+
+
+def spy(name, *args):
+    if name == "cabinet_bn_train_backward":
+        shapes.append((len(eng.trace), name, int(args[11]), int(args[12]), 5))
+    elif name == "cabinet_bn_train_stats":
+        shapes.append((len(eng.trace), name, int(args[3]), int(args[4]), 1))
+    return orig_call(name, *args)
+
+
+eng._call = spy
 eng.start_trace()
 step()
 rows = eng.stop_trace()
+eng._call = orig_call
+for idx, name, M, C, passes in shapes:
+    ms = rows[idx][2]
+    if ms >= 0.05:
+        print(f"{idx:5d} {name:28s} M {M:8d} C {C:4d} {ms:6.3f} ms  {passes * M * C * 2 / ms / 1e6:7.0f} GB/s")
 tot = sum(r[2] for r in rows)
 print(f"{len(rows)} calls, {tot:.2f} ms traced")
 fam = {}
