@@ -1172,6 +1172,35 @@ resample_sep_kernel(const TI* __restrict__ in, long long isn, long long isy, lon
     }
 }
 
+// Planar input, many taps per output (the x8 adjoint of the NCHW logit gradients: 16 x 16 taps): one block = one output
+// row of one plane.  Phase 1 adds the rows of the band into a shared-memory line (coalesced reads along x: every input
+// row is read by two blocks), phase 2 applies the x operator from that line.  Same CSR tables -> same result as the
+// generic kernel up to the summation order (fixed).
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+resample_band_kernel(const TI* __restrict__ in, long long isn, long long isy, long long isc, int W_in, TO* __restrict__ out,
+                     long long osn, long long osy, long long osx, long long osc, int C, int OW, const int* __restrict__ ys,
+                     const int* __restrict__ yi, const float* __restrict__ yw, const int* __restrict__ xs,
+                     const int* __restrict__ xi, const float* __restrict__ xw, int accumulate) {
+    extern __shared__ float s_line[];  // [W_in]
+    const int oy = blockIdx.x, n = blockIdx.y / C, c = blockIdx.y - n * C;
+    const TI* plane = in + n * isn + c * isc;
+    const int a0 = ys[oy], a1 = ys[oy + 1];
+    for (int x = threadIdx.x; x < W_in; x += 256) {
+        float acc = 0.f;
+        for (int a = a0; a < a1; ++a) acc = fmaf(yw[a], ldf(plane + yi[a] * isy + x), acc);
+        s_line[x] = acc;
+    }
+    __syncthreads();
+    for (int ox = threadIdx.x; ox < OW; ox += 256) {
+        float acc = 0.f;
+        for (int b = xs[ox]; b < xs[ox + 1]; ++b) acc = fmaf(xw[b], s_line[xi[b]], acc);
+        TO* o = out + n * osn + oy * osy + ox * osx + c * osc;
+        if (accumulate) acc += ldf(o);
+        *o = from_f32<TO>(acc);
+    }
+}
+
 // Channel-contiguous (NHWC -> NHWC) form: one thread = 8 channels of one output pixel, 16-byte loads per tap.
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
@@ -1801,8 +1830,27 @@ extern "C" int cabinet_resample_sep(const void* in, int in_dtype, long long isn,
     const long long total = static_cast<long long>(N) * OH * OW * C;
     CAB_REQUIRE(total < (1LL << 31), "resample_sep: too many output elements");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int band = (accumulate >> 1) & 1;       // bit 1: planar input with many taps per output -> row-band kernel
     const int few_taps = (accumulate >> 2) & 1;   // bit 2: few taps per output (an upsample, the adjoint of a pool): the
     accumulate &= 1;                              //        8-channel vector kernel pays (with many taps it starves: 8x fewer threads)
+    if (band && isx == 1 && static_cast<long long>(N) * C <= 65535) {
+        // the input line length is not an argument: it is what the x operator indexes, i.e. the row pitch of a dense plane
+        const int W_in = static_cast<int>(isy);
+        CAB_REQUIRE(W_in > 0 && W_in * sizeof(float) <= 48 * 1024, "resample_sep: input line too long for the band kernel");
+        dim3 grid(OH, N * C);
+        const size_t smem = W_in * sizeof(float);
+#define CAB_RB(TI, TO)                                                                                                       \
+    resample_band_kernel<TI, TO><<<grid, 256, smem, s>>>(reinterpret_cast<const TI*>(in), isn, isy, isc, W_in,               \
+                                                         reinterpret_cast<TO*>(out), osn, osy, osx, osc, C, OW, y_start, y_index, \
+                                                         y_weight, x_start, x_index, x_weight, accumulate & 1)
+        if (in_dtype == CABINET_F32 && out_dtype == CABINET_F32) CAB_RB(float, float);
+        else if (in_dtype == CABINET_F32) CAB_RB(float, bf16);
+        else if (out_dtype == CABINET_F32) CAB_RB(bf16, float);
+        else CAB_RB(bf16, bf16);
+#undef CAB_RB
+        CAB_LAUNCH_CHECK();
+        return CABINET_OK;
+    }
     if (few_taps && isc == 1 && osc == 1 && C % 8 == 0 && isn % 8 == 0 && isy % 8 == 0 && isx % 8 == 0 && osn % 8 == 0 && osy % 8 == 0 &&
         osx % 8 == 0 && al16(in) && al16(out)) {
 #define CAB_RSV(TI, TO)                                                                                                        \

@@ -72,7 +72,10 @@ class _Tables:
     def get(self, kind: str, n_in: int, n_out: int, transpose: bool):
         key = (kind, n_in, n_out, transpose)
         if key not in self.cache:
-            m = bilinear_matrix(n_in, n_out) if kind == "bilinear" else adaptive_pool_matrix(n_in, n_out)
+            if kind == "identity":
+                m = np.eye(n_in, dtype=np.float64)
+            else:
+                m = bilinear_matrix(n_in, n_out) if kind == "bilinear" else adaptive_pool_matrix(n_in, n_out)
             s, i, w = csr(m.T if transpose else m)
             self.cache[key] = tuple(torch.from_numpy(a).to(self.dev) for a in (s, i, w))
         return self.cache[key]
@@ -478,15 +481,30 @@ class TrainEngine:
         self.tape.append(backward)
         return out
 
+    def _resample_call(self, src: Map, dst: Map, ty, tx, flags: int):
+        self._call("cabinet_resample_sep", src.ptr, src.dt, src.H * src.W * src.ld, src.W * src.ld, src.ld, 1, dst.ptr, dst.dt,
+                   dst.H * dst.W * dst.ld, dst.W * dst.ld, dst.ld, 1, src.N, dst.H, dst.W, src.C,
+                   *(t.data_ptr() for t in ty), *(t.data_ptr() for t in tx), flags)
+
+    def _reduce_two_pass(self, src: Map, dst: Map, ty, tx, acc: int):
+        """A reducing operator with >= 64 taps per output (a pool to 1 x 1 or 3 x 3, the adjoint of the up-sampling of such
+        a map) as two separable passes, first along x, then along y: 32 + 32 taps per output instead of 1024 gathered by
+        one thread (0.22 -> ~0.03 ms for the 1 x 1 PSP bin)."""
+        tmp = self.new(src.N, src.H, dst.W, src.C, torch.float32)
+        self._resample_call(src, tmp, self.tables.get("identity", src.H, src.H, False), tx, 0)
+        self._resample_call(tmp, dst, ty, self.tables.get("identity", dst.W, dst.W, False), acc)
+
     def resample(self, src: Map, kind: str, OH: int, OW: int, out: Optional[Map] = None, out_dtype=None) -> Map:
         """Bilinear resize (align_corners=False) or adaptive average pool of an NHWC map, + its adjoint on the tape."""
         if out is None:
             out = self.new(src.N, OH, OW, src.C, out_dtype or src.t.dtype)
         ty, tx = self.tables.get(kind, src.H, OH, False), self.tables.get(kind, src.W, OW, False)
         up = OH * OW >= src.H * src.W  # an upsample reads <= 2 x 2 taps per output, its adjoint many (and vice versa for a pool)
-        self._call("cabinet_resample_sep", src.ptr, src.dt, src.H * src.W * src.ld, src.W * src.ld, src.ld, 1, out.ptr, out.dt,
-                   OH * OW * out.ld, OW * out.ld, out.ld, 1, src.N, OH, OW, src.C, *(t.data_ptr() for t in ty),
-                   *(t.data_ptr() for t in tx), 4 if up else 0)  # bit 2: few taps per output -> vector kernel
+        many = max(src.H * src.W, OH * OW) >= 64 * min(src.H * src.W, OH * OW)  # >= 64 taps per output on the reducing side
+        if many and not up:
+            self._reduce_two_pass(src, out, ty, tx, 0)
+        else:
+            self._resample_call(src, out, ty, tx, 4 if up else 0)  # bit 2: few taps per output -> vector kernel
 
         def backward(g: _Grads):
             dy = g.get(out)
@@ -494,9 +512,12 @@ class TrainEngine:
                 return
             dx, acc = g.out(src)
             ay, ax = self.tables.get(kind, src.H, OH, True), self.tables.get(kind, src.W, OW, True)
-            self._call("cabinet_resample_sep", dy.ptr, dy.dt, OH * OW * dy.ld, OW * dy.ld, dy.ld, 1, dx.ptr, dx.dt,
-                       src.H * src.W * dx.ld, src.W * dx.ld, dx.ld, 1, src.N, src.H, src.W, src.C,
-                       *(t.data_ptr() for t in ay), *(t.data_ptr() for t in ax), acc | (0 if up else 4))
+            dym = Map(dy.t, dy.N, OH, OW, dy.C, dy.ld, dy.off)
+            dxm = Map(dx.t, dx.N, src.H, src.W, dx.C, dx.ld, dx.off)
+            if many and up:
+                self._reduce_two_pass(dym, dxm, ay, ax, acc)
+            else:
+                self._resample_call(dym, dxm, ay, ax, acc | (0 if up else 4))
 
         self.tape.append(backward)
         return out
@@ -588,7 +609,7 @@ class TrainEngine:
             ay, ax = self.tables.get("bilinear", src.H, H, True), self.tables.get("bilinear", src.W, W, True)
             self._call("cabinet_resample_sep", dy_nchw.data_ptr(), self._dt(dy_nchw), C * H * W, W, 1, H * W, dx.ptr, dx.dt,
                        src.H * src.W * dx.ld, src.W * dx.ld, dx.ld, 1, N, src.H, src.W, C, *(t.data_ptr() for t in ay),
-                       *(t.data_ptr() for t in ax), acc)
+                       *(t.data_ptr() for t in ax), acc | 2)  # bit 1: planar input, 16 x 16 taps -> row-band kernel
 
         return y, backward
 

@@ -476,8 +476,10 @@ int cabinet_dwconv_wgrad(const void* dy, long long lddy, const void* x, long lon
  * operators as CSR tables (start[O+1], index[], weight[]).  Given the TRANSPOSED matrices of a bilinear resize
  * (align_corners=False) or an adaptive average pool it is the exact adjoint: the backward of F.interpolate
  * (src/models/cabinet.py:228-245, cab.py:70-72) and nn.AdaptiveAvgPool2d (cab.py:55-57).  Element strides on both
- * sides (NHWC maps, NCHW logit gradients).  accumulate: bit 0 = add to out; bit 2 = hint that an output has few taps
- * (an upsample, the adjoint of a pool): channel-contiguous maps then take the 8-channel vector kernel. */
+ * sides (NHWC maps, NCHW logit gradients).  accumulate: bit 0 = add to out; bit 1 = the input is planar (isx = 1,
+ * isy = the dense line length) with many taps per output (the x8 adjoint): one block per output row adds the band of
+ * input rows into a shared-memory line, then applies the x operator; bit 2 = an output has few taps (an upsample, the
+ * adjoint of a pool): channel-contiguous maps then take the 8-channel vector kernel. */
 int cabinet_resample_sep(const void* in, int in_dtype, long long isn, long long isy, long long isx, long long isc,
                          void* out, int out_dtype, long long osn, long long osy, long long osx, long long osc, int N, int OH,
                          int OW, int C, const int* y_start, const int* y_index, const float* y_weight, const int* x_start,
