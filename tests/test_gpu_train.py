@@ -477,3 +477,45 @@ def test_train_mode_surface():
     f2 = model(x)[0]
     assert not torch.equal(f2, f_eval)   # the running statistics moved: the inference pack was rebuilt from them
     assert torch.isfinite(f2).all()
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_train_step_graph_replay_is_bit_identical_to_eager(precision):
+    """The captured forward / backward graphs (TrainEngine.step_forward) against the eager schedule over an SGD run:
+    logits, loss, every gradient and the BatchNorm running statistics bit for bit, with new inputs every step, an unused
+    auxiliary output, and a re-capture after the parameters moved."""
+    C, N, H, W = 5, 2, 96, 64
+    models = []
+    for use_graph in (False, True):
+        m = build_model(C, "small").cuda().train()
+        m.train_precision = precision
+        m.train_engine().use_graph = use_graph
+        models.append((m, torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9)))
+    crit = OhemCELoss(0.7, N * H * W // 16, 255)
+    eng = models[1][0].train_engine()
+    for step in range(9):
+        x = make_input(N, H, W, seed=step).cuda()
+        lb = make_labels(N, H, W, C, seed=step).cuda()
+        if step == 6:  # parameters move (what .to() / .half() / a reload into new storage do): the graphs are re-captured
+            for m, _ in models:
+                for p in m.parameters():
+                    p.data = p.data.clone()
+        res = []
+        for m, opt in models:
+            opt.zero_grad(set_to_none=True)
+            out, out16 = m(x)
+            loss = crit(out, lb) + (crit(out16, lb) if step != 4 else 0.0)  # step 4: the auxiliary output is not used
+            loss.backward()
+            res.append((out.detach().clone(), out16.detach().clone(), loss.detach().clone(),
+                        {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+            opt.step()
+        (o0, a0, l0, g0), (o1, a1, l1, g1) = res
+        assert torch.equal(o0, o1) and torch.equal(a0, a1) and torch.equal(l0, l1), step
+        assert g0.keys() == g1.keys()
+        for k in g0:
+            assert torch.equal(g0[k], g1[k]), (step, k)
+        captured = [st for st in eng._gsteps.values() if st.fwd is not None]
+        assert bool(captured) == (step >= eng.graph_after and step not in (6, 7)), step
+    sd0, sd1 = models[0][0].state_dict(), models[1][0].state_dict()
+    for k in sd0:
+        assert torch.equal(sd0[k], sd1[k]), k

@@ -27,6 +27,7 @@ for _ in range(2):
 eng = model.train_engine()
 # keep (M, C) of the BatchNorm calls: achieved bandwidth per call (backward = 5 tensor passes, statistics 1, apply 2)
 shapes = []
+convs = []
 orig_call = eng._call
 
 
@@ -35,6 +36,12 @@ def spy(name, *args):
         shapes.append((len(eng.trace), name, int(args[11]), int(args[12]), 5))
     elif name == "cabinet_bn_train_stats":
         shapes.append((len(eng.trace), name, int(args[3]), int(args[4]), 1))
+    elif name == "cabinet_conv_wgrad_tc":  # N, H, W, Cin, Cout, k, stride: bytes = x + dy read once
+        N, H, W, Cin, Cout, k, st = (int(args[i]) for i in (5, 6, 7, 8, 9, 10, 12))
+        convs.append((len(eng.trace), name, f"N{N} {H}x{W} {Cin}->{Cout} k{k} s{st}", 2 * N * H * W * (Cin + Cout / (st * st))))
+    elif name == "cabinet_dwconv_wgrad":
+        N, H, W, C, k, st = (int(args[i]) for i in (6, 7, 8, 9, 10, 11))
+        convs.append((len(eng.trace), name, f"N{N} {H}x{W} C{C} k{k} s{st}", 2 * N * H * W * C * (1 + 1 / (st * st))))
     return orig_call(name, *args)
 
 
@@ -47,6 +54,10 @@ for idx, name, M, C, passes in shapes:
     ms = rows[idx][2]
     if ms >= 0.05:
         print(f"{idx:5d} {name:28s} M {M:8d} C {C:4d} {ms:6.3f} ms  {passes * M * C * 2 / ms / 1e6:7.0f} GB/s")
+for idx, name, desc, nbytes in convs:
+    ms = rows[idx][2]
+    if ms >= 0.03:
+        print(f"{idx:5d} {name:24s} {desc:32s} {ms:6.3f} ms  {nbytes / ms / 1e6:7.0f} GB/s")
 tot = sum(r[2] for r in rows)
 print(f"{len(rows)} calls, {tot:.2f} ms traced")
 fam = {}
