@@ -1115,6 +1115,115 @@ dw_wgrad_line_kernel(const T* __restrict__ dy, long long lddy, const T* __restri
     });
 }
 
+// Row-tap variant: one thread = (channel pair, filter row ky, segment of an output line).  It owns the K taps of ONE
+// filter row, i.e. K accumulator pairs and a sliding window over ONE input row: ~50 registers instead of ~130, so 5-6
+// blocks per SM are resident, and it moves U = 4 output pixels per iteration with the 4 S + 4 loads of the NEXT
+// iteration already in flight (the line walker above had one dependent batch of loads per pixel and two blocks per SM:
+// latency bound at 0.2-0.6 TB/s).  Lanes: `cw` channel pairs x 32 / cw segments per warp, warps = K filter rows x 2.
+// Block (bx, by) writes partial[bx][tap][channels of chunk by]; fixed summation order (deterministic).
+template <typename T> struct Raw2;
+template <> struct Raw2<float> {
+    typedef float2 type;
+    static __device__ __forceinline__ float2 zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ float2 load(const float* p) { return *reinterpret_cast<const float2*>(p); }
+    static __device__ __forceinline__ float2 cvt(float2 r) { return r; }
+};
+template <> struct Raw2<bf16> {
+    typedef uint32_t type;
+    static __device__ __forceinline__ uint32_t zero() { return 0u; }
+    static __device__ __forceinline__ uint32_t load(const bf16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+    static __device__ __forceinline__ float2 cvt(uint32_t r) { return make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xffff0000u)); }
+};
+
+constexpr int DWR_SL = 2;  // segment lanes (warps per filter row) of a block
+
+template <typename T, int K, int S>
+__global__ void __launch_bounds__(32 * K * DWR_SL)
+dw_wgrad_row_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx, int H, int W, int C,
+                    int OH, int OW, int n_items, int nseg, int seg_len, int items_per_block, int cw_log2,
+                    float* __restrict__ partial) {
+    constexpr int pad = (K - 1) / 2, U = 4, NCOL = (U - 1) * S + K, NEW = U * S, KEEP = NCOL - NEW;
+    typedef Raw2<T> R;
+    typedef typename R::type raw_t;
+    __shared__ float s_red[K][K][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ky = warp % K, sl = warp / K;
+    const int cw = 1 << cw_log2, nsub = 32 >> cw_log2;
+    const int pl = lane & (cw - 1), sub = lane >> cw_log2;
+    const int c0 = (static_cast<int>(blockIdx.y) * cw + pl) * 2;
+    const bool c_ok = c0 < C;
+    float2 acc[K];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) acc[kx] = make_float2(0.f, 0.f);
+    const int it0 = static_cast<int>(blockIdx.x) * items_per_block, it1 = min(it0 + items_per_block, n_items);
+    for (int item = it0 + sl * nsub + sub; item < it1; item += DWR_SL * nsub) {
+        const unsigned lu = static_cast<unsigned>(item) / static_cast<unsigned>(nseg);
+        const int ox0 = (item - static_cast<int>(lu) * nseg) * seg_len, ox1 = min(OW, ox0 + seg_len);
+        const int oy = static_cast<int>(lu % static_cast<unsigned>(OH)), n = static_cast<int>(lu / static_cast<unsigned>(OH));
+        const int iy = oy * S - pad + ky;
+        if (!c_ok || iy < 0 || iy >= H || ox0 >= ox1) continue;
+        const T* xr = x + (static_cast<long long>(n) * H + iy) * W * ldx + c0;
+        const T* dp = dy + static_cast<long long>(lu) * OW * lddy + c0;
+        float2 win[NCOL];
+#pragma unroll
+        for (int j = 0; j < KEEP; ++j) {  // columns ox0 * S - pad + j
+            const int ix = ox0 * S - pad + j;
+            win[j] = (ix >= 0 && ix < W) ? R::cvt(R::load(xr + static_cast<long long>(ix) * ldx)) : make_float2(0.f, 0.f);
+        }
+        raw_t rx[NEW], rg[U];
+        auto fetch = [&](int ox) {  // the NEW input columns and U gradients of the group starting at output column ox
+#pragma unroll
+            for (int j = 0; j < NEW; ++j) {
+                const int ix = ox * S - pad + KEEP + j;  // >= 0: KEEP = K - S >= pad
+                rx[j] = ix < W ? R::load(xr + static_cast<long long>(ix) * ldx) : R::zero();
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) rg[u] = ox + u < ox1 ? R::load(dp + static_cast<long long>(ox + u) * lddy) : R::zero();
+        };
+        fetch(ox0);
+        for (int ox = ox0; ox < ox1; ox += U) {
+            float2 g[U];
+#pragma unroll
+            for (int j = 0; j < NEW; ++j) win[KEEP + j] = R::cvt(rx[j]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) g[u] = R::cvt(rg[u]);
+            if (ox + U < ox1) fetch(ox + U);  // in flight under the FMAs below
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    acc[kx].x = fmaf(g[u].x, win[u * S + kx].x, acc[kx].x);
+                    acc[kx].y = fmaf(g[u].y, win[u * S + kx].y, acc[kx].y);
+                }
+#pragma unroll
+            for (int j = 0; j < KEEP; ++j) win[j] = win[NEW + j];
+        }
+    }
+    // segments of a warp (fixed butterfly), then the two segment lanes through shared memory
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx)
+        for (int o = cw; o < 32; o <<= 1) {
+            acc[kx].x += __shfl_xor_sync(0xffffffffu, acc[kx].x, o);
+            acc[kx].y += __shfl_xor_sync(0xffffffffu, acc[kx].y, o);
+        }
+    if (sl == 1 && sub == 0) {
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+            s_red[ky][kx][2 * pl] = acc[kx].x;
+            s_red[ky][kx][2 * pl + 1] = acc[kx].y;
+        }
+    }
+    __syncthreads();
+    if (sl == 0 && sub == 0 && c_ok) {
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+            float* out = partial + (static_cast<long long>(blockIdx.x) * (K * K) + ky * K + kx) * C + c0;
+            out[0] = acc[kx].x + s_red[ky][kx][2 * pl];
+            out[1] = acc[kx].y + s_red[ky][kx][2 * pl + 1];
+        }
+    }
+}
+
 // dW ([C][1][k][k]) += sum_b partial[b][tap][c]: one warp per output (lane l adds blocks l, l + 32, ... then a fixed
 // butterfly: deterministic)
 __global__ void dw_wgrad_finalize_kernel(const float* __restrict__ partial, int nb, int C, int taps, float* __restrict__ dw) {
@@ -1740,6 +1849,13 @@ extern "C" int cabinet_dwconv_dgrad(const void* dy, long long lddy, int dtype, c
     return CABINET_OK;
 }
 
+// bench / debug: bit 6 of cabinet_debug_flags keeps the line-walking weight-gradient kernel (A/B against the row-tap one)
+static int cabinet_debug_flags_value() {
+    const int f = cabinet_debug_flags(0);
+    cabinet_debug_flags(f);
+    return f;
+}
+
 extern "C" int cabinet_dwconv_wgrad(const void* dy, long long lddy, const void* x, long long ldx, int dtype, float* dw,
                                     int N, int H, int W, int C, int k, int stride, int OH, int OW, float* scratch,
                                     cabinet_stream_t stream) {
@@ -1749,6 +1865,41 @@ extern "C" int cabinet_dwconv_wgrad(const void* dy, long long lddy, const void* 
     long long rpb;
     const int nb = red_blocks(M, &rpb);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (C % 2 == 0 && lddy % 2 == 0 && ldx % 2 == 0 && (reinterpret_cast<uintptr_t>(dy) & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
+        (stride == 1 || stride == 2) && OW >= 8 && !(cabinet_debug_flags_value() & 64)) {
+        // row-tap kernel.  Channel pairs per warp: the largest power of two <= 32 that pads the channel count by <= 12 %
+        const int pairs = C / 2;
+        int cw_log2 = 5;
+        while (cw_log2 > 2 && (cab_ceil_div(pairs, 1 << cw_log2) << cw_log2) * 100 > pairs * 112) --cw_log2;
+        const int cw = 1 << cw_log2, nsub = 32 / cw, ny = static_cast<int>(cab_ceil_div(pairs, cw));
+        // segments: enough items per chunk column to keep ~5 blocks per SM busy twice over, >= 16 pixels each
+        const long long n_lines = static_cast<long long>(N) * OH;
+        const int want_bx = std::max(1, std::min<int>(nb, (148 * 5 + ny - 1) / ny));
+        const long long want_items = 2LL * want_bx * DWR_SL * nsub;
+        int nseg = static_cast<int>(std::max<long long>(1, std::min<long long>(OW / 16, cab_ceil_div(want_items, n_lines))));
+        const int seg_len = static_cast<int>(cab_ceil_div(cab_ceil_div(OW, nseg), 4) * 4);
+        nseg = (OW + seg_len - 1) / seg_len;
+        const long long n_items = n_lines * nseg;
+        const int bx = static_cast<int>(std::min<long long>(want_bx, cab_ceil_div(n_items, DWR_SL * nsub)));
+        const int ipb = static_cast<int>(cab_ceil_div(cab_ceil_div(n_items, bx), DWR_SL * nsub) * DWR_SL * nsub);
+        const int nbx = static_cast<int>(cab_ceil_div(n_items, ipb));  // <= bx <= nb: fits the scratch
+        dim3 grid(nbx, ny);
+#define CAB_DWR(T, KK, SS)                                                                                                \
+    dw_wgrad_row_kernel<T, KK, SS><<<grid, 32 * KK * DWR_SL, 0, s>>>(reinterpret_cast<const T*>(dy), lddy, reinterpret_cast<const T*>(x), \
+                                                                     ldx, H, W, C, OH, OW, static_cast<int>(n_items), nseg, seg_len, ipb, cw_log2, scratch)
+#define CAB_DWR2(T)                                                                                 \
+    do {                                                                                            \
+        if (k == 3 && stride == 1) CAB_DWR(T, 3, 1); else if (k == 3) CAB_DWR(T, 3, 2);             \
+        else if (stride == 1) CAB_DWR(T, 5, 1); else CAB_DWR(T, 5, 2);                              \
+    } while (0)
+        if (dtype == CABINET_F32) CAB_DWR2(float); else CAB_DWR2(bf16);
+#undef CAB_DWR2
+#undef CAB_DWR
+        CAB_LAUNCH_CHECK();
+        dw_wgrad_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(C * k * k, 8)), 256, 0, s>>>(scratch, nbx, C, k * k, dw);
+        CAB_LAUNCH_CHECK();
+        return CABINET_OK;
+    }
     if (C % 2 == 0 && lddy % 2 == 0 && ldx % 2 == 0 && (reinterpret_cast<uintptr_t>(dy) & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
         (stride == 1 || stride == 2) && OW >= 8 &&
         cab_ceil_div(static_cast<long long>(N) * OH, 2LL * (RED_THREADS / std::min(RED_THREADS, C / 2))) <= nb) {

@@ -228,7 +228,8 @@ def test_stem_im2col_and_embedded_filter(N, H, W):
 
 @pytest.mark.parametrize("N,C,k,s,H,W", [(2, 16, 3, 1, 9, 7), (1, 72, 5, 2, 11, 13), (2, 240, 3, 2, 8, 8), (1, 960, 5, 1, 4, 4),
                                          (2, 64, 3, 2, 32, 40), (1, 120, 5, 1, 16, 24), (2, 16, 3, 1, 24, 9), (1, 72, 5, 2, 33, 31),
-                                         (2, 960, 5, 1, 8, 8), (3, 200, 3, 1, 13, 17)])
+                                         (2, 960, 5, 1, 8, 8), (3, 200, 3, 1, 13, 17), (2, 72, 3, 1, 40, 70), (2, 184, 5, 2, 21, 50),
+                                         (1, 6, 5, 1, 12, 19), (2, 672, 5, 2, 16, 16)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_dwconv_gradients(N, C, k, s, H, W, dtype):
     lib = _lib.load()
