@@ -91,6 +91,9 @@ SIGNATURES = {
     "cabinet_resample_sep": ([_p, _i, _ll, _ll, _ll, _ll, _p, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p,
                               _i, _p], _i),
     "cabinet_softmax_backward": ([_p, _p, _p, _ll, _i, _f, _p], _i),
+    "cabinet_attn_softmax": ([_p, _f, _p, _p, _ll, _i, _p], _i),
+    "cabinet_attn_softmax_backward": ([_p, _p, _p, _ll, _i, _f, _p], _i),
+    "cabinet_transpose_tokens": ([_p, _ll, _p, _i, _i, _i, _p], _i),
     "cabinet_cab_combine_backward": ([_p, _ll, _p, _p, _p, _p, _i, _p, _p, _p, _p, _ll, _i, _i, _p, _p], _i),
     "cabinet_add": ([_p, _ll, _p, _ll, _p, _ll, _i, _ll, _i, _p], _i),
     "cabinet_ohem_ce_forward": ([_p, _i, _p, _i, _i, _i, _ll, _p, _i, _f, _ll, _p, _p, _p, _p], _i),

@@ -1385,6 +1385,65 @@ softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, fl
     for (int c = lane; c < cols; c += 32) out[c] = pr[c] * (dr[c] - dot) * alpha;
 }
 
+// Attention on the tensor cores (training, bf16 mode): the GEMMs run as cabinet_conv_tc_imgw / cabinet_conv_wgrad_tc calls
+// on bf16 operands; these three passes sit between them.
+// p = softmax(scale * s) over rows, written as fp32 (kept for the backward) AND as bf16 (the operand of P V and P^T dO)
+__global__ void __launch_bounds__(256)
+attn_softmax_kernel(const float* __restrict__ s, float scale, float* __restrict__ p, bf16* __restrict__ p16, long long rows,
+                    int cols) {
+    const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= rows) return;
+    const float* in = s + row * cols;
+    float m = -INFINITY;
+    for (int c = lane; c < cols; c += 32) m = fmaxf(m, in[c] * scale);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int c = lane; c < cols; c += 32) sum += expf(in[c] * scale - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    for (int c = lane; c < cols; c += 32) {
+        const float v = expf(in[c] * scale - m) * inv;
+        p[row * cols + c] = v;
+        p16[row * cols + c] = __float2bfloat16_rn(v);
+    }
+}
+
+// ds = p * (dp - sum_j dp_j p_j) * alpha as bf16 (the operand of dS K and dS^T Q)
+__global__ void __launch_bounds__(256)
+attn_softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, bf16* __restrict__ ds, long long rows,
+                        int cols, float alpha) {
+    const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (row >= rows) return;
+    const float* pr = p + row * cols;
+    const float* dr = dp + row * cols;
+    float dot = 0.f;
+    for (int c = lane; c < cols; c += 32) dot = fmaf(pr[c], dr[c], dot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    for (int c = lane; c < cols; c += 32) ds[row * cols + c] = __float2bfloat16_rn(pr[c] * (dr[c] - dot) * alpha);
+}
+
+// out[n][c][l] = x[n][l][c] (bf16): per-image K^T / V^T as cabinet_conv_tc weight matrices ([rows = channels][k = tokens])
+__global__ void __launch_bounds__(256)
+transpose_tokens_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ out, int L, int C) {
+    __shared__ bf16 tile[32][34];
+    const int n = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const bf16* xin = x + static_cast<long long>(n) * L * ldx;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (l0 + r < L && c0 + tx < C) tile[r][tx] = xin[static_cast<long long>(l0 + r) * ldx + c0 + tx];
+    __syncthreads();
+    bf16* o = out + static_cast<long long>(n) * C * L;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (c0 + r < C && l0 + tx < L) o[static_cast<long long>(c0 + r) * L + l0 + tx] = tile[tx][r];
+}
+
 // CAB combine backward: out = gamma * g + x + x * sigmoid(r)
 template <typename T>
 __global__ void __launch_bounds__(RED_THREADS)
@@ -2034,6 +2093,37 @@ extern "C" int cabinet_softmax_backward(const float* p, const float* dp, float* 
     CAB_REQUIRE(p && dp && ds && cols > 0, "softmax_backward: bad arguments");
     if (rows == 0) return CABINET_OK;
     softmax_bwd_kernel<<<static_cast<unsigned>(cab_ceil_div(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, dp, ds, rows, cols, alpha);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_attn_softmax(const float* s, float scale, float* p, void* p_bf16, long long rows, int cols,
+                                    cabinet_stream_t stream) {
+    CAB_REQUIRE(s && p && p_bf16 && cols > 0, "attn_softmax: bad arguments");
+    if (rows == 0) return CABINET_OK;
+    attn_softmax_kernel<<<static_cast<unsigned>(cab_ceil_div(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        s, scale, p, reinterpret_cast<bf16*>(p_bf16), rows, cols);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_attn_softmax_backward(const float* p, const float* dp, void* ds_bf16, long long rows, int cols,
+                                             float alpha, cabinet_stream_t stream) {
+    CAB_REQUIRE(p && dp && ds_bf16 && cols > 0, "attn_softmax_backward: bad arguments");
+    if (rows == 0) return CABINET_OK;
+    attn_softmax_bwd_kernel<<<static_cast<unsigned>(cab_ceil_div(rows, 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        p, dp, reinterpret_cast<bf16*>(ds_bf16), rows, cols, alpha);
+    CAB_LAUNCH_CHECK();
+    return CABINET_OK;
+}
+
+extern "C" int cabinet_transpose_tokens(const void* x, long long ldx, void* out, int N, int L, int C,
+                                        cabinet_stream_t stream) {
+    CAB_REQUIRE(x && out && N >= 0 && L > 0 && C > 0 && ldx >= C && N <= 65535, "transpose_tokens: bad arguments");
+    if (N == 0) return CABINET_OK;
+    dim3 grid(static_cast<unsigned>(cab_ceil_div(L, 32)), static_cast<unsigned>(cab_ceil_div(C, 32)), N);
+    transpose_tokens_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(x), ldx,
+                                                                               reinterpret_cast<bf16*>(out), L, C);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

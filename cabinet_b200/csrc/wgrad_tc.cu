@@ -169,6 +169,30 @@ __global__ void wgrad_tc_finalize_kernel(const float* __restrict__ partial, int 
     dw[(static_cast<long long>(co) * Cin + ci) * taps + tap] += sum;
 }
 
+// The same for many splits (small weight matrices cut over up to 296 pixel ranges): 8 warps of a block walk 8 interleaved
+// split subsets of 32 consecutive outputs (coalesced), then warp 0 adds the 8 sums in order -- a thread per output
+// would walk all splits alone, one dependent L2 round trip after the other (30 us for 4 KB of output).
+constexpr int FZ = 8;
+__global__ void __launch_bounds__(32 * FZ)
+wgrad_tc_finalize_par_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin, int taps, float* __restrict__ dw) {
+    __shared__ float s_sum[FZ][32];
+    const int ti = threadIdx.x & 31, zg = threadIdx.x >> 5;
+    const long long total = static_cast<long long>(Cout) * Cin * taps;
+    const long long i = static_cast<long long>(blockIdx.x) * 32 + ti;
+    float sum = 0.f;
+    if (i < total)
+        for (int z = zg; z < splits; z += FZ) sum += partial[static_cast<long long>(z) * total + i];
+    s_sum[zg][ti] = sum;
+    __syncthreads();
+    if (zg != 0 || i >= total) return;
+#pragma unroll
+    for (int g = 1; g < FZ; ++g) sum += s_sum[g][ti];
+    const int ci = static_cast<int>(i % Cin);
+    const long long t = i / Cin;
+    const int tap = static_cast<int>(t % taps), co = static_cast<int>(t / taps);
+    dw[(static_cast<long long>(co) * Cin + ci) * taps + tap] += sum;
+}
+
 struct WgPlan {
     int TW, TH, tiles_w, tiles_h, flat, NB, n_tiles, m_tiles, splits, tiles_per_split;
     long long n_k_tiles;
@@ -282,8 +306,12 @@ extern "C" int cabinet_conv_wgrad_tc(const void* dy, long long lddy, const void*
     conv_wgrad_tc_kernel<<<grid, WG_THREADS, smem, s>>>(tmDY, tmX[0], tmX[1], tmX[2], tmX[3], p);
     CAB_LAUNCH_CHECK();
     const long long total = static_cast<long long>(Cout) * Cin * p.taps;
-    wgrad_tc_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(total, 256)), 256, 0, s>>>(scratch, g.splits, Cout, Cin, p.taps,
-                                                                                            dw_oihw);
+    if (g.splits >= 2 * FZ)
+        wgrad_tc_finalize_par_kernel<<<static_cast<unsigned>(cab_ceil_div(total, 32)), 32 * FZ, 0, s>>>(scratch, g.splits, Cout, Cin,
+                                                                                                       p.taps, dw_oihw);
+    else
+        wgrad_tc_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(total, 256)), 256, 0, s>>>(scratch, g.splits, Cout, Cin, p.taps,
+                                                                                                dw_oihw);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

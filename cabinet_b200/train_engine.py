@@ -142,6 +142,7 @@ class TrainEngine:
         self.wgrad_tc = True                # tcgen05 weight gradients (stride-1 "same" and stride-2 convolutions)
         self.stem_gemm = True               # both stems as 1x1 GEMMs on one bf16 im2col of the input
         self.dgrad_s2_tc = True             # stride-2 data gradients as four parity-class conv_tc calls
+        self.attn_tc = True                 # attention GEMMs (forward and backward) on the tensor cores
         self._zero_cache: Dict[int, torch.Tensor] = {}
         self.use_graph = True               # replay the step as two CUDA graphs once its geometry has been seen
         self.graph_after = 2                # eager steps per geometry before the capture (lazy tables, attributes)
@@ -555,6 +556,8 @@ class TrainEngine:
         """softmax(q k^T / sqrt(d)) v per image with the probabilities kept for the backward (cab.py:149-153)."""
         N, L, d = q.N, q.H * q.W, q.C
         alpha = float(d) ** -0.5
+        if (self.use_tc and self.attn_tc and L % 128 == 0 and d % 64 == 0 and all(self._tc_ok(t) and t.ld == d for t in (q, k, v))):
+            return self._attention_tc(q, k, v, alpha)
         s = torch.empty((N, L, L), dtype=torch.float32, device=self.dev)
         p = torch.empty((N, L, L), dtype=torch.float32, device=self.dev)
         ctx = self.new(q.N, q.H, q.W, d)
@@ -583,6 +586,64 @@ class TrainEngine:
             # dQ[i][c] = sum_j dS[i][j] K[j][c];  dK[j][c] = sum_i dS[i][j] Q[i][c]
             gemm(ds.data_ptr(), F32, L, 1, L * L, k.ptr, k.dt, 1, k.ld, L * k.ld, dq.ptr, dq.dt, d, L * d, L, L, d)
             gemm(ds.data_ptr(), F32, 1, L, L * L, q.ptr, q.dt, 1, q.ld, L * q.ld, dk.ptr, dk.dt, d, L * d, L, L, d)
+            for tgt, src in ((q, dq), (k, dk), (v, dv)):
+                self.add_grad(g, tgt, src)
+
+        self.tape.append(backward)
+        return ctx
+
+    def _attention_tc(self, q: Map, k: Map, v: Map, alpha: float) -> Map:
+        """The same attention with all six GEMMs on the tensor cores (bf16 operands, fp32 accumulation): a dense [L][d] map
+        of an image IS a cabinet_conv_tc weight matrix (rows = tokens, k = channels), so S = Q K^T and dP = dO V^T are 1x1
+        convolutions with per-image weights K / V, P V and dQ = dS K the same with K^T / V^T ([d][L], one small transpose
+        each), and dV = P^T dO, dK = dS^T Q reduce over the token ("pixel") index: the weight-gradient GEMM, per image."""
+        N, L, d, H, W = q.N, q.H * q.W, q.C, q.H, q.W
+        dev, bf = self.dev, torch.bfloat16
+        s = torch.empty((N, L, L), dtype=torch.float32, device=dev)
+        p = torch.empty((N, L, L), dtype=torch.float32, device=dev)
+        p16 = torch.empty((N, L, L), dtype=bf, device=dev)
+        vt = torch.empty((N, d, L), dtype=bf, device=dev)
+        ctx = self.new(N, H, W, d)
+        zL, zd = self._zeros(L), self._zeros(d)
+
+        def gemm(x_ptr, ldx, cin, w_ptr, cout, bias, y_ptr, ydt, ldy):
+            # y[n][l][co] = sum_k x[n][l][k] w[n][co][k]   (w: [N][cout][cin] bf16, dense)
+            self._call("cabinet_conv_tc_imgw", x_ptr, ldx, N, H, W, cin, w_ptr, cout * cin, cout, 1, 1, 1, 0, bias.data_ptr(),
+                       None, 0, y_ptr, ydt, ldy, H, W, ACT_NONE)
+
+        gemm(q.ptr, q.ld, d, k.ptr, L, zL, s.data_ptr(), F32, L)
+        self._call("cabinet_attn_softmax", s.data_ptr(), alpha, p.data_ptr(), p16.data_ptr(), N * L, L)
+        self._call("cabinet_transpose_tokens", v.ptr, v.ld, vt.data_ptr(), N, L, d)
+        gemm(p16.data_ptr(), L, L, vt.data_ptr(), d, zd, ctx.ptr, ctx.dt, ctx.ld)
+
+        def backward(g: _Grads):
+            do = g.get(ctx)
+            if do is None:
+                return
+            dp = s  # the raw scores are not needed any more: reuse their buffer
+            ds16 = torch.empty((N, L, L), dtype=bf, device=dev)
+            kt = torch.empty((N, d, L), dtype=bf, device=dev)
+            dq = self.new(N, H, W, d)
+            dkv = torch.zeros((2, N, L, d), dtype=torch.float32, device=dev)  # dK, dV: the weight-gradient GEMM adds
+            n_scr = int(self.lib.cabinet_conv_wgrad_tc_scratch_floats(1, H, W, d, L, 1, 1, 1, 0))
+            scr = torch.empty(max(n_scr, 1), dtype=torch.float32, device=dev)
+
+            def wgrad(a_ptr, x_ptr, ldx, out):  # out[j][c] += sum_i a[i][j] x[i][c], one image
+                self._call("cabinet_conv_wgrad_tc", a_ptr, L, x_ptr, ldx, out.data_ptr(), 1, H, W, d, L, 1, 1, 1, 0,
+                           scr.data_ptr())
+
+            for b in range(N):  # dV[j][c] = sum_i P[i][j] dO[i][c]
+                wgrad(p16[b].data_ptr(), do.ptr + b * L * do.ld * 2, do.ld, dkv[1, b])
+            gemm(do.ptr, do.ld, d, v.ptr, L, zL, dp.data_ptr(), F32, L)           # dP[i][j] = sum_c dO[i][c] V[j][c]
+            self._call("cabinet_attn_softmax_backward", p.data_ptr(), dp.data_ptr(), ds16.data_ptr(), N * L, L, alpha)
+            self._call("cabinet_transpose_tokens", k.ptr, k.ld, kt.data_ptr(), N, L, d)
+            gemm(ds16.data_ptr(), L, L, kt.data_ptr(), d, zd, dq.ptr, dq.dt, dq.ld)  # dQ[i][c] = sum_j dS[i][j] K[j][c]
+            for b in range(N):  # dK[j][c] = sum_i dS[i][j] Q[i][c]
+                wgrad(ds16[b].data_ptr(), q.ptr + b * L * q.ld * 2, q.ld, dkv[0, b])
+            dk, dv = self.new(N, H, W, d), self.new(N, H, W, d)
+            for src, dst in ((dkv[0], dk), (dkv[1], dv)):  # fp32 -> the activation dtype
+                self._call("cabinet_affine_act", src.data_ptr(), d, F32, None, None, None, 0.0, None, 0, dst.ptr, dst.ld,
+                           dst.dt, N * L, L, d, ACT_NONE)
             for tgt, src in ((q, dq), (k, dk), (v, dv)):
                 self.add_grad(g, tgt, src)
 
@@ -726,7 +787,7 @@ class TrainEngine:
         self._active = None
         if not self.use_graph or self.trace is not None or torch.cuda.is_current_stream_capturing():
             return self.forward(x, logits_dtype)
-        key = (tuple(x.shape), logits_dtype, self.use_tc, self.wgrad_tc, self.stem_gemm, self.dgrad_s2_tc)
+        key = (tuple(x.shape), logits_dtype, self.use_tc, self.wgrad_tc, self.stem_gemm, self.dgrad_s2_tc, self.attn_tc)
         addr = self._addresses()
         st = self._gsteps.get(key)
         if st is not None and st.fwd is not None and st.addr != addr:

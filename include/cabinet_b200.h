@@ -488,6 +488,20 @@ int cabinet_resample_sep(const void* in, int in_dtype, long long isn, long long 
 /* ds = p * (dp - rowsum(dp * p)) * alpha over rows of `cols` fp32 (softmax backward, cab.py:150-151). */
 int cabinet_softmax_backward(const float* p, const float* dp, float* ds, long long rows, int cols, float alpha,
                              cabinet_stream_t stream);
+
+/* Training-mode attention with its GEMMs on the tensor cores (bf16 mode; src/models/cab.py:149-153 and its autograd
+ * backward): S = Q K^T, P V, dO V^T and dS K run as cabinet_conv_tc_imgw calls (the per-image K / V / K^T / V^T maps ARE
+ * cabinet_conv_tc weight matrices when their row stride equals their width), P^T dO and dS^T Q as per-image
+ * cabinet_conv_wgrad_tc calls.  Between them:
+ *   _attn_softmax: p = softmax(scale * s) per row, as fp32 (kept for the backward) and as bf16 (GEMM operand);
+ *   _attn_softmax_backward: ds = p * (dp - rowsum(dp * p)) * alpha as bf16;
+ *   _transpose_tokens: out[n][c][l] = x[n][l][c], bf16 (x rows ldx apart, out dense). */
+int cabinet_attn_softmax(const float* s, float scale, float* p, void* p_bf16, long long rows, int cols,
+                         cabinet_stream_t stream);
+int cabinet_attn_softmax_backward(const float* p, const float* dp, void* ds_bf16, long long rows, int cols, float alpha,
+                                  cabinet_stream_t stream);
+int cabinet_transpose_tokens(const void* x, long long ldx, void* out, int N, int L, int C, cabinet_stream_t stream);
+
 /* Backward of out = gamma * g + x + x * sigmoid(r) (cab.py:175-184,213-216), dense [n_pixels][C] operands:
  * dg = gamma * dout, dx (+)= dout * (1 + sigmoid(r)), dr = dout * x * sigmoid'(r), *dgamma += sum dout * g.
  * scratch: (n_pixels, C, 1). */
