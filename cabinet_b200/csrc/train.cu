@@ -649,6 +649,50 @@ im2col_nchw_kernel(const float* __restrict__ x, int N, int Cin, int H, int W, in
     }
 }
 
+// Row-segment variant: a block stages the input window of IM2COL_PX consecutive output pixels of one output row
+// ([Cin][K][PX * S + K - S] fp32, coalesced along x, zero outside the image) and a column -> window-offset table in shared
+// memory, then writes the PX dense rows 16 bytes per thread -- no per-element index division, every input element read from
+// global memory once per block instead of once per (pixel, tap) (the per-element kernel above ran at 0.7 TB/s of its
+// output bytes: 0.94 ms for the 1024 x 1024 stem of batch 8).
+constexpr int IM2COL_PX = 64;
+__global__ void __launch_bounds__(256)
+im2col_nchw_row_kernel(const float* __restrict__ x, int Cin, int H, int W, int K, int S, int P, int OH, int OW,
+                       bf16* __restrict__ out, int ld, int segs) {
+    extern __shared__ float s_win[];  // [Cin * K][winw] | int table[ld]
+    const int winw = IM2COL_PX * S + K - S, rows = Cin * K, cols = Cin * K * K;
+    int* s_tab = reinterpret_cast<int*>(s_win + rows * winw);
+    const int seg = blockIdx.x % segs;
+    const int t = blockIdx.x / segs;
+    const int oy = t % OH, n = t / OH;
+    const int ox0 = seg * IM2COL_PX, npx = min(IM2COL_PX, OW - ox0);
+    const int ix0 = ox0 * S - P, iy0 = oy * S - P;
+    for (int i = threadIdx.x; i < rows * winw; i += 256) {
+        const int r = i / winw, j = i - r * winw;
+        const int ci = r / K, ky = r - ci * K;
+        const int iy = iy0 + ky, ix = ix0 + j;
+        s_win[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + ((static_cast<long long>(n) * Cin + ci) * H + iy) * W + ix) : 0.f;
+    }
+    for (int c = threadIdx.x; c < ld; c += 256) {
+        const int r = c / K;  // = ci * K + ky for c = ci*K*K + ky*K + kx
+        s_tab[c] = c < cols ? r * winw + (c - r * K) : -1;
+    }
+    __syncthreads();
+    const int chunks = ld / 8;
+    bf16* orow = out + ((static_cast<long long>(n) * OH + oy) * OW + ox0) * ld;
+    for (int i = threadIdx.x; i < npx * chunks; i += 256) {
+        const int px = i / chunks, ch = i - px * chunks;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int o = s_tab[ch * 8 + j];
+            v[j] = o >= 0 ? s_win[o + px * S] : 0.f;
+        }
+        Vec16<bf16> o;
+        o.pack(v);
+        o.store(orow + static_cast<long long>(px) * ld + ch * 8);
+    }
+}
+
 // dst[r][c0 + c] (+)= src[r][c] for a [rows][cols] block (embedding a 3x3 filter / its gradient in the 7x7 footprint)
 __global__ void embed_filter_kernel(const float* __restrict__ w_small, int Cout, int Cin, int k, int K, float* __restrict__ w_big,
                                     int ld_big, int extract_add) {
@@ -1604,8 +1648,14 @@ extern "C" int cabinet_im2col_nchw(const float* x, int N, int Cin, int H, int W,
     const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
     const long long total = static_cast<long long>(N) * OH * OW;
     CAB_REQUIRE(total * (ld / 8) < (1LL << 31), "im2col_nchw: too many pixels");
-    im2col_nchw_kernel<<<ew_grid(total * (ld / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, N, Cin, H, W, k, stride, pad, OH, OW, reinterpret_cast<bf16*>(out), static_cast<int>(ld));
+    const size_t smem = (static_cast<size_t>(Cin) * k * (IM2COL_PX * stride + k - stride) + static_cast<size_t>(ld)) * 4;
+    const int segs = (OW + IM2COL_PX - 1) / IM2COL_PX;
+    if (smem <= 48 * 1024 && static_cast<long long>(N) * OH * segs < (1LL << 31))
+        im2col_nchw_row_kernel<<<static_cast<unsigned>(static_cast<long long>(N) * OH * segs), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+            x, Cin, H, W, k, stride, pad, OH, OW, reinterpret_cast<bf16*>(out), static_cast<int>(ld), segs);
+    else
+        im2col_nchw_kernel<<<ew_grid(total * (ld / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            x, N, Cin, H, W, k, stride, pad, OH, OW, reinterpret_cast<bf16*>(out), static_cast<int>(ld));
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
 }

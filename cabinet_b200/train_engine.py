@@ -136,6 +136,9 @@ class TrainEngine:
         self.tables = _Tables(self.dev)
         self.tape: List = []
         self.pgrads: Dict[int, torch.Tensor] = {}
+        self._pflat: Optional[torch.Tensor] = None   # flat fp32 storage of this backward's parameter gradients
+        self._pslots: Dict[int, Tuple[int, int]] = {}
+        self._bn_seen: List[torch.Tensor] = []
         self.launches = 0
         self.trace, self.phase = None, "fwd"
         self.use_tc = precision == "bf16"   # tcgen05 / TMA kernels for the GEMM-shaped and depthwise layers
@@ -188,7 +191,14 @@ class TrainEngine:
         """fp32 gradient accumulator of a parameter (zeroed on first use in a backward)."""
         g = self.pgrads.get(id(p))
         if g is None:
-            g = self.pgrads[id(p)] = torch.zeros(p.shape, dtype=torch.float32, device=self.dev)
+            if self._pflat is None:  # one buffer, one fill kernel per backward instead of one per parameter
+                off = 0
+                for q in self.model.parameters():
+                    self._pslots[id(q)] = (off, q.numel())
+                    off += -(-q.numel() // 64) * 64  # 256-byte aligned slots
+                self._pflat = torch.zeros(max(off, 1), dtype=torch.float32, device=self.dev)
+            off, n = self._pslots[id(p)]
+            g = self.pgrads[id(p)] = self._pflat[off:off + n].view(p.shape)
         return g
 
     @staticmethod
@@ -413,7 +423,7 @@ class TrainEngine:
         self._call("cabinet_bn_train_stats", z.ptr, z.ld, z.dt, M, C, bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps),
                    BN_MOMENTUM if bn.momentum is None else float(bn.momentum), bn.running_mean.data_ptr(),
                    bn.running_var.data_ptr(), stats.data_ptr(), sc.data_ptr())
-        bn.num_batches_tracked.add_(1)
+        self._bn_seen.append(bn.num_batches_tracked)  # += 1 for all of them at the end of the forward (one kernel)
         if out is None:
             out = self.new(z.N, z.H, z.W, C)
         self._call("cabinet_affine_act", z.ptr, z.ld, z.dt, stats[2].data_ptr(), stats[3].data_ptr(), None, 0.0,
@@ -693,6 +703,7 @@ class TrainEngine:
             x = x.float().contiguous()
         N, _, H, W = x.shape
         self.tape, self.launches, self.pgrads, self.phase = [], 0, {}, "fwd"
+        self._pflat, self._bn_seen = None, []
         mob, sb, ab, ffm, head = m.mobile, m.sb, m.ab, m.ffm, m.conv_out
         ga, cab = ab.a2block.global_attn, ab.a2block
 
@@ -761,12 +772,14 @@ class TrainEngine:
         final, bwd_final = self.logits_up(final8, H, W, logits_dtype)
         aux, bwd_aux = self.logits_up(aux8, H, W, logits_dtype)
         self._out_bwd = (bwd_final, bwd_aux)
+        if self._bn_seen:
+            torch._foreach_add_(self._bn_seen, 1)
         return final, aux
 
     def backward(self, d_final: Optional[torch.Tensor], d_aux: Optional[torch.Tensor]) -> Dict[int, torch.Tensor]:
         """Gradients of the two logit tensors -> {id(parameter): fp32 gradient}."""
         g = _Grads(self)
-        self.pgrads, self.phase = {}, "bwd"
+        self.pgrads, self.phase, self._pflat = {}, "bwd", None
         for dy, bwd in ((d_final, self._out_bwd[0]), (d_aux, self._out_bwd[1])):
             if dy is not None:
                 bwd(g, dy)

@@ -199,7 +199,7 @@ def test_stride2_dgrad_as_parity_conv_tc(N, cin, cout, k, pad, H, W):
     assert e < 4e-3   # bf16 output rounding
 
 
-@pytest.mark.parametrize("N,H,W", [(2, 20, 24), (1, 17, 13), (2, 64, 48)])
+@pytest.mark.parametrize("N,H,W", [(2, 20, 24), (1, 17, 13), (2, 64, 48), (2, 40, 300), (1, 9, 257)])
 def test_stem_im2col_and_embedded_filter(N, H, W):
     """im2col of the NCHW input over the 7x7/s2/p3 footprint: the 7x7 stem AND the 3x3/s2/p1 stem (centre of the footprint)
     are row-times-matrix products on it."""
