@@ -177,11 +177,24 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nb, lo
     // one WARP per channel: lane l adds blocks l, l + 32, ... in order, then a fixed butterfly (deterministic)
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int b = lane; b < nb; b += 32) {
+    // four independent chains per lane: the loads of a lane's blocks go out together instead of one round trip each
+    double s1 = 0.0, s2 = 0.0, t1[3] = {0.0, 0.0, 0.0}, t2[3] = {0.0, 0.0, 0.0};
+    int b = lane;
+    for (; b + 96 < nb; b += 128) {
+        s1 += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
+        s2 += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            t1[u] += partial[(static_cast<long long>(b + 32 * (u + 1)) * 2 + 0) * C + c];
+            t2[u] += partial[(static_cast<long long>(b + 32 * (u + 1)) * 2 + 1) * C + c];
+        }
+    }
+    for (; b < nb; b += 32) {
         s1 += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
         s2 += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
     }
+    s1 += t1[0] + t1[1] + t1[2];
+    s2 += t2[0] + t2[1] + t2[2];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
@@ -402,11 +415,23 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;  // one warp per channel
     if (c >= C) return;
-    float s1 = 0.f, s2 = 0.f;
-    for (int b = lane; b < nb; b += 32) {
+    float s1 = 0.f, s2 = 0.f, t1[3] = {0.f, 0.f, 0.f}, t2[3] = {0.f, 0.f, 0.f};
+    int b = lane;
+    for (; b + 96 < nb; b += 128) {  // four independent chains per lane (see bn_finalize_kernel)
+        s1 += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
+        s2 += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            t1[u] += partial[(static_cast<long long>(b + 32 * (u + 1)) * 2 + 0) * C + c];
+            t2[u] += partial[(static_cast<long long>(b + 32 * (u + 1)) * 2 + 1) * C + c];
+        }
+    }
+    for (; b < nb; b += 32) {
         s1 += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
         s2 += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
     }
+    s1 += t1[0] + t1[1] + t1[2];
+    s2 += t2[0] + t2[1] + t2[2];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
@@ -1036,6 +1061,60 @@ dw_dgrad_v_kernel(const T* __restrict__ dy, long long lddy, const float* __restr
     }
 }
 
+// stride 2, compile-time filter size: parity tests and shifts instead of runtime divisions, the tap loops unrolled, the
+// tap weights as two 16-byte loads
+template <typename T, int K>
+__global__ void __launch_bounds__(256)
+dw_dgrad_s2_kernel(const T* __restrict__ dy, long long lddy, const float* __restrict__ w, T* __restrict__ dx, long long lddx,
+                   int N, int H, int W, int C, int OH, int OW, int accumulate) {
+    constexpr int V = vec_n<T>(), pad = (K - 1) / 2, NT = (K + 1) / 2;
+    const int CV = C / V;
+    const long long total = static_cast<long long>(N) * H * W * CV;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const unsigned iu = static_cast<unsigned>(i);
+        const int c0 = static_cast<int>(iu % static_cast<unsigned>(CV)) * V;
+        unsigned t = iu / static_cast<unsigned>(CV);
+        const int ix = static_cast<int>(t % static_cast<unsigned>(W));
+        t /= static_cast<unsigned>(W);
+        const int iy = static_cast<int>(t % static_cast<unsigned>(H)), n = static_cast<int>(t / static_cast<unsigned>(H));
+        float acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = 0.f;
+        const int py = (iy + pad) & 1, px = (ix + pad) & 1;
+        const T* dyn = dy + static_cast<long long>(n) * OH * OW * lddy + c0;
+#pragma unroll
+        for (int a = 0; a < NT; ++a) {
+            const int ky = py + 2 * a, ty = iy + pad - ky, oy = ty >> 1;
+            if (ky >= K || ty < 0 || oy >= OH) continue;
+#pragma unroll
+            for (int b = 0; b < NT; ++b) {
+                const int kx = px + 2 * b, tx = ix + pad - kx, ox = tx >> 1;
+                if (kx >= K || tx < 0 || ox >= OW) continue;
+                float g[V];
+                ldv(dyn + (static_cast<long long>(oy) * OW + ox) * lddy, g);
+                const float4* wp = reinterpret_cast<const float4*>(w + (ky * K + kx) * C + c0);
+#pragma unroll
+                for (int v4 = 0; v4 < V / 4; ++v4) {
+                    const float4 wv = __ldg(wp + v4);
+                    acc[4 * v4] = fmaf(g[4 * v4], wv.x, acc[4 * v4]);
+                    acc[4 * v4 + 1] = fmaf(g[4 * v4 + 1], wv.y, acc[4 * v4 + 1]);
+                    acc[4 * v4 + 2] = fmaf(g[4 * v4 + 2], wv.z, acc[4 * v4 + 2]);
+                    acc[4 * v4 + 3] = fmaf(g[4 * v4 + 3], wv.w, acc[4 * v4 + 3]);
+                }
+            }
+        }
+        T* o = dx + ((static_cast<long long>(n) * H + iy) * W + ix) * lddx + c0;
+        if (accumulate) {
+            float old[V];
+            ldv(o, old);
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] += old[v];
+        }
+        stv(o, acc);
+    }
+}
+
 // partial[b][tap][c] = sum over the block's output pixels of dy[pix][c] * x[pix shifted by tap][c]
 template <typename T, int KK>
 __global__ void __launch_bounds__(RED_THREADS)
@@ -1590,6 +1669,29 @@ __global__ void gate_bwd_phase_kernel(int phase, int N, int C, int J, int gate, 
     }
 }
 
+// Phases 2 and 4 with one WARP per output: the lanes stride over the reduction index (C up to 960: a thread per output
+// walked it alone, 16 us per launch), fixed butterfly at the end.
+__global__ void __launch_bounds__(256)
+gate_bwd_dot_kernel(int phase, int N, int C, int J, const float* __restrict__ W1, const float* __restrict__ W2,
+                    const float* __restrict__ h, const float* __restrict__ da2, float* __restrict__ da1, float* __restrict__ dm) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    float acc = 0.f;
+    if (phase == 2) {
+        if (i >= N * J) return;
+        const int n = i / J, j = i - n * J;
+        for (int c = lane; c < C; c += 32) acc = fmaf(da2[n * C + c], W2[c * J + j], acc);
+    } else {
+        if (i >= N * C) return;
+        const int n = i / C, c = i - n * C;
+        for (int j = lane; j < J; j += 32) acc = fmaf(da1[n * J + j], W1[j * C + c], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane != 0) return;
+    if (phase == 2) da1[i] = h[i] > 0.f ? acc : 0.f;
+    else dm[i] = acc;
+}
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline unsigned row_grid(long long M, int lanes) { return static_cast<unsigned>(std::max<long long>(1, std::min<long long>(cab_ceil_div(M, lanes), 148LL * 8))); }
 inline unsigned ew_grid(long long total) { return static_cast<unsigned>(std::min<long long>(cab_ceil_div(total, 256), 148LL * 16)); }
@@ -1940,6 +2042,17 @@ extern "C" int cabinet_dwconv_dgrad(const void* dy, long long lddy, int dtype, c
     if (C % V == 0 && lddy % V == 0 && lddx % V == 0 && al16(dy) && al16(dx) && al16(w_packed) && C % 4 == 0 &&
         static_cast<long long>(N) * H * W * (C / V) < (1LL << 31)) {
         const long long tv = static_cast<long long>(N) * H * W * (C / V);
+        if (stride == 2) {
+            const unsigned g2 = static_cast<unsigned>(std::min<long long>(cab_ceil_div(tv, 256), 148LL * 32));
+#define CAB_DG2(T, KK)                                                                                                          \
+    dw_dgrad_s2_kernel<T, KK><<<g2, 256, 0, s>>>(reinterpret_cast<const T*>(dy), lddy, w_packed, reinterpret_cast<T*>(dx), lddx, N, H, W, \
+                                                 C, OH, OW, accumulate)
+            if (dtype == CABINET_F32) { if (k == 3) CAB_DG2(float, 3); else CAB_DG2(float, 5); }
+            else { if (k == 3) CAB_DG2(bf16, 3); else CAB_DG2(bf16, 5); }
+#undef CAB_DG2
+            CAB_LAUNCH_CHECK();
+            return CABINET_OK;
+        }
         CAB_DT2(dtype,
                 (dw_dgrad_v_kernel<float><<<ew_grid(tv), 256, 0, s>>>(reinterpret_cast<const float*>(dy), lddy, w_packed, reinterpret_cast<float*>(dx), lddx, N, H,
                                                                      W, C, k, stride, OH, OW, accumulate)),
@@ -2227,8 +2340,11 @@ extern "C" int cabinet_gate_mlp_backward(const float* mean, float mean_scale, co
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int sizes[5] = {N * C, C * J, N * J, J * C, N * C};
     for (int ph = 0; ph < 5; ++ph) {
-        gate_bwd_phase_kernel<<<static_cast<unsigned>(cab_ceil_div(sizes[ph], 128)), 128, 0, st>>>(ph, N, C, J, gate, mean_scale, mean, w1, w2, hidden, s, ds, da2, da1,
-                                                                                                    dw1, db1, dw2, db2, dmean);
+        if (ph == 2 || ph == 4)
+            gate_bwd_dot_kernel<<<static_cast<unsigned>(cab_ceil_div(sizes[ph], 8)), 256, 0, st>>>(ph, N, C, J, w1, w2, hidden, da2, da1, dmean);
+        else
+            gate_bwd_phase_kernel<<<static_cast<unsigned>(cab_ceil_div(sizes[ph], 128)), 128, 0, st>>>(ph, N, C, J, gate, mean_scale, mean, w1, w2, hidden, s, ds, da2, da1,
+                                                                                                        dw1, db1, dw2, db2, dmean);
         CAB_LAUNCH_CHECK();
     }
     return CABINET_OK;
