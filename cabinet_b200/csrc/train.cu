@@ -152,7 +152,9 @@ __device__ __forceinline__ void col_reduce_block_v(long long M, int C, long long
 template <typename T> constexpr size_t red_smem_v(int nq) { return static_cast<size_t>(RED_THREADS) * vec_n<T>() * nq * sizeof(float); }
 
 inline int red_blocks(long long M, long long* rows_per_block) {
-    long long nb = std::min<long long>(1024, std::max<long long>(1, M / 64));
+    // at most 8 blocks per SM: the reduction kernels hold 2 or 4 blocks of 256 threads per SM (121 / 64 registers), so
+    // 1184 equal blocks are exactly 4 or 2 full waves (1024 left the last wave half empty)
+    long long nb = std::min<long long>(148 * 8, std::max<long long>(1, M / 64));
     *rows_per_block = cab_ceil_div(M, nb);
     return static_cast<int>(cab_ceil_div(M, *rows_per_block));
 }
@@ -177,24 +179,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nb, lo
     // one WARP per channel: lane l adds blocks l, l + 32, ... in order, then a fixed butterfly (deterministic)
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
-    // four independent chains per lane: the loads of a lane's blocks go out together instead of one round trip each
-    double s1 = 0.0, s2 = 0.0, t1[3] = {0.0, 0.0, 0.0}, t2[3] = {0.0, 0.0, 0.0};
-    int b = lane;
-    for (; b + 96 < nb; b += 128) {
-        s1 += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
-        s2 += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            t1[u] += partial[(static_cast<long long>(b + 32 * (u + 1)) * 2 + 0) * C + c];
-            t2[u] += partial[(static_cast<long long>(b + 32 * (u + 1)) * 2 + 1) * C + c];
-        }
-    }
-    for (; b < nb; b += 32) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = lane; b < nb; b += 32) {
         s1 += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
         s2 += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
     }
-    s1 += t1[0] + t1[1] + t1[2];
-    s2 += t2[0] + t2[1] + t2[2];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
@@ -417,7 +406,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
     if (c >= C) return;
     float s1 = 0.f, s2 = 0.f, t1[3] = {0.f, 0.f, 0.f}, t2[3] = {0.f, 0.f, 0.f};
     int b = lane;
-    for (; b + 96 < nb; b += 128) {  // four independent chains per lane (see bn_finalize_kernel)
+    for (; b + 96 < nb; b += 128) {  // four independent chains per lane (the loads of a lane's blocks go out together)
         s1 += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
         s2 += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
 #pragma unroll
