@@ -10,7 +10,7 @@
 // Activations are NHWC (fp32 or bf16), statistics / gradients of parameters fp32.
 #include <type_traits>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -225,6 +225,135 @@ affine_act_kernel(const TZ* __restrict__ z, long long ldz, const float* __restri
         if (res) u += ldf(res + m * ldres + c);
         y[m * ldy + c] = from_f32<TY>(u);
     }
+}
+
+// ---- The same column reductions with the rows staged through shared memory by bulk copies (dense bf16 tensors only):
+// a producer warp keeps RT_STAGES chunks of up to 16 KB per block in flight (cp.async.bulk + mbarrier ring), the 256
+// consumer threads read their 16-byte channel vectors from shared memory.  The register-fed kernels above hold the
+// bytes in flight in registers (two 16-byte loads per thread and source) and top out at 3.1-3.5 TB/s with 2-4 blocks
+// per SM; here the in-flight bytes cost no registers.  Same per-block summation tree shape (pixel lanes -> shared
+// memory -> fixed-order sum), so the result is deterministic; `nb` blocks write partial[b][q][c] as before.
+constexpr int RT_STAGES = 4, RT_STAGE_BYTES = 16384, RT_THREADS = RED_THREADS + 32;
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     tc::smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+
+// f(row0, row1, acc): row0 / row1 = this thread's 8 channels of one row of source 0 / 1 as fp32
+template <int NQ, int NSRC, typename F>
+__device__ __forceinline__ void col_reduce_tma(const bf16* __restrict__ src0, const bf16* __restrict__ src1, long long M, int C,
+                                               long long rows_per_block, int chunk_rows, float* __restrict__ partial, F f) {
+    constexpr int V = 8;
+    extern __shared__ __align__(128) uint8_t s_ring[];  // [RT_STAGES][NSRC][chunk_rows * C] bf16; reused for the block sum
+    __shared__ __align__(8) uint64_t full_bar[RT_STAGES], empty_bar[RT_STAGES];
+    const int warp = threadIdx.x >> 5;
+    const long long m0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+    const long long m1 = min(m0 + rows_per_block, M);
+    const int n_chunks = static_cast<int>((m1 - m0 + chunk_rows - 1) / chunk_rows);
+    const uint32_t src_bytes = static_cast<uint32_t>(chunk_rows) * C * 2;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RT_STAGES; ++i) {
+            tc::mbar_init(&full_bar[i], 1);
+            tc::mbar_init(&empty_bar[i], RED_THREADS / 32);
+        }
+        tc::mbar_fence_init();
+    }
+    __syncthreads();
+    float acc[NQ * V];
+#pragma unroll
+    for (int q = 0; q < NQ * V; ++q) acc[q] = 0.f;
+    const int cwv = C / V, lanes = RED_THREADS / cwv;
+    const int cv = threadIdx.x % cwv, lane = threadIdx.x / cwv;
+    if (warp == RED_THREADS / 32) {
+        // ---------------- producer
+        if ((threadIdx.x & 31) == 0) {
+            for (int i = 0; i < n_chunks; ++i) {
+                const int st = i % RT_STAGES;
+                if (i >= RT_STAGES) tc::mbar_wait(&empty_bar[st], ((i / RT_STAGES) - 1) & 1);
+                const long long r0 = m0 + static_cast<long long>(i) * chunk_rows;
+                const uint32_t bytes = static_cast<uint32_t>(min(static_cast<long long>(chunk_rows), m1 - r0)) * C * 2;
+                uint8_t* dst = s_ring + static_cast<size_t>(st) * NSRC * src_bytes;
+                tc::mbar_expect_tx(&full_bar[st], bytes * NSRC);
+                bulk_load_1d(dst, src0 + r0 * C, bytes, &full_bar[st]);
+                if (NSRC == 2) bulk_load_1d(dst + src_bytes, src1 + r0 * C, bytes, &full_bar[st]);
+            }
+        }
+    } else {
+        // ---------------- consumers
+        for (int i = 0; i < n_chunks; ++i) {
+            const int st = i % RT_STAGES;
+            tc::mbar_wait(&full_bar[st], (i / RT_STAGES) & 1);
+            const int rows = static_cast<int>(min(static_cast<long long>(chunk_rows), m1 - (m0 + static_cast<long long>(i) * chunk_rows)));
+            const bf16* c0 = reinterpret_cast<const bf16*>(s_ring + static_cast<size_t>(st) * NSRC * src_bytes) + cv * V;
+            const bf16* c1 = reinterpret_cast<const bf16*>(s_ring + static_cast<size_t>(st) * NSRC * src_bytes + src_bytes) + cv * V;
+            if (lane < lanes) {
+                for (int r = lane; r < rows; r += lanes) {
+                    float a[V], b[V];
+                    ldv(c0 + r * C, a);
+                    if (NSRC == 2) ldv(c1 + r * C, b);
+                    f(a, b, acc);
+                }
+            }
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) tc::mbar_arrive(&empty_bar[st]);
+        }
+    }
+    __syncthreads();  // every chunk consumed: the ring is free for the block sum
+    float* s_red = reinterpret_cast<float*>(s_ring);  // [lanes][NQ][C]
+    if (warp < RED_THREADS / 32 && lane < lanes)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int v = 0; v < V; ++v) s_red[(lane * NQ + q) * C + cv * V + v] = acc[q * V + v];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += RT_THREADS) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            float sum = 0.f;
+            for (int l = 0; l < lanes; ++l) sum += s_red[(l * NQ + q) * C + c];
+            partial[(static_cast<long long>(blockIdx.x) * NQ + q) * C + c] = sum;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RT_THREADS)
+bn_stats_tma_kernel(const bf16* __restrict__ x, long long M, int C, long long rpb, int chunk_rows, float* __restrict__ partial) {
+    float kv[8];  // the shift (row 0) of this thread's channel vector
+    ldv(x + (threadIdx.x % (C / 8)) * 8, kv);
+    col_reduce_tma<2, 1>(x, nullptr, M, C, rpb, chunk_rows, partial, [&](const float* xv, const float*, float* acc) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const float d = xv[v] - kv[v];
+            acc[v] += d;
+            acc[8 + v] = fmaf(d, d, acc[8 + v]);
+        }
+    });
+}
+
+__global__ void __launch_bounds__(RT_THREADS)
+bn_bwd_reduce_tma_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const float* __restrict__ stats, int act,
+                         long long M, int C, long long rpb, int chunk_rows, float* __restrict__ partial) {
+    float mean[8], invstd[8], scale[8], shift[8];
+    const int c0 = (threadIdx.x % (C / 8)) * 8;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        mean[v] = stats[c0 + v]; invstd[v] = stats[C + c0 + v]; scale[v] = stats[2 * C + c0 + v]; shift[v] = stats[3 * C + c0 + v];
+    }
+    col_reduce_tma<2, 2>(dy, z, M, C, rpb, chunk_rows, partial, [&](const float* dv, const float* zv, float* acc) {
+        float u[8], ag[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) u[v] = fmaf(zv[v], scale[v], shift[v]);
+        act_grad_vec<8>(u, act, ag);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const float g = dv[v] * ag[v];
+            acc[v] += g;
+            acc[8 + v] = fmaf(g, (zv[v] - mean[v]) * invstd[v], acc[8 + v]);
+        }
+    });
 }
 
 // ---- BN (+activation) backward.  g = dy * act'(u), u = z * scale + shift, xhat = (z - mean) * invstd.
@@ -1768,6 +1897,34 @@ extern "C" long long cabinet_train_scratch_floats(long long M, int C, int nq) {
     return static_cast<long long>(nb) * nq * C;
 }
 
+// bench / debug: bit 6 of cabinet_debug_flags keeps the line-walking weight-gradient kernel (A/B against the row-tap one),
+// bit 7 the register-fed BatchNorm reductions
+static int cabinet_debug_flags_value() {
+    const int f = cabinet_debug_flags(0);
+    cabinet_debug_flags(f);
+    return f;
+}
+
+// Plan of the shared-memory-staged reductions: dense bf16 rows, at least 2 MB, at most three blocks per SM
+struct RtPlan {
+    bool ok;
+    int nb, chunk_rows;
+    long long rpb;
+};
+static RtPlan rt_plan(int dtype, long long M, int C, bool dense, int nsrc, int nb_max) {
+    RtPlan p = {false, 0, 0, 0};
+    if (dtype != CABINET_BF16 || !dense || C % 8 != 0 || C / 8 > RED_THREADS || M * C < (1LL << 20) || (cabinet_debug_flags_value() & 128))
+        return p;
+    const int lanes = RED_THREADS / (C / 8);
+    p.chunk_rows = (RT_STAGE_BYTES / nsrc) / (C * 2) / lanes * lanes;
+    if (p.chunk_rows < lanes) return p;
+    const long long nb = std::min<long long>(nb_max, 148 * (nsrc == 2 ? 2 : 3));  // resident blocks per SM: 91 / 53 registers
+    p.rpb = cab_ceil_div(cab_ceil_div(M, nb), p.chunk_rows) * p.chunk_rows;  // whole chunks per block
+    p.nb = static_cast<int>(cab_ceil_div(M, p.rpb));
+    p.ok = true;
+    return p;
+}
+
 extern "C" int cabinet_bn_train_stats(const void* x, long long ldx, int dtype, long long M, int C, const float* gamma,
                                       const float* beta, float eps, float momentum, float* running_mean,
                                       float* running_var, float* stats, float* scratch, cabinet_stream_t stream) {
@@ -1776,6 +1933,20 @@ extern "C" int cabinet_bn_train_stats(const void* x, long long ldx, int dtype, l
     const int nb = red_blocks(M, &rpb);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int V = dtype == CABINET_F32 ? 4 : 8;
+    const RtPlan tp = rt_plan(dtype, M, C, ldx == C && al16(x), 1, nb);
+    if (tp.ok) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            CAB_CUDA(cudaFuncSetAttribute(bn_stats_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_STAGES * RT_STAGE_BYTES));
+            attr_done = true;
+        }
+        bn_stats_tma_kernel<<<tp.nb, RT_THREADS, RT_STAGES * RT_STAGE_BYTES, s>>>(reinterpret_cast<const bf16*>(x), M, C, tp.rpb, tp.chunk_rows, scratch);
+        CAB_LAUNCH_CHECK();
+        bn_finalize_kernel<bf16><<<static_cast<unsigned>(cab_ceil_div(C, 4)), 128, 0, s>>>(scratch, tp.nb, M, C, reinterpret_cast<const bf16*>(x), gamma, beta, eps,
+                                                                                         momentum, running_mean, running_var, stats);
+        CAB_LAUNCH_CHECK();
+        return CABINET_OK;
+    }
     if (C % V == 0 && ldx % V == 0 && al16(x)) {
         CAB_DT2(dtype,
                 (bn_stats_v_kernel<float><<<nb, RED_THREADS, red_smem_v<float>(2), s>>>(reinterpret_cast<const float*>(x), ldx, M, C, rpb, scratch)),
@@ -1843,7 +2014,18 @@ extern "C" int cabinet_bn_train_backward(const void* dy, long long lddy, const v
     float* coef = scratch + static_cast<long long>(nb) * 2 * C;
     const int V = dtype == CABINET_F32 ? 4 : 8;
     const bool vec = C % V == 0 && C / V <= 256 && lddy % V == 0 && ldz % V == 0 && lddz % V == 0 && al16(dy) && al16(z) && al16(dz);
-    if (vec) {
+    const RtPlan tp = rt_plan(dtype, M, C, vec && lddy == C && ldz == C, 2, nb);
+    int nb_red = nb;
+    if (tp.ok) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            CAB_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_STAGES * RT_STAGE_BYTES));
+            attr_done = true;
+        }
+        bn_bwd_reduce_tma_kernel<<<tp.nb, RT_THREADS, RT_STAGES * RT_STAGE_BYTES, s>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(z), stats, act,
+                                                                                      M, C, tp.rpb, tp.chunk_rows, scratch);
+        nb_red = tp.nb;
+    } else if (vec) {
         CAB_DT2(dtype,
                 (bn_bwd_reduce_v_kernel<float><<<nb, RED_THREADS, red_smem_v<float>(2), s>>>(reinterpret_cast<const float*>(dy), lddy,
                                                                                           reinterpret_cast<const float*>(z), ldz, stats, act, M, C, rpb, scratch)),
@@ -1857,7 +2039,7 @@ extern "C" int cabinet_bn_train_backward(const void* dy, long long lddy, const v
                                                                             reinterpret_cast<const bf16*>(z), ldz, stats, act, M, C, rpb, scratch)));
     }
     CAB_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(C, 4)), 128, 0, s>>>(scratch, nb, M, C, dgamma, dbeta, coef);
+    bn_bwd_finalize_kernel<<<static_cast<unsigned>(cab_ceil_div(C, 4)), 128, 0, s>>>(scratch, nb_red, M, C, dgamma, dbeta, coef);
     CAB_LAUNCH_CHECK();
     if (vec) {
         const unsigned gv = row_grid(M, 256 / (C / V));
@@ -2058,13 +2240,6 @@ extern "C" int cabinet_dwconv_dgrad(const void* dy, long long lddy, int dtype, c
                                                                  C, k, stride, OH, OW, accumulate)));
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
-}
-
-// bench / debug: bit 6 of cabinet_debug_flags keeps the line-walking weight-gradient kernel (A/B against the row-tap one)
-static int cabinet_debug_flags_value() {
-    const int f = cabinet_debug_flags(0);
-    cabinet_debug_flags(f);
-    return f;
 }
 
 extern "C" int cabinet_dwconv_wgrad(const void* dy, long long lddy, const void* x, long long ldx, int dtype, float* dw,

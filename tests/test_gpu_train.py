@@ -62,7 +62,8 @@ def scratch(lib, M, C, nq):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("N,C,H,W,act", [(2, 16, 9, 7, ACT_RELU), (3, 72, 5, 5, ACT_HSWISH), (1, 960, 2, 2, ACT_NONE),
-                                         (2, 300, 17, 13, ACT_RELU)])
+                                         (2, 300, 17, 13, ACT_RELU), (4, 64, 96, 97, ACT_RELU), (2, 120, 80, 73, ACT_HSWISH),
+                                         (1, 960, 41, 40, ACT_NONE), (3, 16, 160, 150, ACT_HSWISH)])
 def test_bn_train_forward_backward(N, C, H, W, act, dtype):
     lib = _lib.load()
     x = q(gen(N, C, H, W, seed=1) * 2 + 5, dtype).requires_grad_(True)   # mean >> std: the shifted sums must not cancel
