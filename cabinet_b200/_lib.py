@@ -86,6 +86,7 @@ SIGNATURES = {
                             _p], _i),
     "cabinet_conv_wgrad_tc_scratch_floats": ([_i, _i, _i, _i, _i, _i, _i, _i, _i], _ll),
     "cabinet_conv_wgrad_tc": ([_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p], _i),
+    "cabinet_conv_wgrad_tc_batched": ([_p, _ll, _p, _ll, _p, _i, _i, _i, _i, _i, _p], _i),
     "cabinet_dwconv_dgrad": ([_p, _ll, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p], _i),
     "cabinet_dwconv_wgrad": ([_p, _ll, _p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p], _i),
     "cabinet_resample_sep": ([_p, _i, _ll, _ll, _ll, _ll, _p, _i, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p,

@@ -240,9 +240,10 @@ extern "C" long long cabinet_conv_wgrad_tc_scratch_floats(int N, int H, int W, i
     return static_cast<long long>(g.splits) * Cout * KH * KW * Cin;
 }
 
-extern "C" int cabinet_conv_wgrad_tc(const void* dy, long long lddy, const void* x, long long ldx, float* dw_oihw, int N,
-                                     int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, float* scratch,
-                                     cabinet_stream_t stream) {
+// per_image: 1x1 only; one pixel split per image and the "partials" ARE the result: out[n][co][ci] (no second level)
+static int wgrad_tc_impl(const void* dy, long long lddy, const void* x, long long ldx, float* dw_oihw, int N, int H, int W,
+                         int Cin, int Cout, int KH, int KW, int stride, int pad, float* scratch, cabinet_stream_t stream,
+                         bool per_image) {
     CAB_REQUIRE(dy && x && dw_oihw && scratch, "conv_wgrad_tc: null pointer");
     CAB_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && KH == KW && pad >= 0 &&
                     ((stride == 1 && 2 * pad == KH - 1) || (stride == 2 && H >= 2 && W >= 2)),
@@ -251,8 +252,14 @@ extern "C" int cabinet_conv_wgrad_tc(const void* dy, long long lddy, const void*
     CAB_REQUIRE(lddy % 8 == 0 && ldx % 8 == 0 && lddy >= Cout && ldx >= Cin && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(x) & 15) == 0,
                 "conv_wgrad_tc: pixel strides must be multiples of 8 and the bases 16-byte aligned");
-    const WgPlan g = wg_plan(N, OH, OW, Cin, Cout, KH, KW, stride);
+    WgPlan g = wg_plan(N, OH, OW, Cin, Cout, KH, KW, stride);
     CAB_REQUIRE(g.n_k_tiles < (1LL << 31) && static_cast<long long>(N) * H * W < (1LL << 31), "conv_wgrad_tc: too many pixels");
+    if (per_image) {
+        CAB_REQUIRE(g.flat && (static_cast<long long>(H) * W) % KT == 0 && N <= 65535,
+                    "conv_wgrad_tc_batched: 1x1, H * W a multiple of 64, at most 65535 images");
+        g.tiles_per_split = H * W / KT;
+        g.splits = N;
+    }
     WgParams p;
     p.Cin = Cin; p.Cout = Cout; p.taps = KH * KW; p.KW = KW; p.pad = pad; p.stride = stride;
     p.TW = g.TW; p.TH = g.TH; p.tiles_w = g.tiles_w; p.tiles_h = g.tiles_h; p.n_k_tiles = static_cast<int>(g.n_k_tiles);
@@ -306,7 +313,9 @@ extern "C" int cabinet_conv_wgrad_tc(const void* dy, long long lddy, const void*
     conv_wgrad_tc_kernel<<<grid, WG_THREADS, smem, s>>>(tmDY, tmX[0], tmX[1], tmX[2], tmX[3], p);
     CAB_LAUNCH_CHECK();
     const long long total = static_cast<long long>(Cout) * Cin * p.taps;
-    if (g.splits >= 2 * FZ)
+    if (per_image) return CABINET_OK;
+    // many splits of a small matrix: 8 warps per 32 outputs; otherwise one thread per output has parallelism enough
+    if (g.splits >= 8 * FZ || (g.splits >= 2 * FZ && total <= 65536))
         wgrad_tc_finalize_par_kernel<<<static_cast<unsigned>(cab_ceil_div(total, 32)), 32 * FZ, 0, s>>>(scratch, g.splits, Cout, Cin,
                                                                                                        p.taps, dw_oihw);
     else
@@ -314,4 +323,16 @@ extern "C" int cabinet_conv_wgrad_tc(const void* dy, long long lddy, const void*
                                                                                                 dw_oihw);
     CAB_LAUNCH_CHECK();
     return CABINET_OK;
+}
+
+extern "C" int cabinet_conv_wgrad_tc(const void* dy, long long lddy, const void* x, long long ldx, float* dw_oihw, int N,
+                                     int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, float* scratch,
+                                     cabinet_stream_t stream) {
+    return wgrad_tc_impl(dy, lddy, x, ldx, dw_oihw, N, H, W, Cin, Cout, KH, KW, stride, pad, scratch, stream, false);
+}
+
+extern "C" int cabinet_conv_wgrad_tc_batched(const void* a, long long lda, const void* x, long long ldx, float* out, int N,
+                                             int H, int W, int Cin, int Cout, cabinet_stream_t stream) {
+    CAB_REQUIRE(out != nullptr, "conv_wgrad_tc_batched: null pointer");
+    return wgrad_tc_impl(a, lda, x, ldx, out, N, H, W, Cin, Cout, 1, 1, 1, 0, out, stream, true);
 }

@@ -606,7 +606,7 @@ class TrainEngine:
         """The same attention with all six GEMMs on the tensor cores (bf16 operands, fp32 accumulation): a dense [L][d] map
         of an image IS a cabinet_conv_tc weight matrix (rows = tokens, k = channels), so S = Q K^T and dP = dO V^T are 1x1
         convolutions with per-image weights K / V, P V and dQ = dS K the same with K^T / V^T ([d][L], one small transpose
-        each), and dV = P^T dO, dK = dS^T Q reduce over the token ("pixel") index: the weight-gradient GEMM, per image."""
+        each), and dV = P^T dO, dK = dS^T Q reduce over the token ("pixel") index: the weight-gradient GEMM, batched per image."""
         N, L, d, H, W = q.N, q.H * q.W, q.C, q.H, q.W
         dev, bf = self.dev, torch.bfloat16
         s = torch.empty((N, L, L), dtype=torch.float32, device=dev)
@@ -634,22 +634,17 @@ class TrainEngine:
             ds16 = torch.empty((N, L, L), dtype=bf, device=dev)
             kt = torch.empty((N, d, L), dtype=bf, device=dev)
             dq = self.new(N, H, W, d)
-            dkv = torch.zeros((2, N, L, d), dtype=torch.float32, device=dev)  # dK, dV: the weight-gradient GEMM adds
-            n_scr = int(self.lib.cabinet_conv_wgrad_tc_scratch_floats(1, H, W, d, L, 1, 1, 1, 0))
-            scr = torch.empty(max(n_scr, 1), dtype=torch.float32, device=dev)
+            dkv = torch.empty((2, N, L, d), dtype=torch.float32, device=dev)
 
-            def wgrad(a_ptr, x_ptr, ldx, out):  # out[j][c] += sum_i a[i][j] x[i][c], one image
-                self._call("cabinet_conv_wgrad_tc", a_ptr, L, x_ptr, ldx, out.data_ptr(), 1, H, W, d, L, 1, 1, 1, 0,
-                           scr.data_ptr())
+            def wgrad(a, x_map, out):  # out[n][j][c] = sum_i a[n][i][j] x[n][i][c]
+                self._call("cabinet_conv_wgrad_tc_batched", a.data_ptr(), L, x_map.ptr, x_map.ld, out.data_ptr(), N, H, W, d, L)
 
-            for b in range(N):  # dV[j][c] = sum_i P[i][j] dO[i][c]
-                wgrad(p16[b].data_ptr(), do.ptr + b * L * do.ld * 2, do.ld, dkv[1, b])
+            wgrad(p16, do, dkv[1])                                                # dV[j][c] = sum_i P[i][j] dO[i][c]
             gemm(do.ptr, do.ld, d, v.ptr, L, zL, dp.data_ptr(), F32, L)           # dP[i][j] = sum_c dO[i][c] V[j][c]
             self._call("cabinet_attn_softmax_backward", p.data_ptr(), dp.data_ptr(), ds16.data_ptr(), N * L, L, alpha)
             self._call("cabinet_transpose_tokens", k.ptr, k.ld, kt.data_ptr(), N, L, d)
             gemm(ds16.data_ptr(), L, L, kt.data_ptr(), d, zd, dq.ptr, dq.dt, dq.ld)  # dQ[i][c] = sum_j dS[i][j] K[j][c]
-            for b in range(N):  # dK[j][c] = sum_i dS[i][j] Q[i][c]
-                wgrad(ds16[b].data_ptr(), q.ptr + b * L * q.ld * 2, q.ld, dkv[0, b])
+            wgrad(ds16, q, dkv[0])                                                # dK[j][c] = sum_i dS[i][j] Q[i][c]
             dk, dv = self.new(N, H, W, d), self.new(N, H, W, d)
             for src, dst in ((dkv[0], dk), (dkv[1], dv)):  # fp32 -> the activation dtype
                 self._call("cabinet_affine_act", src.data_ptr(), d, F32, None, None, None, 0.0, None, 0, dst.ptr, dst.ld,

@@ -466,6 +466,13 @@ int cabinet_conv_wgrad(const void* dy, long long lddy, int dtype, const void* x,
 long long cabinet_conv_wgrad_tc_scratch_floats(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
 int cabinet_conv_wgrad_tc(const void* dy, long long lddy, const void* x, long long ldx, float* dw_oihw, int N, int H, int W,
                           int Cin, int Cout, int KH, int KW, int stride, int pad, float* scratch, cabinet_stream_t stream);
+
+/* Batched form for per-image products (training-mode attention: dV = P^T dO, dK = dS^T Q, src/models/cab.py:149-153):
+ * out[n][co][ci] = sum over the H * W pixels of image n of a[n][pix][co] * x[n][pix][ci]   (fp32, overwritten; one launch,
+ * no second-level sum).  H * W must be a multiple of 64. */
+int cabinet_conv_wgrad_tc_batched(const void* a, long long lda, const void* x, long long ldx, float* out, int N, int H, int W,
+                                  int Cin, int Cout, cabinet_stream_t stream);
+
 /* Depthwise convolution gradients; w_packed [k*k][C] fp32; dw ([C][1][k][k] fp32) +=; scratch: (N*OH*OW, C, k*k). */
 int cabinet_dwconv_dgrad(const void* dy, long long lddy, int dtype, const float* w_packed, void* dx, long long lddx, int N,
                          int H, int W, int C, int k, int stride, int OH, int OW, int accumulate, cabinet_stream_t stream);

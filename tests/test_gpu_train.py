@@ -571,3 +571,16 @@ def test_transpose_tokens_and_attn_softmax():
     check(lib.cabinet_attn_softmax_backward(p.data_ptr(), dp.data_ptr(), ds.data_ptr(), rows, cols, 0.37, stream()), "attn_sm_bwd")
     ref_ds = p * (dp - (dp * p).sum(-1, keepdim=True)) * 0.37
     assert rel_l2(ds.float(), ref_ds) < 4e-3
+
+
+def test_conv_wgrad_tc_batched_per_image_products():
+    lib = _lib.load()
+    N, H, W, cin, cout = 3, 8, 16, 128, 200
+    a = gen(N, H * W, cout, seed=7).cuda().to(torch.bfloat16)
+    x = gen(N, H * W, cin, seed=8).cuda().to(torch.bfloat16)
+    out = torch.full((N, cout, cin), 7.0, device="cuda")
+    check(lib.cabinet_conv_wgrad_tc_batched(a.data_ptr(), cout, x.data_ptr(), cin, out.data_ptr(), N, H, W, cin, cout, stream()),
+          "wgrad_batched")
+    ref = torch.einsum("npo,npi->noi", a.float(), x.float())
+    assert rel_l2(out, ref) < 1e-5
+    assert lib.cabinet_conv_wgrad_tc_batched(a.data_ptr(), cout, x.data_ptr(), cin, out.data_ptr(), N, 3, 5, cin, cout, stream()) != 0
