@@ -149,6 +149,7 @@ class TrainEngine:
         self._zero_cache: Dict[int, torch.Tensor] = {}
         self.use_graph = True               # replay the step as two CUDA graphs once its geometry has been seen
         self.graph_after = 2                # eager steps per geometry before the capture (lazy tables, attributes)
+        self.max_graphs = 2                 # captured geometries kept (each pins a step's activations)
         self._gsteps: Dict[tuple, "_GraphedStep"] = {}
         self._active: Optional["_GraphedStep"] = None
 
@@ -806,6 +807,9 @@ class TrainEngine:
             st.seen += 1
             if st.seen <= self.graph_after:
                 return self.forward(x, logits_dtype)
+            captured = [k for k, v in self._gsteps.items() if v.fwd is not None]
+            for k in captured[:max(0, len(captured) - self.max_graphs + 1)]:
+                del self._gsteps[k]  # oldest geometries first: each one pins its activations in its own pool
             self._capture(st, x, logits_dtype, addr)
         st.x.copy_(x)
         st.fwd.replay()

@@ -584,3 +584,28 @@ def test_conv_wgrad_tc_batched_per_image_products():
     ref = torch.einsum("npo,npi->noi", a.float(), x.float())
     assert rel_l2(out, ref) < 1e-5
     assert lib.cabinet_conv_wgrad_tc_batched(a.data_ptr(), cout, x.data_ptr(), cin, out.data_ptr(), N, 3, 5, cin, cout, stream()) != 0
+
+
+def test_train_graphs_are_evicted_per_geometry():
+    """At most ``max_graphs`` input geometries stay captured (each pins a step's activations); an evicted one is
+    captured again when it comes back, with the same results as the eager schedule."""
+    C = 4
+    m = build_model(C, "small").cuda().train()
+    m.train_precision = "bf16"
+    ref = build_model(C, "small").cuda().train()
+    ref.train_precision = "bf16"
+    ref.train_engine().use_graph = False
+    eng = m.train_engine()
+    for H, W in ((64, 64), (64, 96), (96, 64), (64, 64)):
+        x = make_input(1, H, W, seed=H + W).cuda()
+        for _ in range(eng.graph_after + 2):
+            for net in (m, ref):
+                net.zero_grad(set_to_none=True)
+                o, a = net(x)
+                (o.float().square().mean() + a.float().mean()).backward()
+        assert len([st for st in eng._gsteps.values() if st.fwd is not None]) <= eng.max_graphs
+        assert any(st.fwd is not None and k[0] == (1, 3, H, W) for k, st in eng._gsteps.items())
+        g0, g1 = m.conv_out.conv_out.weight.grad, ref.conv_out.conv_out.weight.grad
+        assert torch.equal(g0, g1)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, ref.state_dict()[k]), k
