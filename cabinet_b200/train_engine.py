@@ -810,7 +810,16 @@ class TrainEngine:
             captured = [k for k, v in self._gsteps.items() if v.fwd is not None]
             for k in captured[:max(0, len(captured) - self.max_graphs + 1)]:
                 del self._gsteps[k]  # oldest geometries first: each one pins its activations in its own pool
-            self._capture(st, x, logits_dtype, addr)
+            try:
+                self._capture(st, x, logits_dtype, addr)
+            except Exception as e:  # e.g. out of memory for the pool: stay on the eager schedule, loudly
+                import warnings
+
+                warnings.warn(f"cabinet_b200: CUDA-graph capture of the training step failed ({e!r}); continuing eagerly")
+                self.use_graph = False
+                self._gsteps.clear()
+                torch.cuda.synchronize(self.dev)
+                return self.forward(x, logits_dtype)
         st.x.copy_(x)
         st.fwd.replay()
         self.launches, self.phase = st.n_fwd, "fwd"
