@@ -709,10 +709,16 @@ def run_train(args):
     ms = max_over_ranks(e0.elapsed_time(e1))
     value = world * B * K / (ms * 1e-3)
     # end to end: host batch in, loss out, every step
+    from cabinet_b200.prefetch import DevicePrefetcher
+
+    feed = DevicePrefetcher([(x_host, lb_host)] * K, dev)  # copies of batch i + 1 run under step i
+    for i, (xd, ld) in enumerate(feed):  # untimed: the side stream's allocator pool
+        step(xd, ld)
+        if i == 1:
+            break
     barrier()
     e0.record()
-    for _ in range(K):
-        xd, ld = x_host.to(dev, non_blocking=True), lb_host.to(dev, non_blocking=True)
+    for xd, ld in feed:
         lv = float(step(xd, ld).item())
     e1.record()
     barrier()
@@ -782,13 +788,13 @@ def run_train(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.train_precision == "bf16" else "f32", "data": "synthetic",
         "config": dict(workload_config(args), outputs="loss + gradients of 398 parameter tensors",
-                       launch="eager kernel launches through the C-ABI (train engine)",
+                       launch="two CUDA graphs (forward, backward) of C-ABI kernel launches, replayed per step after 2 eager steps",
                        cache="activations of a step far exceed the 126 MB L2",
                        loss="2 x OhemCELoss(thresh 0.7, n_min = pixels / 16)", grad_elements=n_grad,
                        grad_sync=f"{len(gb.buckets)} flat fp32 buckets, one async NCCL all-reduce each"),
         "e2e": {"value": world * B * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / K,
                 "h2d_bytes_per_step": x_host.numel() * 4 + lb_host.numel() * 8, "d2h_bytes_per_step": 4,
-                "api": "model.train()(x) -> OhemCELoss x 2 -> loss.backward() -> GradBuckets.all_reduce()", "loss": lv},
+                "api": "DevicePrefetcher(pinned host batches) -> model.train()(x) -> OhemCELoss x 2 -> loss.backward() -> GradBuckets.all_reduce()", "loss": lv},
         "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "kernels": table[:14],
         "traced_ms_per_step": sum(t for _, _, t in rows), "gpu_eager_baseline": eager}))
 

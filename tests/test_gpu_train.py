@@ -609,3 +609,17 @@ def test_train_graphs_are_evicted_per_geometry():
         assert torch.equal(g0, g1)
     for k, v in m.state_dict().items():
         assert torch.equal(v, ref.state_dict()[k]), k
+
+
+def test_device_prefetcher_on_the_gpu():
+    from cabinet_b200.prefetch import DevicePrefetcher
+
+    host = [(torch.randn(4, 3, 64, 64).pin_memory(), torch.randint(0, 5, (4, 64, 64)).pin_memory()) for _ in range(5)]
+    seen = []
+    for x, lb in DevicePrefetcher(host, "cuda"):
+        assert x.is_cuda and lb.is_cuda
+        seen.append((x.clone(), lb.clone()))
+        torch.randn(1 << 20, device="cuda").sum().item()   # work (and a host sync) between the batches
+    assert len(seen) == 5
+    for (x, lb), (hx, hl) in zip(seen, host):
+        assert torch.equal(x.cpu(), hx) and torch.equal(lb.cpu(), hl)
