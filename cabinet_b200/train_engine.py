@@ -21,6 +21,7 @@ shape or engine switch re-captures; tracing (``start_trace``) and steps inside s
 
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Dict, List, Optional, Tuple
 
@@ -146,6 +147,9 @@ class TrainEngine:
         self.stem_gemm = True               # both stems as 1x1 GEMMs on one bf16 im2col of the input
         self.dgrad_s2_tc = True             # stride-2 data gradients as four parity-class conv_tc calls
         self.attn_tc = True                 # attention GEMMs (forward and backward) on the tensor cores
+        self.wgrad_overlap = True           # weight gradients on a second stream (a parallel branch of the backward graph)
+        self._side: Optional[torch.cuda.Stream] = None
+        self._side_used = False
         self._zero_cache: Dict[int, torch.Tensor] = {}
         self.use_graph = True               # replay the step as two CUDA graphs once its geometry has been seen
         self.graph_after = 2                # eager steps per geometry before the capture (lazy tables, attributes)
@@ -192,15 +196,35 @@ class TrainEngine:
         """fp32 gradient accumulator of a parameter (zeroed on first use in a backward)."""
         g = self.pgrads.get(id(p))
         if g is None:
-            if self._pflat is None:  # one buffer, one fill kernel per backward instead of one per parameter
-                off = 0
-                for q in self.model.parameters():
-                    self._pslots[id(q)] = (off, q.numel())
-                    off += -(-q.numel() // 64) * 64  # 256-byte aligned slots
-                self._pflat = torch.zeros(max(off, 1), dtype=torch.float32, device=self.dev)
+            self._ensure_pflat()
             off, n = self._pslots[id(p)]
             g = self.pgrads[id(p)] = self._pflat[off:off + n].view(p.shape)
         return g
+
+    @contextlib.contextmanager
+    def _wgrad_stream(self):
+        """Weight gradients feed nothing but the parameter gradients, so they leave the dy -> dx chain: the block runs on
+        a side stream that waits for everything queued so far (dy is complete) and is joined at the end of ``backward``.
+        Inside a captured backward the fork / join become parallel branches of the graph: the small layers' weight
+        gradients (16-30 us kernels on a fraction of the SMs) run under the data-gradient chain.  Tensors allocated inside
+        the block belong to the side stream's pool; dy / x / the flat parameter-gradient buffer live until the join."""
+        if not self.wgrad_overlap or self.trace is not None:
+            yield
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.dev)
+        self._side.wait_stream(torch.cuda.current_stream(self.dev))
+        self._side_used = True
+        with torch.cuda.stream(self._side):
+            yield
+
+    def _ensure_pflat(self):
+        if self._pflat is None:  # one buffer, one fill kernel per backward instead of one per parameter
+            off = 0
+            for q in self.model.parameters():
+                self._pslots[id(q)] = (off, q.numel())
+                off += -(-q.numel() // 64) * 64  # 256-byte aligned slots
+            self._pflat = torch.zeros(max(off, 1), dtype=torch.float32, device=self.dev)
 
     @staticmethod
     def _dt(t: torch.Tensor) -> int:
@@ -259,21 +283,22 @@ class TrainEngine:
             dy = g.get(out)
             if dy is None:
                 return
-            if b is not None:
-                sc = self.scratch(N * OH * OW, cout, 1)
-                self._call("cabinet_col_sum", dy.ptr, dy.ld, dy.dt, N * OH * OW, cout, self.pgrad(b).data_ptr(), 1,
-                           sc.data_ptr())
-            if (self.use_tc and self.wgrad_tc and nchw is None and kh == kw and self._tc_ok(x) and self._tc_ok(dy)
-                    and ((stride == 1 and 2 * pad == kh - 1) or (stride == 2 and H >= 2 and W >= 2))):
-                n = int(self.lib.cabinet_conv_wgrad_tc_scratch_floats(N, H, W, cin, cout, kh, kw, stride, pad))
-                sc = torch.empty(n, dtype=torch.float32, device=self.dev)
-                self._call("cabinet_conv_wgrad_tc", dy.ptr, dy.ld, x.ptr, x.ld, self.pgrad(w).data_ptr(), N, H, W, cin, cout,
-                           kh, kw, stride, pad, sc.data_ptr())
-            else:
-                n = int(self.lib.cabinet_conv_wgrad_scratch_floats(N, OH, OW, cin, cout, kh, kw))
-                sc = torch.empty(n, dtype=torch.float32, device=self.dev)
-                self._call("cabinet_conv_wgrad", dy.ptr, dy.ld, dy.dt, xptr, xdt, *strides, self.pgrad(w).data_ptr(), N, H,
-                           W, cin, cout, kh, kw, stride, pad, OH, OW, sc.data_ptr())
+            with self._wgrad_stream():
+                if b is not None:
+                    sc = self.scratch(N * OH * OW, cout, 1)
+                    self._call("cabinet_col_sum", dy.ptr, dy.ld, dy.dt, N * OH * OW, cout, self.pgrad(b).data_ptr(), 1,
+                               sc.data_ptr())
+                if (self.use_tc and self.wgrad_tc and nchw is None and kh == kw and self._tc_ok(x) and self._tc_ok(dy)
+                        and ((stride == 1 and 2 * pad == kh - 1) or (stride == 2 and H >= 2 and W >= 2))):
+                    n = int(self.lib.cabinet_conv_wgrad_tc_scratch_floats(N, H, W, cin, cout, kh, kw, stride, pad))
+                    sc = torch.empty(n, dtype=torch.float32, device=self.dev)
+                    self._call("cabinet_conv_wgrad_tc", dy.ptr, dy.ld, x.ptr, x.ld, self.pgrad(w).data_ptr(), N, H, W, cin,
+                               cout, kh, kw, stride, pad, sc.data_ptr())
+                else:
+                    n = int(self.lib.cabinet_conv_wgrad_scratch_floats(N, OH, OW, cin, cout, kh, kw))
+                    sc = torch.empty(n, dtype=torch.float32, device=self.dev)
+                    self._call("cabinet_conv_wgrad", dy.ptr, dy.ld, dy.dt, xptr, xdt, *strides, self.pgrad(w).data_ptr(), N,
+                               H, W, cin, cout, kh, kw, stride, pad, OH, OW, sc.data_ptr())
             if nchw is not None or not need_dx:
                 return
             if dy.dt != x.dt:  # fp32 class-logit gradients into a bf16 activation gradient (pixel stride padded to 8)
@@ -364,13 +389,14 @@ class TrainEngine:
             dy = g.get(out)
             if dy is None:
                 return
-            dwbig = torch.zeros((cout, LD), dtype=torch.float32, device=self.dev)
-            self.launches += 1
-            n = int(self.lib.cabinet_conv_wgrad_tc_scratch_floats(N, OH, OW, LD, cout, 1, 1, 1, 0))
-            sc = torch.empty(n, dtype=torch.float32, device=self.dev)
-            self._call("cabinet_conv_wgrad_tc", dy.ptr, dy.ld, xcol.ptr, xcol.ld, dwbig.data_ptr(), N, OH, OW, LD, cout, 1, 1, 1,
-                       0, sc.data_ptr())
-            self._call("cabinet_embed_filter", self.pgrad(w).data_ptr(), cout, 3, k, self.STEM_K, dwbig.data_ptr(), LD, 1)
+            with self._wgrad_stream():
+                dwbig = torch.zeros((cout, LD), dtype=torch.float32, device=self.dev)
+                self.launches += 1
+                n = int(self.lib.cabinet_conv_wgrad_tc_scratch_floats(N, OH, OW, LD, cout, 1, 1, 1, 0))
+                sc = torch.empty(n, dtype=torch.float32, device=self.dev)
+                self._call("cabinet_conv_wgrad_tc", dy.ptr, dy.ld, xcol.ptr, xcol.ld, dwbig.data_ptr(), N, OH, OW, LD, cout, 1, 1,
+                           1, 0, sc.data_ptr())
+                self._call("cabinet_embed_filter", self.pgrad(w).data_ptr(), cout, 3, k, self.STEM_K, dwbig.data_ptr(), LD, 1)
 
         self.tape.append(backward)
         return out
@@ -397,9 +423,10 @@ class TrainEngine:
             dy = g.get(out)
             if dy is None:
                 return
-            sc = self.scratch(x.N * OH * OW, C, k * k)
-            self._call("cabinet_dwconv_wgrad", dy.ptr, dy.ld, x.ptr, x.ld, x.dt, self.pgrad(w).data_ptr(), x.N, x.H, x.W, C, k,
-                       stride, OH, OW, sc.data_ptr())
+            with self._wgrad_stream():
+                sc = self.scratch(x.N * OH * OW, C, k * k)
+                self._call("cabinet_dwconv_wgrad", dy.ptr, dy.ld, x.ptr, x.ld, x.dt, self.pgrad(w).data_ptr(), x.N, x.H, x.W, C,
+                           k, stride, OH, OW, sc.data_ptr())
             dx, acc = g.out(x)
             if tma and stride == 1 and self._tc_ok(dy):
                 wf = torch.empty((k * k, C), dtype=torch.float32, device=self.dev)
@@ -775,12 +802,15 @@ class TrainEngine:
     def backward(self, d_final: Optional[torch.Tensor], d_aux: Optional[torch.Tensor]) -> Dict[int, torch.Tensor]:
         """Gradients of the two logit tensors -> {id(parameter): fp32 gradient}."""
         g = _Grads(self)
-        self.pgrads, self.phase, self._pflat = {}, "bwd", None
+        self.pgrads, self.phase, self._pflat, self._side_used = {}, "bwd", None, False
+        self._ensure_pflat()  # zero-filled on THIS stream before any branch adds into it
         for dy, bwd in ((d_final, self._out_bwd[0]), (d_aux, self._out_bwd[1])):
             if dy is not None:
                 bwd(g, dy)
         for fn in reversed(self.tape):
             fn(g)
+        if self._side_used:  # join: the parameter gradients are complete when the caller's stream continues
+            torch.cuda.current_stream(self.dev).wait_stream(self._side)
         self.tape = []
         return self.pgrads
 
@@ -796,7 +826,8 @@ class TrainEngine:
         self._active = None
         if not self.use_graph or self.trace is not None or torch.cuda.is_current_stream_capturing():
             return self.forward(x, logits_dtype)
-        key = (tuple(x.shape), logits_dtype, self.use_tc, self.wgrad_tc, self.stem_gemm, self.dgrad_s2_tc, self.attn_tc)
+        key = (tuple(x.shape), logits_dtype, self.use_tc, self.wgrad_tc, self.stem_gemm, self.dgrad_s2_tc, self.attn_tc,
+               self.wgrad_overlap)
         addr = self._addresses()
         st = self._gsteps.get(key)
         if st is not None and st.fwd is not None and st.addr != addr:
