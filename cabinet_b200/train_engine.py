@@ -148,7 +148,10 @@ class TrainEngine:
         self.dgrad_s2_tc = True             # stride-2 data gradients as four parity-class conv_tc calls
         self.attn_tc = True                 # attention GEMMs (forward and backward) on the tensor cores
         self.wgrad_overlap = True           # weight gradients on a second stream (a parallel branch of the backward graph)
+        self.branch_overlap = True          # spatial-branch backward beside the attention-branch / backbone backward
         self._side: Optional[torch.cuda.Stream] = None
+        self._side2: Optional[torch.cuda.Stream] = None
+        self._branch: Optional[Tuple[int, int, int]] = None
         self._side_used = False
         self._zero_cache: Dict[int, torch.Tensor] = {}
         self.use_graph = True               # replay the step as two CUDA graphs once its geometry has been seen
@@ -732,6 +735,7 @@ class TrainEngine:
 
         # ---- spatial branch (cabinet.py:108-129)
         xcol = self.stem_im2col(x) if (self.use_tc and self.stem_gemm) else None
+        sb_lo = len(self.tape)
         s1 = self.bn(self.conv_stem(xcol, sb.conv1.conv) if xcol is not None else self.conv(None, sb.conv1.conv, nchw=x),
                      sb.conv1.bn, ACT_RELU)
         s2 = self.bn(self.conv(s1, sb.conv2.conv), sb.conv2.bn, ACT_RELU)
@@ -740,6 +744,7 @@ class TrainEngine:
         n_sb = sb.conv_out.conv.out_channels
         cat_ffm = self.new(N, H8, W8, n_sb + ab.convb.out_channels)
         self.bn(self.conv(s3, sb.conv_out.conv), sb.conv_out.bn, ACT_RELU, out=cat_ffm.slice(0, n_sb))
+        sb_hi = len(self.tape)
 
         # ---- backbone (mobilenetv3.py:102-159,202-205)
         f = self.bn(self.conv_stem(xcol, mob.features[0][0]) if xcol is not None
@@ -788,6 +793,9 @@ class TrainEngine:
         aux8 = self.resample(high, "bilinear", H8, W8)                                          # cabinet.py:234-239
 
         # ---- feature fusion + head (cabinet.py:142-153,162-172)
+        # backward: once this convolution's data gradient exists, the spatial branch (tape[sb_lo:sb_hi]: big, bandwidth-
+        # bound kernels) is independent of the attention branch / backbone (many small kernels): a branch of its own
+        self._branch = (sb_lo, sb_hi, len(self.tape))
         ff = self.bn(self.conv(cat_ffm, ffm.convblk.conv), ffm.convblk.bn, ACT_RELU)
         ffo = self.gate(ff, ffm.conv1.weight, None, ffm.conv2.weight, None, ACT_SIGMOID, ACT_NONE, 1.0)
         hc = self.bn(self.conv(ffo, head.conv.conv), head.conv.bn, ACT_RELU)
@@ -807,10 +815,23 @@ class TrainEngine:
         for dy, bwd in ((d_final, self._out_bwd[0]), (d_aux, self._out_bwd[1])):
             if dy is not None:
                 bwd(g, dy)
-        for fn in reversed(self.tape):
-            fn(g)
+        lo, hi, ready = self._branch if (self.branch_overlap and self.trace is None and self._branch) else (0, 0, -1)
+        main = torch.cuda.current_stream(self.dev)
+        for i in range(len(self.tape) - 1, -1, -1):
+            if lo <= i < hi:
+                continue  # ran on the branch stream
+            self.tape[i](g)
+            if i == ready:
+                if self._side2 is None:
+                    self._side2 = torch.cuda.Stream(self.dev)
+                self._side2.wait_stream(main)
+                with torch.cuda.stream(self._side2):
+                    for j in range(hi - 1, lo - 1, -1):
+                        self.tape[j](g)
+        if hi > lo:
+            main.wait_stream(self._side2)
         if self._side_used:  # join: the parameter gradients are complete when the caller's stream continues
-            torch.cuda.current_stream(self.dev).wait_stream(self._side)
+            main.wait_stream(self._side)
         self.tape = []
         return self.pgrads
 
@@ -827,7 +848,7 @@ class TrainEngine:
         if not self.use_graph or self.trace is not None or torch.cuda.is_current_stream_capturing():
             return self.forward(x, logits_dtype)
         key = (tuple(x.shape), logits_dtype, self.use_tc, self.wgrad_tc, self.stem_gemm, self.dgrad_s2_tc, self.attn_tc,
-               self.wgrad_overlap)
+               self.wgrad_overlap, self.branch_overlap)
         addr = self._addresses()
         st = self._gsteps.get(key)
         if st is not None and st.fwd is not None and st.addr != addr:
@@ -864,7 +885,7 @@ class TrainEngine:
         if d_final is None or d_aux is None:
             # an unused output: the eager backward over the captured forward's tape (its saved activations are the static
             # buffers the replay just filled) leaves the parameters only that output reaches without a gradient
-            self.tape, self._out_bwd = list(st.tape), st.out_bwd
+            self.tape, self._out_bwd, self._branch = list(st.tape), st.out_bwd, st.branch
             return self.backward(d_final, d_aux)
         st.d_final.copy_(d_final)
         st.d_aux.copy_(d_aux)
@@ -881,7 +902,7 @@ class TrainEngine:
         with torch.cuda.graph(fwd, pool=pool, capture_error_mode="thread_local"):
             st.final, st.aux = self.forward(st.x, logits_dtype)
         st.n_fwd = self.launches
-        st.tape, st.out_bwd = self.tape, self._out_bwd  # keeps every saved activation of the pool alive
+        st.tape, st.out_bwd, st.branch = self.tape, self._out_bwd, self._branch  # keeps every saved activation alive
         st.d_final, st.d_aux = torch.empty_like(st.final), torch.empty_like(st.aux)
         with torch.cuda.graph(bwd, pool=pool, capture_error_mode="thread_local"):
             st.grads = dict(self.backward(st.d_final, st.d_aux))
@@ -896,7 +917,7 @@ class _GraphedStep:
         self.seen = 0
         self.fwd = self.bwd = None
         self.x = self.final = self.aux = self.d_final = self.d_aux = None
-        self.tape = self.out_bwd = self.grads = self.addr = None
+        self.tape = self.out_bwd = self.grads = self.addr = self.branch = None
         self.n_fwd = self.n_bwd = 0
 
 
