@@ -211,7 +211,7 @@ class TrainEngine:
         Inside a captured backward the fork / join become parallel branches of the graph: the small layers' weight
         gradients (16-30 us kernels on a fraction of the SMs) run under the data-gradient chain.  Tensors allocated inside
         the block belong to the side stream's pool; dy / x / the flat parameter-gradient buffer live until the join."""
-        if not self.wgrad_overlap or self.trace is not None:
+        if not self.wgrad_overlap or self.trace is not None or torch.device(self.dev).type != "cuda":
             yield
             return
         if self._side is None:
@@ -815,8 +815,9 @@ class TrainEngine:
         for dy, bwd in ((d_final, self._out_bwd[0]), (d_aux, self._out_bwd[1])):
             if dy is not None:
                 bwd(g, dy)
-        lo, hi, ready = self._branch if (self.branch_overlap and self.trace is None and self._branch) else (0, 0, -1)
-        main = torch.cuda.current_stream(self.dev)
+        on_gpu = torch.device(self.dev).type == "cuda"  # (the host-only dry run of the schedule has no streams)
+        lo, hi, ready = self._branch if (self.branch_overlap and self.trace is None and self._branch and on_gpu) else (0, 0, -1)
+        main = torch.cuda.current_stream(self.dev) if on_gpu else None
         for i in range(len(self.tape) - 1, -1, -1):
             if lo <= i < hi:
                 continue  # ran on the branch stream
