@@ -1531,15 +1531,47 @@ __global__ void __launch_bounds__(256)
 resample_band_kernel(const TI* __restrict__ in, long long isn, long long isy, long long isc, int W_in, TO* __restrict__ out,
                      long long osn, long long osy, long long osx, long long osc, int C, int OW, const int* __restrict__ ys,
                      const int* __restrict__ yi, const float* __restrict__ yw, const int* __restrict__ xs,
-                     const int* __restrict__ xi, const float* __restrict__ xw, int accumulate) {
+                     const int* __restrict__ xi, const float* __restrict__ xw, int accumulate, int vec) {
     extern __shared__ float s_line[];  // [W_in]
     const int oy = blockIdx.x, n = blockIdx.y / C, c = blockIdx.y - n * C;
     const TI* plane = in + n * isn + c * isc;
     const int a0 = ys[oy], a1 = ys[oy + 1];
-    for (int x = threadIdx.x; x < W_in; x += 256) {
-        float acc = 0.f;
-        for (int a = a0; a < a1; ++a) acc = fmaf(yw[a], ldf(plane + yi[a] * isy + x), acc);
-        s_line[x] = acc;
+    if (vec) {
+        // 16-byte loads (8 bf16 / 4 fp32 columns per thread), the band's rows unrolled four at a time: up to 64 bytes in
+        // flight per thread instead of one 2-byte load per tap
+        constexpr int V = vec_n<TI>();
+        for (int x = threadIdx.x * V; x < W_in; x += 256 * V) {
+            float acc[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = 0.f;
+            int a = a0;
+            for (; a + 4 <= a1; a += 4) {
+                float r[4][V];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ldv(plane + yi[a + u] * isy + x, r[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float w = yw[a + u];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) acc[v] = fmaf(w, r[u][v], acc[v]);
+                }
+            }
+            for (; a < a1; ++a) {
+                float r[V];
+                ldv(plane + yi[a] * isy + x, r);
+                const float w = yw[a];
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] = fmaf(w, r[v], acc[v]);
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) s_line[x + v] = acc[v];
+        }
+    } else {
+        for (int x = threadIdx.x; x < W_in; x += 256) {
+            float acc = 0.f;
+            for (int a = a0; a < a1; ++a) acc = fmaf(yw[a], ldf(plane + yi[a] * isy + x), acc);
+            s_line[x] = acc;
+        }
     }
     __syncthreads();
     for (int ox = threadIdx.x; ox < OW; ox += 256) {
@@ -2379,7 +2411,9 @@ extern "C" int cabinet_resample_sep(const void* in, int in_dtype, long long isn,
 #define CAB_RB(TI, TO)                                                                                                       \
     resample_band_kernel<TI, TO><<<grid, 256, smem, s>>>(reinterpret_cast<const TI*>(in), isn, isy, isc, W_in,               \
                                                          reinterpret_cast<TO*>(out), osn, osy, osx, osc, C, OW, y_start, y_index, \
-                                                         y_weight, x_start, x_index, x_weight, accumulate & 1)
+                                                         y_weight, x_start, x_index, x_weight, accumulate & 1, vec)
+        const int vw = in_dtype == CABINET_F32 ? 4 : 8;  // columns per 16-byte load
+        const int vec = (W_in % vw == 0 && isn % vw == 0 && isc % vw == 0 && al16(in)) ? 1 : 0;
         if (in_dtype == CABINET_F32 && out_dtype == CABINET_F32) CAB_RB(float, float);
         else if (in_dtype == CABINET_F32) CAB_RB(float, bf16);
         else if (out_dtype == CABINET_F32) CAB_RB(bf16, float);

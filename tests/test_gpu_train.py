@@ -623,3 +623,26 @@ def test_device_prefetcher_on_the_gpu():
     assert len(seen) == 5
     for (x, lb), (hx, hl) in zip(seen, host):
         assert torch.equal(x.cpu(), hx) and torch.equal(lb.cpu(), hl)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("h,w", [(5, 5), (4, 11), (3, 21)])
+def test_resample_band_kernel_x8_adjoint(h, w, dtype):
+    """The x8 adjoint of planar (NCHW) logit gradients through the row-band kernel (accumulate bit 1), with line lengths
+    that take the 16-byte path (8 * w a multiple of 8) for both dtypes, against the autograd backward of F.interpolate."""
+    lib = _lib.load()
+    N, C, H, W = 2, 3, 8 * h, 8 * w
+    x = gen(N, C, h, w, seed=1).requires_grad_(True)
+    y = F.interpolate(x, (H, W), mode="bilinear", align_corners=False)
+    dy = q(gen(N, C, H, W, seed=2), dtype)
+    y.backward(dy)
+    up = lambda a: [torch.from_numpy(t).cuda() for t in csr(a)]  # noqa: E731
+    (ys, yi, yw), (xs, xi, xw) = up(bilinear_matrix(h, H).T), up(bilinear_matrix(w, W).T)
+    dyd = dy.cuda().to(dtype).contiguous()
+    for base in (0.0, 1.5):  # overwrite / accumulate
+        dx = torch.full((N, h, w, C), base, device="cuda")
+        check(lib.cabinet_resample_sep(dyd.data_ptr(), DT[dtype], C * H * W, W, 1, H * W, dx.data_ptr(), F32, h * w * C, w * C, C,
+                                       1, N, h, w, C, ys.data_ptr(), yi.data_ptr(), yw.data_ptr(), xs.data_ptr(), xi.data_ptr(),
+                                       xw.data_ptr(), 2 | (1 if base else 0), stream()), "resample_band")
+        torch.cuda.synchronize()
+        assert rel_l2(nchw(dx) - base, x.grad) < 2e-6
