@@ -677,7 +677,8 @@ def run_train(args):
         out, out16 = model(xd)
         loss = crit_p(out, ld) + crit_16(out16, ld)
         loss.backward()
-        gb.all_reduce()
+        if not os.environ.get("CABINET_BENCH_NO_GRAD_SYNC"):  # diagnostic: independent replicas (max over ranks without NCCL)
+            gb.all_reduce()
         return loss
 
     def barrier():
